@@ -1,0 +1,642 @@
+/*
+ * oracle/pg_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C restatement ("port") of the reference's Polya-Gamma sampler layer:
+ *   /root/reference/Code/C/PolyaGamma.cpp      Devroye PG(1,z), sum of PG(1), sum of gammas, moments
+ *   /root/reference/Code/C/PolyaGammaAlt.cpp   alternate sampler, h in [1,4] chunks
+ *   /root/reference/Code/C/PolyaGammaSP.cpp    saddle-point sampler
+ *   /root/reference/Code/C/InvertY.cpp         y -> v inversion
+ *   /root/reference/Code/C/LogitWrapper.cpp    rpg_* batch loops and the hybrid dispatch
+ * Every function cites the reference lines it follows.  Arithmetic is written in
+ * the reference's evaluation order so results agree bit for bit with
+ * oracle/_ref/libpg_ref.so (the reference's own sources compiled in place) --
+ * tests/test_oracle_vs_ref.py checks exactly that on every regime.
+ *
+ * PARITY PIN: the reference ships no golden vectors, so this
+ * port is pinned against outputs of the reference itself run here
+ * (oracle/_ref) and against tests/golden/ vectors generated from oracle/_ref
+ * by tests/golden/make_golden.py.  The L0 layer underneath both (oracle/l0.c)
+ * is "parity unpinned": the reference's RNG library is absent.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "batch.h"
+#include "l0.h"
+#include "pg_tables.h"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* PolyaGamma.h:34-38 */
+static const double PI_ = 3.141592653589793238462643383279502884197;
+static const double T_DEV = 0.64;
+
+/* ------------------------------------------------------------------------- */
+/* Devroye sampler for PG(1,z)                                                */
+/* ------------------------------------------------------------------------- */
+
+/* Jacobi-series coefficient a_n(x), two-piece at t = 0.64.  PolyaGamma.cpp:41-55 */
+static double dev_coef(int n, double x)
+{
+    double K = (n + 0.5) * PI_;
+    if (x > T_DEV) return K * exp(-0.5 * K * K * x);
+    if (x > 0) {
+        double e = -1.5 * (log(0.5 * PI_) + log(x)) + log(K) - 2.0 * (n + 0.5) * (n + 0.5) / x;
+        return exp(e);
+    }
+    return 0.0;
+}
+
+/* Probability of proposing from the exponential (right) piece, computed in log
+ * space.  PolyaGamma.cpp:65-80 */
+static double dev_right_mass(double Z)
+{
+    double t = T_DEV;
+    double fz = 0.125 * PI_ * PI_ + 0.5 * Z * Z;
+    double b = sqrt(1.0 / t) * (t * Z - 1);
+    double a = sqrt(1.0 / t) * (t * Z + 1) * -1.0;
+    double x0 = log(fz) + fz * t;
+    double xb = x0 - Z + pgo_p_norm(b, 1);
+    double xa = x0 + Z + pgo_p_norm(a, 1);
+    double qdivp = 4 / PI_ * (exp(xb) + exp(xa));
+    return 1.0 / (1.0 + qdivp);
+}
+
+/* Inverse-Gaussian(1/Z, 1) truncated to (0, t].  PolyaGamma.cpp:82-115.
+ * Z < 1/t: right-truncated inverse chi^2 by exponential pairs, thinned with
+ * exp(-Z^2 X/2) (note the uniform compared against alpha=0 before the first
+ * proposal, :88-89).  Otherwise Michael-Schucany-Haas draws until X <= t. */
+static double dev_trunc_igauss(pgo_src *s, double Z)
+{
+    double t = T_DEV;
+    double X = t + 1.0;
+    Z = fabs(Z);
+    if (1.0 / T_DEV > Z) {
+        double alpha = 0.0;
+        while (pgo_unif(s) > alpha) {
+            double E1 = pgo_expon(s) / 1.0;
+            double E2 = pgo_expon(s) / 1.0;
+            while (E1 * E1 > 2 * E2 / t) {
+                E1 = pgo_expon(s) / 1.0;
+                E2 = pgo_expon(s) / 1.0;
+            }
+            X = 1 + E1 * t;
+            X = t / (X * X);
+            alpha = exp(-0.5 * Z * Z * X);
+        }
+    } else {
+        double mu = 1.0 / Z;
+        while (X > t) {
+            double Y = 1.0 * pgo_norm(s);
+            Y *= Y;
+            double half_mu = 0.5 * mu;
+            double mu_Y = mu * Y;
+            X = mu + half_mu * mu_Y - half_mu * sqrt(4 * mu_Y + mu_Y * mu_Y);
+            if (pgo_unif(s) > mu / (mu + X)) X = mu * mu / X;
+        }
+    }
+    return X;
+}
+
+/* One PG(1,z) draw = J*(1, |z|/2) / 4.  PolyaGamma.cpp:151-202 */
+static double dev_draw_one(pgo_src *s, double z)
+{
+    double Z = fabs(z) * 0.5;
+    double fz = 0.125 * PI_ * PI_ + 0.5 * Z * Z;
+    for (;;) {
+        double X;
+        if (pgo_unif(s) < dev_right_mass(Z))
+            X = T_DEV + (pgo_expon(s) / 1) / fz;
+        else
+            X = dev_trunc_igauss(s, Z);
+        double S = dev_coef(0, X);
+        double Y = pgo_unif(s) * S;
+        int n = 0;
+        for (;;) {
+            ++n;
+            if (n % 2 == 1) {
+                S = S - dev_coef(n, X);
+                if (Y <= S) return 0.25 * X;
+            } else {
+                S = S + dev_coef(n, X);
+                if (Y > S) break;
+            }
+        }
+    }
+}
+
+/* Sum of n PG(1,z) draws; n < 1 is clamped to 1 (the -DNTHROW behaviour the
+ * package builds with, PolyaGamma.cpp:126-140, src/Makevars:11). */
+static double dev_draw(pgo_src *s, int n, double z)
+{
+    if (n < 1) n = 1;
+    double sum = 0.0;
+    for (int i = 0; i < n; ++i) sum += dev_draw_one(s, z);
+    return sum;
+}
+
+/* Truncated sum of gammas, 2 sum_k G_k / (4 pi^2 (k+1/2)^2 + z^2).
+ * PolyaGamma.cpp:142-149 with the table of :19-39 (trunc < 1 clamped to 1). */
+static double gam_draw(pgo_src *s, double b, double z, int T)
+{
+    if (T < 1) T = 1;
+    double x = 0.0;
+    double kappa = z * z;
+    for (int k = 0; k < T; ++k) {
+        double d = (double)k + 0.5;
+        double bk = (4 * PI_ * PI_) * d * d;
+        x += (1.0 * pgo_gamma(s, b)) / (bk + kappa);
+    }
+    return 2.0 * x;
+}
+
+/* Exact first two moments.  PolyaGamma.cpp:208-239 */
+static double jj_m1(double b, double z)
+{
+    z = fabs(z);
+    if (z > 1e-12) return b * tanh(z) / z;
+    return b * (1 - (1.0 / 3) * pow(z, 2) + (2.0 / 15) * pow(z, 4) - (17.0 / 315) * pow(z, 6));
+}
+
+static double jj_m2(double b, double z)
+{
+    z = fabs(z);
+    if (z > 1e-12)
+        return (b + 1) * b * pow(tanh(z) / z, 2) + b * ((tanh(z) - z) / pow(z, 3));
+    return (b + 1) * b * pow(1 - (1.0 / 3) * pow(z, 2) + (2.0 / 15) * pow(z, 4) - (17.0 / 315) * pow(z, 6), 2)
+         + b * ((-1.0 / 3) + (2.0 / 15) * pow(z, 2) - (17.0 / 315) * pow(z, 4));
+}
+
+double pgb_pg_m1(double b, double z) { return jj_m1(b, 0.5 * z) * 0.25; }
+double pgb_pg_m2(double b, double z) { return jj_m2(b, 0.5 * z) * 0.0625; }
+
+/* ------------------------------------------------------------------------- */
+/* Alternate sampler, h in [1,4]                                              */
+/* ------------------------------------------------------------------------- */
+
+/* Right-truncated inverse chi^2 by exponential pairs (the Alt sampler's own
+ * free function).  PolyaGammaAlt.cpp:6-22 */
+static double alt_rtinvchi2(pgo_src *s, double h, double trunc)
+{
+    double h2 = h * h;
+    double R = trunc / h2;
+    double E1 = pgo_expon(s) / 1.0;
+    double E2 = pgo_expon(s) / 1.0;
+    while ((E1 * E1) > (2 * E2 / R)) {
+        E1 = pgo_expon(s) / 1.0;
+        E2 = pgo_expon(s) / 1.0;
+    }
+    double X = 1 + E1 * R;
+    X = R / (X * X);
+    return h2 * X;
+}
+
+/* Series coefficient with the Gamma ratio carried by recursion; the ratio state
+ * `g` persists across proposals of one draw.  PolyaGammaAlt.cpp:37-49 */
+static double alt_coef(double n, double x, double h, double coef_h, double *g)
+{
+    double d_n = 2.0 * n + h;
+    if (n != 0)
+        *g *= (n + h - 1) / n;
+    else
+        *g = 1.0;
+    double coef = coef_h * *g;
+    double log_kernel = -0.5 * (log(x * x * x) + d_n * d_n / x) + log(d_n);
+    return coef * exp(log_kernel);
+}
+
+/* Inverse-Gaussian CDF in the naive (non-log) form the Alt sampler uses.
+ * PolyaGammaAlt.cpp:51-58 */
+static double alt_pigauss(double x, double z, double lambda)
+{
+    double b = sqrt(lambda / x) * (x * z - 1);
+    double a = sqrt(lambda / x) * (x * z + 1) * -1.0;
+    return pgo_p_norm(b, 0) + exp(2 * lambda * z) * pgo_p_norm(a, 0);
+}
+
+/* Mixture weights.  PolyaGammaAlt.cpp:60-75 */
+static double alt_w_left(double trunc, double h, double z)
+{
+    if (z != 0) return exp(h * (log(2.0) - z)) * alt_pigauss(trunc, z / h, h * h);
+    return exp(h * log(2.0)) * (1.0 - pgo_p_gamma_rate(1 / trunc, 0.5, 0.5 * h * h));
+}
+
+static double alt_w_right(double trunc, double h, double z)
+{
+    double lambda_z = PI_ * PI_ * 0.125 + 0.5 * z * z;
+    return exp(h * log((0.5 * PI_) / lambda_z)) * (1.0 - pgo_p_gamma_rate(trunc, h, lambda_z));
+}
+
+/* Truncated inverse-Gaussian proposal.  PolyaGammaAlt.cpp:77-97 */
+static double alt_trunc_igauss(pgo_src *s, double h, double z, double trunc)
+{
+    z = fabs(z);
+    double mu = h / z;
+    double X = trunc + 1.0;
+    if (mu > trunc) {
+        double alpha = 0.0;
+        while (pgo_unif(s) > alpha) {
+            X = alt_rtinvchi2(s, h, trunc);
+            alpha = exp(-0.5 * z * z * X);
+        }
+    } else {
+        while (X > trunc) X = pgo_igauss(s, mu, h * h);
+    }
+    return X;
+}
+
+/* Envelope.  PolyaGammaAlt.cpp:99-108 */
+static double alt_envelope(double x, double h, double trunc)
+{
+    if (x > trunc)
+        return exp(h * log(0.5 * PI_) + (h - 1) * log(x) - PI_ * PI_ * 0.125 * x - pgo_Gamma(h, 1));
+    return h * exp(h * log(2.0) - 0.5 * log(2.0 * PI_ * x * x * x) - 0.5 * h * h / x);
+}
+
+/* One draw for h in [1,4]; 0 for h outside, -1 after 10000 failed proposals;
+ * inner series capped at 200 terms and required to be decreasing.
+ * PolyaGammaAlt.cpp:114-203 */
+static double alt_draw_chunk(pgo_src *s, double h, double z)
+{
+    const int max_inner = 200;
+    if (h < 1 || h > 4) return 0;
+    z = fabs(z) * 0.5;
+    int idx = (int)floor((h - 1.0) * 100.0);
+    double trunc = PG_TRUNC_SCHEDULE[idx];
+    double rate_z = 0.125 * PI_ * PI_ + 0.5 * z * z;
+    double wl = alt_w_left(trunc, h, z);
+    double wr = alt_w_right(trunc, h, z);
+    double prob_right = wr / (wr + wl);
+    double coef1_h = exp(h * log(2.0) - 0.5 * log(2.0 * PI_));
+    double g = 1.0;
+    for (int trial = 0; trial < 10000; ++trial) {
+        double X;
+        double uu = pgo_unif(s);
+        if (uu < prob_right)
+            X = pgo_ltgamma(s, h, rate_z, trunc);
+        else
+            X = alt_trunc_igauss(s, h, z, trunc);
+        double S = alt_coef(0.0, X, h, coef1_h, &g);
+        double a_n = S;
+        double gt = alt_envelope(X, h, trunc);
+        double Y = pgo_unif(s) * gt;
+        int n = 0, go = 1;
+        while (go && n < max_inner) {
+            ++n;
+            double prev = a_n;
+            a_n = alt_coef((double)n, X, h, coef1_h, &g);
+            int decreasing = a_n <= prev;
+            if (n % 2 == 1) {
+                S = S - a_n;
+                if (Y <= S && decreasing) return 0.25 * X;
+            } else {
+                S = S + a_n;
+                if (Y > S && decreasing) go = 0;
+            }
+        }
+    }
+    return -1.0;
+}
+
+/* h >= 1: floor((h-1)/4) chunks of 4 plus a remainder in [1,5) (split in two
+ * when it exceeds 4).  PolyaGammaAlt.cpp:205-225 */
+static double alt_draw(pgo_src *s, double h, double z)
+{
+    if (h < 1) return 0;
+    double n = floor((h - 1.0) / 4.0);
+    double remain = h - 4.0 * n;
+    double x = 0.0;
+    for (int i = 0; i < (int)n; i++) x += alt_draw_chunk(s, 4.0, z);
+    if (remain > 4.0) {
+        /* the reference writes draw(r/2)+draw(r/2) in one expression; gcc
+         * evaluates the left operand first, as done here */
+        double first = alt_draw_chunk(s, 0.5 * remain, z);
+        double second = alt_draw_chunk(s, 0.5 * remain, z);
+        x += first + second;
+    } else {
+        x += alt_draw_chunk(s, remain, z);
+    }
+    return x;
+}
+
+/* ------------------------------------------------------------------------- */
+/* y(v) inversion                                                             */
+/* ------------------------------------------------------------------------- */
+
+/* y(v) = tan(sqrt v)/sqrt v, tanh(sqrt -v)/sqrt -v; constant 1 inside |v| <= tol
+ * because the series coefficients are integer divisions equal to zero.
+ * InvertY.cpp:10-21 (tol 1e-8), PolyaGammaSP.cpp:78-90 (tol 1e-6). */
+static double y_of_v(double v, double tol)
+{
+    double r = sqrt(fabs(v));
+    if (v > tol) return tan(r) / r;
+    if (v < -1 * tol) return tanh(r) / r;
+    return 1 + 0 * v + 0 * v * v + 0 * v * v * v;
+}
+
+/* v = y^{-1}: closed forms outside [2^-4, 2^4], else Newton from the lower grid
+ * node clamped to the bracketing nodes.  InvertY.cpp:57-99, :23-35.
+ * Deviation on a measure-zero input: y == 16 exactly makes the reference read
+ * vgrid[81] (one past the end); here the upper node is clamped to index 80. */
+double pgb_v_eval(double y)
+{
+    const double tol = 1e-9;
+    const int max_iter = 1000;
+    if (y < PG_YGRID[0]) return -1. / (y * y);
+    if (y > PG_YGRID[PG_YGRID_LEN - 1]) {
+        double v = atan(0.5 * y * PI_);
+        return v * v;
+    }
+    if (y == 1) return 0.0;
+    double id = (log(y) / log(2.0) + 4.0) / 0.1;
+    int idlow = (int)id;
+    int idhigh = idlow + 1;
+    if (idhigh > PG_VGRID_LEN - 1) idhigh = PG_VGRID_LEN - 1;
+    double vl = PG_VGRID[idlow];
+    double vh = PG_VGRID[idhigh];
+    int iter = 0;
+    double diff = tol + 1.0;
+    double vnew = vl, vold = vl;
+    while (diff > tol && iter < max_iter) {
+        iter++;
+        vold = vnew;
+        double yv = y_of_v(vold, 1e-8);
+        double f0 = yv - y;
+        double f1;
+        if (fabs(vold) >= 1e-8)
+            f1 = 0.5 * (yv * yv + (1 - yv) / vold);
+        else
+            f1 = 0.5 * (yv * yv - 0 - 0 * vold);
+        vnew = vold - f0 / f1;
+        vnew = vnew > vh ? vh : vnew;
+        vnew = vnew < vl ? vl : vnew;
+        diff = fabs(vnew - vold);
+    }
+    return vnew;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Saddle-point sampler                                                       */
+/* ------------------------------------------------------------------------- */
+
+/* cos(sqrt v) for v >= 0, cosh(sqrt -v) otherwise.  PolyaGammaSP.cpp:92-101 */
+static double sp_cos_rt(double v)
+{
+    double r = sqrt(fabs(v));
+    return v >= 0 ? cos(r) : cosh(r);
+}
+
+/* Tangent line to eta = phi - delta at x: returns slope and intercept.
+ * PolyaGammaSP.cpp:103-146 */
+static void sp_tangent(double x, double z, double mid, double *slope, double *icept)
+{
+    double v = pgb_v_eval(x);
+    double u = 0.5 * v;
+    double t = u + 0.5 * z * z;
+    double phi_val = log(cosh(fabs(z))) - log(sp_cos_rt(v)) - t * x;
+    double phi_der = -1.0 * t;
+    double delta_val, delta_der;
+    if (x >= mid) {
+        delta_val = log(x) - log(mid);
+        delta_der = 1.0 / x;
+    } else {
+        delta_val = 0.5 * (1 - 1.0 / x) - 0.5 * (1 - 1.0 / mid);
+        delta_der = 0.5 / (x * x);
+    }
+    double eta_val = phi_val - delta_val;
+    double eta_der = phi_der - delta_der;
+    *slope = eta_der;
+    *icept = eta_val - eta_der * x;
+}
+
+/* Saddle-point density approximation.  PolyaGammaSP.cpp:148-167 ((1/3) and
+ * (2/15) are integer divisions = 0 there). */
+static double sp_density(double x, double n, double z)
+{
+    double v = pgb_v_eval(x);
+    double u = 0.5 * v;
+    double z2 = z * z;
+    double t = u + 0.5 * z2;
+    double phi = log(cosh(z)) - log(sp_cos_rt(v)) - t * x;
+    double K2;
+    if (fabs(v) >= 1e-6)
+        K2 = x * x + (1 - x) / v;
+    else
+        K2 = x * x - 0 - 0 * v;
+    double log_spa = 0.5 * log(0.5 * n / PI_) - 0.5 * log(K2) + n * phi;
+    return exp(log_spa);
+}
+
+/* Truncated inverse-Gaussian(mu, lambda) on (0, trunc].  PolyaGammaSP.cpp:57-76 */
+static double sp_trunc_igauss(pgo_src *s, double mu, double lambda, double trunc)
+{
+    double X = trunc + 1.0;
+    if (trunc < mu) {
+        double alpha = 0.0;
+        while (pgo_unif(s) > alpha) {
+            X = pgo_rtinvchi2(s, lambda, trunc);
+            alpha = exp(-0.5 * lambda / (mu * mu) * X);
+        }
+    } else {
+        while (X > trunc) X = pgo_igauss(s, mu, lambda);
+    }
+    return X;
+}
+
+/* One draw of PG(n, z) for large n; returns the proposal count, writes the draw
+ * (the last proposal even when 200 proposals were exhausted).
+ * PolyaGammaSP.cpp:169-264 */
+static int sp_draw(pgo_src *s, double *d, double n, double z)
+{
+    const int maxiter = 200;
+    z = 0.5 * fabs(z);
+    double xl = y_of_v(-1 * z * z, 1e-6);
+    double md = xl * 1.1;
+    double xr = xl * 1.2;
+    double vmd = pgb_v_eval(md);
+    double K2md;
+    if (fabs(vmd) >= 1e-6)
+        K2md = md * md + (1 - md) / vmd;
+    else
+        K2md = md * md - 0 - 0 * vmd;
+    double m2 = md * md;
+    double al = m2 * md / K2md;
+    double ar = m2 / K2md;
+    double sl, il, sr, ir;
+    sp_tangent(xl, z, md, &sl, &il);
+    sp_tangent(xr, z, md, &sr, &ir);
+    double rl = -1. * sl;
+    double rr = -1. * sr;
+    double lcn = 0.5 * log(0.5 * n / PI_);
+    double rt2rl = sqrt(2 * rl);
+    double wl = exp(0.5 * log(al) - n * rt2rl + n * il + 0.5 * n * 1. / md)
+              * pgo_p_igauss(md, 1. / rt2rl, n);
+    double wr = exp(0.5 * log(ar) + lcn - n * log(n * rr) + n * ir - n * log(md))
+              * pgo_Gamma(n, 0) * (1.0 - pgo_p_gamma_rate(md, n, n * rr));
+    double wt = wl + wr;
+    double pl = wl / wt;
+    int go = 1, iter = 0;
+    double X = 2.0, F = 0.0;
+    while (go && iter < maxiter) {
+        iter++;
+        double phi_ev;
+        if (pgo_unif(s) < pl) {
+            X = sp_trunc_igauss(s, 1. / rt2rl, n, md);
+            phi_ev = n * (il - rl * X) + 0.5 * n * ((1. - 1. / X) - (1. - 1. / md));
+            F = exp(0.5 * log(al) + lcn - 1.5 * log(X) + phi_ev);
+        } else {
+            X = pgo_ltgamma(s, n, n * rr, md);
+            phi_ev = n * (ir - rr * X) + n * (log(X) - log(md));
+            F = exp(0.5 * log(ar) + lcn + phi_ev) / X;
+        }
+        double spa = sp_density(X, n, z);
+        if (F * pgo_unif(s) < spa) go = 0;
+    }
+    *d = n * 0.25 * X;
+    return iter;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Batch loops                                                                */
+/* ------------------------------------------------------------------------- */
+
+static void open_stream(pgo_src *s, const pgb_stream *st, int i)
+{
+    if (st->mode == PGO_MODE_TAPE) {
+        pgo_src_tape(s,
+                     st->tu ? st->tu + (size_t)i * st->lu : NULL, st->lu,
+                     st->te ? st->te + (size_t)i * st->le : NULL, st->le,
+                     st->tn ? st->tn + (size_t)i * st->ln : NULL, st->ln,
+                     st->tg ? st->tg + (size_t)i * st->lg : NULL, st->lg);
+    } else {
+        pgo_src_philox(s, st->seed, st->obs0 + (uint64_t)i, st->call_id);
+    }
+}
+
+static void close_stream(const pgo_src *s, int *trace, int i, int aux)
+{
+    if (!trace) return;
+    int *t = trace + (size_t)i * PGB_TRACE_W;
+    t[PGB_TR_U] = s->cu;
+    t[PGB_TR_E] = s->ce;
+    t[PGB_TR_N] = s->cn;
+    t[PGB_TR_G] = s->cg;
+    t[PGB_TR_EXHAUSTED] = s->exhausted;
+    t[PGB_TR_AUX] = aux;
+}
+
+static int pick_threads(int nthreads)
+{
+#ifdef _OPENMP
+    return nthreads > 0 ? nthreads : omp_get_max_threads();
+#else
+    (void)nthreads;
+    return 1;
+#endif
+}
+
+const char *pgb_kind(void) { return "port"; }
+
+/* LogitWrapper.cpp:66-85 */
+void pgb_rpg_devroye(double *x, const int *n, const double *z, int num,
+                     const pgb_stream *st, int *trace, int nthreads)
+{
+    int nt = pick_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nt)
+    for (int i = 0; i < num; ++i) {
+        pgo_src s;
+        open_stream(&s, st, i);
+        x[i] = n[i] != 0 ? dev_draw(&s, n[i], z[i]) : 0.0;
+        if (s.exhausted) x[i] = NAN;
+        close_stream(&s, trace, i, 0);
+    }
+}
+
+/* LogitWrapper.cpp:39-62 */
+void pgb_rpg_gamma(double *x, const double *n, const double *z, int num, int trunc,
+                   const pgb_stream *st, int *trace, int nthreads)
+{
+    int nt = pick_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nt)
+    for (int i = 0; i < num; ++i) {
+        pgo_src s;
+        open_stream(&s, st, i);
+        x[i] = n[i] != 0.0 ? gam_draw(&s, n[i], z[i], trunc) : 0.0;
+        if (s.exhausted) x[i] = NAN;
+        close_stream(&s, trace, i, 0);
+    }
+}
+
+/* LogitWrapper.cpp:87-106 */
+void pgb_rpg_alt(double *x, const double *h, const double *z, int num,
+                 const pgb_stream *st, int *trace, int nthreads)
+{
+    int nt = pick_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nt)
+    for (int i = 0; i < num; ++i) {
+        pgo_src s;
+        open_stream(&s, st, i);
+        x[i] = h[i] != 0 ? alt_draw(&s, h[i], z[i]) : 0.0;
+        if (s.exhausted) x[i] = NAN;
+        close_stream(&s, trace, i, 0);
+    }
+}
+
+/* LogitWrapper.cpp:108-127; iter[i] untouched when h[i] == 0, as there */
+void pgb_rpg_sp(double *x, const double *h, const double *z, int num, int *iter,
+                const pgb_stream *st, int *trace, int nthreads)
+{
+    int nt = pick_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nt)
+    for (int i = 0; i < num; ++i) {
+        pgo_src s;
+        open_stream(&s, st, i);
+        int it = 0;
+        if (h[i] != 0) {
+            it = sp_draw(&s, &x[i], h[i], z[i]);
+            if (iter) iter[i] = it;
+        } else {
+            x[i] = 0.0;
+        }
+        if (s.exhausted) x[i] = NAN;
+        close_stream(&s, trace, i, it);
+    }
+}
+
+/* Regime dispatch.  LogitWrapper.cpp:129-167 (rpg_hybrid uses the default
+ * PolyaGamma constructor, so the sum of gammas truncates at 200 terms). */
+void pgb_rpg_hybrid(double *x, const double *h, const double *z, int num,
+                    const pgb_stream *st, int *trace, int nthreads)
+{
+    int nt = pick_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nt)
+    for (int i = 0; i < num; ++i) {
+        pgo_src s;
+        open_stream(&s, st, i);
+        double b = h[i];
+        int aux = 0;
+        if (b > 170) {
+            double m = pgb_pg_m1(b, z[i]);
+            double v = pgb_pg_m2(b, z[i]) - m * m;
+            x[i] = m + sqrt(v) * pgo_norm(&s);
+        } else if (b > 13) {
+            aux = sp_draw(&s, &x[i], b, z[i]);
+        } else if (b == 1 || b == 2) {
+            x[i] = dev_draw(&s, (int)b, z[i]);
+        } else if (b > 1) {
+            x[i] = alt_draw(&s, b, z[i]);
+        } else if (b > 0) {
+            x[i] = gam_draw(&s, b, z[i], 200);
+        } else {
+            x[i] = 0.0;
+        }
+        if (s.exhausted) x[i] = NAN;
+        close_stream(&s, trace, i, aux);
+    }
+}
