@@ -1,0 +1,425 @@
+// C ABI of the engine: the reference's rpg_* entry points (LogitWrapper.h:27-35)
+// plus the bl_* extensions declared in include/bayeslogit_b200.h.
+//
+// Host-pointer entry points stream the batch through HBM in chunks over three
+// CUDA streams (H2D of chunk k+1 and D2H of chunk k-1 overlap the kernel of chunk
+// k; fully asynchronous when the caller's buffers are pinned).  There is no CPU
+// path: any CUDA failure is reported and the outputs are left untouched, which
+// is how the reference behaves on an exception (LogitWrapper.cpp:226-229).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "engine.h"
+
+namespace bl {
+
+namespace {
+
+constexpr int kSlots = 3;
+constexpr int64_t kChunk = 1 << 22;  // observations per pipeline chunk
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    void *shape = nullptr;
+    double *z = nullptr, *x = nullptr;
+    int *iter = nullptr;
+    int64_t cap = 0;
+};
+
+struct Context {
+    std::mutex mu;
+    bool ready = false;
+    int device = -1;
+    uint64_t seed = 0;
+    uint32_t call = 0;
+    Slot slot[kSlots];
+    std::string err;
+};
+
+Context g;
+std::atomic<uint64_t> g_launches{0};
+thread_local std::string t_err;
+
+int fail(const std::string &msg)
+{
+    t_err = msg;
+    g.err = msg;
+    fprintf(stderr, "Error: %s\n", msg.c_str());
+    return 1;
+}
+
+#define BL_CK(expr)                                                                         \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(std::string(#expr) + ": " + cudaGetErrorString(e_));                \
+    } while (0)
+
+int ensure_ready()
+{
+    if (g.ready) return 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(std::string("bayeslogit_b200: no usable CUDA device (") +
+                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                    "); this engine has no CPU fallback");
+    int dev = g.device;
+    if (dev < 0) {
+        const char *env = getenv("BAYESLOGIT_DEVICE");
+        if (!env) env = getenv("LOCAL_RANK");
+        dev = env ? atoi(env) % count : 0;
+    }
+    BL_CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    BL_CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(std::string("bayeslogit_b200: device '") + prop.name +
+                    "' is not sm_100 class; this library carries sm_100a code only");
+    g.device = dev;
+    for (int s = 0; s < kSlots; ++s) BL_CK(cudaStreamCreateWithFlags(&g.slot[s].stream, cudaStreamNonBlocking));
+    if (g.seed == 0) {
+        const char *env = getenv("BAYESLOGIT_SEED");
+        g.seed = env ? strtoull(env, nullptr, 0)
+                     : (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count() *
+                           0x9E3779B97F4A7C15ull;
+    }
+    g.ready = true;
+    return 0;
+}
+
+int slot_reserve(Slot &s, int64_t n)
+{
+    if (n <= s.cap) return 0;
+    BL_CK(cudaStreamSynchronize(s.stream));
+    if (s.shape) cudaFree(s.shape);
+    if (s.z) cudaFree(s.z);
+    if (s.x) cudaFree(s.x);
+    if (s.iter) cudaFree(s.iter);
+    s.shape = s.z = s.x = nullptr;
+    s.iter = nullptr;
+    s.cap = 0;
+    BL_CK(cudaMalloc(&s.shape, n * sizeof(double)));
+    BL_CK(cudaMalloc((void **)&s.z, n * sizeof(double)));
+    BL_CK(cudaMalloc((void **)&s.x, n * sizeof(double)));
+    BL_CK(cudaMalloc((void **)&s.iter, n * sizeof(int)));
+    s.cap = n;
+    return 0;
+}
+
+size_t shape_size(Method m) { return m == kDevroye ? sizeof(int) : sizeof(double); }
+
+// Host-pointer batch through the chunk pipeline.
+int run_host(Method m, double *x, const void *shape, const double *z, int64_t num, int trunc,
+             int *iter, StreamId id)
+{
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (ensure_ready()) return 1;
+    if (num < 0) return fail("negative batch size");
+    if (num == 0) return 0;
+    if (!x || !shape || !z) return fail("null argument");
+    int64_t chunk = num < kChunk ? num : kChunk;
+    int64_t nchunks = (num + chunk - 1) / chunk;
+    for (int s = 0; s < kSlots && s < nchunks; ++s)
+        if (slot_reserve(g.slot[s], chunk)) return 1;
+    size_t ss = shape_size(m);
+    for (int64_t c = 0; c < nchunks; ++c) {
+        Slot &s = g.slot[c % kSlots];
+        int64_t off = c * chunk;
+        int64_t n = num - off < chunk ? num - off : chunk;
+        BL_CK(cudaMemcpyAsync(s.shape, (const char *)shape + off * ss, n * ss, cudaMemcpyHostToDevice, s.stream));
+        BL_CK(cudaMemcpyAsync(s.z, z + off, n * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        if (iter) BL_CK(cudaMemcpyAsync(s.iter, iter + off, n * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+        StreamId cid = id;
+        cid.obs0 += (uint64_t)off;
+        BL_CK(launch_rpg(m, s.x, s.shape, s.z, n, trunc, iter ? s.iter : nullptr, cid, s.stream));
+        BL_CK(cudaMemcpyAsync(x + off, s.x, n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (iter) BL_CK(cudaMemcpyAsync(iter + off, s.iter, n * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (int s = 0; s < kSlots && s < nchunks; ++s) BL_CK(cudaStreamSynchronize(g.slot[s].stream));
+    return 0;
+}
+
+// Drop-in flavour: global seed + call counter.
+int run_dropin(Method m, double *x, const void *shape, const double *z, const int *num, int trunc,
+               int *iter)
+{
+    if (!num) return fail("null argument");
+    uint64_t seed;
+    uint32_t call;
+    {
+        std::lock_guard<std::mutex> lock(g.mu);
+        if (ensure_ready()) return 1;
+        seed = g.seed;
+        call = g.call++;
+    }
+    return run_host(m, x, shape, z, (int64_t)*num, trunc, iter, StreamId{seed, 0, call});
+}
+
+int run_dev(Method m, double *x, const void *shape, const double *z, int64_t num, int trunc,
+            int *iter, StreamId id, void *stream)
+{
+    {
+        std::lock_guard<std::mutex> lock(g.mu);
+        if (ensure_ready()) return 1;
+    }
+    if (num < 0) return fail("negative batch size");
+    BL_CK(launch_rpg(m, x, shape, z, num, trunc, iter, id, (cudaStream_t)stream));
+    return 0;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int put(const void *host, size_t bytes)
+    {
+        if (bytes == 0) return 0;
+        BL_CK(cudaMalloc(&p, bytes));
+        if (host) BL_CK(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice));
+        return 0;
+    }
+    int get(void *host, size_t bytes)
+    {
+        if (bytes == 0 || !host) return 0;
+        BL_CK(cudaMemcpy(host, p, bytes, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+};
+
+int run_tape(Method m, double *x, const void *shape, const double *z, int64_t num, int trunc,
+             int *iter, const bl_tape *tape, int *trace)
+{
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (ensure_ready()) return 1;
+    if (num <= 0) return num < 0 ? fail("negative batch size") : 0;
+    if (!x || !shape || !z || !tape) return fail("null argument");
+    DevBuf dx, dshape, dz, diter, dtr, du, de, dn, dg;
+    size_t n = (size_t)num;
+    if (dx.put(nullptr, n * 8) || dshape.put(shape, n * shape_size(m)) || dz.put(z, n * 8)) return 1;
+    if (iter && diter.put(iter, n * 4)) return 1;
+    if (trace && dtr.put(nullptr, n * BL_TRACE_W * 4)) return 1;
+    if (tape->tu && du.put(tape->tu, n * tape->lu * 8)) return 1;
+    if (tape->te && de.put(tape->te, n * tape->le * 8)) return 1;
+    if (tape->tn && dn.put(tape->tn, n * tape->ln * 8)) return 1;
+    if (tape->tg && dg.put(tape->tg, n * tape->lg * 8)) return 1;
+    DevTape tp{(const double *)du.p, (const double *)de.p, (const double *)dn.p, (const double *)dg.p,
+               tape->lu, tape->le, tape->ln, tape->lg};
+    cudaStream_t st = g.slot[0].stream;
+    BL_CK(launch_rpg_tape(m, (double *)dx.p, dshape.p, (const double *)dz.p, num, trunc,
+                          iter ? (int *)diter.p : nullptr, tp, trace ? (int *)dtr.p : nullptr, st));
+    BL_CK(cudaStreamSynchronize(st));
+    if (dx.get(x, n * 8)) return 1;
+    if (iter && diter.get(iter, n * 4)) return 1;
+    if (trace && dtr.get(trace, n * BL_TRACE_W * 4)) return 1;
+    return 0;
+}
+
+}  // namespace
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+}  // namespace bl
+
+using namespace bl;
+
+extern "C" {
+
+// ---- Part 1: reference entry points -------------------------------------------------
+
+void rpg_gamma(double *x, double *n, double *z, int *num, int *trunc)
+{
+    run_dropin(kGamma, x, n, z, num, trunc ? *trunc : 200, nullptr);
+}
+
+void rpg_devroye(double *x, int *n, double *z, int *num)
+{
+    run_dropin(kDevroye, x, n, z, num, 0, nullptr);
+}
+
+void rpg_alt(double *x, double *h, double *z, int *num)
+{
+    run_dropin(kAlt, x, h, z, num, 0, nullptr);
+}
+
+void rpg_sp(double *x, double *h, double *z, int *num, int *iter)
+{
+    run_dropin(kSP, x, h, z, num, 0, iter);
+}
+
+void rpg_hybrid(double *x, double *h, double *z, int *num)
+{
+    run_dropin(kHybrid, x, h, z, num, 0, nullptr);
+}
+
+// ---- Part 2: extensions ---------------------------------------------------------------
+
+int bl_version(void) { return 100; }
+
+const char *bl_last_error(void) { return g.err.c_str(); }
+
+void bl_clear_error(void)
+{
+    std::lock_guard<std::mutex> lock(g.mu);
+    g.err.clear();
+}
+
+int bl_set_device(int device)
+{
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (g.ready && device != g.device)
+        return fail("bl_set_device: the engine is already bound to another device (one process per GPU)");
+    g.device = device;
+    return ensure_ready();
+}
+
+int bl_get_device(void) { return g.device; }
+
+void bl_set_seed(uint64_t seed)
+{
+    std::lock_guard<std::mutex> lock(g.mu);
+    g.seed = seed ? seed : 0x9E3779B97F4A7C15ull;
+    g.call = 0;
+}
+
+uint64_t bl_get_seed(void) { return g.seed; }
+uint32_t bl_get_call_counter(void) { return g.call; }
+
+int bl_rpg_devroye_dev(double *x, const int *n, const double *z, int64_t num, uint64_t seed,
+                       uint32_t call_id, uint64_t obs0, void *stream)
+{
+    return run_dev(kDevroye, x, n, z, num, 0, nullptr, StreamId{seed, obs0, call_id}, stream);
+}
+int bl_rpg_gamma_dev(double *x, const double *n, const double *z, int64_t num, int trunc,
+                     uint64_t seed, uint32_t call_id, uint64_t obs0, void *stream)
+{
+    return run_dev(kGamma, x, n, z, num, trunc, nullptr, StreamId{seed, obs0, call_id}, stream);
+}
+int bl_rpg_alt_dev(double *x, const double *h, const double *z, int64_t num, uint64_t seed,
+                   uint32_t call_id, uint64_t obs0, void *stream)
+{
+    return run_dev(kAlt, x, h, z, num, 0, nullptr, StreamId{seed, obs0, call_id}, stream);
+}
+int bl_rpg_sp_dev(double *x, const double *h, const double *z, int64_t num, int *iter,
+                  uint64_t seed, uint32_t call_id, uint64_t obs0, void *stream)
+{
+    return run_dev(kSP, x, h, z, num, 0, iter, StreamId{seed, obs0, call_id}, stream);
+}
+int bl_rpg_hybrid_dev(double *x, const double *h, const double *z, int64_t num, uint64_t seed,
+                      uint32_t call_id, uint64_t obs0, void *stream)
+{
+    return run_dev(kHybrid, x, h, z, num, 0, nullptr, StreamId{seed, obs0, call_id}, stream);
+}
+
+int bl_rpg_devroye_seeded(double *x, const int *n, const double *z, int64_t num, uint64_t seed,
+                          uint32_t call_id, uint64_t obs0)
+{
+    return run_host(kDevroye, x, n, z, num, 0, nullptr, StreamId{seed, obs0, call_id});
+}
+int bl_rpg_gamma_seeded(double *x, const double *n, const double *z, int64_t num, int trunc,
+                        uint64_t seed, uint32_t call_id, uint64_t obs0)
+{
+    return run_host(kGamma, x, n, z, num, trunc, nullptr, StreamId{seed, obs0, call_id});
+}
+int bl_rpg_alt_seeded(double *x, const double *h, const double *z, int64_t num, uint64_t seed,
+                      uint32_t call_id, uint64_t obs0)
+{
+    return run_host(kAlt, x, h, z, num, 0, nullptr, StreamId{seed, obs0, call_id});
+}
+int bl_rpg_sp_seeded(double *x, const double *h, const double *z, int64_t num, int *iter,
+                     uint64_t seed, uint32_t call_id, uint64_t obs0)
+{
+    return run_host(kSP, x, h, z, num, 0, iter, StreamId{seed, obs0, call_id});
+}
+int bl_rpg_hybrid_seeded(double *x, const double *h, const double *z, int64_t num, uint64_t seed,
+                         uint32_t call_id, uint64_t obs0)
+{
+    return run_host(kHybrid, x, h, z, num, 0, nullptr, StreamId{seed, obs0, call_id});
+}
+
+int bl_rpg_devroye_tape(double *x, const int *n, const double *z, int64_t num, const bl_tape *tape,
+                        int *trace)
+{
+    return run_tape(kDevroye, x, n, z, num, 0, nullptr, tape, trace);
+}
+int bl_rpg_gamma_tape(double *x, const double *n, const double *z, int64_t num, int trunc,
+                      const bl_tape *tape, int *trace)
+{
+    return run_tape(kGamma, x, n, z, num, trunc, nullptr, tape, trace);
+}
+int bl_rpg_alt_tape(double *x, const double *h, const double *z, int64_t num, const bl_tape *tape,
+                    int *trace)
+{
+    return run_tape(kAlt, x, h, z, num, 0, nullptr, tape, trace);
+}
+int bl_rpg_sp_tape(double *x, const double *h, const double *z, int64_t num, int *iter,
+                   const bl_tape *tape, int *trace)
+{
+    return run_tape(kSP, x, h, z, num, 0, iter, tape, trace);
+}
+int bl_rpg_hybrid_tape(double *x, const double *h, const double *z, int64_t num,
+                       const bl_tape *tape, int *trace)
+{
+    return run_tape(kHybrid, x, h, z, num, 0, nullptr, tape, trace);
+}
+
+int bl_probe_pg_moments(double *m1, double *m2, const double *b, const double *z, int64_t num)
+{
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (ensure_ready()) return 1;
+    DevBuf d1, d2, db, dz;
+    size_t n = (size_t)num * 8;
+    if (d1.put(nullptr, n) || d2.put(nullptr, n) || db.put(b, n) || dz.put(z, n)) return 1;
+    BL_CK(launch_probe_moments((double *)d1.p, (double *)d2.p, (const double *)db.p,
+                               (const double *)dz.p, num, g.slot[0].stream));
+    BL_CK(cudaStreamSynchronize(g.slot[0].stream));
+    return d1.get(m1, n) || d2.get(m2, n);
+}
+
+int bl_probe_v_eval(double *v, const double *y, int64_t num)
+{
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (ensure_ready()) return 1;
+    DevBuf dv, dy;
+    size_t n = (size_t)num * 8;
+    if (dv.put(nullptr, n) || dy.put(y, n)) return 1;
+    BL_CK(launch_probe_v_eval((double *)dv.p, (const double *)dy.p, num, g.slot[0].stream));
+    BL_CK(cudaStreamSynchronize(g.slot[0].stream));
+    return dv.get(v, n);
+}
+
+int bl_probe_specfun(double *out, int which, const double *a, const double *b, const double *c,
+                     int64_t num)
+{
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (ensure_ready()) return 1;
+    DevBuf dout, da, db, dc;
+    size_t n = (size_t)num * 8;
+    if (dout.put(nullptr, n) || da.put(a, n) || db.put(b ? b : a, n) || dc.put(c ? c : a, n)) return 1;
+    BL_CK(launch_probe_specfun((double *)dout.p, which, (const double *)da.p, (const double *)db.p,
+                               (const double *)dc.p, num, g.slot[0].stream));
+    BL_CK(cudaStreamSynchronize(g.slot[0].stream));
+    return dout.get(out, n);
+}
+
+int bl_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2)
+{
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (ensure_ready()) return 1;
+    DevBuf dout, dc, dk;
+    if (dout.put(nullptr, 16) || dc.put(ctr4, 16) || dk.put(key2, 8)) return 1;
+    BL_CK(launch_probe_philox((uint32_t *)dout.p, (const uint32_t *)dc.p, (const uint32_t *)dk.p,
+                              g.slot[0].stream));
+    BL_CK(cudaStreamSynchronize(g.slot[0].stream));
+    return dout.get(out4, 16);
+}
+
+uint64_t bl_kernel_launches(void) { return g_launches.load(); }
+
+}  // extern "C"

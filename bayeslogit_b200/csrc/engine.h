@@ -1,0 +1,45 @@
+// Internal host-side interface between the C ABI (capi.cu) and the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/bayeslogit_b200.h"
+
+namespace bl {
+
+enum Method { kDevroye = 0, kGamma = 1, kAlt = 2, kSP = 3, kHybrid = 4 };
+
+// Stream identity of a batch (see philox.cuh).
+struct StreamId {
+    uint64_t seed;
+    uint64_t obs0;
+    uint32_t call_id;
+};
+
+// Device-side tape descriptor (device pointers).
+struct DevTape {
+    const double *tu, *te, *tn, *tg;
+    int lu, le, ln, lg;
+};
+
+// Batch draw, Philox streams.  shape: int32 for kDevroye, double otherwise.
+cudaError_t launch_rpg(Method m, double *x, const void *shape, const double *z, int64_t num,
+                       int trunc, int *iter, StreamId id, cudaStream_t stream);
+
+// Batch draw from tapes; trace may be null.
+cudaError_t launch_rpg_tape(Method m, double *x, const void *shape, const double *z, int64_t num,
+                            int trunc, int *iter, DevTape tape, int *trace, cudaStream_t stream);
+
+cudaError_t launch_probe_moments(double *m1, double *m2, const double *b, const double *z,
+                                 int64_t num, cudaStream_t stream);
+cudaError_t launch_probe_v_eval(double *v, const double *y, int64_t num, cudaStream_t stream);
+cudaError_t launch_probe_specfun(double *out, int which, const double *a, const double *b,
+                                 const double *c, int64_t num, cudaStream_t stream);
+cudaError_t launch_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2,
+                                cudaStream_t stream);
+
+void count_launch(int n = 1);
+
+}  // namespace bl

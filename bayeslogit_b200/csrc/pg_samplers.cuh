@@ -1,0 +1,559 @@
+// Per-lane Polya-Gamma samplers (fp64), templated on the variate source so the
+// very same code runs from the Philox stream and from an injected tape.
+//
+// What each routine computes, and the reference statement it has to agree with:
+//   devroye_one      PG(1,z)            PolyaGamma.cpp:151-202 (+ :41-55, :65-80, :82-115)
+//   devroye_sum      sum of n PG(1,z)   PolyaGamma.cpp:126-140
+//   gamma_sum        truncated sum      PolyaGamma.cpp:142-149, :19-39
+//   alt_chunk/alt    PG(h,z), h>=1      PolyaGammaAlt.cpp:114-203, :205-225
+//   v_eval           y -> v             InvertY.cpp:57-99
+//   sp_draw          PG(n,z), n large   PolyaGammaSP.cpp:169-264
+//   pg_m1 / pg_m2    exact moments      PolyaGamma.cpp:208-239
+//   hybrid           regime dispatch    LogitWrapper.cpp:140-162
+// Composite variates (the reference takes them from its absent RNG library) follow
+// the in-tree R statements: Ch.R:83-114 (left-truncated gamma), Ch.R:403-413
+// (inverse Gaussian), SPSample.R:534-550 (right-truncated inverse chi^2 through a
+// one-sided truncated normal, Robert 1995).
+//
+// Differences from the reference that do NOT change any decision or value:
+//   * the right-piece proposal mass depends on Z only and is computed once per
+//     draw instead of once per proposal (PolyaGamma.cpp:170 recomputes it);
+//   * constant logarithms are folded.
+#pragma once
+
+#include "philox.cuh"
+#include "specfun.cuh"
+
+#define PG_TABLE_QUAL static __device__ __constant__
+#include "pg_tables.h"
+
+namespace bl {
+
+constexpr double kTrunc = 0.64;  // PolyaGamma.h:37
+
+// ----------------------------------------------------------------------------
+// Devroye PG(1,z)
+// ----------------------------------------------------------------------------
+
+__device__ __forceinline__ double dev_coef(int n, double x)
+{
+    double K = (n + 0.5) * kPi;
+    if (x > kTrunc) return K * exp(-0.5 * K * K * x);
+    if (x > 0) {
+        double e = -1.5 * (log(0.5 * kPi) + log(x)) + log(K) - 2.0 * (n + 0.5) * (n + 0.5) / x;
+        return exp(e);
+    }
+    return 0.0;
+}
+
+__device__ __forceinline__ double dev_right_mass(double Z)
+{
+    const double t = kTrunc;
+    double fz = 0.125 * kPi * kPi + 0.5 * Z * Z;
+    double b = sqrt(1.0 / t) * (t * Z - 1);
+    double a = sqrt(1.0 / t) * (t * Z + 1) * -1.0;
+    double x0 = log(fz) + fz * t;
+    double xb = x0 - Z + log_p_norm(b);
+    double xa = x0 + Z + log_p_norm(a);
+    double qdivp = 4 / kPi * (exp(xb) + exp(xa));
+    return 1.0 / (1.0 + qdivp);
+}
+
+template <class Src>
+__device__ __forceinline__ double dev_trunc_igauss(Src &s, double Z)
+{
+    const double t = kTrunc;
+    double X = t + 1.0;
+    if (1.0 / kTrunc > Z) {
+        double alpha = 0.0;
+        while (s.unif() > alpha) {
+            double E1 = s.expon();
+            double E2 = s.expon();
+            while (E1 * E1 > 2 * E2 / t) {
+                E1 = s.expon();
+                E2 = s.expon();
+            }
+            X = 1 + E1 * t;
+            X = t / (X * X);
+            alpha = exp(-0.5 * Z * Z * X);
+        }
+    } else {
+        double mu = 1.0 / Z;
+        while (X > t) {
+            double Y = s.norm();
+            Y *= Y;
+            double half_mu = 0.5 * mu;
+            double mu_Y = mu * Y;
+            X = mu + half_mu * mu_Y - half_mu * sqrt(4 * mu_Y + mu_Y * mu_Y);
+            if (s.unif() > mu / (mu + X)) X = mu * mu / X;
+        }
+    }
+    return X;
+}
+
+template <class Src>
+__device__ __forceinline__ double devroye_one(Src &s, double Z, double fz, double right_mass)
+{
+    for (;;) {
+        double X;
+        if (s.unif() < right_mass)
+            X = kTrunc + s.expon() / fz;
+        else
+            X = dev_trunc_igauss(s, Z);
+        double S = dev_coef(0, X);
+        double Y = s.unif() * S;
+        int n = 0;
+        for (;;) {
+            ++n;
+            if (n & 1) {
+                S = S - dev_coef(n, X);
+                if (Y <= S) return 0.25 * X;
+            } else {
+                S = S + dev_coef(n, X);
+                if (Y > S) break;
+            }
+        }
+    }
+}
+
+template <class Src>
+__device__ __forceinline__ double devroye_sum(Src &s, int n, double z)
+{
+    if (n < 1) n = 1;  // the package builds with -DNTHROW: clamp, PolyaGamma.cpp:128-135
+    double Z = fabs(z) * 0.5;
+    double fz = 0.125 * kPi * kPi + 0.5 * Z * Z;
+    double pr = dev_right_mass(Z);
+    double sum = 0.0;
+    for (int i = 0; i < n; ++i) sum += devroye_one(s, Z, fz, pr);
+    return sum;
+}
+
+// ----------------------------------------------------------------------------
+// Truncated sum of gammas
+// ----------------------------------------------------------------------------
+
+template <class Src>
+__device__ __forceinline__ double gamma_sum(Src &s, double b, double z, int T)
+{
+    if (T < 1) T = 1;
+    double x = 0.0;
+    double kappa = z * z;
+    for (int k = 0; k < T; ++k) {
+        double d = (double)k + 0.5;
+        double bk = (4 * kPi * kPi) * d * d;
+        x += s.gamma(b) / (bk + kappa);
+    }
+    return 2.0 * x;
+}
+
+// ----------------------------------------------------------------------------
+// Exact moments
+// ----------------------------------------------------------------------------
+
+__device__ __forceinline__ double jj_m1(double b, double z)
+{
+    z = fabs(z);
+    if (z > 1e-12) return b * tanh(z) / z;
+    return b * (1 - (1.0 / 3) * pow(z, 2) + (2.0 / 15) * pow(z, 4) - (17.0 / 315) * pow(z, 6));
+}
+
+__device__ __forceinline__ double jj_m2(double b, double z)
+{
+    z = fabs(z);
+    if (z > 1e-12) {
+        double tz = tanh(z) / z;
+        return (b + 1) * b * (tz * tz) + b * ((tanh(z) - z) / (z * z * z));
+    }
+    double p = 1 - (1.0 / 3) * pow(z, 2) + (2.0 / 15) * pow(z, 4) - (17.0 / 315) * pow(z, 6);
+    return (b + 1) * b * (p * p) + b * ((-1.0 / 3) + (2.0 / 15) * pow(z, 2) - (17.0 / 315) * pow(z, 4));
+}
+
+__device__ __forceinline__ double pg_m1(double b, double z) { return jj_m1(b, 0.5 * z) * 0.25; }
+__device__ __forceinline__ double pg_m2(double b, double z) { return jj_m2(b, 0.5 * z) * 0.0625; }
+
+// ----------------------------------------------------------------------------
+// Composite variates
+// ----------------------------------------------------------------------------
+
+template <class Src>
+__device__ __forceinline__ double igauss(Src &s, double mu, double lambda)
+{
+    double nu = s.norm();
+    double y = nu * nu;
+    double x = mu + 0.5 * mu * mu * y / lambda
+             - 0.5 * mu / lambda * sqrt(4.0 * mu * lambda * y + (mu * y) * (mu * y));
+    if (s.unif() > mu / (mu + x)) x = mu * mu / x;
+    return x;
+}
+
+template <class Src>
+__device__ __forceinline__ double ltgamma(Src &s, double shape, double rate, double trunc)
+{
+    double a = shape;
+    double b = rate * trunc;
+    if (trunc <= 0.0 || shape < 1.0) return 0.0;
+    if (shape == 1.0) return s.expon() / rate + trunc;
+    double d1 = b - a;
+    double d3 = a - 1.0;
+    double c0 = 0.5 * (d1 + sqrt(d1 * d1 + 4.0 * b)) / b;
+    double l_M = d3 * log(d3 / (1.0 - c0)) - d3;
+    double x;
+    for (;;) {
+        x = b + s.expon() / c0;
+        double u = s.unif();
+        double l_rho = d3 * log(x) - x * (1.0 - c0);
+        if (log(u) <= l_rho - l_M) break;
+    }
+    return trunc * (x / b);
+}
+
+template <class Src>
+__device__ __forceinline__ double tnorm_left(Src &s, double left)
+{
+    if (left < 0.0) {
+        for (;;) {
+            double z = s.norm();
+            if (z > left) return z;
+        }
+    }
+    double astar = 0.5 * (left + sqrt(left * left + 4.0));
+    for (;;) {
+        double z = s.expon() / astar + left;
+        double rho = exp(-0.5 * (z - astar) * (z - astar));
+        if (s.unif() < rho) return z;
+    }
+}
+
+template <class Src>
+__device__ __forceinline__ double rtinvchi2(Src &s, double scale, double trunc)
+{
+    double R = trunc / scale;
+    double z = tnorm_left(s, 1.0 / sqrt(R));
+    return scale / (z * z);
+}
+
+// ----------------------------------------------------------------------------
+// Alternate sampler
+// ----------------------------------------------------------------------------
+
+template <class Src>
+__device__ __forceinline__ double alt_rtinvchi2(Src &s, double h, double trunc)
+{
+    double h2 = h * h;
+    double R = trunc / h2;
+    double E1 = s.expon();
+    double E2 = s.expon();
+    while ((E1 * E1) > (2 * E2 / R)) {
+        E1 = s.expon();
+        E2 = s.expon();
+    }
+    double X = 1 + E1 * R;
+    X = R / (X * X);
+    return h2 * X;
+}
+
+__device__ __forceinline__ double alt_coef(double n, double x, double h, double coef_h, double &g)
+{
+    double d_n = 2.0 * n + h;
+    if (n != 0)
+        g *= (n + h - 1) / n;
+    else
+        g = 1.0;
+    double coef = coef_h * g;
+    double log_kernel = -0.5 * (log(x * x * x) + d_n * d_n / x) + log(d_n);
+    return coef * exp(log_kernel);
+}
+
+__device__ __forceinline__ double alt_pigauss(double x, double z, double lambda)
+{
+    double sq = sqrt(lambda / x);
+    double b = sq * (x * z - 1);
+    double a = sq * (x * z + 1) * -1.0;
+    return p_norm(b) + exp(2 * lambda * z) * p_norm(a);
+}
+
+__device__ __forceinline__ double alt_envelope(double x, double h, double trunc)
+{
+    if (x > trunc)
+        return exp(h * log(0.5 * kPi) + (h - 1) * log(x) - kPi * kPi * 0.125 * x - lgamma(h));
+    return h * exp(h * log(2.0) - 0.5 * log(2.0 * kPi * x * x * x) - 0.5 * h * h / x);
+}
+
+template <class Src>
+__device__ double alt_chunk(Src &s, double h, double z)
+{
+    const int max_inner = 200;
+    if (h < 1 || h > 4) return 0;
+    z = fabs(z) * 0.5;
+    int idx = (int)floor((h - 1.0) * 100.0);
+    double trunc = PG_TRUNC_SCHEDULE[idx];
+    double rate_z = 0.125 * kPi * kPi + 0.5 * z * z;
+    double wl, wr;
+    if (z != 0)
+        wl = exp(h * (log(2.0) - z)) * alt_pigauss(trunc, z / h, h * h);
+    else
+        wl = exp(h * log(2.0)) * (1.0 - p_gamma_rate(1 / trunc, 0.5, 0.5 * h * h));
+    {
+        double lambda_z = kPi * kPi * 0.125 + 0.5 * z * z;
+        wr = exp(h * log((0.5 * kPi) / lambda_z)) * (1.0 - p_gamma_rate(trunc, h, lambda_z));
+    }
+    double prob_right = wr / (wr + wl);
+    double coef1_h = exp(h * log(2.0) - 0.5 * log(2.0 * kPi));
+    double g = 1.0;
+    for (int trial = 0; trial < 10000; ++trial) {
+        double X;
+        double uu = s.unif();
+        if (uu < prob_right) {
+            X = ltgamma(s, h, rate_z, trunc);
+        } else {
+            double mu = h / z;
+            X = trunc + 1.0;
+            if (mu > trunc) {
+                double alpha = 0.0;
+                while (s.unif() > alpha) {
+                    X = alt_rtinvchi2(s, h, trunc);
+                    alpha = exp(-0.5 * z * z * X);
+                }
+            } else {
+                while (X > trunc) X = igauss(s, mu, h * h);
+            }
+        }
+        double S = alt_coef(0.0, X, h, coef1_h, g);
+        double a_n = S;
+        double gt = alt_envelope(X, h, trunc);
+        double Y = s.unif() * gt;
+        int n = 0;
+        bool go = true;
+        while (go && n < max_inner) {
+            ++n;
+            double prev = a_n;
+            a_n = alt_coef((double)n, X, h, coef1_h, g);
+            bool decreasing = a_n <= prev;
+            if (n & 1) {
+                S = S - a_n;
+                if (Y <= S && decreasing) return 0.25 * X;
+            } else {
+                S = S + a_n;
+                if (Y > S && decreasing) go = false;
+            }
+        }
+    }
+    return -1.0;
+}
+
+template <class Src>
+__device__ double alt_draw(Src &s, double h, double z)
+{
+    if (h < 1) return 0;
+    double n = floor((h - 1.0) / 4.0);
+    double remain = h - 4.0 * n;
+    double x = 0.0;
+    for (int i = 0; i < (int)n; i++) x += alt_chunk(s, 4.0, z);
+    if (remain > 4.0) {
+        double first = alt_chunk(s, 0.5 * remain, z);
+        double second = alt_chunk(s, 0.5 * remain, z);
+        x += first + second;
+    } else {
+        x += alt_chunk(s, remain, z);
+    }
+    return x;
+}
+
+// ----------------------------------------------------------------------------
+// y(v) inversion and the saddle-point sampler
+// ----------------------------------------------------------------------------
+
+// y(v): the series branch is the constant 1 because the reference's coefficients
+// (1/3), (2/15), (17/315) are integer divisions (InvertY.cpp:19, PolyaGammaSP.cpp:88).
+__device__ __forceinline__ double y_of_v(double v, double tol)
+{
+    double r = sqrt(fabs(v));
+    if (v > tol) return tan(r) / r;
+    if (v < -1 * tol) return tanh(r) / r;
+    return 1.0;
+}
+
+__device__ inline double v_eval(double y)
+{
+    const double tol = 1e-9;
+    const int max_iter = 1000;
+    if (y < PG_YGRID[0]) return -1. / (y * y);
+    if (y > PG_YGRID[PG_YGRID_LEN - 1]) {
+        double v = atan(0.5 * y * kPi);
+        return v * v;
+    }
+    if (y == 1) return 0.0;
+    double id = (log(y) / log(2.0) + 4.0) / 0.1;
+    int idlow = (int)id;
+    int idhigh = idlow + 1;
+    if (idhigh > PG_VGRID_LEN - 1) idhigh = PG_VGRID_LEN - 1;  // y == 16 exactly, see DESIGN.md
+    double vl = PG_VGRID[idlow];
+    double vh = PG_VGRID[idhigh];
+    int iter = 0;
+    double diff = tol + 1.0;
+    double vnew = vl, vold = vl;
+    while (diff > tol && iter < max_iter) {
+        iter++;
+        vold = vnew;
+        double yv = y_of_v(vold, 1e-8);
+        double f0 = yv - y;
+        double f1;
+        if (fabs(vold) >= 1e-8)
+            f1 = 0.5 * (yv * yv + (1 - yv) / vold);
+        else
+            f1 = 0.5 * (yv * yv);
+        vnew = vold - f0 / f1;
+        vnew = vnew > vh ? vh : vnew;
+        vnew = vnew < vl ? vl : vnew;
+        diff = fabs(vnew - vold);
+    }
+    return vnew;
+}
+
+__device__ __forceinline__ double sp_cos_rt(double v)
+{
+    double r = sqrt(fabs(v));
+    return v >= 0 ? cos(r) : cosh(r);
+}
+
+__device__ inline void sp_tangent(double x, double z, double mid, double &slope, double &icept)
+{
+    double v = v_eval(x);
+    double u = 0.5 * v;
+    double t = u + 0.5 * z * z;
+    double phi_val = log(cosh(fabs(z))) - log(sp_cos_rt(v)) - t * x;
+    double phi_der = -1.0 * t;
+    double delta_val, delta_der;
+    if (x >= mid) {
+        delta_val = log(x) - log(mid);
+        delta_der = 1.0 / x;
+    } else {
+        delta_val = 0.5 * (1 - 1.0 / x) - 0.5 * (1 - 1.0 / mid);
+        delta_der = 0.5 / (x * x);
+    }
+    double eta_val = phi_val - delta_val;
+    double eta_der = phi_der - delta_der;
+    slope = eta_der;
+    icept = eta_val - eta_der * x;
+}
+
+__device__ inline double sp_density(double x, double n, double z)
+{
+    double v = v_eval(x);
+    double u = 0.5 * v;
+    double z2 = z * z;
+    double t = u + 0.5 * z2;
+    double phi = log(cosh(z)) - log(sp_cos_rt(v)) - t * x;
+    double K2;
+    if (fabs(v) >= 1e-6)
+        K2 = x * x + (1 - x) / v;
+    else
+        K2 = x * x;
+    double log_spa = 0.5 * log(0.5 * n / kPi) - 0.5 * log(K2) + n * phi;
+    return exp(log_spa);
+}
+
+template <class Src>
+__device__ int sp_draw(Src &s, double &d, double n, double z)
+{
+    const int maxiter = 200;
+    z = 0.5 * fabs(z);
+    double xl = y_of_v(-1 * z * z, 1e-6);
+    double md = xl * 1.1;
+    double xr = xl * 1.2;
+    double vmd = v_eval(md);
+    double K2md;
+    if (fabs(vmd) >= 1e-6)
+        K2md = md * md + (1 - md) / vmd;
+    else
+        K2md = md * md;
+    double m2 = md * md;
+    double al = m2 * md / K2md;
+    double ar = m2 / K2md;
+    double sl, il, sr, ir;
+    sp_tangent(xl, z, md, sl, il);
+    sp_tangent(xr, z, md, sr, ir);
+    double rl = -1. * sl;
+    double rr = -1. * sr;
+    double lcn = 0.5 * log(0.5 * n / kPi);
+    double rt2rl = sqrt(2 * rl);
+    double wl = exp(0.5 * log(al) - n * rt2rl + n * il + 0.5 * n * 1. / md) * p_igauss(md, 1. / rt2rl, n);
+    double wr = exp(0.5 * log(ar) + lcn - n * log(n * rr) + n * ir - n * log(md)) * tgamma(n)
+              * (1.0 - p_gamma_rate(md, n, n * rr));
+    double wt = wl + wr;
+    double pl = wl / wt;
+    bool go = true;
+    int iter = 0;
+    double X = 2.0, F = 0.0;
+    while (go && iter < maxiter) {
+        iter++;
+        double phi_ev;
+        if (s.unif() < pl) {
+            double mu = 1. / rt2rl;
+            X = md + 1.0;
+            if (md < mu) {
+                double alpha = 0.0;
+                while (s.unif() > alpha) {
+                    X = rtinvchi2(s, n, md);
+                    alpha = exp(-0.5 * n / (mu * mu) * X);
+                }
+            } else {
+                while (X > md) X = igauss(s, mu, n);
+            }
+            phi_ev = n * (il - rl * X) + 0.5 * n * ((1. - 1. / X) - (1. - 1. / md));
+            F = exp(0.5 * log(al) + lcn - 1.5 * log(X) + phi_ev);
+        } else {
+            X = ltgamma(s, n, n * rr, md);
+            phi_ev = n * (ir - rr * X) + n * (log(X) - log(md));
+            F = exp(0.5 * log(ar) + lcn + phi_ev) / X;
+        }
+        double spa = sp_density(X, n, z);
+        if (F * s.unif() < spa) go = false;
+    }
+    d = n * 0.25 * X;
+    return iter;
+}
+
+// ----------------------------------------------------------------------------
+// Regime dispatch
+// ----------------------------------------------------------------------------
+
+enum Regime { kRegZero = 0, kRegGamma = 1, kRegDevroye = 2, kRegAlt = 3, kRegSP = 4, kRegNormal = 5 };
+
+__device__ __forceinline__ int regime_of(double b)
+{
+    if (b > 170) return kRegNormal;
+    if (b > 13) return kRegSP;
+    if (b == 1 || b == 2) return kRegDevroye;
+    if (b > 1) return kRegAlt;
+    if (b > 0) return kRegGamma;
+    return kRegZero;
+}
+
+template <class Src>
+__device__ double hybrid_draw(Src &s, double b, double z, int &aux)
+{
+    aux = 0;
+    switch (regime_of(b)) {
+    case kRegNormal: {
+        double m = pg_m1(b, z);
+        double v = pg_m2(b, z) - m * m;
+        return m + sqrt(v) * s.norm();
+    }
+    case kRegSP: {
+        double d;
+        aux = sp_draw(s, d, b, z);
+        return d;
+    }
+    case kRegDevroye:
+        return devroye_sum(s, (int)b, z);
+    case kRegAlt:
+        return alt_draw(s, b, z);
+    case kRegGamma:
+        return gamma_sum(s, b, z, 200);
+    default:
+        return 0.0;
+    }
+}
+
+}  // namespace bl

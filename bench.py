@@ -1,0 +1,318 @@
+#!/usr/bin/env python3
+"""Benchmark of the Polya-Gamma hot path (bench contract: see the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference]
+                    [--workload hybrid|pg1] [--num DRAWS]
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): 100M mixed-shape
+PG(b,z) draws per GPU -- b: 50% real U(0.5,200), 50% integer U{1..200};
+z ~ U(-5,5); seed 20240002 -- exercising the Devroye / sum-of-gammas / alternate /
+saddle-point / normal dispatch of rpg_hybrid (LogitWrapper.cpp:129-167).
+A step is one pass of rpg_hybrid over the whole batch.
+
+  value  : draws/s with inputs resident in HBM (CUDA events on the launch stream)
+  e2e    : draws/s through the reference-facing C ABI `rpg_hybrid` with pinned HOST
+           buffers, H2D + D2H inside the timed region
+  roofline, cpu_baseline, clocks, gpu_launches: see DESIGN.md "Measurement"
+
+`--impl reference` times the reference's own CPU sampler (oracle/_ref: the
+reference sources compiled in place; the plain-C port if that is absent) on all
+host cores, on a bounded sample of the same workload.
+
+N > 1: one process per GPU under torchrun; observations are sharded, rank r draws
+global observations [r*num, (r+1)*num) -- no data-path collective ("weak").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20240002
+CPU_SAMPLE = {"hybrid": 16_000_000, "pg1": 64_000_000}
+# algorithmic HBM bytes per draw: shape in + z in + omega out (fp64; n is int32 for pg1)
+BYTES_PER_DRAW = {"hybrid": 24, "pg1": 20}
+# fp64-equivalent flop model per draw, SURVEY.md section 8(d): 0.9 kFLOP for a Devroye
+# PG(1,z) draw; the mixed workload is weighted by its regime shares (SP ~ 10x).
+KFLOP_PER_DRAW = {"pg1": 0.9, "hybrid": 0.786 * 9.0 + 0.058 * 3.0 + 0.15 * 0.3 + 0.005 * 1.35 + 0.0013 * 60.0}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="hybrid", choices=["hybrid", "pg1"])
+    ap.add_argument("--num", type=int, default=100_000_000, help="draws per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def make_inputs_numpy(workload, num, obs0=0):
+    """The workload's (shape, z) for global observations [obs0, obs0+num) -- host side."""
+    import numpy as np
+    rng = np.random.default_rng([SEED, obs0])
+    z = rng.uniform(-5.0, 5.0, num)
+    if workload == "pg1":
+        return np.ones(num, dtype=np.int32), z
+    real = rng.uniform(0.5, 200.0, num)
+    integer = rng.integers(1, 201, num).astype(np.float64)
+    return np.where(rng.random(num) < 0.5, real, integer), z
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [t.strip() for t in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.3] or [r for _, r in self.rows]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows if len(r) > 2)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 5 + k and r[5 + k] == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def load_oracle():
+    from oracle import loader
+    if loader.available("reference"):
+        return loader.Oracle("reference")
+    if not loader.available("port"):
+        loader.build(("port",))
+    return loader.Oracle("port")
+
+
+def time_cpu(workload, sample, nthreads):
+    """Reference CPU sampler on `sample` draws of the workload; returns (seconds, kind)."""
+    O = load_oracle()
+    shape, z = make_inputs_numpy(workload, sample)
+    t = time.perf_counter()
+    if workload == "pg1":
+        O.rpg_devroye(shape, z, seed=SEED, nthreads=nthreads)
+    else:
+        O.rpg_hybrid(shape, z, seed=SEED, nthreads=nthreads)
+    return time.perf_counter() - t, O.kind
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = min(CPU_SAMPLE[args.workload], args.num)
+    for _ in range(args.warmup):
+        time_cpu(args.workload, max(sample // 16, 1), cores)
+    t = 0.0
+    kind = "port"
+    for _ in range(args.steps):
+        dt, kind = time_cpu(args.workload, sample, cores)
+        t += dt
+    value = sample * args.steps / t
+    desc = f"first {sample} draws of the workload per step, all {cores} host threads (OpenMP, one RNG+sampler per thread)"
+    print(json.dumps({
+        "impl": "reference", "metric": "pg_draws_per_sec", "value": value, "unit": "draws/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "draws/s", "cores": cores, "kind": kind, "sample": desc},
+        "e2e": {"value": value, "unit": "draws/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args):
+    name = ("rpg_hybrid mixed-shape PG(b,z): b 50% real U(0.5,200) + 50% integer U{1..200}, z~U(-5,5)"
+            if args.workload == "hybrid" else "rpg_devroye PG(1,z), z~U(-5,5)")
+    return {"workload": name, "draws_per_gpu_per_step": args.num, "seed": SEED,
+            "l2": "inputs_larger_than_l2" if args.num * 16 > 126e6 else "l2_flushed_between_steps",
+            "parallelism": f"obs-shard x{args.gpus}"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from bayeslogit_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L = _lib.lib()
+    _lib.check(L.bl_set_device(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    num = args.num
+    obs0 = rank * num
+    wl = args.workload
+    shape_h, z_h = make_inputs_numpy(wl, num, obs0)
+    # device-resident inputs for `value`
+    shape_d = torch.from_numpy(shape_h).to(dev)
+    z_d = torch.from_numpy(z_h).to(dev)
+    x_d = torch.empty(num, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if num * 16 <= 126e6 else None
+    stream = torch.cuda.current_stream().cuda_stream
+    fn_dev = L.bl_rpg_hybrid_dev if wl == "hybrid" else L.bl_rpg_devroye_dev
+
+    def step_dev(call):
+        if flush is not None:
+            flush.zero_()
+        st = fn_dev(x_d.data_ptr(), shape_d.data_ptr(), z_d.data_ptr(), num, SEED, call, obs0, stream)
+        if st:
+            _lib.check(st)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing ----------------------------------------------------
+    for w in range(args.warmup):
+        step_dev(1000 + w)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = L.bl_kernel_launches()
+    t_wall0 = time.time()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kern_ms = 0.0
+    ev[0].record()
+    for k in range(args.steps):
+        if flush is not None:
+            flush.zero_()
+            e_a = torch.cuda.Event(enable_timing=True); e_a.record()
+        st = fn_dev(x_d.data_ptr(), shape_d.data_ptr(), z_d.data_ptr(), num, SEED, k, obs0, stream)
+        if st:
+            _lib.check(st)
+        ev[k + 1].record()
+        if flush is not None:
+            ev[k + 1].synchronize()
+            kern_ms += e_a.elapsed_time(ev[k + 1])
+    barrier()
+    t_wall1 = time.time()
+    launches = L.bl_kernel_launches() - launches0
+    total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
+    if flush is None:
+        kern_ms = ev[0].elapsed_time(ev[-1])
+    kern_ms = max_over_ranks(kern_ms) / args.steps       # dominant kernel, per launch
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    value = world * num * args.steps / (total_ms * 1e-3)
+    mean_omega = float(x_d[: 1 << 20].mean().item())
+
+    # ---- end to end through the reference-facing C ABI, pinned host buffers ------------
+    e2e = None
+    if not args.no_e2e:
+        shape_p = torch.from_numpy(shape_h).pin_memory()
+        z_p = torch.from_numpy(z_h).pin_memory()
+        x_p = torch.empty(num, dtype=torch.float64).pin_memory()
+        import ctypes as C
+        fn_host = L.bl_rpg_hybrid_seeded if wl == "hybrid" else L.bl_rpg_devroye_seeded
+        e_steps = max(2, min(args.steps, 3))
+        for w in range(2):
+            _lib.check(fn_host(x_p.data_ptr(), shape_p.data_ptr(), z_p.data_ptr(), num, SEED, 2000 + w, obs0))
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e_steps):
+            _lib.check(fn_host(x_p.data_ptr(), shape_p.data_ptr(), z_p.data_ptr(), num, SEED, k, obs0))
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        # the host copy must equal the device-resident result of the same stream identity
+        step_dev(0)
+        torch.cuda.synchronize()
+        fn_host(x_p.data_ptr(), shape_p.data_ptr(), z_p.data_ptr(), num, SEED, 0, obs0)
+        same = bool(torch.equal(x_p[: 1 << 20], x_d[: 1 << 20].cpu()))
+        e2e = {"value": world * num * e_steps / dt, "unit": "draws/s",
+               "h2d_bytes_per_step": int(world * num * (BYTES_PER_DRAW[wl] - 8)),
+               "d2h_bytes_per_step": int(world * num * 8), "steps": e_steps,
+               "api": "rpg_hybrid C ABI, host pointers (pinned)" if wl == "hybrid" else "rpg_devroye C ABI, host pointers (pinned)",
+               "matches_device_resident": same}
+
+    # ---- CPU baseline on rank 0, N = 1 only --------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = min(CPU_SAMPLE[wl], num)
+        time_cpu(wl, max(sample // 16, 1), cores)
+        dt, kind = time_cpu(wl, sample, cores)
+        cpu = {"value": sample / dt, "unit": "draws/s", "cores": cores, "kind": kind,
+               "sample": f"first {sample} draws of the workload, all {cores} host threads, {dt:.2f} s wall"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        achieved = num * BYTES_PER_DRAW[wl] / (kern_ms * 1e-3) / 1e9
+        fp64_peak = 37.0   # TFLOP/s, B200 vector FP64 (not in MEASURED_PEAKS.json)
+        tf = num * KFLOP_PER_DRAW[wl] * 1e3 / (kern_ms * 1e-3) / 1e12
+        out = {
+            "metric": "pg_draws_per_sec", "value": value, "unit": "draws/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None,
+                         "peak_source": "measured" if peaks else "fallback",
+                         "kernel": "k_rpg_philox<hybrid>" if wl == "hybrid" else "k_rpg_philox<devroye>",
+                         "kernel_ms": kern_ms,
+                         "note": "the sampler is bound by the FP64/ALU pipes, not HBM (SURVEY.md 8d); see roofline_compute"},
+            "roofline_compute": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s(fp64-equivalent model)",
+                                 "frac": tf / fp64_peak, "kflop_per_draw": KFLOP_PER_DRAW[wl]},
+            "cpu_baseline": cpu, "mean_omega_first_1M": mean_omega,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,162 @@
+/*
+ * bayeslogit_b200.h -- C ABI of the B200-native Polya-Gamma engine.
+ *
+ * Part 1 is the DROP-IN BOUNDARY: exactly the symbols of the reference's
+ * Code/C/LogitWrapper.h:23-64, the functions R reaches through
+ * .C("rpg_devroye", ...), .C("gibbs", ...) etc. (Code/R/LogitWrapper.R:29,49,69,92,
+ * 118,177,229,277,342,395).  Same names, same argument meaning, all arguments
+ * pointers into caller-owned HOST memory, void return; errors are reported the
+ * way the reference reports them (a message on the console, outputs left as
+ * they were, LogitWrapper.cpp:226-229) and can additionally be read back with
+ * bl_last_error().
+ *
+ * Part 2 are engine extensions (prefix bl_): seeding, device selection,
+ * device-resident and streaming variants, and the injected-variate ("tape")
+ * variants used for tier-1 parity.  There is NO CPU fallback anywhere in this
+ * library: without a usable sm_100 device every entry point fails loudly.
+ *
+ * All matrices are column-major (R layout), see INTEGRATION.md.
+ */
+#ifndef BAYESLOGIT_B200_H
+#define BAYESLOGIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------ */
+/* Part 1 -- reference entry points (Code/C/LogitWrapper.h)                  */
+/* ------------------------------------------------------------------------ */
+
+/* LogitWrapper.h:27 / LogitWrapper.cpp:39-62.  x[i] = n[i] != 0 ? truncated
+ * sum-of-gammas PG(n[i], z[i]) with *trunc terms : 0. */
+void rpg_gamma(double *x, double *n, double *z, int *num, int *trunc);
+
+/* LogitWrapper.h:29 / LogitWrapper.cpp:66-85.  x[i] = n[i] != 0 ? sum of n[i]
+ * Devroye PG(1, z[i]) draws : 0. */
+void rpg_devroye(double *x, int *n, double *z, int *num);
+
+/* LogitWrapper.h:31 / LogitWrapper.cpp:87-106.  Alternate sampler, h >= 1. */
+void rpg_alt(double *x, double *h, double *z, int *num);
+
+/* LogitWrapper.h:33 / LogitWrapper.cpp:108-127.  Saddle-point sampler; iter[i]
+ * receives the proposal count (left untouched where h[i] == 0, as there). */
+void rpg_sp(double *x, double *h, double *z, int *num, int *iter);
+
+/* LogitWrapper.h:35 / LogitWrapper.cpp:129-167.  Regime dispatch on h[i]:
+ * >170 normal approximation, >13 saddle point, ==1 or ==2 Devroye, >1 alternate,
+ * >0 sum of gammas (200 terms), else 0. */
+void rpg_hybrid(double *x, double *h, double *z, int *num);
+
+/* LogitWrapper.h:39-43 / LogitWrapper.cpp:176-234.  Binomial-logit Gibbs.
+ * wp: N x samp, betap: P x samp, yp: N (proportions), tXp: P x N, np: N,
+ * m0p: P, P0p: P x P (precision). */
+void gibbs(double *wp, double *betap, double *yp, double *tXp, double *np,
+           double *m0p, double *P0p, int *N, int *P, int *samp, int *burn);
+
+/* LogitWrapper.h:45-48 / LogitWrapper.cpp:238-273.  Posterior mode by EM. */
+void EM(double *betap, double *yp, double *tXp, double *np, int *Np, int *Pp,
+        double *tolp, int *max_iterp);
+
+/* LogitWrapper.h:50-51 / LogitWrapper.cpp:279-310.  Merge duplicate rows. */
+void combine(double *yp, double *tXp, double *np, int *N, int *P);
+
+/* LogitWrapper.h:55-59 / LogitWrapper.cpp:316-374.  Multinomial-logit Gibbs.
+ * wp: N x (J-1) x samp, betap: P x (J-1) x samp, typ: (J-1) x N, tXp: P x N,
+ * m0p: P x (J-1), P0p: P x P x (J-1). */
+void mult_gibbs(double *wp, double *betap, double *typ, double *tXp, double *np,
+                double *m0p, double *P0p, int *N, int *P, int *J, int *sampp, int *burnp);
+
+/* LogitWrapper.h:61-62 / LogitWrapper.cpp:376-409. */
+void mult_combine(double *typ, double *tXp, double *np, int *N, int *P, int *J);
+
+/* ------------------------------------------------------------------------ */
+/* Part 2 -- engine extensions                                               */
+/* ------------------------------------------------------------------------ */
+
+/* Status: 0 = ok, nonzero = error (message through bl_last_error()). */
+int bl_version(void);
+const char *bl_last_error(void);
+void bl_clear_error(void);
+
+/* Select the CUDA device of this process (one process per GPU). */
+int bl_set_device(int device);
+int bl_get_device(void);
+
+/* Seed of the Philox stream contract.  The reference has no seed argument: its
+ * draws come from R's global generator (GetRNGstate/PutRNGstate,
+ * LogitWrapper.cpp:44-46).  Here the drop-in entry points use (seed, call
+ * counter); bl_set_seed() also resets the call counter to 0 so a sequence of
+ * calls is reproducible. */
+void bl_set_seed(uint64_t seed);
+uint64_t bl_get_seed(void);
+uint32_t bl_get_call_counter(void);
+
+/* Device-resident batch draws: all pointers are DEVICE pointers; the work is
+ * enqueued on `stream` (a cudaStream_t, NULL = legacy default stream) and the
+ * call returns without synchronising.  Observation i uses the Philox stream of
+ * global index obs0 + i, so shards of one logical batch can be drawn on
+ * different GPUs with results independent of the sharding. */
+int bl_rpg_devroye_dev(double *x, const int *n, const double *z, int64_t num,
+                       uint64_t seed, uint32_t call_id, uint64_t obs0, void *stream);
+int bl_rpg_gamma_dev(double *x, const double *n, const double *z, int64_t num, int trunc,
+                     uint64_t seed, uint32_t call_id, uint64_t obs0, void *stream);
+int bl_rpg_alt_dev(double *x, const double *h, const double *z, int64_t num,
+                   uint64_t seed, uint32_t call_id, uint64_t obs0, void *stream);
+int bl_rpg_sp_dev(double *x, const double *h, const double *z, int64_t num, int *iter,
+                  uint64_t seed, uint32_t call_id, uint64_t obs0, void *stream);
+int bl_rpg_hybrid_dev(double *x, const double *h, const double *z, int64_t num,
+                      uint64_t seed, uint32_t call_id, uint64_t obs0, void *stream);
+
+/* Host-pointer draws with an explicit stream identity (what the drop-in entry
+ * points call with the global seed / call counter). */
+int bl_rpg_devroye_seeded(double *x, const int *n, const double *z, int64_t num,
+                          uint64_t seed, uint32_t call_id, uint64_t obs0);
+int bl_rpg_gamma_seeded(double *x, const double *n, const double *z, int64_t num, int trunc,
+                        uint64_t seed, uint32_t call_id, uint64_t obs0);
+int bl_rpg_alt_seeded(double *x, const double *h, const double *z, int64_t num,
+                      uint64_t seed, uint32_t call_id, uint64_t obs0);
+int bl_rpg_sp_seeded(double *x, const double *h, const double *z, int64_t num, int *iter,
+                     uint64_t seed, uint32_t call_id, uint64_t obs0);
+int bl_rpg_hybrid_seeded(double *x, const double *h, const double *z, int64_t num,
+                         uint64_t seed, uint32_t call_id, uint64_t obs0);
+
+/* Injected-variate ("tape") variants, host pointers.  Observation i consumes
+ * uniforms tu[i*lu ..], exponentials te[i*le ..], normals tn[i*ln ..] and gamma
+ * variates tg[i*lg ..] in the reference's statement order.
+ * trace (may be NULL) receives 6 ints per observation: #U, #E, #N, #G consumed,
+ * a tape-exhausted flag, and an auxiliary count (saddle-point proposals).
+ * Draws whose tape ran dry are returned as NaN. */
+#define BL_TRACE_W 6
+typedef struct bl_tape {
+    const double *tu, *te, *tn, *tg;
+    int32_t lu, le, ln, lg;
+} bl_tape;
+
+int bl_rpg_devroye_tape(double *x, const int *n, const double *z, int64_t num,
+                        const bl_tape *tape, int *trace);
+int bl_rpg_gamma_tape(double *x, const double *n, const double *z, int64_t num, int trunc,
+                      const bl_tape *tape, int *trace);
+int bl_rpg_alt_tape(double *x, const double *h, const double *z, int64_t num,
+                    const bl_tape *tape, int *trace);
+int bl_rpg_sp_tape(double *x, const double *h, const double *z, int64_t num, int *iter,
+                   const bl_tape *tape, int *trace);
+int bl_rpg_hybrid_tape(double *x, const double *h, const double *z, int64_t num,
+                       const bl_tape *tape, int *trace);
+
+/* Component probes for parity tests (host pointers, elementwise). */
+int bl_probe_pg_moments(double *m1, double *m2, const double *b, const double *z, int64_t num);
+int bl_probe_v_eval(double *v, const double *y, int64_t num);
+int bl_probe_specfun(double *out, int which, const double *a, const double *b, const double *c,
+                     int64_t num);
+int bl_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2);
+
+/* Number of kernels this library has launched since load (bench accounting). */
+uint64_t bl_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,1 +1,438 @@
-/* oracle/gibbs_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.  (filled in below) */
+/*
+ * oracle/gibbs_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C restatement of the reference's Gibbs sweeps that consume PG draws:
+ *   binary/binomial logit   /root/reference/Code/C/Logit.hpp:174-183, 283-481
+ *                           (driver: LogitWrapper.cpp:176-234)
+ *   multinomial logit       /root/reference/Code/C/MultLogit.hpp:214-219, 234-372,
+ *                           include/Normal.hpp:98-131 (driver: LogitWrapper.cpp:316-374)
+ *   negative binomial       /root/reference/Code/R/NBPG-logmean.R:13-113 (beta | omega, d fixed)
+ * The reference's own model layer cannot be compiled here (it needs the absent
+ * jwindle/Matrix library + BLAS/LAPACK), so dense algebra is
+ * written as plain loops with the LAPACK semantics the reference calls
+ * (dpotrf/dtrsm/dposv) and omega is drawn with the port sampler of pg_oracle.c.
+ * PARITY STATUS: "parity unpinned" for this layer -- no reference output exists
+ * to pin it; it is validated against the closed-form posterior in
+ * tests/test_gibbs_oracle.py.
+ *
+ * Stream contract for the sweep: iteration t (0-based, burn-in
+ * included) draws omega_i from the Philox stream (seed, obs i, call t) -- for
+ * mlogit call t*(J-1)+j -- and the beta draw of that iteration from the stream
+ * (seed, obs 2^64-1, same call), consuming variates in the reference's statement
+ * order (Appendix A.6 of SURVEY.md).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "batch.h"
+#include "l0.h"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+double pgo_dev_draw(pgo_src *s, int n, double z);   /* pg_oracle.c */
+double pgo_hybrid_draw(pgo_src *s, double b, double z);
+
+#define BETA_OBS 0xFFFFFFFFFFFFFFFFull
+
+/* ---- dense helpers (column-major, leading dimension = rows) -------------------- */
+
+/* Upper Cholesky A = U'U (LAPACK dpotrf 'U'); A is overwritten, strictly lower part zeroed.
+ * Returns 0, or k+1 if the leading minor of order k+1 is not positive definite. */
+static int chol_upper(double *A, int P)
+{
+    for (int j = 0; j < P; ++j) {
+        double d = A[j + P * j];
+        for (int k = 0; k < j; ++k) d -= A[k + P * j] * A[k + P * j];
+        if (!(d > 0.0)) return j + 1;
+        d = sqrt(d);
+        A[j + P * j] = d;
+        for (int i = j + 1; i < P; ++i) {
+            double s = A[j + P * i];
+            for (int k = 0; k < j; ++k) s -= A[k + P * j] * A[k + P * i];
+            A[j + P * i] = s / d;
+        }
+    }
+    for (int j = 0; j < P; ++j)
+        for (int i = j + 1; i < P; ++i) A[i + P * j] = 0.0;
+    return 0;
+}
+
+/* Lower Cholesky A = LL' (dpotrf 'L'). */
+static int chol_lower(double *A, int P)
+{
+    for (int j = 0; j < P; ++j) {
+        double d = A[j + P * j];
+        for (int k = 0; k < j; ++k) d -= A[j + P * k] * A[j + P * k];
+        if (!(d > 0.0)) return j + 1;
+        d = sqrt(d);
+        A[j + P * j] = d;
+        for (int i = j + 1; i < P; ++i) {
+            double s = A[i + P * j];
+            for (int k = 0; k < j; ++k) s -= A[i + P * k] * A[j + P * k];
+            A[i + P * j] = s / d;
+        }
+    }
+    for (int j = 0; j < P; ++j)
+        for (int i = 0; i < j; ++i) A[i + P * j] = 0.0;
+    return 0;
+}
+
+/* x <- U^{-T} x  (trsm 'U','L','T') */
+static void solve_Ut(const double *U, double *x, int P)
+{
+    for (int i = 0; i < P; ++i) {
+        double s = x[i];
+        for (int k = 0; k < i; ++k) s -= U[k + P * i] * x[k];
+        x[i] = s / U[i + P * i];
+    }
+}
+
+/* x <- U^{-1} x  (trsm 'U','L','N') */
+static void solve_U(const double *U, double *x, int P)
+{
+    for (int i = P - 1; i >= 0; --i) {
+        double s = x[i];
+        for (int k = i + 1; k < P; ++k) s -= U[i + P * k] * x[k];
+        x[i] = s / U[i + P * i];
+    }
+}
+
+/* x <- L^{-1} x  (trsm 'L','L','N') */
+static void solve_L(const double *L, double *x, int P)
+{
+    for (int i = 0; i < P; ++i) {
+        double s = x[i];
+        for (int k = 0; k < i; ++k) s -= L[i + P * k] * x[k];
+        x[i] = s / L[i + P * i];
+    }
+}
+
+/* PP = P0 + sum_i w_i x_i x_i'  (Logit.hpp:293-301: scale columns by sqrt(w), syrk) */
+static void weighted_gram(double *PP, const double *P0, const double *tX, const double *w,
+                          int N, int P, int nthreads)
+{
+    memcpy(PP, P0, sizeof(double) * P * P);
+#pragma omp parallel num_threads(nthreads)
+    {
+        double *acc = (double *)calloc((size_t)P * P, sizeof(double));
+        double *col = (double *)malloc(sizeof(double) * P);
+#pragma omp for schedule(static)
+        for (int i = 0; i < N; ++i) {
+            double rt = sqrt(w[i]);
+            for (int a = 0; a < P; ++a) col[a] = tX[a + (size_t)P * i] * rt;
+            for (int b = 0; b < P; ++b)
+                for (int a = 0; a <= b; ++a) acc[a + P * b] += col[a] * col[b];
+        }
+#pragma omp critical
+        for (int b = 0; b < P; ++b)
+            for (int a = 0; a <= b; ++a) PP[a + P * b] += acc[a + P * b];
+        free(acc);
+        free(col);
+    }
+    for (int b = 0; b < P; ++b)
+        for (int a = 0; a < b; ++a) PP[b + P * a] = PP[a + P * b];
+}
+
+/* psi = X beta  (gemm(psi, tX, beta, 'T'), Logit.hpp:421,431) */
+static void xbeta(double *psi, const double *tX, const double *beta, int N, int P, int nthreads)
+{
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int i = 0; i < N; ++i) {
+        double s = 0.0;
+        for (int a = 0; a < P; ++a) s += tX[a + (size_t)P * i] * beta[a];
+        psi[i] = s;
+    }
+}
+
+/* Unconstrained draw beta ~ N(PP^{-1} bP, PP^{-1}).  Logit.hpp:291-320 */
+static int draw_beta_plain(double *beta, double *PP, const double *bP, int P, pgo_src *s)
+{
+    if (chol_upper(PP, P)) return 1;
+    double *mP = (double *)malloc(sizeof(double) * P);
+    for (int i = 0; i < P; ++i) beta[i] = 1.0 * pgo_norm(s);
+    memcpy(mP, bP, sizeof(double) * P);
+    solve_Ut(PP, mP, P);
+    solve_U(PP, mP, P);
+    solve_U(PP, beta, P);
+    for (int i = 0; i < P; ++i) beta[i] += mP[i];
+    free(mP);
+    return 0;
+}
+
+/* Constrained coordinate-wise draw, beta_j >= 0 for j < P-1 (the variant the
+ * reference actually calls, Logit.hpp:322-400 via :429). */
+static int draw_beta_constrained(double *beta, double *PP, const double *bP, const double *beta_prev,
+                                 int P, pgo_src *s)
+{
+    if (chol_upper(PP, P)) return 1;
+    double *S = (double *)calloc((size_t)P * P, sizeof(double));
+    double *mP = (double *)malloc(sizeof(double) * P);
+    double *z = (double *)malloc(sizeof(double) * P);
+    unsigned *is = (unsigned *)malloc(sizeof(unsigned) * P);
+    for (int j = 0; j < P; ++j) {
+        S[j + P * j] = 1.0;
+        solve_Ut(PP, S + (size_t)P * j, P);
+        solve_U(PP, S + (size_t)P * j, P);
+    }
+    int bad = chol_lower(S, P);
+    if (!bad) {
+        const double *L = S;
+        memcpy(mP, bP, sizeof(double) * P);
+        solve_Ut(PP, mP, P);
+        solve_U(PP, mP, P);
+        for (int i = 0; i < P; ++i) {
+            z[i] = beta_prev[i] - mP[i];
+            beta[i] = beta_prev[i];
+        }
+        solve_L(L, z, P);
+        for (int i = 0; i < P; ++i) is[i] = (unsigned)i;
+        for (int k = 0; k < P; ++k) {
+            for (int i = 0; i < P - 1; ++i) {
+                double f = (double)i + ((double)P - (double)i) * pgo_unif(s);   /* r.flat(i, P) */
+                unsigned t = (unsigned)f;
+                if (t > (unsigned)(P - 1)) t = (unsigned)(P - 1);
+                unsigned tmp = is[i]; is[i] = is[t]; is[t] = tmp;
+            }
+            for (int i = 0; i < P; ++i) {
+                unsigned c = is[i];
+                double cmin = -INFINITY, cmax = INFINITY;
+                double z1 = z[c];
+                for (unsigned j = c; j + 1 < (unsigned)P; ++j) {
+                    double l1 = L[j + (size_t)P * c];
+                    double c1 = z1 - beta[j] / l1;
+                    if (l1 > 0.0 && c1 > cmin) cmin = c1;
+                    else if (l1 < 0.0 && c1 < cmax) cmax = c1;
+                }
+                double z2 = pgo_tnorm(s, cmin, cmax, 0.0, 1.0);
+                z[c] = z2;
+                for (unsigned j = c; j < (unsigned)P; ++j) beta[j] += L[j + (size_t)P * c] * (z2 - z1);
+            }
+        }
+    }
+    free(S); free(mP); free(z); free(is);
+    return bad;
+}
+
+/* Logit::gibbs with Logit::gibbs_block's slot semantics (Logit.hpp:402-481):
+ * burn-in overwrites slot 0; sampling restarts from slot 0 and writes iteration m
+ * into slot m-1.  w: N x samp, beta: P x samp, both zero-initialised by the
+ * caller like Matrix::resize does.  Returns 0 on success. */
+int pgb_logit_gibbs(double *w, double *beta, const double *y, const double *tX, const double *n,
+                    const double *m0, const double *P0, int N, int P, int samp, int burn,
+                    uint64_t seed, int constrained, int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+    double *bP = (double *)calloc(P, sizeof(double));
+    double *PP = (double *)malloc(sizeof(double) * P * P);
+    double *psi = (double *)malloc(sizeof(double) * N);
+    double *bnew = (double *)malloc(sizeof(double) * P);
+    /* set_prior: b0 = P0 m0; set_bP: bP = b0 + tX (n o (y - 1/2)).  Logit.hpp:174-190 */
+    for (int a = 0; a < P; ++a)
+        for (int b = 0; b < P; ++b) bP[a] += P0[a + P * b] * m0[b];
+    for (int i = 0; i < N; ++i) {
+        double alpha = n[i] * (y[i] - 0.5);
+        for (int a = 0; a < P; ++a) bP[a] += tX[a + (size_t)P * i] * alpha;
+    }
+    memset(w, 0, sizeof(double) * (size_t)N * samp);
+    memset(beta, 0, sizeof(double) * (size_t)P * samp);
+    int status = 0;
+    uint32_t t = 0;
+    for (int phase = 0; phase < 2 && !status; ++phase) {
+        int iters = phase == 0 ? burn : samp;
+        double *bcur = beta, *bprev = beta, *wcur = w;
+        xbeta(psi, tX, bcur, N, P, nthreads);
+        for (int m = 1; m <= iters && !status; ++m, ++t) {
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
+            for (int i = 0; i < N; ++i) {
+                pgo_src s;
+                pgo_src_philox(&s, seed, (uint64_t)i, t);
+                wcur[i] = pgo_dev_draw(&s, (int)n[i], psi[i]);
+            }
+            weighted_gram(PP, P0, tX, wcur, N, P, nthreads);
+            pgo_src sb;
+            pgo_src_philox(&sb, seed, BETA_OBS, t);
+            status = constrained ? draw_beta_constrained(bnew, PP, bP, bprev, P, &sb)
+                                 : draw_beta_plain(bnew, PP, bP, P, &sb);
+            memcpy(bcur, bnew, sizeof(double) * P);
+            xbeta(psi, tX, bcur, N, P, nthreads);
+            if (phase == 1) {   /* period 1: advance the slot after every iteration */
+                bprev = bcur;
+                if (m < iters) { bcur += P; wcur += N; }
+            }
+        }
+    }
+    free(bP); free(PP); free(psi); free(bnew);
+    return status;
+}
+
+/* ---- multinomial logit ----------------------------------------------------------- */
+
+/* beta ~ N(P1^{-1} b1, P1^{-1}) the way Normal::set_from_likelihood + draw do it:
+ * V = P1^{-1} (symsolve on I), mean = V b1, lower = chol(V,'L'), draw = mean + lower*N.
+ * include/Normal.hpp:98-131 */
+static int draw_mvn_from_likelihood(double *beta, double *P1, const double *b1, int P, pgo_src *s)
+{
+    if (chol_upper(P1, P)) return 1;
+    double *V = (double *)calloc((size_t)P * P, sizeof(double));
+    double *e = (double *)malloc(sizeof(double) * P);
+    for (int j = 0; j < P; ++j) {
+        V[j + P * j] = 1.0;
+        solve_Ut(P1, V + (size_t)P * j, P);
+        solve_U(P1, V + (size_t)P * j, P);
+    }
+    for (int a = 0; a < P; ++a) {
+        double m = 0.0;
+        for (int b = 0; b < P; ++b) m += V[a + P * b] * b1[b];
+        beta[a] = m;
+    }
+    int bad = chol_lower(V, P);
+    if (!bad) {
+        for (int a = 0; a < P; ++a) e[a] = pgo_norm(s);
+        for (int a = 0; a < P; ++a) {
+            double v = 0.0;
+            for (int b = 0; b <= a; ++b) v += V[a + P * b] * e[b];
+            beta[a] += v;
+        }
+    }
+    free(V); free(e);
+    return bad;
+}
+
+/* MultLogit::gibbs (MultLogit.hpp:261-372).  w: N x (J-1) x samp, beta: P x (J-1) x samp,
+ * ty: (J-1) x N, m0: P x (J-1), P0: P x P x (J-1).  burn+1 iterations go into slice 0,
+ * then samp-1 more; slice m starts from slice m-1's beta only through XB. */
+int pgb_mlogit_gibbs(double *w, double *beta, const double *ty, const double *tX, const double *n,
+                     const double *m0, const double *P0, int N, int P, int J, int samp, int burn,
+                     uint64_t seed, int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+    int U = J - 1;
+    double *Z = (double *)calloc((size_t)P * U, sizeof(double));
+    double *b0 = (double *)calloc((size_t)P * U, sizeof(double));
+    double *XB = (double *)calloc((size_t)N * J, sizeof(double));     /* last column stays 0 */
+    double *XBno = (double *)malloc(sizeof(double) * (size_t)N * U);
+    double *cj = (double *)malloc(sizeof(double) * N);
+    double *eta = (double *)malloc(sizeof(double) * N);
+    double *P1 = (double *)malloc(sizeof(double) * P * P);
+    double *b1 = (double *)malloc(sizeof(double) * P);
+    /* Z = tX tkappa', kappa = n (y - 1/2).  MultLogit.hpp:214-219 */
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < U; ++j) {
+            double k = n[i] * (ty[j + (size_t)U * i] - 0.5);
+            for (int a = 0; a < P; ++a) Z[a + (size_t)P * j] += tX[a + (size_t)P * i] * k;
+        }
+    for (int j = 0; j < U; ++j)
+        for (int a = 0; a < P; ++a)
+            for (int b = 0; b < P; ++b)
+                b0[a + (size_t)P * j] += P0[a + P * b + (size_t)P * P * j] * m0[b + (size_t)P * j];
+    memset(w, 0, sizeof(double) * (size_t)N * U * samp);
+    memset(beta, 0, sizeof(double) * (size_t)P * U * samp);
+    int status = 0;
+    int total = burn + samp;      /* burn+1 into slice 0, samp-1 after */
+    for (int t = 0; t < total && !status; ++t) {
+        int slice = t <= burn ? 0 : t - burn;
+        double *wS = w + (size_t)N * U * slice;
+        double *bS = beta + (size_t)P * U * slice;
+        /* XB_no_j <- columns 1..J-1 of XB */
+        for (int j = 0; j < U; ++j) memcpy(XBno + (size_t)N * j, XB + (size_t)N * (j + 1), sizeof(double) * N);
+        for (int j = 0; j < U && !status; ++j) {
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+            for (int i = 0; i < N; ++i) {
+                double A = 0.0;
+                for (int k = 0; k < U; ++k) A += exp(XBno[i + (size_t)N * k]);
+                cj[i] = log(A);
+                eta[i] = XB[i + (size_t)N * j] - cj[i];
+            }
+            uint32_t call = (uint32_t)t * (uint32_t)U + (uint32_t)j;
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
+            for (int i = 0; i < N; ++i) {
+                pgo_src s;
+                pgo_src_philox(&s, seed, (uint64_t)i, call);
+                wS[i + (size_t)N * j] = pgo_dev_draw(&s, (int)n[i], eta[i]);
+            }
+            /* P1 = tX Om X + P0_j ; b1 = Z_j + tX Om c_j + b0_j.  MultLogit.hpp:246-253 */
+            for (int a = 0; a < P * P; ++a) P1[a] = 0.0;
+            for (int a = 0; a < P; ++a) b1[a] = 0.0;
+            for (int i = 0; i < N; ++i) {
+                double wi = wS[i + (size_t)N * j];
+                const double *xi = tX + (size_t)P * i;
+                for (int b = 0; b < P; ++b) {
+                    double xw = xi[b] * wi;
+                    b1[b] += xw * cj[i];
+                    for (int a = 0; a <= b; ++a) P1[a + P * b] += xi[a] * xw;
+                }
+            }
+            for (int b = 0; b < P; ++b)
+                for (int a = 0; a <= b; ++a) {
+                    P1[a + P * b] += P0[a + P * b + (size_t)P * P * j];
+                    P1[b + P * a] = P1[a + P * b];
+                }
+            for (int a = 0; a < P; ++a) b1[a] = Z[a + (size_t)P * j] + b1[a] + b0[a + (size_t)P * j];
+            pgo_src sb;
+            pgo_src_philox(&sb, seed, BETA_OBS, call);
+            status = draw_mvn_from_likelihood(bS + (size_t)P * j, P1, b1, P, &sb);
+            xbeta(XB + (size_t)N * j, tX, bS + (size_t)P * j, N, P, nthreads);
+            if (j < U - 1) memcpy(XBno + (size_t)N * j, XB + (size_t)N * j, sizeof(double) * N);
+        }
+    }
+    free(Z); free(b0); free(XB); free(XBno); free(cj); free(eta); free(P1); free(b1);
+    return status;
+}
+
+/* ---- negative binomial, d fixed ---------------------------------------------------- */
+
+/* NB.PG.gibbs with the dispersion d held fixed (NBPG-logmean.R:77-106 without the
+ * draw.df step): psi = X beta - log d; w = rpg(N, y+d, psi) (hybrid); kappa = (y-d)/2;
+ * beta ~ N(PN^{-1}(X'(kappa + w log d) + P0 b0), PN^{-1}), PN = X'OmX + P0 (:13-34).
+ * beta: P x samp (all iterations kept, no burn-in split), w_last: N. */
+int pgb_nb_gibbs(double *w_last, double *beta, const double *y, const double *tX, double d,
+                 const double *m0, const double *P0, int N, int P, int samp,
+                 uint64_t seed, int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+    double *b0 = (double *)calloc(P, sizeof(double));
+    double *PP = (double *)malloc(sizeof(double) * P * P);
+    double *bP = (double *)malloc(sizeof(double) * P);
+    double *psi = (double *)malloc(sizeof(double) * N);
+    double *bcur = (double *)calloc(P, sizeof(double));
+    double ld = log(d);
+    for (int a = 0; a < P; ++a)
+        for (int b = 0; b < P; ++b) b0[a] += P0[a + P * b] * m0[b];
+    int status = 0;
+    for (int t = 0; t < samp && !status; ++t) {
+        xbeta(psi, tX, bcur, N, P, nthreads);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
+        for (int i = 0; i < N; ++i) {
+            pgo_src s;
+            pgo_src_philox(&s, seed, (uint64_t)i, (uint32_t)t);
+            w_last[i] = pgo_hybrid_draw(&s, y[i] + d, psi[i] - ld);
+        }
+        weighted_gram(PP, P0, tX, w_last, N, P, nthreads);
+        memcpy(bP, b0, sizeof(double) * P);
+        for (int i = 0; i < N; ++i) {
+            double k = 0.5 * (y[i] - d) + w_last[i] * ld;
+            for (int a = 0; a < P; ++a) bP[a] += tX[a + (size_t)P * i] * k;
+        }
+        pgo_src sb;
+        pgo_src_philox(&sb, seed, BETA_OBS, (uint32_t)t);
+        status = draw_beta_plain(bcur, PP, bP, P, &sb);
+        memcpy(beta + (size_t)P * t, bcur, sizeof(double) * P);
+    }
+    free(b0); free(PP); free(bP); free(psi); free(bcur);
+    return status;
+}

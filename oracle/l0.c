@@ -291,6 +291,22 @@ double pgo_p_norm(double x, int use_log)
     return -0.5 * x2 - log(-x) - 0.5 * log(2.0 * M_PI) + log(sum);
 }
 
+/* log of x^a e^-x / Gamma(a).  For a >= 10 the three ~a-sized terms of the direct
+ * form cancel to O(1) and lose ~log10(a) digits, so the prefix is rearranged
+ * around Stirling's series: -a (mu - log1p mu) - S(a) + log sqrt(a/2pi),
+ * mu = (x-a)/a, S(a) = 1/(12a) - 1/(360a^3) + ... (Temme 1979; the same
+ * rearrangement Boost.Math calls regularised_gamma_prefix). */
+static double gamma_log_prefix(double a, double x)
+{
+    if (a < 10.0) return a * log(x) - x - lgamma(a);
+    double mu = (x - a) / a;
+    double phi = mu - log1p(mu);
+    double ia = 1.0 / a, ia2 = ia * ia;
+    double S = ia * (1.0 / 12 - ia2 * (1.0 / 360 - ia2 * (1.0 / 1260 - ia2 * (1.0 / 1680
+             - ia2 * (1.0 / 1188 - ia2 * (691.0 / 360360 - ia2 * (1.0 / 156)))))));
+    return -a * phi - S + 0.5 * log(a / (2.0 * 3.14159265358979323846));
+}
+
 /* Regularised lower incomplete gamma P(a, x) (Numerical-Recipes-style split:
  * power series for x < a+1, modified-Lentz continued fraction for Q otherwise,
  * returning 1-Q).  Callers always use `1.0 - P` (PolyaGammaAlt.cpp:66,73;
@@ -299,7 +315,7 @@ static double pgamma_lower(double a, double x)
 {
     if (x <= 0.0) return 0.0;
     if (isinf(x)) return 1.0;
-    double lpre = a * log(x) - x - lgamma(a);
+    double lpre = gamma_log_prefix(a, x);
     if (x < a + 1.0) {
         double ap = a, del = 1.0 / a, sum = del;
         for (int n = 0; n < 2000; ++n) {
