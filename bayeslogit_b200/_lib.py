@@ -61,6 +61,8 @@ def lib():
     L.bl_kernel_launches.restype = u64
     tail = [u64, u32, u64]
     L.bl_rpg_devroye_dev.argtypes = [vp, vp, vp, i64, *tail, vp]
+    L.bl_rpg_devroye_plain_dev.argtypes = [vp, vp, vp, i64, *tail, vp]
+    L.bl_rpg_devroye_loop_dev.argtypes = [vp, vp, vp, i64, *tail, vp]
     L.bl_rpg_gamma_dev.argtypes = [vp, vp, vp, i64, ci, *tail, vp]
     L.bl_rpg_alt_dev.argtypes = [vp, vp, vp, i64, *tail, vp]
     L.bl_rpg_sp_dev.argtypes = [vp, vp, vp, i64, vp, *tail, vp]
@@ -72,6 +74,7 @@ def lib():
     L.bl_rpg_hybrid_seeded.argtypes = [vp, vp, vp, i64, *tail]
     tp = C.POINTER(Tape)
     L.bl_rpg_devroye_tape.argtypes = [vp, vp, vp, i64, tp, vp]
+    L.bl_rpg_devroye_plain_tape.argtypes = [vp, vp, vp, i64, tp, vp]
     L.bl_rpg_gamma_tape.argtypes = [vp, vp, vp, i64, ci, tp, vp]
     L.bl_rpg_alt_tape.argtypes = [vp, vp, vp, i64, tp, vp]
     L.bl_rpg_sp_tape.argtypes = [vp, vp, vp, i64, vp, tp, vp]

@@ -115,6 +115,7 @@ _SEEDED = {"devroye": ("bl_rpg_devroye_seeded", np.int32), "gamma": ("bl_rpg_gam
            "alt": ("bl_rpg_alt_seeded", np.float64), "sp": ("bl_rpg_sp_seeded", np.float64),
            "hybrid": ("bl_rpg_hybrid_seeded", np.float64)}
 _TAPE = {k: v[0].replace("_seeded", "_tape") for k, v in _SEEDED.items()}
+_TAPE["devroye_plain"] = "bl_rpg_devroye_plain_tape"   # all-fp64 path without the fp32 decision filters
 
 
 def rpg_seeded(method, shape, z, seed, call_id=0, obs0=0, trunc=200):
@@ -139,7 +140,7 @@ def rpg_seeded(method, shape, z, seed, call_id=0, obs0=0, trunc=200):
 def rpg_tape(method, shape, z, tape, trunc=200, trace=True):
     """Draw from injected variate tapes (dict with optional 'u','e','n','g' [num x L] arrays)."""
     fn = _TAPE[method]
-    dt = _SEEDED[method][1]
+    dt = np.int32 if method.startswith("devroye") else np.float64
     z = np.ascontiguousarray(z, dtype=np.float64)
     shape = np.ascontiguousarray(shape, dtype=dt)
     num = z.size

@@ -114,7 +114,10 @@ int slot_reserve(Slot &s, int64_t n)
     return 0;
 }
 
-size_t shape_size(Method m) { return m == kDevroye ? sizeof(int) : sizeof(double); }
+size_t shape_size(Method m)
+{
+    return (m == kDevroye || m == kDevroyePlain || m == kDevroyeLoop) ? sizeof(int) : sizeof(double);
+}
 
 // Host-pointer batch through the chunk pipeline.
 int run_host(Method m, double *x, const void *shape, const double *z, int64_t num, int trunc,
@@ -295,6 +298,21 @@ int bl_rpg_devroye_dev(double *x, const int *n, const double *z, int64_t num, ui
                        uint32_t call_id, uint64_t obs0, void *stream)
 {
     return run_dev(kDevroye, x, n, z, num, 0, nullptr, StreamId{seed, obs0, call_id}, stream);
+}
+int bl_rpg_devroye_plain_dev(double *x, const int *n, const double *z, int64_t num, uint64_t seed,
+                             uint32_t call_id, uint64_t obs0, void *stream)
+{
+    return run_dev(kDevroyePlain, x, n, z, num, 0, nullptr, StreamId{seed, obs0, call_id}, stream);
+}
+int bl_rpg_devroye_loop_dev(double *x, const int *n, const double *z, int64_t num, uint64_t seed,
+                            uint32_t call_id, uint64_t obs0, void *stream)
+{
+    return run_dev(kDevroyeLoop, x, n, z, num, 0, nullptr, StreamId{seed, obs0, call_id}, stream);
+}
+int bl_rpg_devroye_plain_tape(double *x, const int *n, const double *z, int64_t num,
+                              const bl_tape *tape, int *trace)
+{
+    return run_tape(kDevroyePlain, x, n, z, num, 0, nullptr, tape, trace);
 }
 int bl_rpg_gamma_dev(double *x, const double *n, const double *z, int64_t num, int trunc,
                      uint64_t seed, uint32_t call_id, uint64_t obs0, void *stream)

@@ -9,7 +9,9 @@
 
 namespace bl {
 
-enum Method { kDevroye = 0, kGamma = 1, kAlt = 2, kSP = 3, kHybrid = 4 };
+// kDevroyePlain: the unfiltered all-fp64 Devroye path, kept for A/B equality tests
+// kDevroyeLoop: the filtered sampler in a plain per-lane loop (no persistent-lane refill)
+enum Method { kDevroye = 0, kGamma = 1, kAlt = 2, kSP = 3, kHybrid = 4, kDevroyePlain = 5, kDevroyeLoop = 6 };
 
 // Stream identity of a batch (see philox.cuh).
 struct StreamId {
@@ -39,6 +41,9 @@ cudaError_t launch_probe_specfun(double *out, int which, const double *a, const 
                                  const double *c, int64_t num, cudaStream_t stream);
 cudaError_t launch_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2,
                                 cudaStream_t stream);
+
+cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int64_t num,
+                                  StreamId id, cudaStream_t stream);
 
 void count_launch(int n = 1);
 

@@ -6,7 +6,7 @@
 // in, omega (8 B) out, all coalesced; the kernels are bound by the fp64/ALU
 // pipes, not by HBM (DESIGN.md "Rooflines").
 #include "engine.h"
-#include "pg_samplers.cuh"
+#include "pg_devroye_fast.cuh"
 
 namespace bl {
 
@@ -26,7 +26,10 @@ __device__ __forceinline__ double draw_one(Src &s, const void *shape, const doub
                                            int trunc, int *iter, int &aux)
 {
     aux = 0;
-    if (M == kDevroye) {
+    if (M == kDevroye || M == kDevroyeLoop) {
+        int n = ((const int *)shape)[i];
+        return n != 0 ? devroye_sum_fast(s, n, z[i]) : 0.0;
+    } else if (M == kDevroyePlain) {
         int n = ((const int *)shape)[i];
         return n != 0 ? devroye_sum(s, n, z[i]) : 0.0;
     } else if (M == kGamma) {
@@ -155,11 +158,13 @@ cudaError_t launch_rpg(Method m, double *x, const void *shape, const double *z, 
                        int trunc, int *iter, StreamId id, cudaStream_t st)
 {
     switch (m) {
-    case kDevroye: return launch_philox_m<kDevroye>(x, shape, z, num, trunc, iter, id, st);
+    case kDevroye: return launch_devroye_refill(x, (const int *)shape, z, num, id, st);
+    case kDevroyeLoop: return launch_philox_m<kDevroyeLoop>(x, shape, z, num, trunc, iter, id, st);
     case kGamma: return launch_philox_m<kGamma>(x, shape, z, num, trunc, iter, id, st);
     case kAlt: return launch_philox_m<kAlt>(x, shape, z, num, trunc, iter, id, st);
     case kSP: return launch_philox_m<kSP>(x, shape, z, num, trunc, iter, id, st);
     case kHybrid: return launch_philox_m<kHybrid>(x, shape, z, num, trunc, iter, id, st);
+    case kDevroyePlain: return launch_philox_m<kDevroyePlain>(x, shape, z, num, trunc, iter, id, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -173,6 +178,8 @@ cudaError_t launch_rpg_tape(Method m, double *x, const void *shape, const double
     case kAlt: return launch_tape_m<kAlt>(x, shape, z, num, trunc, iter, tp, trace, st);
     case kSP: return launch_tape_m<kSP>(x, shape, z, num, trunc, iter, tp, trace, st);
     case kHybrid: return launch_tape_m<kHybrid>(x, shape, z, num, trunc, iter, tp, trace, st);
+    case kDevroyePlain: return launch_tape_m<kDevroyePlain>(x, shape, z, num, trunc, iter, tp, trace, st);
+    case kDevroyeLoop: return launch_tape_m<kDevroye>(x, shape, z, num, trunc, iter, tp, trace, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -59,6 +59,48 @@ __device__ __forceinline__ double dev_right_mass(double Z)
     return 1.0 / (1.0 + qdivp);
 }
 
+// The three proposal formulas, written with explicitly rounded fp64 operations
+// (no FMA contraction) so that, given the same variates, X carries the same bits
+// as the reference's x86-64 arithmetic and as every other code path of this engine.
+//   right piece        X = t + E/fz                         PolyaGamma.cpp:171
+//   inverse chi^2 pair X = t / (1 + E1 t)^2                 PolyaGamma.cpp:98-99
+//   inverse Gaussian   X = mu + mu/2 muY - mu/2 sqrt(4 muY + muY^2), maybe mu^2/X   :107-111
+// fz = pi^2/8 + Z^2/2 (PolyaGamma.cpp:157), unfused like the reference's x86-64 build
+__device__ __forceinline__ double dev_fz(double Z)
+{
+    return __dadd_rn(0.125 * kPi * kPi, __dmul_rn(__dmul_rn(0.5, Z), Z));
+}
+
+__device__ __forceinline__ double dev_x_right(double E, double fz)
+{
+    return __dadd_rn(kTrunc, __ddiv_rn(E, fz));
+}
+
+__device__ __forceinline__ double dev_x_pair(double E1)
+{
+    double X = __dadd_rn(1.0, __dmul_rn(E1, kTrunc));
+    return __ddiv_rn(kTrunc, __dmul_rn(X, X));
+}
+
+__device__ __forceinline__ double dev_x_ig(double N, double mu)
+{
+    double Y = __dmul_rn(N, N);
+    double half_mu = __dmul_rn(0.5, mu);
+    double mu_Y = __dmul_rn(mu, Y);
+    double rad = __dsqrt_rn(__dadd_rn(__dmul_rn(4.0, mu_Y), __dmul_rn(mu_Y, mu_Y)));
+    return __dadd_rn(__dadd_rn(mu, __dmul_rn(half_mu, mu_Y)), -__dmul_rn(half_mu, rad));
+}
+
+__device__ __forceinline__ double dev_ig_flip_threshold(double X, double mu)
+{
+    return __ddiv_rn(mu, __dadd_rn(mu, X));
+}
+
+__device__ __forceinline__ double dev_x_ig_flip(double X, double mu)
+{
+    return __ddiv_rn(__dmul_rn(mu, mu), X);
+}
+
 template <class Src>
 __device__ __forceinline__ double dev_trunc_igauss(Src &s, double Z)
 {
@@ -73,19 +115,14 @@ __device__ __forceinline__ double dev_trunc_igauss(Src &s, double Z)
                 E1 = s.expon();
                 E2 = s.expon();
             }
-            X = 1 + E1 * t;
-            X = t / (X * X);
+            X = dev_x_pair(E1);
             alpha = exp(-0.5 * Z * Z * X);
         }
     } else {
         double mu = 1.0 / Z;
         while (X > t) {
-            double Y = s.norm();
-            Y *= Y;
-            double half_mu = 0.5 * mu;
-            double mu_Y = mu * Y;
-            X = mu + half_mu * mu_Y - half_mu * sqrt(4 * mu_Y + mu_Y * mu_Y);
-            if (s.unif() > mu / (mu + X)) X = mu * mu / X;
+            X = dev_x_ig(s.norm(), mu);
+            if (s.unif() > dev_ig_flip_threshold(X, mu)) X = dev_x_ig_flip(X, mu);
         }
     }
     return X;
@@ -97,7 +134,7 @@ __device__ __forceinline__ double devroye_one(Src &s, double Z, double fz, doubl
     for (;;) {
         double X;
         if (s.unif() < right_mass)
-            X = kTrunc + s.expon() / fz;
+            X = dev_x_right(s.expon(), fz);
         else
             X = dev_trunc_igauss(s, Z);
         double S = dev_coef(0, X);
@@ -121,7 +158,7 @@ __device__ __forceinline__ double devroye_sum(Src &s, int n, double z)
 {
     if (n < 1) n = 1;  // the package builds with -DNTHROW: clamp, PolyaGamma.cpp:128-135
     double Z = fabs(z) * 0.5;
-    double fz = 0.125 * kPi * kPi + 0.5 * Z * Z;
+    double fz = dev_fz(Z);
     double pr = dev_right_mass(Z);
     double sum = 0.0;
     for (int i = 0; i < n; ++i) sum += devroye_one(s, Z, fz, pr);
@@ -531,6 +568,9 @@ __device__ __forceinline__ int regime_of(double b)
 }
 
 template <class Src>
+__device__ double devroye_sum_fast(Src &s, int n, double z);   // pg_devroye_fast.cuh
+
+template <class Src>
 __device__ double hybrid_draw(Src &s, double b, double z, int &aux)
 {
     aux = 0;
@@ -546,7 +586,7 @@ __device__ double hybrid_draw(Src &s, double b, double z, int &aux)
         return d;
     }
     case kRegDevroye:
-        return devroye_sum(s, (int)b, z);
+        return devroye_sum_fast(s, (int)b, z);
     case kRegAlt:
         return alt_draw(s, b, z);
     case kRegGamma:

@@ -58,39 +58,62 @@ struct PhiloxSource {
         pos = 4;
     }
 
+    // Out of line on purpose: the ten Philox rounds are ~90 instructions and word() has
+    // many call sites; inlining them blows the samplers past the instruction cache.
+    __device__ __noinline__ void refill()
+    {
+        buf = Philox4x32::block(make_uint4(c0, c1, blk, c3), key);
+        ++blk;
+        pos = 0;
+    }
+
     __device__ __forceinline__ uint32_t word()
     {
-        if (pos == 4) {
-            buf = Philox4x32::block(make_uint4(c0, c1, blk, c3), key);
-            ++blk;
-            pos = 0;
-        }
+        if (pos == 4) refill();
         uint32_t w = pos == 0 ? buf.x : pos == 1 ? buf.y : pos == 2 ? buf.z : buf.w;
         ++pos;
         return w;
     }
 
-    __device__ __forceinline__ double unif() { return word_to_unif(word()); }
+    // Lazy variates: the handle pins the stream words now; the fp32 estimate (for the
+    // decision pre-filters of pg_devroye_fast.cuh) and the fp64 value can be had later.
+    struct LazyE { uint32_t w; int k; };
+    struct LazyN { uint32_t w0, w1, w2; };
 
-    __device__ __forceinline__ double expon()
+    __device__ __forceinline__ LazyE expon_lazy()
     {
-        double acc = 0.0;
-        uint32_t w = word();
-        while (w == 0u) {
-            acc += 32.0 * 0.693147180559945309417232;
-            w = word();
-        }
-        return acc - log(word_to_unif(w));
+        LazyE e{word(), 0};
+        while (e.w == 0u) { ++e.k; e.w = word(); }
+        return e;
     }
-
-    __device__ __forceinline__ double norm()
+    __device__ __forceinline__ static float approx(const LazyE &e)
     {
-        uint32_t w0 = word(), w1 = word(), w2 = word();
-        uint64_t m = ((uint64_t)w0 << 21) | (uint64_t)(w1 >> 11);
+        return (float)e.k * 22.18070977791825f - __logf(((float)e.w + 0.5f) * 0x1p-32f);
+    }
+    __device__ __forceinline__ static double exact(const LazyE &e)
+    {
+        return (double)e.k * (32.0 * 0.693147180559945309417232) - log(word_to_unif(e.w));
+    }
+    __device__ __forceinline__ LazyN norm_lazy() { return LazyN{word(), word(), word()}; }
+    __device__ __forceinline__ static float approx(const LazyN &n)
+    {
+        float u1 = ((float)n.w0 + 0.5f) * 0x1p-32f;   // top 32 of the 53 radius bits
+        float u2 = ((float)n.w2 + 0.5f) * 0x1p-32f;
+        return sqrtf(-2.0f * __logf(u1)) * cospif(2.0f * u2);
+    }
+    __device__ __forceinline__ static double exact(const LazyN &n)
+    {
+        uint64_t m = ((uint64_t)n.w0 << 21) | (uint64_t)(n.w1 >> 11);
         double u1 = ((double)m + 0.5) * 0x1p-53;
-        double u2 = word_to_unif(w2);
+        double u2 = word_to_unif(n.w2);
         return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
     }
+
+    __device__ __forceinline__ double unif() { return word_to_unif(word()); }
+
+    __device__ __forceinline__ double expon() { return exact(expon_lazy()); }
+
+    __device__ __forceinline__ double norm() { return exact(norm_lazy()); }
 
     __device__ double gamma(double a)
     {
@@ -161,6 +184,15 @@ struct TapeSource {
         if (k >= lg) { dry = true; return fb.expon(); }
         return tg[k];
     }
+    struct LazyE { double v; };
+    struct LazyN { double v; };
+    __device__ LazyE expon_lazy() { return LazyE{expon()}; }
+    __device__ LazyN norm_lazy() { return LazyN{norm()}; }
+    __device__ static float approx(const LazyE &e) { return (float)e.v; }
+    __device__ static double exact(const LazyE &e) { return e.v; }
+    __device__ static float approx(const LazyN &n) { return (float)n.v; }
+    __device__ static double exact(const LazyN &n) { return n.v; }
+
     __device__ bool exhausted() const { return dry; }
     __device__ void counts(int *t) const { t[0] = cu; t[1] = ce; t[2] = cn; t[3] = cg; }
 };

@@ -101,6 +101,13 @@ uint32_t bl_get_call_counter(void);
  * different GPUs with results independent of the sharding. */
 int bl_rpg_devroye_dev(double *x, const int *n, const double *z, int64_t num,
                        uint64_t seed, uint32_t call_id, uint64_t obs0, void *stream);
+/* The same draws through the unfiltered all-fp64 Devroye path (A/B check of the fp32
+ * decision pre-filters: results must be identical). */
+int bl_rpg_devroye_plain_dev(double *x, const int *n, const double *z, int64_t num,
+                             uint64_t seed, uint32_t call_id, uint64_t obs0, void *stream);
+/* ... and through the filtered sampler in a plain per-lane loop (no persistent-lane refill). */
+int bl_rpg_devroye_loop_dev(double *x, const int *n, const double *z, int64_t num,
+                            uint64_t seed, uint32_t call_id, uint64_t obs0, void *stream);
 int bl_rpg_gamma_dev(double *x, const double *n, const double *z, int64_t num, int trunc,
                      uint64_t seed, uint32_t call_id, uint64_t obs0, void *stream);
 int bl_rpg_alt_dev(double *x, const double *h, const double *z, int64_t num,
@@ -137,6 +144,8 @@ typedef struct bl_tape {
 
 int bl_rpg_devroye_tape(double *x, const int *n, const double *z, int64_t num,
                         const bl_tape *tape, int *trace);
+int bl_rpg_devroye_plain_tape(double *x, const int *n, const double *z, int64_t num,
+                              const bl_tape *tape, int *trace);
 int bl_rpg_gamma_tape(double *x, const double *n, const double *z, int64_t num, int trunc,
                       const bl_tape *tape, int *trace);
 int bl_rpg_alt_tape(double *x, const double *h, const double *z, int64_t num,

@@ -10,7 +10,7 @@
  * Every function cites the reference lines it follows.  Arithmetic is written in
  * the reference's evaluation order so results agree bit for bit with
  * oracle/_ref/libpg_ref.so (the reference's own sources compiled in place) --
- * tests/test_oracle_vs_ref.py checks exactly that on every regime.
+ * tests/test_oracle_port.py checks exactly that on every regime.
  *
  * PARITY PIN: the reference ships no golden vectors, so this
  * port is pinned against outputs of the reference itself run here
@@ -639,4 +639,24 @@ void pgb_rpg_hybrid(double *x, const double *h, const double *z, int num,
         if (s.exhausted) x[i] = NAN;
         close_stream(&s, trace, i, aux);
     }
+}
+
+/* ---- single-draw entry points used by gibbs_oracle.c ------------------------------- */
+
+double pgo_dev_draw(pgo_src *s, int n, double z) { return dev_draw(s, n, z); }
+
+/* LogitWrapper.cpp:140-162 for one (b, z) */
+double pgo_hybrid_draw(pgo_src *s, double b, double z)
+{
+    double x;
+    if (b > 170) {
+        double m = pgb_pg_m1(b, z);
+        double v = pgb_pg_m2(b, z) - m * m;
+        return m + sqrt(v) * pgo_norm(s);
+    }
+    if (b > 13) { sp_draw(s, &x, b, z); return x; }
+    if (b == 1 || b == 2) return dev_draw(s, (int)b, z);
+    if (b > 1) return alt_draw(s, b, z);
+    if (b > 0) return gam_draw(s, b, z, 200);
+    return 0.0;
 }
