@@ -30,8 +30,12 @@ struct Slot {
     void *shape = nullptr;
     double *z = nullptr, *x = nullptr;
     int *iter = nullptr;
+    void *work = nullptr;      // regime-binning scratch (pg_hybrid.cu)
     int64_t cap = 0;
 };
+
+constexpr int64_t kBinMin = 1 << 15;         // below this the per-lane dispatch kernel is used
+constexpr int64_t kBinMax = 1 << 30;         // observations per binned launch (int32 index lists)
 
 struct Context {
     std::mutex mu;
@@ -40,6 +44,8 @@ struct Context {
     uint64_t seed = 0;
     uint32_t call = 0;
     Slot slot[kSlots];
+    void *devwork = nullptr;   // scratch of the device-resident entry points (stream-ordered)
+    size_t devwork_cap = 0;
     std::string err;
 };
 
@@ -103,13 +109,16 @@ int slot_reserve(Slot &s, int64_t n)
     if (s.z) cudaFree(s.z);
     if (s.x) cudaFree(s.x);
     if (s.iter) cudaFree(s.iter);
+    if (s.work) cudaFree(s.work);
     s.shape = s.z = s.x = nullptr;
     s.iter = nullptr;
+    s.work = nullptr;
     s.cap = 0;
     BL_CK(cudaMalloc(&s.shape, n * sizeof(double)));
     BL_CK(cudaMalloc((void **)&s.z, n * sizeof(double)));
     BL_CK(cudaMalloc((void **)&s.x, n * sizeof(double)));
     BL_CK(cudaMalloc((void **)&s.iter, n * sizeof(int)));
+    BL_CK(cudaMalloc(&s.work, hybrid_workspace_bytes(n)));
     s.cap = n;
     return 0;
 }
@@ -142,7 +151,10 @@ int run_host(Method m, double *x, const void *shape, const double *z, int64_t nu
         if (iter) BL_CK(cudaMemcpyAsync(s.iter, iter + off, n * sizeof(int), cudaMemcpyHostToDevice, s.stream));
         StreamId cid = id;
         cid.obs0 += (uint64_t)off;
-        BL_CK(launch_rpg(m, s.x, s.shape, s.z, n, trunc, iter ? s.iter : nullptr, cid, s.stream));
+        if (m == kHybrid && n >= kBinMin)
+            BL_CK(launch_hybrid_binned(s.x, (const double *)s.shape, s.z, (int)n, cid, s.work, s.stream));
+        else
+            BL_CK(launch_rpg(m, s.x, s.shape, s.z, n, trunc, iter ? s.iter : nullptr, cid, s.stream));
         BL_CK(cudaMemcpyAsync(x + off, s.x, n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         if (iter) BL_CK(cudaMemcpyAsync(iter + off, s.iter, n * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     }
@@ -174,6 +186,27 @@ int run_dev(Method m, double *x, const void *shape, const double *z, int64_t num
         if (ensure_ready()) return 1;
     }
     if (num < 0) return fail("negative batch size");
+    if (m == kHybrid && num >= kBinMin) {
+        std::lock_guard<std::mutex> lock(g.mu);
+        int64_t per = num < kBinMax ? num : kBinMax;
+        size_t need = hybrid_workspace_bytes(per);
+        if (need > g.devwork_cap) {
+            BL_CK(cudaDeviceSynchronize());
+            if (g.devwork) cudaFree(g.devwork);
+            g.devwork = nullptr;
+            g.devwork_cap = 0;
+            BL_CK(cudaMalloc(&g.devwork, need));
+            g.devwork_cap = need;
+        }
+        for (int64_t off = 0; off < num; off += per) {
+            int64_t n = num - off < per ? num - off : per;
+            StreamId cid = id;
+            cid.obs0 += (uint64_t)off;
+            BL_CK(launch_hybrid_binned(x + off, (const double *)shape + off, z + off, (int)n, cid,
+                                       g.devwork, (cudaStream_t)stream));
+        }
+        return 0;
+    }
     BL_CK(launch_rpg(m, x, shape, z, num, trunc, iter, id, (cudaStream_t)stream));
     return 0;
 }

@@ -45,6 +45,12 @@ cudaError_t launch_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint
 cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int64_t num,
                                   StreamId id, cudaStream_t stream);
 
+// rpg_hybrid through regime binning (pg_hybrid.cu); num <= 2^31-1, `work` = device scratch of
+// hybrid_workspace_bytes(num) bytes that stays valid until the stream has drained.
+size_t hybrid_workspace_bytes(int64_t num);
+cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, int num, StreamId id,
+                                 void *work, cudaStream_t stream);
+
 void count_launch(int n = 1);
 
 }  // namespace bl

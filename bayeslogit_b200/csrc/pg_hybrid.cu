@@ -1,0 +1,164 @@
+// rpg_hybrid on the device: regime binning + one kernel per regime.
+//
+// The reference dispatches per observation inside one serial loop
+// (LogitWrapper.cpp:140-162; same logic in PolyaGammaHybrid.h:26-55).  Running that
+// switch per lane makes every warp execute every sampler its 32 observations need
+// and makes the kernel's code footprint the sum of all samplers (~400 KB of SASS,
+// far beyond the instruction cache -- the profile in profiles/r1_00_* shows 65 of
+// 70 stall cycles per instruction waiting on instruction fetch).  Instead:
+//
+//   1. k_hyb_count    histogram of regimes (block-aggregated atomics)
+//   2. k_hyb_offsets  exclusive prefix -> list offsets
+//   3. k_hyb_scatter  counting sort of observation indices by regime into one
+//                     int32 list (block-level ballot ranking, ascending within a
+//                     block so gathers stay nearly coalesced); b <= 0 -> x = 0
+//   4. one kernel per regime over its index list: every warp runs ONE sampler.
+//
+// Results are unchanged by the re-ordering: each observation draws from the Philox
+// stream keyed by its own global index (philox.cuh).
+#include "engine.h"
+#include "pg_devroye_fast.cuh"
+
+namespace bl {
+
+namespace {
+
+constexpr int kBinThreads = 256;
+constexpr int kMetaCounts = 0;    // meta[0..7]   regime counts
+constexpr int kMetaOffsets = 8;   // meta[8..15]  list offsets
+constexpr int kMetaCursor = 16;   // meta[16..23] scatter cursors
+
+__global__ void __launch_bounds__(kBinThreads)
+k_hyb_count(const double *__restrict__ h, int n, int *__restrict__ meta)
+{
+    __shared__ int cnt[8];
+    if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int local[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        local[regime_of(h[i])]++;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        int v = local[r];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&cnt[r], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 6 && cnt[threadIdx.x]) atomicAdd(&meta[kMetaCounts + threadIdx.x], cnt[threadIdx.x]);
+}
+
+__global__ void k_hyb_offsets(int *meta)
+{
+    int acc = 0;
+    for (int r = 1; r < 6; ++r) {   // regime 0 (b <= 0) needs no list
+        meta[kMetaOffsets + r] = acc;
+        meta[kMetaCursor + r] = 0;
+        acc += meta[kMetaCounts + r];
+    }
+}
+
+__global__ void __launch_bounds__(kBinThreads)
+k_hyb_scatter(const double *__restrict__ h, int n, int *__restrict__ meta, int *__restrict__ idx,
+              double *__restrict__ x)
+{
+    __shared__ int wcnt[kBinThreads / 32][8];
+    __shared__ int base[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    int tiles = (n + kBinThreads - 1) / kBinThreads;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        int i = tile * kBinThreads + threadIdx.x;
+        int reg = i < n ? regime_of(h[i]) : -1;
+        if (reg == kRegZero) x[i] = 0.0;                      // LogitWrapper.cpp:159-161
+        int rank = 0;
+#pragma unroll
+        for (int r = 1; r < 6; ++r) {
+            unsigned m = __ballot_sync(0xffffffffu, reg == r);
+            if (reg == r) rank = __popc(m & lt);
+            if (lane == 0) wcnt[warp][r] = __popc(m);
+        }
+        __syncthreads();
+        if (threadIdx.x >= 1 && threadIdx.x < 6) {
+            int r = threadIdx.x, tot = 0;
+            for (int w = 0; w < kBinThreads / 32; ++w) tot += wcnt[w][r];
+            base[r] = tot ? meta[kMetaOffsets + r] + atomicAdd(&meta[kMetaCursor + r], tot) : 0;
+        }
+        __syncthreads();
+        if (reg > 0) {
+            int off = base[reg];
+            for (int w = 0; w < warp; ++w) off += wcnt[w][reg];
+            idx[off + rank] = i;
+        }
+        __syncthreads();
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(128)
+k_hyb_regime(double *__restrict__ x, const double *__restrict__ h, const double *__restrict__ z,
+             const int *__restrict__ idx, const int *__restrict__ meta, StreamId id)
+{
+    const int count = meta[kMetaCounts + R];
+    const int *list = idx + meta[kMetaOffsets + R];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
+        int i = list[j];
+        PhiloxSource s;
+        s.open(id.seed, id.obs0 + (uint64_t)i, id.call_id);
+        double b = h[i], zi = z[i], v;
+        if (R == kRegNormal) {
+            double m = pg_m1(b, zi);
+            double var = pg_m2(b, zi) - m * m;
+            v = m + sqrt(var) * s.norm();
+        } else if (R == kRegSP) {
+            sp_draw(s, v, b, zi);
+        } else if (R == kRegDevroye) {
+            v = devroye_sum_fast(s, (int)b, zi);
+        } else if (R == kRegAlt) {
+            v = alt_draw(s, b, zi);
+        } else {
+            v = gamma_sum(s, b, zi, 200);
+        }
+        x[i] = v;
+    }
+}
+
+template <int R>
+void launch_regime(double *x, const double *h, const double *z, const int *idx, const int *meta,
+                   StreamId id, int n, int ctas_per_sm, cudaStream_t st)
+{
+    int need = (n + 127) / 128;
+    int cap = 148 * ctas_per_sm;
+    k_hyb_regime<R><<<need < cap ? need : cap, 128, 0, st>>>(x, h, z, idx, meta, id);
+    count_launch();
+}
+
+}  // namespace
+
+size_t hybrid_workspace_bytes(int64_t num) { return 32 * sizeof(int) + (size_t)num * sizeof(int); }
+
+// One rpg_hybrid batch of at most 2^31-1 observations.  `work` holds
+// hybrid_workspace_bytes(num) bytes of device scratch owned by the caller's stream.
+cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, int num, StreamId id,
+                                 void *work, cudaStream_t st)
+{
+    if (num <= 0) return cudaSuccess;
+    int *meta = (int *)work;
+    int *idx = meta + 32;
+    cudaError_t e = cudaMemsetAsync(meta, 0, 32 * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    int tiles = (num + kBinThreads - 1) / kBinThreads;
+    int grid = tiles < 148 * 8 ? tiles : 148 * 8;
+    k_hyb_count<<<grid, kBinThreads, 0, st>>>(h, num, meta);
+    k_hyb_offsets<<<1, 1, 0, st>>>(meta);
+    k_hyb_scatter<<<grid, kBinThreads, 0, st>>>(h, num, meta, idx, x);
+    count_launch(3);
+    // heavy regimes first so the light ones fill the tail
+    launch_regime<kRegSP>(x, h, z, idx, meta, id, num, 4, st);
+    launch_regime<kRegAlt>(x, h, z, idx, meta, id, num, 4, st);
+    launch_regime<kRegGamma>(x, h, z, idx, meta, id, num, 8, st);
+    launch_regime<kRegNormal>(x, h, z, idx, meta, id, num, 8, st);
+    launch_regime<kRegDevroye>(x, h, z, idx, meta, id, num, 8, st);
+    return cudaGetLastError();
+}
+
+}  // namespace bl

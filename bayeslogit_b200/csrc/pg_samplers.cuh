@@ -224,7 +224,7 @@ __device__ __forceinline__ double igauss(Src &s, double mu, double lambda)
 }
 
 template <class Src>
-__device__ __forceinline__ double ltgamma(Src &s, double shape, double rate, double trunc)
+__device__ __noinline__ double ltgamma(Src &s, double shape, double rate, double trunc)
 {
     double a = shape;
     double b = rate * trunc;
@@ -317,7 +317,7 @@ __device__ __forceinline__ double alt_envelope(double x, double h, double trunc)
 }
 
 template <class Src>
-__device__ double alt_chunk(Src &s, double h, double z)
+__device__ __noinline__ double alt_chunk(Src &s, double h, double z)
 {
     const int max_inner = 200;
     if (h < 1 || h > 4) return 0;
@@ -410,7 +410,7 @@ __device__ __forceinline__ double y_of_v(double v, double tol)
     return 1.0;
 }
 
-__device__ inline double v_eval(double y)
+static __device__ __noinline__ double v_eval(double y)
 {
     const double tol = 1e-9;
     const int max_iter = 1000;
@@ -453,7 +453,7 @@ __device__ __forceinline__ double sp_cos_rt(double v)
     return v >= 0 ? cos(r) : cosh(r);
 }
 
-__device__ inline void sp_tangent(double x, double z, double mid, double &slope, double &icept)
+static __device__ __noinline__ void sp_tangent(double x, double z, double mid, double &slope, double &icept)
 {
     double v = v_eval(x);
     double u = 0.5 * v;
@@ -474,7 +474,7 @@ __device__ inline void sp_tangent(double x, double z, double mid, double &slope,
     icept = eta_val - eta_der * x;
 }
 
-__device__ inline double sp_density(double x, double n, double z)
+static __device__ __noinline__ double sp_density(double x, double n, double z)
 {
     double v = v_eval(x);
     double u = 0.5 * v;

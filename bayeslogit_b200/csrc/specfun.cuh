@@ -17,7 +17,7 @@ __device__ __forceinline__ double p_norm(double x) { return 0.5 * erfc(-x * kSqr
 // log Phi(x).  Lower tail through the scaled complementary error function so the
 // far tail (x ~ -1e3, reached for |z| ~ 1e3 in mass_texpon) neither underflows
 // nor loses relative accuracy.
-__device__ __forceinline__ double log_p_norm(double x)
+static __device__ __noinline__ double log_p_norm(double x)
 {
     if (x > 0.0) return log1p(-0.5 * erfc(x * kSqrt1_2));
     double t = -x * kSqrt1_2;
@@ -43,7 +43,7 @@ __device__ inline double gamma_log_prefix(double a, double x)
 // Regularised lower incomplete gamma P(a, x): power series for x < a+1, modified
 // Lentz continued fraction for Q otherwise (returned as 1-Q).  The samplers only
 // ever use 1.0 - P, so absolute accuracy is what matters.
-__device__ inline double p_gamma_lower(double a, double x)
+static __device__ __noinline__ double p_gamma_lower(double a, double x)
 {
     if (x <= 0.0) return 0.0;
     if (isinf(x)) return 1.0;
