@@ -79,6 +79,15 @@ def lib():
     L.bl_rpg_alt_tape.argtypes = [vp, vp, vp, i64, tp, vp]
     L.bl_rpg_sp_tape.argtypes = [vp, vp, vp, i64, vp, tp, vp]
     L.bl_rpg_hybrid_tape.argtypes = [vp, vp, vp, i64, tp, vp]
+    cd = C.c_double
+    L.bl_logit_gibbs.argtypes = [vp] * 7 + [ci, ci, ci, ci, u64, ci]
+    L.bl_mlogit_gibbs.argtypes = [vp] * 7 + [ci, ci, ci, ci, ci, u64, ci]
+    L.bl_nb_gibbs.argtypes = [vp, vp, vp, vp, cd, vp, vp, ci, ci, ci, u64]
+    L.bl_logit_gibbs_dev.argtypes = [vp] * 7 + [i64, ci, ci, ci, u64, ci, u64, vp]
+    L.bl_mlogit_gibbs_dev.argtypes = [vp] * 7 + [i64, ci, ci, ci, ci, u64, ci, u64, vp]
+    L.bl_nb_gibbs_dev.argtypes = [vp, vp, vp, vp, cd, vp, vp, i64, ci, ci, u64, u64, vp]
+    L.bl_comm_unique_id.argtypes = [vp]
+    L.bl_comm_init.argtypes = [vp, ci, ci]
     L.bl_probe_pg_moments.argtypes = [vp, vp, vp, vp, i64]
     L.bl_probe_v_eval.argtypes = [vp, vp, i64]
     L.bl_probe_specfun.argtypes = [vp, ci, vp, vp, vp, i64]

@@ -473,4 +473,20 @@ int bl_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2)
 
 uint64_t bl_kernel_launches(void) { return g_launches.load(); }
 
+int bl_ensure_ready_internal(void)
+{
+    std::lock_guard<std::mutex> lock(g.mu);
+    return ensure_ready();
+}
+
+void bl_set_error_internal(const char *msg) { g.err = msg ? msg : ""; }
+
+void *bl_stream_internal(void) { return (void *)g.slot[0].stream; }
+
+uint64_t bl_next_call_internal(void)
+{
+    std::lock_guard<std::mutex> lock(g.mu);
+    return g.call++;
+}
+
 }  // extern "C"

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <string>
 
 #include "../../include/bayeslogit_b200.h"
 
@@ -51,6 +52,36 @@ size_t hybrid_workspace_bytes(int64_t num);
 cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, int num, StreamId id,
                                  void *work, cudaStream_t stream);
 
+// Gibbs sweeps on device-resident data (gibbs.cu); return 0 on success, message in err.
+int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const double *tX,
+                       const double *n, const double *m0, const double *P0, int64_t N, int P,
+                       int samp, int burn, uint64_t seed, int flags, uint64_t obs0,
+                       cudaStream_t st, std::string &err);
+int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const double *tX,
+                        const double *n, const double *m0, const double *P0, int64_t N, int P, int J,
+                        int samp, int burn, uint64_t seed, int flags, uint64_t obs0,
+                        cudaStream_t st, std::string &err);
+int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const double *tX, double d,
+                    const double *m0, const double *P0, int64_t N, int P, int samp, uint64_t seed,
+                    uint64_t obs0, cudaStream_t st, std::string &err);
+int logit_em_device(double *beta, const double *y, const double *tX, const double *n, int64_t N,
+                    int P, double tol, int max_iter, int *iters, cudaStream_t st, std::string &err);
+int comm_unique_id(void *out128, std::string &err);
+int comm_init(const void *id128, int rank, int world, std::string &err);
+void comm_destroy();
+
 void count_launch(int n = 1);
+
+}  // namespace bl
+
+// internal hooks of the context in capi.cu
+extern "C" {
+int bl_ensure_ready_internal(void);
+void bl_set_error_internal(const char *msg);
+void *bl_stream_internal(void);
+uint64_t bl_next_call_internal(void);
+}
+
+namespace bl {
 
 }  // namespace bl

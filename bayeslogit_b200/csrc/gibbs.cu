@@ -1,0 +1,509 @@
+// Gibbs sweeps on the device: binary/binomial logit, multinomial logit, negative
+// binomial.  Host drivers + the reference's `gibbs` / `mult_gibbs` C entry points
+// (LogitWrapper.cpp:176-234, :316-374) and their bl_* extensions.
+//
+// One iteration = psi = X beta (k_xbeta, HBM-bound) -> omega = PG(n, psi) (the
+// sampler kernels of pg_devroye_kernel.cu / pg_hybrid.cu) -> X' Omega X (+ X'v)
+// (k_gram_partial, FP64-pipe-bound; fixed-order reduce) -> [all-reduce of P^2+P
+// doubles when observations are sharded across GPUs] -> beta draw (one CTA,
+// replicated).  Nothing returns to the host inside the loop.
+//
+// Stream contract: iteration t draws omega_i from Philox (seed, obs i, call t)
+// (mlogit: call t*(J-1)+j) and beta from (seed, obs 2^64-1, same call); i is the
+// GLOBAL observation index, so sharding does not change the chain.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+#include "gibbs_beta.cuh"
+#include "gibbs_kernels.cuh"
+
+namespace bl {
+
+// ------------------------------------------------------------------------------------
+// optional NCCL communicator (resolved at run time: no link-time dependency)
+// ------------------------------------------------------------------------------------
+namespace {
+
+struct Nccl {
+    void *lib = nullptr;
+    void *comm = nullptr;
+    int rank = 0, world = 1;
+    int (*CommInitRank)(void **, int, char[128], int) = nullptr;   // ncclUniqueId by value (128 bytes)
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+} g_nccl;
+
+struct UniqueId { char bytes[128]; };
+
+bool nccl_load(std::string &err)
+{
+    if (g_nccl.lib) return true;
+    g_nccl.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl.lib) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+    g_nccl.GetUniqueId = (int (*)(void *))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    void *init = dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.CommInitRank = (int (*)(void **, int, char[128], int))init;
+    if (!g_nccl.GetUniqueId || !g_nccl.AllReduce || !init) { err = "libnccl.so.2 lacks expected symbols"; return false; }
+    return true;
+}
+
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// kernels that need the single-CTA algebra
+// ------------------------------------------------------------------------------------
+
+// acc[0..P^2) = Gram sum (no prior), acc[P^2..P^2+P) = optional X'v sum.
+// PP = acc + P0; rhs = base_rhs (+ acc tail); then the draw.
+__global__ void __launch_bounds__(256)
+k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__ P0,
+            const double *__restrict__ base_rhs, int add_tail, const double *beta_prev,
+            double *beta_out, double *gwork, int P, uint64_t seed, uint32_t call, int *status,
+            int use_smem)
+{
+    extern __shared__ double sm[];
+    double *A = use_smem ? sm : gwork;
+    double *B = A + (size_t)P * P;
+    double *v = B + (size_t)P * P;
+    double *rhs = v + 4 * P;
+    for (int k = threadIdx.x; k < P * P; k += blockDim.x) A[k] = acc[k] + (P0 ? P0[k] : 0.0);
+    for (int k = threadIdx.x; k < P; k += blockDim.x)
+        rhs[k] = (base_rhs ? base_rhs[k] : 0.0) + (add_tail ? acc[(size_t)P * P + k] : 0.0);
+    __syncthreads();
+    cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, seed, call, status);
+}
+
+__global__ void k_matvec(double *out, const double *A, const double *x, int P)   // out = A x, col-major
+{
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= P) return;
+    double s = 0.0;
+    for (int b = 0; b < P; ++b) s = fma(A[a + (size_t)P * b], x[b], s);
+    out[a] = s;
+}
+
+namespace {
+
+#define GB_CK(expr)                                                                  \
+    do {                                                                             \
+        cudaError_t e_ = (expr);                                                     \
+        if (e_ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e_); return 1; } \
+    } while (0)
+
+struct DevMem {
+    std::vector<void *> ptrs;
+    ~DevMem() { for (void *p : ptrs) cudaFree(p); }
+    template <class T>
+    cudaError_t get(T **p, size_t count)
+    {
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) { ptrs.push_back(q); *p = (T *)q; }
+        return e;
+    }
+};
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Shared machinery of the three sweeps.
+struct Sweep {
+    int64_t N = 0;          // local observations
+    int P = 0;
+    uint64_t obs0 = 0;      // global index of local observation 0
+    cudaStream_t st = nullptr;
+    const double *tX = nullptr;
+    double *psi = nullptr, *w = nullptr, *acc = nullptr, *part = nullptr, *xtv_part = nullptr;
+    double *gwork = nullptr;
+    int *status = nullptr;
+    int nt = 1, nslab = 1, xtv_slabs = 1;
+    bool use_smem = true;
+    size_t beta_smem = 0;
+
+    int init(DevMem &m, std::string &err)
+    {
+        nt = cdiv(P, kGramTile);
+        int tiles = nt * (nt + 1) / 2;
+        nslab = (int)std::min<int64_t>(std::max<int64_t>(1, 148 * 2 / tiles), std::max<int64_t>(1, N / kGramRows));
+        if (nslab < 1) nslab = 1;
+        xtv_slabs = (int)std::min<int64_t>(148 * 2, std::max<int64_t>(1, N / 64));
+        GB_CK(m.get(&psi, N));
+        GB_CK(m.get(&w, N));
+        GB_CK(m.get(&acc, (size_t)P * P + P));
+        GB_CK(m.get(&part, (size_t)tiles * nslab * kGramTile * kGramTile));
+        GB_CK(m.get(&xtv_part, (size_t)xtv_slabs * P));
+        GB_CK(m.get(&gwork, 2 * (size_t)P * P + 5 * (size_t)P));
+        GB_CK(m.get(&status, 1));
+        GB_CK(cudaMemsetAsync(status, 0, sizeof(int), st));
+        GB_CK(cudaMemsetAsync(acc, 0, ((size_t)P * P + P) * sizeof(double), st));
+        beta_smem = (2 * (size_t)P * P + 5 * (size_t)P) * sizeof(double);
+        use_smem = beta_smem <= 200 * 1024;
+        if (use_smem && beta_smem > 48 * 1024)
+            GB_CK(cudaFuncSetAttribute(k_beta_draw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem));
+        return 0;
+    }
+
+    void xbeta(double *out, const double *beta, const double *off, double off_scale, double shift = 0.0)
+    {
+        int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (N + 7) / 8));
+        k_xbeta<<<grid, 256, P * sizeof(double), st>>>(out, tX, beta, off, off_scale, shift, N, P);
+        count_launch();
+    }
+
+    // acc[0..P^2) <- sum_i w_i x_i x_i'  (local shard)
+    void gram(const double *wv)
+    {
+        int tiles = nt * (nt + 1) / 2;
+        k_gram_partial<<<dim3(nslab, tiles), 256, 0, st>>>(part, tX, wv, N, P, nt);
+        k_gram_reduce<<<cdiv((int64_t)P * P, 256), 256, 0, st>>>(acc, nullptr, part, P, nt, nslab);
+        count_launch(2);
+    }
+
+    // acc[P^2..P^2+P) <- X'(c0 v0 + c1 v1 v2)
+    void xtv(const double *v0, double c0, const double *v1, const double *v2, double c1)
+    {
+        k_xtv_partial<<<xtv_slabs, 256, 8 * P * sizeof(double), st>>>(xtv_part, tX, v0, c0, v1, v2, c1, N, P);
+        k_xtv_reduce<<<cdiv(P, 128), 128, 0, st>>>(acc + (size_t)P * P, nullptr, nullptr, xtv_part, P, xtv_slabs);
+        count_launch(2);
+    }
+
+    int allreduce(bool with_tail, std::string &err)
+    {
+        if (g_nccl.world <= 1 || !g_nccl.comm) return 0;
+        size_t cnt = (size_t)P * P + (with_tail ? P : 0);
+        int r = g_nccl.AllReduce(acc, acc, cnt, kNcclFloat64, kNcclSum, g_nccl.comm, st);
+        if (r != 0) { err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return 1; }
+        return 0;
+    }
+
+    void beta_draw(int mode, const double *P0, const double *base_rhs, bool add_tail,
+                   const double *beta_prev, double *beta_out, uint64_t seed, uint32_t call)
+    {
+        k_beta_draw<<<1, 256, use_smem ? beta_smem : 0, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0,
+                                                               beta_prev, beta_out, gwork, P, seed, call,
+                                                               status, use_smem ? 1 : 0);
+        count_launch();
+    }
+
+    int check_status(std::string &err, const char *what)
+    {
+        int h = 0;
+        GB_CK(cudaMemcpyAsync(&h, status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GB_CK(cudaStreamSynchronize(st));
+        if (h != 0) { err = std::string(what) + ": posterior precision is not positive definite"; return 1; }
+        return 0;
+    }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// Binary / binomial logit (Logit::gibbs, Logit.hpp:460-481 with gibbs_block :402-457)
+// ------------------------------------------------------------------------------------
+// All pointers are DEVICE pointers.  y, n: local shard [N]; tX: P x N local shard;
+// w_out: N x samp or null (flags & BL_GIBBS_NO_W); beta_out: P x samp.
+int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const double *tX,
+                       const double *n, const double *m0, const double *P0, int64_t N, int P,
+                       int samp, int burn, uint64_t seed, int flags, uint64_t obs0,
+                       cudaStream_t st, std::string &err)
+{
+    if (N <= 0 || P <= 0 || samp <= 0 || burn < 0) { err = "gibbs: bad dimensions"; return 1; }
+    DevMem mem;
+    Sweep s;
+    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX;
+    if (s.init(mem, err)) return 1;
+    double *kappa, *b0, *bP;
+    int *shape;
+    GB_CK(mem.get(&kappa, N));
+    GB_CK(mem.get(&shape, N));
+    GB_CK(mem.get(&b0, P));
+    GB_CK(mem.get(&bP, P));
+    const bool keep_w = !(flags & BL_GIBBS_NO_W) && w_out;
+    const int mode = (flags & BL_GIBBS_PLAIN_BETA) ? kBetaPlain : kBetaConstrained;
+
+    // set_prior / set_bP: b0 = P0 m0, bP = b0 + X'(n (y - 1/2))   (Logit.hpp:174-190)
+    k_kappa<<<cdiv(N, 256), 256, 0, st>>>(kappa, y, n, 0.0, N);
+    k_shape_int<<<cdiv(N, 256), 256, 0, st>>>(shape, n, N);
+    k_matvec<<<cdiv(P, 128), 128, 0, st>>>(b0, P0, m0, P);
+    count_launch(3);
+    s.xtv(kappa, 1.0, nullptr, nullptr, 0.0);
+    if (g_nccl.world > 1 && g_nccl.comm) {
+        int r = g_nccl.AllReduce(s.acc + (size_t)P * P, s.acc + (size_t)P * P, (size_t)P, kNcclFloat64, kNcclSum, g_nccl.comm, st);
+        if (r != 0) { err = "ncclAllReduce failed"; return 1; }
+    }
+    k_xtv_reduce<<<cdiv(P, 128), 128, 0, st>>>(bP, b0, s.acc + (size_t)P * P, s.xtv_part, P, 0);
+    count_launch();
+
+    GB_CK(cudaMemsetAsync(beta_out, 0, sizeof(double) * (size_t)P * samp, st));
+    if (keep_w) GB_CK(cudaMemsetAsync(w_out, 0, sizeof(double) * (size_t)N * samp, st));
+    uint32_t t = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        int iters = phase == 0 ? burn : samp;
+        double *bcur = beta_out, *bprev = beta_out;
+        double *wcur = keep_w ? w_out : s.w;
+        s.xbeta(s.psi, bcur, nullptr, 0.0);
+        for (int m = 1; m <= iters; ++m, ++t) {
+            cudaError_t e = launch_devroye_refill(wcur, shape, s.psi, N, StreamId{seed, obs0, t}, st);
+            if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
+            s.gram(wcur);
+            if (s.allreduce(false, err)) return 1;
+            s.beta_draw(mode, P0, bP, false, bprev, bcur, seed, t);
+            s.xbeta(s.psi, bcur, nullptr, 0.0);
+            if (phase == 1) {
+                bprev = bcur;
+                if (m < iters) { bcur += P; if (keep_w) wcur += N; }
+            }
+        }
+    }
+    GB_CK(cudaGetLastError());
+    return s.check_status(err, "gibbs");
+}
+
+// ------------------------------------------------------------------------------------
+// Multinomial logit (MultLogit::gibbs, MultLogit.hpp:261-372)
+// ------------------------------------------------------------------------------------
+// w_out: N x (J-1) x samp (or null), beta_out: P x (J-1) x samp, ty: (J-1) x N,
+// m0: P x (J-1), P0: P x P x (J-1).
+int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const double *tX,
+                        const double *n, const double *m0, const double *P0, int64_t N, int P, int J,
+                        int samp, int burn, uint64_t seed, int flags, uint64_t obs0,
+                        cudaStream_t st, std::string &err)
+{
+    if (N <= 0 || P <= 0 || J < 2 || samp <= 0 || burn < 0) { err = "mult_gibbs: bad dimensions"; return 1; }
+    const int U = J - 1;
+    DevMem mem;
+    Sweep s;
+    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX;
+    if (s.init(mem, err)) return 1;
+    double *Z, *b0, *XB, *cj, *eta, *yj, *base;
+    int *shape;
+    GB_CK(mem.get(&Z, (size_t)P * U));
+    GB_CK(mem.get(&b0, (size_t)P * U));
+    GB_CK(mem.get(&base, (size_t)P * U));
+    GB_CK(mem.get(&XB, (size_t)N * U));
+    GB_CK(mem.get(&cj, N));
+    GB_CK(mem.get(&eta, N));
+    GB_CK(mem.get(&yj, N));
+    GB_CK(mem.get(&shape, N));
+    const bool keep_w = !(flags & BL_GIBBS_NO_W) && w_out;
+    k_shape_int<<<cdiv(N, 256), 256, 0, st>>>(shape, n, N);
+    count_launch();
+    // Z_j = X'(n (y_j - 1/2)), b0_j = P0_j m0_j ; base_j = Z_j + b0_j   (MultLogit.hpp:214-219, :271-273)
+    for (int j = 0; j < U; ++j) {
+        GB_CK(cudaMemcpy2DAsync(yj, sizeof(double), ty + j, sizeof(double) * U, sizeof(double), N,
+                                cudaMemcpyDeviceToDevice, st));
+        k_kappa<<<cdiv(N, 256), 256, 0, st>>>(cj, yj, n, 0.0, N);
+        k_matvec<<<cdiv(P, 128), 128, 0, st>>>(b0 + (size_t)P * j, P0 + (size_t)P * P * j, m0 + (size_t)P * j, P);
+        count_launch(2);
+        s.xtv(cj, 1.0, nullptr, nullptr, 0.0);
+        if (g_nccl.world > 1 && g_nccl.comm)
+            g_nccl.AllReduce(s.acc + (size_t)P * P, s.acc + (size_t)P * P, (size_t)P, kNcclFloat64, kNcclSum, g_nccl.comm, st);
+        k_xtv_reduce<<<cdiv(P, 128), 128, 0, st>>>(base + (size_t)P * j, b0 + (size_t)P * j, s.acc + (size_t)P * P, s.xtv_part, P, 0);
+        count_launch();
+    }
+    GB_CK(cudaMemsetAsync(beta_out, 0, sizeof(double) * (size_t)P * U * samp, st));
+    if (keep_w) GB_CK(cudaMemsetAsync(w_out, 0, sizeof(double) * (size_t)N * U * samp, st));
+    GB_CK(cudaMemsetAsync(XB, 0, sizeof(double) * (size_t)N * U, st));
+    const int total = burn + samp;
+    for (int t = 0; t < total; ++t) {
+        int slice = t <= burn ? 0 : t - burn;
+        double *bS = beta_out + (size_t)P * U * slice;
+        double *wS = keep_w ? w_out + (size_t)N * U * slice : nullptr;
+        for (int j = 0; j < U; ++j) {
+            uint32_t call = (uint32_t)t * (uint32_t)U + (uint32_t)j;
+            k_mlogit_offsets<<<cdiv(N, 256), 256, 0, st>>>(cj, eta, XB, N, U, j);
+            count_launch();
+            double *wj = wS ? wS + (size_t)N * j : s.w;
+            cudaError_t e = launch_devroye_refill(wj, shape, eta, N, StreamId{seed, obs0, call}, st);
+            if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
+            s.gram(wj);
+            s.xtv(nullptr, 0.0, wj, cj, 1.0);              // X' Omega c_j
+            if (s.allreduce(true, err)) return 1;
+            s.beta_draw(kBetaMvn, P0 + (size_t)P * P * j, base + (size_t)P * j, true, nullptr,
+                        bS + (size_t)P * j, seed, call);
+            s.xbeta(XB + (size_t)N * j, bS + (size_t)P * j, nullptr, 0.0);
+        }
+    }
+    GB_CK(cudaGetLastError());
+    return s.check_status(err, "mult_gibbs");
+}
+
+// ------------------------------------------------------------------------------------
+// Negative binomial, dispersion d fixed (NBPG-logmean.R:13-34, 77-106 without draw.df)
+// ------------------------------------------------------------------------------------
+// beta_out: P x samp (every iteration kept), w_out: N (last omega) or null.
+int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const double *tX, double d,
+                    const double *m0, const double *P0, int64_t N, int P, int samp, uint64_t seed,
+                    uint64_t obs0, cudaStream_t st, std::string &err)
+{
+    if (N <= 0 || P <= 0 || samp <= 0 || !(d > 0)) { err = "nb_gibbs: bad arguments"; return 1; }
+    DevMem mem;
+    Sweep s;
+    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX;
+    if (s.init(mem, err)) return 1;
+    double *kappa, *b0, *shape, *beta0;
+    void *work;
+    GB_CK(mem.get(&kappa, N));
+    GB_CK(mem.get(&shape, N));
+    GB_CK(mem.get(&b0, P));
+    GB_CK(mem.get(&beta0, P));
+    GB_CK(mem.get((char **)&work, hybrid_workspace_bytes(N)));
+    const double ld = log(d);
+    k_kappa<<<cdiv(N, 256), 256, 0, st>>>(kappa, y, nullptr, d, N);          // (y - d)/2
+    k_shape_add<<<cdiv(N, 256), 256, 0, st>>>(shape, y, d, N);                // b = y + d
+    k_matvec<<<cdiv(P, 128), 128, 0, st>>>(b0, P0, m0, P);
+    count_launch(3);
+    GB_CK(cudaMemsetAsync(beta0, 0, sizeof(double) * P, st));
+    double *w = w_out ? w_out : s.w;
+    for (int t = 0; t < samp; ++t) {
+        const double *bprev = t == 0 ? beta0 : beta_out + (size_t)P * (t - 1);
+        s.xbeta(s.psi, bprev, nullptr, 0.0, -ld);                              // psi = X beta - log d
+        StreamId id{seed, obs0, (uint32_t)t};
+        cudaError_t e = N >= (1 << 15)
+            ? launch_hybrid_binned(w, shape, s.psi, (int)N, id, work, st)
+            : launch_rpg(kHybrid, w, shape, s.psi, N, 0, nullptr, id, st);
+        if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
+        s.gram(w);
+        s.xtv(kappa, 1.0, w, nullptr, ld);                                     // X'(kappa + omega log d)
+        if (s.allreduce(true, err)) return 1;
+        s.beta_draw(kBetaPlain, P0, b0, true, nullptr, beta_out + (size_t)P * t, seed, (uint32_t)t);
+    }
+    GB_CK(cudaGetLastError());
+    return s.check_status(err, "nb_gibbs");
+}
+
+// ------------------------------------------------------------------------------------
+// Posterior mode by EM (Logit::EM, Logit.hpp:488-554): the same psi / Gram / Cholesky
+// kernels with omega replaced by its conditional mean.
+// ------------------------------------------------------------------------------------
+__global__ void k_em_weights(double *__restrict__ w, const double *__restrict__ psi,
+                             const double *__restrict__ n, int64_t N)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double h = psi[i] * 0.5;
+    if (fabs(h) < 0.01)
+        w[i] = n[i] / cosh(h) * (1 + h * h / 6.0 + pow(h, 4.0) / 120.0 + pow(h, 6.0) / 5040.0) * 0.25;
+    else
+        w[i] = n[i] * tanh(h) / h * 0.25;
+}
+
+// beta_new = (acc)^-1 rhs by Cholesky; dist = max |beta_new - beta_old|  (Logit.hpp:538-548)
+__global__ void __launch_bounds__(256)
+k_em_solve(const double *__restrict__ acc, const double *__restrict__ rhs, double *beta, double *dist,
+           double *gwork, int P, int *status, int use_smem)
+{
+    extern __shared__ double sm[];
+    __shared__ int ok;
+    double *A = use_smem ? sm : gwork;
+    double *x = A + (size_t)P * P;
+    for (int k = threadIdx.x; k < P * P; k += blockDim.x) A[k] = acc[k];
+    for (int k = threadIdx.x; k < P; k += blockDim.x) x[k] = rhs[k];
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    cta_chol_upper(A, P, &ok);
+    if (!ok) { if (threadIdx.x == 0) *status = 1; return; }
+    if (threadIdx.x < 32) {
+        int lane = threadIdx.x;
+        warp_solve_ut(A, x, P, lane);
+        warp_solve_u(A, x, P, lane);
+        double d = 0.0;
+        for (int i = lane; i < P; i += 32) {
+            d = fmax(d, fabs(x[i] - beta[i]));
+            beta[i] = x[i];
+        }
+        for (int o = 16; o; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+        if (lane == 0) *dist = d;
+    }
+}
+
+int logit_em_device(double *beta, const double *y, const double *tX, const double *n, int64_t N,
+                    int P, double tol, int max_iter, int *iters, cudaStream_t st, std::string &err)
+{
+    if (N <= 0 || P <= 0) { err = "EM: bad dimensions"; return 1; }
+    DevMem mem;
+    Sweep s;
+    s.N = N; s.P = P; s.st = st; s.tX = tX;
+    if (s.init(mem, err)) return 1;
+    double *kappa, *bP, *dist;
+    GB_CK(mem.get(&kappa, N));
+    GB_CK(mem.get(&bP, P));
+    GB_CK(mem.get(&dist, 1));
+    k_kappa<<<cdiv(N, 256), 256, 0, st>>>(kappa, y, n, 0.0, N);
+    count_launch();
+    s.xtv(kappa, 1.0, nullptr, nullptr, 0.0);                       // bP = X' kappa (default prior b0 = 0)
+    k_xtv_reduce<<<cdiv(P, 128), 128, 0, st>>>(bP, s.acc + (size_t)P * P, nullptr, s.xtv_part, P, 0);
+    count_launch();
+    GB_CK(cudaMemsetAsync(beta, 0, sizeof(double) * P, st));
+    size_t smem = ((size_t)P * P + P) * sizeof(double);
+    bool use_smem = smem <= 200 * 1024;
+    if (use_smem && smem > 48 * 1024)
+        GB_CK(cudaFuncSetAttribute(k_em_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    double hdist = tol + 1.0;
+    int iter = 0;
+    while (hdist > tol && iter < max_iter) {
+        s.xbeta(s.psi, beta, nullptr, 0.0);
+        k_em_weights<<<cdiv(N, 256), 256, 0, st>>>(s.w, s.psi, n, N);
+        count_launch();
+        s.gram(s.w);
+        k_em_solve<<<1, 256, use_smem ? smem : 0, st>>>(s.acc, bP, beta, dist, s.gwork, P, s.status, use_smem ? 1 : 0);
+        count_launch();
+        GB_CK(cudaMemcpyAsync(&hdist, dist, sizeof(double), cudaMemcpyDeviceToHost, st));
+        GB_CK(cudaStreamSynchronize(st));
+        ++iter;
+        int h = 0;
+        GB_CK(cudaMemcpy(&h, s.status, sizeof(int), cudaMemcpyDeviceToHost));
+        if (h) { err = "EM: X' Omega X is not positive definite"; return 1; }
+    }
+    *iters = iter;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// communicator
+// ------------------------------------------------------------------------------------
+int comm_unique_id(void *out128, std::string &err)
+{
+    if (!nccl_load(err)) return 1;
+    int r = g_nccl.GetUniqueId(out128);
+    if (r != 0) { err = "ncclGetUniqueId failed"; return 1; }
+    return 0;
+}
+
+int comm_init(const void *id128, int rank, int world, std::string &err)
+{
+    if (world <= 1) { g_nccl.world = 1; g_nccl.rank = 0; return 0; }
+    if (!nccl_load(err)) return 1;
+    UniqueId id;
+    memcpy(id.bytes, id128, 128);
+    // ncclCommInitRank(ncclComm_t*, int nranks, ncclUniqueId commId /*by value*/, int rank)
+    typedef int (*init_fn)(void **, int, UniqueId, int);
+    init_fn init = (init_fn)dlsym(g_nccl.lib, "ncclCommInitRank");
+    int r = init(&g_nccl.comm, world, id, rank);
+    if (r != 0) { err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return 1; }
+    g_nccl.rank = rank;
+    g_nccl.world = world;
+    return 0;
+}
+
+void comm_destroy()
+{
+    if (g_nccl.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g_nccl.comm);
+    g_nccl.comm = nullptr;
+    g_nccl.world = 1;
+    g_nccl.rank = 0;
+}
+
+}  // namespace bl

@@ -1,0 +1,281 @@
+// Single-CTA dense algebra and the three beta draws of the Gibbs sweeps.
+//
+// P is small (<= 256) and the draw sits on the critical path between two sweeps, so
+// one CTA does the whole thing out of shared memory (global scratch when 2 P^2
+// doubles do not fit): Cholesky, triangular solves, the draw.  It is replicated on
+// every GPU with an identical Philox stream, so beta stays bit-identical across
+// ranks without a broadcast.  Reference statements:
+//   plain        beta ~ N(PP^-1 bP, PP^-1)                  Logit.hpp:291-320
+//   constrained  coordinate-wise truncated normals, beta_j >= 0 for j < P-1
+//                (the draw Logit::gibbs_block actually calls)     Logit.hpp:322-400
+//   mvn          Normal::set_from_likelihood + draw               Normal.hpp:98-131
+// Variates come from the stream (seed, obs 2^64-1, call t) in statement order:
+// plain/mvn: P normals; constrained: per sweep P-1 uniforms (r.flat) then P
+// uniforms (r.tnorm by inverse CDF on one uniform -- the reference's own
+// truncated-normal generator lives in its absent RNG library).
+#pragma once
+
+#include "philox.cuh"
+#include "specfun.cuh"
+
+namespace bl {
+
+enum BetaDraw { kBetaConstrained = 0, kBetaPlain = 1, kBetaMvn = 2 };
+
+// A = U'U in place (upper triangle of column-major A, ld = P); strict lower part zeroed.
+// Returns false through *ok when a pivot is not positive.
+__device__ inline void cta_chol_upper(double *A, int P, int *ok)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = 0; j < P; ++j) {
+        __syncthreads();
+        double d = A[j + (size_t)P * j];
+        if (!(d > 0.0)) { if (tid == 0) *ok = 0; __syncthreads(); return; }
+        d = sqrt(d);
+        __syncthreads();
+        for (int k = j + tid; k < P; k += nt) A[j + (size_t)P * k] = k == j ? d : A[j + (size_t)P * k] / d;
+        __syncthreads();
+        int m = P - j - 1;
+        for (int e = tid; e < m * m; e += nt) {
+            int i = j + 1 + e % m, k = j + 1 + e / m;
+            if (i <= k) A[i + (size_t)P * k] = fma(-A[j + (size_t)P * i], A[j + (size_t)P * k], A[i + (size_t)P * k]);
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < P * P; e += nt) {
+        int i = e % P, k = e / P;
+        if (i > k) A[e] = 0.0;
+    }
+    __syncthreads();
+}
+
+// A = LL' in place (lower triangle); strict upper part zeroed.
+__device__ inline void cta_chol_lower(double *A, int P, int *ok)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = 0; j < P; ++j) {
+        __syncthreads();
+        double d = A[j + (size_t)P * j];
+        if (!(d > 0.0)) { if (tid == 0) *ok = 0; __syncthreads(); return; }
+        d = sqrt(d);
+        __syncthreads();
+        for (int i = j + tid; i < P; i += nt) A[i + (size_t)P * j] = i == j ? d : A[i + (size_t)P * j] / d;
+        __syncthreads();
+        int m = P - j - 1;
+        for (int e = tid; e < m * m; e += nt) {
+            int i = j + 1 + e % m, k = j + 1 + e / m;
+            if (i >= k) A[i + (size_t)P * k] = fma(-A[i + (size_t)P * j], A[k + (size_t)P * j], A[i + (size_t)P * k]);
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < P * P; e += nt) {
+        int i = e % P, k = e / P;
+        if (i < k) A[e] = 0.0;
+    }
+    __syncthreads();
+}
+
+// x <- (U'U)^-1 x for ncol right-hand sides (columns of X, ld = P): one thread per
+// column, no synchronisation inside.
+__device__ inline void cta_solve_utu(const double *U, double *X, int P, int ncol)
+{
+    for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+        double *x = X + (size_t)P * c;
+        for (int i = 0; i < P; ++i) {
+            double s = x[i];
+            for (int k = 0; k < i; ++k) s = fma(-U[k + (size_t)P * i], x[k], s);
+            x[i] = s / U[i + (size_t)P * i];
+        }
+        for (int i = P - 1; i >= 0; --i) {
+            double s = x[i];
+            for (int k = i + 1; k < P; ++k) s = fma(-U[i + (size_t)P * k], x[k], s);
+            x[i] = s / U[i + (size_t)P * i];
+        }
+    }
+    __syncthreads();
+}
+
+// Warp-cooperative single right-hand side solves (lane-parallel dot products).
+__device__ inline double warp_sum(double v)
+{
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// x <- U^-T x (forward), one warp.
+__device__ inline void warp_solve_ut(const double *U, double *x, int P, int lane)
+{
+    for (int i = 0; i < P; ++i) {
+        double s = 0.0;
+        for (int k = lane; k < i; k += 32) s = fma(U[k + (size_t)P * i], x[k], s);
+        s = warp_sum(s);
+        if (lane == 0) x[i] = (x[i] - s) / U[i + (size_t)P * i];
+        __syncwarp();
+    }
+}
+
+// x <- U^-1 x (backward), one warp.
+__device__ inline void warp_solve_u(const double *U, double *x, int P, int lane)
+{
+    for (int i = P - 1; i >= 0; --i) {
+        double s = 0.0;
+        for (int k = i + 1 + lane; k < P; k += 32) s = fma(U[i + (size_t)P * k], x[k], s);
+        s = warp_sum(s);
+        if (lane == 0) x[i] = (x[i] - s) / U[i + (size_t)P * i];
+        __syncwarp();
+    }
+}
+
+// x <- L^-1 x (forward, lower), one warp.
+__device__ inline void warp_solve_l(const double *L, double *x, int P, int lane)
+{
+    for (int i = 0; i < P; ++i) {
+        double s = 0.0;
+        for (int k = lane; k < i; k += 32) s = fma(L[i + (size_t)P * k], x[k], s);
+        s = warp_sum(s);
+        if (lane == 0) x[i] = (x[i] - s) / L[i + (size_t)P * i];
+        __syncwarp();
+    }
+}
+
+// Truncated N(0,1) on (a, b) by inverse CDF on one uniform, evaluated on the tail
+// that keeps precision (same construction as the oracle's pgo_tnorm).
+__device__ inline double tnorm_std(double a, double b, double u)
+{
+    double z;
+    if (a >= 0.0 || (a > -INFINITY && -a < b)) {
+        double qa = isinf(a) ? 1.0 : 0.5 * erfc(a * kSqrt1_2);
+        double qb = isinf(b) ? 0.0 : 0.5 * erfc(b * kSqrt1_2);
+        double q = qa - u * (qa - qb);
+        z = q <= 0.0 ? INFINITY : q >= 1.0 ? -INFINITY : -normcdfinv(q);
+    } else {
+        double pa = isinf(a) ? 0.0 : 0.5 * erfc(-a * kSqrt1_2);
+        double pb = isinf(b) ? 1.0 : 0.5 * erfc(-b * kSqrt1_2);
+        double p = pa + u * (pb - pa);
+        z = p <= 0.0 ? -INFINITY : p >= 1.0 ? INFINITY : normcdfinv(p);
+    }
+    if (z < a) z = a;
+    if (z > b) z = b;
+    return z;
+}
+
+// One beta draw.  Workspace (all column-major, ld = P):
+//   A  [P*P]  in: PP (posterior precision, full symmetric)   -> U
+//   B  [P*P]  scratch: S = PP^-1 -> L                        (constrained, mvn)
+//   v  [4*P]  scratch vectors
+// rhs = bP (precision-weighted mean), beta_prev (constrained only), beta_out.
+__device__ inline void cta_beta_draw(int mode, double *A, double *B, double *v, const double *rhs,
+                                     const double *beta_prev, double *beta_out, int P,
+                                     uint64_t seed, uint32_t call, int *status)
+{
+    __shared__ int ok;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) ok = 1;
+    __syncthreads();
+    cta_chol_upper(A, P, &ok);
+    if (!ok) { if (tid == 0) *status = 1; return; }
+    double *mP = v, *z = v + P, *e = v + 2 * P;
+    PhiloxSource src;
+    src.open(seed, 0xFFFFFFFFFFFFFFFFull, call);
+
+    if (mode == kBetaPlain) {
+        if (tid < 32) {
+            if (lane == 0)
+                for (int i = 0; i < P; ++i) e[i] = src.norm();
+            for (int i = lane; i < P; i += 32) mP[i] = rhs[i];
+            __syncwarp();
+            warp_solve_ut(A, mP, P, lane);
+            warp_solve_u(A, mP, P, lane);
+            warp_solve_u(A, e, P, lane);
+            for (int i = lane; i < P; i += 32) beta_out[i] = e[i] + mP[i];
+        }
+        __syncthreads();
+        return;
+    }
+
+    // S = PP^-1 by solving against the identity (Logit.hpp:338-347; Normal.hpp:106-107)
+    for (int k = tid; k < P * P; k += blockDim.x) B[k] = (k % P == k / P) ? 1.0 : 0.0;
+    __syncthreads();
+    cta_solve_utu(A, B, P, P);
+
+    if (mode == kBetaMvn) {
+        // mean = V b1 ; lower = chol(V) ; draw = mean + lower * N(0,I)
+        for (int a = tid; a < P; a += blockDim.x) {
+            double m = 0.0;
+            for (int b = 0; b < P; ++b) m = fma(B[a + (size_t)P * b], rhs[b], m);
+            mP[a] = m;
+        }
+        __syncthreads();
+        cta_chol_lower(B, P, &ok);
+        if (!ok) { if (tid == 0) *status = 2; return; }
+        if (tid == 0)
+            for (int i = 0; i < P; ++i) e[i] = src.norm();
+        __syncthreads();
+        for (int a = tid; a < P; a += blockDim.x) {
+            double s = 0.0;
+            for (int b = 0; b <= a; ++b) s = fma(B[a + (size_t)P * b], e[b], s);
+            beta_out[a] = mP[a] + s;
+        }
+        __syncthreads();
+        return;
+    }
+
+    // constrained coordinate-wise draw (Logit.hpp:349-399)
+    cta_chol_lower(B, P, &ok);
+    if (!ok) { if (tid == 0) *status = 2; return; }
+    const double *L = B;
+    if (tid < 32) {
+        double *beta = v + 3 * P;
+        for (int i = lane; i < P; i += 32) mP[i] = rhs[i];
+        __syncwarp();
+        warp_solve_ut(A, mP, P, lane);
+        warp_solve_u(A, mP, P, lane);
+        for (int i = lane; i < P; i += 32) {
+            z[i] = beta_prev[i] - mP[i];
+            beta[i] = beta_prev[i];
+        }
+        __syncwarp();
+        warp_solve_l(L, z, P, lane);
+        // the permutation lives in the e[] scratch as ints
+        int *is = (int *)e;
+        for (int i = lane; i < P; i += 32) is[i] = i;
+        __syncwarp();
+        for (int k = 0; k < P; ++k) {
+            // every lane draws (so all 32 copies of the stream state stay in step); lane 0 swaps
+            for (int i = 0; i < P - 1; ++i) {
+                double f = (double)i + ((double)P - (double)i) * src.unif();       // r.flat(i, P)
+                unsigned t = (unsigned)f;
+                if (t > (unsigned)(P - 1)) t = (unsigned)(P - 1);
+                if (lane == 0) { int tmp = is[i]; is[i] = is[t]; is[t] = tmp; }
+            }
+            __syncwarp();
+            for (int i = 0; i < P; ++i) {
+                int c = is[i];
+                double z1 = z[c];
+                double cmin = -INFINITY, cmax = INFINITY;
+                for (int j = c + lane; j < P - 1; j += 32) {
+                    double l1 = L[j + (size_t)P * c];
+                    double c1 = z1 - beta[j] / l1;
+                    if (l1 > 0.0 && c1 > cmin) cmin = c1;
+                    else if (l1 < 0.0 && c1 < cmax) cmax = c1;
+                }
+                for (int o = 16; o; o >>= 1) {
+                    double a = __shfl_xor_sync(0xffffffffu, cmin, o);
+                    double b = __shfl_xor_sync(0xffffffffu, cmax, o);
+                    if (a > cmin) cmin = a;
+                    if (b < cmax) cmax = b;
+                }
+                double u = src.unif();                 // every lane keeps the same stream state
+                double z2 = tnorm_std(cmin, cmax, u);
+                double dz = z2 - z1;
+                for (int j = c + lane; j < P; j += 32) beta[j] = fma(L[j + (size_t)P * c], dz, beta[j]);
+                if (lane == 0) z[c] = z2;
+                __syncwarp();
+            }
+        }
+        for (int i = lane; i < P; i += 32) beta_out[i] = beta[i];
+    }
+    __syncthreads();
+}
+
+}  // namespace bl

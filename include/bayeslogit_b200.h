@@ -155,6 +155,46 @@ int bl_rpg_sp_tape(double *x, const double *h, const double *z, int64_t num, int
 int bl_rpg_hybrid_tape(double *x, const double *h, const double *z, int64_t num,
                        const bl_tape *tape, int *trace);
 
+/* ---- Gibbs sweeps --------------------------------------------------------- */
+
+/* flags */
+#define BL_GIBBS_PLAIN_BETA 1   /* unconstrained beta ~ N(PP^-1 bP, PP^-1) (Logit.hpp:291-320) instead of
+                                   the constrained coordinate-wise draw the reference calls (:322-400) */
+#define BL_GIBBS_NO_W 2         /* do not return the omega chains (w may be NULL) */
+
+/* `gibbs` with an explicit seed and flags; host pointers, layouts as `gibbs`. */
+int bl_logit_gibbs(double *w, double *beta, const double *y, const double *tX, const double *n,
+                   const double *m0, const double *P0, int N, int P, int samp, int burn,
+                   uint64_t seed, int flags);
+/* `mult_gibbs` with an explicit seed (no duplicate-row merge: call mult_combine first). */
+int bl_mlogit_gibbs(double *w, double *beta, const double *ty, const double *tX, const double *n,
+                    const double *m0, const double *P0, int N, int P, int J, int samp, int burn,
+                    uint64_t seed, int flags);
+/* Negative-binomial regression sweep with fixed dispersion d (the reference has no C entry
+ * for it: Code/R/NBPG-logmean.R:13-34,77-106).  y: counts [N]; beta: P x samp; w_last: N or NULL. */
+int bl_nb_gibbs(double *w_last, double *beta, const double *y, const double *tX, double d,
+                const double *m0, const double *P0, int N, int P, int samp, uint64_t seed);
+
+/* Device-resident shards (all pointers DEVICE pointers; one process per GPU).  Rank r holds
+ * observations [obs0, obs0+N) of the global data set; with a communicator (bl_comm_init) the
+ * ranks exchange one all-reduce of P*P+P doubles per beta draw and produce the same chain a
+ * single GPU would. */
+int bl_logit_gibbs_dev(double *w, double *beta, const double *y, const double *tX, const double *n,
+                       const double *m0, const double *P0, int64_t N, int P, int samp, int burn,
+                       uint64_t seed, int flags, uint64_t obs0, void *stream);
+int bl_mlogit_gibbs_dev(double *w, double *beta, const double *ty, const double *tX, const double *n,
+                        const double *m0, const double *P0, int64_t N, int P, int J, int samp, int burn,
+                        uint64_t seed, int flags, uint64_t obs0, void *stream);
+int bl_nb_gibbs_dev(double *w_last, double *beta, const double *y, const double *tX, double d,
+                    const double *m0, const double *P0, int64_t N, int P, int samp, uint64_t seed,
+                    uint64_t obs0, void *stream);
+
+/* Communicator over NCCL (NVLink/NVSwitch): rank 0 creates a 128-byte id, the host side
+ * broadcasts it (e.g. torch.distributed), every rank calls bl_comm_init. */
+int bl_comm_unique_id(void *out128);
+int bl_comm_init(const void *id128, int rank, int world);
+int bl_comm_destroy(void);
+
 /* Component probes for parity tests (host pointers, elementwise). */
 int bl_probe_pg_moments(double *m1, double *m2, const double *b, const double *z, int64_t num);
 int bl_probe_v_eval(double *v, const double *y, int64_t num);

@@ -64,6 +64,11 @@ class Oracle:
             f.restype = C.c_double
         lib.pgb_v_eval.argtypes = [C.c_double]
         lib.pgb_v_eval.restype = C.c_double
+        if kind == "port":   # the Gibbs restatements exist only in the plain-C port
+            vp, ci, u64 = C.c_void_p, C.c_int, C.c_uint64
+            lib.pgb_logit_gibbs.argtypes = [vp] * 7 + [ci, ci, ci, ci, u64, ci, ci]
+            lib.pgb_mlogit_gibbs.argtypes = [vp] * 7 + [ci, ci, ci, ci, ci, u64, ci]
+            lib.pgb_nb_gibbs.argtypes = [vp, vp, vp, vp, C.c_double, vp, vp, ci, ci, ci, u64, ci]
 
     # -- stream helpers ------------------------------------------------------
     @staticmethod
@@ -137,6 +142,63 @@ class Oracle:
 
     def v_eval(self, y):
         return self.lib.pgb_v_eval(float(y))
+
+
+def _gibbs_port():
+    if not available("port"):
+        build(("port",))
+    return Oracle("port")
+
+
+def logit_gibbs(y, X, n, m0, P0, samp, burn, seed, constrained=True, nthreads=0):
+    """CPU restatement of Logit::gibbs (oracle/gibbs_oracle.c).  X: N x P row-major.
+    Returns (w [samp x N], beta [samp x P])."""
+    O = _gibbs_port()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    N, P = X.shape
+    y, n, m0 = _f64(y).ravel(), _f64(n).ravel(), _f64(m0).ravel()
+    P0c = np.asfortranarray(_f64(P0))
+    w, beta = np.zeros((samp, N)), np.zeros((samp, P))
+    st = O.lib.pgb_logit_gibbs(w.ctypes.data, beta.ctypes.data, y.ctypes.data, X.ctypes.data,
+                               n.ctypes.data, m0.ctypes.data, P0c.ctypes.data, N, P, samp, burn,
+                               int(seed), 1 if constrained else 0, nthreads)
+    if st:
+        raise RuntimeError("oracle logit_gibbs: precision not positive definite")
+    return w, beta
+
+
+def mlogit_gibbs(y, X, n, m0, P0, samp, burn, seed, nthreads=0):
+    """CPU restatement of MultLogit::gibbs.  y: N x (J-1).  Returns (w [samp x (J-1) x N],
+    beta [samp x (J-1) x P])."""
+    O = _gibbs_port()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    N, P = X.shape
+    U = y.shape[1]
+    n = _f64(n).ravel()
+    m0c, P0c = np.asfortranarray(_f64(m0)), np.asfortranarray(_f64(P0))
+    w, beta = np.zeros((samp, U, N)), np.zeros((samp, U, P))
+    st = O.lib.pgb_mlogit_gibbs(w.ctypes.data, beta.ctypes.data, y.ctypes.data, X.ctypes.data,
+                                n.ctypes.data, m0c.ctypes.data, P0c.ctypes.data, N, P, U + 1, samp, burn,
+                                int(seed), nthreads)
+    if st:
+        raise RuntimeError("oracle mlogit_gibbs: precision not positive definite")
+    return w, beta
+
+
+def nb_gibbs(y, X, d, m0, P0, samp, seed, nthreads=0):
+    """CPU restatement of the NB sweep with fixed d.  Returns (w_last [N], beta [samp x P])."""
+    O = _gibbs_port()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    N, P = X.shape
+    y, m0 = _f64(y).ravel(), _f64(m0).ravel()
+    P0c = np.asfortranarray(_f64(P0))
+    w, beta = np.zeros(N), np.zeros((samp, P))
+    st = O.lib.pgb_nb_gibbs(w.ctypes.data, beta.ctypes.data, y.ctypes.data, X.ctypes.data, float(d),
+                            m0.ctypes.data, P0c.ctypes.data, N, P, samp, int(seed), nthreads)
+    if st:
+        raise RuntimeError("oracle nb_gibbs: precision not positive definite")
+    return w, beta
 
 
 def make_tape(num, lu=0, le=0, ln=0, lg=0, g_shape=None, seed=0):

@@ -1,0 +1,140 @@
+"""GPU parity tests of the Gibbs sweeps against the CPU
+restatements in oracle/gibbs_oracle.c, through the C ABI.
+
+Engine and oracle share the stream contract (iteration t: omega_i from Philox
+(seed, obs i, call t), beta from (seed, obs 2^64-1, call t)), so for the same seed the
+two CHAINS must agree -- not just their distributions.  Tolerance CHAIN_REL = 1e-8 on beta
+and omega over tens of iterations: the per-draw bar is 1e-12, the Gram is an N-term sum
+evaluated in a different order on the device (relative 1e-13..1e-12), and the chain map
+amplifies that mildly from one iteration to the next.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import loader
+
+pytestmark = pytest.mark.gpu
+
+CHAIN_REL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def gapi(engine):
+    from bayeslogit_b200 import gibbs_api
+    return gibbs_api
+
+
+def synth_logit(N, P, seed, binomial=False):
+    rng = np.random.default_rng(seed)
+    X = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
+    bt = np.r_[np.abs(rng.normal(0, 0.4, P - 1)), -0.5]
+    p = 1 / (1 + np.exp(-X @ bt))
+    if binomial:
+        n = rng.integers(1, 6, N).astype(float)
+        y = rng.binomial(n.astype(int), p) / n
+    else:
+        n = np.ones(N)
+        y = (rng.random(N) < p).astype(float)
+    return X, y, n, bt
+
+
+def close(a, b, rel=CHAIN_REL):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+    assert np.all(np.isfinite(a)) and err.max() <= rel, float(err.max())
+
+
+@pytest.mark.parametrize("constrained", [False, True])
+@pytest.mark.parametrize("N,P,binomial", [(3000, 7, False), (1500, 64, False), (2000, 5, True), (700, 70, False)])
+def test_logit_chain_matches_oracle(gapi, constrained, N, P, binomial):
+    X, y, n, _ = synth_logit(N, P, 10 + P, binomial)
+    m0 = np.linspace(-0.1, 0.1, P)
+    P0 = 0.5 * np.eye(P) + 0.01
+    samp, burn = (12, 6) if P < 32 else (5, 3)
+    flags = 0 if constrained else gapi.PLAIN_BETA
+    w, b = gapi.logit_gibbs(y, X, n, m0, P0, samp, burn, seed=77, flags=flags)
+    wo, bo = loader.logit_gibbs(y, X, n, m0, P0, samp, burn, seed=77, constrained=constrained)
+    close(b, bo)
+    close(w, wo)
+    if constrained:
+        assert np.all(b[:, :-1] >= 0)
+
+
+def test_logit_burn_zero_and_no_w(gapi):
+    X, y, n, _ = synth_logit(1000, 4, 5)
+    P0 = np.eye(4)
+    w, b = gapi.logit_gibbs(y, X, n, np.zeros(4), P0, 6, 0, seed=3, flags=gapi.PLAIN_BETA)
+    wo, bo = loader.logit_gibbs(y, X, n, np.zeros(4), P0, 6, 0, seed=3, constrained=False)
+    close(b, bo); close(w, wo)
+    w2, b2 = gapi.logit_gibbs(y, X, n, np.zeros(4), P0, 6, 0, seed=3, flags=gapi.PLAIN_BETA, keep_w=False)
+    assert w2 is None and np.array_equal(b2, b)
+
+
+def test_mlogit_chain_matches_oracle(gapi):
+    rng = np.random.default_rng(4)
+    N, P, J = 2500, 6, 4
+    X = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
+    B = rng.normal(0, 0.7, (P, J - 1))
+    eta = np.c_[X @ B, np.zeros(N)]
+    pr = np.exp(eta); pr /= pr.sum(1, keepdims=True)
+    cat = (pr.cumsum(1) < rng.random(N)[:, None]).sum(1)
+    Y = np.eye(J)[cat][:, :J - 1]
+    m0 = rng.normal(0, 0.1, (P, J - 1))
+    P0 = np.stack([(0.3 + 0.1 * j) * np.eye(P) for j in range(J - 1)], axis=2)
+    w, b = gapi.mlogit_gibbs(Y, X, np.ones(N), m0, P0, 6, 3, seed=21)
+    wo, bo = loader.mlogit_gibbs(Y, X, np.ones(N), m0, P0, 6, 3, seed=21)
+    close(b, bo); close(w, wo)
+
+
+def test_nb_chain_matches_oracle(gapi):
+    rng = np.random.default_rng(6)
+    N, P, d = 2000, 5, 3.0
+    X = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
+    bt = np.array([0.9, -0.7, 0.6, 0.5, 2.6])          # counts 0..500: b = y + d spans Alt/SP/normal
+    mu = np.exp(X @ bt)
+    y = rng.negative_binomial(d, d / (mu + d)).astype(float)
+    assert (y + d > 170).any() and (y + d < 13).any()
+    w, b = gapi.nb_gibbs(y, X, d, np.zeros(P), 0.01 * np.eye(P), 6, seed=8)
+    wo, bo = loader.nb_gibbs(y, X, d, np.zeros(P), 0.01 * np.eye(P), 6, seed=8)
+    close(b, bo, 1e-7); close(w, wo, 1e-7)
+
+
+def test_em_matches_newton_mode(gapi):
+    """logit.EM (Logit.hpp:488-554): flat prior -> the MLE."""
+    X, y, n, _ = synth_logit(4000, 6, 9, binomial=True)
+    out = gapi.logit_EM(y, X, n, tol=1e-10, max_iter=200)
+    b = np.zeros(6)
+    for _ in range(60):
+        p = 1 / (1 + np.exp(-X @ b))
+        b = b + np.linalg.solve(X.T @ (X * (n * p * (1 - p))[:, None]), X.T @ (n * (y - p)))
+    assert out["iter"] < 200
+    assert np.allclose(out["beta"], b, rtol=1e-6, atol=1e-8)
+
+
+def test_dropin_logit_and_mlogit_wrappers(gapi, engine):
+    """The R-facing wrappers: combine first, then .C("gibbs") / .C("mult_gibbs")."""
+    X, y, n, bt = synth_logit(5000, 4, 12)
+    X = np.vstack([X, X[:50]]); y = np.r_[y, y[:50]]; n = np.r_[n, n[:50]]      # 50 duplicate rows
+    engine.set_seed(5)
+    out = gapi.logit(y, X, n, samp=300, burn=100, P0=0.01 * np.eye(4))
+    assert out["X"].shape == (5000, 4) and out["w"].shape == (300, 5000) and out["beta"].shape == (300, 4)
+    assert np.all(out["beta"][:, :-1] >= 0)                      # the reference's constrained draw
+    assert np.max(np.abs(out["beta"].mean(0) - bt)) < 0.2
+    engine.set_seed(5)
+    again = gapi.logit(y, X, n, samp=300, burn=100, P0=0.01 * np.eye(4))
+    assert np.array_equal(again["beta"], out["beta"])            # set.seed analogue
+    assert gapi.logit(np.array([2.0, 0.0]), np.eye(2)) == -1     # check.parameters
+    rng = np.random.default_rng(3)
+    N, P, J = 3000, 3, 3
+    Xm = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
+    B = rng.normal(0, 0.8, (P, J - 1))
+    eta = np.c_[Xm @ B, np.zeros(N)]
+    pr = np.exp(eta); pr /= pr.sum(1, keepdims=True)
+    cat = (pr.cumsum(1) < rng.random(N)[:, None]).sum(1)
+    Y = np.eye(J)[cat][:, :J - 1]
+    om = gapi.mlogit(Y, Xm, samp=200, burn=100, P0=np.stack([0.01 * np.eye(P)] * (J - 1), axis=2))
+    assert om["beta"].shape == (200, P, J - 1) and om["w"].shape == (200, N, J - 1)
+    assert np.max(np.abs(om["beta"].mean(0) - B)) < 0.3
