@@ -15,6 +15,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -75,15 +76,17 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
             int use_smem)
 {
     extern __shared__ double sm[];
+    const int ld = P | 1;                     // odd leading dimension: row and column walks both conflict-free
     double *A = use_smem ? sm : gwork;
-    double *B = A + (size_t)P * P;
-    double *v = B + (size_t)P * P;
+    double *B = A + (size_t)ld * P;
+    double *v = B + (size_t)ld * P;
     double *rhs = v + 4 * P;
-    for (int k = threadIdx.x; k < P * P; k += blockDim.x) A[k] = acc[k] + (P0 ? P0[k] : 0.0);
+    for (int k = threadIdx.x; k < P * P; k += blockDim.x)
+        A[k % P + (size_t)ld * (k / P)] = acc[k] + (P0 ? P0[k] : 0.0);
     for (int k = threadIdx.x; k < P; k += blockDim.x)
         rhs[k] = (base_rhs ? base_rhs[k] : 0.0) + (add_tail ? acc[(size_t)P * P + k] : 0.0);
     __syncthreads();
-    cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, seed, call, status);
+    cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status);
 }
 
 __global__ void k_matvec(double *out, const double *A, const double *x, int P)   // out = A x, col-major
@@ -103,14 +106,16 @@ namespace {
         if (e_ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e_); return 1; } \
     } while (0)
 
+// Stream-ordered scratch (cudaMallocAsync pool): no device-wide synchronisation per chain.
 struct DevMem {
     std::vector<void *> ptrs;
-    ~DevMem() { for (void *p : ptrs) cudaFree(p); }
+    cudaStream_t st = nullptr;
+    ~DevMem() { for (void *p : ptrs) cudaFreeAsync(p, st); }
     template <class T>
     cudaError_t get(T **p, size_t count)
     {
         void *q = nullptr;
-        cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+        cudaError_t e = cudaMallocAsync(&q, (count ? count : 1) * sizeof(T), st);
         if (e == cudaSuccess) { ptrs.push_back(q); *p = (T *)q; }
         return e;
     }
@@ -136,7 +141,7 @@ struct Sweep {
     {
         nt = cdiv(P, kGramTile);
         int tiles = nt * (nt + 1) / 2;
-        nslab = (int)std::min<int64_t>(std::max<int64_t>(1, 148 * 2 / tiles), std::max<int64_t>(1, N / kGramRows));
+        nslab = (int)std::min<int64_t>(std::max<int64_t>(1, 148 * 3 / tiles), std::max<int64_t>(1, N / (4 * kGramRows)));
         if (nslab < 1) nslab = 1;
         xtv_slabs = (int)std::min<int64_t>(148 * 2, std::max<int64_t>(1, N / 64));
         GB_CK(m.get(&psi, N));
@@ -144,11 +149,14 @@ struct Sweep {
         GB_CK(m.get(&acc, (size_t)P * P + P));
         GB_CK(m.get(&part, (size_t)tiles * nslab * kGramTile * kGramTile));
         GB_CK(m.get(&xtv_part, (size_t)xtv_slabs * P));
-        GB_CK(m.get(&gwork, 2 * (size_t)P * P + 5 * (size_t)P));
+        GB_CK(m.get(&gwork, 2 * (size_t)(P + 1) * P + 5 * (size_t)P));
         GB_CK(m.get(&status, 1));
         GB_CK(cudaMemsetAsync(status, 0, sizeof(int), st));
         GB_CK(cudaMemsetAsync(acc, 0, ((size_t)P * P + P) * sizeof(double), st));
-        beta_smem = (2 * (size_t)P * P + 5 * (size_t)P) * sizeof(double);
+        beta_smem = (2 * (size_t)(P | 1) * P + 5 * (size_t)P) * sizeof(double);
+        if (gram_smem_bytes(nt > 1) > 48 * 1024)
+            GB_CK(cudaFuncSetAttribute(k_gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)gram_smem_bytes(true)));
         use_smem = beta_smem <= 200 * 1024;
         if (use_smem && beta_smem > 48 * 1024)
             GB_CK(cudaFuncSetAttribute(k_beta_draw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem));
@@ -157,7 +165,7 @@ struct Sweep {
 
     void xbeta(double *out, const double *beta, const double *off, double off_scale, double shift = 0.0)
     {
-        int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (N + 7) / 8));
+        int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (N + 31) / 32));
         k_xbeta<<<grid, 256, P * sizeof(double), st>>>(out, tX, beta, off, off_scale, shift, N, P);
         count_launch();
     }
@@ -166,8 +174,8 @@ struct Sweep {
     void gram(const double *wv)
     {
         int tiles = nt * (nt + 1) / 2;
-        k_gram_partial<<<dim3(nslab, tiles), 256, 0, st>>>(part, tX, wv, N, P, nt);
-        k_gram_reduce<<<cdiv((int64_t)P * P, 256), 256, 0, st>>>(acc, nullptr, part, P, nt, nslab);
+        k_gram_partial<<<dim3(nslab, tiles), 256, gram_smem_bytes(nt > 1), st>>>(part, tX, wv, N, P, nt);
+        k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nslab);
         count_launch(2);
     }
 
@@ -221,6 +229,7 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
 {
     if (N <= 0 || P <= 0 || samp <= 0 || burn < 0) { err = "gibbs: bad dimensions"; return 1; }
     DevMem mem;
+    mem.st = st;
     Sweep s;
     s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX;
     if (s.init(mem, err)) return 1;
@@ -248,6 +257,9 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
 
     GB_CK(cudaMemsetAsync(beta_out, 0, sizeof(double) * (size_t)P * samp, st));
     if (keep_w) GB_CK(cudaMemsetAsync(w_out, 0, sizeof(double) * (size_t)N * samp, st));
+    const bool timing = getenv("BL_GIBBS_TIMING") != nullptr;
+    cudaEvent_t ev[6];
+    if (timing) for (auto &x : ev) cudaEventCreate(&x);
     uint32_t t = 0;
     for (int phase = 0; phase < 2; ++phase) {
         int iters = phase == 0 ? burn : samp;
@@ -255,12 +267,26 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
         double *wcur = keep_w ? w_out : s.w;
         s.xbeta(s.psi, bcur, nullptr, 0.0);
         for (int m = 1; m <= iters; ++m, ++t) {
+            const bool tm = timing && phase == 1 && m == iters;       // BL_GIBBS_TIMING=1: stage times
+            if (tm) cudaEventRecord(ev[0], st);
             cudaError_t e = launch_devroye_refill(wcur, shape, s.psi, N, StreamId{seed, obs0, t}, st);
             if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
+            if (tm) cudaEventRecord(ev[1], st);
             s.gram(wcur);
+            if (tm) cudaEventRecord(ev[2], st);
             if (s.allreduce(false, err)) return 1;
+            if (tm) cudaEventRecord(ev[3], st);
             s.beta_draw(mode, P0, bP, false, bprev, bcur, seed, t);
+            if (tm) cudaEventRecord(ev[4], st);
             s.xbeta(s.psi, bcur, nullptr, 0.0);
+            if (tm) {
+                cudaEventRecord(ev[5], st);
+                cudaEventSynchronize(ev[5]);
+                float d[5];
+                for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&d[k], ev[k], ev[k + 1]);
+                fprintf(stderr, "[bl gibbs timing, us] draw %.1f gram %.1f allreduce %.1f beta %.1f xbeta %.1f\n",
+                        d[0] * 1e3, d[1] * 1e3, d[2] * 1e3, d[3] * 1e3, d[4] * 1e3);
+            }
             if (phase == 1) {
                 bprev = bcur;
                 if (m < iters) { bcur += P; if (keep_w) wcur += N; }
@@ -284,6 +310,7 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
     if (N <= 0 || P <= 0 || J < 2 || samp <= 0 || burn < 0) { err = "mult_gibbs: bad dimensions"; return 1; }
     const int U = J - 1;
     DevMem mem;
+    mem.st = st;
     Sweep s;
     s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX;
     if (s.init(mem, err)) return 1;
@@ -350,6 +377,7 @@ int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const doub
 {
     if (N <= 0 || P <= 0 || samp <= 0 || !(d > 0)) { err = "nb_gibbs: bad arguments"; return 1; }
     DevMem mem;
+    mem.st = st;
     Sweep s;
     s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX;
     if (s.init(mem, err)) return 1;
@@ -407,18 +435,19 @@ k_em_solve(const double *__restrict__ acc, const double *__restrict__ rhs, doubl
 {
     extern __shared__ double sm[];
     __shared__ int ok;
+    const int ld = P | 1;
     double *A = use_smem ? sm : gwork;
-    double *x = A + (size_t)P * P;
-    for (int k = threadIdx.x; k < P * P; k += blockDim.x) A[k] = acc[k];
+    double *x = A + (size_t)ld * P;
+    for (int k = threadIdx.x; k < P * P; k += blockDim.x) A[k % P + (size_t)ld * (k / P)] = acc[k];
     for (int k = threadIdx.x; k < P; k += blockDim.x) x[k] = rhs[k];
     if (threadIdx.x == 0) ok = 1;
     __syncthreads();
-    cta_chol_upper(A, P, &ok);
+    cta_chol_upper(A, P, ld, &ok);
     if (!ok) { if (threadIdx.x == 0) *status = 1; return; }
     if (threadIdx.x < 32) {
         int lane = threadIdx.x;
-        warp_solve_ut(A, x, P, lane);
-        warp_solve_u(A, x, P, lane);
+        warp_solve_ut(A, x, P, ld, lane);
+        warp_solve_u(A, x, P, ld, lane);
         double d = 0.0;
         for (int i = lane; i < P; i += 32) {
             d = fmax(d, fabs(x[i] - beta[i]));
@@ -434,6 +463,7 @@ int logit_em_device(double *beta, const double *y, const double *tX, const doubl
 {
     if (N <= 0 || P <= 0) { err = "EM: bad dimensions"; return 1; }
     DevMem mem;
+    mem.st = st;
     Sweep s;
     s.N = N; s.P = P; s.st = st; s.tX = tX;
     if (s.init(mem, err)) return 1;
@@ -447,7 +477,7 @@ int logit_em_device(double *beta, const double *y, const double *tX, const doubl
     k_xtv_reduce<<<cdiv(P, 128), 128, 0, st>>>(bP, s.acc + (size_t)P * P, nullptr, s.xtv_part, P, 0);
     count_launch();
     GB_CK(cudaMemsetAsync(beta, 0, sizeof(double) * P, st));
-    size_t smem = ((size_t)P * P + P) * sizeof(double);
+    size_t smem = ((size_t)(P | 1) * P + P) * sizeof(double);
     bool use_smem = smem <= 200 * 1024;
     if (use_smem && smem > 48 * 1024)
         GB_CK(cudaFuncSetAttribute(k_em_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -11,8 +11,8 @@
 //   mvn          Normal::set_from_likelihood + draw               Normal.hpp:98-131
 // Variates come from the stream (seed, obs 2^64-1, call t) in statement order:
 // plain/mvn: P normals; constrained: per sweep P-1 uniforms (r.flat) then P
-// uniforms (r.tnorm by inverse CDF on one uniform -- the reference's own
-// truncated-normal generator lives in its absent RNG library).
+// truncated normals (r.tnorm: inverse CDF on one uniform, Robert's rejection samplers
+// in the far tails -- the reference's own generator lives in its absent RNG library).
 #pragma once
 
 #include "philox.cuh"
@@ -24,72 +24,73 @@ enum BetaDraw { kBetaConstrained = 0, kBetaPlain = 1, kBetaMvn = 2 };
 
 // A = U'U in place (upper triangle of column-major A, ld = P); strict lower part zeroed.
 // Returns false through *ok when a pivot is not positive.
-__device__ inline void cta_chol_upper(double *A, int P, int *ok)
+__device__ inline void cta_chol_upper(double *A, int P, int ld, int *ok)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int j = 0; j < P; ++j) {
         __syncthreads();
-        double d = A[j + (size_t)P * j];
+        double d = A[j + (size_t)ld * j];
         if (!(d > 0.0)) { if (tid == 0) *ok = 0; __syncthreads(); return; }
         d = sqrt(d);
         __syncthreads();
-        for (int k = j + tid; k < P; k += nt) A[j + (size_t)P * k] = k == j ? d : A[j + (size_t)P * k] / d;
+        for (int k = j + tid; k < P; k += nt) A[j + (size_t)ld * k] = k == j ? d : A[j + (size_t)ld * k] / d;
         __syncthreads();
-        int m = P - j - 1;
-        for (int e = tid; e < m * m; e += nt) {
-            int i = j + 1 + e % m, k = j + 1 + e / m;
-            if (i <= k) A[i + (size_t)P * k] = fma(-A[j + (size_t)P * i], A[j + (size_t)P * k], A[i + (size_t)P * k]);
+        // trailing update on a 16-wide thread grid (no integer division in the index math)
+        for (int k = j + 1 + (tid >> 4); k < P; k += nt >> 4) {
+            double ujk = A[j + (size_t)ld * k];
+            for (int i = j + 1 + (tid & 15); i <= k; i += 16)
+                A[i + (size_t)ld * k] = fma(-A[j + (size_t)ld * i], ujk, A[i + (size_t)ld * k]);
         }
     }
     __syncthreads();
     for (int e = tid; e < P * P; e += nt) {
         int i = e % P, k = e / P;
-        if (i > k) A[e] = 0.0;
+        if (i > k) A[i + (size_t)ld * k] = 0.0;
     }
     __syncthreads();
 }
 
 // A = LL' in place (lower triangle); strict upper part zeroed.
-__device__ inline void cta_chol_lower(double *A, int P, int *ok)
+__device__ inline void cta_chol_lower(double *A, int P, int ld, int *ok)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int j = 0; j < P; ++j) {
         __syncthreads();
-        double d = A[j + (size_t)P * j];
+        double d = A[j + (size_t)ld * j];
         if (!(d > 0.0)) { if (tid == 0) *ok = 0; __syncthreads(); return; }
         d = sqrt(d);
         __syncthreads();
-        for (int i = j + tid; i < P; i += nt) A[i + (size_t)P * j] = i == j ? d : A[i + (size_t)P * j] / d;
+        for (int i = j + tid; i < P; i += nt) A[i + (size_t)ld * j] = i == j ? d : A[i + (size_t)ld * j] / d;
         __syncthreads();
-        int m = P - j - 1;
-        for (int e = tid; e < m * m; e += nt) {
-            int i = j + 1 + e % m, k = j + 1 + e / m;
-            if (i >= k) A[i + (size_t)P * k] = fma(-A[i + (size_t)P * j], A[k + (size_t)P * j], A[i + (size_t)P * k]);
+        for (int k = j + 1 + (tid >> 4); k < P; k += nt >> 4) {
+            double lkj = A[k + (size_t)ld * j];
+            for (int i = k + (tid & 15); i < P; i += 16)
+                A[i + (size_t)ld * k] = fma(-A[i + (size_t)ld * j], lkj, A[i + (size_t)ld * k]);
         }
     }
     __syncthreads();
     for (int e = tid; e < P * P; e += nt) {
         int i = e % P, k = e / P;
-        if (i < k) A[e] = 0.0;
+        if (i < k) A[i + (size_t)ld * k] = 0.0;
     }
     __syncthreads();
 }
 
 // x <- (U'U)^-1 x for ncol right-hand sides (columns of X, ld = P): one thread per
 // column, no synchronisation inside.
-__device__ inline void cta_solve_utu(const double *U, double *X, int P, int ncol)
+__device__ inline void cta_solve_utu(const double *U, double *X, int P, int ld, int ncol)
 {
     for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
-        double *x = X + (size_t)P * c;
+        double *x = X + (size_t)ld * c;
         for (int i = 0; i < P; ++i) {
             double s = x[i];
-            for (int k = 0; k < i; ++k) s = fma(-U[k + (size_t)P * i], x[k], s);
-            x[i] = s / U[i + (size_t)P * i];
+            for (int k = 0; k < i; ++k) s = fma(-U[k + (size_t)ld * i], x[k], s);
+            x[i] = s / U[i + (size_t)ld * i];
         }
         for (int i = P - 1; i >= 0; --i) {
             double s = x[i];
-            for (int k = i + 1; k < P; ++k) s = fma(-U[i + (size_t)P * k], x[k], s);
-            x[i] = s / U[i + (size_t)P * i];
+            for (int k = i + 1; k < P; ++k) s = fma(-U[i + (size_t)ld * k], x[k], s);
+            x[i] = s / U[i + (size_t)ld * i];
         }
     }
     __syncthreads();
@@ -103,45 +104,68 @@ __device__ inline double warp_sum(double v)
 }
 
 // x <- U^-T x (forward), one warp.
-__device__ inline void warp_solve_ut(const double *U, double *x, int P, int lane)
+__device__ inline void warp_solve_ut(const double *U, double *x, int P, int ld, int lane)
 {
     for (int i = 0; i < P; ++i) {
         double s = 0.0;
-        for (int k = lane; k < i; k += 32) s = fma(U[k + (size_t)P * i], x[k], s);
+        for (int k = lane; k < i; k += 32) s = fma(U[k + (size_t)ld * i], x[k], s);
         s = warp_sum(s);
-        if (lane == 0) x[i] = (x[i] - s) / U[i + (size_t)P * i];
+        if (lane == 0) x[i] = (x[i] - s) / U[i + (size_t)ld * i];
         __syncwarp();
     }
 }
 
 // x <- U^-1 x (backward), one warp.
-__device__ inline void warp_solve_u(const double *U, double *x, int P, int lane)
+__device__ inline void warp_solve_u(const double *U, double *x, int P, int ld, int lane)
 {
     for (int i = P - 1; i >= 0; --i) {
         double s = 0.0;
-        for (int k = i + 1 + lane; k < P; k += 32) s = fma(U[i + (size_t)P * k], x[k], s);
+        for (int k = i + 1 + lane; k < P; k += 32) s = fma(U[i + (size_t)ld * k], x[k], s);
         s = warp_sum(s);
-        if (lane == 0) x[i] = (x[i] - s) / U[i + (size_t)P * i];
+        if (lane == 0) x[i] = (x[i] - s) / U[i + (size_t)ld * i];
         __syncwarp();
     }
 }
 
 // x <- L^-1 x (forward, lower), one warp.
-__device__ inline void warp_solve_l(const double *L, double *x, int P, int lane)
+__device__ inline void warp_solve_l(const double *L, double *x, int P, int ld, int lane)
 {
     for (int i = 0; i < P; ++i) {
         double s = 0.0;
-        for (int k = lane; k < i; k += 32) s = fma(L[i + (size_t)P * k], x[k], s);
+        for (int k = lane; k < i; k += 32) s = fma(L[i + (size_t)ld * k], x[k], s);
         s = warp_sum(s);
-        if (lane == 0) x[i] = (x[i] - s) / L[i + (size_t)P * i];
+        if (lane == 0) x[i] = (x[i] - s) / L[i + (size_t)ld * i];
         __syncwarp();
     }
 }
 
-// Truncated N(0,1) on (a, b) by inverse CDF on one uniform, evaluated on the tail
-// that keeps precision (same construction as the oracle's pgo_tnorm).
-__device__ inline double tnorm_std(double a, double b, double u)
+// Truncated N(0,1) on (a, b); same construction as the oracle's pgo_tnorm (the reference's
+// RNG::tnorm lives in its absent library).  Far tails (a >= 4, or b <= -4 mirrored) use the
+// rejection samplers of Robert (1995): uniform proposal on a narrow interval ((U U)+),
+// translated exponential otherwise ((E [U])+); elsewhere inverse CDF on one uniform,
+// evaluated on the tail that keeps precision.
+__device__ inline double tnorm_tail(PhiloxSource &s, double a, double b)
 {
+    if (b < INFINITY && (b - a) * a < 1.0) {
+        for (;;) {
+            double z = a + (b - a) * s.unif();
+            if (s.unif() < exp(0.5 * (a * a - z * z))) return z;
+        }
+    }
+    double astar = 0.5 * (a + sqrt(a * a + 4.0));
+    for (;;) {
+        double z = a + s.expon() / astar;
+        if (z > b) continue;
+        if (s.unif() < exp(-0.5 * (z - astar) * (z - astar))) return z;
+    }
+}
+
+__device__ inline double tnorm_std(PhiloxSource &s, double a, double b)
+{
+    if (!(a < b)) return a;
+    if (b <= -4.0) return -tnorm_tail(s, -b, -a);
+    if (a >= 4.0) return tnorm_tail(s, a, b);
+    double u = s.unif();
     double z;
     if (a >= 0.0 || (a > -INFINITY && -a < b)) {
         double qa = isinf(a) ? 1.0 : 0.5 * erfc(a * kSqrt1_2);
@@ -159,20 +183,32 @@ __device__ inline double tnorm_std(double a, double b, double u)
     return z;
 }
 
+// k-th normal of the beta stream (seed, obs 2^64-1, call): a normal always takes three
+// words, so the k-th one starts at word 3k -- counter-based generation lets every lane
+// jump straight to its own.
+__device__ inline double stream_normal(uint64_t seed, uint32_t call, int k)
+{
+    PhiloxSource s;
+    s.open(seed, 0xFFFFFFFFFFFFFFFFull, call);
+    s.blk = (uint32_t)(3 * k) >> 2;
+    for (int skip = (3 * k) & 3; skip > 0; --skip) s.word();
+    return s.norm();
+}
+
 // One beta draw.  Workspace (all column-major, ld = P):
 //   A  [P*P]  in: PP (posterior precision, full symmetric)   -> U
 //   B  [P*P]  scratch: S = PP^-1 -> L                        (constrained, mvn)
 //   v  [4*P]  scratch vectors
 // rhs = bP (precision-weighted mean), beta_prev (constrained only), beta_out.
 __device__ inline void cta_beta_draw(int mode, double *A, double *B, double *v, const double *rhs,
-                                     const double *beta_prev, double *beta_out, int P,
+                                     const double *beta_prev, double *beta_out, int P, int ld,
                                      uint64_t seed, uint32_t call, int *status)
 {
     __shared__ int ok;
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) ok = 1;
     __syncthreads();
-    cta_chol_upper(A, P, &ok);
+    cta_chol_upper(A, P, ld, &ok);
     if (!ok) { if (tid == 0) *status = 1; return; }
     double *mP = v, *z = v + P, *e = v + 2 * P;
     PhiloxSource src;
@@ -180,13 +216,12 @@ __device__ inline void cta_beta_draw(int mode, double *A, double *B, double *v, 
 
     if (mode == kBetaPlain) {
         if (tid < 32) {
-            if (lane == 0)
-                for (int i = 0; i < P; ++i) e[i] = src.norm();
+            for (int i = lane; i < P; i += 32) e[i] = stream_normal(seed, call, i);
             for (int i = lane; i < P; i += 32) mP[i] = rhs[i];
             __syncwarp();
-            warp_solve_ut(A, mP, P, lane);
-            warp_solve_u(A, mP, P, lane);
-            warp_solve_u(A, e, P, lane);
+            warp_solve_ut(A, mP, P, ld, lane);
+            warp_solve_u(A, mP, P, ld, lane);
+            warp_solve_u(A, e, P, ld, lane);
             for (int i = lane; i < P; i += 32) beta_out[i] = e[i] + mP[i];
         }
         __syncthreads();
@@ -194,26 +229,25 @@ __device__ inline void cta_beta_draw(int mode, double *A, double *B, double *v, 
     }
 
     // S = PP^-1 by solving against the identity (Logit.hpp:338-347; Normal.hpp:106-107)
-    for (int k = tid; k < P * P; k += blockDim.x) B[k] = (k % P == k / P) ? 1.0 : 0.0;
+    for (int k = tid; k < P * P; k += blockDim.x) B[k % P + (size_t)ld * (k / P)] = (k % P == k / P) ? 1.0 : 0.0;
     __syncthreads();
-    cta_solve_utu(A, B, P, P);
+    cta_solve_utu(A, B, P, ld, P);
 
     if (mode == kBetaMvn) {
         // mean = V b1 ; lower = chol(V) ; draw = mean + lower * N(0,I)
         for (int a = tid; a < P; a += blockDim.x) {
             double m = 0.0;
-            for (int b = 0; b < P; ++b) m = fma(B[a + (size_t)P * b], rhs[b], m);
+            for (int b = 0; b < P; ++b) m = fma(B[a + (size_t)ld * b], rhs[b], m);
             mP[a] = m;
         }
         __syncthreads();
-        cta_chol_lower(B, P, &ok);
+        cta_chol_lower(B, P, ld, &ok);
         if (!ok) { if (tid == 0) *status = 2; return; }
-        if (tid == 0)
-            for (int i = 0; i < P; ++i) e[i] = src.norm();
+        for (int i = tid; i < P; i += blockDim.x) e[i] = stream_normal(seed, call, i);
         __syncthreads();
         for (int a = tid; a < P; a += blockDim.x) {
             double s = 0.0;
-            for (int b = 0; b <= a; ++b) s = fma(B[a + (size_t)P * b], e[b], s);
+            for (int b = 0; b <= a; ++b) s = fma(B[a + (size_t)ld * b], e[b], s);
             beta_out[a] = mP[a] + s;
         }
         __syncthreads();
@@ -221,21 +255,21 @@ __device__ inline void cta_beta_draw(int mode, double *A, double *B, double *v, 
     }
 
     // constrained coordinate-wise draw (Logit.hpp:349-399)
-    cta_chol_lower(B, P, &ok);
+    cta_chol_lower(B, P, ld, &ok);
     if (!ok) { if (tid == 0) *status = 2; return; }
     const double *L = B;
     if (tid < 32) {
         double *beta = v + 3 * P;
         for (int i = lane; i < P; i += 32) mP[i] = rhs[i];
         __syncwarp();
-        warp_solve_ut(A, mP, P, lane);
-        warp_solve_u(A, mP, P, lane);
+        warp_solve_ut(A, mP, P, ld, lane);
+        warp_solve_u(A, mP, P, ld, lane);
         for (int i = lane; i < P; i += 32) {
             z[i] = beta_prev[i] - mP[i];
             beta[i] = beta_prev[i];
         }
         __syncwarp();
-        warp_solve_l(L, z, P, lane);
+        warp_solve_l(L, z, P, ld, lane);
         // the permutation lives in the e[] scratch as ints
         int *is = (int *)e;
         for (int i = lane; i < P; i += 32) is[i] = i;
@@ -254,7 +288,7 @@ __device__ inline void cta_beta_draw(int mode, double *A, double *B, double *v, 
                 double z1 = z[c];
                 double cmin = -INFINITY, cmax = INFINITY;
                 for (int j = c + lane; j < P - 1; j += 32) {
-                    double l1 = L[j + (size_t)P * c];
+                    double l1 = L[j + (size_t)ld * c];
                     double c1 = z1 - beta[j] / l1;
                     if (l1 > 0.0 && c1 > cmin) cmin = c1;
                     else if (l1 < 0.0 && c1 < cmax) cmax = c1;
@@ -265,10 +299,9 @@ __device__ inline void cta_beta_draw(int mode, double *A, double *B, double *v, 
                     if (a > cmin) cmin = a;
                     if (b < cmax) cmax = b;
                 }
-                double u = src.unif();                 // every lane keeps the same stream state
-                double z2 = tnorm_std(cmin, cmax, u);
+                double z2 = tnorm_std(src, cmin, cmax);     // every lane keeps the same stream state
                 double dz = z2 - z1;
-                for (int j = c + lane; j < P; j += 32) beta[j] = fma(L[j + (size_t)P * c], dz, beta[j]);
+                for (int j = c + lane; j < P; j += 32) beta[j] = fma(L[j + (size_t)ld * c], dz, beta[j]);
                 if (lane == 0) z[c] = z2;
                 __syncwarp();
             }

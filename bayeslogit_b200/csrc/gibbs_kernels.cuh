@@ -36,43 +36,81 @@ k_xbeta(double *__restrict__ psi, const double *__restrict__ tX, const double *_
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < N; i += warps) {
-        const double *row = tX + i * P;
-        double s = 0.0;
-        for (int p = lane; p < P; p += 32) s = fma(row[p], sbeta[p], s);
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) psi[i] = (off ? s + off_scale * off[i] : s) + shift;
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    constexpr int R = 4;                       // rows per warp-trip: 4x the loads in flight
+    for (int64_t i0 = wid * R; i0 < N; i0 += warps * R) {
+        double s[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) s[r] = 0.0;
+        for (int p = lane; p < P; p += 32) {
+            double bp = sbeta[p];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (i0 + r < N) s[r] = fma(__ldg(tX + (i0 + r) * P + p), bp, s[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double v = s[r];
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && i0 + r < N) psi[i0 + r] = (off ? v + off_scale * off[i0 + r] : v) + shift;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------
-// Weighted Gram, SYRK-shaped: G += sum_i w_i x_i x_i' over a slab of rows.
-// CTA = 256 threads as a 16x16 grid of 4x4 register tiles -> one 64x64 output tile
-// (tile (bi,bj), bi <= bj, over blockIdx.y); row slabs over blockIdx.x.  Row chunks of
-// kGramRows rows are staged in shared memory (x and w*x panels) so each X element is
-// read from HBM once per output-tile row of the grid.  Per-CTA partial tiles go to
-// `part` and are summed in a fixed order by k_gram_reduce: deterministic, no atomics.
-// Bound by the FP64 pipe: 2*N*P^2 flops (P^2 + P when only the upper triangle counts).
+// Weighted Gram, SYRK-shaped: G = sum_i w_i x_i x_i' over a slab of rows, computed the way
+// the reference does it -- scale the rows by sqrt(w_i), then X~' X~ (Logit.hpp:325-332).
+//
+// Grid: blockIdx.y = output tile (bi, bj), bi <= bj, of 64 x 64; blockIdx.x = row slab.
+// CTA = 256 threads.  Row chunks of kGramRows rows stream HBM -> shared memory with
+// cp.async (LDGSTS) into a two-stage ring, so the next chunk's loads fly while the
+// current one is multiplied; a short pass scales the landed chunk by sqrt(w) in place.
+// Compute: a 16 x 16 thread grid of 4 x 4 register tiles, thread (ty, tx) owning rows
+// {ty + 16p} and columns {tx + 16q} (shared-memory reads are then conflict-free: lanes
+// read consecutive doubles / broadcast).  On a diagonal tile thread (tx, ty) would only
+// recompute the transpose of thread (ty, tx), so just the 136 threads with ty <= tx --
+// packed into the first 4.25 warps -- run: the symmetry really frees FP64 issue slots.
+// Per-CTA partial tiles go to `part`; k_gram_reduce sums them in a fixed order
+// (deterministic, no atomics).  Bound by the FP64 pipe: ~N P^2 (1 + 1/16) FMA.
 // ---------------------------------------------------------------------------------
 constexpr int kGramRows = 32;
 constexpr int kGramTile = 64;
+constexpr int kGramLd = kGramTile;          // dense rows: column reads are lane-consecutive
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 8 : 0;                 // src-size 0 -> zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc, bool valid)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__global__ void __launch_bounds__(256, 3)
 k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const double *__restrict__ w,
                int64_t N, int P, int nt)
 {
-    __shared__ __align__(16) double sa[kGramRows][kGramTile + 2];   // w_i * x_i[bi panel]
-    __shared__ __align__(16) double sb[kGramRows][kGramTile + 2];   // x_i[bj panel]
+    extern __shared__ __align__(16) double gsm[];
     // decode (bi, bj), bi <= bj, from blockIdx.y
     int t = blockIdx.y, bi = 0;
     while (t >= nt - bi) { t -= nt - bi; ++bi; }
     const int bj = bi + t;
-    // thread -> 4x4 output block (ty, tx): rows 4ty.., cols 4tx...  On a diagonal tile only
-    // the 136 blocks with ty <= tx are needed; they are packed into the first 136 threads
-    // (4.25 warps) so the skipped half really frees FP64 issue slots.
+    const bool diag = bi == bj;
+    const int npanel = diag ? 1 : 2;
+    const int stage_elems = npanel * kGramRows * kGramLd;
+    double *stage[2] = {gsm, gsm + stage_elems};
+    double *srw = gsm + 2 * stage_elems;                  // [2][kGramRows] sqrt(w)
+
     int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     bool live = true;
-    if (bi == bj) {
+    if (diag) {
         int r = threadIdx.x;
         live = r < 136;
         ty = 0;
@@ -84,30 +122,58 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
     const int64_t slab = (N + gridDim.x - 1) / gridDim.x;
     const int64_t r0 = (int64_t)blockIdx.x * slab;
     const int64_t r1 = r0 + slab < N ? r0 + slab : N;
-    for (int64_t base = r0; base < r1; base += kGramRows) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < kGramRows * kGramTile; e += 256) {
-            int r = e >> 6, c = e & 63;
-            int64_t i = base + r;
-            double xa = 0.0, xb = 0.0;
-            if (i < r1) {
-                int ca = bi * kGramTile + c, cb = bj * kGramTile + c;
-                double wi = w[i];
-                if (ca < P) xa = tX[i * P + ca] * wi;
-                if (cb < P) xb = tX[i * P + cb];
+    const bool vec16 = (P % 2 == 0) && ((reinterpret_cast<uintptr_t>(tX) & 15) == 0);
+
+    auto issue = [&](int64_t base, int sidx) {
+        double *dst = stage[sidx];
+        if (vec16) {
+            for (int e = threadIdx.x; e < npanel * kGramRows * (kGramTile / 2); e += 256) {
+                int pnl = e / (kGramRows * (kGramTile / 2));
+                int rem = e - pnl * (kGramRows * (kGramTile / 2));
+                int r = rem / (kGramTile / 2), c = (rem % (kGramTile / 2)) * 2;
+                int64_t i = base + r;
+                int col = (pnl == 0 ? bi : bj) * kGramTile + c;
+                bool ok = i < r1 && col < P;             // P even: col and col+1 valid together
+                cp_async16(dst + (pnl * kGramRows + r) * kGramLd + c, ok ? tX + i * P + col : tX, ok);
             }
-            sa[r][c] = xa;
-            sb[r][c] = xb;
+        } else {
+            for (int e = threadIdx.x; e < npanel * kGramRows * kGramTile; e += 256) {
+                int pnl = e / (kGramRows * kGramTile);
+                int rem = e - pnl * (kGramRows * kGramTile);
+                int r = rem / kGramTile, c = rem % kGramTile;
+                int64_t i = base + r;
+                int col = (pnl == 0 ? bi : bj) * kGramTile + c;
+                bool ok = i < r1 && col < P;
+                cp_async8(dst + (pnl * kGramRows + r) * kGramLd + c, ok ? tX + i * P + col : tX, ok);
+            }
+        }
+        if (threadIdx.x < kGramRows) {
+            int64_t i = base + threadIdx.x;
+            srw[sidx * kGramRows + threadIdx.x] = i < r1 ? sqrt(w[i]) : 0.0;
+        }
+        cp_async_commit();
+    };
+
+    int cur = 0;
+    if (r0 < r1) issue(r0, 0);
+    for (int64_t base = r0; base < r1; base += kGramRows, cur ^= 1) {
+        cp_async_wait<0>();
+        __syncthreads();                                  // chunk `cur` landed; chunk cur^1 free again
+        if (base + kGramRows < r1) issue(base + kGramRows, cur ^ 1);
+        double *xs = stage[cur];
+        const double *sw = srw + cur * kGramRows;
+        for (int e = threadIdx.x; e < npanel * kGramRows * kGramTile; e += 256) {
+            int r = (e / kGramTile) % kGramRows;
+            xs[e] *= sw[r];                               // rows scaled by sqrt(w): Logit.hpp:325-328
         }
         __syncthreads();
         if (live) {
+            const double *pa = xs + ty, *pb = xs + (npanel - 1) * kGramRows * kGramLd + tx;
 #pragma unroll 4
             for (int r = 0; r < kGramRows; ++r) {
                 double a[4], b[4];
-                const double2 a01 = *(const double2 *)&sa[r][4 * ty], a23 = *(const double2 *)&sa[r][4 * ty + 2];
-                const double2 b01 = *(const double2 *)&sb[r][4 * tx], b23 = *(const double2 *)&sb[r][4 * tx + 2];
-                a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y;
-                b[0] = b01.x; b[1] = b01.y; b[2] = b23.x; b[3] = b23.y;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { a[k] = pa[r * kGramLd + 16 * k]; b[k] = pb[r * kGramLd + 16 * k]; }
 #pragma unroll
                 for (int p = 0; p < 4; ++p)
 #pragma unroll
@@ -115,34 +181,54 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
             }
         }
     }
+    // element (ty+16p, tx+16q) of the tile; on a diagonal tile only threads ty <= tx exist
     double *out = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kGramTile * kGramTile);
+    if (live) {
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+        for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (live) out[(4 * ty + p) * kGramTile + 4 * tx + q] = acc[p][q];   // blocks below the diagonal are never read
+            for (int q = 0; q < 4; ++q) out[(ty + 16 * p) * kGramTile + tx + 16 * q] = acc[p][q];
+    }
+}
+
+inline size_t gram_smem_bytes(bool any_offdiag)
+{
+    return (size_t)(2 * (any_offdiag ? 2 : 1) * kGramRows * kGramLd + 2 * kGramRows) * sizeof(double);
 }
 
 // PP = P0 + sum over slabs of the partial tiles, mirrored to a full symmetric P x P
-// column-major matrix.  One thread per upper-triangle element, fixed summation order.
-__global__ void k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
-                              const double *__restrict__ part, int P, int nt, int nslab)
+// column-major matrix.  One warp-row of threads per output element group: each CTA owns
+// 32 upper-triangle candidates, its 8 warps split the slabs, fixed summation order.
+__global__ void __launch_bounds__(256)
+k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
+              const double *__restrict__ part, int P, int nt, int nslab)
 {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= P * P) return;
+    __shared__ double red[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int e = blockIdx.x * 32 + lane;
     int a = e % P, b = e / P;
-    if (a > b) return;
-    int bi = a / kGramTile, bj = b / kGramTile;
-    int tile = 0;
-    for (int k = 0; k < bi; ++k) tile += nt - k;
-    tile += bj - bi;
-    const double *src = part + (size_t)tile * nslab * (kGramTile * kGramTile)
-                      + (a % kGramTile) * kGramTile + (b % kGramTile);
+    bool want = e < P * P && a <= b;
     double s = 0.0;
-    for (int k = 0; k < nslab; ++k) s += src[(size_t)k * (kGramTile * kGramTile)];
-    double v = s + (P0 ? P0[a + (size_t)P * b] : 0.0);
-    PP[a + (size_t)P * b] = v;
-    PP[b + (size_t)P * a] = v;
+    if (want) {
+        int bi = a / kGramTile, bj = b / kGramTile;
+        int tile = 0;
+        for (int k = 0; k < bi; ++k) tile += nt - k;
+        tile += bj - bi;
+        int la = a % kGramTile, lb = b % kGramTile;
+        // a diagonal tile holds (row, col) only where row % 16 <= col % 16; otherwise read the transpose
+        if (bi == bj && (la & 15) > (lb & 15)) { int tmp = la; la = lb; lb = tmp; }
+        const double *src = part + (size_t)tile * nslab * (kGramTile * kGramTile) + la * kGramTile + lb;
+        for (int k = warp; k < nslab; k += 8) s += src[(size_t)k * (kGramTile * kGramTile)];
+    }
+    red[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && want) {
+        double v = 0.0;
+        for (int k = 0; k < 8; ++k) v += red[k][lane];
+        v += P0 ? P0[a + (size_t)P * b] : 0.0;
+        PP[a + (size_t)P * b] = v;
+        PP[b + (size_t)P * a] = v;
+    }
 }
 
 // out_p = sum_i x_i[p] * v_i  (X'v), v_i = c0*v0_i + c1*v1_i*v2_i  (v1/v2 optional).

@@ -21,7 +21,7 @@ namespace bl {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kChunkObs = 512;
+constexpr int kChunkObs = 128;
 
 __global__ void __launch_bounds__(kThreads)
 k_devroye_refill(double *__restrict__ x, const int *__restrict__ n, const double *__restrict__ z,

@@ -224,14 +224,39 @@ double pgo_rtinvchi2(pgo_src *s, double scale, double trunc)
 }
 
 /* Two-sided truncated normal N(mu, sd^2) on (left, right), used only by the
- * constrained beta draw (Logit.hpp:393).  No in-tree statement exists: inverse
- * CDF on one U is used, evaluated on whichever tail keeps precision. */
+ * constrained beta draw (Logit.hpp:393).  No in-tree statement exists (the
+ * reference's RNG::tnorm is in the absent library).  Standardised bounds (a, b):
+ *   far tails (a >= 4, or b <= -4 mirrored): rejection samplers of Robert (1995) --
+ *     narrow interval ((b-a) a < 1): uniform proposal, accept exp((a^2 - z^2)/2), pops (U U)+;
+ *     otherwise translated-exponential proposal with rate a* = (a + sqrt(a^2+4))/2,
+ *     rejected beyond b, accept exp(-(z - a*)^2/2), pops (E [U])+;
+ *   elsewhere: inverse CDF on one U, evaluated on whichever tail keeps precision. */
 static double inv_phi_upper(double q);
+
+static double tnorm_tail(pgo_src *s, double a, double b)
+{
+    if (b < INFINITY && (b - a) * a < 1.0) {
+        for (;;) {
+            double z = a + (b - a) * pgo_unif(s);
+            if (pgo_unif(s) < exp(0.5 * (a * a - z * z))) return z;
+        }
+    }
+    double astar = 0.5 * (a + sqrt(a * a + 4.0));
+    for (;;) {
+        double z = a + pgo_expon(s) / astar;
+        if (z > b) continue;
+        if (pgo_unif(s) < exp(-0.5 * (z - astar) * (z - astar))) return z;
+    }
+}
+
 double pgo_tnorm(pgo_src *s, double left, double right, double mu, double sd)
 {
     double a = (left - mu) / sd, b = (right - mu) / sd;
-    double u = pgo_unif(s);
     double z;
+    if (!(a < b)) return mu + sd * a;
+    if (b <= -4.0) return mu - sd * tnorm_tail(s, -b, -a);
+    if (a >= 4.0) return mu + sd * tnorm_tail(s, a, b);
+    double u = pgo_unif(s);
     if (a >= 0.0 || (a > -INFINITY && -a < b)) {
         /* work with upper tails Q(x) = 1 - Phi(x) */
         double qa = isinf(a) ? 1.0 : 0.5 * erfc(a / M_SQRT2);

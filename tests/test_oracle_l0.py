@@ -164,8 +164,23 @@ def test_composite_variates(port):
     cdf = lambda v: stats.norm.sf(np.sqrt(scale / v)) / stats.norm.sf(left)
     assert stats.kstest(x, cdf).pvalue > 1e-3
     # two-sided truncated normal
-    for lo, hi in ((-0.5, 1.5), (2.0, np.inf), (-np.inf, -3.0), (4.0, 4.5)):
+    # (far tails use Robert's rejection samplers, the rest an inverse CDF)
+    for lo, hi in ((-0.5, 1.5), (2.0, np.inf), (-np.inf, -3.0), (4.0, 4.5), (6.0, 6.05), (5.0, np.inf),
+                   (-np.inf, -7.0), (-300.0, -250.0), (40.0, 41.0), (-3.0, 60.0)):
         x = _draw_many(port, lambda s: lib.pgo_tnorm(s, lo, hi, 0.0, 1.0), 5000, 8)
-        assert x.min() >= lo and x.max() <= hi
-        cdf = lambda v: (stats.norm.cdf(v) - stats.norm.cdf(lo)) / (stats.norm.cdf(hi) - stats.norm.cdf(lo))
-        assert stats.kstest(x, cdf).pvalue > 1e-3
+        assert np.all(np.isfinite(x)) and x.min() >= lo and x.max() <= hi
+        if lo >= 0:      # evaluate the conditional CDF on the tail that keeps precision
+            cdf = lambda v: (stats.norm.logsf(lo) - 0 > -np.inf) * \
+                (1 - np.exp(stats.norm.logsf(v) - stats.norm.logsf(lo))) / \
+                (1 - np.exp(stats.norm.logsf(hi) - stats.norm.logsf(lo)))
+        elif hi <= 0:
+            cdf = lambda v: (np.exp(stats.norm.logcdf(v) - stats.norm.logcdf(hi)) -
+                             np.exp(stats.norm.logcdf(lo) - stats.norm.logcdf(hi))) / \
+                (1 - np.exp(stats.norm.logcdf(lo) - stats.norm.logcdf(hi)))
+        else:
+            cdf = lambda v: (stats.norm.cdf(v) - stats.norm.cdf(lo)) / (stats.norm.cdf(hi) - stats.norm.cdf(lo))
+        assert stats.kstest(x, cdf).pvalue > 1e-3, (lo, hi)
+    # with a location and scale, and a degenerate interval
+    x = _draw_many(port, lambda s: lib.pgo_tnorm(s, 1.0, 2.0, 5.0, 0.5), 4000, 9)
+    assert x.min() >= 1.0 and x.max() <= 2.0 and x.mean() > 1.8
+    assert lib.pgo_tnorm(C.byref((C.c_byte * 256)()), 2.0, 2.0, 0.0, 1.0) == 2.0
