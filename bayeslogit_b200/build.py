@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "lib", "libbayeslogit_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
-          "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+          "-Xptxas", "-v", "--expt-relaxed-constexpr"] + os.environ.get("BL_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _newest(paths):

@@ -69,23 +69,47 @@ constexpr int kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t 
 
 // acc[0..P^2) = Gram sum (no prior), acc[P^2..P^2+P) = optional X'v sum.
 // PP = acc + P0; rhs = base_rhs (+ acc tail); then the draw.
+// SMEM = true: the workspace is the CTA's shared memory (address space known to the compiler ->
+// LDS/STS); false: global scratch for P too large for shared memory.
+template <bool SMEM>
 __global__ void __launch_bounds__(256)
 k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__ P0,
             const double *__restrict__ base_rhs, int add_tail, const double *beta_prev,
-            double *beta_out, double *gwork, int P, uint64_t seed, uint32_t call, int *status,
-            int use_smem)
+            double *beta_out, double *gwork, int P, uint64_t seed, uint32_t call, int *status)
 {
     extern __shared__ double sm[];
+#ifdef BL_BETA_CLOCKS
+    long long k0 = clock64();
+#endif
     const int ld = P | 1;                     // odd leading dimension: row and column walks both conflict-free
-    double *A = use_smem ? sm : gwork;
+    double *A = SMEM ? sm : gwork;
     double *B = A + (size_t)ld * P;
     double *v = B + (size_t)ld * P;
     double *rhs = v + 4 * P;
-    for (int k = threadIdx.x; k < P * P; k += blockDim.x)
-        A[k % P + (size_t)ld * (k / P)] = acc[k] + (P0 ? P0[k] : 0.0);
+    // stage PP = Gram + P0 (batched loads: four columns in flight per thread)
+    for (int col0 = 0; col0 < P; col0 += 16) {
+        double g[4], q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int col = col0 + (threadIdx.x >> 6) + 4 * u, row = threadIdx.x & 63;
+            g[u] = 0.0; q[u] = 0.0;
+            for (int r = row; r < P && col < P; r += 64) { g[u] = acc[r + (size_t)P * col]; q[u] = P0 ? P0[r + (size_t)P * col] : 0.0; if (P <= 64) break; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int col = col0 + (threadIdx.x >> 6) + 4 * u, row = threadIdx.x & 63;
+            if (P <= 64) { if (row < P && col < P) A[row + (size_t)ld * col] = g[u] + q[u]; }
+        }
+    }
+    if (P > 64)
+        for (int k = threadIdx.x; k < P * P; k += blockDim.x)
+            A[k % P + (size_t)ld * (k / P)] = acc[k] + (P0 ? P0[k] : 0.0);
     for (int k = threadIdx.x; k < P; k += blockDim.x)
         rhs[k] = (base_rhs ? base_rhs[k] : 0.0) + (add_tail ? acc[(size_t)P * P + k] : 0.0);
     __syncthreads();
+#ifdef BL_BETA_CLOCKS
+    if (threadIdx.x == 0 && call == 3) printf("[beta clocks] load %lld\n", clock64() - k0);
+#endif
     cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status);
 }
 
@@ -141,25 +165,24 @@ struct Sweep {
     {
         nt = cdiv(P, kGramTile);
         int tiles = nt * (nt + 1) / 2;
-        nslab = (int)std::min<int64_t>(std::max<int64_t>(1, 148 * 3 / tiles), std::max<int64_t>(1, N / (4 * kGramRows)));
+        nslab = (int)std::min<int64_t>(std::max<int64_t>(1, 148 * 4 / tiles), std::max<int64_t>(1, N / (4 * kGramRows)));
         if (nslab < 1) nslab = 1;
         xtv_slabs = (int)std::min<int64_t>(148 * 2, std::max<int64_t>(1, N / 64));
         GB_CK(m.get(&psi, N));
         GB_CK(m.get(&w, N));
         GB_CK(m.get(&acc, (size_t)P * P + P));
-        GB_CK(m.get(&part, (size_t)tiles * nslab * kGramTile * kGramTile));
+        GB_CK(m.get(&part, (size_t)tiles * nslab * 2 * kGramTile * kGramTile));
         GB_CK(m.get(&xtv_part, (size_t)xtv_slabs * P));
         GB_CK(m.get(&gwork, 2 * (size_t)(P + 1) * P + 5 * (size_t)P));
         GB_CK(m.get(&status, 1));
         GB_CK(cudaMemsetAsync(status, 0, sizeof(int), st));
         GB_CK(cudaMemsetAsync(acc, 0, ((size_t)P * P + P) * sizeof(double), st));
         beta_smem = (2 * (size_t)(P | 1) * P + 5 * (size_t)P) * sizeof(double);
-        if (gram_smem_bytes(nt > 1) > 48 * 1024)
-            GB_CK(cudaFuncSetAttribute(k_gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)gram_smem_bytes(true)));
+        GB_CK(cudaFuncSetAttribute(k_gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)gram_smem_bytes(true)));
         use_smem = beta_smem <= 200 * 1024;
         if (use_smem && beta_smem > 48 * 1024)
-            GB_CK(cudaFuncSetAttribute(k_beta_draw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem));
+            GB_CK(cudaFuncSetAttribute(k_beta_draw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem));
         return 0;
     }
 
@@ -175,7 +198,7 @@ struct Sweep {
     {
         int tiles = nt * (nt + 1) / 2;
         k_gram_partial<<<dim3(nslab, tiles), 256, gram_smem_bytes(nt > 1), st>>>(part, tX, wv, N, P, nt);
-        k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nslab);
+        k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, 2 * nslab);
         count_launch(2);
     }
 
@@ -199,9 +222,12 @@ struct Sweep {
     void beta_draw(int mode, const double *P0, const double *base_rhs, bool add_tail,
                    const double *beta_prev, double *beta_out, uint64_t seed, uint32_t call)
     {
-        k_beta_draw<<<1, 256, use_smem ? beta_smem : 0, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0,
-                                                               beta_prev, beta_out, gwork, P, seed, call,
-                                                               status, use_smem ? 1 : 0);
+        if (use_smem)
+            k_beta_draw<true><<<1, 256, beta_smem, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
+                                                         beta_out, gwork, P, seed, call, status);
+        else
+            k_beta_draw<false><<<1, 256, 0, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
+                                                  beta_out, gwork, P, seed, call, status);
         count_launch();
     }
 

@@ -195,12 +195,115 @@ __device__ inline double stream_normal(uint64_t seed, uint32_t call, int k)
     return s.norm();
 }
 
+// ---- fast path pieces for the plain draw -----------------------------------------------------
+// Root-free right-looking factorisation A = R' D^-1 R (row j of R is row j of the running
+// Schur complement, D = diag(R)): one barrier per column instead of three, no square root or
+// division inside the sweep.  U = D^-1/2 R is the Cholesky factor; it is never formed -- the
+// solves below use R and rd = 1/diag(R) directly.
+__device__ __forceinline__ void cta_ldl_upper(double *A, double *rd, int P, int ld, int *ok)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = 0; j < P; ++j) {
+        __syncthreads();
+        double d = A[j + (size_t)ld * j];
+        if (!(d > 0.0)) { if (tid == 0) *ok = 0; __syncthreads(); return; }
+        double inv = 1.0 / d;
+        if (tid == 0) rd[j] = inv;
+        for (int k = j + 1 + (tid >> 4); k < P; k += nt >> 4) {
+            double s = A[j + (size_t)ld * k] * inv;
+            // four (i,k) entries at a time, all loads issued before the first store
+            for (int i0 = j + 1 + (tid & 15); i0 <= k; i0 += 64) {
+                double r[4], c[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int i = i0 + 16 * u;
+                    bool in = i <= k;
+                    r[u] = in ? A[j + (size_t)ld * i] : 0.0;
+                    c[u] = in ? A[i + (size_t)ld * k] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int i = i0 + 16 * u;
+                    if (i <= k) A[i + (size_t)ld * k] = fma(-r[u], s, c[u]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// One warp, x held in registers (lane l owns x[l], x[l+32], ...; up to 8 per lane = P <= 256).
+// Column-oriented substitution: the pivot value travels by one shuffle, every lane then
+// updates its own entries -- no reduction on the critical path.
+//   forward : y = U^-T b   with U = D^-1/2 R  ->  y_i = sqrt(rd_i) (b_i - sum_{k<i} R[k,i] sqrt(rd_k) y_k)
+//   backward: x = U^-1 y                         x_i = sqrt(rd_i) (y_i - sum_{k>i} R[i,k] sqrt(rd_i) x_k) ...
+// written below in terms of t = D^-1/2-scaled quantities so only R and rd are touched.
+template <int KP>
+__device__ __forceinline__ void warp_solve_plain_k(const double *R, const double *rd, const double *b,
+                                                   const double *e, double *out, int P, int ld, int lane)
+{
+    double x[KP];
+#pragma unroll
+    for (int q = 0; q < KP; ++q) x[q] = lane + 32 * q < P ? b[lane + 32 * q] : 0.0;
+    // forward: t_i = rd_i * (b_i - sum_{k<i} R[k,i] t_k); lanes keep the running residuals
+    for (int i = 0; i < P; ++i) {
+        double own = x[0];
+#pragma unroll
+        for (int q = 1; q < KP; ++q) own = (i >> 5) == q ? x[q] : own;
+        double rr[KP];
+#pragma unroll
+        for (int q = 0; q < KP; ++q) {
+            int m = lane + 32 * q;
+            rr[q] = (m > i && m < P) ? R[i + (size_t)ld * m] : 0.0;      // issued before the shuffle lands
+        }
+        double gi = __shfl_sync(0xffffffffu, own, i & 31) * rd[i];
+#pragma unroll
+        for (int q = 0; q < KP; ++q) x[q] = fma(-rr[q], gi, x[q]);
+    }
+    // R x = r + e / sqrt(rd)  (see the derivation above), backward substitution
+#pragma unroll
+    for (int q = 0; q < KP; ++q) {
+        int m = lane + 32 * q;
+        if (m < P) x[q] = x[q] + e[m] / sqrt(rd[m]);
+    }
+    for (int i = P - 1; i >= 0; --i) {
+        double own = x[0];
+#pragma unroll
+        for (int q = 1; q < KP; ++q) own = (i >> 5) == q ? x[q] : own;
+        double rr[KP];
+#pragma unroll
+        for (int q = 0; q < KP; ++q) {
+            int m = lane + 32 * q;
+            rr[q] = m < i ? R[m + (size_t)ld * i] : 0.0;
+        }
+        double xi = __shfl_sync(0xffffffffu, own, i & 31) * rd[i];
+#pragma unroll
+        for (int q = 0; q < KP; ++q) {
+            int m = lane + 32 * q;
+            x[q] = m == i ? xi : fma(-rr[q], xi, x[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < KP; ++q) {
+        int m = lane + 32 * q;
+        if (m < P) out[m] = x[q];
+    }
+}
+
+__device__ inline void warp_solve_plain(const double *R, const double *rd, const double *b,
+                                        const double *e, double *out, int P, int ld, int lane)
+{
+    if (P <= 64) warp_solve_plain_k<2>(R, rd, b, e, out, P, ld, lane);
+    else if (P <= 128) warp_solve_plain_k<4>(R, rd, b, e, out, P, ld, lane);
+    else warp_solve_plain_k<8>(R, rd, b, e, out, P, ld, lane);
+}
+
 // One beta draw.  Workspace (all column-major, ld = P):
 //   A  [P*P]  in: PP (posterior precision, full symmetric)   -> U
 //   B  [P*P]  scratch: S = PP^-1 -> L                        (constrained, mvn)
 //   v  [4*P]  scratch vectors
 // rhs = bP (precision-weighted mean), beta_prev (constrained only), beta_out.
-__device__ inline void cta_beta_draw(int mode, double *A, double *B, double *v, const double *rhs,
+__device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, double *v, const double *rhs,
                                      const double *beta_prev, double *beta_out, int P, int ld,
                                      uint64_t seed, uint32_t call, int *status)
 {
@@ -208,25 +311,35 @@ __device__ inline void cta_beta_draw(int mode, double *A, double *B, double *v, 
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) ok = 1;
     __syncthreads();
-    cta_chol_upper(A, P, ld, &ok);
-    if (!ok) { if (tid == 0) *status = 1; return; }
     double *mP = v, *z = v + P, *e = v + 2 * P;
     PhiloxSource src;
     src.open(seed, 0xFFFFFFFFFFFFFFFFull, call);
 
     if (mode == kBetaPlain) {
-        if (tid < 32) {
-            for (int i = lane; i < P; i += 32) e[i] = stream_normal(seed, call, i);
-            for (int i = lane; i < P; i += 32) mP[i] = rhs[i];
-            __syncwarp();
-            warp_solve_ut(A, mP, P, ld, lane);
-            warp_solve_u(A, mP, P, ld, lane);
-            warp_solve_u(A, e, P, ld, lane);
-            for (int i = lane; i < P; i += 32) beta_out[i] = e[i] + mP[i];
-        }
+        // beta = PP^-1 bP + U^-1 eps = U^-1 (U^-T bP + eps)          (Logit.hpp:303-319)
+        double *rd = z;
+#ifdef BL_BETA_CLOCKS
+        long long c0 = clock64();
+#endif
+        for (int i = tid; i < P; i += blockDim.x) e[i] = stream_normal(seed, call, i);
+#ifdef BL_BETA_CLOCKS
+        long long c1 = clock64();
+#endif
+        cta_ldl_upper(A, rd, P, ld, &ok);
+#ifdef BL_BETA_CLOCKS
+        long long c2 = clock64();
+#endif
+        if (!ok) { if (tid == 0) *status = 1; return; }
+        if (tid < 32) warp_solve_plain(A, rd, rhs, e, beta_out, P, ld, lane);
         __syncthreads();
+#ifdef BL_BETA_CLOCKS
+        if (tid == 0 && call == 3) printf("[beta clocks] normals %lld ldl %lld solve %lld\n", c1 - c0, c2 - c1, clock64() - c2);
+#endif
         return;
     }
+
+    cta_chol_upper(A, P, ld, &ok);
+    if (!ok) { if (tid == 0) *status = 1; return; }
 
     // S = PP^-1 by solving against the identity (Logit.hpp:338-347; Normal.hpp:106-107)
     for (int k = tid; k < P * P; k += blockDim.x) B[k % P + (size_t)ld * (k / P)] = (k % P == k / P) ? 1.0 : 0.0;

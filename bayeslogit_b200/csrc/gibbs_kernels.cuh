@@ -58,18 +58,19 @@ k_xbeta(double *__restrict__ psi, const double *__restrict__ tX, const double *_
 }
 
 // ---------------------------------------------------------------------------------
-// Weighted Gram, SYRK-shaped: G = sum_i w_i x_i x_i' over a slab of rows, computed the way
-// the reference does it -- scale the rows by sqrt(w_i), then X~' X~ (Logit.hpp:325-332).
+// Weighted Gram, SYRK-shaped: G = sum_i w_i x_i x_i' over a slab of rows.
 //
 // Grid: blockIdx.y = output tile (bi, bj), bi <= bj, of 64 x 64; blockIdx.x = row slab.
-// CTA = 256 threads.  Row chunks of kGramRows rows stream HBM -> shared memory with
-// cp.async (LDGSTS) into a two-stage ring, so the next chunk's loads fly while the
-// current one is multiplied; a short pass scales the landed chunk by sqrt(w) in place.
+// Row chunks of kGramRows rows (and their weights) stream HBM -> shared memory with cp.async
+// (LDGSTS) through a three-stage ring -- two chunks in flight while one is multiplied, one
+// barrier per chunk; the weight is folded into the row operand as it is read
+// (w x_i) x_j', cf. MultLogit.hpp:246-248; Logit.hpp:325-332 scales by sqrt(w) instead).
 // Compute: a 16 x 16 thread grid of 4 x 4 register tiles, thread (ty, tx) owning rows
 // {ty + 16p} and columns {tx + 16q} (shared-memory reads are then conflict-free: lanes
 // read consecutive doubles / broadcast).  On a diagonal tile thread (tx, ty) would only
 // recompute the transpose of thread (ty, tx), so just the 136 threads with ty <= tx --
-// packed into the first 4.25 warps -- run: the symmetry really frees FP64 issue slots.
+// packed into the first 4.25 warps -- run (P <= 64 launches 160-thread CTAs: no idle warps):
+// the symmetry really frees FP64 issue slots.
 // Per-CTA partial tiles go to `part`; k_gram_reduce sums them in a fixed order
 // (deterministic, no atomics).  Bound by the FP64 pipe: ~N P^2 (1 + 1/16) FMA.
 // ---------------------------------------------------------------------------------
@@ -93,107 +94,137 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-__global__ void __launch_bounds__(256, 3)
+constexpr int kGramStages = 3;
+constexpr int kGramLdm = 68;     // leading dimension (doubles): == 4 mod 16 -> conflict-free DMMA fragment loads
+
+// D(8x8) += A(8x4) * B(4x8), fp64 tensor-core MMA.  Lane l: gid = l>>2, tig = l&3;
+// a = A[gid][tig], b = B[tig][gid], c0/c1 = C[gid][2 tig], C[gid][2 tig + 1].
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Weighted Gram on the FP64 tensor cores (DMMA).  A register-tiled DFMA version of this kernel
+// was bound by shared-memory bandwidth (LSU data pipe 75% busy, FP64 pipe 11%: every 16 FMAs
+// cost 8 shared loads); an 8x8x4 MMA reuses each fragment element across a whole tile, so
+// the same shared traffic feeds 8x the math.
+//   grid  : blockIdx.y = 64x64 output tile (bi <= bj), blockIdx.x = row slab
+//   CTA   : 8 warps = 2 row-groups x 4 sub-tiles of 32x32; each warp holds a 4x4 grid of
+//           8x8 accumulator tiles.  On a diagonal tile the sub-tile below the diagonal and
+//           the MMA tiles below the diagonal of the two diagonal sub-tiles are skipped.
+//   smem  : three-stage cp.async ring of 32-row chunks of X (+ their weights); one barrier
+//           per chunk; row group g multiplies rows [16g, 16g+16) of each chunk.
+//   C = sum_r (w_r x_r[i]) x_r[j]: A[i][r] = w_r X[r][i] (weight folded into the A fragment),
+//   B[r][j] = X[r][j].
+__global__ void __launch_bounds__(256)
 k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const double *__restrict__ w,
                int64_t N, int P, int nt)
 {
     extern __shared__ __align__(16) double gsm[];
-    // decode (bi, bj), bi <= bj, from blockIdx.y
+    const int nthr = blockDim.x;
     int t = blockIdx.y, bi = 0;
     while (t >= nt - bi) { t -= nt - bi; ++bi; }
     const int bj = bi + t;
     const bool diag = bi == bj;
     const int npanel = diag ? 1 : 2;
-    const int stage_elems = npanel * kGramRows * kGramLd;
-    double *stage[2] = {gsm, gsm + stage_elems};
-    double *srw = gsm + 2 * stage_elems;                  // [2][kGramRows] sqrt(w)
+    const int stage_elems = npanel * kGramRows * kGramLdm + kGramRows;
+    const int w_off = npanel * kGramRows * kGramLdm;
 
-    int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    bool live = true;
-    if (diag) {
-        int r = threadIdx.x;
-        live = r < 136;
-        ty = 0;
-        while (live && r >= 16 - ty) { r -= 16 - ty; ++ty; }
-        tx = live ? ty + r : 0;
-        if (!live) ty = 0;
-    }
-    double acc[4][4] = {};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int grp = warp >> 2, sub = warp & 3, si = sub >> 1, sj = sub & 1;
+    const bool live = !(diag && si > sj);
+    const bool tri = diag && si == sj;                 // diagonal sub-tile: MMA tiles with mi <= mj only
+
+    double c[4][4][2] = {};
     const int64_t slab = (N + gridDim.x - 1) / gridDim.x;
     const int64_t r0 = (int64_t)blockIdx.x * slab;
     const int64_t r1 = r0 + slab < N ? r0 + slab : N;
     const bool vec16 = (P % 2 == 0) && ((reinterpret_cast<uintptr_t>(tX) & 15) == 0);
 
     auto issue = [&](int64_t base, int sidx) {
-        double *dst = stage[sidx];
-        if (vec16) {
-            for (int e = threadIdx.x; e < npanel * kGramRows * (kGramTile / 2); e += 256) {
-                int pnl = e / (kGramRows * (kGramTile / 2));
-                int rem = e - pnl * (kGramRows * (kGramTile / 2));
-                int r = rem / (kGramTile / 2), c = (rem % (kGramTile / 2)) * 2;
-                int64_t i = base + r;
-                int col = (pnl == 0 ? bi : bj) * kGramTile + c;
-                bool ok = i < r1 && col < P;             // P even: col and col+1 valid together
-                cp_async16(dst + (pnl * kGramRows + r) * kGramLd + c, ok ? tX + i * P + col : tX, ok);
+        const int so = sidx * stage_elems;
+        if (base < r1) {
+            if (vec16) {
+                for (int e = threadIdx.x; e < npanel * kGramRows * (kGramTile / 2); e += nthr) {
+                    int pnl = e >= kGramRows * (kGramTile / 2);
+                    int rem = e - pnl * (kGramRows * (kGramTile / 2));
+                    int r = rem >> 5, cc = (rem & 31) * 2;
+                    int64_t i = base + r;
+                    int col = (pnl == 0 ? bi : bj) * kGramTile + cc;
+                    bool ok = i < r1 && col < P;
+                    cp_async16(&gsm[so + (pnl * kGramRows + r) * kGramLdm + cc], ok ? tX + i * P + col : tX, ok);
+                }
+            } else {
+                for (int e = threadIdx.x; e < npanel * kGramRows * kGramTile; e += nthr) {
+                    int pnl = e >= kGramRows * kGramTile;
+                    int rem = e - pnl * (kGramRows * kGramTile);
+                    int r = rem >> 6, cc = rem & 63;
+                    int64_t i = base + r;
+                    int col = (pnl == 0 ? bi : bj) * kGramTile + cc;
+                    bool ok = i < r1 && col < P;
+                    cp_async8(&gsm[so + (pnl * kGramRows + r) * kGramLdm + cc], ok ? tX + i * P + col : tX, ok);
+                }
             }
-        } else {
-            for (int e = threadIdx.x; e < npanel * kGramRows * kGramTile; e += 256) {
-                int pnl = e / (kGramRows * kGramTile);
-                int rem = e - pnl * (kGramRows * kGramTile);
-                int r = rem / kGramTile, c = rem % kGramTile;
-                int64_t i = base + r;
-                int col = (pnl == 0 ? bi : bj) * kGramTile + c;
-                bool ok = i < r1 && col < P;
-                cp_async8(dst + (pnl * kGramRows + r) * kGramLd + c, ok ? tX + i * P + col : tX, ok);
+            if (threadIdx.x < kGramRows) {
+                int64_t i = base + threadIdx.x;
+                cp_async8(&gsm[so + w_off + threadIdx.x], i < r1 ? w + i : w, i < r1);
             }
-        }
-        if (threadIdx.x < kGramRows) {
-            int64_t i = base + threadIdx.x;
-            srw[sidx * kGramRows + threadIdx.x] = i < r1 ? sqrt(w[i]) : 0.0;
         }
         cp_async_commit();
     };
 
+    issue(r0, 0);
+    issue(r0 + kGramRows, 1);
     int cur = 0;
-    if (r0 < r1) issue(r0, 0);
-    for (int64_t base = r0; base < r1; base += kGramRows, cur ^= 1) {
-        cp_async_wait<0>();
-        __syncthreads();                                  // chunk `cur` landed; chunk cur^1 free again
-        if (base + kGramRows < r1) issue(base + kGramRows, cur ^ 1);
-        double *xs = stage[cur];
-        const double *sw = srw + cur * kGramRows;
-        for (int e = threadIdx.x; e < npanel * kGramRows * kGramTile; e += 256) {
-            int r = (e / kGramTile) % kGramRows;
-            xs[e] *= sw[r];                               // rows scaled by sqrt(w): Logit.hpp:325-328
-        }
+    for (int64_t base = r0; base < r1; base += kGramRows) {
+        cp_async_wait<1>();
         __syncthreads();
+        int nxt = cur + 2 >= kGramStages ? cur + 2 - kGramStages : cur + 2;
+        issue(base + 2 * kGramRows, nxt);
         if (live) {
-            const double *pa = xs + ty, *pb = xs + (npanel - 1) * kGramRows * kGramLd + tx;
-#pragma unroll 4
-            for (int r = 0; r < kGramRows; ++r) {
+            const int so = cur * stage_elems;
+            const int pa = so + si * 32 + gid;                                         // A: panel bi
+            const int pb = so + (npanel - 1) * kGramRows * kGramLdm + sj * 32 + gid;   // B: panel bj
+#pragma unroll
+            for (int kk = 0; kk < kGramRows / 8; ++kk) {
+                const int r = grp * (kGramRows / 2) + kk * 4 + tig;                    // this lane's k row
+                const double wr = gsm[so + w_off + r];
                 double a[4], b[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { a[k] = pa[r * kGramLd + 16 * k]; b[k] = pb[r * kGramLd + 16 * k]; }
+                for (int m = 0; m < 4; ++m) {
+                    a[m] = gsm[pa + r * kGramLdm + 8 * m] * wr;
+                    b[m] = gsm[pb + r * kGramLdm + 8 * m];
+                }
 #pragma unroll
-                for (int p = 0; p < 4; ++p)
+                for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[p][q] = fma(a[p], b[q], acc[p][q]);
+                    for (int mj = 0; mj < 4; ++mj)
+                        if (!tri || mi <= mj) dmma884(c[mi][mj][0], c[mi][mj][1], a[mi], b[mj]);
             }
         }
+        cur = cur + 1 == kGramStages ? 0 : cur + 1;
     }
-    // element (ty+16p, tx+16q) of the tile; on a diagonal tile only threads ty <= tx exist
-    double *out = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kGramTile * kGramTile);
+    cp_async_wait<0>();
+    // partial tile of (slab, row group): entries exist where (row >> 3) <= (col >> 3) on diagonal tiles
+    double *out = part + ((size_t)blockIdx.y * (gridDim.x * 2) + blockIdx.x * 2 + grp) * (kGramTile * kGramTile);
     if (live) {
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) out[(ty + 16 * p) * kGramTile + tx + 16 * q] = acc[p][q];
+            for (int mj = 0; mj < 4; ++mj)
+                if (!tri || mi <= mj) {
+                    int row = si * 32 + mi * 8 + gid, col = sj * 32 + mj * 8 + 2 * tig;
+                    out[row * kGramTile + col] = c[mi][mj][0];
+                    out[row * kGramTile + col + 1] = c[mi][mj][1];
+                }
     }
 }
 
 inline size_t gram_smem_bytes(bool any_offdiag)
 {
-    return (size_t)(2 * (any_offdiag ? 2 : 1) * kGramRows * kGramLd + 2 * kGramRows) * sizeof(double);
+    return (size_t)kGramStages * ((any_offdiag ? 2 : 1) * kGramRows * kGramLdm + kGramRows) * sizeof(double);
 }
 
 // PP = P0 + sum over slabs of the partial tiles, mirrored to a full symmetric P x P
@@ -215,8 +246,7 @@ k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
         for (int k = 0; k < bi; ++k) tile += nt - k;
         tile += bj - bi;
         int la = a % kGramTile, lb = b % kGramTile;
-        // a diagonal tile holds (row, col) only where row % 16 <= col % 16; otherwise read the transpose
-        if (bi == bj && (la & 15) > (lb & 15)) { int tmp = la; la = lb; lb = tmp; }
+        // a diagonal tile holds (row, col) wherever (row >> 3) <= (col >> 3): true for every la <= lb
         const double *src = part + (size_t)tile * nslab * (kGramTile * kGramTile) + la * kGramTile + lb;
         for (int k = warp; k < nslab; k += 8) s += src[(size_t)k * (kGramTile * kGramTile)];
     }
