@@ -473,6 +473,10 @@ int bl_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2)
 
 uint64_t bl_kernel_launches(void) { return g_launches.load(); }
 
+void bl_hybrid_timing(int enable) { hybrid_timing_enable(enable != 0); }
+
+int bl_hybrid_timing_last(double *ms6) { return hybrid_timing_last(ms6); }
+
 int bl_ensure_ready_internal(void)
 {
     std::lock_guard<std::mutex> lock(g.mu);

@@ -70,6 +70,9 @@ int comm_unique_id(void *out128, std::string &err);
 int comm_init(const void *id128, int rank, int world, std::string &err);
 void comm_destroy();
 
+void hybrid_timing_enable(bool on);
+int hybrid_timing_last(double *out6);
+
 void count_launch(int n = 1);
 
 }  // namespace bl

@@ -134,6 +134,33 @@ void launch_regime(double *x, const double *h, const double *z, const int *idx, 
 
 }  // namespace
 
+// optional per-stage timing of the last binned launch (bench.py's roofline leg)
+static bool g_hyb_timing = false;
+static cudaEvent_t g_hyb_ev[7];
+static bool g_hyb_ev_ready = false;
+
+void hybrid_timing_enable(bool on)
+{
+    g_hyb_timing = on;
+    if (on && !g_hyb_ev_ready) {
+        for (auto &e : g_hyb_ev) cudaEventCreate(&e);
+        g_hyb_ev_ready = true;
+    }
+}
+
+// ms of [binning, SP, Alt, sum-of-gammas, normal, Devroye] of the last timed launch
+int hybrid_timing_last(double *out6)
+{
+    if (!g_hyb_ev_ready) return 1;
+    if (cudaEventSynchronize(g_hyb_ev[6]) != cudaSuccess) return 1;
+    for (int k = 0; k < 6; ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_hyb_ev[k], g_hyb_ev[k + 1]);
+        out6[k] = ms;
+    }
+    return 0;
+}
+
 size_t hybrid_workspace_bytes(int64_t num) { return 32 * sizeof(int) + (size_t)num * sizeof(int); }
 
 // One rpg_hybrid batch of at most 2^31-1 observations.  `work` holds
@@ -148,16 +175,24 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
     if (e != cudaSuccess) return e;
     int tiles = (num + kBinThreads - 1) / kBinThreads;
     int grid = tiles < 148 * 8 ? tiles : 148 * 8;
+    const bool tm = g_hyb_timing;
+    if (tm) cudaEventRecord(g_hyb_ev[0], st);
     k_hyb_count<<<grid, kBinThreads, 0, st>>>(h, num, meta);
     k_hyb_offsets<<<1, 1, 0, st>>>(meta);
     k_hyb_scatter<<<grid, kBinThreads, 0, st>>>(h, num, meta, idx, x);
     count_launch(3);
     // heavy regimes first so the light ones fill the tail
+    if (tm) cudaEventRecord(g_hyb_ev[1], st);
     launch_regime<kRegSP>(x, h, z, idx, meta, id, num, 4, st);
+    if (tm) cudaEventRecord(g_hyb_ev[2], st);
     launch_regime<kRegAlt>(x, h, z, idx, meta, id, num, 4, st);
+    if (tm) cudaEventRecord(g_hyb_ev[3], st);
     launch_regime<kRegGamma>(x, h, z, idx, meta, id, num, 8, st);
+    if (tm) cudaEventRecord(g_hyb_ev[4], st);
     launch_regime<kRegNormal>(x, h, z, idx, meta, id, num, 8, st);
+    if (tm) cudaEventRecord(g_hyb_ev[5], st);
     launch_regime<kRegDevroye>(x, h, z, idx, meta, id, num, 8, st);
+    if (tm) cudaEventRecord(g_hyb_ev[6], st);
     return cudaGetLastError();
 }
 

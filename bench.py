@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--num", type=int, default=100_000_000, help="draws per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the PG(1,z) and logit-Gibbs extras")
+    ap.add_argument("--gibbs-iters", type=int, default=200)
     return ap.parse_args()
 
 
@@ -244,6 +246,28 @@ def main():
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     value = world * num * args.steps / (total_ms * 1e-3)
     mean_omega = float(x_d[: 1 << 20].mean().item())
+    # dominant kernel of the step, timed live with CUDA events on the launch stream (separate,
+    # untimed pass so the event records do not sit inside the headline region)
+    stage_ms, regime_counts = None, None
+    if wl == "hybrid":
+        import ctypes as C
+        L.bl_hybrid_timing(1)
+        acc6 = [0.0] * 6
+        reps = max(1, min(3, args.steps))
+        for k in range(reps):
+            step_dev(3000 + k)
+            buf = (C.c_double * 6)()
+            if L.bl_hybrid_timing_last(C.cast(buf, C.c_void_p)) == 0:
+                acc6 = [a + b for a, b in zip(acc6, buf)]
+        L.bl_hybrid_timing(0)
+        stage_ms = dict(zip(["binning", "saddle_point", "alternate", "sum_of_gammas", "normal", "devroye"],
+                            [max_over_ranks(v / reps) for v in acc6]))
+        hh = shape_d
+        regime_counts = {"saddle_point": int(((hh > 13) & (hh <= 170)).sum().item()),
+                         "normal": int((hh > 170).sum().item()),
+                         "alternate": int(((hh > 1) & (hh <= 13) & (hh != 2)).sum().item()),
+                         "devroye": int(((hh == 1) | (hh == 2)).sum().item()),
+                         "sum_of_gammas": int(((hh > 0) & (hh < 1)).sum().item())}
 
     # ---- end to end through the reference-facing C ABI, pinned host buffers ------------
     e2e = None
@@ -283,6 +307,44 @@ def main():
         cpu = {"value": sample / dt, "unit": "draws/s", "cores": cores, "kind": kind,
                "sample": f"first {sample} draws of the workload, all {cores} host threads, {dt:.2f} s wall"}
 
+    # ---- extras: the two other figures BASELINE.json's metric names -------------------------
+    extras = {}
+    if not args.no_extras:
+        # (i) PG(1,z) draws/s, z~U(-5,5), 2^27 draws per GPU (north_star target: >= 1e10 on one B200)
+        del shape_d, z_d, x_d
+        torch.cuda.empty_cache()
+        n1 = 1 << 27
+        g = torch.Generator(device=dev); g.manual_seed(SEED + rank)
+        z1 = torch.rand(n1, generator=g, device=dev, dtype=torch.float64) * 10 - 5
+        s1 = torch.ones(n1, device=dev, dtype=torch.int32)
+        x1 = torch.empty(n1, device=dev, dtype=torch.float64)
+        for w in range(3):
+            L.bl_rpg_devroye_dev(x1.data_ptr(), s1.data_ptr(), z1.data_ptr(), n1, SEED, 500 + w, rank * n1, stream)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for k in range(5):
+            L.bl_rpg_devroye_dev(x1.data_ptr(), s1.data_ptr(), z1.data_ptr(), n1, SEED, k, rank * n1, stream)
+        b.record()
+        barrier()
+        ms1 = max_over_ranks(a.elapsed_time(b)) / 5
+        extras["pg1"] = {"draws_per_sec": world * n1 / (ms1 * 1e-3), "ms_per_launch": ms1, "draws_per_gpu": n1,
+                         "workload": "rpg_devroye PG(1,z), z~U(-5,5), device-resident",
+                         "kernel": "k_devroye_refill",
+                         "roofline_compute_frac": world * n1 / (ms1 * 1e-3) * 0.9e3 / 1e12 / (37.0 * world),
+                         "hbm_GBs": n1 * 20 / (ms1 * 1e-3) / 1e9}
+        del z1, s1, x1
+        torch.cuda.empty_cache()
+        # (ii) logit Gibbs iterations/s at N=1M, P=64 (strong scaling: the N rows are sharded)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_gibbs
+        if world > 1:
+            from bayeslogit_b200 import dist as bdist
+            bdist.init_comm(rank, world, dev)
+        gp = bench_gibbs.run(1_000_000, 64, args.gibbs_iters, 5, False, rank, world, local)
+        gc = bench_gibbs.run(1_000_000, 64, max(10, args.gibbs_iters // 10), 2, True, rank, world, local)
+        extras["gibbs_logit_N1M_P64"] = {"plain_beta": gp, "reference_constrained_beta": gc, "scaling": "strong"}
+
     if rank == 0:
         peaks = {}
         try:
@@ -290,9 +352,15 @@ def main():
         except OSError:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        achieved = num * BYTES_PER_DRAW[wl] / (kern_ms * 1e-3) / 1e9
         fp64_peak = 37.0   # TFLOP/s, B200 vector FP64 (not in MEASURED_PEAKS.json)
-        tf = num * KFLOP_PER_DRAW[wl] * 1e3 / (kern_ms * 1e-3) / 1e12
+        if stage_ms:
+            # dominant kernel = the saddle-point regime kernel: its own draws, its own launch time
+            dom_units, dom_ms, dom_name = regime_counts["saddle_point"], stage_ms["saddle_point"], "k_hyb_regime<saddle-point>"
+            dom_kflop = 9.0
+        else:
+            dom_units, dom_ms, dom_name, dom_kflop = num, kern_ms, "k_devroye_refill", KFLOP_PER_DRAW[wl]
+        achieved = dom_units * BYTES_PER_DRAW[wl] / (dom_ms * 1e-3) / 1e9
+        tf = dom_units * dom_kflop * 1e3 / (dom_ms * 1e-3) / 1e12
         out = {
             "metric": "pg_draws_per_sec", "value": value, "unit": "draws/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -302,12 +370,14 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None,
                          "peak_source": "measured" if peaks else "fallback",
-                         "kernel": "k_rpg_philox<hybrid>" if wl == "hybrid" else "k_rpg_philox<devroye>",
-                         "kernel_ms": kern_ms,
+                         "kernel": dom_name, "kernel_ms": dom_ms, "units_per_launch": dom_units,
+                         "bytes_per_unit": BYTES_PER_DRAW[wl], "share_of_step": dom_ms / (total_ms / args.steps),
+                         "stage_ms": stage_ms, "regime_counts": regime_counts,
                          "note": "the sampler is bound by the FP64/ALU pipes, not HBM (SURVEY.md 8d); see roofline_compute"},
             "roofline_compute": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s(fp64-equivalent model)",
-                                 "frac": tf / fp64_peak, "kflop_per_draw": KFLOP_PER_DRAW[wl]},
-            "cpu_baseline": cpu, "mean_omega_first_1M": mean_omega,
+                                 "frac": tf / fp64_peak, "kflop_per_draw": dom_kflop, "kernel": dom_name,
+                                 "peak_source": "nominal B200 vector FP64 (no measured FP64 peak in MEASURED_PEAKS.json)"},
+            "cpu_baseline": cpu, "mean_omega_first_1M": mean_omega, "extras": extras,
         }
         print(json.dumps(out))
     if world > 1:

@@ -205,6 +205,12 @@ int bl_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2);
 /* Number of kernels this library has launched since load (bench accounting). */
 uint64_t bl_kernel_launches(void);
 
+/* Per-stage CUDA-event timing of the regime-binned rpg_hybrid path (measurement aid): after
+ * bl_hybrid_timing(1), bl_hybrid_timing_last() returns the milliseconds of
+ * [binning, saddle-point, alternate, sum-of-gammas, normal, Devroye] of the last launch. */
+void bl_hybrid_timing(int enable);
+int bl_hybrid_timing_last(double *ms6);
+
 #ifdef __cplusplus
 }
 #endif

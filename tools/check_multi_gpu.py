@@ -1,0 +1,60 @@
+#!/usr/bin/env python3
+"""Multi-GPU check (run under torchrun, one rank per GPU): the sharded logit chain with the
+in-stream NCCL all-reduce equals the single-GPU chain, and the sampler's shards equal the
+unsharded batch.  Prints MULTI_GPU_OK on rank 0."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bayeslogit_b200 import _lib, dist as bdist  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+L = _lib.lib()
+_lib.check(L.bl_set_device(local))
+dist.init_process_group("nccl", device_id=dev)
+
+rng = np.random.default_rng(0)
+N, P, samp, burn = 200_003, 16, 12, 4
+X = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
+bt = np.r_[np.abs(rng.normal(0, 0.3, P - 1)), -0.5]
+y = (rng.random(N) < 1 / (1 + np.exp(-X @ bt))).astype(float)
+st = torch.cuda.current_stream().cuda_stream
+
+
+def chain(lo, hi, flags):
+    Xd = torch.from_numpy(X[lo:hi].copy()).to(dev); yd = torch.from_numpy(y[lo:hi].copy()).to(dev)
+    nd = torch.ones(hi - lo, device=dev, dtype=torch.float64)
+    m0 = torch.zeros(P, device=dev, dtype=torch.float64)
+    P0 = (0.1 * torch.eye(P, device=dev, dtype=torch.float64)).contiguous()
+    beta = torch.zeros(samp, P, device=dev, dtype=torch.float64)
+    w = torch.zeros(samp, hi - lo, device=dev, dtype=torch.float64)
+    rc = L.bl_logit_gibbs_dev(w.data_ptr(), beta.data_ptr(), yd.data_ptr(), Xd.data_ptr(), nd.data_ptr(),
+                              m0.data_ptr(), P0.data_ptr(), hi - lo, P, samp, burn, 4242, flags, lo, st)
+    if rc:
+        _lib.check(rc)
+    torch.cuda.synchronize()
+    return beta.cpu().numpy(), w.cpu().numpy()
+
+
+full = {f: chain(0, N, f) for f in (0, 1)}          # before the communicator exists: single-GPU chains
+bdist.init_comm(rank, world, dev)
+lo, hi = bdist.shard_range(rank, world, N)
+ok = True
+for f in (0, 1):
+    b, w = chain(lo, hi, f)
+    eb = np.max(np.abs(b - full[f][0]) / np.abs(full[f][0]))
+    ew = np.max(np.abs(w - full[f][1][:, lo:hi]) / full[f][1][:, lo:hi])
+    t = torch.tensor([eb, ew], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"flags={f}: world={world} max rel diff beta {t[0].item():.2e} omega {t[1].item():.2e}")
+    ok = ok and t.max().item() < 1e-8
+if rank == 0:
+    print("MULTI_GPU_OK" if ok else "MULTI_GPU_MISMATCH")
+dist.destroy_process_group()
