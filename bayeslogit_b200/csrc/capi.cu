@@ -153,6 +153,8 @@ int run_host(Method m, double *x, const void *shape, const double *z, int64_t nu
         cid.obs0 += (uint64_t)off;
         if (m == kHybrid && n >= kBinMin)
             BL_CK(launch_hybrid_binned(s.x, (const double *)s.shape, s.z, (int)n, cid, s.work, s.stream));
+        else if (m == kDevroye)
+            BL_CK(launch_devroye_refill(s.x, (const int *)s.shape, s.z, n, cid, s.stream, s.work));
         else
             BL_CK(launch_rpg(m, s.x, s.shape, s.z, n, trunc, iter ? s.iter : nullptr, cid, s.stream));
         BL_CK(cudaMemcpyAsync(x + off, s.x, n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
@@ -186,7 +188,7 @@ int run_dev(Method m, double *x, const void *shape, const double *z, int64_t num
         if (ensure_ready()) return 1;
     }
     if (num < 0) return fail("negative batch size");
-    if (m == kHybrid && num >= kBinMin) {
+    if ((m == kHybrid && num >= kBinMin) || (m == kDevroye && num >= (1 << 20))) {
         std::lock_guard<std::mutex> lock(g.mu);
         int64_t per = num < kBinMax ? num : kBinMax;
         size_t need = hybrid_workspace_bytes(per);
@@ -202,8 +204,12 @@ int run_dev(Method m, double *x, const void *shape, const double *z, int64_t num
             int64_t n = num - off < per ? num - off : per;
             StreamId cid = id;
             cid.obs0 += (uint64_t)off;
-            BL_CK(launch_hybrid_binned(x + off, (const double *)shape + off, z + off, (int)n, cid,
-                                       g.devwork, (cudaStream_t)stream));
+            if (m == kHybrid)
+                BL_CK(launch_hybrid_binned(x + off, (const double *)shape + off, z + off, (int)n, cid,
+                                           g.devwork, (cudaStream_t)stream));
+            else
+                BL_CK(launch_devroye_refill(x + off, (const int *)shape + off, z + off, n, cid,
+                                            (cudaStream_t)stream, g.devwork));
         }
         return 0;
     }

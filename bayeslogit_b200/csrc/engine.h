@@ -43,8 +43,9 @@ cudaError_t launch_probe_specfun(double *out, int which, const double *a, const 
 cudaError_t launch_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2,
                                 cudaStream_t stream);
 
+// `work` (optional, hybrid_workspace_bytes(num) bytes): enables branch-class binning for large batches
 cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int64_t num,
-                                  StreamId id, cudaStream_t stream);
+                                  StreamId id, cudaStream_t stream, void *work = nullptr);
 
 // rpg_hybrid through regime binning (pg_hybrid.cu); num <= 2^31-1, `work` = device scratch of
 // hybrid_workspace_bytes(num) bytes that stays valid until the stream has drained.

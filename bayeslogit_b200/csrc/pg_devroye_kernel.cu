@@ -23,9 +23,63 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kChunkObs = 128;
 
+// Branch-class binning (large batches): the left proposal is the inverse-chi^2 pair loop when
+// Z = |z|/2 < 1/0.64 and the inverse-Gaussian loop otherwise (PolyaGamma.cpp:87), a property of
+// the observation alone.  A counting sort of the observation indices by that class makes every
+// warp's chunk class-pure, so a warp runs two proposal branches instead of three.
+constexpr int kBinThreads = 256;
+
+__device__ __forceinline__ int dev_class(double z) { return fabs(z) * 0.5 >= 1.0 / kTrunc ? 1 : 0; }
+
+__global__ void __launch_bounds__(kBinThreads)
+k_cls_count(const double *__restrict__ z, int n, int *__restrict__ meta)
+{
+    int c = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += dev_class(z[i]);
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    __shared__ int tot;
+    if (threadIdx.x == 0) tot = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&tot, c);
+    __syncthreads();
+    if (threadIdx.x == 0 && tot) atomicAdd(&meta[0], tot);
+}
+
+__global__ void __launch_bounds__(kBinThreads)
+k_cls_scatter(const double *__restrict__ z, int n, int *__restrict__ meta, int *__restrict__ idx)
+{
+    __shared__ int wcnt[kBinThreads / 32][2];
+    __shared__ int base[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int off1 = n - meta[0];                                  // class 1 starts after all of class 0
+    int tiles = (n + kBinThreads - 1) / kBinThreads;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        int i = tile * kBinThreads + threadIdx.x;
+        int cls = i < n ? dev_class(z[i]) : -1;
+        unsigned m1 = __ballot_sync(0xffffffffu, cls == 1), m0 = __ballot_sync(0xffffffffu, cls == 0);
+        int rank = __popc((cls == 1 ? m1 : m0) & lt);
+        if (lane == 0) { wcnt[warp][0] = __popc(m0); wcnt[warp][1] = __popc(m1); }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            int t = 0;
+            for (int w = 0; w < kBinThreads / 32; ++w) t += wcnt[w][threadIdx.x];
+            base[threadIdx.x] = (threadIdx.x ? off1 : 0) + (t ? atomicAdd(&meta[1 + threadIdx.x], t) : 0);
+        }
+        __syncthreads();
+        if (cls >= 0) {
+            int off = base[cls];
+            for (int w = 0; w < warp; ++w) off += wcnt[w][cls];
+            idx[off + rank] = i;
+        }
+        __syncthreads();
+    }
+}
+
+template <bool kIndexed>
 __global__ void __launch_bounds__(kThreads)
 k_devroye_refill(double *__restrict__ x, const int *__restrict__ n, const double *__restrict__ z,
-                 int64_t num, StreamId id)
+                 int64_t num, StreamId id, const int *__restrict__ idx)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -50,6 +104,7 @@ k_devroye_refill(double *__restrict__ x, const int *__restrict__ n, const double
             int64_t cand = cur + rank;
             if (cand >= cend) cand += stride - kChunkObs;
             if (!active && cand < num) {
+                if (kIndexed) cand = idx[cand];                  // position in the class-sorted list -> observation
                 int ni = n[cand];
                 if (ni == 0) {
                     x[cand] = 0.0;                    // LogitWrapper.cpp:76-79
@@ -89,15 +144,27 @@ k_devroye_refill(double *__restrict__ x, const int *__restrict__ n, const double
 }  // namespace
 
 cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int64_t num,
-                                  StreamId id, cudaStream_t st)
+                                  StreamId id, cudaStream_t st, void *work)
 {
     if (num <= 0) return cudaSuccess;
     int64_t chunks = (num + kChunkObs - 1) / kChunkObs;
     int64_t blocks = (chunks + (kThreads / 32) - 1) / (kThreads / 32);
     int64_t cap = 148LL * 4;                 // 148 SMs x resident CTAs
     int grid = (int)(blocks < cap ? blocks : cap);
-    k_devroye_refill<<<grid, kThreads, 0, st>>>(x, n, z, num, id);
-    count_launch();
+    if (work && num >= (1 << 20) && num < (1LL << 31)) {
+        int *meta = (int *)work, *idx = meta + 32;
+        cudaError_t e = cudaMemsetAsync(meta, 0, 32 * sizeof(int), st);
+        if (e != cudaSuccess) return e;
+        int tiles = (int)((num + kBinThreads - 1) / kBinThreads);
+        int bgrid = tiles < 148 * 8 ? tiles : 148 * 8;
+        k_cls_count<<<bgrid, kBinThreads, 0, st>>>(z, (int)num, meta);
+        k_cls_scatter<<<bgrid, kBinThreads, 0, st>>>(z, (int)num, meta, idx);
+        k_devroye_refill<true><<<grid, kThreads, 0, st>>>(x, n, z, num, id, idx);
+        count_launch(3);
+    } else {
+        k_devroye_refill<false><<<grid, kThreads, 0, st>>>(x, n, z, num, id, nullptr);
+        count_launch();
+    }
     return cudaGetLastError();
 }
 
