@@ -31,6 +31,23 @@ namespace bl {
 
 constexpr double kTrunc = 0.64;  // PolyaGamma.h:37
 
+// Out-of-line libm entry points for the big samplers (alternate, saddle point).  Inlined,
+// every log/exp/tan/... call site carries its own 40-200 instruction body and the saddle-point
+// kernel grows to ~140 KB of SASS: its profile (profiles/r1_05_*) showed 15 of 20 stall cycles
+// per instruction waiting on instruction fetch.  One shared body per function keeps the kernels
+// near the instruction cache; results are unchanged (same libdevice code).
+namespace ool {
+static __device__ __noinline__ double log_(double x) { return ::log(x); }
+static __device__ __noinline__ double exp_(double x) { return ::exp(x); }
+static __device__ __noinline__ double tan_(double x) { return ::tan(x); }
+static __device__ __noinline__ double tanh_(double x) { return ::tanh(x); }
+static __device__ __noinline__ double cos_(double x) { return ::cos(x); }
+static __device__ __noinline__ double cosh_(double x) { return ::cosh(x); }
+static __device__ __noinline__ double atan_(double x) { return ::atan(x); }
+static __device__ __noinline__ double lgamma_(double x) { return ::lgamma(x); }
+static __device__ __noinline__ double tgamma_(double x) { return ::tgamma(x); }
+}  // namespace ool
+
 // ----------------------------------------------------------------------------
 // Devroye PG(1,z)
 // ----------------------------------------------------------------------------
@@ -233,13 +250,13 @@ __device__ __noinline__ double ltgamma(Src &s, double shape, double rate, double
     double d1 = b - a;
     double d3 = a - 1.0;
     double c0 = 0.5 * (d1 + sqrt(d1 * d1 + 4.0 * b)) / b;
-    double l_M = d3 * log(d3 / (1.0 - c0)) - d3;
+    double l_M = d3 * ool::log_(d3 / (1.0 - c0)) - d3;
     double x;
     for (;;) {
         x = b + s.expon() / c0;
         double u = s.unif();
-        double l_rho = d3 * log(x) - x * (1.0 - c0);
-        if (log(u) <= l_rho - l_M) break;
+        double l_rho = d3 * ool::log_(x) - x * (1.0 - c0);
+        if (ool::log_(u) <= l_rho - l_M) break;
     }
     return trunc * (x / b);
 }
@@ -256,7 +273,7 @@ __device__ __forceinline__ double tnorm_left(Src &s, double left)
     double astar = 0.5 * (left + sqrt(left * left + 4.0));
     for (;;) {
         double z = s.expon() / astar + left;
-        double rho = exp(-0.5 * (z - astar) * (z - astar));
+        double rho = ool::exp_(-0.5 * (z - astar) * (z - astar));
         if (s.unif() < rho) return z;
     }
 }
@@ -297,8 +314,8 @@ __device__ __forceinline__ double alt_coef(double n, double x, double h, double 
     else
         g = 1.0;
     double coef = coef_h * g;
-    double log_kernel = -0.5 * (log(x * x * x) + d_n * d_n / x) + log(d_n);
-    return coef * exp(log_kernel);
+    double log_kernel = -0.5 * (ool::log_(x * x * x) + d_n * d_n / x) + ool::log_(d_n);
+    return coef * ool::exp_(log_kernel);
 }
 
 __device__ __forceinline__ double alt_pigauss(double x, double z, double lambda)
@@ -306,14 +323,14 @@ __device__ __forceinline__ double alt_pigauss(double x, double z, double lambda)
     double sq = sqrt(lambda / x);
     double b = sq * (x * z - 1);
     double a = sq * (x * z + 1) * -1.0;
-    return p_norm(b) + exp(2 * lambda * z) * p_norm(a);
+    return p_norm(b) + ool::exp_(2 * lambda * z) * p_norm(a);
 }
 
 __device__ __forceinline__ double alt_envelope(double x, double h, double trunc)
 {
     if (x > trunc)
-        return exp(h * log(0.5 * kPi) + (h - 1) * log(x) - kPi * kPi * 0.125 * x - lgamma(h));
-    return h * exp(h * log(2.0) - 0.5 * log(2.0 * kPi * x * x * x) - 0.5 * h * h / x);
+        return ool::exp_(h * ool::log_(0.5 * kPi) + (h - 1) * ool::log_(x) - kPi * kPi * 0.125 * x - ool::lgamma_(h));
+    return h * ool::exp_(h * ool::log_(2.0) - 0.5 * ool::log_(2.0 * kPi * x * x * x) - 0.5 * h * h / x);
 }
 
 template <class Src>
@@ -327,15 +344,15 @@ __device__ __noinline__ double alt_chunk(Src &s, double h, double z)
     double rate_z = 0.125 * kPi * kPi + 0.5 * z * z;
     double wl, wr;
     if (z != 0)
-        wl = exp(h * (log(2.0) - z)) * alt_pigauss(trunc, z / h, h * h);
+        wl = ool::exp_(h * (ool::log_(2.0) - z)) * alt_pigauss(trunc, z / h, h * h);
     else
-        wl = exp(h * log(2.0)) * (1.0 - p_gamma_rate(1 / trunc, 0.5, 0.5 * h * h));
+        wl = ool::exp_(h * ool::log_(2.0)) * (1.0 - p_gamma_rate(1 / trunc, 0.5, 0.5 * h * h));
     {
         double lambda_z = kPi * kPi * 0.125 + 0.5 * z * z;
-        wr = exp(h * log((0.5 * kPi) / lambda_z)) * (1.0 - p_gamma_rate(trunc, h, lambda_z));
+        wr = ool::exp_(h * ool::log_((0.5 * kPi) / lambda_z)) * (1.0 - p_gamma_rate(trunc, h, lambda_z));
     }
     double prob_right = wr / (wr + wl);
-    double coef1_h = exp(h * log(2.0) - 0.5 * log(2.0 * kPi));
+    double coef1_h = ool::exp_(h * ool::log_(2.0) - 0.5 * ool::log_(2.0 * kPi));
     double g = 1.0;
     for (int trial = 0; trial < 10000; ++trial) {
         double X;
@@ -349,7 +366,7 @@ __device__ __noinline__ double alt_chunk(Src &s, double h, double z)
                 double alpha = 0.0;
                 while (s.unif() > alpha) {
                     X = alt_rtinvchi2(s, h, trunc);
-                    alpha = exp(-0.5 * z * z * X);
+                    alpha = ool::exp_(-0.5 * z * z * X);
                 }
             } else {
                 while (X > trunc) X = igauss(s, mu, h * h);
@@ -396,160 +413,11 @@ __device__ double alt_draw(Src &s, double h, double z)
     return x;
 }
 
-// ----------------------------------------------------------------------------
-// y(v) inversion and the saddle-point sampler
-// ----------------------------------------------------------------------------
+}  // namespace bl
 
-// y(v): the series branch is the constant 1 because the reference's coefficients
-// (1/3), (2/15), (17/315) are integer divisions (InvertY.cpp:19, PolyaGammaSP.cpp:88).
-__device__ __forceinline__ double y_of_v(double v, double tol)
-{
-    double r = sqrt(fabs(v));
-    if (v > tol) return tan(r) / r;
-    if (v < -1 * tol) return tanh(r) / r;
-    return 1.0;
-}
+#include "pg_sp.cuh"   // y(v) inversion and the saddle-point sampler
 
-static __device__ __noinline__ double v_eval(double y)
-{
-    const double tol = 1e-9;
-    const int max_iter = 1000;
-    if (y < PG_YGRID[0]) return -1. / (y * y);
-    if (y > PG_YGRID[PG_YGRID_LEN - 1]) {
-        double v = atan(0.5 * y * kPi);
-        return v * v;
-    }
-    if (y == 1) return 0.0;
-    double id = (log(y) / log(2.0) + 4.0) / 0.1;
-    int idlow = (int)id;
-    int idhigh = idlow + 1;
-    if (idhigh > PG_VGRID_LEN - 1) idhigh = PG_VGRID_LEN - 1;  // y == 16 exactly, see DESIGN.md
-    double vl = PG_VGRID[idlow];
-    double vh = PG_VGRID[idhigh];
-    int iter = 0;
-    double diff = tol + 1.0;
-    double vnew = vl, vold = vl;
-    while (diff > tol && iter < max_iter) {
-        iter++;
-        vold = vnew;
-        double yv = y_of_v(vold, 1e-8);
-        double f0 = yv - y;
-        double f1;
-        if (fabs(vold) >= 1e-8)
-            f1 = 0.5 * (yv * yv + (1 - yv) / vold);
-        else
-            f1 = 0.5 * (yv * yv);
-        vnew = vold - f0 / f1;
-        vnew = vnew > vh ? vh : vnew;
-        vnew = vnew < vl ? vl : vnew;
-        diff = fabs(vnew - vold);
-    }
-    return vnew;
-}
-
-__device__ __forceinline__ double sp_cos_rt(double v)
-{
-    double r = sqrt(fabs(v));
-    return v >= 0 ? cos(r) : cosh(r);
-}
-
-static __device__ __noinline__ void sp_tangent(double x, double z, double mid, double &slope, double &icept)
-{
-    double v = v_eval(x);
-    double u = 0.5 * v;
-    double t = u + 0.5 * z * z;
-    double phi_val = log(cosh(fabs(z))) - log(sp_cos_rt(v)) - t * x;
-    double phi_der = -1.0 * t;
-    double delta_val, delta_der;
-    if (x >= mid) {
-        delta_val = log(x) - log(mid);
-        delta_der = 1.0 / x;
-    } else {
-        delta_val = 0.5 * (1 - 1.0 / x) - 0.5 * (1 - 1.0 / mid);
-        delta_der = 0.5 / (x * x);
-    }
-    double eta_val = phi_val - delta_val;
-    double eta_der = phi_der - delta_der;
-    slope = eta_der;
-    icept = eta_val - eta_der * x;
-}
-
-static __device__ __noinline__ double sp_density(double x, double n, double z)
-{
-    double v = v_eval(x);
-    double u = 0.5 * v;
-    double z2 = z * z;
-    double t = u + 0.5 * z2;
-    double phi = log(cosh(z)) - log(sp_cos_rt(v)) - t * x;
-    double K2;
-    if (fabs(v) >= 1e-6)
-        K2 = x * x + (1 - x) / v;
-    else
-        K2 = x * x;
-    double log_spa = 0.5 * log(0.5 * n / kPi) - 0.5 * log(K2) + n * phi;
-    return exp(log_spa);
-}
-
-template <class Src>
-__device__ int sp_draw(Src &s, double &d, double n, double z)
-{
-    const int maxiter = 200;
-    z = 0.5 * fabs(z);
-    double xl = y_of_v(-1 * z * z, 1e-6);
-    double md = xl * 1.1;
-    double xr = xl * 1.2;
-    double vmd = v_eval(md);
-    double K2md;
-    if (fabs(vmd) >= 1e-6)
-        K2md = md * md + (1 - md) / vmd;
-    else
-        K2md = md * md;
-    double m2 = md * md;
-    double al = m2 * md / K2md;
-    double ar = m2 / K2md;
-    double sl, il, sr, ir;
-    sp_tangent(xl, z, md, sl, il);
-    sp_tangent(xr, z, md, sr, ir);
-    double rl = -1. * sl;
-    double rr = -1. * sr;
-    double lcn = 0.5 * log(0.5 * n / kPi);
-    double rt2rl = sqrt(2 * rl);
-    double wl = exp(0.5 * log(al) - n * rt2rl + n * il + 0.5 * n * 1. / md) * p_igauss(md, 1. / rt2rl, n);
-    double wr = exp(0.5 * log(ar) + lcn - n * log(n * rr) + n * ir - n * log(md)) * tgamma(n)
-              * (1.0 - p_gamma_rate(md, n, n * rr));
-    double wt = wl + wr;
-    double pl = wl / wt;
-    bool go = true;
-    int iter = 0;
-    double X = 2.0, F = 0.0;
-    while (go && iter < maxiter) {
-        iter++;
-        double phi_ev;
-        if (s.unif() < pl) {
-            double mu = 1. / rt2rl;
-            X = md + 1.0;
-            if (md < mu) {
-                double alpha = 0.0;
-                while (s.unif() > alpha) {
-                    X = rtinvchi2(s, n, md);
-                    alpha = exp(-0.5 * n / (mu * mu) * X);
-                }
-            } else {
-                while (X > md) X = igauss(s, mu, n);
-            }
-            phi_ev = n * (il - rl * X) + 0.5 * n * ((1. - 1. / X) - (1. - 1. / md));
-            F = exp(0.5 * log(al) + lcn - 1.5 * log(X) + phi_ev);
-        } else {
-            X = ltgamma(s, n, n * rr, md);
-            phi_ev = n * (ir - rr * X) + n * (log(X) - log(md));
-            F = exp(0.5 * log(ar) + lcn + phi_ev) / X;
-        }
-        double spa = sp_density(X, n, z);
-        if (F * s.unif() < spa) go = false;
-    }
-    d = n * 0.25 * X;
-    return iter;
-}
+namespace bl {
 
 // ----------------------------------------------------------------------------
 // Regime dispatch

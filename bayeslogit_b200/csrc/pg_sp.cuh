@@ -1,0 +1,280 @@
+// Saddle-point Polya-Gamma sampler J*(n, |z|/2)/n for large shape (fp64).
+//
+// Reference statements this file has to agree with:
+//   v_eval                y -> v            InvertY.cpp:57-99 (+ :10-48)
+//   sp_setup              envelope set-up   PolyaGammaSP.cpp:169-226 (+ :78-146)
+//   sp_loop               propose / accept  PolyaGammaSP.cpp:228-264 (+ :57-76, :148-167)
+//
+// The sampler is split in two so that the binned rpg_hybrid path (pg_hybrid.cu) can run the
+// set-up and the rejection loop as two kernels with a 12-double state per draw in HBM: one
+// monolithic kernel was ~110-140 KB of SASS against a 32 KB instruction cache and spent 15 of
+// every 20 stall cycles waiting for instructions (profiles/r1_05_*).  The per-lane kernels and
+// the tape path call both halves back to back (sp_draw).
+//
+// y -> v.  The reference runs Newton from an 81-point grid until |dv| <= 1e-9 -- the root to fp64
+// rounding -- and clamps every iterate to the grid bracket.  Here V(y) and G(y) = log cos_rt(V(y))
+// come from degree-9 polynomials on 128 binary intervals (tools/gen_sp_tables.py; fp64 Horner
+// error < 2e-16 max(1,|.|)), which removes the tan/tanh Newton loop, the sqrt and the log from
+// every evaluation.  The reference's own iteration (v_eval_ref) still runs wherever its result is
+// NOT the plain root: y outside [2^-4, 2^4) (closed forms), y within 5e-5 (2e-4 above y = 2) grid steps of a grid
+// point (iterates clamped to the 7-digit table), and |y - 1| < 1e-6 (series branch).
+#pragma once
+
+#include "pg_sp_tables.h"
+
+namespace bl {
+
+// y(v): the series branch is the constant 1 because the reference's coefficients
+// (1/3), (2/15), (17/315) are integer divisions (InvertY.cpp:19, PolyaGammaSP.cpp:88).
+__device__ __forceinline__ double y_of_v(double v, double tol)
+{
+    double r = sqrt(fabs(v));
+    if (v > tol) return ool::tan_(r) / r;
+    if (v < -1 * tol) return ool::tanh_(r) / r;
+    return 1.0;
+}
+
+// InvertY.cpp:57-99 as written
+static __device__ __noinline__ double v_eval_ref(double y)
+{
+    const double tol = 1e-9;
+    const int max_iter = 1000;
+    if (y < PG_YGRID[0]) return -1. / (y * y);
+    if (y > PG_YGRID[PG_YGRID_LEN - 1]) {
+        double v = ool::atan_(0.5 * y * kPi);
+        return v * v;
+    }
+    if (y == 1) return 0.0;
+    double id = (ool::log_(y) / ool::log_(2.0) + 4.0) / 0.1;
+    int idlow = (int)id;
+    int idhigh = idlow + 1;
+    if (idhigh > PG_VGRID_LEN - 1) idhigh = PG_VGRID_LEN - 1;  // y == 16 exactly, see DESIGN.md
+    double vl = PG_VGRID[idlow];
+    double vh = PG_VGRID[idhigh];
+    int iter = 0;
+    double diff = tol + 1.0;
+    double vnew = vl, vold = vl;
+    while (diff > tol && iter < max_iter) {
+        iter++;
+        vold = vnew;
+        double yv = y_of_v(vold, 1e-8);
+        double f0 = yv - y;
+        double f1;
+        if (fabs(vold) >= 1e-8)
+            f1 = 0.5 * (yv * yv + (1 - yv) / vold);
+        else
+            f1 = 0.5 * (yv * yv);
+        vnew = vold - f0 / f1;
+        vnew = vnew > vh ? vh : vnew;
+        vnew = vnew < vl ? vl : vnew;
+        diff = fabs(vnew - vold);
+    }
+    return vnew;
+}
+
+__device__ __forceinline__ double sp_cos_rt(double v)
+{
+    double r = sqrt(fabs(v));
+    return v >= 0 ? ool::cos_(r) : ool::cosh_(r);
+}
+
+// Table path of (V, G); false when the reference's iteration has to decide (see header).
+__device__ __forceinline__ bool sp_vg_table(double y, double &v, double &g)
+{
+    if (!(y >= 0.0625 && y < 16.0)) return false;
+    if (fabs(y - 1.0) < 1e-6) return false;
+    // Position inside the reference's grid in grid steps; fp32 log2 leaves |err| < 1.5e-5 steps.
+    // The grid's 7-digit v values sit within 5e-6 steps of the true roots for y < 2 and within
+    // 3.8e-5 steps up to y = 16 (tools/gen_sp_tables.py --check-grid), hence the two margins.
+    float tt = (__log2f((float)y) + 4.0f) * 10.0f;
+    float fr = tt - floorf(tt);
+    float margin = tt > 48.0f ? 2e-4f : 5e-5f;
+    if (fr < margin || fr > 1.0f - margin) return false;
+    int hi = __double2hiint(y), lo = __double2loint(y);
+    int e = (hi >> 20) - 1023;                       // -4 .. 3
+    int j = (hi >> (20 - SP_TAB_K)) & ((1 << SP_TAB_K) - 1);
+    double f = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);   // mantissa in [1,2)
+    double u = (f - 1.0) * (double)(2 << SP_TAB_K) - (double)(2 * j + 1);   // exact
+    int row = ((e - SP_TAB_ELO) << SP_TAB_K) + j;
+    const double2 *cv = reinterpret_cast<const double2 *>(SP_VTAB + row * (SP_TAB_DEG + 1));
+    const double2 *cg = reinterpret_cast<const double2 *>(SP_GTAB + row * (SP_TAB_DEG + 1));
+    double2 a = __ldg(cv), b = __ldg(cg);
+    double pv = fma(a.x, u, a.y), pg = fma(b.x, u, b.y);
+#pragma unroll
+    for (int k = 1; k < (SP_TAB_DEG + 1) / 2; ++k) {
+        a = __ldg(cv + k);
+        b = __ldg(cg + k);
+        pv = fma(fma(pv, u, a.x), u, a.y);
+        pg = fma(fma(pg, u, b.x), u, b.y);
+    }
+    v = pv;
+    g = pg;
+    return true;
+}
+
+static __device__ __noinline__ void sp_vg_ref(double y, double &v, double &g)
+{
+    v = v_eval_ref(y);
+    g = ool::log_(sp_cos_rt(v));
+}
+
+__device__ __forceinline__ void sp_vg(double y, double &v, double &g)
+{
+    if (!sp_vg_table(y, v, g)) sp_vg_ref(y, v, g);
+}
+
+// what the engine uses for InvertY.cpp's v_eval
+__device__ __forceinline__ double v_eval(double y)
+{
+    double v, g;
+    if (sp_vg_table(y, v, g)) return v;
+    return v_eval_ref(y);
+}
+
+// Envelope of one draw: everything PolyaGammaSP.cpp:176-226 computes before its loop.
+struct SpState {
+    double md;      // mid point 1.1 xl, PolyaGammaSP.cpp:183
+    double pl;      // mass of the left (inverse-Gaussian) piece, :226
+    double rt2rl;   // sqrt(2 rl), :216
+    double rl, il;  // left tangent line: rate -slope and intercept, :209-214
+    double rr, ir;  // right tangent line
+    double cl, cr;  // 0.5 log(al) + lcn and 0.5 log(ar) + lcn, :245, :252
+    double lmd;     // log(md)
+    double lcz;     // log cosh(|z|/2)
+    double lcn;     // 0.5 log(n / 2 pi), :215
+};
+constexpr int kSpStateDoubles = 12;
+
+// PolyaGammaSP.cpp:128-146 (tangent_to_eta) with phi_func :115-126 and delta_func :103-113
+__device__ __forceinline__ void sp_tangent(double x, double z, double mid, double lcz, double &slope,
+                                           double &icept)
+{
+    double v, g;
+    sp_vg(x, v, g);
+    double u = 0.5 * v;
+    double t = u + 0.5 * z * z;
+    double phi_val = lcz - g - t * x;
+    double phi_der = -1.0 * t;
+    double delta_val, delta_der;
+    if (x >= mid) {
+        delta_val = ool::log_(x) - ool::log_(mid);
+        delta_der = 1.0 / x;
+    } else {
+        delta_val = 0.5 * (1 - 1.0 / x) - 0.5 * (1 - 1.0 / mid);
+        delta_der = 0.5 / (x * x);
+    }
+    double eta_val = phi_val - delta_val;
+    double eta_der = phi_der - delta_der;
+    slope = eta_der;
+    icept = eta_val - eta_der * x;
+}
+
+// n: shape, zraw: tilting parameter as passed to the sampler (the halving is done here)
+__device__ __forceinline__ void sp_setup(double n, double zraw, SpState &s)
+{
+    double z = 0.5 * fabs(zraw);
+    double xl = y_of_v(-1 * z * z, 1e-6);
+    double md = xl * 1.1;
+    double xr = xl * 1.2;
+    double vmd = v_eval(md);
+    double K2md;
+    if (fabs(vmd) >= 1e-6)
+        K2md = md * md + (1 - md) / vmd;
+    else
+        K2md = md * md;
+    double m2 = md * md;
+    double al = m2 * md / K2md;
+    double ar = m2 / K2md;
+    double lcz = ool::log_(ool::cosh_(z));
+    double sl, il, sr, ir;
+    sp_tangent(xl, z, md, lcz, sl, il);
+    sp_tangent(xr, z, md, lcz, sr, ir);
+    double rl = -1. * sl;
+    double rr = -1. * sr;
+    double lcn = 0.5 * ool::log_(0.5 * n / kPi);
+    double rt2rl = sqrt(2 * rl);
+    double hla = 0.5 * ool::log_(al), hra = 0.5 * ool::log_(ar), lmd = ool::log_(md);
+    double wl = ool::exp_(hla - n * rt2rl + n * il + 0.5 * n * 1. / md) * p_igauss(md, 1. / rt2rl, n);
+    double wr = ool::exp_(hra + lcn - n * ool::log_(n * rr) + n * ir - n * lmd) * ool::tgamma_(n)
+              * (1.0 - p_gamma_rate(md, n, n * rr));
+    double wt = wl + wr;
+    s.md = md;
+    s.pl = wl / wt;
+    s.rt2rl = rt2rl;
+    s.rl = rl;
+    s.il = il;
+    s.rr = rr;
+    s.ir = ir;
+    s.cl = hla + lcn;
+    s.cr = hra + lcn;
+    s.lmd = lmd;
+    s.lcz = lcz;
+    s.lcn = lcn;
+}
+
+// PolyaGammaSP.cpp:148-167 (sp_approx)
+__device__ __forceinline__ double sp_density(double x, double n, double z, const SpState &s)
+{
+    double v, g;
+    sp_vg(x, v, g);
+    double u = 0.5 * v;
+    double z2 = z * z;
+    double t = u + 0.5 * z2;
+    double phi = s.lcz - g - t * x;
+    double K2;
+    if (fabs(v) >= 1e-6)
+        K2 = x * x + (1 - x) / v;
+    else
+        K2 = x * x;
+    double log_spa = s.lcn - 0.5 * ool::log_(K2) + n * phi;
+    return ool::exp_(log_spa);
+}
+
+// The rejection loop, PolyaGammaSP.cpp:228-264: returns the number of proposals, d = n X / 4.
+template <class Src>
+__device__ __forceinline__ int sp_loop(Src &src, double &d, double n, double zraw, const SpState &s)
+{
+    const int maxiter = 200;
+    double z = 0.5 * fabs(zraw);
+    const double md = s.md;
+    bool go = true;
+    int iter = 0;
+    double X = 2.0, F = 0.0;
+    while (go && iter < maxiter) {
+        iter++;
+        double phi_ev;
+        if (src.unif() < s.pl) {
+            double mu = 1. / s.rt2rl;
+            X = md + 1.0;
+            if (md < mu) {
+                double alpha = 0.0;
+                while (src.unif() > alpha) {
+                    X = rtinvchi2(src, n, md);
+                    alpha = ool::exp_(-0.5 * n / (mu * mu) * X);
+                }
+            } else {
+                while (X > md) X = igauss(src, mu, n);
+            }
+            phi_ev = n * (s.il - s.rl * X) + 0.5 * n * ((1. - 1. / X) - (1. - 1. / md));
+            F = ool::exp_(s.cl - 1.5 * ool::log_(X) + phi_ev);
+        } else {
+            X = ltgamma(src, n, n * s.rr, md);
+            phi_ev = n * (s.ir - s.rr * X) + n * (ool::log_(X) - s.lmd);
+            F = ool::exp_(s.cr + phi_ev) / X;
+        }
+        double spa = sp_density(X, n, z, s);
+        if (F * src.unif() < spa) go = false;
+    }
+    d = n * 0.25 * X;
+    return iter;
+}
+
+template <class Src>
+__device__ int sp_draw(Src &src, double &d, double n, double z)
+{
+    SpState s;
+    sp_setup(n, z, s);
+    return sp_loop(src, d, n, z, s);
+}
+
+}  // namespace bl

@@ -111,9 +111,11 @@ struct PhiloxSource {
 
     __device__ __forceinline__ double unif() { return word_to_unif(word()); }
 
-    __device__ __forceinline__ double expon() { return exact(expon_lazy()); }
+    // Out of line like refill(): the big samplers (alternate, saddle point) have many call sites
+    // and live or die by their code footprint; the Devroye fast path uses the lazy forms above.
+    __device__ __noinline__ double expon() { return exact(expon_lazy()); }
 
-    __device__ __forceinline__ double norm() { return exact(norm_lazy()); }
+    __device__ __noinline__ double norm() { return exact(norm_lazy()); }
 
     __device__ double gamma(double a)
     {
