@@ -122,10 +122,10 @@ k_hyb_regime(double *__restrict__ x, const double *__restrict__ h, const double 
     }
 }
 
-// Saddle-point regime as two kernels (pg_sp.cuh): set-up -> 12-double state per draw in HBM
+// Saddle-point regime as two kernels (pg_sp.cuh): set-up -> 15-double state per draw in HBM
 // (struct of arrays over the chunk, coalesced) -> rejection loop.  Each kernel's working set of
-// code stays near the 32 KB instruction cache; the state costs 192 B of HBM traffic per draw,
-// ~1.5 % of HBM bandwidth at the rates these kernels reach.
+// code stays near the 32 KB instruction cache; the state costs 240 B of HBM traffic per draw,
+// ~2 % of HBM bandwidth at the rates these kernels reach.
 __global__ void __launch_bounds__(128)
 k_sp_setup(const double *__restrict__ h, const double *__restrict__ z, const int *__restrict__ idx,
            const int *__restrict__ meta, double *__restrict__ state, int c0, int cap)
@@ -136,50 +136,72 @@ k_sp_setup(const double *__restrict__ h, const double *__restrict__ z, const int
         int i = list[j];
         SpState s;
         sp_setup(h[i], z[i], s);
-        double *o = state + j;
-        o[0 * (size_t)cap] = s.md;
-        o[1 * (size_t)cap] = s.pl;
-        o[2 * (size_t)cap] = s.rt2rl;
-        o[3 * (size_t)cap] = s.rl;
-        o[4 * (size_t)cap] = s.il;
-        o[5 * (size_t)cap] = s.rr;
-        o[6 * (size_t)cap] = s.ir;
-        o[7 * (size_t)cap] = s.cl;
-        o[8 * (size_t)cap] = s.cr;
-        o[9 * (size_t)cap] = s.lmd;
-        o[10 * (size_t)cap] = s.lcz;
-        o[11 * (size_t)cap] = s.lcn;
+#pragma unroll
+        for (int k = 0; k < kSpStateDoubles; ++k) state[(size_t)k * cap + j] = s.f[k];
     }
 }
 
-__global__ void __launch_bounds__(128)
+// Rejection loop on persistent lanes: a lane makes one trip (sp_trip) per pass and, when its draw
+// is complete, takes the next list position of its warp's chunk through a ballot-compacted
+// refill, so rejected proposals and slow inner loops of one draw do not idle the other 31 lanes.
+constexpr int kSpLoopThreads = 128;
+constexpr int kSpLaneChunk = 128;   // consecutive list positions a warp works through
+
+__global__ void __launch_bounds__(kSpLoopThreads)
 k_sp_loop(double *__restrict__ x, const double *__restrict__ h, const double *__restrict__ z,
           const int *__restrict__ idx, const int *__restrict__ meta, const double *__restrict__ state,
           int c0, int cap, StreamId id)
 {
+    const unsigned full = 0xffffffffu;
     const int count = min(meta[kMetaCounts + kRegSP] - c0, cap);
+    if (count <= 0) return;
     const int *list = idx + meta[kMetaOffsets + kRegSP] + c0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
-        int i = list[j];
-        const double *o = state + j;
-        SpState s;
-        s.md = o[0 * (size_t)cap];
-        s.pl = o[1 * (size_t)cap];
-        s.rt2rl = o[2 * (size_t)cap];
-        s.rl = o[3 * (size_t)cap];
-        s.il = o[4 * (size_t)cap];
-        s.rr = o[5 * (size_t)cap];
-        s.ir = o[6 * (size_t)cap];
-        s.cl = o[7 * (size_t)cap];
-        s.cr = o[8 * (size_t)cap];
-        s.lmd = o[9 * (size_t)cap];
-        s.lcz = o[10 * (size_t)cap];
-        s.lcn = o[11 * (size_t)cap];
-        PhiloxSource src;
-        src.open(id.seed, id.obs0 + (uint64_t)i, id.call_id);
-        double d;
-        sp_loop(src, d, h[i], z[i], s);
-        x[i] = d;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int warp = blockIdx.x * (kSpLoopThreads / 32) + (threadIdx.x >> 5);
+    const int stride = gridDim.x * (kSpLoopThreads / 32) * kSpLaneChunk;
+
+    int cur = warp * kSpLaneChunk;     // next unassigned list position of this warp (uniform)
+    int cend = cur + kSpLaneChunk;     // end of the current chunk (uniform)
+
+    bool active = false;
+    int obs = 0;
+    double n = 0.0, zh = 0.0;
+    SpStateRef st{state, (size_t)cap};
+    SpLane L;
+    L.start();
+    PhiloxSource src;
+
+    for (;;) {
+        unsigned want = __ballot_sync(full, !active);
+        if (want && cur < count) {
+            int rank = __popc(want & lt_mask);
+            int cand = cur + rank;
+            if (cand >= cend) cand += stride - kSpLaneChunk;
+            if (!active && cand < count) {
+                obs = list[cand];
+                n = h[obs];
+                zh = 0.5 * fabs(z[obs]);
+                st.o = state + cand;
+                L.start();
+                src.open(id.seed, id.obs0 + (uint64_t)obs, id.call_id);
+                active = true;
+            }
+            cur += __popc(want);
+            if (cur >= cend) {
+                int over = cur - cend;
+                cend += stride;
+                cur = cend - kSpLaneChunk + over;
+            }
+        }
+        if (!__any_sync(full, active)) {
+            if (cur >= count) break;
+            continue;
+        }
+        if (active && sp_trip(src, L, n, zh, st)) {
+            x[obs] = n * 0.25 * L.X;
+            active = false;
+        }
     }
 }
 

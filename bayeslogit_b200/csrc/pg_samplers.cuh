@@ -286,135 +286,9 @@ __device__ __forceinline__ double rtinvchi2(Src &s, double scale, double trunc)
     return scale / (z * z);
 }
 
-// ----------------------------------------------------------------------------
-// Alternate sampler
-// ----------------------------------------------------------------------------
-
-template <class Src>
-__device__ __forceinline__ double alt_rtinvchi2(Src &s, double h, double trunc)
-{
-    double h2 = h * h;
-    double R = trunc / h2;
-    double E1 = s.expon();
-    double E2 = s.expon();
-    while ((E1 * E1) > (2 * E2 / R)) {
-        E1 = s.expon();
-        E2 = s.expon();
-    }
-    double X = 1 + E1 * R;
-    X = R / (X * X);
-    return h2 * X;
-}
-
-__device__ __forceinline__ double alt_coef(double n, double x, double h, double coef_h, double &g)
-{
-    double d_n = 2.0 * n + h;
-    if (n != 0)
-        g *= (n + h - 1) / n;
-    else
-        g = 1.0;
-    double coef = coef_h * g;
-    double log_kernel = -0.5 * (ool::log_(x * x * x) + d_n * d_n / x) + ool::log_(d_n);
-    return coef * ool::exp_(log_kernel);
-}
-
-__device__ __forceinline__ double alt_pigauss(double x, double z, double lambda)
-{
-    double sq = sqrt(lambda / x);
-    double b = sq * (x * z - 1);
-    double a = sq * (x * z + 1) * -1.0;
-    return p_norm(b) + ool::exp_(2 * lambda * z) * p_norm(a);
-}
-
-__device__ __forceinline__ double alt_envelope(double x, double h, double trunc)
-{
-    if (x > trunc)
-        return ool::exp_(h * ool::log_(0.5 * kPi) + (h - 1) * ool::log_(x) - kPi * kPi * 0.125 * x - ool::lgamma_(h));
-    return h * ool::exp_(h * ool::log_(2.0) - 0.5 * ool::log_(2.0 * kPi * x * x * x) - 0.5 * h * h / x);
-}
-
-template <class Src>
-__device__ __noinline__ double alt_chunk(Src &s, double h, double z)
-{
-    const int max_inner = 200;
-    if (h < 1 || h > 4) return 0;
-    z = fabs(z) * 0.5;
-    int idx = (int)floor((h - 1.0) * 100.0);
-    double trunc = PG_TRUNC_SCHEDULE[idx];
-    double rate_z = 0.125 * kPi * kPi + 0.5 * z * z;
-    double wl, wr;
-    if (z != 0)
-        wl = ool::exp_(h * (ool::log_(2.0) - z)) * alt_pigauss(trunc, z / h, h * h);
-    else
-        wl = ool::exp_(h * ool::log_(2.0)) * (1.0 - p_gamma_rate(1 / trunc, 0.5, 0.5 * h * h));
-    {
-        double lambda_z = kPi * kPi * 0.125 + 0.5 * z * z;
-        wr = ool::exp_(h * ool::log_((0.5 * kPi) / lambda_z)) * (1.0 - p_gamma_rate(trunc, h, lambda_z));
-    }
-    double prob_right = wr / (wr + wl);
-    double coef1_h = ool::exp_(h * ool::log_(2.0) - 0.5 * ool::log_(2.0 * kPi));
-    double g = 1.0;
-    for (int trial = 0; trial < 10000; ++trial) {
-        double X;
-        double uu = s.unif();
-        if (uu < prob_right) {
-            X = ltgamma(s, h, rate_z, trunc);
-        } else {
-            double mu = h / z;
-            X = trunc + 1.0;
-            if (mu > trunc) {
-                double alpha = 0.0;
-                while (s.unif() > alpha) {
-                    X = alt_rtinvchi2(s, h, trunc);
-                    alpha = ool::exp_(-0.5 * z * z * X);
-                }
-            } else {
-                while (X > trunc) X = igauss(s, mu, h * h);
-            }
-        }
-        double S = alt_coef(0.0, X, h, coef1_h, g);
-        double a_n = S;
-        double gt = alt_envelope(X, h, trunc);
-        double Y = s.unif() * gt;
-        int n = 0;
-        bool go = true;
-        while (go && n < max_inner) {
-            ++n;
-            double prev = a_n;
-            a_n = alt_coef((double)n, X, h, coef1_h, g);
-            bool decreasing = a_n <= prev;
-            if (n & 1) {
-                S = S - a_n;
-                if (Y <= S && decreasing) return 0.25 * X;
-            } else {
-                S = S + a_n;
-                if (Y > S && decreasing) go = false;
-            }
-        }
-    }
-    return -1.0;
-}
-
-template <class Src>
-__device__ double alt_draw(Src &s, double h, double z)
-{
-    if (h < 1) return 0;
-    double n = floor((h - 1.0) / 4.0);
-    double remain = h - 4.0 * n;
-    double x = 0.0;
-    for (int i = 0; i < (int)n; i++) x += alt_chunk(s, 4.0, z);
-    if (remain > 4.0) {
-        double first = alt_chunk(s, 0.5 * remain, z);
-        double second = alt_chunk(s, 0.5 * remain, z);
-        x += first + second;
-    } else {
-        x += alt_chunk(s, remain, z);
-    }
-    return x;
-}
-
 }  // namespace bl
 
+#include "pg_alt.cuh"  // alternate sampler, 1 <= shape, in chunks of at most 4
 #include "pg_sp.cuh"   // y(v) inversion and the saddle-point sampler
 
 namespace bl {

@@ -131,19 +131,36 @@ __device__ __forceinline__ double v_eval(double y)
     return v_eval_ref(y);
 }
 
-// Envelope of one draw: everything PolyaGammaSP.cpp:176-226 computes before its loop.
-struct SpState {
-    double md;      // mid point 1.1 xl, PolyaGammaSP.cpp:183
-    double pl;      // mass of the left (inverse-Gaussian) piece, :226
-    double rt2rl;   // sqrt(2 rl), :216
-    double rl, il;  // left tangent line: rate -slope and intercept, :209-214
-    double rr, ir;  // right tangent line
-    double cl, cr;  // 0.5 log(al) + lcn and 0.5 log(ar) + lcn, :245, :252
-    double lmd;     // log(md)
-    double lcz;     // log cosh(|z|/2)
-    double lcn;     // 0.5 log(n / 2 pi), :215
+// Envelope of one draw: everything PolyaGammaSP.cpp:176-226 computes before its loop, plus the
+// constants of the right piece's left-truncated-gamma sampler (Ch.R:83-114 computes them on
+// every call from the same three arguments).
+enum SpField {
+    kSpMd = 0,   // mid point 1.1 xl, PolyaGammaSP.cpp:183
+    kSpPl,       // mass of the left (inverse-Gaussian) piece, :226
+    kSpRt2rl,    // sqrt(2 rl), :216
+    kSpRl, kSpIl,   // left tangent line: rate (-slope) and intercept, :209-214
+    kSpRr, kSpIr,   // right tangent line
+    kSpCl, kSpCr,   // 0.5 log(al) + lcn and 0.5 log(ar) + lcn, :245, :252
+    kSpLmd,      // log(md)
+    kSpLcz,      // log cosh(|z|/2)
+    kSpLcn,      // 0.5 log(n / 2 pi), :215
+    kSpLtB, kSpLtC0, kSpLtLM,   // ltgamma(n, n rr, md): b = rate * trunc, c0, log M
+    kSpStateDoubles
 };
-constexpr int kSpStateDoubles = 12;
+
+// by value (per-lane kernels, tape path)
+struct SpState {
+    double f[kSpStateDoubles];
+    __device__ __forceinline__ double get(int k) const { return f[k]; }
+};
+
+// in HBM, struct of arrays over a chunk of `cap` draws (binned path): fields are fetched where
+// they are used instead of being held in 30 registers across the whole rejection loop
+struct SpStateRef {
+    const double *o;
+    size_t cap;
+    __device__ __forceinline__ double get(int k) const { return __ldg(o + (size_t)k * cap); }
+};
 
 // PolyaGammaSP.cpp:128-146 (tangent_to_eta) with phi_func :115-126 and delta_func :103-113
 __device__ __forceinline__ void sp_tangent(double x, double z, double mid, double lcz, double &slope,
@@ -167,6 +184,14 @@ __device__ __forceinline__ void sp_tangent(double x, double z, double mid, doubl
     double eta_der = phi_der - delta_der;
     slope = eta_der;
     icept = eta_val - eta_der * x;
+}
+
+// Weight of the right (gamma) piece as PolyaGammaSP.cpp:220-223 writes it
+static __device__ __noinline__ double sp_wr_ref(double hra, double lcn, double n, double rr, double ir,
+                                                double lmd, double md)
+{
+    return ool::exp_(hra + lcn - n * ool::log_(n * rr) + n * ir - n * lmd) * ool::tgamma_(n)
+         * (1.0 - p_gamma_rate(md, n, n * rr));
 }
 
 // n: shape, zraw: tilting parameter as passed to the sampler (the halving is done here)
@@ -194,79 +219,136 @@ __device__ __forceinline__ void sp_setup(double n, double zraw, SpState &s)
     double lcn = 0.5 * ool::log_(0.5 * n / kPi);
     double rt2rl = sqrt(2 * rl);
     double hla = 0.5 * ool::log_(al), hra = 0.5 * ool::log_(ar), lmd = ool::log_(md);
-    double wl = ool::exp_(hla - n * rt2rl + n * il + 0.5 * n * 1. / md) * p_igauss(md, 1. / rt2rl, n);
-    double wr = ool::exp_(hra + lcn - n * ool::log_(n * rr) + n * ir - n * lmd) * ool::tgamma_(n)
-              * (1.0 - p_gamma_rate(md, n, n * rr));
+    // Proposal weights (:217-226).  They only enter the decision U < pl.  Written as in the
+    // reference, wr = exp(.. - n log(n rr) - n log(md)) Gamma(n) (1 - P(n, x)) with x = md n rr.
+    // For x >= n + 1, Gamma(n) Q(n, x) = e^-x x^n CF(n, x) and the three large terms cancel
+    // exactly, leaving exp(hra + lcn + n ir - x) CF(n, x).  That form is used while Q stays above
+    // ~4e-7, i.e. while the written form's 1 - P loses less than 3e-10 of Q to rounding
+    // (Q >= exp(-n (r-1)^2 / (r+1)) / (sqrt(2 pi n) (r-1)), r = x / n).  Further out in the tail
+    // the reference's 1 - P rounds to a few ulps or to 0 and pl becomes 1: that behaviour, and
+    // shapes whose Gamma(n) overflows, keep the written form.
+    double ltb = (n * rr) * md;
+    double wl = ool::exp_(hla - n * rt2rl + n * il + 0.5 * n * 1. / md) * p_igauss_direct(md, 1. / rt2rl, n);
+    double wr;
+    double dx = ltb - n;
+    if (dx >= 1.0 && n <= 171.0 && dx * dx <= 12.0 * (ltb + n))
+        wr = ool::exp_(hra + lcn + n * ir - ltb) * upper_gamma_cf(n, ltb);
+    else
+        wr = sp_wr_ref(hra, lcn, n, rr, ir, lmd, md);
     double wt = wl + wr;
-    s.md = md;
-    s.pl = wl / wt;
-    s.rt2rl = rt2rl;
-    s.rl = rl;
-    s.il = il;
-    s.rr = rr;
-    s.ir = ir;
-    s.cl = hla + lcn;
-    s.cr = hra + lcn;
-    s.lmd = lmd;
-    s.lcz = lcz;
-    s.lcn = lcn;
+    // left-truncated gamma constants, Ch.R:96-101 with shape n, rate n rr, truncation md
+    double d1 = ltb - n;
+    double d3 = n - 1.0;
+    double c0 = 0.5 * (d1 + sqrt(d1 * d1 + 4.0 * ltb)) / ltb;
+    double l_M = d3 * ool::log_(d3 / (1.0 - c0)) - d3;
+    s.f[kSpMd] = md;
+    s.f[kSpPl] = wl / wt;
+    s.f[kSpRt2rl] = rt2rl;
+    s.f[kSpRl] = rl;
+    s.f[kSpIl] = il;
+    s.f[kSpRr] = rr;
+    s.f[kSpIr] = ir;
+    s.f[kSpCl] = hla + lcn;
+    s.f[kSpCr] = hra + lcn;
+    s.f[kSpLmd] = lmd;
+    s.f[kSpLcz] = lcz;
+    s.f[kSpLcn] = lcn;
+    s.f[kSpLtB] = ltb;
+    s.f[kSpLtC0] = c0;
+    s.f[kSpLtLM] = l_M;
 }
 
 // PolyaGammaSP.cpp:148-167 (sp_approx)
-__device__ __forceinline__ double sp_density(double x, double n, double z, const SpState &s)
+template <class St>
+__device__ __forceinline__ double sp_density(double x, double n, double z, const St &s)
 {
     double v, g;
     sp_vg(x, v, g);
     double u = 0.5 * v;
     double z2 = z * z;
     double t = u + 0.5 * z2;
-    double phi = s.lcz - g - t * x;
+    double phi = s.get(kSpLcz) - g - t * x;
     double K2;
     if (fabs(v) >= 1e-6)
         K2 = x * x + (1 - x) / v;
     else
         K2 = x * x;
-    double log_spa = s.lcn - 0.5 * ool::log_(K2) + n * phi;
+    double log_spa = s.get(kSpLcn) - 0.5 * ool::log_(K2) + n * phi;
     return ool::exp_(log_spa);
 }
 
-// The rejection loop, PolyaGammaSP.cpp:228-264: returns the number of proposals, d = n X / 4.
-template <class Src>
-__device__ __forceinline__ int sp_loop(Src &src, double &d, double n, double zraw, const SpState &s)
+// One lane's position inside the rejection loop PolyaGammaSP.cpp:228-264.  A trip makes ONE
+// attempt at a proposal (one inverse-Gaussian draw, or one pass of the truncated-gamma
+// rejection) and, once a proposal exists, the accept test; the persistent-lane kernel runs
+// trips of many draws side by side, the per-lane kernels just loop over trips.  Variates are
+// consumed in the reference's order.
+struct SpLane {
+    double X;
+    int iter;
+    int phase;   // 0 pick a piece, 1 left piece, 2 right piece, 3 / 4 proposal ready (left / right)
+    __device__ __forceinline__ void start() { X = 2.0; iter = 0; phase = 0; }
+};
+
+// returns true when the draw is complete: L.X holds X (omega = n X / 4), L.iter the proposals made.
+// z is |z|/2.
+template <class Src, class St>
+__device__ __forceinline__ bool sp_trip(Src &src, SpLane &L, double n, double z, const St &s)
 {
     const int maxiter = 200;
-    double z = 0.5 * fabs(zraw);
-    const double md = s.md;
-    bool go = true;
-    int iter = 0;
-    double X = 2.0, F = 0.0;
-    while (go && iter < maxiter) {
-        iter++;
-        double phi_ev;
-        if (src.unif() < s.pl) {
-            double mu = 1. / s.rt2rl;
-            X = md + 1.0;
-            if (md < mu) {
-                double alpha = 0.0;
-                while (src.unif() > alpha) {
-                    X = rtinvchi2(src, n, md);
-                    alpha = ool::exp_(-0.5 * n / (mu * mu) * X);
-                }
-            } else {
-                while (X > md) X = igauss(src, mu, n);
+    const double md = s.get(kSpMd);
+    if (L.phase == 0) {
+        if (L.iter >= maxiter) return true;   // only when maxiter proposals were all rejected
+        L.iter++;
+        L.phase = src.unif() < s.get(kSpPl) ? 1 : 2;
+    }
+    if (L.phase == 1) {
+        double mu = 1. / s.get(kSpRt2rl);
+        if (md < mu) {
+            double X = md + 1.0, alpha = 0.0;
+            while (src.unif() > alpha) {
+                X = rtinvchi2(src, n, md);
+                alpha = ool::exp_(-0.5 * n / (mu * mu) * X);
             }
-            phi_ev = n * (s.il - s.rl * X) + 0.5 * n * ((1. - 1. / X) - (1. - 1. / md));
-            F = ool::exp_(s.cl - 1.5 * ool::log_(X) + phi_ev);
+            L.X = X;
+            L.phase = 3;
         } else {
-            X = ltgamma(src, n, n * s.rr, md);
-            phi_ev = n * (s.ir - s.rr * X) + n * (ool::log_(X) - s.lmd);
-            F = ool::exp_(s.cr + phi_ev) / X;
+            double X = igauss(src, mu, n);
+            if (!(X > md)) {
+                L.X = X;
+                L.phase = 3;
+            }
+        }
+    } else if (L.phase == 2) {
+        if (n > 1.0 && md > 0.0) {
+            // one pass of ltgamma's rejection loop (Ch.R:102-111)
+            double b = s.get(kSpLtB), c0 = s.get(kSpLtC0);
+            double x = b + src.expon() / c0;
+            double u = src.unif();
+            double l_rho = (n - 1.0) * ool::log_(x) - x * (1.0 - c0);
+            if (ool::log_(u) <= l_rho - s.get(kSpLtLM)) {
+                L.X = md * (x / b);
+                L.phase = 4;
+            }
+        } else {
+            L.X = ltgamma(src, n, n * s.get(kSpRr), md);
+            L.phase = 4;
+        }
+    }
+    if (L.phase >= 3) {
+        double X = L.X, F;
+        if (L.phase == 3) {
+            double phi_ev = n * (s.get(kSpIl) - s.get(kSpRl) * X) + 0.5 * n * ((1. - 1. / X) - (1. - 1. / md));
+            F = ool::exp_(s.get(kSpCl) - 1.5 * ool::log_(X) + phi_ev);
+        } else {
+            double phi_ev = n * (s.get(kSpIr) - s.get(kSpRr) * X) + n * (ool::log_(X) - s.get(kSpLmd));
+            F = ool::exp_(s.get(kSpCr) + phi_ev) / X;
         }
         double spa = sp_density(X, n, z, s);
-        if (F * src.unif() < spa) go = false;
+        if (F * src.unif() < spa) return true;
+        L.phase = 0;
+        if (L.iter >= maxiter) return true;
     }
-    d = n * 0.25 * X;
-    return iter;
+    return false;
 }
 
 template <class Src>
@@ -274,7 +356,12 @@ __device__ int sp_draw(Src &src, double &d, double n, double z)
 {
     SpState s;
     sp_setup(n, z, s);
-    return sp_loop(src, d, n, z, s);
+    SpLane L;
+    L.start();
+    double zh = 0.5 * fabs(z);
+    while (!sp_trip(src, L, n, zh, s)) {}
+    d = n * 0.25 * L.X;
+    return L.iter;
 }
 
 }  // namespace bl

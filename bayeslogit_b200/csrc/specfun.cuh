@@ -78,6 +78,46 @@ static __device__ __noinline__ double p_gamma_lower(double a, double x)
     return 1.0 - exp(lpre) * h;
 }
 
+// Gamma(a, x) e^x x^-a = 1 / (x+1-a - 1(1-a)/(x+3-a - 2(2-a)/(x+5-a - ...))), x >= a + 1: the same
+// Legendre continued fraction as above, evaluated by the forward (Wallis) recurrence
+// A_k = b_k A_{k-1} + a_k A_{k-2} (B alike), so a term costs a dozen FMAs and no division.
+// Convergence is read off the determinant A_k B_{k-1} - A_{k-1} B_k = prod(-a_j), which is
+// carried as a product (no cancellation): |f_k - f_{k-1}| <= 1e-16 |f_k|.
+__device__ __forceinline__ double upper_gamma_cf(double a, double x)
+{
+    double b = x + 1.0 - a;
+    double A0 = 0.0, B0 = 1.0;      // k - 1
+    double A1 = 1.0, B1 = b;        // k
+    double det = 1.0, di = 0.0;
+    for (int i = 1; i < 2000; ++i) {
+        di += 1.0;
+        double an = -di * (di - a);
+        b += 2.0;
+        double A2 = fma(b, A1, an * A0);
+        double B2 = fma(b, B1, an * B0);
+        det *= -an;
+        A0 = A1; B0 = B1; A1 = A2; B1 = B2;
+        if (fabs(det) <= 1e-16 * fabs(A1 * B0)) break;
+        if (fabs(B1) > 0x1p200) {
+            A0 *= 0x1p-200; B0 *= 0x1p-200; A1 *= 0x1p-200; B1 *= 0x1p-200;
+            det *= 0x1p-400;
+        }
+    }
+    return A1 / B1;
+}
+
+// Inverse-Gaussian CDF with the two normal tails taken directly from erfc / erfcx instead of
+// through log Phi: Phi(b) + exp(2 lambda / mu) Phi(a), a < 0 (same quantity as p_igauss below;
+// used where only a proposal weight depends on it).
+__device__ __forceinline__ double p_igauss_direct(double x, double mu, double lambda)
+{
+    double Z = 1.0 / mu;
+    double s = sqrt(lambda / x);
+    double b = s * (x * Z - 1.0);
+    double t = s * (x * Z + 1.0) * kSqrt1_2;
+    return 0.5 * erfc(-b * kSqrt1_2) + 0.5 * erfcx(t) * exp(2.0 * lambda * Z - t * t);
+}
+
 // RNG::p_gamma_rate(x, shape, rate) = P(shape, x * rate)
 __device__ __forceinline__ double p_gamma_rate(double x, double shape, double rate)
 {
