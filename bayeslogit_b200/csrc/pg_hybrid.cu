@@ -16,6 +16,8 @@
 //
 // Results are unchanged by the re-ordering: each observation draws from the Philox
 // stream keyed by its own global index (philox.cuh).
+#include <algorithm>
+
 #include "engine.h"
 #include "pg_devroye_fast.cuh"
 
@@ -141,71 +143,164 @@ k_sp_setup(const double *__restrict__ h, const double *__restrict__ z, const int
     }
 }
 
-// Rejection loop on persistent lanes: a lane makes one trip (sp_trip) per pass and, when its draw
-// is complete, takes the next list position of its warp's chunk through a ballot-compacted
-// refill, so rejected proposals and slow inner loops of one draw do not idle the other 31 lanes.
-constexpr int kSpLoopThreads = 128;
-constexpr int kSpLaneChunk = 128;   // consecutive list positions a warp works through
+// Rejection loops on persistent lanes: a lane makes one trip (sp_trip / alt_trip) per pass and,
+// when its draw is complete, takes the next list position of its warp's chunk through a
+// ballot-compacted refill, so rejected proposals and slow inner loops of one draw do not idle the
+// other 31 lanes.  Task: begin(pos) loads list position pos, trip() advances it and returns true
+// when the draw is complete (and stored).
+constexpr int kLoopThreads = 128;
+constexpr int kLaneChunk = 128;   // consecutive list positions a warp works through
 
-__global__ void __launch_bounds__(kSpLoopThreads)
-k_sp_loop(double *__restrict__ x, const double *__restrict__ h, const double *__restrict__ z,
-          const int *__restrict__ idx, const int *__restrict__ meta, const double *__restrict__ state,
-          int c0, int cap, StreamId id)
+template <class Task>
+__device__ __forceinline__ void run_persistent_lanes(int count, Task &task)
 {
     const unsigned full = 0xffffffffu;
-    const int count = min(meta[kMetaCounts + kRegSP] - c0, cap);
-    if (count <= 0) return;
-    const int *list = idx + meta[kMetaOffsets + kRegSP] + c0;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int warp = blockIdx.x * (kSpLoopThreads / 32) + (threadIdx.x >> 5);
-    const int stride = gridDim.x * (kSpLoopThreads / 32) * kSpLaneChunk;
-
-    int cur = warp * kSpLaneChunk;     // next unassigned list position of this warp (uniform)
-    int cend = cur + kSpLaneChunk;     // end of the current chunk (uniform)
-
+    const int warp = blockIdx.x * (kLoopThreads / 32) + (threadIdx.x >> 5);
+    const int stride = gridDim.x * (kLoopThreads / 32) * kLaneChunk;
+    int cur = warp * kLaneChunk;     // next unassigned list position of this warp (uniform)
+    int cend = cur + kLaneChunk;     // end of the current chunk (uniform)
     bool active = false;
-    int obs = 0;
-    double n = 0.0, zh = 0.0;
-    SpStateRef st{state, (size_t)cap};
-    SpLane L;
-    L.start();
-    PhiloxSource src;
-
     for (;;) {
         unsigned want = __ballot_sync(full, !active);
         if (want && cur < count) {
             int rank = __popc(want & lt_mask);
             int cand = cur + rank;
-            if (cand >= cend) cand += stride - kSpLaneChunk;
+            if (cand >= cend) cand += stride - kLaneChunk;
             if (!active && cand < count) {
-                obs = list[cand];
-                n = h[obs];
-                zh = 0.5 * fabs(z[obs]);
-                st.o = state + cand;
-                L.start();
-                src.open(id.seed, id.obs0 + (uint64_t)obs, id.call_id);
+                task.begin(cand);
                 active = true;
             }
             cur += __popc(want);
             if (cur >= cend) {
                 int over = cur - cend;
                 cend += stride;
-                cur = cend - kSpLaneChunk + over;
+                cur = cend - kLaneChunk + over;
             }
         }
         if (!__any_sync(full, active)) {
             if (cur >= count) break;
             continue;
         }
-        if (active && sp_trip(src, L, n, zh, st)) {
-            x[obs] = n * 0.25 * L.X;
-            active = false;
+        if (active && task.trip()) active = false;
+    }
+}
+
+struct SpTask {
+    double *x;
+    const double *h, *z, *state;
+    const int *list;
+    size_t cap;
+    StreamId id;
+    int obs;
+    double n, zh;
+    SpStateRef st;
+    SpLane L;
+    PhiloxSource src;
+    __device__ __forceinline__ void begin(int pos)
+    {
+        obs = list[pos];
+        n = h[obs];
+        zh = 0.5 * fabs(z[obs]);
+        st.o = state + pos;
+        st.cap = cap;
+        L.start();
+        src.open(id.seed, id.obs0 + (uint64_t)obs, id.call_id);
+    }
+    __device__ __forceinline__ bool trip()
+    {
+        if (!sp_trip(src, L, n, zh, st)) return false;
+        x[obs] = n * 0.25 * L.X;
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(kLoopThreads)
+k_sp_loop(double *__restrict__ x, const double *__restrict__ h, const double *__restrict__ z,
+          const int *__restrict__ idx, const int *__restrict__ meta, const double *__restrict__ state,
+          int c0, int cap, StreamId id)
+{
+    const int count = min(meta[kMetaCounts + kRegSP] - c0, cap);
+    if (count <= 0) return;
+    SpTask t;
+    t.x = x; t.h = h; t.z = z; t.state = state; t.cap = (size_t)cap; t.id = id;
+    t.list = idx + meta[kMetaOffsets + kRegSP] + c0;
+    run_persistent_lanes(count, t);
+}
+
+// Alternate regime, same two-kernel shape: the constants of the (at most) two chunk shapes of a
+// draw -> 20 doubles per draw in HBM -> persistent-lane loop over chunks and proposals.
+__global__ void __launch_bounds__(128)
+k_alt_setup(const double *__restrict__ h, const double *__restrict__ z, const int *__restrict__ idx,
+            const int *__restrict__ meta, double *__restrict__ state, int c0, int cap)
+{
+    const int count = min(meta[kMetaCounts + kRegAlt] - c0, cap);
+    const int *list = idx + meta[kMetaOffsets + kRegAlt] + c0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
+        int i = list[j];
+        int nfull, nrem;
+        double hrem, zh = 0.5 * fabs(z[i]);
+        alt_plan(h[i], nfull, nrem, hrem);
+        double f[kAltSetupDoubles];
+        // remainder shape first: every draw has one; the shape-4 constants only if it has a full chunk
+        alt_setup(hrem, zh, f);
+#pragma unroll
+        for (int k = 0; k < kAltSetupDoubles; ++k) state[(size_t)(kAltSetupDoubles + k) * cap + j] = f[k];
+        if (nfull > 0) {
+            alt_setup(4.0, zh, f);
+#pragma unroll
+            for (int k = 0; k < kAltSetupDoubles; ++k) state[(size_t)k * cap + j] = f[k];
         }
     }
 }
 
-constexpr int kSpChunk = 1 << 24;   // draws per set-up/loop kernel pair (1.6 GB of state)
+struct AltTask {
+    double *x;
+    const double *h, *z, *state;
+    const int *list;
+    size_t cap;
+    StreamId id;
+    int obs;
+    double zh;
+    AltStateRef st;
+    AltLane L;
+    PhiloxSource src;
+    __device__ __forceinline__ void begin(int pos)
+    {
+        obs = list[pos];
+        zh = 0.5 * fabs(z[obs]);
+        int nfull, nrem;
+        double hrem;
+        alt_plan(h[obs], nfull, nrem, hrem);
+        st.o = state + pos;
+        st.cap = cap;
+        L.start(nfull, nrem);
+        src.open(id.seed, id.obs0 + (uint64_t)obs, id.call_id);
+    }
+    __device__ __forceinline__ bool trip()
+    {
+        if (!alt_trip(src, L, zh, st)) return false;
+        x[obs] = L.sum;
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(kLoopThreads)
+k_alt_loop(double *__restrict__ x, const double *__restrict__ h, const double *__restrict__ z,
+           const int *__restrict__ idx, const int *__restrict__ meta, const double *__restrict__ state,
+           int c0, int cap, StreamId id)
+{
+    const int count = min(meta[kMetaCounts + kRegAlt] - c0, cap);
+    if (count <= 0) return;
+    AltTask t;
+    t.x = x; t.h = h; t.z = z; t.state = state; t.cap = (size_t)cap; t.id = id;
+    t.list = idx + meta[kMetaOffsets + kRegAlt] + c0;
+    run_persistent_lanes(count, t);
+}
+
+constexpr int kStateChunk = 1 << 23;   // draws per set-up/loop kernel pair (1.3 GB of state)
+constexpr int kStateDoubles = kSpStateDoubles > kAltStateDoubles ? kSpStateDoubles : kAltStateDoubles;
 
 template <int R>
 void launch_regime(double *x, const double *h, const double *z, const int *idx, const int *meta,
@@ -246,13 +341,13 @@ int hybrid_timing_last(double *out6)
     return 0;
 }
 
-// [meta: 32 ints][index list: num ints, padded to 16 B][saddle-point state: 12 x min(num, chunk) doubles]
+// [meta: 32 ints][index list: num ints, padded to 16 B][sampler state: 20 x min(num, chunk) doubles]
 static size_t hybrid_state_offset(int64_t num) { return ((32 + (size_t)num) * sizeof(int) + 15) / 16 * 16; }
 
 size_t hybrid_workspace_bytes(int64_t num)
 {
-    size_t cap = (size_t)(num < kSpChunk ? num : kSpChunk);
-    return hybrid_state_offset(num) + cap * kSpStateDoubles * sizeof(double);
+    size_t cap = (size_t)(num < kStateChunk ? num : kStateChunk);
+    return hybrid_state_offset(num) + cap * kStateDoubles * sizeof(double);
 }
 
 // One rpg_hybrid batch of at most 2^31-1 observations.  `work` holds
@@ -275,19 +370,23 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
     count_launch(3);
     // heavy regimes first so the light ones fill the tail
     if (tm) cudaEventRecord(g_hyb_ev[1], st);
-    {
-        double *state = (double *)((char *)work + hybrid_state_offset(num));
-        int cap = num < kSpChunk ? num : kSpChunk;
-        int need = (cap + 127) / 128;
-        int grid = need < 148 * 8 ? need : 148 * 8;
-        for (int c0 = 0; c0 < num; c0 += cap) {   // pairs past the regime's count return at once
-            k_sp_setup<<<grid, 128, 0, st>>>(h, z, idx, meta, state, c0, cap);
-            k_sp_loop<<<grid, 128, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
-            count_launch(2);
-        }
+    double *state = (double *)((char *)work + hybrid_state_offset(num));
+    const int cap = num < kStateChunk ? num : kStateChunk;
+    const int sgrid = std::min((cap + 127) / 128, 148 * 8);
+    const int lgrid = std::min((cap + kLaneChunk * (kLoopThreads / 32) - 1) / (kLaneChunk * (kLoopThreads / 32)), 148 * 8);
+    // One set-up/loop pair per state chunk.  The regime counts live on the device, so pairs are
+    // issued for the largest possible count; those past the regime's count return at once.
+    for (int c0 = 0; c0 < num; c0 += cap) {
+        k_sp_setup<<<sgrid, 128, 0, st>>>(h, z, idx, meta, state, c0, cap);
+        k_sp_loop<<<lgrid, kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
+        count_launch(2);
     }
     if (tm) cudaEventRecord(g_hyb_ev[2], st);
-    launch_regime<kRegAlt>(x, h, z, idx, meta, id, num, 4, st);
+    for (int c0 = 0; c0 < num; c0 += cap) {
+        k_alt_setup<<<sgrid, 128, 0, st>>>(h, z, idx, meta, state, c0, cap);
+        k_alt_loop<<<lgrid, kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
+        count_launch(2);
+    }
     if (tm) cudaEventRecord(g_hyb_ev[3], st);
     launch_regime<kRegGamma>(x, h, z, idx, meta, id, num, 8, st);
     if (tm) cudaEventRecord(g_hyb_ev[4], st);
