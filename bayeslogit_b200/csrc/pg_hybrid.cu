@@ -124,9 +124,9 @@ k_hyb_regime(double *__restrict__ x, const double *__restrict__ h, const double 
     }
 }
 
-// Saddle-point regime as two kernels (pg_sp.cuh): set-up -> 15-double state per draw in HBM
+// Saddle-point regime as two kernels (pg_sp.cuh): set-up -> 16-double state per draw in HBM
 // (struct of arrays over the chunk, coalesced) -> rejection loop.  Each kernel's working set of
-// code stays near the 32 KB instruction cache; the state costs 240 B of HBM traffic per draw,
+// code stays near the 32 KB instruction cache; the state costs 256 B of HBM traffic per draw,
 // ~2 % of HBM bandwidth at the rates these kernels reach.
 __global__ void __launch_bounds__(128)
 k_sp_setup(const double *__restrict__ h, const double *__restrict__ z, const int *__restrict__ idx,
@@ -210,7 +210,7 @@ struct SpTask {
     }
     __device__ __forceinline__ bool trip()
     {
-        if (!sp_trip(src, L, n, zh, st)) return false;
+        if (!sp_trip_staged(src, L, n, zh, st)) return false;
         x[obs] = n * 0.25 * L.X;
         return true;
     }

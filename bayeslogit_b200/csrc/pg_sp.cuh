@@ -145,6 +145,9 @@ enum SpField {
     kSpLcz,      // log cosh(|z|/2)
     kSpLcn,      // 0.5 log(n / 2 pi), :215
     kSpLtB, kSpLtC0, kSpLtLM,   // ltgamma(n, n rr, md): b = rate * trunc, c0, log M
+    kSpLLtB,     // log b
+    kSpMu,       // 1 / sqrt(2 rl), mean of the left piece's inverse Gaussian, :232
+    kSpC1md,     // 1 - 1/md
     kSpStateDoubles
 };
 
@@ -162,9 +165,12 @@ struct SpStateRef {
     __device__ __forceinline__ double get(int k) const { return __ldg(o + (size_t)k * cap); }
 };
 
-// PolyaGammaSP.cpp:128-146 (tangent_to_eta) with phi_func :115-126 and delta_func :103-113
-__device__ __forceinline__ void sp_tangent(double x, double z, double mid, double lcz, double &slope,
-                                           double &icept)
+// PolyaGammaSP.cpp:128-146 (tangent_to_eta) with phi_func :115-126 and delta_func :103-113.
+// The tangent lines only shape the envelope's masses and the accept test.  Right of the mid
+// point the reference takes log(x) - log(mid) at x = 1.2 xl, mid = 1.1 xl: the constant
+// log(12/11) to within 3e-16.
+__device__ __forceinline__ void sp_tangent(double x, double z, double mid, double lcz, bool right,
+                                           double &slope, double &icept)
 {
     double v, g;
     sp_vg(x, v, g);
@@ -173,8 +179,8 @@ __device__ __forceinline__ void sp_tangent(double x, double z, double mid, doubl
     double phi_val = lcz - g - t * x;
     double phi_der = -1.0 * t;
     double delta_val, delta_der;
-    if (x >= mid) {
-        delta_val = ool::log_(x) - ool::log_(mid);
+    if (right) {
+        delta_val = 0.087011376989629699;   // log(1.2 / 1.1)
         delta_der = 1.0 / x;
     } else {
         delta_val = 0.5 * (1 - 1.0 / x) - 0.5 * (1 - 1.0 / mid);
@@ -212,13 +218,16 @@ __device__ __forceinline__ void sp_setup(double n, double zraw, SpState &s)
     double ar = m2 / K2md;
     double lcz = ool::log_(ool::cosh_(z));
     double sl, il, sr, ir;
-    sp_tangent(xl, z, md, lcz, sl, il);
-    sp_tangent(xr, z, md, lcz, sr, ir);
+    sp_tangent(xl, z, md, lcz, false, sl, il);
+    sp_tangent(xr, z, md, lcz, true, sr, ir);
     double rl = -1. * sl;
     double rr = -1. * sr;
     double lcn = 0.5 * ool::log_(0.5 * n / kPi);
     double rt2rl = sqrt(2 * rl);
-    double hla = 0.5 * ool::log_(al), hra = 0.5 * ool::log_(ar), lmd = ool::log_(md);
+    // ar = al / md: 0.5 log(ar) is taken as 0.5 log(al) - 0.5 log(md) (weights and accept test only)
+    double lmd = ool::log_(md);
+    double hla = 0.5 * ool::log_(al), hra = hla - 0.5 * lmd;
+    (void)ar;
     // Proposal weights (:217-226).  They only enter the decision U < pl.  Written as in the
     // reference, wr = exp(.. - n log(n rr) - n log(md)) Gamma(n) (1 - P(n, x)) with x = md n rr.
     // For x >= n + 1, Gamma(n) Q(n, x) = e^-x x^n CF(n, x) and the three large terms cancel
@@ -256,6 +265,9 @@ __device__ __forceinline__ void sp_setup(double n, double zraw, SpState &s)
     s.f[kSpLtB] = ltb;
     s.f[kSpLtC0] = c0;
     s.f[kSpLtLM] = l_M;
+    s.f[kSpLLtB] = ool::log_(ltb);
+    s.f[kSpMu] = 1. / rt2rl;
+    s.f[kSpC1md] = 1. - 1. / md;
 }
 
 // PolyaGammaSP.cpp:148-167 (sp_approx)
@@ -349,6 +361,133 @@ __device__ __forceinline__ bool sp_trip(Src &src, SpLane &L, double n, double z,
         if (L.iter >= maxiter) return true;
     }
     return false;
+}
+
+// Exact forms of the two decisions the staged trip pre-filters in fp32 (cold code).
+static __device__ __noinline__ bool sp_ltgamma_accept_exact(double u, double x, double n, double c0, double l_M)
+{
+    return ool::log_(u) <= (n - 1.0) * ool::log_(x) - x * (1.0 - c0) - l_M;     // Ch.R:108-110
+}
+
+template <class St>
+static __device__ __noinline__ bool sp_accept_exact(double X, bool left, double n, double z, double u,
+                                                    const St &s)
+{
+    double F;                                                                     // PolyaGammaSP.cpp:243-258
+    if (left) {
+        double phi_ev = n * (s.get(kSpIl) - s.get(kSpRl) * X) + 0.5 * n * ((1. - 1. / X) - (1. - 1. / s.get(kSpMd)));
+        F = ool::exp_(s.get(kSpCl) - 1.5 * ool::log_(X) + phi_ev);
+    } else {
+        double phi_ev = n * (s.get(kSpIr) - s.get(kSpRr) * X) + n * (ool::log_(X) - s.get(kSpLmd));
+        F = ool::exp_(s.get(kSpCr) + phi_ev) / X;
+    }
+    return F * u < sp_density(X, n, z, s);
+}
+
+// The same trip for Philox streams, laid out so that the lanes of a warp share their expensive
+// calls and so that fp64 transcendentals are spent only where a VALUE is produced:
+//   * whichever piece a lane proposes from, its first variate needs one fp64 logarithm
+//     (Box-Muller radius on the left, exponential on the right): one shared call;
+//   * X is computed in fp64 by the formulas of igauss() / ltgamma() from the same words;
+//   * the two DECISIONS -- the truncated-gamma accept test (Ch.R:108-110) and F U < spa
+//     (PolyaGammaSP.cpp:259) -- are compared in the log domain, linear terms in fp64, the
+//     logarithms of X, K2, U and the final exponential in fp32 (MUFU).  Each comparison carries
+//     a band >= 2.4x its error bound (__logf: 2^-21.4 abs on [0.5,2], 3 ulp elsewhere; __expf:
+//     2 + 1.17|x| ulp; float conversion 2^-24); inside the band, or when an exponent leaves
+//     (-700, 700), the reference's fp64 expression decides.  The decision taken is therefore the
+//     fp64 decision (up to the reference's own rounding, ~1e-13, far inside the band).
+template <class St>
+__device__ __forceinline__ bool sp_trip_staged(PhiloxSource &src, SpLane &L, double n, double z, const St &s)
+{
+    const int maxiter = 200;
+    const double md = s.get(kSpMd);
+    const double mu = s.get(kSpMu);
+    if (!(n > 1.0 && md > 0.0 && md >= mu)) return sp_trip(src, L, n, z, s);   // rare shapes
+    if (L.phase == 0) {
+        if (L.iter >= maxiter) return true;
+        L.iter++;
+        L.phase = src.unif() < s.get(kSpPl) ? 1 : 2;
+    }
+    const bool left = L.phase == 1;
+    PhiloxSource::LazyN ln = {0u, 0u, 0u};
+    PhiloxSource::LazyE le = {0u, 0};
+    double a1;
+    if (left) {
+        ln = src.norm_lazy();
+        uint64_t m = ((uint64_t)ln.w0 << 21) | (uint64_t)(ln.w1 >> 11);
+        a1 = ((double)m + 0.5) * 0x1p-53;
+    } else {
+        le = src.expon_lazy();
+        a1 = word_to_unif(le.w);
+    }
+    const double L1 = ool::log_(a1);
+    const double u = src.unif();
+    double X;
+    bool ok;
+    float lx;
+    if (left) {
+        double nu = sqrt(-2.0 * L1) * cospi(2.0 * word_to_unif(ln.w2));
+        double y = nu * nu;
+        double x = mu + 0.5 * mu * mu * y / n - 0.5 * mu / n * sqrt(4.0 * mu * n * y + (mu * y) * (mu * y));
+        if (u > mu / (mu + x)) x = mu * mu / x;
+        X = x;
+        ok = !(X > md);
+        lx = __logf((float)X);
+    } else {
+        double E = (double)le.k * (32.0 * 0.693147180559945309417232) - L1;
+        double c0 = s.get(kSpLtC0), b = s.get(kSpLtB);
+        double xg = b + E / c0;
+        lx = __logf((float)xg);
+        float lu = __logf((float)u);
+        double d = (n - 1.0) * (double)lx - xg * (1.0 - c0) - s.get(kSpLtLM) - (double)lu;
+        double band = 1e-6 * ((n - 1.0) * (1.0 + fabs((double)lx)) + 2.0 + fabs((double)lu));
+        if (d > band) ok = true;
+        else if (d < -band) ok = false;
+        else ok = sp_ltgamma_accept_exact(u, xg, n, c0, s.get(kSpLtLM));
+        X = md * (xg / b);
+    }
+    if (!ok) return false;
+    L.X = X;
+    // accept test F U < spa, as log(spa) - log(F) against log U
+    const double u2 = src.unif();
+    double logX, logF, kx;
+    if (left) {
+        logX = (double)lx;
+        logF = s.get(kSpCl) - 1.5 * logX + n * (s.get(kSpIl) - s.get(kSpRl) * X)
+             + 0.5 * n * ((1. - 1. / X) - s.get(kSpC1md));
+        kx = 1.5;
+    } else {
+        double dl = (double)lx - s.get(kSpLLtB);                 // log(x / b) = log(X / md)
+        logX = s.get(kSpLmd) + dl;
+        logF = s.get(kSpCr) + n * (s.get(kSpIr) - s.get(kSpRr) * X) + n * dl - logX;
+        kx = n + 1.0;
+    }
+    double v, g;
+    sp_vg(X, v, g);
+    double t = 0.5 * v + 0.5 * (z * z);
+    double phi = s.get(kSpLcz) - g - t * X;
+    double K2 = fabs(v) >= 1e-6 ? X * X + (1 - X) / v : X * X;
+    float lK2 = __logf((float)K2);
+    double log_spa = s.get(kSpLcn) - 0.5 * (double)lK2 + n * phi;
+    double a = log_spa - logF;
+    bool accept;
+    if (fabs(logF) < 700.0 && fabs(log_spa) < 700.0) {
+        double band = 1e-6 * (kx * (1.0 + fabs((double)lx)) + 0.5 * (1.0 + fabs((double)lK2)));
+        if (a >= band) {
+            accept = true;                                       // exp(a - band) >= 1 > U
+        } else {
+            double thr = (double)__expf((float)a);
+            double rb = band + 5e-7 * (1.0 + fabs(a));
+            if (u2 < thr * (1.0 - rb)) accept = true;
+            else if (u2 > thr * (1.0 + rb)) accept = false;
+            else accept = sp_accept_exact(X, left, n, z, u2, s);
+        }
+    } else {
+        accept = sp_accept_exact(X, left, n, z, u2, s);
+    }
+    if (accept) return true;
+    L.phase = 0;
+    return L.iter >= maxiter;
 }
 
 template <class Src>

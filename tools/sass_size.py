@@ -40,6 +40,6 @@ with tempfile.TemporaryDirectory() as tmp:
             tot = sum(d.values())
             print("%6d instr %6.1f KB  %s" % (tot, tot * 16 / 1024, name[:110]))
             if flt:
-                for f, n in sorted(d.items(), key=lambda kv: -kv[1]):
+                for f, n in d.items():   # layout order
                     fname = subprocess.run(["c++filt", f], capture_output=True, text=True).stdout.strip()
                     print("        %6d  %s" % (n, fname[:100]))
