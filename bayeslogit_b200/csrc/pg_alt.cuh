@@ -63,10 +63,11 @@ struct AltState {
     __device__ __forceinline__ double get(int k) const { return f[k]; }
 };
 
+// strided view: field k at o[k * stride] (shared-memory copy of the lane's draw, see SpStateRef)
 struct AltStateRef {
     const double *o;
-    size_t cap;
-    __device__ __forceinline__ double get(int k) const { return __ldg(o + (size_t)k * cap); }
+    size_t stride;
+    __device__ __forceinline__ double get(int k) const { return o[(size_t)k * stride]; }
 };
 
 // PolyaGammaAlt.cpp:205-225: nfull chunks of shape 4, then nrem (1 or 2) chunks of shape hrem

@@ -193,6 +193,7 @@ struct SpTask {
     const int *list;
     size_t cap;
     StreamId id;
+    double *smem;      // this lane's column of the CTA's [field][lane] state copy
     int obs;
     double n, zh;
     SpStateRef st;
@@ -203,8 +204,8 @@ struct SpTask {
         obs = list[pos];
         n = h[obs];
         zh = 0.5 * fabs(z[obs]);
-        st.o = state + pos;
-        st.cap = cap;
+#pragma unroll
+        for (int k = 0; k < kSpStateDoubles; ++k) smem[k * kLoopThreads] = __ldg(state + (size_t)k * cap + pos);
         L.start();
         src.open(id.seed, id.obs0 + (uint64_t)obs, id.call_id);
     }
@@ -223,8 +224,12 @@ k_sp_loop(double *__restrict__ x, const double *__restrict__ h, const double *__
 {
     const int count = min(meta[kMetaCounts + kRegSP] - c0, cap);
     if (count <= 0) return;
+    __shared__ double sh[kSpStateDoubles * kLoopThreads];
     SpTask t;
     t.x = x; t.h = h; t.z = z; t.state = state; t.cap = (size_t)cap; t.id = id;
+    t.smem = sh + threadIdx.x;
+    t.st.o = t.smem;
+    t.st.stride = kLoopThreads;
     t.list = idx + meta[kMetaOffsets + kRegSP] + c0;
     run_persistent_lanes(count, t);
 }
@@ -261,6 +266,7 @@ struct AltTask {
     const int *list;
     size_t cap;
     StreamId id;
+    double *smem;
     int obs;
     double zh;
     AltStateRef st;
@@ -273,8 +279,8 @@ struct AltTask {
         int nfull, nrem;
         double hrem;
         alt_plan(h[obs], nfull, nrem, hrem);
-        st.o = state + pos;
-        st.cap = cap;
+#pragma unroll
+        for (int k = 0; k < kAltStateDoubles; ++k) smem[k * kLoopThreads] = __ldg(state + (size_t)k * cap + pos);
         L.start(nfull, nrem);
         src.open(id.seed, id.obs0 + (uint64_t)obs, id.call_id);
     }
@@ -293,8 +299,12 @@ k_alt_loop(double *__restrict__ x, const double *__restrict__ h, const double *_
 {
     const int count = min(meta[kMetaCounts + kRegAlt] - c0, cap);
     if (count <= 0) return;
+    __shared__ double sh[kAltStateDoubles * kLoopThreads];
     AltTask t;
     t.x = x; t.h = h; t.z = z; t.state = state; t.cap = (size_t)cap; t.id = id;
+    t.smem = sh + threadIdx.x;
+    t.st.o = t.smem;
+    t.st.stride = kLoopThreads;
     t.list = idx + meta[kMetaOffsets + kRegAlt] + c0;
     run_persistent_lanes(count, t);
 }
@@ -302,12 +312,27 @@ k_alt_loop(double *__restrict__ x, const double *__restrict__ h, const double *_
 constexpr int kStateChunk = 1 << 23;   // draws per set-up/loop kernel pair (1.3 GB of state)
 constexpr int kStateDoubles = kSpStateDoubles > kAltStateDoubles ? kSpStateDoubles : kAltStateDoubles;
 
+// Persistent grids are sized to exactly the CTAs that are resident at once (148 SMs x occupancy):
+// one CTA more per SM would run alone in a second wave at a fraction of the occupancy.
+template <class K>
+int resident_grid(K kernel, int threads, int need)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int cap = sms * per_sm;
+    return need < cap ? (need > 0 ? need : 1) : cap;
+}
+
 template <int R>
 void launch_regime(double *x, const double *h, const double *z, const int *idx, const int *meta,
-                   StreamId id, int n, int ctas_per_sm, cudaStream_t st)
+                   StreamId id, int n, cudaStream_t st)
 {
+    static const int cap = resident_grid(k_hyb_regime<R>, 128, 1 << 30);
     int need = (n + 127) / 128;
-    int cap = 148 * ctas_per_sm;
     k_hyb_regime<R><<<need < cap ? need : cap, 128, 0, st>>>(x, h, z, idx, meta, id);
     count_launch();
 }
@@ -372,27 +397,31 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
     if (tm) cudaEventRecord(g_hyb_ev[1], st);
     double *state = (double *)((char *)work + hybrid_state_offset(num));
     const int cap = num < kStateChunk ? num : kStateChunk;
-    const int sgrid = std::min((cap + 127) / 128, 148 * 8);
-    const int lgrid = std::min((cap + kLaneChunk * (kLoopThreads / 32) - 1) / (kLaneChunk * (kLoopThreads / 32)), 148 * 8);
+    static const int g_sp_setup = resident_grid(k_sp_setup, 128, 1 << 30);
+    static const int g_sp_loop = resident_grid(k_sp_loop, kLoopThreads, 1 << 30);
+    static const int g_alt_setup = resident_grid(k_alt_setup, 128, 1 << 30);
+    static const int g_alt_loop = resident_grid(k_alt_loop, kLoopThreads, 1 << 30);
+    const int sneed = (cap + 127) / 128;
+    const int lneed = (cap + kLaneChunk * (kLoopThreads / 32) - 1) / (kLaneChunk * (kLoopThreads / 32));
     // One set-up/loop pair per state chunk.  The regime counts live on the device, so pairs are
     // issued for the largest possible count; those past the regime's count return at once.
     for (int c0 = 0; c0 < num; c0 += cap) {
-        k_sp_setup<<<sgrid, 128, 0, st>>>(h, z, idx, meta, state, c0, cap);
-        k_sp_loop<<<lgrid, kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
+        k_sp_setup<<<std::min(sneed, g_sp_setup), 128, 0, st>>>(h, z, idx, meta, state, c0, cap);
+        k_sp_loop<<<std::min(lneed, g_sp_loop), kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
         count_launch(2);
     }
     if (tm) cudaEventRecord(g_hyb_ev[2], st);
     for (int c0 = 0; c0 < num; c0 += cap) {
-        k_alt_setup<<<sgrid, 128, 0, st>>>(h, z, idx, meta, state, c0, cap);
-        k_alt_loop<<<lgrid, kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
+        k_alt_setup<<<std::min(sneed, g_alt_setup), 128, 0, st>>>(h, z, idx, meta, state, c0, cap);
+        k_alt_loop<<<std::min(lneed, g_alt_loop), kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
         count_launch(2);
     }
     if (tm) cudaEventRecord(g_hyb_ev[3], st);
-    launch_regime<kRegGamma>(x, h, z, idx, meta, id, num, 8, st);
+    launch_regime<kRegGamma>(x, h, z, idx, meta, id, num, st);
     if (tm) cudaEventRecord(g_hyb_ev[4], st);
-    launch_regime<kRegNormal>(x, h, z, idx, meta, id, num, 8, st);
+    launch_regime<kRegNormal>(x, h, z, idx, meta, id, num, st);
     if (tm) cudaEventRecord(g_hyb_ev[5], st);
-    launch_regime<kRegDevroye>(x, h, z, idx, meta, id, num, 8, st);
+    launch_regime<kRegDevroye>(x, h, z, idx, meta, id, num, st);
     if (tm) cudaEventRecord(g_hyb_ev[6], st);
     return cudaGetLastError();
 }

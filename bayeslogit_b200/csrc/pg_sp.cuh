@@ -157,12 +157,14 @@ struct SpState {
     __device__ __forceinline__ double get(int k) const { return f[k]; }
 };
 
-// in HBM, struct of arrays over a chunk of `cap` draws (binned path): fields are fetched where
-// they are used instead of being held in 30 registers across the whole rejection loop
+// strided view (binned path): field k of this lane's draw at o[k * stride].  The loop kernel
+// copies a draw's fields from the HBM struct of arrays into shared memory when the lane takes the
+// draw, [field][lane] so the reads are conflict-free; they are then fetched where they are used
+// instead of being held in 36 registers across the whole rejection loop.
 struct SpStateRef {
     const double *o;
-    size_t cap;
-    __device__ __forceinline__ double get(int k) const { return __ldg(o + (size_t)k * cap); }
+    size_t stride;
+    __device__ __forceinline__ double get(int k) const { return o[(size_t)k * stride]; }
 };
 
 // PolyaGammaSP.cpp:128-146 (tangent_to_eta) with phi_func :115-126 and delta_func :103-113.
