@@ -481,7 +481,7 @@ uint64_t bl_kernel_launches(void) { return g_launches.load(); }
 
 void bl_hybrid_timing(int enable) { hybrid_timing_enable(enable != 0); }
 
-int bl_hybrid_timing_last(double *ms6) { return hybrid_timing_last(ms6); }
+int bl_hybrid_timing_last(double *ms8, int *launches8) { return hybrid_timing_last(ms8, launches8); }
 
 int bl_ensure_ready_internal(void)
 {

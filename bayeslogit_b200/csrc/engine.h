@@ -72,7 +72,7 @@ int comm_init(const void *id128, int rank, int world, std::string &err);
 void comm_destroy();
 
 void hybrid_timing_enable(bool on);
-int hybrid_timing_last(double *out6);
+int hybrid_timing_last(double *ms8, int *launches8);
 
 void count_launch(int n = 1);
 

@@ -17,6 +17,7 @@
 // Results are unchanged by the re-ordering: each observation draws from the Philox
 // stream keyed by its own global index (philox.cuh).
 #include <algorithm>
+#include <vector>
 
 #include "engine.h"
 #include "pg_devroye_fast.cuh"
@@ -128,7 +129,7 @@ k_hyb_regime(double *__restrict__ x, const double *__restrict__ h, const double 
 // (struct of arrays over the chunk, coalesced) -> rejection loop.  Each kernel's working set of
 // code stays near the 32 KB instruction cache; the state costs 256 B of HBM traffic per draw,
 // ~2 % of HBM bandwidth at the rates these kernels reach.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 k_sp_setup(const double *__restrict__ h, const double *__restrict__ z, const int *__restrict__ idx,
            const int *__restrict__ meta, double *__restrict__ state, int c0, int cap)
 {
@@ -339,29 +340,48 @@ void launch_regime(double *x, const double *h, const double *z, const int *idx, 
 
 }  // namespace
 
-// optional per-stage timing of the last binned launch (bench.py's roofline leg)
+// Optional per-kernel timing of the last binned launch (bench.py's roofline leg): CUDA events on
+// the launch stream around every kernel, summed per stage.
+enum HybStage { kStBin = 0, kStSpSetup, kStSpLoop, kStAltSetup, kStAltLoop, kStGamma, kStNormal, kStDevroye, kStCount };
 static bool g_hyb_timing = false;
-static cudaEvent_t g_hyb_ev[7];
-static bool g_hyb_ev_ready = false;
+static std::vector<cudaEvent_t> g_hyb_pool;
+struct HybSpan { int stage; int a, b; };
+static std::vector<HybSpan> g_hyb_spans;
+static int g_hyb_used = 0;
 
-void hybrid_timing_enable(bool on)
+void hybrid_timing_enable(bool on) { g_hyb_timing = on; }
+
+static int hyb_mark(cudaStream_t st)
 {
-    g_hyb_timing = on;
-    if (on && !g_hyb_ev_ready) {
-        for (auto &e : g_hyb_ev) cudaEventCreate(&e);
-        g_hyb_ev_ready = true;
+    if ((int)g_hyb_pool.size() <= g_hyb_used) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        g_hyb_pool.push_back(e);
     }
+    cudaEventRecord(g_hyb_pool[g_hyb_used], st);
+    return g_hyb_used++;
 }
 
-// ms of [binning, SP, Alt, sum-of-gammas, normal, Devroye] of the last timed launch
-int hybrid_timing_last(double *out6)
+struct HybTimer {
+    bool on;
+    cudaStream_t st;
+    int stage, a;
+    HybTimer(bool on_, cudaStream_t st_, int stage_) : on(on_), st(st_), stage(stage_), a(on_ ? hyb_mark(st_) : 0) {}
+    ~HybTimer() { if (on) g_hyb_spans.push_back(HybSpan{stage, a, hyb_mark(st)}); }
+};
+
+// ms of [binning, SP set-up, SP loop, Alt set-up, Alt loop, sum-of-gammas, normal, Devroye] and the
+// number of non-empty launches per stage of the last timed launch_hybrid_binned
+int hybrid_timing_last(double *ms8, int *launches8)
 {
-    if (!g_hyb_ev_ready) return 1;
-    if (cudaEventSynchronize(g_hyb_ev[6]) != cudaSuccess) return 1;
-    for (int k = 0; k < 6; ++k) {
+    if (g_hyb_spans.empty()) return 1;
+    for (int k = 0; k < kStCount; ++k) { ms8[k] = 0.0; if (launches8) launches8[k] = 0; }
+    if (cudaEventSynchronize(g_hyb_pool[g_hyb_used - 1]) != cudaSuccess) return 1;
+    for (const HybSpan &sp : g_hyb_spans) {
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, g_hyb_ev[k], g_hyb_ev[k + 1]);
-        out6[k] = ms;
+        cudaEventElapsedTime(&ms, g_hyb_pool[sp.a], g_hyb_pool[sp.b]);
+        ms8[sp.stage] += ms;
+        if (launches8 && ms > 0.02f) launches8[sp.stage]++;   // pairs past the regime's count return in a few us
     }
     return 0;
 }
@@ -374,6 +394,24 @@ size_t hybrid_workspace_bytes(int64_t num)
     size_t cap = (size_t)(num < kStateChunk ? num : kStateChunk);
     return hybrid_state_offset(num) + cap * kStateDoubles * sizeof(double);
 }
+
+// side stream of the light regimes, one per device context (created on first use)
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaStream_t get()
+    {
+        if (!s) {
+            int lo = 0, hi = 0;   // lowest priority: its CTAs fill SM slots the main stream leaves free
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, lo);
+            cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+        }
+        return s;
+    }
+};
+static SideStream g_side;
 
 // One rpg_hybrid batch of at most 2^31-1 observations.  `work` holds
 // hybrid_workspace_bytes(num) bytes of device scratch owned by the caller's stream.
@@ -388,13 +426,32 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
     int tiles = (num + kBinThreads - 1) / kBinThreads;
     int grid = tiles < 148 * 8 ? tiles : 148 * 8;
     const bool tm = g_hyb_timing;
-    if (tm) cudaEventRecord(g_hyb_ev[0], st);
-    k_hyb_count<<<grid, kBinThreads, 0, st>>>(h, num, meta);
-    k_hyb_offsets<<<1, 1, 0, st>>>(meta);
-    k_hyb_scatter<<<grid, kBinThreads, 0, st>>>(h, num, meta, idx, x);
-    count_launch(3);
-    // heavy regimes first so the light ones fill the tail
-    if (tm) cudaEventRecord(g_hyb_ev[1], st);
+    if (tm) { g_hyb_spans.clear(); g_hyb_used = 0; }
+    {
+        HybTimer t(tm, st, kStBin);
+        k_hyb_count<<<grid, kBinThreads, 0, st>>>(h, num, meta);
+        k_hyb_offsets<<<1, 1, 0, st>>>(meta);
+        k_hyb_scatter<<<grid, kBinThreads, 0, st>>>(h, num, meta, idx, x);
+        count_launch(3);
+    }
+    // The three light regimes (0.15 % + 15 % + 0.5 % of this workload's draws; the sum of gammas
+    // is 200 sequential gamma variates per draw at single-digit occupancy) run on a side stream
+    // forked here and joined at the end, underneath the saddle-point and alternate kernels.
+    cudaStream_t side = g_side.get();
+    cudaEventRecord(g_side.fork, st);
+    cudaStreamWaitEvent(side, g_side.fork, 0);
+    {
+        HybTimer t(tm, side, kStGamma);
+        launch_regime<kRegGamma>(x, h, z, idx, meta, id, num, side);
+    }
+    {
+        HybTimer t(tm, side, kStNormal);
+        launch_regime<kRegNormal>(x, h, z, idx, meta, id, num, side);
+    }
+    {
+        HybTimer t(tm, side, kStDevroye);
+        launch_regime<kRegDevroye>(x, h, z, idx, meta, id, num, side);
+    }
     double *state = (double *)((char *)work + hybrid_state_offset(num));
     const int cap = num < kStateChunk ? num : kStateChunk;
     static const int g_sp_setup = resident_grid(k_sp_setup, 128, 1 << 30);
@@ -406,23 +463,29 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
     // One set-up/loop pair per state chunk.  The regime counts live on the device, so pairs are
     // issued for the largest possible count; those past the regime's count return at once.
     for (int c0 = 0; c0 < num; c0 += cap) {
-        k_sp_setup<<<std::min(sneed, g_sp_setup), 128, 0, st>>>(h, z, idx, meta, state, c0, cap);
-        k_sp_loop<<<std::min(lneed, g_sp_loop), kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
+        {
+            HybTimer t(tm, st, kStSpSetup);
+            k_sp_setup<<<std::min(sneed, g_sp_setup), 128, 0, st>>>(h, z, idx, meta, state, c0, cap);
+        }
+        {
+            HybTimer t(tm, st, kStSpLoop);
+            k_sp_loop<<<std::min(lneed, g_sp_loop), kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
+        }
         count_launch(2);
     }
-    if (tm) cudaEventRecord(g_hyb_ev[2], st);
     for (int c0 = 0; c0 < num; c0 += cap) {
-        k_alt_setup<<<std::min(sneed, g_alt_setup), 128, 0, st>>>(h, z, idx, meta, state, c0, cap);
-        k_alt_loop<<<std::min(lneed, g_alt_loop), kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
+        {
+            HybTimer t(tm, st, kStAltSetup);
+            k_alt_setup<<<std::min(sneed, g_alt_setup), 128, 0, st>>>(h, z, idx, meta, state, c0, cap);
+        }
+        {
+            HybTimer t(tm, st, kStAltLoop);
+            k_alt_loop<<<std::min(lneed, g_alt_loop), kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
+        }
         count_launch(2);
     }
-    if (tm) cudaEventRecord(g_hyb_ev[3], st);
-    launch_regime<kRegGamma>(x, h, z, idx, meta, id, num, st);
-    if (tm) cudaEventRecord(g_hyb_ev[4], st);
-    launch_regime<kRegNormal>(x, h, z, idx, meta, id, num, st);
-    if (tm) cudaEventRecord(g_hyb_ev[5], st);
-    launch_regime<kRegDevroye>(x, h, z, idx, meta, id, num, st);
-    if (tm) cudaEventRecord(g_hyb_ev[6], st);
+    cudaEventRecord(g_side.join, side);
+    cudaStreamWaitEvent(st, g_side.join, 0);
     return cudaGetLastError();
 }
 

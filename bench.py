@@ -248,20 +248,23 @@ def main():
     mean_omega = float(x_d[: 1 << 20].mean().item())
     # dominant kernel of the step, timed live with CUDA events on the launch stream (separate,
     # untimed pass so the event records do not sit inside the headline region)
-    stage_ms, regime_counts = None, None
+    stage_ms, stage_launches, regime_counts = None, None, None
     if wl == "hybrid":
         import ctypes as C
+        names = ["binning", "sp_setup", "sp_loop", "alt_setup", "alt_loop", "sum_of_gammas", "normal", "devroye"]
         L.bl_hybrid_timing(1)
-        acc6 = [0.0] * 6
+        acc = [0.0] * 8
+        nl = [0] * 8
         reps = max(1, min(3, args.steps))
         for k in range(reps):
             step_dev(3000 + k)
-            buf = (C.c_double * 6)()
-            if L.bl_hybrid_timing_last(C.cast(buf, C.c_void_p)) == 0:
-                acc6 = [a + b for a, b in zip(acc6, buf)]
+            buf, cnt = (C.c_double * 8)(), (C.c_int * 8)()
+            if L.bl_hybrid_timing_last(C.cast(buf, C.c_void_p), C.cast(cnt, C.c_void_p)) == 0:
+                acc = [a + b for a, b in zip(acc, buf)]
+                nl = list(cnt)
         L.bl_hybrid_timing(0)
-        stage_ms = dict(zip(["binning", "saddle_point", "alternate", "sum_of_gammas", "normal", "devroye"],
-                            [max_over_ranks(v / reps) for v in acc6]))
+        stage_ms = dict(zip(names, [max_over_ranks(v / reps) for v in acc]))
+        stage_launches = dict(zip(names, nl))
         hh = shape_d
         regime_counts = {"saddle_point": int(((hh > 13) & (hh <= 170)).sum().item()),
                          "normal": int((hh > 170).sum().item()),
@@ -353,14 +356,38 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         fp64_peak = 37.0   # TFLOP/s, B200 vector FP64 (not in MEASURED_PEAKS.json)
+        counters = {}
+        try:
+            counters = json.load(open(os.path.join(ROOT, "profiles", "ncu_counters.json")))
+        except OSError:
+            pass
         if stage_ms:
-            # dominant kernel = the saddle-point regime kernel: its own draws, its own launch time
-            dom_units, dom_ms, dom_name = regime_counts["saddle_point"], stage_ms["saddle_point"], "k_hyb_regime<saddle-point>"
+            # dominant kernel = the larger of the two saddle-point kernels (set-up, rejection loop);
+            # a step launches it once per state chunk: figures are per launch, averaged over the
+            # non-empty launches of the timed pass
+            dom_stage = "sp_setup" if stage_ms["sp_setup"] >= stage_ms["sp_loop"] else "sp_loop"
+            dom_name = "k_" + dom_stage
+            n_launch = max(1, stage_launches[dom_stage])
+            dom_units, dom_ms = regime_counts["saddle_point"] / n_launch, stage_ms[dom_stage] / n_launch
+            dom_share = stage_ms[dom_stage] / (total_ms / args.steps)
             dom_kflop = 9.0
+            # HBM bytes the design moves per saddle-point draw in this kernel:
+            # set-up: idx 4 + h 8 + z 8 in, 18 state doubles out; loop: idx 4 + h 8 + z 8 + state in, x 8 out
+            design_bytes = {"sp_setup": 20 + 144, "sp_loop": 20 + 144 + 8}[dom_stage]
         else:
             dom_units, dom_ms, dom_name, dom_kflop = num, kern_ms, "k_devroye_refill", KFLOP_PER_DRAW[wl]
+            dom_share, n_launch, design_bytes = 1.0, 1, BYTES_PER_DRAW[wl]
         achieved = dom_units * BYTES_PER_DRAW[wl] / (dom_ms * 1e-3) / 1e9
-        tf = dom_units * dom_kflop * 1e3 / (dom_ms * 1e-3) / 1e12
+        ctr = counters.get(dom_name, {})
+        traffic = None
+        if ctr.get("dram_bytes_per_unit") is not None:
+            traffic = ctr["dram_bytes_per_unit"] * dom_units
+        tf_all = None
+        if stage_ms:
+            sp_ms = stage_ms["sp_setup"] + stage_ms["sp_loop"]
+            tf_all = regime_counts["saddle_point"] * dom_kflop * 1e3 / (sp_ms * 1e-3) / 1e12
+        else:
+            tf_all = dom_units * dom_kflop * 1e3 / (dom_ms * 1e-3) / 1e12
         out = {
             "metric": "pg_draws_per_sec", "value": value, "unit": "draws/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -368,15 +395,26 @@ def main():
             "data": "synthetic", "config": workload_config(args),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None,
+                         "frac": achieved / hbm_peak, "traffic": traffic,
                          "peak_source": "measured" if peaks else "fallback",
-                         "kernel": dom_name, "kernel_ms": dom_ms, "units_per_launch": dom_units,
-                         "bytes_per_unit": BYTES_PER_DRAW[wl], "share_of_step": dom_ms / (total_ms / args.steps),
-                         "stage_ms": stage_ms, "regime_counts": regime_counts,
-                         "note": "the sampler is bound by the FP64/ALU pipes, not HBM (SURVEY.md 8d); see roofline_compute"},
-            "roofline_compute": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s(fp64-equivalent model)",
-                                 "frac": tf / fp64_peak, "kflop_per_draw": dom_kflop, "kernel": dom_name,
-                                 "peak_source": "nominal B200 vector FP64 (no measured FP64 peak in MEASURED_PEAKS.json)"},
+                         "kernel": dom_name, "kernel_ms": dom_ms, "launches_per_step": n_launch,
+                         "units_per_launch": dom_units, "bytes_per_unit": BYTES_PER_DRAW[wl],
+                         "design_bytes_per_unit": design_bytes,
+                         "share_of_step": dom_share,
+                         "stage_ms": stage_ms, "stage_launches": stage_launches, "regime_counts": regime_counts,
+                         "note": "the sampler is bound by the issue slots / FP64 pipe, not HBM (SURVEY.md 8d): "
+                                 "see roofline_compute; traffic = ncu dram bytes per draw (profiles/ncu_counters.json) "
+                                 "x units_per_launch"},
+            "roofline_compute": {"bound": "sm issue / fp64 pipe", "kernel": dom_name,
+                                 "ncu": {k: ctr.get(k) for k in ("issue_slots_busy_pct", "fp64_pipe_pct", "alu_pipe_pct",
+                                                                  "xu_pipe_pct", "active_threads_per_warp_instr",
+                                                                  "warp_instr_per_unit", "source")} if ctr else None,
+                                 "reference_equivalent": {
+                                     "achieved": tf_all, "peak": fp64_peak, "frac": tf_all / fp64_peak,
+                                     "unit": "TFLOP/s the REFERENCE algorithm would need at this draw rate "
+                                             "(SURVEY.md 8d cost model, %.1f kFLOP/draw); the engine executes far fewer "
+                                             "(tables instead of Newton, fp32 decision filters)" % dom_kflop,
+                                     "peak_source": "nominal B200 vector FP64 (no measured FP64 peak in MEASURED_PEAKS.json)"}},
             "cpu_baseline": cpu, "mean_omega_first_1M": mean_omega, "extras": extras,
         }
         print(json.dumps(out))

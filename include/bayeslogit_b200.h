@@ -206,10 +206,12 @@ int bl_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2);
 uint64_t bl_kernel_launches(void);
 
 /* Per-stage CUDA-event timing of the regime-binned rpg_hybrid path (measurement aid): after
- * bl_hybrid_timing(1), bl_hybrid_timing_last() returns the milliseconds of
- * [binning, saddle-point, alternate, sum-of-gammas, normal, Devroye] of the last launch. */
+ * bl_hybrid_timing(1), bl_hybrid_timing_last() returns, for the last launch, the milliseconds of
+ * [binning, saddle-point set-up, saddle-point loop, alternate set-up, alternate loop,
+ *  sum-of-gammas, normal, Devroye] and (launches8 may be null) the non-empty kernel launches
+ * each figure sums over. */
 void bl_hybrid_timing(int enable);
-int bl_hybrid_timing_last(double *ms6);
+int bl_hybrid_timing_last(double *ms8, int *launches8);
 
 #ifdef __cplusplus
 }
