@@ -165,7 +165,7 @@ struct Sweep {
     {
         nt = cdiv(P, kGramTile);
         int tiles = nt * (nt + 1) / 2;
-        nslab = (int)std::min<int64_t>(std::max<int64_t>(1, 148 * 4 / tiles), std::max<int64_t>(1, N / (4 * kGramRows)));
+        nslab = (int)std::min<int64_t>(std::max<int64_t>(1, 148 * 2 / tiles), std::max<int64_t>(1, N / (4 * kGramRows)));   // 2 CTAs/SM resident: one wave
         if (nslab < 1) nslab = 1;
         xtv_slabs = (int)std::min<int64_t>(148 * 2, std::max<int64_t>(1, N / 64));
         GB_CK(m.get(&psi, N));
@@ -178,8 +178,10 @@ struct Sweep {
         GB_CK(cudaMemsetAsync(status, 0, sizeof(int), st));
         GB_CK(cudaMemsetAsync(acc, 0, ((size_t)P * P + P) * sizeof(double), st));
         beta_smem = (2 * (size_t)(P | 1) * P + 5 * (size_t)P) * sizeof(double);
-        GB_CK(cudaFuncSetAttribute(k_gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRows, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)gram_smem_bytes(true)));
+        GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRowsDiag, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)gram_smem_bytes(false)));
         use_smem = beta_smem <= 200 * 1024;
         if (use_smem && beta_smem > 48 * 1024)
             GB_CK(cudaFuncSetAttribute(k_beta_draw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem));
@@ -197,7 +199,10 @@ struct Sweep {
     void gram(const double *wv)
     {
         int tiles = nt * (nt + 1) / 2;
-        k_gram_partial<<<dim3(nslab, tiles), 256, gram_smem_bytes(nt > 1), st>>>(part, tX, wv, N, P, nt);
+        if (nt > 1)
+            k_gram_partial<kGramRows, false><<<dim3(nslab, tiles), 256, gram_smem_bytes(true), st>>>(part, tX, wv, N, P, nt);
+        else
+            k_gram_partial<kGramRowsDiag, true><<<dim3(nslab, tiles), 256, gram_smem_bytes(false), st>>>(part, tX, wv, N, P, nt);
         k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, 2 * nslab);
         count_launch(2);
     }

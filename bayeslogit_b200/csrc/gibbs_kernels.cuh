@@ -37,7 +37,7 @@ k_xbeta(double *__restrict__ psi, const double *__restrict__ tX, const double *_
     const int lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    constexpr int R = 4;                       // rows per warp-trip: 4x the loads in flight
+    constexpr int R = 8;                       // rows per warp-trip: 8x the loads in flight
     for (int64_t i0 = wid * R; i0 < N; i0 += warps * R) {
         double s[R];
 #pragma unroll
@@ -74,7 +74,8 @@ k_xbeta(double *__restrict__ psi, const double *__restrict__ tX, const double *_
 // Per-CTA partial tiles go to `part`; k_gram_reduce sums them in a fixed order
 // (deterministic, no atomics).  Bound by the FP64 pipe: ~N P^2 (1 + 1/16) FMA.
 // ---------------------------------------------------------------------------------
-constexpr int kGramRows = 32;
+constexpr int kGramRows = 32;       // rows per chunk when a CTA streams two column panels (P > 64)
+constexpr int kGramRowsDiag = 64;   // P <= 64: one panel per chunk, so twice the rows fit and barriers halve
 constexpr int kGramTile = 64;
 constexpr int kGramLd = kGramTile;          // dense rows: column reads are lane-consecutive
 
@@ -117,6 +118,52 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 //           per chunk; row group g multiplies rows [16g, 16g+16) of each chunk.
 //   C = sum_r (w_r x_r[i]) x_r[j]: A[i][r] = w_r X[r][i] (weight folded into the A fragment),
 //   B[r][j] = X[r][j].
+// Diagonal 64x64 tile, balanced over the CTA's warps.  Its 36 live 8x8 MMA tiles (mi <= mj) are
+// dealt to four warp slots as the row pairs (A, 7 - A): (8 - A) + (A + 1) = 9 tiles each, and the
+// two row groups split the chunk's rows, so all 8 warps issue the same 9 DMMAs per k-step.  (With
+// 32x32 sub-tiles per warp, one of four warps had nothing to do and one had 16 tiles against
+// 10: the DMMA pipe idled 44 % of the time waiting at the chunk barrier.)
+// c[0 .. 8-A): tiles (A, A..7); c[8-A .. 9): tiles (7-A, 7-A..7)
+template <int A, int kRows>
+__device__ __forceinline__ void gram_diag_chunk(double (&c)[9][2], const double *chunk, const double *wts,
+                                                int grp, int gid, int tig)
+{
+    constexpr int kLo = 8 - A;
+#pragma unroll
+    for (int kk = 0; kk < kRows / 8; ++kk) {
+        const int r = grp * (kRows / 2) + kk * 4 + tig;          // this lane's k row
+        const double wr = wts[r];
+        const double *row = chunk + r * kGramLdm + gid;
+        double b[8];
+#pragma unroll
+        for (int j = A; j < 8; ++j) b[j] = row[8 * j];
+        const double alo = b[A] * wr, ahi = b[7 - A] * wr;
+#pragma unroll
+        for (int j = A; j < 8; ++j) dmma884(c[j - A][0], c[j - A][1], alo, b[j]);
+#pragma unroll
+        for (int j = 7 - A; j < 8; ++j) dmma884(c[kLo + j - (7 - A)][0], c[kLo + j - (7 - A)][1], ahi, b[j]);
+    }
+}
+
+template <int A>
+__device__ __forceinline__ void gram_diag_store(const double (&c)[9][2], double *out, int gid, int tig)
+{
+    constexpr int kLo = 8 - A;
+#pragma unroll
+    for (int j = A; j < 8; ++j) {
+        int row = 8 * A + gid, col = 8 * j + 2 * tig;
+        out[row * kGramTile + col] = c[j - A][0];
+        out[row * kGramTile + col + 1] = c[j - A][1];
+    }
+#pragma unroll
+    for (int j = 7 - A; j < 8; ++j) {
+        int row = 8 * (7 - A) + gid, col = 8 * j + 2 * tig;
+        out[row * kGramTile + col] = c[kLo + j - (7 - A)][0];
+        out[row * kGramTile + col + 1] = c[kLo + j - (7 - A)][1];
+    }
+}
+
+template <int kRows, bool kBalancedDiag>
 __global__ void __launch_bounds__(256)
 k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const double *__restrict__ w,
                int64_t N, int P, int nt)
@@ -128,8 +175,8 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
     const int bj = bi + t;
     const bool diag = bi == bj;
     const int npanel = diag ? 1 : 2;
-    const int stage_elems = npanel * kGramRows * kGramLdm + kGramRows;
-    const int w_off = npanel * kGramRows * kGramLdm;
+    const int stage_elems = npanel * kRows * kGramLdm + kRows;
+    const int w_off = npanel * kRows * kGramLdm;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
@@ -138,6 +185,7 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
     const bool tri = diag && si == sj;                 // diagonal sub-tile: MMA tiles with mi <= mj only
 
     double c[4][4][2] = {};
+    double c9[9][2] = {};                               // kBalancedDiag: this warp's 9 tiles
     const int64_t slab = (N + gridDim.x - 1) / gridDim.x;
     const int64_t r0 = (int64_t)blockIdx.x * slab;
     const int64_t r1 = r0 + slab < N ? r0 + slab : N;
@@ -147,27 +195,27 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
         const int so = sidx * stage_elems;
         if (base < r1) {
             if (vec16) {
-                for (int e = threadIdx.x; e < npanel * kGramRows * (kGramTile / 2); e += nthr) {
-                    int pnl = e >= kGramRows * (kGramTile / 2);
-                    int rem = e - pnl * (kGramRows * (kGramTile / 2));
+                for (int e = threadIdx.x; e < npanel * kRows * (kGramTile / 2); e += nthr) {
+                    int pnl = e >= kRows * (kGramTile / 2);
+                    int rem = e - pnl * (kRows * (kGramTile / 2));
                     int r = rem >> 5, cc = (rem & 31) * 2;
                     int64_t i = base + r;
                     int col = (pnl == 0 ? bi : bj) * kGramTile + cc;
                     bool ok = i < r1 && col < P;
-                    cp_async16(&gsm[so + (pnl * kGramRows + r) * kGramLdm + cc], ok ? tX + i * P + col : tX, ok);
+                    cp_async16(&gsm[so + (pnl * kRows + r) * kGramLdm + cc], ok ? tX + i * P + col : tX, ok);
                 }
             } else {
-                for (int e = threadIdx.x; e < npanel * kGramRows * kGramTile; e += nthr) {
-                    int pnl = e >= kGramRows * kGramTile;
-                    int rem = e - pnl * (kGramRows * kGramTile);
+                for (int e = threadIdx.x; e < npanel * kRows * kGramTile; e += nthr) {
+                    int pnl = e >= kRows * kGramTile;
+                    int rem = e - pnl * (kRows * kGramTile);
                     int r = rem >> 6, cc = rem & 63;
                     int64_t i = base + r;
                     int col = (pnl == 0 ? bi : bj) * kGramTile + cc;
                     bool ok = i < r1 && col < P;
-                    cp_async8(&gsm[so + (pnl * kGramRows + r) * kGramLdm + cc], ok ? tX + i * P + col : tX, ok);
+                    cp_async8(&gsm[so + (pnl * kRows + r) * kGramLdm + cc], ok ? tX + i * P + col : tX, ok);
                 }
             }
-            if (threadIdx.x < kGramRows) {
+            if (threadIdx.x < kRows) {
                 int64_t i = base + threadIdx.x;
                 cp_async8(&gsm[so + w_off + threadIdx.x], i < r1 ? w + i : w, i < r1);
             }
@@ -176,20 +224,28 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
     };
 
     issue(r0, 0);
-    issue(r0 + kGramRows, 1);
+    issue(r0 + kRows, 1);
     int cur = 0;
-    for (int64_t base = r0; base < r1; base += kGramRows) {
+    for (int64_t base = r0; base < r1; base += kRows) {
         cp_async_wait<1>();
         __syncthreads();
         int nxt = cur + 2 >= kGramStages ? cur + 2 - kGramStages : cur + 2;
-        issue(base + 2 * kGramRows, nxt);
-        if (live) {
+        issue(base + 2 * kRows, nxt);
+        if (kBalancedDiag) {
+            const double *chunk = gsm + cur * stage_elems;
+            switch (sub) {
+            case 0: gram_diag_chunk<0, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
+            case 1: gram_diag_chunk<1, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
+            case 2: gram_diag_chunk<2, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
+            default: gram_diag_chunk<3, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
+            }
+        } else if (live) {
             const int so = cur * stage_elems;
             const int pa = so + si * 32 + gid;                                         // A: panel bi
-            const int pb = so + (npanel - 1) * kGramRows * kGramLdm + sj * 32 + gid;   // B: panel bj
+            const int pb = so + (npanel - 1) * kRows * kGramLdm + sj * 32 + gid;   // B: panel bj
 #pragma unroll
-            for (int kk = 0; kk < kGramRows / 8; ++kk) {
-                const int r = grp * (kGramRows / 2) + kk * 4 + tig;                    // this lane's k row
+            for (int kk = 0; kk < kRows / 8; ++kk) {
+                const int r = grp * (kRows / 2) + kk * 4 + tig;                    // this lane's k row
                 const double wr = gsm[so + w_off + r];
                 double a[4], b[4];
 #pragma unroll
@@ -209,7 +265,14 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
     cp_async_wait<0>();
     // partial tile of (slab, row group): entries exist where (row >> 3) <= (col >> 3) on diagonal tiles
     double *out = part + ((size_t)blockIdx.y * (gridDim.x * 2) + blockIdx.x * 2 + grp) * (kGramTile * kGramTile);
-    if (live) {
+    if (kBalancedDiag) {
+        switch (sub) {
+        case 0: gram_diag_store<0>(c9, out, gid, tig); break;
+        case 1: gram_diag_store<1>(c9, out, gid, tig); break;
+        case 2: gram_diag_store<2>(c9, out, gid, tig); break;
+        default: gram_diag_store<3>(c9, out, gid, tig); break;
+        }
+    } else if (live) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -222,9 +285,12 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
     }
 }
 
+inline int gram_rows(bool any_offdiag) { return any_offdiag ? kGramRows : kGramRowsDiag; }
+
 inline size_t gram_smem_bytes(bool any_offdiag)
 {
-    return (size_t)kGramStages * ((any_offdiag ? 2 : 1) * kGramRows * kGramLdm + kGramRows) * sizeof(double);
+    int rows = gram_rows(any_offdiag);
+    return (size_t)kGramStages * ((any_offdiag ? 2 : 1) * rows * kGramLdm + rows) * sizeof(double);
 }
 
 // PP = P0 + sum over slabs of the partial tiles, mirrored to a full symmetric P x P

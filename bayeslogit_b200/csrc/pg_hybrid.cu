@@ -17,6 +17,7 @@
 // Results are unchanged by the re-ordering: each observation draws from the Philox
 // stream keyed by its own global index (philox.cuh).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "engine.h"
@@ -437,9 +438,12 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
     // The three light regimes (0.15 % + 15 % + 0.5 % of this workload's draws; the sum of gammas
     // is 200 sequential gamma variates per draw at single-digit occupancy) run on a side stream
     // forked here and joined at the end, underneath the saddle-point and alternate kernels.
-    cudaStream_t side = g_side.get();
-    cudaEventRecord(g_side.fork, st);
-    cudaStreamWaitEvent(side, g_side.fork, 0);
+    static const bool use_side = getenv("BL_HYBRID_NO_SIDE_STREAM") == nullptr;
+    cudaStream_t side = use_side ? g_side.get() : st;
+    if (use_side) {
+        cudaEventRecord(g_side.fork, st);
+        cudaStreamWaitEvent(side, g_side.fork, 0);
+    }
     {
         HybTimer t(tm, side, kStGamma);
         launch_regime<kRegGamma>(x, h, z, idx, meta, id, num, side);
@@ -484,8 +488,10 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
         }
         count_launch(2);
     }
-    cudaEventRecord(g_side.join, side);
-    cudaStreamWaitEvent(st, g_side.join, 0);
+    if (use_side) {
+        cudaEventRecord(g_side.join, side);
+        cudaStreamWaitEvent(st, g_side.join, 0);
+    }
     return cudaGetLastError();
 }
 

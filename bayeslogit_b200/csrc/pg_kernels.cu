@@ -105,7 +105,11 @@ __global__ void k_probe_v_eval(double *v, const double *y, int64_t num)
 
 // which: 0 Phi(a), 1 log Phi(a), 2 P(shape=b, a*c) [= RNG::p_gamma_rate(a,b,c)],
 //        3 p_igauss(a, mu=b, lambda=c), 4 lgamma(a), 5 tgamma(a), 6 right mass of the
-//        Devroye proposal at Z=a, 7 Devroye coefficient a_n(x): n=b, x=a
+//        Devroye proposal at Z=a, 7 Devroye coefficient a_n(x): n=b, x=a,
+//        8 Gamma(b, a) e^a a^-b by the forward continued fraction (a >= b + 1),
+//        9 p_igauss_direct(a, mu=b, lambda=c), 10 log cos_rt(v(a)) as the saddle-point sampler
+//        takes it (table or reference iteration), 11 v(a) from the table path alone (NaN where
+//        the table path hands over to the reference iteration)
 __global__ void k_probe_specfun(double *out, int which, const double *a, const double *b,
                                 const double *c, int64_t num)
 {
@@ -121,6 +125,10 @@ __global__ void k_probe_specfun(double *out, int which, const double *a, const d
     case 5: r = tgamma(a[i]); break;
     case 6: r = dev_right_mass(a[i]); break;
     case 7: r = dev_coef((int)b[i], a[i]); break;
+    case 8: r = upper_gamma_cf(b[i], a[i]); break;
+    case 9: r = p_igauss_direct(a[i], b[i], c[i]); break;
+    case 10: { double v, g; sp_vg(a[i], v, g); r = g; break; }
+    case 11: { double v, g; r = sp_vg_table(a[i], v, g) ? v : nan(""); break; }
     }
     out[i] = r;
 }

@@ -104,6 +104,49 @@ def test_moments_and_v_eval_match_golden(engine, gold):
     np.testing.assert_allclose(engine.v_eval(gold["vev_y"]), gold["vev_v"], rtol=1e-12, atol=1e-14)
 
 
+def test_saddle_point_tables_match_mpmath_golden(engine, oracle):
+    """V(y) = y^-1(y) and G(y) = log cos_rt(V(y)) as the saddle-point kernels take them (degree-9
+    tables, reference Newton where its iterates clamp) against 40-digit values
+    (tests/golden/make_sp_golden.py)."""
+    g = dict(np.load(os.path.join(os.path.dirname(GOLD), "sp_tables_golden.npz")))
+    y = g["y"]
+    vt = engine.specfun("sp_v_table", y)
+    on_table = ~np.isnan(vt)
+    assert on_table.mean() > 0.98                       # random y: the table path is the path taken
+    assert np.max(np.abs(vt[on_table] - g["y_v"][on_table]) / np.maximum(1, np.abs(g["y_v"][on_table]))) < 4e-16
+    gg = engine.specfun("sp_log_cos_rt", y)
+    assert np.max(np.abs(gg[on_table] - g["y_g"][on_table]) / np.maximum(1, np.abs(g["y_g"][on_table]))) < 4e-16
+    # off the table the reference's own iteration decides (its iterates clamp to a 7-digit grid
+    # there, so the answer is NOT the root): the engine has to agree with the reference, not mpmath
+    off = ~on_table
+    v = engine.v_eval(y)
+    assert np.array_equal(v[on_table], vt[on_table])
+    vo = np.array([oracle.v_eval(float(t)) for t in y[off]])
+    np.testing.assert_allclose(v[off], vo, rtol=1e-12, atol=1e-14)
+    cos_rt = np.where(vo >= 0, np.cos(np.sqrt(np.abs(vo))), np.cosh(np.sqrt(np.abs(vo))))
+    np.testing.assert_allclose(gg[off], np.log(cos_rt), rtol=1e-12, atol=1e-14)
+    # hugging the reference's grid points and y = 1 the table path must decline: there the reference's
+    # answer is its grid bracket / series branch, not the root
+    near = engine.specfun("sp_v_table", g["y_near"])
+    d = np.abs(np.log2(g["y_near"]) * 10 - np.round(np.log2(g["y_near"]) * 10))
+    assert np.all(np.isnan(near[d < 2e-5]))
+    assert np.all(np.isnan(near[np.abs(g["y_near"] - 1) < 5e-7]))
+
+
+def test_saddle_point_weight_functions(engine):
+    """Forward continued fraction of Gamma(a,x) e^x x^-a and the direct inverse-Gaussian CDF."""
+    rng = np.random.default_rng(5)
+    a = rng.uniform(1, 171, 4000)
+    x = np.maximum(a + 1.0, a * rng.uniform(1.0, 2.5, a.size))
+    got = engine.specfun("upper_gamma_cf", x, a)
+    want = np.exp(np.log(special.gammaincc(a, x)) + special.gammaln(a) + x - a * np.log(x))
+    ok = special.gammaincc(a, x) > 1e-280
+    np.testing.assert_allclose(got[ok], want[ok], rtol=2e-12)      # scipy's own Q carries ~1e-13
+    xi, mu, lam = rng.uniform(0.05, 1.1, 2000), rng.uniform(0.05, 5, 2000), rng.uniform(1, 170, 2000)
+    np.testing.assert_allclose(engine.specfun("p_igauss_direct", xi, mu, lam),
+                               engine.specfun("p_igauss", xi, mu, lam), rtol=2e-12, atol=1e-300)
+
+
 # ----------------------------------------------------------------------------------
 # tier 1: golden vectors made from the reference itself
 # ----------------------------------------------------------------------------------
