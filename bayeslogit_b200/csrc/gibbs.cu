@@ -190,7 +190,7 @@ struct Sweep {
 
     void xbeta(double *out, const double *beta, const double *off, double off_scale, double shift = 0.0)
     {
-        int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (N + 31) / 32));
+        int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (N + 255) / 256));
         k_xbeta<<<grid, 256, P * sizeof(double), st>>>(out, tX, beta, off, off_scale, shift, N, P);
         count_launch();
     }

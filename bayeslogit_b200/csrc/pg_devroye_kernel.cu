@@ -79,16 +79,16 @@ k_cls_scatter(const double *__restrict__ z, int n, int *__restrict__ meta, int *
 template <bool kIndexed>
 __global__ void __launch_bounds__(kThreads)
 k_devroye_refill(double *__restrict__ x, const int *__restrict__ n, const double *__restrict__ z,
-                 int64_t num, StreamId id, const int *__restrict__ idx)
+                 int64_t num, StreamId id, const int *__restrict__ idx, int chunk)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t stride = (int64_t)gridDim.x * (kThreads / 32) * kChunkObs;
+    const int64_t stride = (int64_t)gridDim.x * (kThreads / 32) * chunk;
 
-    int64_t cur = warp * kChunkObs;       // next unassigned observation of this warp (uniform)
-    int64_t cend = cur + kChunkObs;       // end of the current chunk (uniform)
+    int64_t cur = warp * chunk;       // next unassigned observation of this warp (uniform)
+    int64_t cend = cur + chunk;       // end of the current chunk (uniform)
 
     bool active = false;
     int64_t obs = 0;
@@ -102,7 +102,7 @@ k_devroye_refill(double *__restrict__ x, const int *__restrict__ n, const double
         if (want && cur < num) {
             int rank = __popc(want & lt_mask);
             int64_t cand = cur + rank;
-            if (cand >= cend) cand += stride - kChunkObs;
+            if (cand >= cend) cand += stride - chunk;
             if (!active && cand < num) {
                 if (kIndexed) cand = idx[cand];                  // position in the class-sorted list -> observation
                 int ni = n[cand];
@@ -121,7 +121,7 @@ k_devroye_refill(double *__restrict__ x, const int *__restrict__ n, const double
             if (cur >= cend) {
                 int64_t over = cur - cend;
                 cend += stride;
-                cur = cend - kChunkObs + over;
+                cur = cend - chunk + over;
             }
         }
         if (!__any_sync(full, active)) {
@@ -147,9 +147,13 @@ cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int6
                                   StreamId id, cudaStream_t st, void *work)
 {
     if (num <= 0) return cudaSuccess;
-    int64_t chunks = (num + kChunkObs - 1) / kChunkObs;
-    int64_t blocks = (chunks + (kThreads / 32) - 1) / (kThreads / 32);
     int64_t cap = 148LL * 4;                 // 148 SMs x resident CTAs
+    // Chunks are dealt round-robin to warps; a warp should see at least ~8 of them or the last
+    // round leaves part of the chip idle (N = 1M rows of a Gibbs sweep is only 1.65 chunks of 128
+    // per resident warp).
+    int chunk = num >= cap * (kThreads / 32) * kChunkObs * 8 ? kChunkObs : kChunkObs / 4;
+    int64_t chunks = (num + chunk - 1) / chunk;
+    int64_t blocks = (chunks + (kThreads / 32) - 1) / (kThreads / 32);
     int grid = (int)(blocks < cap ? blocks : cap);
     if (work && num >= (1 << 20) && num < (1LL << 31)) {
         int *meta = (int *)work, *idx = meta + 32;
@@ -159,10 +163,10 @@ cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int6
         int bgrid = tiles < 148 * 8 ? tiles : 148 * 8;
         k_cls_count<<<bgrid, kBinThreads, 0, st>>>(z, (int)num, meta);
         k_cls_scatter<<<bgrid, kBinThreads, 0, st>>>(z, (int)num, meta, idx);
-        k_devroye_refill<true><<<grid, kThreads, 0, st>>>(x, n, z, num, id, idx);
+        k_devroye_refill<true><<<grid, kThreads, 0, st>>>(x, n, z, num, id, idx, chunk);
         count_launch(3);
     } else {
-        k_devroye_refill<false><<<grid, kThreads, 0, st>>>(x, n, z, num, id, nullptr);
+        k_devroye_refill<false><<<grid, kThreads, 0, st>>>(x, n, z, num, id, nullptr, chunk);
         count_launch();
     }
     return cudaGetLastError();
