@@ -203,7 +203,7 @@ struct Sweep {
             k_gram_partial<kGramRows, false><<<dim3(nslab, tiles), 256, gram_smem_bytes(true), st>>>(part, tX, wv, N, P, nt);
         else
             k_gram_partial<kGramRowsDiag, true><<<dim3(nslab, tiles), 256, gram_smem_bytes(false), st>>>(part, tX, wv, N, P, nt);
-        k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, 2 * nslab);
+        k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nt > 1 ? 2 * nslab : nslab);
         count_launch(2);
     }
 

@@ -196,40 +196,71 @@ __device__ inline double stream_normal(uint64_t seed, uint32_t call, int k)
 }
 
 // ---- fast path pieces for the plain draw -----------------------------------------------------
-// Root-free right-looking factorisation A = R' D^-1 R (row j of R is row j of the running
-// Schur complement, D = diag(R)): one barrier per column instead of three, no square root or
-// division inside the sweep.  U = D^-1/2 R is the Cholesky factor; it is never formed -- the
-// solves below use R and rd = 1/diag(R) directly.
+// Root-free factorisation A = R' D^-1 R (row j of R is row j of the running Schur complement,
+// D = diag(R)); U = D^-1/2 R is the Cholesky factor and is never formed -- the solves below use
+// R and rd = 1/diag(R) directly.  Blocked by panels of 8 rows so that the CTA meets at three
+// barriers per panel instead of one per column (a column-at-a-time sweep spent ~1000 cycles per
+// column, 32 us at P = 64, mostly waiting at barriers with one division on the critical path):
+//   (a) warp 0 factorises the 8 x 8 diagonal block (the only sequential part: 8 reciprocals);
+//   (b) one thread per column right of the block finishes the 8 panel rows of that column
+//       (forward substitution with the block, no barrier inside);
+//   (c) all threads apply the rank-8 update to the trailing matrix.
 __device__ __forceinline__ void cta_ldl_upper(double *A, double *rd, int P, int ld, int *ok)
 {
+    constexpr int NB = 8;
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int j = 0; j < P; ++j) {
-        __syncthreads();
-        double d = A[j + (size_t)ld * j];
-        if (!(d > 0.0)) { if (tid == 0) *ok = 0; __syncthreads(); return; }
-        double inv = 1.0 / d;
-        if (tid == 0) rd[j] = inv;
-        for (int k = j + 1 + (tid >> 4); k < P; k += nt >> 4) {
-            double s = A[j + (size_t)ld * k] * inv;
-            // four (i,k) entries at a time, all loads issued before the first store
-            for (int i0 = j + 1 + (tid & 15); i0 <= k; i0 += 64) {
-                double r[4], c[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    int i = i0 + 16 * u;
-                    bool in = i <= k;
-                    r[u] = in ? A[j + (size_t)ld * i] : 0.0;
-                    c[u] = in ? A[i + (size_t)ld * k] : 0.0;
+    for (int k0 = 0; k0 < P; k0 += NB) {
+        const int nb = P - k0 < NB ? P - k0 : NB;
+        const int kend = k0 + nb;
+        if (tid < 32) {
+            for (int j = k0; j < kend; ++j) {
+                double d = A[j + (size_t)ld * j];
+                if (!(d > 0.0)) { if (tid == 0) *ok = 0; break; }
+                double inv = 1.0 / d;
+                if (tid == 0) rd[j] = inv;
+                const int k = k0 + (tid & 7);
+                if (k > j && k < kend) {
+                    double s = A[j + (size_t)ld * k] * inv;
+                    for (int i = j + 1 + (tid >> 3); i <= k; i += 4)
+                        A[i + (size_t)ld * k] = fma(-A[j + (size_t)ld * i], s, A[i + (size_t)ld * k]);
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    int i = i0 + 16 * u;
-                    if (i <= k) A[i + (size_t)ld * k] = fma(-r[u], s, c[u]);
-                }
+                __syncwarp();
             }
         }
+        __syncthreads();
+        if (!*ok) return;
+        for (int k = kend + tid; k < P; k += nt) {
+            double r[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) r[j] = j < nb ? A[(k0 + j) + (size_t)ld * k] : 0.0;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                if (j < nb) {
+                    double s = r[j] * rd[k0 + j];
+#pragma unroll
+                    for (int j2 = j + 1; j2 < NB; ++j2)
+                        if (j2 < nb) r[j2] = fma(-A[(k0 + j) + (size_t)ld * (k0 + j2)], s, r[j2]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+                if (j < nb) A[(k0 + j) + (size_t)ld * k] = r[j];
+        }
+        __syncthreads();
+        for (int k = kend + (tid >> 4); k < P; k += nt >> 4) {
+            double s[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) s[j] = j < nb ? A[(k0 + j) + (size_t)ld * k] * rd[k0 + j] : 0.0;
+            for (int i = kend + (tid & 15); i <= k; i += 16) {
+                double acc = A[i + (size_t)ld * k];
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                    if (j < nb) acc = fma(-A[(k0 + j) + (size_t)ld * i], s[j], acc);
+                A[i + (size_t)ld * k] = acc;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
 }
 
 // One warp, x held in registers (lane l owns x[l], x[l+32], ...; up to 8 per lane = P <= 256).

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256, 2)
 k_xbeta(double *__restrict__ psi, const double *__restrict__ tX, const double *__restrict__ beta,
         const double *__restrict__ off, double off_scale, double shift, int64_t N, int P)
 {
-    extern __shared__ double sbeta[];
+    extern __shared__ __align__(16) double sbeta[];
     for (int p = threadIdx.x; p < P; p += blockDim.x) sbeta[p] = beta[p];
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -281,10 +281,27 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
         cur = cur + 1 == kGramStages ? 0 : cur + 1;
     }
     cp_async_wait<0>();
-    // partial tile of (slab, row group): entries exist where (row >> 3) <= (col >> 3) on diagonal tiles
-    double *out = part + ((size_t)blockIdx.y * (gridDim.x * 2) + blockIdx.x * 2 + grp) * (kGramTile * kGramTile);
     if (kBalancedDiag) {
-        switch (sub) {
+        // fold the two row groups inside the CTA (through the drained pipeline buffers): one
+        // partial tile per CTA instead of two halves the reduce kernel's traffic
+        __syncthreads();
+        double *fold = gsm + (sub * 32 + lane) * 19;          // odd stride: conflict-free
+        if (grp == 1) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) { fold[2 * t] = c9[t][0]; fold[2 * t + 1] = c9[t][1]; }
+        }
+        __syncthreads();
+        if (grp == 0) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) { c9[t][0] += fold[2 * t]; c9[t][1] += fold[2 * t + 1]; }
+        }
+    }
+    // partial tile of (slab[, row group]): entries exist where (row >> 3) <= (col >> 3) on diagonal tiles
+    double *out = kBalancedDiag
+        ? part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kGramTile * kGramTile)
+        : part + ((size_t)blockIdx.y * (gridDim.x * 2) + blockIdx.x * 2 + grp) * (kGramTile * kGramTile);
+    if (kBalancedDiag) {
+        if (grp == 0) switch (sub) {
         case 0: gram_diag_store<0>(c9, out, gid, tig); break;
         case 1: gram_diag_store<1>(c9, out, gid, tig); break;
         case 2: gram_diag_store<2>(c9, out, gid, tig); break;
@@ -332,6 +349,7 @@ k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
         int la = a % kGramTile, lb = b % kGramTile;
         // a diagonal tile holds (row, col) wherever (row >> 3) <= (col >> 3): true for every la <= lb
         const double *src = part + (size_t)tile * nslab * (kGramTile * kGramTile) + la * kGramTile + lb;
+#pragma unroll 8
         for (int k = warp; k < nslab; k += 8) s += src[(size_t)k * (kGramTile * kGramTile)];
     }
     red[warp][lane] = s;
