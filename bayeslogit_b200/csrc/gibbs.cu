@@ -163,6 +163,8 @@ struct Sweep {
 
     int init(DevMem &m, std::string &err)
     {
+        // the beta draws keep a vector in registers, 8 entries per lane of one warp (gibbs_beta.cuh)
+        if (P > 256) { err = "P > 256 covariates is not supported by the single-CTA beta draw"; return 1; }
         nt = cdiv(P, kGramTile);
         int tiles = nt * (nt + 1) / 2;
         nslab = (int)std::min<int64_t>(std::max<int64_t>(1, 148 * 2 / tiles), std::max<int64_t>(1, N / (4 * kGramRows)));   // 2 CTAs/SM resident: one wave

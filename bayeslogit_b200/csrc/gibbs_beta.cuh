@@ -183,6 +183,36 @@ __device__ inline double tnorm_std(PhiloxSource &s, double a, double b)
     return z;
 }
 
+// tnorm_std for a whole warp holding identical (a, b) and identical stream state: the two tail
+// probabilities are evaluated side by side on lanes 0 and 1 and exchanged by shuffle, which halves
+// the dependent-instruction chain of the inverse-CDF branch (the constrained beta draw runs P^2 of
+// these back to back on one warp).  Same values as tnorm_std.
+__device__ inline double tnorm_std_warp(PhiloxSource &s, double a, double b, int lane)
+{
+    if (!(a < b)) return a;
+    if (b <= -4.0) return -tnorm_tail(s, -b, -a);
+    if (a >= 4.0) return tnorm_tail(s, a, b);
+    double u = s.unif();
+    const bool upper = a >= 0.0 || (a > -INFINITY && -a < b);
+    const double sg = upper ? 1.0 : -1.0;
+    // lane 0: tail probability at a, lane 1: at b (upper tails Q if `upper`, lower tails P otherwise)
+    double arg = lane == 0 ? a : b;
+    double t = 0.0;
+    if (lane < 2) t = isinf(arg) ? ((arg > 0) == upper ? 0.0 : 1.0) : 0.5 * erfc(sg * arg * kSqrt1_2);
+    const double ta = __shfl_sync(0xffffffffu, t, 0), tb = __shfl_sync(0xffffffffu, t, 1);
+    double z;
+    if (upper) {
+        double q = ta - u * (ta - tb);
+        z = q <= 0.0 ? INFINITY : q >= 1.0 ? -INFINITY : -normcdfinv(q);
+    } else {
+        double p = ta + u * (tb - ta);
+        z = p <= 0.0 ? -INFINITY : p >= 1.0 ? INFINITY : normcdfinv(p);
+    }
+    if (z < a) z = a;
+    if (z > b) z = b;
+    return z;
+}
+
 // k-th normal of the beta stream (seed, obs 2^64-1, call): a normal always takes three
 // words, so the k-th one starts at word 3k -- counter-based generation lets every lane
 // jump straight to its own.
@@ -329,6 +359,75 @@ __device__ inline void warp_solve_plain(const double *R, const double *rd, const
     else warp_solve_plain_k<8>(R, rd, b, e, out, P, ld, lane);
 }
 
+// The coordinate-wise constrained draw, Logit.hpp:366-399, on one warp with beta and z held in
+// registers (lane l owns entries l, l + 32, ...), 1 / L precomputed (iL), and the truncated normal
+// split across lanes: what sits between two consecutive updates is one shuffle (z1), one FMA per
+// owned entry, a 5-stage min/max butterfly, the truncated normal, and one FMA per owned entry.
+// `is` is the permutation scratch (shared memory); all lanes draw every variate so their 32 copies
+// of the stream stay in step.
+template <int KP>
+__device__ __forceinline__ void warp_constrained_sweeps(const double *L, const double *iL, const double *z_in,
+                                                        const double *beta_prev, double *beta_out, int *is,
+                                                        PhiloxSource &src, int P, int ld, int lane)
+{
+    double beta[KP], z[KP];
+#pragma unroll
+    for (int q = 0; q < KP; ++q) {
+        int m = lane + 32 * q;
+        beta[q] = m < P ? beta_prev[m] : 0.0;
+        z[q] = m < P ? z_in[m] : 0.0;
+    }
+    for (int i = lane; i < P; i += 32) is[i] = i;
+    __syncwarp();
+    for (int k = 0; k < P; ++k) {
+        for (int i = 0; i < P - 1; ++i) {
+            double f = (double)i + ((double)P - (double)i) * src.unif();       // r.flat(i, P)
+            unsigned t = (unsigned)f;
+            if (t > (unsigned)(P - 1)) t = (unsigned)(P - 1);
+            if (lane == 0) { int tmp = is[i]; is[i] = is[t]; is[t] = tmp; }
+        }
+        __syncwarp();
+        for (int i = 0; i < P; ++i) {
+            const int c = is[i];
+            double zc = z[0];
+#pragma unroll
+            for (int q = 1; q < KP; ++q) zc = (c >> 5) == q ? z[q] : zc;
+            const double z1 = __shfl_sync(0xffffffffu, zc, c & 31);
+            double cmin = -INFINITY, cmax = INFINITY;
+#pragma unroll
+            for (int q = 0; q < KP; ++q) {
+                int j = lane + 32 * q;
+                if (j >= c && j < P - 1) {
+                    double l1 = L[j + (size_t)ld * c];
+                    double c1 = fma(-beta[q], iL[j + (size_t)ld * c], z1);
+                    if (l1 > 0.0 && c1 > cmin) cmin = c1;
+                    else if (l1 < 0.0 && c1 < cmax) cmax = c1;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                double a = __shfl_xor_sync(0xffffffffu, cmin, o);
+                double b = __shfl_xor_sync(0xffffffffu, cmax, o);
+                if (a > cmin) cmin = a;
+                if (b < cmax) cmax = b;
+            }
+            const double z2 = tnorm_std_warp(src, cmin, cmax, lane);
+            const double dz = z2 - z1;
+#pragma unroll
+            for (int q = 0; q < KP; ++q) {
+                int j = lane + 32 * q;
+                if (j >= c && j < P) beta[q] = fma(L[j + (size_t)ld * c], dz, beta[q]);
+                if (j == c) z[q] = z2;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < KP; ++q) {
+        int m = lane + 32 * q;
+        if (m < P) beta_out[m] = beta[q];
+    }
+}
+
 // One beta draw.  Workspace (all column-major, ld = P):
 //   A  [P*P]  in: PP (posterior precision, full symmetric)   -> U
 //   B  [P*P]  scratch: S = PP^-1 -> L                        (constrained, mvn)
@@ -403,54 +502,27 @@ __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, do
     if (!ok) { if (tid == 0) *status = 2; return; }
     const double *L = B;
     if (tid < 32) {
-        double *beta = v + 3 * P;
         for (int i = lane; i < P; i += 32) mP[i] = rhs[i];
         __syncwarp();
         warp_solve_ut(A, mP, P, ld, lane);
         warp_solve_u(A, mP, P, ld, lane);
-        for (int i = lane; i < P; i += 32) {
-            z[i] = beta_prev[i] - mP[i];
-            beta[i] = beta_prev[i];
-        }
+        for (int i = lane; i < P; i += 32) z[i] = beta_prev[i] - mP[i];
         __syncwarp();
         warp_solve_l(L, z, P, ld, lane);
-        // the permutation lives in the e[] scratch as ints
-        int *is = (int *)e;
-        for (int i = lane; i < P; i += 32) is[i] = i;
-        __syncwarp();
-        for (int k = 0; k < P; ++k) {
-            // every lane draws (so all 32 copies of the stream state stay in step); lane 0 swaps
-            for (int i = 0; i < P - 1; ++i) {
-                double f = (double)i + ((double)P - (double)i) * src.unif();       // r.flat(i, P)
-                unsigned t = (unsigned)f;
-                if (t > (unsigned)(P - 1)) t = (unsigned)(P - 1);
-                if (lane == 0) { int tmp = is[i]; is[i] = is[t]; is[t] = tmp; }
-            }
-            __syncwarp();
-            for (int i = 0; i < P; ++i) {
-                int c = is[i];
-                double z1 = z[c];
-                double cmin = -INFINITY, cmax = INFINITY;
-                for (int j = c + lane; j < P - 1; j += 32) {
-                    double l1 = L[j + (size_t)ld * c];
-                    double c1 = z1 - beta[j] / l1;
-                    if (l1 > 0.0 && c1 > cmin) cmin = c1;
-                    else if (l1 < 0.0 && c1 < cmax) cmax = c1;
-                }
-                for (int o = 16; o; o >>= 1) {
-                    double a = __shfl_xor_sync(0xffffffffu, cmin, o);
-                    double b = __shfl_xor_sync(0xffffffffu, cmax, o);
-                    if (a > cmin) cmin = a;
-                    if (b < cmax) cmax = b;
-                }
-                double z2 = tnorm_std(src, cmin, cmax);     // every lane keeps the same stream state
-                double dz = z2 - z1;
-                for (int j = c + lane; j < P; j += 32) beta[j] = fma(L[j + (size_t)ld * c], dz, beta[j]);
-                if (lane == 0) z[c] = z2;
-                __syncwarp();
-            }
-        }
-        for (int i = lane; i < P; i += 32) beta_out[i] = beta[i];
+    }
+    __syncthreads();
+    // U is no longer needed: its storage takes 1 / L for the sweeps (entries on and below the diagonal)
+    double *iL = A;
+    for (int e2 = tid; e2 < P * P; e2 += blockDim.x) {
+        int j = e2 % P, c = e2 / P;
+        if (j >= c) iL[j + (size_t)ld * c] = 1.0 / L[j + (size_t)ld * c];
+    }
+    __syncthreads();
+    if (tid < 32) {
+        int *is = (int *)e;                  // the permutation lives in the e[] scratch as ints
+        if (P <= 64) warp_constrained_sweeps<2>(L, iL, z, beta_prev, beta_out, is, src, P, ld, lane);
+        else if (P <= 128) warp_constrained_sweeps<4>(L, iL, z, beta_prev, beta_out, is, src, P, ld, lane);
+        else warp_constrained_sweeps<8>(L, iL, z, beta_prev, beta_out, is, src, P, ld, lane);
     }
     __syncthreads();
 }
