@@ -294,7 +294,21 @@ def main():
         torch.cuda.synchronize()
         fn_host(x_p.data_ptr(), shape_p.data_ptr(), z_p.data_ptr(), num, SEED, 0, obs0)
         same = bool(torch.equal(x_p[: 1 << 20], x_d[: 1 << 20].cpu()))
+        # the floor under e2e: pinned host->device bandwidth of this rank's link, measured now
+        # (16 of the 24 bytes per draw go that way; the 8 B coming back overlap on the other direction)
+        probe = torch.empty(1 << 26, dtype=torch.float64).pin_memory()
+        probe_d = torch.empty(1 << 26, dtype=torch.float64, device=dev)
+        probe_d.copy_(probe, non_blocking=True)
+        torch.cuda.synchronize()
+        tp0 = time.perf_counter()
+        for _ in range(3):
+            probe_d.copy_(probe, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = 3 * probe.numel() * 8 / (time.perf_counter() - tp0) / 1e9
+        del probe, probe_d
         e2e = {"value": world * num * e_steps / dt, "unit": "draws/s",
+               "h2d_GBs_measured": h2d_gbs,
+               "pcie_bound_draws_per_s": world * h2d_gbs * 1e9 / (BYTES_PER_DRAW[wl] - 8),
                "h2d_bytes_per_step": int(world * num * (BYTES_PER_DRAW[wl] - 8)),
                "d2h_bytes_per_step": int(world * num * 8), "steps": e_steps,
                "api": "rpg_hybrid C ABI, host pointers (pinned)" if wl == "hybrid" else "rpg_devroye C ABI, host pointers (pinned)",

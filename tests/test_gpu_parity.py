@@ -394,19 +394,25 @@ def test_dropin_entry_points_mirror_r_wrappers(engine, oracle, capsys):
     assert abs(g.mean() - 2.0 / 2 * np.tanh(0.5)) < 0.05
 
 
-def test_large_batch_chunk_pipeline(engine, oracle):
-    """More than one pipeline chunk (4M observations each) through the host-pointer ABI."""
-    num = (1 << 22) * 2 + 12345
+@pytest.mark.parametrize("method", ["devroye", "hybrid"])
+def test_large_batch_chunk_pipeline(engine, oracle, method):
+    """Several pipeline chunks (8M observations each, three slots in rotation) through the host-pointer
+    ABI: draws on both sides of the chunk boundaries equal the oracle's for the same global
+    observation index."""
+    M = 1 << 20
+    num = 34 * M + 12345
     rng = np.random.default_rng(1)
     z = rng.uniform(-5, 5, num)
-    n = np.ones(num, dtype=np.int32)
-    x = engine.rpg_seeded("devroye", n, z, seed=77, call_id=2)
-    idx = np.concatenate([np.arange(0, 5000), np.arange((1 << 22) - 2500, (1 << 22) + 2500),
-                          np.arange(num - 5000, num)])
-    want = oracle.rpg_devroye(n[: 1 << 16], z[: 1 << 16], seed=77, call_id=2)
-    assert_close(x[: 1 << 16], want)
-    for i0 in ((1 << 22) - 2500, num - 5000):
-        want = oracle.rpg_devroye(n[i0:i0 + 5000], z[i0:i0 + 5000], seed=77, call_id=2, obs0=i0)
-        assert_close(x[i0:i0 + 5000], want)
-    m = 0.5 / z * np.tanh(z / 2)
-    assert abs((x - m).mean()) < 5 * 0.2 / np.sqrt(num)
+    if method == "devroye":
+        shape = np.ones(num, dtype=np.int32)
+    else:
+        shape = np.where(rng.random(num) < 0.5, rng.uniform(0.5, 200, num), rng.integers(1, 201, num).astype(float))
+    x = engine.rpg_seeded(method, shape, z, seed=77, call_id=2)
+    fn = getattr(oracle, "rpg_" + method)
+    scale_all = normal_regime_amplification(shape, z) if method == "hybrid" else None
+    for i0 in (0, 8 * M - 2500, 16 * M - 2500, 24 * M - 2500, 32 * M - 2500, num - 5000):
+        want = fn(shape[i0:i0 + 5000], z[i0:i0 + 5000], seed=77, call_id=2, obs0=i0)
+        assert_close(x[i0:i0 + 5000], want, scale=None if scale_all is None else scale_all[i0:i0 + 5000])
+    if method == "devroye":
+        m = 0.5 / z * np.tanh(z / 2)
+        assert abs((x - m).mean()) < 5 * 0.2 / np.sqrt(num)
