@@ -224,7 +224,13 @@ struct DevBuf {
     {
         if (bytes == 0) return 0;
         BL_CK(cudaMalloc(&p, bytes));
-        if (host) BL_CK(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice));
+        if (host) {
+            // a pageable-memory cudaMemcpy may return once the data sits in the driver's staging buffer;
+            // the kernels run on non-blocking streams that do not order against the legacy stream, so
+            // wait for the DMA itself before anything can read the buffer
+            BL_CK(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice));
+            BL_CK(cudaStreamSynchronize(cudaStreamLegacy));
+        }
         return 0;
     }
     int get(void *host, size_t bytes)

@@ -38,6 +38,9 @@ struct Dev {
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(double));
         if (e == cudaSuccess && host) e = cudaMemcpy(p, host, count * sizeof(double), cudaMemcpyHostToDevice);
+        // pageable source: wait for the DMA itself, the sweeps run on a stream that does not order
+        // against the legacy stream
+        if (e == cudaSuccess && host) e = cudaStreamSynchronize(cudaStreamLegacy);
         if (e != cudaSuccess) { err = std::string("device buffer: ") + cudaGetErrorString(e); if (p) cudaFree(p); return nullptr; }
         ptrs.push_back(p);
         return (double *)p;

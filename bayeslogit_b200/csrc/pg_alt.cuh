@@ -143,30 +143,46 @@ __device__ __forceinline__ double alt_coef(double n, double lx3, double ldn, dou
     return coef * ool::exp_(log_kernel);
 }
 
+// The piece the next proposal comes from (PolyaGammaAlt.cpp:141-147): phase 0 -> 1, 2 or 3.  When
+// the chunk's 10000 proposals are used up it closes with -1 instead (:202).  Returns true when
+// that closed the whole draw.  z is |z|/2.
+template <class Src, class St>
+__device__ __forceinline__ bool alt_pick(Src &src, AltLane &L, double z, const St &st)
+{
+    const int o = L.nfull > 0 ? 0 : kAltSetupDoubles;
+    if (L.trial >= 10000) {
+        L.sum += -1.0;
+        L.trial = 0;
+        if (L.nfull > 0)
+            L.nfull--;
+        else
+            L.nrem--;
+        return L.nfull == 0 && L.nrem == 0;
+    }
+    L.trial++;
+    if (src.unif() < st.get(o + kAltPr)) {
+        L.phase = 1;
+    } else {
+        L.phase = (st.get(o + kAltH) / z > st.get(o + kAltTrunc)) ? 2 : 3;
+        L.alpha = 0.0;
+    }
+    return false;
+}
+
 // One trip of a lane: returns true when the whole draw is complete (L.sum = omega).  z is |z|/2.
 template <class Src, class St>
 __device__ __forceinline__ bool alt_trip(Src &src, AltLane &L, double z, const St &st)
 {
     const int max_inner = 200;
+    if (L.phase == 0) {
+        if (alt_pick(src, L, z, st)) return true;
+        if (L.phase == 0) return false;                                // chunk closed at its proposal cap
+    }
     const int o = L.nfull > 0 ? 0 : kAltSetupDoubles;
     const double h = st.get(o + kAltH);
     const double trunc = st.get(o + kAltTrunc);
     bool chunk_done = false;
     double chunk_val = 0.0;
-    if (L.phase == 0) {
-        if (L.trial >= 10000) {
-            chunk_done = true;
-            chunk_val = -1.0;                                          // :202
-        } else {
-            L.trial++;
-            if (src.unif() < st.get(o + kAltPr)) {
-                L.phase = 1;
-            } else {
-                L.phase = (h / z > trunc) ? 2 : 3;
-                L.alpha = 0.0;
-            }
-        }
-    }
     if (L.phase == 1) {
         double rate_z = 0.125 * kPi * kPi + 0.5 * z * z;
         if (h == 1.0) {

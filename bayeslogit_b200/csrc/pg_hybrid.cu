@@ -236,6 +236,233 @@ k_sp_loop(double *__restrict__ x, const double *__restrict__ h, const double *__
     run_persistent_lanes(count, t);
 }
 
+// Rejection loops with CTA-level regrouping by proposal piece.
+//
+// In the persistent-lane loops above a lane owns a draw, and every trip of a warp runs ALL the
+// proposal generators of its sampler (saddle point: inverse Gaussian on the left piece, truncated
+// gamma on the right; alternate: truncated gamma, inverse chi^2, inverse Gaussian) because its 32
+// lanes are a coin-flip mix of them: 14 of 32 lanes were active in the average instruction of the
+// saddle-point loop, 8 of 32 in the alternate one.  Here the draws live in SLOTS in shared memory
+// -- envelope state, position in the loop, Philox position -- and any thread can advance any
+// slot.  Every trip the CTA (i) refills empty slots (each warp from its own chunks of the list, as
+// before), (ii) sorts the live slots by the piece their pending proposal comes from (ballot ranks
+// + a small prefix over the warps; first piece from the front of `perm`, last piece from the back,
+// a third one behind the first), (iii) lets thread t advance slot perm[t] by one trip.  All warps
+// but those on a boundary then run a single generator.  The piece of a draw's NEXT proposal is
+// decided (one uniform) by whichever thread finishes the previous one, so it is always known when
+// the slots are sorted.  Variates are consumed per draw in the same order as everywhere else.
+constexpr int kRgThreads = 256;
+
+template <int F, int D, int I>
+struct RgSlots {
+    double f[F][kRgThreads];                   // envelope / chunk constants, [field][slot]
+    double d[D][kRgThreads];                   // per-draw doubles of the sampler's lane state
+    uint4 buf[kRgThreads];                     // Philox: current block
+    uint32_t blk[kRgThreads];                  //         next block counter
+    int pos[kRgThreads];                       //         next word of buf
+    int i[I][kRgThreads];                      // per-draw ints of the lane state
+    int obs[kRgThreads];
+    int phase[kRgThreads];                     // -1 empty, else the pending piece (1, 2[, 3])
+    int perm[kRgThreads];
+    int wcnt[kRgThreads / 32][3];
+};
+
+// Saddle point: pieces 1 (left) and 2 (right); d = {n, |z|/2, X}, i = {proposals made}
+struct SpRegroup {
+    static constexpr int F = kSpStateDoubles, D = 3, I = 1, kClasses = 2, kRegime = kRegSP;
+    using Slots = RgSlots<F, D, I>;
+    // new draw: first piece (PolyaGammaSP.cpp:229-231)
+    __device__ static void begin(Slots &S, int t, double shape, double zraw, PhiloxSource &src)
+    {
+        S.d[0][t] = shape;
+        S.d[1][t] = 0.5 * fabs(zraw);
+        S.d[2][t] = 2.0;
+        S.i[0][t] = 1;
+        S.phase[t] = src.unif() < S.f[kSpPl][t] ? 1 : 2;
+    }
+    // one trip of slot sl; returns true when the draw is complete and writes omega
+    __device__ static bool advance(Slots &S, int sl, PhiloxSource &src, double &omega)
+    {
+        SpLane L;
+        L.X = S.d[2][sl];
+        L.iter = S.i[0][sl];
+        L.phase = S.phase[sl];
+        const double n = S.d[0][sl];
+        SpStateRef st{&S.f[0][sl], (size_t)kRgThreads};
+        bool done = sp_trip_staged(src, L, n, S.d[1][sl], st);
+        if (!done && L.phase == 0) {                                    // rejected: piece of the next proposal
+            if (L.iter >= 200) {
+                done = true;
+            } else {
+                L.iter++;
+                L.phase = src.unif() < st.get(kSpPl) ? 1 : 2;
+            }
+        }
+        if (done) {
+            omega = n * 0.25 * L.X;
+        } else {
+            S.d[2][sl] = L.X;
+            S.i[0][sl] = L.iter;
+            S.phase[sl] = L.phase;
+        }
+        return done;
+    }
+};
+
+// Alternate: pieces 1 (truncated gamma), 2 (inverse chi^2), 3 (inverse Gaussian);
+// d = {|z|/2, X, alpha, sum}, i = {trial, nfull, nrem}
+struct AltRegroup {
+    static constexpr int F = kAltStateDoubles, D = 4, I = 3, kClasses = 3, kRegime = kRegAlt;
+    using Slots = RgSlots<F, D, I>;
+    __device__ static void load(const Slots &S, int sl, AltLane &L)
+    {
+        L.X = S.d[1][sl]; L.alpha = S.d[2][sl]; L.sum = S.d[3][sl];
+        L.trial = S.i[0][sl]; L.nfull = S.i[1][sl]; L.nrem = S.i[2][sl];
+        L.phase = S.phase[sl];
+    }
+    __device__ static void store(Slots &S, int sl, const AltLane &L)
+    {
+        S.d[1][sl] = L.X; S.d[2][sl] = L.alpha; S.d[3][sl] = L.sum;
+        S.i[0][sl] = L.trial; S.i[1][sl] = L.nfull; S.i[2][sl] = L.nrem;
+        S.phase[sl] = L.phase;
+    }
+    __device__ static void begin(Slots &S, int t, double shape, double zraw, PhiloxSource &src)
+    {
+        int nfull, nrem;
+        double hrem;
+        alt_plan(shape, nfull, nrem, hrem);
+        AltLane L;
+        L.start(nfull, nrem);
+        const double zh = 0.5 * fabs(zraw);
+        S.d[0][t] = zh;
+        AltStateRef st{&S.f[0][t], (size_t)kRgThreads};
+        alt_pick(src, L, zh, st);                                       // first proposal: cannot hit the cap
+        store(S, t, L);
+    }
+    __device__ static bool advance(Slots &S, int sl, PhiloxSource &src, double &omega)
+    {
+        AltLane L;
+        load(S, sl, L);
+        const double zh = S.d[0][sl];
+        AltStateRef st{&S.f[0][sl], (size_t)kRgThreads};
+        bool done = alt_trip(src, L, zh, st);
+        while (!done && L.phase == 0) done = alt_pick(src, L, zh, st);  // piece of the next proposal
+        if (done)
+            omega = L.sum;
+        else
+            store(S, sl, L);
+        return done;
+    }
+};
+
+template <class R>
+__global__ void __launch_bounds__(kRgThreads)
+k_loop_regroup(double *__restrict__ x, const double *__restrict__ h, const double *__restrict__ z,
+               const int *__restrict__ idx, const int *__restrict__ meta, const double *__restrict__ state,
+               int c0, int cap, StreamId id)
+{
+    using Slots = typename R::Slots;
+    extern __shared__ __align__(16) unsigned char rg_raw[];
+    Slots &S = *reinterpret_cast<Slots *>(rg_raw);
+    const int count = min(meta[kMetaCounts + R::kRegime] - c0, cap);
+    if (count <= 0) return;
+    const int *list = idx + meta[kMetaOffsets + R::kRegime] + c0;
+    const unsigned full = 0xffffffffu;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    constexpr int kWarps = kRgThreads / 32;
+    const int gwarp = blockIdx.x * kWarps + warp;
+    const int stride = gridDim.x * kWarps * kLaneChunk;
+    int cur = gwarp * kLaneChunk, cend = cur + kLaneChunk;
+
+    S.phase[t] = -1;
+    __syncthreads();
+    for (;;) {
+        // (i) refill this warp's empty home slots from its chunk
+        const bool empty = S.phase[t] < 0;
+        const unsigned want = __ballot_sync(full, empty);
+        if (want && cur < count) {
+            int rank = __popc(want & lt_mask);
+            int cand = cur + rank;
+            if (cand >= cend) cand += stride - kLaneChunk;
+            if (empty && cand < count) {
+                const int obs = list[cand];
+#pragma unroll
+                for (int k = 0; k < R::F; ++k) S.f[k][t] = __ldg(state + (size_t)k * cap + cand);
+                S.obs[t] = obs;
+                PhiloxSource src;
+                src.open(id.seed, id.obs0 + (uint64_t)obs, id.call_id);
+                R::begin(S, t, h[obs], z[obs], src);
+                S.buf[t] = src.buf;
+                S.blk[t] = src.blk;
+                S.pos[t] = src.pos;
+            }
+            cur += __popc(want);
+            if (cur >= cend) {
+                int over = cur - cend;
+                cend += stride;
+                cur = cend - kLaneChunk + over;
+            }
+        }
+        // (ii) sort live slots by piece
+        const int ph = S.phase[t];
+        const unsigned m1 = __ballot_sync(full, ph == 1), m2 = __ballot_sync(full, ph == 2);
+        const unsigned m3 = R::kClasses > 2 ? __ballot_sync(full, ph == 3) : 0u;
+        if (lane == 0) { S.wcnt[warp][0] = __popc(m1); S.wcnt[warp][1] = __popc(m2); S.wcnt[warp][2] = __popc(m3); }
+        __syncthreads();
+        int tot1 = 0, tot2 = 0, tot3 = 0, b1 = 0, b2 = 0, b3 = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            int a = S.wcnt[w][0], b = S.wcnt[w][1], c = S.wcnt[w][2];
+            if (w < warp) { b1 += a; b2 += b; b3 += c; }
+            tot1 += a;
+            tot2 += b;
+            tot3 += c;
+        }
+        if (tot1 + tot2 + tot3 == 0) {
+            if (!__syncthreads_or(cur < count)) break;                  // nothing live, nothing left anywhere
+            continue;
+        }
+        // piece 1 from the front, piece 3 right behind it, piece 2 from the back
+        if (ph == 1) S.perm[b1 + __popc(m1 & lt_mask)] = t;
+        else if (ph == 3) S.perm[tot1 + b3 + __popc(m3 & lt_mask)] = t;
+        else if (ph == 2) S.perm[kRgThreads - 1 - (b2 + __popc(m2 & lt_mask))] = t;
+        __syncthreads();
+        // (iii) thread t advances slot perm[t] by one trip
+        if (t < tot1 + tot3 || t >= kRgThreads - tot2) {
+            const int sl = S.perm[t];
+            PhiloxSource src;
+            src.open(id.seed, id.obs0 + (uint64_t)S.obs[sl], id.call_id);
+            src.buf = S.buf[sl];
+            src.blk = S.blk[sl];
+            src.pos = S.pos[sl];
+            double omega;
+            if (R::advance(S, sl, src, omega)) {
+                x[S.obs[sl]] = omega;
+                S.phase[sl] = -1;
+            } else {
+                S.buf[sl] = src.buf;
+                S.blk[sl] = src.blk;
+                S.pos[sl] = src.pos;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <class R>
+int regroup_grid()
+{
+    using Slots = typename R::Slots;
+    cudaFuncSetAttribute(k_loop_regroup<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Slots));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_loop_regroup<R>, kRgThreads, sizeof(Slots)) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * per_sm;
+}
+
 // Alternate regime, same two-kernel shape: the constants of the (at most) two chunk shapes of a
 // draw -> 20 doubles per draw in HBM -> persistent-lane loop over chunks and proposals.
 __global__ void __launch_bounds__(128)
@@ -462,6 +689,10 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
     static const int g_sp_loop = resident_grid(k_sp_loop, kLoopThreads, 1 << 30);
     static const int g_alt_setup = resident_grid(k_alt_setup, 128, 1 << 30);
     static const int g_alt_loop = resident_grid(k_alt_loop, kLoopThreads, 1 << 30);
+    static const bool regroup = getenv("BL_SP_LOOP_LANES") == nullptr;
+    static const int g_sp_regroup = regroup_grid<SpRegroup>();
+    static const int g_alt_regroup = regroup_grid<AltRegroup>();
+    const int rneed = (cap + kLaneChunk * (kRgThreads / 32) - 1) / (kLaneChunk * (kRgThreads / 32));
     const int sneed = (cap + 127) / 128;
     const int lneed = (cap + kLaneChunk * (kLoopThreads / 32) - 1) / (kLaneChunk * (kLoopThreads / 32));
     // One set-up/loop pair per state chunk.  The regime counts live on the device, so pairs are
@@ -473,7 +704,10 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
         }
         {
             HybTimer t(tm, st, kStSpLoop);
-            k_sp_loop<<<std::min(lneed, g_sp_loop), kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
+            if (regroup)
+                k_loop_regroup<SpRegroup><<<std::min(rneed, g_sp_regroup), kRgThreads, sizeof(SpRegroup::Slots), st>>>(x, h, z, idx, meta, state, c0, cap, id);
+            else
+                k_sp_loop<<<std::min(lneed, g_sp_loop), kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
         }
         count_launch(2);
     }
@@ -484,7 +718,10 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
         }
         {
             HybTimer t(tm, st, kStAltLoop);
-            k_alt_loop<<<std::min(lneed, g_alt_loop), kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
+            if (regroup)
+                k_loop_regroup<AltRegroup><<<std::min(rneed, g_alt_regroup), kRgThreads, sizeof(AltRegroup::Slots), st>>>(x, h, z, idx, meta, state, c0, cap, id);
+            else
+                k_alt_loop<<<std::min(lneed, g_alt_loop), kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
         }
         count_launch(2);
     }

@@ -404,7 +404,17 @@ __device__ __forceinline__ bool sp_trip_staged(PhiloxSource &src, SpLane &L, dou
     const int maxiter = 200;
     const double md = s.get(kSpMd);
     const double mu = s.get(kSpMu);
-    if (!(n > 1.0 && md > 0.0 && md >= mu)) return sp_trip(src, L, n, z, s);   // rare shapes
+    if (!(n > 1.0 && md > 0.0 && md >= mu)) {
+        // rare shapes: the generic trip, on COPIES of the stream and lane state -- its out-of-line
+        // helpers take the stream by reference, which would otherwise pin `src` in local memory
+        // for the whole kernel
+        PhiloxSource tsrc = src;
+        SpLane tl = L;
+        bool r = sp_trip(tsrc, tl, n, z, s);
+        src = tsrc;
+        L = tl;
+        return r;
+    }
     if (L.phase == 0) {
         if (L.iter >= maxiter) return true;
         L.iter++;

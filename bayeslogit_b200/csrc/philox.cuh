@@ -58,14 +58,13 @@ struct PhiloxSource {
         pos = 4;
     }
 
-    // Out of line on purpose: the ten Philox rounds are ~90 instructions and word() has
-    // many call sites; inlining them blows the samplers past the instruction cache.
-    __device__ __noinline__ void refill()
-    {
-        buf = Philox4x32::block(make_uint4(c0, c1, blk, c3), key);
-        ++blk;
-        pos = 0;
-    }
+    // The ten Philox rounds (~70 instructions) stay out of line -- word() has many call sites and
+    // the samplers live or die by their code footprint -- but as a PURE function of register
+    // arguments (philox_block_ool below): a member taking `this` out of line would pin the whole
+    // stream state in local memory, and with ~1000 resident threads those stack frames do not fit
+    // the L1 next to the kernels' shared memory (the saddle-point loop spent 60 % of its
+    // long-scoreboard stalls on local loads of pos / buf / the counter).
+    __device__ __forceinline__ void refill();
 
     __device__ __forceinline__ uint32_t word()
     {
@@ -111,11 +110,9 @@ struct PhiloxSource {
 
     __device__ __forceinline__ double unif() { return word_to_unif(word()); }
 
-    // Out of line like refill(): the big samplers (alternate, saddle point) have many call sites
-    // and live or die by their code footprint; the Devroye fast path uses the lazy forms above.
-    __device__ __noinline__ double expon() { return exact(expon_lazy()); }
-
-    __device__ __noinline__ double norm() { return exact(norm_lazy()); }
+    // the transcendental part of E and N out of line (pure functions of the pinned words)
+    __device__ __forceinline__ double expon();
+    __device__ __forceinline__ double norm();
 
     __device__ double gamma(double a)
     {
@@ -139,6 +136,36 @@ struct PhiloxSource {
     __device__ __forceinline__ bool exhausted() const { return false; }
     __device__ __forceinline__ void counts(int *t) const { t[0] = t[1] = t[2] = t[3] = 0; }
 };
+
+static __device__ __noinline__ uint4 philox_block_ool(uint32_t c0, uint32_t c1, uint32_t blk, uint32_t c3, uint2 key)
+{
+    return Philox4x32::block(make_uint4(c0, c1, blk, c3), key);
+}
+static __device__ __noinline__ double philox_expon_ool(uint32_t w, int k)
+{
+    return PhiloxSource::exact(PhiloxSource::LazyE{w, k});
+}
+static __device__ __noinline__ double philox_norm_ool(uint32_t w0, uint32_t w1, uint32_t w2)
+{
+    return PhiloxSource::exact(PhiloxSource::LazyN{w0, w1, w2});
+}
+
+__device__ __forceinline__ void PhiloxSource::refill()
+{
+    buf = philox_block_ool(c0, c1, blk, c3, key);
+    ++blk;
+    pos = 0;
+}
+__device__ __forceinline__ double PhiloxSource::expon()
+{
+    LazyE e = expon_lazy();
+    return philox_expon_ool(e.w, e.k);
+}
+__device__ __forceinline__ double PhiloxSource::norm()
+{
+    LazyN n = norm_lazy();
+    return philox_norm_ool(n.w0, n.w1, n.w2);
+}
 
 // Injected variate tape (tier-1 parity): one segment per observation and kind,
 // consumed in the reference's statement order.  A dry segment flags the draw as
