@@ -126,10 +126,10 @@ k_hyb_regime(double *__restrict__ x, const double *__restrict__ h, const double 
     }
 }
 
-// Saddle-point regime as two kernels (pg_sp.cuh): set-up -> 16-double state per draw in HBM
+// Saddle-point regime as two kernels (pg_sp.cuh): set-up -> 19-double state per draw in HBM
 // (struct of arrays over the chunk, coalesced) -> rejection loop.  Each kernel's working set of
-// code stays near the 32 KB instruction cache; the state costs 256 B of HBM traffic per draw,
-// ~2 % of HBM bandwidth at the rates these kernels reach.
+// code stays near the 32 KB instruction cache; the state costs 304 B of HBM traffic per draw,
+// ~3 % of HBM bandwidth at the rates these kernels reach.
 __global__ void __launch_bounds__(128, 8)
 k_sp_setup(const double *__restrict__ h, const double *__restrict__ z, const int *__restrict__ idx,
            const int *__restrict__ meta, double *__restrict__ state, int c0, int cap)
@@ -139,102 +139,13 @@ k_sp_setup(const double *__restrict__ h, const double *__restrict__ z, const int
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
         int i = list[j];
         SpState s;
-        sp_setup(h[i], z[i], s);
+        sp_setup<true>(h[i], z[i], s);      // pl as an fp32 estimate + band where one is offered
 #pragma unroll
         for (int k = 0; k < kSpStateDoubles; ++k) state[(size_t)k * cap + j] = s.f[k];
     }
 }
 
-// Rejection loops on persistent lanes: a lane makes one trip (sp_trip / alt_trip) per pass and,
-// when its draw is complete, takes the next list position of its warp's chunk through a
-// ballot-compacted refill, so rejected proposals and slow inner loops of one draw do not idle the
-// other 31 lanes.  Task: begin(pos) loads list position pos, trip() advances it and returns true
-// when the draw is complete (and stored).
-constexpr int kLoopThreads = 128;
 constexpr int kLaneChunk = 128;   // consecutive list positions a warp works through
-
-template <class Task>
-__device__ __forceinline__ void run_persistent_lanes(int count, Task &task)
-{
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const int warp = blockIdx.x * (kLoopThreads / 32) + (threadIdx.x >> 5);
-    const int stride = gridDim.x * (kLoopThreads / 32) * kLaneChunk;
-    int cur = warp * kLaneChunk;     // next unassigned list position of this warp (uniform)
-    int cend = cur + kLaneChunk;     // end of the current chunk (uniform)
-    bool active = false;
-    for (;;) {
-        unsigned want = __ballot_sync(full, !active);
-        if (want && cur < count) {
-            int rank = __popc(want & lt_mask);
-            int cand = cur + rank;
-            if (cand >= cend) cand += stride - kLaneChunk;
-            if (!active && cand < count) {
-                task.begin(cand);
-                active = true;
-            }
-            cur += __popc(want);
-            if (cur >= cend) {
-                int over = cur - cend;
-                cend += stride;
-                cur = cend - kLaneChunk + over;
-            }
-        }
-        if (!__any_sync(full, active)) {
-            if (cur >= count) break;
-            continue;
-        }
-        if (active && task.trip()) active = false;
-    }
-}
-
-struct SpTask {
-    double *x;
-    const double *h, *z, *state;
-    const int *list;
-    size_t cap;
-    StreamId id;
-    double *smem;      // this lane's column of the CTA's [field][lane] state copy
-    int obs;
-    double n, zh;
-    SpStateRef st;
-    SpLane L;
-    PhiloxSource src;
-    __device__ __forceinline__ void begin(int pos)
-    {
-        obs = list[pos];
-        n = h[obs];
-        zh = 0.5 * fabs(z[obs]);
-#pragma unroll
-        for (int k = 0; k < kSpStateDoubles; ++k) smem[k * kLoopThreads] = __ldg(state + (size_t)k * cap + pos);
-        L.start();
-        src.open(id.seed, id.obs0 + (uint64_t)obs, id.call_id);
-    }
-    __device__ __forceinline__ bool trip()
-    {
-        if (!sp_trip_staged(src, L, n, zh, st)) return false;
-        x[obs] = n * 0.25 * L.X;
-        return true;
-    }
-};
-
-__global__ void __launch_bounds__(kLoopThreads)
-k_sp_loop(double *__restrict__ x, const double *__restrict__ h, const double *__restrict__ z,
-          const int *__restrict__ idx, const int *__restrict__ meta, const double *__restrict__ state,
-          int c0, int cap, StreamId id)
-{
-    const int count = min(meta[kMetaCounts + kRegSP] - c0, cap);
-    if (count <= 0) return;
-    __shared__ double sh[kSpStateDoubles * kLoopThreads];
-    SpTask t;
-    t.x = x; t.h = h; t.z = z; t.state = state; t.cap = (size_t)cap; t.id = id;
-    t.smem = sh + threadIdx.x;
-    t.st.o = t.smem;
-    t.st.stride = kLoopThreads;
-    t.list = idx + meta[kMetaOffsets + kRegSP] + c0;
-    run_persistent_lanes(count, t);
-}
 
 // Rejection loops with CTA-level regrouping by proposal piece.
 //
@@ -278,7 +189,8 @@ struct SpRegroup {
         S.d[1][t] = 0.5 * fabs(zraw);
         S.d[2][t] = 2.0;
         S.i[0][t] = 1;
-        S.phase[t] = src.unif() < S.f[kSpPl][t] ? 1 : 2;
+        SpStateRef st{&S.f[0][t], (size_t)kRgThreads};
+        S.phase[t] = sp_pick_left(src.unif(), st, shape) ? 1 : 2;
     }
     // one trip of slot sl; returns true when the draw is complete and writes omega
     __device__ static bool advance(Slots &S, int sl, PhiloxSource &src, double &omega)
@@ -295,7 +207,7 @@ struct SpRegroup {
                 done = true;
             } else {
                 L.iter++;
-                L.phase = src.unif() < st.get(kSpPl) ? 1 : 2;
+                L.phase = sp_pick_left(src.unif(), st, n) ? 1 : 2;
             }
         }
         if (done) {
@@ -489,55 +401,6 @@ k_alt_setup(const double *__restrict__ h, const double *__restrict__ z, const in
     }
 }
 
-struct AltTask {
-    double *x;
-    const double *h, *z, *state;
-    const int *list;
-    size_t cap;
-    StreamId id;
-    double *smem;
-    int obs;
-    double zh;
-    AltStateRef st;
-    AltLane L;
-    PhiloxSource src;
-    __device__ __forceinline__ void begin(int pos)
-    {
-        obs = list[pos];
-        zh = 0.5 * fabs(z[obs]);
-        int nfull, nrem;
-        double hrem;
-        alt_plan(h[obs], nfull, nrem, hrem);
-#pragma unroll
-        for (int k = 0; k < kAltStateDoubles; ++k) smem[k * kLoopThreads] = __ldg(state + (size_t)k * cap + pos);
-        L.start(nfull, nrem);
-        src.open(id.seed, id.obs0 + (uint64_t)obs, id.call_id);
-    }
-    __device__ __forceinline__ bool trip()
-    {
-        if (!alt_trip(src, L, zh, st)) return false;
-        x[obs] = L.sum;
-        return true;
-    }
-};
-
-__global__ void __launch_bounds__(kLoopThreads)
-k_alt_loop(double *__restrict__ x, const double *__restrict__ h, const double *__restrict__ z,
-           const int *__restrict__ idx, const int *__restrict__ meta, const double *__restrict__ state,
-           int c0, int cap, StreamId id)
-{
-    const int count = min(meta[kMetaCounts + kRegAlt] - c0, cap);
-    if (count <= 0) return;
-    __shared__ double sh[kAltStateDoubles * kLoopThreads];
-    AltTask t;
-    t.x = x; t.h = h; t.z = z; t.state = state; t.cap = (size_t)cap; t.id = id;
-    t.smem = sh + threadIdx.x;
-    t.st.o = t.smem;
-    t.st.stride = kLoopThreads;
-    t.list = idx + meta[kMetaOffsets + kRegAlt] + c0;
-    run_persistent_lanes(count, t);
-}
-
 constexpr int kStateChunk = 1 << 23;   // draws per set-up/loop kernel pair (1.3 GB of state)
 constexpr int kStateDoubles = kSpStateDoubles > kAltStateDoubles ? kSpStateDoubles : kAltStateDoubles;
 
@@ -686,15 +549,11 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
     double *state = (double *)((char *)work + hybrid_state_offset(num));
     const int cap = num < kStateChunk ? num : kStateChunk;
     static const int g_sp_setup = resident_grid(k_sp_setup, 128, 1 << 30);
-    static const int g_sp_loop = resident_grid(k_sp_loop, kLoopThreads, 1 << 30);
     static const int g_alt_setup = resident_grid(k_alt_setup, 128, 1 << 30);
-    static const int g_alt_loop = resident_grid(k_alt_loop, kLoopThreads, 1 << 30);
-    static const bool regroup = getenv("BL_SP_LOOP_LANES") == nullptr;
     static const int g_sp_regroup = regroup_grid<SpRegroup>();
     static const int g_alt_regroup = regroup_grid<AltRegroup>();
     const int rneed = (cap + kLaneChunk * (kRgThreads / 32) - 1) / (kLaneChunk * (kRgThreads / 32));
     const int sneed = (cap + 127) / 128;
-    const int lneed = (cap + kLaneChunk * (kLoopThreads / 32) - 1) / (kLaneChunk * (kLoopThreads / 32));
     // One set-up/loop pair per state chunk.  The regime counts live on the device, so pairs are
     // issued for the largest possible count; those past the regime's count return at once.
     for (int c0 = 0; c0 < num; c0 += cap) {
@@ -704,10 +563,7 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
         }
         {
             HybTimer t(tm, st, kStSpLoop);
-            if (regroup)
-                k_loop_regroup<SpRegroup><<<std::min(rneed, g_sp_regroup), kRgThreads, sizeof(SpRegroup::Slots), st>>>(x, h, z, idx, meta, state, c0, cap, id);
-            else
-                k_sp_loop<<<std::min(lneed, g_sp_loop), kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
+            k_loop_regroup<SpRegroup><<<std::min(rneed, g_sp_regroup), kRgThreads, sizeof(SpRegroup::Slots), st>>>(x, h, z, idx, meta, state, c0, cap, id);
         }
         count_launch(2);
     }
@@ -718,10 +574,7 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
         }
         {
             HybTimer t(tm, st, kStAltLoop);
-            if (regroup)
-                k_loop_regroup<AltRegroup><<<std::min(rneed, g_alt_regroup), kRgThreads, sizeof(AltRegroup::Slots), st>>>(x, h, z, idx, meta, state, c0, cap, id);
-            else
-                k_alt_loop<<<std::min(lneed, g_alt_loop), kLoopThreads, 0, st>>>(x, h, z, idx, meta, state, c0, cap, id);
+            k_loop_regroup<AltRegroup><<<std::min(rneed, g_alt_regroup), kRgThreads, sizeof(AltRegroup::Slots), st>>>(x, h, z, idx, meta, state, c0, cap, id);
         }
         count_launch(2);
     }

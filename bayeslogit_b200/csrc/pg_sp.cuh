@@ -136,7 +136,7 @@ __device__ __forceinline__ double v_eval(double y)
 // every call from the same three arguments).
 enum SpField {
     kSpMd = 0,   // mid point 1.1 xl, PolyaGammaSP.cpp:183
-    kSpPl,       // mass of the left (inverse-Gaussian) piece, :226
+    kSpPl,       // mass of the left (inverse-Gaussian) piece, :226 (fp64, or an fp32 estimate: see kSpPlBand)
     kSpRt2rl,    // sqrt(2 rl), :216
     kSpRl, kSpIl,   // left tangent line: rate (-slope) and intercept, :209-214
     kSpRr, kSpIr,   // right tangent line
@@ -148,6 +148,7 @@ enum SpField {
     kSpLLtB,     // log b
     kSpMu,       // 1 / sqrt(2 rl), mean of the left piece's inverse Gaussian, :232
     kSpC1md,     // 1 - 1/md
+    kSpPlBand,   // 0: kSpPl is the fp64 mass; > 0: kSpPl is an estimate within this distance of it
     kSpStateDoubles
 };
 
@@ -202,7 +203,96 @@ static __device__ __noinline__ double sp_wr_ref(double hra, double lcn, double n
          * (1.0 - p_gamma_rate(md, n, n * rr));
 }
 
+// Mass of the left piece, pl = wl / (wl + wr) (PolyaGammaSP.cpp:217-226), fp64.  Written as in the
+// reference, wr = exp(.. - n log(n rr) - n log(md)) Gamma(n) (1 - P(n, x)) with x = md n rr.
+// For x >= n + 1, Gamma(n) Q(n, x) = e^-x x^n CF(n, x) and the three large terms cancel
+// exactly, leaving exp(hra + lcn + n ir - x) CF(n, x).  That form is used while Q stays above
+// ~4e-7, i.e. while the written form's 1 - P loses less than 3e-10 of Q to rounding
+// (Q >= exp(-n (r-1)^2 / (r+1)) / (sqrt(2 pi n) (r-1)), r = x / n).  Further out in the tail
+// the reference's 1 - P rounds to a few ulps or to 0 and pl becomes 1: that behaviour, and
+// shapes whose Gamma(n) overflows, keep the written form.
+__device__ __forceinline__ bool sp_cf_form_applies(double n, double ltb)
+{
+    double dx = ltb - n;
+    return dx >= 1.0 && n <= 171.0 && dx * dx <= 12.0 * (ltb + n);
+}
+
+__device__ __forceinline__ double sp_pl_fp64(double n, double md, double rt2rl, double il, double ir, double rr,
+                                             double hla, double hra, double lmd, double lcn, double ltb)
+{
+    double wl = ool::exp_(hla - n * rt2rl + n * il + 0.5 * n * 1. / md) * p_igauss_direct(md, 1. / rt2rl, n);
+    double wr;
+    if (sp_cf_form_applies(n, ltb))
+        wr = ool::exp_(hra + lcn + n * ir - ltb) * upper_gamma_cf(n, ltb);
+    else
+        wr = sp_wr_ref(hra, lcn, n, rr, ir, lmd, md);
+    return wl / (wl + wr);
+}
+
+// fp32 estimate of pl for the binned path's set-up kernel, where the fp64 weights were 40 % of
+// the instructions and the FP64 pipe the limiter.  pl only ever meets a uniform, so the loop
+// kernel compares against pl_est -+ kSpPlBand and evaluates sp_pl_fp64 (from the state) only inside
+// the band.  wr / wl = exp(D) CF / PIG with D = log-ratio of the two exponential prefactors
+// (fp64, a dozen FMAs: |D| < 60 or no estimate), CF by modified Lentz in fp32 (<= 64 terms,
+// relative error < 1e-5 incl. the float arguments), PIG = Phi(b) + e^(-b^2/2) erfcx(t) / 2 from
+// erfcf / erfcxf (4 ulp) with b = s (md Z - 1) formed in fp64 before the cast.  Measured against
+// sp_pl_fp64 over the shapes the regime sees: |pl_est - pl| < 2e-6 (test_saddle_point_pl_estimate);
+// the band is 2e-5.  Returns a negative value when no estimate is offered.
+constexpr double kSpPlBandWidth = 2e-5;
+
+__device__ __forceinline__ float sp_pl_estimate(double n, double md, double rt2rl, double il, double ir,
+                                                double lmd, double lcn, double ltb)
+{
+    if (!sp_cf_form_applies(n, ltb)) return -1.0f;
+    const double D = -0.5 * lmd + lcn + n * (ir - il) - ltb + n * rt2rl - 0.5 * n / md;
+    if (!(fabs(D) < 60.0)) return -1.0f;
+    const float s = sqrtf((float)(n / md));
+    const float b = s * (float)(md * rt2rl - 1.0);
+    const float t = s * (float)(md * rt2rl + 1.0) * 0.70710678f;
+    const float pig = 0.5f * erfcf(-b * 0.70710678f) + 0.5f * erfcxf(t) * __expf(-0.5f * b * b);
+    // Gamma(a, x) e^x x^-a, modified Lentz
+    const float a = (float)n, x = (float)ltb;
+    float bb = x + 1.0f - a;
+    float c = 1e30f, d = 1.0f / bb, hcf = d;
+    bool conv = false;
+    for (int i = 1; i <= 64; ++i) {
+        float an = -(float)i * ((float)i - a);
+        bb += 2.0f;
+        d = an * d + bb;
+        d = fabsf(d) < 1e-30f ? 1e-30f : d;
+        c = bb + an / c;
+        c = fabsf(c) < 1e-30f ? 1e-30f : c;
+        d = 1.0f / d;
+        float del = d * c;
+        hcf *= del;
+        if (fabsf(del - 1.0f) < 3e-7f) { conv = true; break; }
+    }
+    if (!conv || !(pig > 0.0f)) return -1.0f;
+    const float R = __expf((float)D) * hcf / pig;
+    if (!(R >= 0.0f) || isinf(R)) return -1.0f;
+    return 1.0f / (1.0f + R);
+}
+
+// U < pl ?  (PolyaGammaSP.cpp:231) against the state's pl, exact or estimated
+template <class St>
+static __device__ __noinline__ double sp_pl_from_state(const St &s, double n)
+{
+    double lcn = s.get(kSpLcn);
+    return sp_pl_fp64(n, s.get(kSpMd), s.get(kSpRt2rl), s.get(kSpIl), s.get(kSpIr), s.get(kSpRr),
+                      s.get(kSpCl) - lcn, s.get(kSpCr) - lcn, s.get(kSpLmd), lcn, s.get(kSpLtB));
+}
+
+template <class St>
+__device__ __forceinline__ bool sp_pick_left(double u, const St &s, double n)
+{
+    const double pl = s.get(kSpPl), band = s.get(kSpPlBand);
+    if (u < pl - band) return true;
+    if (u > pl + band || band == 0.0) return false;
+    return u < sp_pl_from_state(s, n);
+}
+
 // n: shape, zraw: tilting parameter as passed to the sampler (the halving is done here)
+template <bool kEstimatePl = false>
 __device__ __forceinline__ void sp_setup(double n, double zraw, SpState &s)
 {
     double z = 0.5 * fabs(zraw);
@@ -230,30 +320,24 @@ __device__ __forceinline__ void sp_setup(double n, double zraw, SpState &s)
     double lmd = ool::log_(md);
     double hla = 0.5 * ool::log_(al), hra = hla - 0.5 * lmd;
     (void)ar;
-    // Proposal weights (:217-226).  They only enter the decision U < pl.  Written as in the
-    // reference, wr = exp(.. - n log(n rr) - n log(md)) Gamma(n) (1 - P(n, x)) with x = md n rr.
-    // For x >= n + 1, Gamma(n) Q(n, x) = e^-x x^n CF(n, x) and the three large terms cancel
-    // exactly, leaving exp(hra + lcn + n ir - x) CF(n, x).  That form is used while Q stays above
-    // ~4e-7, i.e. while the written form's 1 - P loses less than 3e-10 of Q to rounding
-    // (Q >= exp(-n (r-1)^2 / (r+1)) / (sqrt(2 pi n) (r-1)), r = x / n).  Further out in the tail
-    // the reference's 1 - P rounds to a few ulps or to 0 and pl becomes 1: that behaviour, and
-    // shapes whose Gamma(n) overflows, keep the written form.
+    // Proposal weights (:217-226): they only enter the decision U < pl (sp_pl_fp64 / sp_pl_estimate)
     double ltb = (n * rr) * md;
-    double wl = ool::exp_(hla - n * rt2rl + n * il + 0.5 * n * 1. / md) * p_igauss_direct(md, 1. / rt2rl, n);
-    double wr;
-    double dx = ltb - n;
-    if (dx >= 1.0 && n <= 171.0 && dx * dx <= 12.0 * (ltb + n))
-        wr = ool::exp_(hra + lcn + n * ir - ltb) * upper_gamma_cf(n, ltb);
-    else
-        wr = sp_wr_ref(hra, lcn, n, rr, ir, lmd, md);
-    double wt = wl + wr;
+    double pl, pl_band = 0.0;
+    float est = kEstimatePl ? sp_pl_estimate(n, md, rt2rl, il, ir, lmd, lcn, ltb) : -1.0f;
+    if (est >= 0.0f) {
+        pl = (double)est;
+        pl_band = kSpPlBandWidth;
+    } else {
+        pl = sp_pl_fp64(n, md, rt2rl, il, ir, rr, hla, hra, lmd, lcn, ltb);
+    }
     // left-truncated gamma constants, Ch.R:96-101 with shape n, rate n rr, truncation md
     double d1 = ltb - n;
     double d3 = n - 1.0;
     double c0 = 0.5 * (d1 + sqrt(d1 * d1 + 4.0 * ltb)) / ltb;
     double l_M = d3 * ool::log_(d3 / (1.0 - c0)) - d3;
     s.f[kSpMd] = md;
-    s.f[kSpPl] = wl / wt;
+    s.f[kSpPl] = pl;
+    s.f[kSpPlBand] = pl_band;
     s.f[kSpRt2rl] = rt2rl;
     s.f[kSpRl] = rl;
     s.f[kSpIl] = il;
@@ -313,7 +397,7 @@ __device__ __forceinline__ bool sp_trip(Src &src, SpLane &L, double n, double z,
     if (L.phase == 0) {
         if (L.iter >= maxiter) return true;   // only when maxiter proposals were all rejected
         L.iter++;
-        L.phase = src.unif() < s.get(kSpPl) ? 1 : 2;
+        L.phase = sp_pick_left(src.unif(), s, n) ? 1 : 2;
     }
     if (L.phase == 1) {
         double mu = 1. / s.get(kSpRt2rl);
@@ -418,7 +502,7 @@ __device__ __forceinline__ bool sp_trip_staged(PhiloxSource &src, SpLane &L, dou
     if (L.phase == 0) {
         if (L.iter >= maxiter) return true;
         L.iter++;
-        L.phase = src.unif() < s.get(kSpPl) ? 1 : 2;
+        L.phase = sp_pick_left(src.unif(), s, n) ? 1 : 2;
     }
     const bool left = L.phase == 1;
     PhiloxSource::LazyN ln = {0u, 0u, 0u};

@@ -147,6 +147,25 @@ def test_saddle_point_weight_functions(engine):
                                engine.specfun("p_igauss", xi, mu, lam), rtol=2e-12, atol=1e-300)
 
 
+def test_saddle_point_pl_estimate(engine):
+    """The binned path decides U < pl against an fp32 estimate of pl with a band of 2e-5 and asks
+    the fp64 weights only inside the band: the estimate has to sit well inside that band wherever
+    one is offered, over the shapes and tilts the regime sees (and beyond)."""
+    rng = np.random.default_rng(11)
+    n = np.concatenate([rng.uniform(13, 170, 60000), rng.integers(14, 171, 20000).astype(float),
+                        rng.uniform(1.5, 13, 5000), rng.uniform(170, 400, 2000)])
+    z = np.concatenate([rng.uniform(-5, 5, 70000), rng.uniform(-30, 30, 17000)])
+    pl = engine.specfun("sp_pl", n, z)
+    est = engine.specfun("sp_pl_estimate", n, z)
+    have = ~np.isnan(est)
+    core = (n > 13) & (n <= 170) & (np.abs(z) <= 5)
+    assert have[core].mean() > 0.999            # the benchmark regime runs on the estimate
+    ok = n <= 170       # beyond, the reference's Gamma(n) overflows and its pl is 0 or NaN (reproduced as is)
+    assert np.all(np.isfinite(pl[ok])) and np.all((pl[ok] >= 0) & (pl[ok] <= 1))
+    assert not have[n > 171].any()
+    assert np.max(np.abs(est[have] - pl[have])) < 5e-6
+
+
 # ----------------------------------------------------------------------------------
 # tier 1: golden vectors made from the reference itself
 # ----------------------------------------------------------------------------------
