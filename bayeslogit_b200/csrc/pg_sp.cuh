@@ -308,7 +308,17 @@ __device__ __forceinline__ void sp_setup(double n, double zraw, SpState &s)
     double m2 = md * md;
     double al = m2 * md / K2md;
     double ar = m2 / K2md;
-    double lcz = ool::log_(ool::cosh_(z));
+    // log cosh z enters both tangent intercepts and the density with the same coefficient n, i.e.
+    // F and spa -- and wl and wr -- as one common factor: every decision is invariant to its
+    // value.  The binned path therefore takes it in fp32 (its error scales F and spa alike by
+    // e^(n 1e-7)); the per-lane / tape path keeps the fp64 value the reference computes.
+    double lcz;
+    if (kEstimatePl) {
+        float zf = (float)z;
+        lcz = zf < 12.0f ? (double)__logf(coshf(zf)) : (double)(zf - 0.69314718f);
+    } else {
+        lcz = ool::log_(ool::cosh_(z));
+    }
     double sl, il, sr, ir;
     sp_tangent(xl, z, md, lcz, false, sl, il);
     sp_tangent(xr, z, md, lcz, true, sr, ir);
