@@ -12,7 +12,13 @@
 //   3. k_hyb_scatter  counting sort of observation indices by regime into one
 //                     int32 list (block-level ballot ranking, ascending within a
 //                     block so gathers stay nearly coalesced); b <= 0 -> x = 0
-//   4. one kernel per regime over its index list: every warp runs ONE sampler.
+//   4. kernels per regime over its index list, so that every warp runs ONE sampler:
+//        saddle point (13 < b <= 170) and alternate (1 < b <= 13, b != 2): a set-up kernel
+//          (envelope / chunk constants -> struct-of-arrays state in HBM) followed by a rejection-loop
+//          kernel that regroups draws by proposal piece across the CTA (k_loop_regroup), once per
+//          state chunk of 2^23 draws;
+//        sum of gammas (b < 1), normal approximation (b > 170), Devroye (b = 1, 2): one grid-stride
+//          kernel each, on a low-priority side stream underneath the two heavy regimes.
 //
 // Results are unchanged by the re-ordering: each observation draws from the Philox
 // stream keyed by its own global index (philox.cuh).
