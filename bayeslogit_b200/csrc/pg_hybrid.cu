@@ -67,37 +67,57 @@ __global__ void k_hyb_offsets(int *meta)
     }
 }
 
+// Four observations per thread and tile (i = tile * 1024 + k * 256 + thread): one round of
+// barriers and one cursor atomic per regime for 1024 observations.
+constexpr int kBinPer = 4;
+
 __global__ void __launch_bounds__(kBinThreads)
 k_hyb_scatter(const double *__restrict__ h, int n, int *__restrict__ meta, int *__restrict__ idx,
               double *__restrict__ x)
 {
-    __shared__ int wcnt[kBinThreads / 32][8];
+    constexpr int kCells = kBinPer * (kBinThreads / 32);          // (k, warp) cells of a tile, ascending i
+    __shared__ int wcnt[kCells][8];                                // counts, then exclusive prefixes
     __shared__ int base[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    int tiles = (n + kBinThreads - 1) / kBinThreads;
+    const int tile_obs = kBinThreads * kBinPer;
+    int tiles = (n + tile_obs - 1) / tile_obs;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        int i = tile * kBinThreads + threadIdx.x;
-        int reg = i < n ? regime_of(h[i]) : -1;
-        if (reg == kRegZero) x[i] = 0.0;                      // LogitWrapper.cpp:159-161
-        int rank = 0;
+        int reg[kBinPer], rank[kBinPer];
 #pragma unroll
-        for (int r = 1; r < 6; ++r) {
-            unsigned m = __ballot_sync(0xffffffffu, reg == r);
-            if (reg == r) rank = __popc(m & lt);
-            if (lane == 0) wcnt[warp][r] = __popc(m);
+        for (int k = 0; k < kBinPer; ++k) {
+            int i = tile * tile_obs + k * kBinThreads + threadIdx.x;
+            reg[k] = i < n ? regime_of(h[i]) : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < kBinPer; ++k) {
+            int i = tile * tile_obs + k * kBinThreads + threadIdx.x;
+            if (reg[k] == kRegZero) x[i] = 0.0;                   // LogitWrapper.cpp:159-161
+            rank[k] = 0;
+#pragma unroll
+            for (int r = 1; r < 6; ++r) {
+                unsigned m = __ballot_sync(0xffffffffu, reg[k] == r);
+                if (reg[k] == r) rank[k] = __popc(m & lt);
+                if (lane == 0) wcnt[k * (kBinThreads / 32) + warp][r] = __popc(m);
+            }
         }
         __syncthreads();
         if (threadIdx.x >= 1 && threadIdx.x < 6) {
-            int r = threadIdx.x, tot = 0;
-            for (int w = 0; w < kBinThreads / 32; ++w) tot += wcnt[w][r];
-            base[r] = tot ? meta[kMetaOffsets + r] + atomicAdd(&meta[kMetaCursor + r], tot) : 0;
+            int r = threadIdx.x, run = 0;
+            for (int c = 0; c < kCells; ++c) {
+                int v = wcnt[c][r];
+                wcnt[c][r] = run;
+                run += v;
+            }
+            base[r] = run ? meta[kMetaOffsets + r] + atomicAdd(&meta[kMetaCursor + r], run) : 0;
         }
         __syncthreads();
-        if (reg > 0) {
-            int off = base[reg];
-            for (int w = 0; w < warp; ++w) off += wcnt[w][reg];
-            idx[off + rank] = i;
+#pragma unroll
+        for (int k = 0; k < kBinPer; ++k) {
+            if (reg[k] > 0) {
+                int i = tile * tile_obs + k * kBinThreads + threadIdx.x;
+                idx[base[reg[k]] + wcnt[k * (kBinThreads / 32) + warp][reg[k]] + rank[k]] = i;
+            }
         }
         __syncthreads();
     }
@@ -522,13 +542,15 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
     if (e != cudaSuccess) return e;
     int tiles = (num + kBinThreads - 1) / kBinThreads;
     int grid = tiles < 148 * 8 ? tiles : 148 * 8;
+    int stiles = (num + kBinThreads * kBinPer - 1) / (kBinThreads * kBinPer);
+    int sgrid = stiles < 148 * 8 ? stiles : 148 * 8;
     const bool tm = g_hyb_timing;
     if (tm) { g_hyb_spans.clear(); g_hyb_used = 0; }
     {
         HybTimer t(tm, st, kStBin);
         k_hyb_count<<<grid, kBinThreads, 0, st>>>(h, num, meta);
         k_hyb_offsets<<<1, 1, 0, st>>>(meta);
-        k_hyb_scatter<<<grid, kBinThreads, 0, st>>>(h, num, meta, idx, x);
+        k_hyb_scatter<<<sgrid, kBinThreads, 0, st>>>(h, num, meta, idx, x);
         count_launch(3);
     }
     // The three light regimes (0.15 % + 15 % + 0.5 % of this workload's draws; the sum of gammas

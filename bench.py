@@ -380,14 +380,14 @@ def main():
             # a step launches it once per state chunk: figures are per launch, averaged over the
             # non-empty launches of the timed pass
             dom_stage = "sp_setup" if stage_ms["sp_setup"] >= stage_ms["sp_loop"] else "sp_loop"
-            dom_name = "k_" + dom_stage
+            dom_name = {"sp_setup": "k_sp_setup", "sp_loop": "k_loop_regroup<SpRegroup>"}[dom_stage]
             n_launch = max(1, stage_launches[dom_stage])
             dom_units, dom_ms = regime_counts["saddle_point"] / n_launch, stage_ms[dom_stage] / n_launch
             dom_share = stage_ms[dom_stage] / (total_ms / args.steps)
             dom_kflop = 9.0
             # HBM bytes the design moves per saddle-point draw in this kernel:
-            # set-up: idx 4 + h 8 + z 8 in, 18 state doubles out; loop: idx 4 + h 8 + z 8 + state in, x 8 out
-            design_bytes = {"sp_setup": 20 + 144, "sp_loop": 20 + 144 + 8}[dom_stage]
+            # set-up: idx 4 + h 8 + z 8 in, 19 state doubles out; loop: idx 4 + h 8 + z 8 + state in, x 8 out
+            design_bytes = {"sp_setup": 20 + 152, "sp_loop": 20 + 152 + 8}[dom_stage]
         else:
             dom_units, dom_ms, dom_name, dom_kflop = num, kern_ms, "k_devroye_refill", KFLOP_PER_DRAW[wl]
             dom_share, n_launch, design_bytes = 1.0, 1, BYTES_PER_DRAW[wl]

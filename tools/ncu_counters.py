@@ -2,10 +2,10 @@
 """Extract the per-kernel counters bench.py quotes (profiles/ncu_counters.json) from an
 `ncu --set full` report of `bench.py` at its default size.
 
-    python tools/ncu_counters.py gpurun_out/x.ncu-rep kernel=units [kernel=units ...] > profiles/ncu_counters.json
+    python tools/ncu_counters.py gpurun_out/x.ncu-rep key:match=units [key:match=units ...] > profiles/ncu_counters.json
 
-units = work items (draws) the captured launch of that kernel processed; the first launch whose
-name contains `kernel` is used.  DRAM bytes are reported per unit so that bench.py can scale
+units = work items (draws) the captured launch processed; the first launch whose name contains
+`match` is used and reported under `key` (key alone: match = key).  DRAM bytes are reported per unit so that bench.py can scale
 them to the launch it timed.
 """
 import csv
@@ -15,7 +15,11 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-want = dict(a.split("=") for a in sys.argv[2:])
+want = {}
+for a in sys.argv[2:]:
+    km, units = a.split("=")
+    key, _, match = km.partition(":")
+    want[key] = (match or key, units)
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[0]
@@ -37,8 +41,8 @@ def num(d, k):
 
 for r in rows[2:]:
     d = dict(zip(hdr, r))
-    for k, units in want.items():
-        if k in d["Kernel Name"] and k not in res:
+    for k, (match, units) in want.items():
+        if match in d["Kernel Name"] and k not in res:
             units = float(units)
             rd, wr = num(d, "dram__bytes_read.sum"), num(d, "dram__bytes_write.sum")
             res[k] = {
