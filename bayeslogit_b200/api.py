@@ -193,7 +193,8 @@ def v_eval(y):
 
 SPECFUN = {"p_norm": 0, "log_p_norm": 1, "p_gamma_rate": 2, "p_igauss": 3, "lgamma": 4, "tgamma": 5,
            "dev_right_mass": 6, "dev_coef": 7, "upper_gamma_cf": 8, "p_igauss_direct": 9, "sp_log_cos_rt": 10,
-           "sp_v_table": 11, "sp_pl": 12, "sp_pl_estimate": 13}
+           "sp_v_table": 11, "sp_pl": 12, "sp_pl_estimate": 13,
+           "alt_pr": 14, "alt_pr_estimate": 15}
 
 
 def specfun(which, a, b=None, c=None):

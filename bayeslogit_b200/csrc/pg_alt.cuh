@@ -54,6 +54,7 @@ enum AltField {
     kAltLgh,       // lgamma(h'), for g~ right of t (:101)
     kAltLd0, kAltLd1,            // log(h'), log(h' + 2): log d_n of the first two coefficients (:45)
     kAltLtB, kAltLtC0, kAltLtLM, // ltgamma(h', rate_z, t): b = rate * trunc, c0, log M (Ch.R:96-101)
+    kAltPrBand,    // 0: kAltPr is the fp64 mass; > 0: an fp32 estimate within this distance of it
     kAltSetupDoubles
 };
 constexpr int kAltStateDoubles = 2 * kAltSetupDoubles;   // [0]: shape 4, [1]: remainder shape
@@ -85,25 +86,81 @@ __device__ __forceinline__ void alt_plan(double h, int &nfull, int &nrem, double
     }
 }
 
+// Mass of the right (gamma) piece of a chunk of shape h at tilt z = |z|/2, fp64, as
+// PolyaGammaAlt.cpp:124-137 computes it (w_left :60-68 with the naive pigauss, w_right :70-75).
+static __device__ __noinline__ double alt_pr_fp64(double h, double z, double trunc)
+{
+    const double kLog2 = 0.693147180559945309417232;
+    double wl, wr;
+    if (z != 0)
+        wl = ool::exp_(h * (kLog2 - z)) * alt_pigauss(trunc, z / h, h * h);
+    else
+        wl = ool::exp_(h * kLog2) * (1.0 - p_gamma_rate(1 / trunc, 0.5, 0.5 * h * h));
+    double lambda_z = kPi * kPi * 0.125 + 0.5 * z * z;
+    wr = ool::exp_(h * ool::log_((0.5 * kPi) / lambda_z)) * (1.0 - p_gamma_rate(trunc, h, lambda_z));
+    return wr / (wr + wl);
+}
+
+// fp32 estimate of the same mass for the binned path's set-up kernel: it only ever meets a
+// uniform, so the loop compares against estimate -+ kAltPrBand and evaluates alt_pr_fp64 only
+// inside the band (same scheme as the saddle-point sampler's pl).
+//   wl = 2^h [e^(-hz) Phi(b) + e^(hz) Phi(a)], b = s (t z / h - 1), a = -s (t z / h + 1), s = h / sqrt(t)
+//        with the second term as erfcx(-a / sqrt 2) e^(hz - a^2/2) / 2 (no overflow);
+//   wr = (pi/2 / lambda)^h Q(h, t lambda), Q by the power series of P or the continued fraction.
+// No estimate (negative) when z is large; measured
+// |estimate - mass| < 2e-6 elsewhere (test_alternate_pr_estimate), band 2e-5.
+constexpr double kAltPrBandWidth = 2e-5;
+
+__device__ __forceinline__ float alt_pr_estimate(double h, double z, double trunc)
+{
+    const float hf = (float)h, zf = (float)z, tf = (float)trunc;
+    if (!(zf < 12.0f)) return -1.0f;
+    const float s = hf * rsqrtf(tf);
+    const float tz = tf * zf / hf;
+    const float b = s * (tz - 1.0f), na = s * (tz + 1.0f);             // na = -a > 0
+    const float phib = 0.5f * erfcf(-b * 0.70710678f);
+    const float wl = exp2f(hf) * (__expf(-hf * zf) * phib
+                                  + 0.5f * erfcxf(na * 0.70710678f) * __expf(hf * zf - 0.5f * na * na));
+    const float lam = 1.2337005501361697f + 0.5f * zf * zf;
+    const float x = tf * lam;
+    // Q(h, x) = 1 - P(h, x): left of the mode region by the power series of P,
+    //           P = x^h e^-x / Gamma(h + 1) * sum_k x^k / ((h+1)..(h+k)); right of it by the continued
+    //           fraction of Gamma(h, x) directly (1 - P would cancel)
+    const float lpre = hf * __logf(x) - x;
+    float Q;
+    if (x < hf + 1.0f) {
+        float term = 1.0f, sum = 1.0f, ap = hf;
+        for (int k = 0; k < 60; ++k) {
+            ap += 1.0f;
+            term *= x / ap;
+            sum += term;
+            if (term < 1e-8f * sum) break;
+        }
+        Q = 1.0f - sum * __expf(lpre - lgammaf(hf + 1.0f));
+    } else {
+        float cf = upper_gamma_cf_f32(hf, x);
+        if (!(cf > 0.0f)) return -1.0f;
+        Q = cf * __expf(lpre - lgammaf(hf));
+    }
+    if (!(Q > 0.0f)) return -1.0f;
+    const float wr = __expf(hf * __logf(1.5707963267948966f / lam)) * Q;
+    const float pr = wr / (wr + wl);
+    return pr >= 0.0f && pr <= 1.0f ? pr : -1.0f;
+}
+
 // z is |z|/2; writes kAltSetupDoubles values
+template <bool kEstimatePr>
 static __device__ __noinline__ void alt_setup(double h, double z, double *out)
 {
     const double kLog2 = 0.693147180559945309417232;
     int idx = (int)floor((h - 1.0) * 100.0);
     double trunc = PG_TRUNC_SCHEDULE[idx];
     double rate_z = 0.125 * kPi * kPi + 0.5 * z * z;
-    double wl, wr;
-    if (z != 0)
-        wl = ool::exp_(h * (kLog2 - z)) * alt_pigauss(trunc, z / h, h * h);
-    else
-        wl = ool::exp_(h * kLog2) * (1.0 - p_gamma_rate(1 / trunc, 0.5, 0.5 * h * h));
-    {
-        double lambda_z = kPi * kPi * 0.125 + 0.5 * z * z;
-        wr = ool::exp_(h * ool::log_((0.5 * kPi) / lambda_z)) * (1.0 - p_gamma_rate(trunc, h, lambda_z));
-    }
+    float est = kEstimatePr ? alt_pr_estimate(h, z, trunc) : -1.0f;
     out[kAltH] = h;
     out[kAltTrunc] = trunc;
-    out[kAltPr] = wr / (wr + wl);
+    out[kAltPr] = est >= 0.0f ? (double)est : alt_pr_fp64(h, z, trunc);
+    out[kAltPrBand] = est >= 0.0f ? kAltPrBandWidth : 0.0;
     out[kAltCoef] = ool::exp_(h * kLog2 - 0.5 * 1.8378770664093454835606594728112 /* log(2 pi) */);
     out[kAltLgh] = ool::lgamma_(h);
     out[kAltLd0] = ool::log_(h);
@@ -115,6 +172,16 @@ static __device__ __noinline__ void alt_setup(double h, double z, double *out)
     out[kAltLtB] = b;
     out[kAltLtC0] = c0;
     out[kAltLtLM] = d3 * ool::log_(d3 / (1.0 - c0)) - d3;   // unused when h' == 1
+}
+
+// U < mass of the right piece ?  (PolyaGammaAlt.cpp:143) against the state's mass, exact or estimated
+template <class St>
+__device__ __forceinline__ bool alt_pick_right(double u, const St &st, int o, double z)
+{
+    const double pr = st.get(o + kAltPr), band = st.get(o + kAltPrBand);
+    if (u < pr - band) return true;
+    if (u > pr + band || band == 0.0) return false;
+    return u < alt_pr_fp64(st.get(o + kAltH), z, st.get(o + kAltTrunc));
 }
 
 struct AltLane {
@@ -160,7 +227,7 @@ __device__ __forceinline__ bool alt_pick(Src &src, AltLane &L, double z, const S
         return L.nfull == 0 && L.nrem == 0;
     }
     L.trial++;
-    if (src.unif() < st.get(o + kAltPr)) {
+    if (alt_pick_right(src.unif(), st, o, z)) {
         L.phase = 1;
     } else {
         L.phase = (st.get(o + kAltH) / z > st.get(o + kAltTrunc)) ? 2 : 3;
@@ -275,8 +342,8 @@ __device__ double alt_draw(Src &s, double h, double z)
     alt_plan(h, nfull, nrem, hrem);
     double zh = fabs(z) * 0.5;
     AltState st;
-    if (nfull > 0) alt_setup(4.0, zh, st.f);
-    alt_setup(hrem, zh, st.f + kAltSetupDoubles);
+    if (nfull > 0) alt_setup<false>(4.0, zh, st.f);
+    alt_setup<false>(hrem, zh, st.f + kAltSetupDoubles);
     AltLane L;
     L.start(nfull, nrem);
     while (!alt_trip(s, L, zh, st)) {}

@@ -402,7 +402,7 @@ int regroup_grid()
 }
 
 // Alternate regime, same two-kernel shape: the constants of the (at most) two chunk shapes of a
-// draw -> 20 doubles per draw in HBM -> persistent-lane loop over chunks and proposals.
+// draw -> 22 doubles per draw in HBM -> persistent-lane loop over chunks and proposals.
 __global__ void __launch_bounds__(128)
 k_alt_setup(const double *__restrict__ h, const double *__restrict__ z, const int *__restrict__ idx,
             const int *__restrict__ meta, double *__restrict__ state, int c0, int cap)
@@ -416,11 +416,11 @@ k_alt_setup(const double *__restrict__ h, const double *__restrict__ z, const in
         alt_plan(h[i], nfull, nrem, hrem);
         double f[kAltSetupDoubles];
         // remainder shape first: every draw has one; the shape-4 constants only if it has a full chunk
-        alt_setup(hrem, zh, f);
+        alt_setup<true>(hrem, zh, f);
 #pragma unroll
         for (int k = 0; k < kAltSetupDoubles; ++k) state[(size_t)(kAltSetupDoubles + k) * cap + j] = f[k];
         if (nfull > 0) {
-            alt_setup(4.0, zh, f);
+            alt_setup<true>(4.0, zh, f);
 #pragma unroll
             for (int k = 0; k < kAltSetupDoubles; ++k) state[(size_t)k * cap + j] = f[k];
         }

@@ -110,7 +110,8 @@ __global__ void k_probe_v_eval(double *v, const double *y, int64_t num)
 //        9 p_igauss_direct(a, mu=b, lambda=c), 10 log cos_rt(v(a)) as the saddle-point sampler
 //        takes it (table or reference iteration), 11 v(a) from the table path alone (NaN where
 //        the table path hands over to the reference iteration), 12 / 13 mass of the saddle-point
-//        sampler's left piece for shape a, tilt b: fp64, and the fp32 estimate (NaN: none offered)
+//        sampler's left piece for shape a, tilt b: fp64, and the fp32 estimate (NaN: none offered),
+//        14 / 15 mass of the alternate sampler's right piece for chunk shape a in [1,4], tilt b: same pair
 __global__ void k_probe_specfun(double *out, int which, const double *a, const double *b,
                                 const double *c, int64_t num)
 {
@@ -132,6 +133,8 @@ __global__ void k_probe_specfun(double *out, int which, const double *a, const d
     case 11: { double v, g; r = sp_vg_table(a[i], v, g) ? v : nan(""); break; }
     case 12: { SpState st; sp_setup<false>(a[i], b[i], st); r = st.f[kSpPl]; break; }
     case 13: { SpState st; sp_setup<true>(a[i], b[i], st); r = st.f[kSpPlBand] > 0.0 ? st.f[kSpPl] : nan(""); break; }
+    case 14: { double f[kAltSetupDoubles]; alt_setup<false>(a[i], 0.5 * fabs(b[i]), f); r = f[kAltPr]; break; }
+    case 15: { double f[kAltSetupDoubles]; alt_setup<true>(a[i], 0.5 * fabs(b[i]), f); r = f[kAltPrBand] > 0.0 ? f[kAltPr] : nan(""); break; }
     }
     out[i] = r;
 }

@@ -250,24 +250,8 @@ __device__ __forceinline__ float sp_pl_estimate(double n, double md, double rt2r
     const float b = s * (float)(md * rt2rl - 1.0);
     const float t = s * (float)(md * rt2rl + 1.0) * 0.70710678f;
     const float pig = 0.5f * erfcf(-b * 0.70710678f) + 0.5f * erfcxf(t) * __expf(-0.5f * b * b);
-    // Gamma(a, x) e^x x^-a, modified Lentz
-    const float a = (float)n, x = (float)ltb;
-    float bb = x + 1.0f - a;
-    float c = 1e30f, d = 1.0f / bb, hcf = d;
-    bool conv = false;
-    for (int i = 1; i <= 64; ++i) {
-        float an = -(float)i * ((float)i - a);
-        bb += 2.0f;
-        d = an * d + bb;
-        d = fabsf(d) < 1e-30f ? 1e-30f : d;
-        c = bb + an / c;
-        c = fabsf(c) < 1e-30f ? 1e-30f : c;
-        d = 1.0f / d;
-        float del = d * c;
-        hcf *= del;
-        if (fabsf(del - 1.0f) < 3e-7f) { conv = true; break; }
-    }
-    if (!conv || !(pig > 0.0f)) return -1.0f;
+    const float hcf = upper_gamma_cf_f32((float)n, (float)ltb);     // Gamma(n, x) e^x x^-n
+    if (!(hcf > 0.0f) || !(pig > 0.0f)) return -1.0f;
     const float R = __expf((float)D) * hcf / pig;
     if (!(R >= 0.0f) || isinf(R)) return -1.0f;
     return 1.0f / (1.0f + R);

@@ -166,6 +166,19 @@ def test_saddle_point_pl_estimate(engine):
     assert np.max(np.abs(est[have] - pl[have])) < 5e-6
 
 
+def test_alternate_pr_estimate(engine):
+    """Same scheme for the alternate sampler's right-piece mass (chunk shapes 1 .. 4)."""
+    rng = np.random.default_rng(12)
+    h = np.concatenate([rng.uniform(1, 4, 60000), np.full(20000, 4.0), rng.integers(1, 5, 5000).astype(float)])
+    z = np.concatenate([rng.uniform(-5, 5, 70000), rng.uniform(-40, 40, 15000)])
+    pr = engine.specfun("alt_pr", h, z)
+    est = engine.specfun("alt_pr_estimate", h, z)
+    have = ~np.isnan(est)
+    assert have[np.abs(z) <= 5].mean() > 0.99
+    assert np.all(np.isfinite(pr)) and np.all((pr >= 0) & (pr <= 1))
+    assert np.max(np.abs(est[have] - pr[have])) < 5e-6
+
+
 # ----------------------------------------------------------------------------------
 # tier 1: golden vectors made from the reference itself
 # ----------------------------------------------------------------------------------

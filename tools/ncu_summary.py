@@ -21,7 +21,7 @@ KEYS = [
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe %"),
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU (MUFU) pipe %"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
-    ("sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active", "DMMA pipe %"),
+    ("sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active", "DMMA (FP64 tensor) pipe %"),
     ("sm__icc_request_hit_rate.pct", "instruction cache hit %"),
     ("gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed", "GPC instr-cache requests % of peak"),
     ("smsp__average_warp_latency_per_inst_issued.ratio", "warp cycles / issued instr"),
