@@ -237,11 +237,13 @@ __device__ __forceinline__ bool alt_pick(Src &src, AltLane &L, double z, const S
 }
 
 // One trip of a lane: returns true when the whole draw is complete (L.sum = omega).  z is |z|/2.
-template <class Src, class St>
+// kPickInside = false: the caller guarantees a piece has been picked (L.phase != 0) -- the
+// regrouping kernel picks when the previous trip ends, and should not carry a second copy.
+template <bool kPickInside = true, class Src, class St>
 __device__ __forceinline__ bool alt_trip(Src &src, AltLane &L, double z, const St &st)
 {
     const int max_inner = 200;
-    if (L.phase == 0) {
+    if (kPickInside && L.phase == 0) {
         if (alt_pick(src, L, z, st)) return true;
         if (L.phase == 0) return false;                                // chunk closed at its proposal cap
     }

@@ -283,7 +283,7 @@ struct AltRegroup {
         load(S, sl, L);
         const double zh = S.d[0][sl];
         AltStateRef st{&S.f[0][sl], (size_t)kRgThreads};
-        bool done = alt_trip(src, L, zh, st);
+        bool done = alt_trip<false>(src, L, zh, st);
         while (!done && L.phase == 0) done = alt_pick(src, L, zh, st);  // piece of the next proposal
         if (done)
             omega = L.sum;

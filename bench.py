@@ -294,20 +294,31 @@ def main():
         torch.cuda.synchronize()
         fn_host(x_p.data_ptr(), shape_p.data_ptr(), z_p.data_ptr(), num, SEED, 0, obs0)
         same = bool(torch.equal(x_p[: 1 << 20], x_d[: 1 << 20].cpu()))
-        # the floor under e2e: pinned host->device bandwidth of this rank's link, measured now
-        # (16 of the 24 bytes per draw go that way; the 8 B coming back overlap on the other direction)
+        # the floor under e2e: pinned host->device bandwidth of this rank's link while the
+        # device->host direction is busy too, measured now (16 of the 24 bytes per draw go in, 8 come
+        # back; the pipeline keeps both directions busy, which costs each ~10 % of its solo rate)
         probe = torch.empty(1 << 26, dtype=torch.float64).pin_memory()
+        probe_o = torch.empty(1 << 25, dtype=torch.float64).pin_memory()
         probe_d = torch.empty(1 << 26, dtype=torch.float64, device=dev)
-        probe_d.copy_(probe, non_blocking=True)
+        probe_do = torch.empty(1 << 25, dtype=torch.float64, device=dev)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def both():
+            with torch.cuda.stream(s_in):
+                probe_d.copy_(probe, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                probe_o.copy_(probe_do, non_blocking=True)
+
+        both()
         torch.cuda.synchronize()
         tp0 = time.perf_counter()
         for _ in range(3):
-            probe_d.copy_(probe, non_blocking=True)
+            both()
         torch.cuda.synchronize()
         h2d_gbs = 3 * probe.numel() * 8 / (time.perf_counter() - tp0) / 1e9
-        del probe, probe_d
+        del probe, probe_d, probe_o, probe_do
         e2e = {"value": world * num * e_steps / dt, "unit": "draws/s",
-               "h2d_GBs_measured": h2d_gbs,
+               "h2d_GBs_measured_with_d2h_busy": h2d_gbs,
                "pcie_bound_draws_per_s": world * h2d_gbs * 1e9 / (BYTES_PER_DRAW[wl] - 8),
                "h2d_bytes_per_step": int(world * num * (BYTES_PER_DRAW[wl] - 8)),
                "d2h_bytes_per_step": int(world * num * 8), "steps": e_steps,
