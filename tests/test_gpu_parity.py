@@ -296,6 +296,21 @@ def test_philox_stream_parity(engine, oracle, method, num):
     assert_close(got, want, scale=scale)
 
 
+def test_philox_stream_parity_binned_path_wide_tilt(engine, oracle):
+    """The regime-binned rpg_hybrid kernels over tilts far outside the benchmark's range: there the
+    fp32 mass estimates are not offered, the gamma tail leaves the continued-fraction form, the
+    saddle-point abscissae leave the V/G tables and Gamma(n) overflows -- every hand-over to the
+    reference-faithful forms is exercised, draw for draw against the oracle."""
+    rng = np.random.default_rng(17)
+    num = 400_000
+    z = np.concatenate([rng.uniform(-40, 40, num // 2), rng.normal(0, 1e-3, num // 4), rng.uniform(-90, 90, num // 4)])
+    z[:100] = 0.0
+    shape = np.where(rng.random(num) < 0.5, rng.uniform(0.5, 200, num), rng.integers(1, 201, num).astype(float))
+    got = engine.rpg_seeded("hybrid", shape, z, seed=0xBEEF, call_id=1, obs0=123)
+    want = oracle.rpg_hybrid(shape, z, seed=0xBEEF, call_id=1, obs0=123, nthreads=8)
+    assert_close(got, want, scale=normal_regime_amplification(shape, z))
+
+
 def test_results_independent_of_chunking_and_sharding(engine):
     """obs0 keys the stream by global observation index: two half batches equal one full batch."""
     rng = np.random.default_rng(3)
