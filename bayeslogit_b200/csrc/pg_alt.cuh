@@ -236,13 +236,87 @@ __device__ __forceinline__ bool alt_pick(Src &src, AltLane &L, double z, const S
     return false;
 }
 
+// The alternating-series test of a proposal X against Y = U g~(X), PolyaGammaAlt.cpp:160-200, in fp64
+// as written (a_n by the recursive form :37-49, monotonicity required, 200-term cap).
+template <class St>
+static __device__ __noinline__ bool alt_series_exact(double X, double u, double h, double trunc, const St &st, int o)
+{
+    const int max_inner = 200;
+    const double coef_h = st.get(o + kAltCoef);
+    const double lx3 = ool::log_(X * X * X);
+    double g = 1.0;
+    double S = alt_coef(0.0, lx3, st.get(o + kAltLd0), X, h, coef_h, g);
+    double a_n = S;
+    double gt;                                                          // g~(x), :99-108
+    if (X > trunc)
+        gt = ool::exp_(h * 0.45158270528945486472619522989488 /* log(pi/2) */ + (h - 1) * (lx3 * (1.0 / 3.0))
+                       - kPi * kPi * 0.125 * X - st.get(o + kAltLgh));
+    else
+        gt = h * ool::exp_(h * 0.693147180559945309417232 - 0.5 * (1.8378770664093454835606594728112 + lx3)
+                           - 0.5 * h * h / X);
+    double Y = u * gt;
+    int n = 0;
+    bool go = true, accept = false;
+    while (go && n < max_inner) {
+        ++n;
+        double prev = a_n;
+        double ldn = n == 1 ? st.get(o + kAltLd1) : ool::log_(2.0 * n + h);
+        a_n = alt_coef((double)n, lx3, ldn, X, h, coef_h, g);
+        bool decreasing = a_n <= prev;
+        if (n & 1) {
+            S = S - a_n;
+            if (Y <= S && decreasing) {
+                accept = true;
+                go = false;
+            }
+        } else {
+            S = S + a_n;
+            if (Y > S && decreasing) go = false;
+        }
+    }
+    return accept;
+}
+
+// fp32 pre-filter of that test.  Dividing by g~ turns it into U against partial sums of
+// r_n = a_n / g~ = coef g_n d_n exp(-(3/2) log x - d_n^2 / 2x - log g~): the linear parts are fp64,
+// log x and the three exponentials fp32 (MUFU).  Nearly every proposal leaves at the first odd
+// term (accept) or the first even term (reject); those two exits are taken when the comparison
+// and the monotonicity condition both clear a band of >= 3x the fp32 error bound
+// (r_n carries |e_n| 2^-24 + 2 ulp of __expf + 2 |dlog x|, < 3e-6 for any r_n > 1e-8).  Everything
+// else -- in-band, later terms, non-monotone coefficients, NaN -- goes to alt_series_exact, so the
+// decision taken is always the fp64 decision.
+template <class St>
+__device__ __forceinline__ bool alt_series_test(double X, double u, double h, double trunc, const St &st, int o)
+{
+    const double coef_h = st.get(o + kAltCoef);
+    const double iX = 1.0 / X;
+    const double lx3 = 3.0 * (double)__logf((float)X);
+    double lgt;
+    if (X > trunc)
+        lgt = h * 0.45158270528945486472619522989488 + (h - 1) * (lx3 * (1.0 / 3.0)) - kPi * kPi * 0.125 * X
+            - st.get(o + kAltLgh);
+    else
+        lgt = st.get(o + kAltLd0) + h * 0.693147180559945309417232 - 0.5 * (1.8378770664093454835606594728112 + lx3)
+            - 0.5 * h * h * iX;
+    const double base = -0.5 * lx3 - lgt;
+    const double d0 = h, d1 = h + 2.0, d2 = h + 4.0;
+    const double r0 = coef_h * d0 * (double)__expf((float)(base - 0.5 * d0 * d0 * iX));
+    const double r1 = coef_h * h * d1 * (double)__expf((float)(base - 0.5 * d1 * d1 * iX));
+    const double r2 = coef_h * (0.5 * h * (h + 1.0)) * d2 * (double)__expf((float)(base - 0.5 * d2 * d2 * iX));
+    const double band = 1e-5 * (r0 + r1 + r2) + 1e-9;
+    const double s1 = r0 - r1;
+    if (u <= s1 - band && r1 <= r0 - band) return true;                     // accepted at n = 1
+    const bool not_at_1 = u > s1 + band || r1 > r0 + band;
+    if (not_at_1 && u > s1 + r2 + band && r2 <= r1 - band) return false;    // rejected at n = 2
+    return alt_series_exact(X, u, h, trunc, st, o);
+}
+
 // One trip of a lane: returns true when the whole draw is complete (L.sum = omega).  z is |z|/2.
 // kPickInside = false: the caller guarantees a piece has been picked (L.phase != 0) -- the
 // regrouping kernel picks when the previous trip ends, and should not carry a second copy.
 template <bool kPickInside = true, class Src, class St>
 __device__ __forceinline__ bool alt_trip(Src &src, AltLane &L, double z, const St &st)
 {
-    const int max_inner = 200;
     if (kPickInside && L.phase == 0) {
         if (alt_pick(src, L, z, st)) return true;
         if (L.phase == 0) return false;                                // chunk closed at its proposal cap
@@ -283,38 +357,7 @@ __device__ __forceinline__ bool alt_trip(Src &src, AltLane &L, double z, const S
     }
     if (L.phase == 4) {
         const double X = L.X;
-        const double coef_h = st.get(o + kAltCoef);
-        const double lx3 = ool::log_(X * X * X);
-        double g = 1.0;
-        double S = alt_coef(0.0, lx3, st.get(o + kAltLd0), X, h, coef_h, g);
-        double a_n = S;
-        double gt;                                                      // g~(x), :99-108
-        if (X > trunc)
-            gt = ool::exp_(h * 0.45158270528945486472619522989488 /* log(pi/2) */ + (h - 1) * (lx3 * (1.0 / 3.0))
-                           - kPi * kPi * 0.125 * X - st.get(o + kAltLgh));
-        else
-            gt = h * ool::exp_(h * 0.693147180559945309417232 - 0.5 * (1.8378770664093454835606594728112 + lx3)
-                               - 0.5 * h * h / X);
-        double Y = src.unif() * gt;
-        int n = 0;
-        bool go = true, accept = false;
-        while (go && n < max_inner) {
-            ++n;
-            double prev = a_n;
-            double ldn = n == 1 ? st.get(o + kAltLd1) : ool::log_(2.0 * n + h);
-            a_n = alt_coef((double)n, lx3, ldn, X, h, coef_h, g);
-            bool decreasing = a_n <= prev;
-            if (n & 1) {
-                S = S - a_n;
-                if (Y <= S && decreasing) {
-                    accept = true;
-                    go = false;
-                }
-            } else {
-                S = S + a_n;
-                if (Y > S && decreasing) go = false;
-            }
-        }
+        const bool accept = alt_series_test(X, src.unif(), h, trunc, st, o);
         L.phase = 0;
         if (accept) {
             chunk_done = true;
