@@ -1,0 +1,29 @@
+#!/usr/bin/env python3
+"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck): the regime-binned
+rpg_hybrid path (set-up kernels, regrouping loop kernels, side stream), PG(1,z) with class binning
+off and on, and a short logit Gibbs chain with both beta draws.
+
+    compute-sanitizer --tool racecheck python tools/sanitize_small.py
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bayeslogit_b200 import api, gibbs_api  # noqa: E402
+
+rng = np.random.default_rng(0)
+num = int(os.environ.get("BL_SANITIZE_NUM", "120000"))
+z = rng.uniform(-8, 8, num)
+h = np.where(rng.random(num) < 0.5, rng.uniform(0.5, 200, num), rng.integers(1, 201, num).astype(float))
+x = api.rpg_seeded("hybrid", h, z, seed=1)
+print("hybrid", float(x.mean()))
+n1 = np.ones(num, dtype=np.int32)
+print("devroye", float(api.rpg_seeded("devroye", n1, z, seed=2).mean()))
+N, P = 4000, 16
+X = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
+y = (rng.random(N) < 0.5).astype(float)
+for flags in (0, gibbs_api.PLAIN_BETA):
+    w, b = gibbs_api.logit_gibbs(y, X, np.ones(N), np.zeros(P), np.eye(P), 3, 2, seed=5, flags=flags)
+    print("gibbs", flags, float(b.sum()))
