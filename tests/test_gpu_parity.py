@@ -311,6 +311,21 @@ def test_philox_stream_parity_binned_path_wide_tilt(engine, oracle):
     assert_close(got, want, scale=normal_regime_amplification(shape, z))
 
 
+def test_binned_path_is_deterministic(engine):
+    """The loop kernels hand draws from thread to thread through shared-memory slots and sort them
+    every trip; which thread advances which draw depends on scheduling.  Results must not: three
+    runs of the same 2M-draw batch are bit-identical (compute-sanitizer is not available on the
+    pool, this is the race check that is)."""
+    rng = np.random.default_rng(23)
+    num = 2_000_000
+    z = rng.uniform(-6, 6, num)
+    h = np.where(rng.random(num) < 0.5, rng.uniform(0.5, 200, num), rng.integers(1, 201, num).astype(float))
+    a = engine.rpg_seeded("hybrid", h, z, seed=5, call_id=3)
+    for _ in range(2):
+        assert np.array_equal(a, engine.rpg_seeded("hybrid", h, z, seed=5, call_id=3))
+    assert np.all(np.isfinite(a)) and np.all(a > 0)
+
+
 def test_results_independent_of_chunking_and_sharding(engine):
     """obs0 keys the stream by global observation index: two half batches equal one full batch."""
     rng = np.random.default_rng(3)

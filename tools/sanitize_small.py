@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck): the regime-binned
+"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck) where a pool allows it
+(this round's pool does not; tests/test_gpu_parity.py::test_binned_path_is_deterministic is the
+race check that runs everywhere): the regime-binned
 rpg_hybrid path (set-up kernels, regrouping loop kernels, side stream), PG(1,z) with class binning
 off and on, and a short logit Gibbs chain with both beta draws.
 
