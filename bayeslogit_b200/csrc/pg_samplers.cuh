@@ -5,9 +5,9 @@
 //   devroye_one      PG(1,z)            PolyaGamma.cpp:151-202 (+ :41-55, :65-80, :82-115)
 //   devroye_sum      sum of n PG(1,z)   PolyaGamma.cpp:126-140
 //   gamma_sum        truncated sum      PolyaGamma.cpp:142-149, :19-39
-//   alt_chunk/alt    PG(h,z), h>=1      PolyaGammaAlt.cpp:114-203, :205-225
-//   v_eval           y -> v             InvertY.cpp:57-99
-//   sp_draw          PG(n,z), n large   PolyaGammaSP.cpp:169-264
+//   alt_draw         PG(h,z), h>=1      PolyaGammaAlt.cpp:114-203, :205-225   (pg_alt.cuh)
+//   v_eval           y -> v             InvertY.cpp:57-99                      (pg_sp.cuh)
+//   sp_draw          PG(n,z), n large   PolyaGammaSP.cpp:169-264               (pg_sp.cuh)
 //   pg_m1 / pg_m2    exact moments      PolyaGamma.cpp:208-239
 //   hybrid           regime dispatch    LogitWrapper.cpp:140-162
 // Composite variates (the reference takes them from its absent RNG library) follow
