@@ -83,6 +83,8 @@ def lib():
     L.bl_logit_gibbs.argtypes = [vp] * 7 + [ci, ci, ci, ci, u64, ci]
     L.bl_mlogit_gibbs.argtypes = [vp] * 7 + [ci, ci, ci, ci, ci, u64, ci]
     L.bl_nb_gibbs.argtypes = [vp, vp, vp, vp, cd, vp, vp, ci, ci, ci, u64]
+    L.bl_nb_gibbs_df.argtypes = [vp, vp, vp, vp, vp, cd, vp, vp, ci, ci, ci, ci, u64]
+    L.bl_nb_gibbs_df_dev.argtypes = [vp, vp, vp, vp, vp, cd, vp, vp, i64, ci, ci, ci, u64, u64, vp]
     L.bl_logit_gibbs_dev.argtypes = [vp] * 7 + [i64, ci, ci, ci, u64, ci, u64, vp]
     L.bl_mlogit_gibbs_dev.argtypes = [vp] * 7 + [i64, ci, ci, ci, ci, u64, ci, u64, vp]
     L.bl_nb_gibbs_dev.argtypes = [vp, vp, vp, vp, cd, vp, vp, i64, ci, ci, u64, u64, vp]

@@ -266,6 +266,38 @@ int bl_nb_gibbs(double *w_last, double *beta, const double *y, const double *tX,
     return 0;
 }
 
+int bl_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
+                   const double *m0, const double *P0, int N, int P, int samp, int burn, uint64_t seed)
+{
+    if (bl_ensure_ready_internal()) return 1;
+    std::string err;
+    Dev dv;
+    double *dy = dv.put(y, N, err), *dX = dv.put(tX, (size_t)N * P, err);
+    double *dm0 = dv.put(m0, P, err), *dP0 = dv.put(P0, (size_t)P * P, err);
+    double *dw = dv.put(nullptr, N, err), *dbeta = dv.put(nullptr, (size_t)P * samp, err);
+    double *dd = dv.put(nullptr, samp, err);
+    if (!err.empty()) return report(err, "Aborting Gibbs sampler.");
+    if (nb_gibbs_df_device(dw, dbeta, dd, dy, dX, d0, dm0, dP0, N, P, samp, burn, seed, 0,
+                           (cudaStream_t)bl_stream_internal(), err))
+        return report(err, "Aborting Gibbs sampler.");
+    cudaError_t e = cudaMemcpy(beta, dbeta, sizeof(double) * (size_t)P * samp, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(d_out, dd, sizeof(double) * samp, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && w_last) e = cudaMemcpy(w_last, dw, sizeof(double) * N, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return report(cudaGetErrorString(e), "Aborting Gibbs sampler.");
+    return 0;
+}
+
+int bl_nb_gibbs_df_dev(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
+                       const double *m0, const double *P0, int64_t N, int P, int samp, int burn, uint64_t seed,
+                       uint64_t obs0, void *stream)
+{
+    if (bl_ensure_ready_internal()) return 1;
+    std::string err;
+    if (nb_gibbs_df_device(w_last, beta, d_out, y, tX, d0, m0, P0, N, P, samp, burn, seed, obs0, (cudaStream_t)stream, err))
+        return report(err, nullptr);
+    return 0;
+}
+
 int bl_logit_gibbs_dev(double *w, double *beta, const double *y, const double *tX, const double *n,
                        const double *m0, const double *P0, int64_t N, int P, int samp, int burn,
                        uint64_t seed, int flags, uint64_t obs0, void *stream)

@@ -65,6 +65,9 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
 int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const double *tX, double d,
                     const double *m0, const double *P0, int64_t N, int P, int samp, uint64_t seed,
                     uint64_t obs0, cudaStream_t st, std::string &err);
+int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const double *y, const double *tX,
+                       double d0, const double *m0, const double *P0, int64_t N, int P, int samp, int burn,
+                       uint64_t seed, uint64_t obs0, cudaStream_t st, std::string &err);
 int logit_em_device(double *beta, const double *y, const double *tX, const double *n, int64_t N,
                     int P, double tol, int max_iter, int *iters, cudaStream_t st, std::string &err);
 int comm_unique_id(void *out128, std::string &err);

@@ -210,9 +210,10 @@ struct Sweep {
     }
 
     // acc[P^2..P^2+P) <- X'(c0 v0 + c1 v1 v2)
-    void xtv(const double *v0, double c0, const double *v1, const double *v2, double c1)
+    void xtv(const double *v0, double c0, const double *v1, const double *v2, double c1,
+             const double *c1_dev = nullptr)
     {
-        k_xtv_partial<<<xtv_slabs, 256, 8 * P * sizeof(double), st>>>(xtv_part, tX, v0, c0, v1, v2, c1, N, P);
+        k_xtv_partial<<<xtv_slabs, 256, 8 * P * sizeof(double), st>>>(xtv_part, tX, v0, c0, v1, v2, c1, N, P, c1_dev);
         k_xtv_reduce<<<cdiv(P, 128), 128, 0, st>>>(acc + (size_t)P * P, nullptr, nullptr, xtv_part, P, xtv_slabs);
         count_launch(2);
     }
@@ -443,6 +444,84 @@ int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const doub
     }
     GB_CK(cudaGetLastError());
     return s.check_status(err, "nb_gibbs");
+}
+
+// ------------------------------------------------------------------------------------
+// Negative binomial with the dispersion sampled (NB.PG.gibbs, NBPG-logmean.R:36-113, with
+// draw.df, NB-Shape.R:9-53): per iteration phi = X beta; d | beta by one random-walk
+// Metropolis step; psi = phi - log d; omega = PG(y + d, psi); beta | omega, d.  d, log d and
+// everything derived from them stay on the device.  beta_out: P x samp, d_out: samp (recorded
+// past burn-in), w_out: N (last omega) or null.  One GPU: the N-term log-likelihood sums are not
+// all-reduced.
+// ------------------------------------------------------------------------------------
+int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const double *y, const double *tX,
+                       double d0, const double *m0, const double *P0, int64_t N, int P, int samp, int burn,
+                       uint64_t seed, uint64_t obs0, cudaStream_t st, std::string &err)
+{
+    if (N <= 0 || P <= 0 || samp <= 0 || burn < 0 || !(d0 >= 1.0) || d0 != floor(d0)) {
+        err = "nb_gibbs_df: bad arguments (d0 must be a positive integer)";
+        return 1;
+    }
+    if (g_nccl.world > 1 && g_nccl.comm) { err = "nb_gibbs_df: sharded data is not supported"; return 1; }
+    DevMem mem;
+    mem.st = st;
+    Sweep s;
+    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX;
+    if (s.init(mem, err)) return 1;
+    double *kappa, *b0, *shape, *bcur, *dpair, *G, *dfpart;
+    int *ymax_d;
+    void *work;
+    GB_CK(mem.get(&kappa, N));
+    GB_CK(mem.get(&shape, N));
+    GB_CK(mem.get(&b0, P));
+    GB_CK(mem.get(&bcur, 2 * (size_t)P));
+    GB_CK(mem.get(&dpair, 2));                 // d, log d
+    GB_CK(mem.get(&ymax_d, 1));
+    GB_CK(mem.get((char **)&work, hybrid_workspace_bytes(N)));
+    const int nblk = (int)std::min<int64_t>(148 * 4, std::max<int64_t>(1, N / 1024));
+    GB_CK(mem.get(&dfpart, (size_t)nblk * 4));
+    // ymax, G
+    GB_CK(cudaMemsetAsync(ymax_d, 0, sizeof(int), st));
+    k_nb_ymax<<<148 * 2, 256, 0, st>>>(ymax_d, y, N);
+    int ymax = 0;
+    GB_CK(cudaMemcpyAsync(&ymax, ymax_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GB_CK(cudaStreamSynchronize(st));
+    unsigned long long *hist;
+    GB_CK(mem.get(&hist, (size_t)ymax + 2));
+    GB_CK(mem.get(&G, (size_t)ymax + 1));
+    GB_CK(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * ((size_t)ymax + 2), st));
+    k_nb_hist<<<148 * 2, 256, 0, st>>>(hist, y, N);
+    k_nb_suffix<<<1, 1, 0, st>>>(G, hist, ymax);
+    k_matvec<<<cdiv(P, 128), 128, 0, st>>>(b0, P0, m0, P);
+    count_launch(4);
+    const double dinit[2] = {d0, log(d0)};
+    GB_CK(cudaMemcpyAsync(dpair, dinit, sizeof(dinit), cudaMemcpyHostToDevice, st));
+    GB_CK(cudaMemsetAsync(bcur, 0, sizeof(double) * 2 * P, st));
+    double *w = w_out ? w_out : s.w;
+    for (int t = 0; t < samp + burn; ++t) {
+        const double *bprev = bcur + (size_t)P * (t & 1);
+        double *bnext = t >= burn ? beta_out + (size_t)P * (t - burn) : bcur + (size_t)P * ((t + 1) & 1);
+        s.xbeta(s.psi, bprev, nullptr, 0.0);                                   // phi = X beta
+        k_nb_df_partial<<<nblk, 256, 0, st>>>(dfpart, s.psi, y, dpair, N, seed, (uint32_t)t);
+        k_nb_df_decide<<<1, 32, 0, st>>>(dpair, dpair + 1, t >= burn ? d_out + (t - burn) : nullptr, dfpart, nblk, G,
+                                         ymax, seed, (uint32_t)t);
+        k_nb_prepare<<<cdiv(N, 256), 256, 0, st>>>(s.psi, shape, kappa, y, dpair, dpair + 1, N);
+        count_launch(3);
+        StreamId id{seed, obs0, (uint32_t)t};
+        cudaError_t e = N >= (1 << 15)
+            ? launch_hybrid_binned(w, shape, s.psi, (int)N, id, work, st)
+            : launch_rpg(kHybrid, w, shape, s.psi, N, 0, nullptr, id, st);
+        if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
+        s.gram(w);
+        s.xtv(kappa, 1.0, w, nullptr, 0.0, dpair + 1);                         // X'(kappa + omega log d)
+        s.beta_draw(kBetaPlain, P0, b0, true, nullptr, bnext, seed, (uint32_t)t);
+        // the next iteration reads beta from where this one wrote it
+        if (t >= burn) {
+            GB_CK(cudaMemcpyAsync(bcur + (size_t)P * ((t + 1) & 1), bnext, sizeof(double) * P, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    GB_CK(cudaGetLastError());
+    return s.check_status(err, "nb_gibbs_df");
 }
 
 // ------------------------------------------------------------------------------------

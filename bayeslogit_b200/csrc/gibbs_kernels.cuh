@@ -368,8 +368,9 @@ k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
 __global__ void __launch_bounds__(256)
 k_xtv_partial(double *__restrict__ part, const double *__restrict__ tX, const double *__restrict__ v0,
               double c0, const double *__restrict__ v1, const double *__restrict__ v2, double c1,
-              int64_t N, int P)
+              int64_t N, int P, const double *__restrict__ c1_dev = nullptr)
 {
+    if (c1_dev) c1 = *c1_dev;                  // coefficient produced on the device (NB: log d)
     extern __shared__ double sacc[];   // [warps][P]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int p = threadIdx.x; p < nw * P; p += blockDim.x) sacc[p] = 0.0;
@@ -422,6 +423,127 @@ __global__ void k_shape_add(double *__restrict__ out, const double *__restrict__
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < N) out[i] = y[i] + d;
+}
+
+// ---------------------------------------------------------------------------------
+// Negative-binomial dispersion update, draw.df of Code/R/NB-Shape.R:21-53 (kernel 1: random walk on
+// the integers) with df.llh :9-19.  d lives in device memory; nothing returns to the host.
+//   proposal: uniform on max(d-1,1) .. d+1 from the first uniform of stream (seed, 2^64-2, call)
+//   llh(d) = sum_j log(d+j) G[j] + d sum_i (log d - log(e^phi_i + d)) + sum_i y_i (phi_i - log(e^phi_i + d))
+// k_nb_df_partial: per-CTA sums of the two N-term series for d and the proposal (fixed order);
+// k_nb_df_decide: one warp adds them up, adds the G series, applies the Metropolis test with the
+// stream's second uniform and publishes d, log d (and the recorded draw).
+// ---------------------------------------------------------------------------------
+constexpr uint64_t kDfObs = 0xFFFFFFFFFFFFFFFEull;
+
+__device__ __forceinline__ double nb_df_proposal(double d, uint64_t seed, uint32_t call, double *u_accept)
+{
+    PhiloxSource s;
+    s.open(seed, kDfObs, call);
+    double lower = d - 1.0 > 1.0 ? d - 1.0 : 1.0;
+    int nn = (int)(d + 1.0 - lower) + 1;
+    int k = (int)floor(s.unif() * nn);
+    if (k > nn - 1) k = nn - 1;
+    if (u_accept) *u_accept = s.unif();
+    return lower + k;
+}
+
+__global__ void __launch_bounds__(256)
+k_nb_df_partial(double *__restrict__ part, const double *__restrict__ phi, const double *__restrict__ y,
+                const double *__restrict__ dptr, int64_t N, uint64_t seed, uint32_t call)
+{
+    __shared__ double red[8][4];
+    const double d = *dptr, dp = nb_df_proposal(d, seed, call, nullptr);
+    const double ld = log(d), ldp = log(dp);
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    const int64_t slab = (N + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * slab, r1 = r0 + slab < N ? r0 + slab : N;
+    for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+        double ph = phi[i], mu = exp(ph), yi = y[i];
+        double l0 = log(mu + d), l1 = log(mu + dp);
+        s[0] += ld - l0;
+        s[1] += yi * (ph - l0);
+        s[2] += ldp - l1;
+        s[3] += yi * (ph - l1);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double v = s[k];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        part[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+    }
+}
+
+__global__ void k_nb_df_decide(double *__restrict__ dptr, double *__restrict__ ldptr, double *__restrict__ d_rec,
+                               const double *__restrict__ part, int nblk, const double *__restrict__ G, int ymax,
+                               uint64_t seed, uint32_t call)
+{
+    const int lane = threadIdx.x;
+    const double d = *dptr;
+    double u_acc;
+    const double dp = nb_df_proposal(d, seed, call, &u_acc);
+    double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int b = lane; b < nblk; b += 32)
+        for (int k = 0; k < 4; ++k) s[k] += part[(size_t)b * 4 + k];
+    for (int j = lane; j < ymax; j += 32) {
+        s[4] += log(d + j) * G[j];
+        s[5] += log(dp + j) * G[j];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    if (lane == 0) {
+        double llh_prev = s[4] + d * s[0] + s[1];
+        double llh_prop = s[5] + dp * s[2] + s[3];
+        double lppsl = log(dp == 1.0 ? 0.5 : 1.0 / 3.0) - log(d == 1.0 ? 0.5 : 1.0 / 3.0);
+        double dn = u_acc < exp(llh_prop - llh_prev + lppsl) ? dp : d;
+        *dptr = dn;
+        *ldptr = log(dn);
+        if (d_rec) *d_rec = dn;
+    }
+}
+
+// psi <- phi - log d, shape <- y + d, kappa <- (y - d)/2 with d from device memory (NBPG-logmean.R:88-94)
+__global__ void k_nb_prepare(double *__restrict__ psi, double *__restrict__ shape, double *__restrict__ kappa,
+                             const double *__restrict__ y, const double *__restrict__ dptr,
+                             const double *__restrict__ ldptr, int64_t N)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double d = *dptr, ld = *ldptr;
+    psi[i] -= ld;
+    shape[i] = y[i] + d;
+    kappa[i] = 0.5 * (y[i] - d);
+}
+
+// ymax and G[j] = #{y_i > j} (NBPG-logmean.R:65-67)
+__global__ void k_nb_ymax(int *__restrict__ ymax, const double *__restrict__ y, int64_t N)
+{
+    int m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, (int)y[i]);
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(ymax, m);
+}
+__global__ void k_nb_hist(unsigned long long *__restrict__ hist, const double *__restrict__ y, int64_t N)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&hist[(int)y[i]], 1ull);
+}
+__global__ void k_nb_suffix(double *__restrict__ G, const unsigned long long *__restrict__ hist, int ymax)
+{
+    unsigned long long run = 0;                    // G[j] = sum_{k > j} hist[k], j = ymax-1 .. 0
+    for (int j = ymax - 1; j >= 0; --j) {
+        run += hist[j + 1];
+        G[j] = (double)run;
+    }
 }
 
 // mlogit offsets for category j: A = sum_{k != j, k < J-1} exp(XB_k) + exp(0),

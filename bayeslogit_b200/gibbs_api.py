@@ -224,3 +224,20 @@ def nb_gibbs(y, X, d, m0, P0, samp, seed):
                                 N, P, samp, int(seed))
     _lib.check(st)
     return w, beta
+
+
+def nb_gibbs_df(y, X, m0, P0, samp, burn, seed, d0=1.0):
+    """NB regression with the dispersion sampled (NB.PG.gibbs, NBPG-logmean.R:36-113).
+    Returns (w_last [N], beta [samp x P], d [samp])."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    N, P = X.shape
+    y, m0 = _f(y).ravel(), _f(m0).ravel()
+    P0c = np.asfortranarray(_f(P0))
+    beta = np.zeros((samp, P))
+    d = np.zeros(samp)
+    w = np.zeros(N)
+    st = _lib.lib().bl_nb_gibbs_df(_p(w), _p(beta), _p(d), _p(y), _p(X), float(d0), _p(m0), P0c.ctypes.data,
+                                   N, P, samp, burn, int(seed))
+    _lib.check(st)
+    return w, beta, d
+

@@ -174,6 +174,13 @@ int bl_mlogit_gibbs(double *w, double *beta, const double *ty, const double *tX,
  * for it: Code/R/NBPG-logmean.R:13-34,77-106).  y: counts [N]; beta: P x samp; w_last: N or NULL. */
 int bl_nb_gibbs(double *w_last, double *beta, const double *y, const double *tX, double d,
                 const double *m0, const double *P0, int N, int P, int samp, uint64_t seed);
+/* The full NB.PG.gibbs of Code/R/NBPG-logmean.R:36-113: the dispersion d is sampled every
+ * iteration by draw.df (Code/R/NB-Shape.R:21-53, random-walk Metropolis on the integers, two
+ * uniforms per iteration from the stream (seed, obs 2^64-2, iteration)); burn iterations are
+ * discarded.  d0: initial integer dispersion (the reference starts at 1); beta: P x samp;
+ * d_out: samp; w_last: N (omega of the last iteration) or NULL. */
+int bl_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
+                   const double *m0, const double *P0, int N, int P, int samp, int burn, uint64_t seed);
 
 /* Device-resident shards (all pointers DEVICE pointers; one process per GPU).  Rank r holds
  * observations [obs0, obs0+N) of the global data set; with a communicator (bl_comm_init) the
@@ -188,6 +195,10 @@ int bl_mlogit_gibbs_dev(double *w, double *beta, const double *ty, const double 
 int bl_nb_gibbs_dev(double *w_last, double *beta, const double *y, const double *tX, double d,
                     const double *m0, const double *P0, int64_t N, int P, int samp, uint64_t seed,
                     uint64_t obs0, void *stream);
+/* single GPU only: the dispersion update's log-likelihood sums are not all-reduced */
+int bl_nb_gibbs_df_dev(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
+                       const double *m0, const double *P0, int64_t N, int P, int samp, int burn, uint64_t seed,
+                       uint64_t obs0, void *stream);
 
 /* Communicator over NCCL (NVLink/NVSwitch): rank 0 creates a 128-byte id, the host side
  * broadcasts it (e.g. torch.distributed), every rank calls bl_comm_init. */

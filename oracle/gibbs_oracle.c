@@ -436,3 +436,94 @@ int pgb_nb_gibbs(double *w_last, double *beta, const double *y, const double *tX
     free(b0); free(PP); free(bP); free(psi); free(bcur);
     return status;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * NB.PG.gibbs with the dispersion sampled (NBPG-logmean.R:36-113 with draw.df, NB-Shape.R:9-53,
+ * kernel 1: random-walk Metropolis on the integers).
+ *   G[j] = #{y_i > j}, j = 0..ymax-1                                  NBPG-logmean.R:65-67
+ *   df.llh(d) = sum_j log(d+j) G[j] + d sum_i (log d - log(mu_i+d)) + sum_i y_i (log mu_i - log(mu_i+d)),
+ *               mu_i = exp(phi_i) (log mu_i taken as phi_i)            NB-Shape.R:9-19
+ *   proposal uniform on max(d-1,1) .. d+1; accept with exp(llh(d') - llh(d) + lppsl)  :36-50
+ * Per iteration j (reference order, :82-95): phi = X beta; d = draw.df; psi = phi - log d;
+ * w = rpg(y + d, psi); kappa = (y - d)/2; beta | w, d.
+ * Variates of draw.df: two uniforms from the Philox stream (seed, obs 2^64-2, call j):
+ * the pick (index floor(U n) into the grid -- R's sample() lives in R's generator) and the
+ * accept test.  beta: P x samp, d_out: samp (recorded past burn-in), w_last: N.
+ * --------------------------------------------------------------------------------------------- */
+#define DF_OBS 0xFFFFFFFFFFFFFFFEull
+
+static double df_llh(const double *y, double d, const double *phi, const double *G, int ymax, int N)
+{
+    double llh1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int j = 0; j < ymax; ++j) llh1 += log(d + j) * G[j];
+    double ld = log(d);
+    for (int i = 0; i < N; ++i) {
+        double lmd = log(exp(phi[i]) + d);
+        s2 += ld - lmd;
+        s3 += y[i] * (phi[i] - lmd);
+    }
+    return llh1 + d * s2 + s3;
+}
+
+int pgb_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y, const double *tX,
+                    double d0, const double *m0, const double *P0, int N, int P, int samp, int burn,
+                    uint64_t seed, int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+    int ymax = 0;
+    for (int i = 0; i < N; ++i) if ((int)y[i] > ymax) ymax = (int)y[i];
+    double *G = (double *)calloc(ymax > 0 ? ymax : 1, sizeof(double));
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < (int)y[i]; ++j) G[j] += 1.0;
+    double *b0 = (double *)calloc(P, sizeof(double));
+    double *PP = (double *)malloc(sizeof(double) * P * P);
+    double *bP = (double *)malloc(sizeof(double) * P);
+    double *phi = (double *)malloc(sizeof(double) * N);
+    double *bcur = (double *)calloc(P, sizeof(double));
+    for (int a = 0; a < P; ++a)
+        for (int b = 0; b < P; ++b) b0[a] += P0[a + P * b] * m0[b];
+    double d = d0;
+    int status = 0;
+    for (int t = 0; t < samp + burn && !status; ++t) {
+        xbeta(phi, tX, bcur, N, P, nthreads);
+        {   /* draw.df */
+            pgo_src sd;
+            pgo_src_philox(&sd, seed, DF_OBS, (uint32_t)t);
+            double lower = d - 1.0 > 1.0 ? d - 1.0 : 1.0;
+            int nn = (int)(d + 1.0 - lower) + 1;
+            int k = (int)floor(pgo_unif(&sd) * nn);
+            if (k > nn - 1) k = nn - 1;
+            double dp = lower + k;
+            double ltarget = df_llh(y, dp, phi, G, ymax, N) - df_llh(y, d, phi, G, ymax, N);
+            double lppsl = log(dp == 1.0 ? 0.5 : 1.0 / 3.0) - log(d == 1.0 ? 0.5 : 1.0 / 3.0);
+            if (pgo_unif(&sd) < exp(ltarget + lppsl)) d = dp;
+        }
+        double ld = log(d);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
+        for (int i = 0; i < N; ++i) {
+            pgo_src s;
+            pgo_src_philox(&s, seed, (uint64_t)i, (uint32_t)t);
+            w_last[i] = pgo_hybrid_draw(&s, y[i] + d, phi[i] - ld);
+        }
+        weighted_gram(PP, P0, tX, w_last, N, P, nthreads);
+        memcpy(bP, b0, sizeof(double) * P);
+        for (int i = 0; i < N; ++i) {
+            double k = 0.5 * (y[i] - d) + w_last[i] * ld;
+            for (int a = 0; a < P; ++a) bP[a] += tX[a + (size_t)P * i] * k;
+        }
+        pgo_src sb;
+        pgo_src_philox(&sb, seed, BETA_OBS, (uint32_t)t);
+        status = draw_beta_plain(bcur, PP, bP, P, &sb);
+        if (t >= burn) {
+            memcpy(beta + (size_t)P * (t - burn), bcur, sizeof(double) * P);
+            d_out[t - burn] = d;
+        }
+    }
+    free(G); free(b0); free(PP); free(bP); free(phi); free(bcur);
+    return status;
+}
+

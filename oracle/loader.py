@@ -69,6 +69,7 @@ class Oracle:
             lib.pgb_logit_gibbs.argtypes = [vp] * 7 + [ci, ci, ci, ci, u64, ci, ci]
             lib.pgb_mlogit_gibbs.argtypes = [vp] * 7 + [ci, ci, ci, ci, ci, u64, ci]
             lib.pgb_nb_gibbs.argtypes = [vp, vp, vp, vp, C.c_double, vp, vp, ci, ci, ci, u64, ci]
+            lib.pgb_nb_gibbs_df.argtypes = [vp, vp, vp, vp, vp, C.c_double, vp, vp, ci, ci, ci, ci, u64, ci]
 
     # -- stream helpers ------------------------------------------------------
     @staticmethod
@@ -199,6 +200,21 @@ def nb_gibbs(y, X, d, m0, P0, samp, seed, nthreads=0):
     if st:
         raise RuntimeError("oracle nb_gibbs: precision not positive definite")
     return w, beta
+
+
+def nb_gibbs_df(y, X, m0, P0, samp, burn, seed, d0=1.0, nthreads=0):
+    """CPU restatement of NB.PG.gibbs with draw.df.  Returns (w_last [N], beta [samp x P], d [samp])."""
+    O = _gibbs_port()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    N, P = X.shape
+    y, m0 = _f64(y).ravel(), _f64(m0).ravel()
+    P0c = np.asfortranarray(_f64(P0))
+    w, beta, d = np.zeros(N), np.zeros((samp, P)), np.zeros(samp)
+    st = O.lib.pgb_nb_gibbs_df(w.ctypes.data, beta.ctypes.data, d.ctypes.data, y.ctypes.data, X.ctypes.data,
+                               float(d0), m0.ctypes.data, P0c.ctypes.data, N, P, samp, burn, int(seed), nthreads)
+    if st:
+        raise RuntimeError("oracle nb_gibbs_df: precision not positive definite")
+    return w, beta, d
 
 
 def make_tape(num, lu=0, le=0, ln=0, lg=0, g_shape=None, seed=0):

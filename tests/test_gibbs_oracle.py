@@ -82,6 +82,21 @@ def test_mlogit_and_nb_oracle_recover_truth():
     assert np.max(np.abs(bn[100:].mean(0) - bt)) < 0.1
 
 
+def test_nb_oracle_with_dispersion_update_recovers_d_and_beta():
+    """NB.PG.gibbs with draw.df (NBPG-logmean.R:36-113, NB-Shape.R:9-53): started at d = 1, the
+    random-walk Metropolis step has to walk to the true dispersion and stay around it."""
+    rng = np.random.default_rng(14)
+    N, P, d = 3000, 3, 6.0
+    X = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
+    bt = np.array([0.3, -0.2, 1.2])
+    mu = np.exp(X @ bt)
+    y = rng.negative_binomial(d, d / (mu + d)).astype(float)
+    _, b, ds = loader.nb_gibbs_df(y, X, np.zeros(P), 0.01 * np.eye(P), 400, 200, seed=3)
+    assert np.all(ds == np.floor(ds)) and ds.min() >= 1
+    assert abs(ds.mean() - d) < 1.5
+    assert np.max(np.abs(b.mean(0) - bt)) < 0.1
+
+
 @pytest.fixture(scope="module")
 def englib():
     from bayeslogit_b200 import _lib, build

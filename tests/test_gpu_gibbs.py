@@ -102,6 +102,29 @@ def test_nb_chain_matches_oracle(gapi):
     close(b, bo, 1e-7); close(w, wo, 1e-7)
 
 
+def test_nb_chain_with_dispersion_update_matches_oracle(gapi):
+    """The full NB.PG.gibbs (dispersion sampled on the device by draw.df): d equal step for step,
+    beta and omega within the chain tolerance."""
+    rng = np.random.default_rng(16)
+    N, P, d = 2500, 4, 4.0
+    X = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
+    bt = np.array([0.8, -0.6, 0.5, 2.2])
+    mu = np.exp(X @ bt)
+    y = rng.negative_binomial(d, d / (mu + d)).astype(float)
+    w, b, ds = gapi.nb_gibbs_df(y, X, np.zeros(P), 0.01 * np.eye(P), 14, 6, seed=8)
+    wo, bo, dso = loader.nb_gibbs_df(y, X, np.zeros(P), 0.01 * np.eye(P), 14, 6, seed=8)
+    assert np.array_equal(ds, dso) and len(set(ds)) > 1     # it moves, and moves identically
+    close(b, bo, 1e-7); close(w, wo, 1e-7)
+    # a batch large enough for the regime-binned draw path
+    N2 = 40_000
+    X2 = np.c_[rng.standard_normal((N2, P - 1)), np.ones(N2)]
+    y2 = rng.negative_binomial(d, d / (np.exp(X2 @ bt) + d)).astype(float)
+    w, b, ds = gapi.nb_gibbs_df(y2, X2, np.zeros(P), 0.01 * np.eye(P), 5, 3, seed=9, d0=3.0)
+    wo, bo, dso = loader.nb_gibbs_df(y2, X2, np.zeros(P), 0.01 * np.eye(P), 5, 3, seed=9, d0=3.0)
+    assert np.array_equal(ds, dso)
+    close(b, bo, 1e-7); close(w, wo, 1e-7)
+
+
 def test_em_matches_newton_mode(gapi):
     """logit.EM (Logit.hpp:488-554): flat prior -> the MLE."""
     X, y, n, _ = synth_logit(4000, 6, 9, binomial=True)
