@@ -88,8 +88,12 @@ def lib():
     L.bl_logit_gibbs_dev.argtypes = [vp] * 7 + [i64, ci, ci, ci, u64, ci, u64, vp]
     L.bl_mlogit_gibbs_dev.argtypes = [vp] * 7 + [i64, ci, ci, ci, ci, u64, ci, u64, vp]
     L.bl_nb_gibbs_dev.argtypes = [vp, vp, vp, vp, cd, vp, vp, i64, ci, ci, u64, u64, vp]
+    L.bl_logit_chains.argtypes = [vp] * 6 + [ci, ci, ci, ci, ci, u64, ci]
+    L.bl_logit_chains_dev.argtypes = [vp] * 6 + [ci, i64, ci, ci, ci, u64, ci, vp]
     L.bl_comm_unique_id.argtypes = [vp]
     L.bl_comm_init.argtypes = [vp, ci, ci]
+    L.bl_comm_peer_handle.argtypes = [vp]
+    L.bl_comm_peer_open.argtypes = [vp]
     L.bl_probe_pg_moments.argtypes = [vp, vp, vp, vp, i64]
     L.bl_probe_v_eval.argtypes = [vp, vp, i64]
     L.bl_probe_specfun.argtypes = [vp, ci, vp, vp, vp, i64]

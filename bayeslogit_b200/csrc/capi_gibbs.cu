@@ -309,6 +309,37 @@ int bl_logit_gibbs_dev(double *w, double *beta, const double *y, const double *t
     return 0;
 }
 
+int bl_logit_chains_dev(double *beta, const double *y, const double *tX, const double *n, const double *m0,
+                        const double *P0, int chains, int64_t N, int P, int samp, int burn, uint64_t seed,
+                        int flags, void *stream)
+{
+    if (bl_ensure_ready_internal()) return 1;
+    std::string err;
+    if (logit_chains_device(beta, y, tX, n, m0, P0, chains, N, P, samp, burn, seed, flags, (cudaStream_t)stream, err))
+        return report(err, nullptr);
+    return 0;
+}
+
+int bl_logit_chains(double *beta, const double *y, const double *tX, const double *n, const double *m0,
+                    const double *P0, int chains, int N, int P, int samp, int burn, uint64_t seed, int flags)
+{
+    if (bl_ensure_ready_internal()) return 1;
+    if (chains <= 0 || N <= 0 || P <= 0 || samp <= 0 || burn < 0) return report("logit_chains: bad dimensions", nullptr);
+    std::string err;
+    Dev d;
+    const size_t T = (size_t)chains * N;
+    double *dy = d.put(y, T, err), *dX = d.put(tX, T * P, err), *dn = d.put(n, T, err);
+    double *dm0 = d.put(m0, P, err), *dP0 = d.put(P0, (size_t)P * P, err);
+    double *dbeta = d.put(nullptr, (size_t)chains * P * samp, err);
+    if (!err.empty()) return report(err, nullptr);
+    if (logit_chains_device(dbeta, dy, dX, dn, dm0, dP0, chains, N, P, samp, burn, seed, flags,
+                            (cudaStream_t)bl_stream_internal(), err))
+        return report(err, nullptr);
+    cudaError_t e = cudaMemcpy(beta, dbeta, sizeof(double) * (size_t)chains * P * samp, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return report(cudaGetErrorString(e), nullptr);
+    return 0;
+}
+
 int bl_mlogit_gibbs_dev(double *w, double *beta, const double *ty, const double *tX, const double *n,
                         const double *m0, const double *P0, int64_t N, int P, int J, int samp, int burn,
                         uint64_t seed, int flags, uint64_t obs0, void *stream)
@@ -345,6 +376,30 @@ int bl_comm_init(const void *id128, int rank, int world)
     if (comm_init(id128, rank, world, err)) return report(err, nullptr);
     return 0;
 }
+
+int bl_comm_peer_handle(void *out64)
+{
+    if (bl_ensure_ready_internal()) return 1;
+    std::string err;
+    if (comm_peer_handle(out64, err)) return report(err, nullptr);
+    return 0;
+}
+
+int bl_comm_peer_open(const void *handles)
+{
+    if (bl_ensure_ready_internal()) return 1;
+    std::string err;
+    if (comm_peer_open(handles, err)) return report(err, nullptr);
+    return 0;
+}
+
+int bl_comm_peer_close(void)
+{
+    comm_peer_close();
+    return 0;
+}
+
+int bl_comm_peer_active(void) { return comm_peer_active(); }
 
 int bl_comm_destroy(void)
 {

@@ -19,6 +19,9 @@ struct StreamId {
     uint64_t seed;
     uint64_t obs0;
     uint32_t call_id;
+    // batched independent chains: > 0 means position i of the batch is observation i % chain_len of
+    // chain i / chain_len, whose streams are keyed by seed + chain (batch size < 2^31)
+    uint32_t chain_len = 0;
 };
 
 // Device-side tape descriptor (device pointers).
@@ -68,11 +71,18 @@ int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const doub
 int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const double *y, const double *tX,
                        double d0, const double *m0, const double *P0, int64_t N, int P, int samp, int burn,
                        uint64_t seed, uint64_t obs0, cudaStream_t st, std::string &err);
+int logit_chains_device(double *beta_out, const double *y, const double *tX, const double *n,
+                        const double *m0, const double *P0, int chains, int64_t N, int P, int samp, int burn,
+                        uint64_t seed, int flags, cudaStream_t st, std::string &err);
 int logit_em_device(double *beta, const double *y, const double *tX, const double *n, int64_t N,
                     int P, double tol, int max_iter, int *iters, cudaStream_t st, std::string &err);
 int comm_unique_id(void *out128, std::string &err);
 int comm_init(const void *id128, int rank, int world, std::string &err);
 void comm_destroy();
+int comm_peer_handle(void *out64, std::string &err);
+int comm_peer_open(const void *handles, std::string &err);
+void comm_peer_close();
+int comm_peer_active();
 
 void hybrid_timing_enable(bool on);
 int hybrid_timing_last(double *ms8, int *launches8);

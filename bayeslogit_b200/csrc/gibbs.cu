@@ -61,6 +61,32 @@ bool nccl_load(std::string &err)
 
 constexpr int kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
+// ------------------------------------------------------------------------------------
+// Peer exchange over NVLink (one node): every rank owns one cudaMalloc'd window that its peers
+// map through CUDA IPC.  Window = flags u32 [2 parities][8 ranks] (256 bytes reserved), then
+// slots double [2 parities][8 ranks][slot_doubles].  Exchange e (parity e & 1): the Gram reduce
+// kernel of rank r STORES its P^2 (+P) sums into slot [parity][r] of every rank's window (posted
+// NVLink writes, spread over the reduce kernel's CTAs), fences, and the last CTA stores e into flag
+// [parity][r] of every window; the beta-draw kernel of each rank waits on its LOCAL flags and adds
+// the slots in rank order, so every rank forms bit-identical sums and the replicated beta draw
+// needs no broadcast.  Parity double-buffering is enough: rank A starts exchange e+2 only after
+// its beta draw e+1, which waited for every peer's flag e+1, which each peer raised after its own
+// beta draw e (the reader of slots e) had completed in stream order.
+// ------------------------------------------------------------------------------------
+struct Peer {
+    void *base = nullptr;                  // this rank's window
+    void *win[kMaxPeers] = {};             // every rank's window as mapped here (win[rank] == base)
+    unsigned *done = nullptr;              // CTA completion counter of the pushing kernel
+    size_t slot_doubles = 0;
+    uint32_t epoch = 0;                    // exchanges issued so far (identical on every rank: SPMD)
+    bool open = false;
+} g_peer;
+
+constexpr size_t kPeerFlagBytes = 256;
+constexpr int kPeerMaxP = 256;
+
+bool peer_active() { return g_peer.open && g_nccl.world > 1; }
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------
@@ -75,9 +101,16 @@ template <bool SMEM>
 __global__ void __launch_bounds__(256)
 k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__ P0,
             const double *__restrict__ base_rhs, int add_tail, const double *beta_prev,
-            double *beta_out, double *gwork, int P, uint64_t seed, uint32_t call, int *status)
+            double *beta_out, double *gwork, int P, uint64_t seed, uint32_t call, int *status,
+            PeerWait pw, int64_t chain_stride)
 {
     extern __shared__ double sm[];
+    // batched independent chains: blockIdx.x = chain (own sums, own rhs, own beta, seed + chain; P0 shared)
+    acc += (size_t)blockIdx.x * ((size_t)P * P + P);
+    if (base_rhs) base_rhs += (size_t)blockIdx.x * P;
+    if (beta_prev) beta_prev += blockIdx.x * chain_stride;
+    beta_out += blockIdx.x * chain_stride;
+    seed += blockIdx.x;
 #ifdef BL_BETA_CLOCKS
     long long k0 = clock64();
 #endif
@@ -86,6 +119,19 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
     double *B = A + (size_t)ld * P;
     double *v = B + (size_t)ld * P;
     double *rhs = v + 4 * P;
+    if (pw.world > 1) {
+        // sharded data: PP and the rhs tail are the rank-ordered sums of the slots the peers pushed
+        peer_wait(pw, status);
+        switch (pw.world) {
+        case 2: peer_stage<2>(pw, A, rhs, P0, base_rhs, add_tail, P, ld); break;
+        case 4: peer_stage<4>(pw, A, rhs, P0, base_rhs, add_tail, P, ld); break;
+        case 8: peer_stage<8>(pw, A, rhs, P0, base_rhs, add_tail, P, ld); break;
+        default: peer_stage<0>(pw, A, rhs, P0, base_rhs, add_tail, P, ld); break;
+        }
+        __syncthreads();
+        cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status);
+        return;
+    }
     // stage PP = Gram + P0 (batched loads: four columns in flight per thread)
     for (int col0 = 0; col0 < P; col0 += 16) {
         double g[4], q[4];
@@ -160,6 +206,8 @@ struct Sweep {
     int nt = 1, nslab = 1, xtv_slabs = 1;
     bool use_smem = true;
     size_t beta_smem = 0;
+    bool exchange = false;  // sharded sweep: the Gram (+ tail) sums are exchanged between ranks before the beta draw
+    PeerWait pending{};     // set by gram() when it pushed to the peers; consumed by beta_draw()
 
     int init(DevMem &m, std::string &err)
     {
@@ -197,15 +245,34 @@ struct Sweep {
         count_launch();
     }
 
-    // acc[0..P^2) <- sum_i w_i x_i x_i'  (local shard)
-    void gram(const double *wv)
+    // acc[0..P^2) <- sum_i w_i x_i x_i'  (local shard).  Sharded sweeps with the peer windows open:
+    // the reduce kernel stores the sums (and, with_tail, the P sums xtv() left in acc[P^2..]) into
+    // every rank's window instead, and beta_draw() picks them up there -- call xtv() before gram().
+    void gram(const double *wv, bool with_tail = false)
     {
         int tiles = nt * (nt + 1) / 2;
         if (nt > 1)
             k_gram_partial<kGramRows, false><<<dim3(nslab, tiles), 256, gram_smem_bytes(true), st>>>(part, tX, wv, N, P, nt);
         else
             k_gram_partial<kGramRowsDiag, true><<<dim3(nslab, tiles), 256, gram_smem_bytes(false), st>>>(part, tX, wv, N, P, nt);
-        k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nt > 1 ? 2 * nslab : nslab);
+        PeerPush px{};
+        pending = PeerWait{};
+        if (exchange && peer_active()) {
+            const unsigned e = ++g_peer.epoch;
+            const int par = (int)(e & 1u), me = g_nccl.rank;
+            px.world = pending.world = g_nccl.world;
+            px.epoch = pending.epoch = e;
+            px.done = g_peer.done;
+            px.tail = with_tail ? acc + (size_t)P * P : nullptr;
+            for (int r = 0; r < g_nccl.world; ++r) {
+                char *w = (char *)g_peer.win[r];
+                px.flag[r] = (unsigned *)w + par * kMaxPeers + me;
+                px.slot[r] = (double *)(w + kPeerFlagBytes) + ((size_t)par * kMaxPeers + me) * g_peer.slot_doubles;
+                pending.slot[r] = (const double *)((char *)g_peer.base + kPeerFlagBytes) + ((size_t)par * kMaxPeers + r) * g_peer.slot_doubles;
+            }
+            pending.flag = (const unsigned *)g_peer.base + par * kMaxPeers;
+        }
+        k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nt > 1 ? 2 * nslab : nslab, px);
         count_launch(2);
     }
 
@@ -221,6 +288,7 @@ struct Sweep {
     int allreduce(bool with_tail, std::string &err)
     {
         if (g_nccl.world <= 1 || !g_nccl.comm) return 0;
+        if (pending.world > 1) return 0;          // already pushed through the peer windows by gram()
         size_t cnt = (size_t)P * P + (with_tail ? P : 0);
         int r = g_nccl.AllReduce(acc, acc, cnt, kNcclFloat64, kNcclSum, g_nccl.comm, st);
         if (r != 0) { err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return 1; }
@@ -232,10 +300,11 @@ struct Sweep {
     {
         if (use_smem)
             k_beta_draw<true><<<1, 256, beta_smem, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
-                                                         beta_out, gwork, P, seed, call, status);
+                                                         beta_out, gwork, P, seed, call, status, pending, 0);
         else
             k_beta_draw<false><<<1, 256, 0, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
-                                                  beta_out, gwork, P, seed, call, status);
+                                                  beta_out, gwork, P, seed, call, status, pending, 0);
+        pending = PeerWait{};
         count_launch();
     }
 
@@ -244,6 +313,7 @@ struct Sweep {
         int h = 0;
         GB_CK(cudaMemcpyAsync(&h, status, sizeof(int), cudaMemcpyDeviceToHost, st));
         GB_CK(cudaStreamSynchronize(st));
+        if (h == 2) { err = std::string(what) + ": peer exchange timed out (a rank did not arrive)"; return 1; }
         if (h != 0) { err = std::string(what) + ": posterior precision is not positive definite"; return 1; }
         return 0;
     }
@@ -265,7 +335,7 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
     DevMem mem;
     mem.st = st;
     Sweep s;
-    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX;
+    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX; s.exchange = true;
     if (s.init(mem, err)) return 1;
     double *kappa, *b0, *bP;
     int *shape;
@@ -332,6 +402,103 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
 }
 
 // ------------------------------------------------------------------------------------
+// A batch of independent binary / binomial logit chains (BASELINE config 5: 4096 chains of
+// N = 10k, P = 32; SURVEY.md section 8e "independent chains").  Chain c owns rows [c N, (c+1) N)
+// of tX / y / n, shares the prior, and is exactly the chain logit_gibbs_device runs on its rows
+// with seed + c (same streams, same slot semantics); every kernel of the sweep is launched once
+// for the whole batch with the chain as a grid dimension, so the one-CTA beta draws of the chains
+// run side by side instead of sitting on each chain's critical path.  omega is not returned.
+// beta_out: [chains][samp][P].
+// ------------------------------------------------------------------------------------
+int logit_chains_device(double *beta_out, const double *y, const double *tX, const double *n,
+                        const double *m0, const double *P0, int chains, int64_t N, int P, int samp, int burn,
+                        uint64_t seed, int flags, cudaStream_t st, std::string &err)
+{
+    if (chains <= 0 || N <= 0 || P <= 0 || samp <= 0 || burn < 0) { err = "logit_chains: bad dimensions"; return 1; }
+    const int64_t T = (int64_t)chains * N;
+    if (T >= (1LL << 31)) { err = "logit_chains: chains * N must stay below 2^31 observations per call"; return 1; }
+    if (P > 256) { err = "P > 256 covariates is not supported by the single-CTA beta draw"; return 1; }
+    const size_t beta_smem = (2 * (size_t)(P | 1) * P + 5 * (size_t)P) * sizeof(double);
+    if (beta_smem > 200 * 1024) { err = "logit_chains: P too large for the shared-memory beta draw"; return 1; }
+    DevMem mem;
+    mem.st = st;
+    const int nt = cdiv(P, kGramTile), tiles = nt * (nt + 1) / 2;
+    int nslab = (int)std::min<int64_t>(std::max<int64_t>(1, cdiv(148 * 2, (int64_t)tiles * chains)),
+                                       std::max<int64_t>(1, N / (4 * kGramRows)));
+    const int slabs_total = nt > 1 ? 2 * nslab : nslab;
+    const size_t accn = (size_t)P * P + P;
+    double *psi, *w, *kappa, *acc, *part, *xtv_part, *b0, *bP;
+    int *shape, *status;
+    void *work;
+    GB_CK(mem.get(&psi, T));
+    GB_CK(mem.get(&w, T));
+    GB_CK(mem.get(&kappa, T));
+    GB_CK(mem.get(&shape, T));
+    GB_CK(mem.get(&acc, accn * chains));
+    GB_CK(mem.get(&part, (size_t)chains * tiles * slabs_total * kGramTile * kGramTile));
+    GB_CK(mem.get(&xtv_part, (size_t)chains * P));
+    GB_CK(mem.get(&b0, P));
+    GB_CK(mem.get(&bP, (size_t)chains * P));
+    GB_CK(mem.get(&status, 1));
+    GB_CK(mem.get((char **)&work, (32 + (size_t)T) * sizeof(int)));      // branch-class binning of the draw: [meta][index list]
+    GB_CK(cudaMemsetAsync(status, 0, sizeof(int), st));
+    GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRows, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)gram_smem_bytes(true)));
+    GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRowsDiag, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)gram_smem_bytes(false)));
+    if (beta_smem > 48 * 1024)
+        GB_CK(cudaFuncSetAttribute(k_beta_draw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem));
+    const int mode = (flags & BL_GIBBS_PLAIN_BETA) ? kBetaPlain : kBetaConstrained;
+    const int64_t bstride = (int64_t)P * samp;
+
+    // bP_c = P0 m0 + X_c'(n (y - 1/2))
+    k_kappa<<<cdiv(T, 256), 256, 0, st>>>(kappa, y, n, 0.0, T);
+    k_shape_int<<<cdiv(T, 256), 256, 0, st>>>(shape, n, T);
+    k_matvec<<<cdiv(P, 128), 128, 0, st>>>(b0, P0, m0, P);
+    k_xtv_partial<<<dim3(1, chains), 256, 8 * P * sizeof(double), st>>>(xtv_part, tX, kappa, 1.0, nullptr, nullptr, 0.0, N, P);
+    k_xtv_reduce<<<dim3(cdiv(P, 128), chains), 128, 0, st>>>(bP, b0, nullptr, xtv_part, P, 1);
+    count_launch(5);
+    GB_CK(cudaMemsetAsync(beta_out, 0, sizeof(double) * (size_t)bstride * chains, st));
+
+    auto xbeta = [&](const double *beta) {
+        const int64_t trips = (int64_t)chains * ((N + 31) / 32);
+        int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (trips + 7) / 8));
+        k_xbeta_chains<<<grid, 256, 0, st>>>(psi, tX, beta, bstride, chains, (int)N, P);
+        count_launch();
+    };
+    uint32_t t = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        int iters = phase == 0 ? burn : samp;
+        double *bcur = beta_out, *bprev = beta_out;
+        xbeta(bcur);
+        for (int m = 1; m <= iters; ++m, ++t) {
+            StreamId id{seed, 0, t, (uint32_t)N};
+            cudaError_t e = launch_devroye_refill(w, shape, psi, T, id, st, work);
+            if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
+            if (nt > 1)
+                k_gram_partial<kGramRows, false><<<dim3(nslab, tiles, chains), 256, gram_smem_bytes(true), st>>>(part, tX, w, N, P, nt);
+            else
+                k_gram_partial<kGramRowsDiag, true><<<dim3(nslab, tiles, chains), 256, gram_smem_bytes(false), st>>>(part, tX, w, N, P, nt);
+            k_gram_reduce<<<dim3(cdiv((int64_t)P * P, 32), chains), 256, 0, st>>>(acc, nullptr, part, P, nt, slabs_total, PeerPush{});
+            k_beta_draw<true><<<chains, 256, beta_smem, st>>>(mode, acc, P0, bP, 0, bprev, bcur, nullptr, P, seed, t, status,
+                                                           PeerWait{}, bstride);
+            count_launch(3);
+            xbeta(bcur);
+            if (phase == 1) {
+                bprev = bcur;
+                if (m < iters) bcur += P;
+            }
+        }
+    }
+    GB_CK(cudaGetLastError());
+    int h = 0;
+    GB_CK(cudaMemcpyAsync(&h, status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GB_CK(cudaStreamSynchronize(st));
+    if (h != 0) { err = "logit_chains: a chain's posterior precision is not positive definite"; return 1; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
 // Multinomial logit (MultLogit::gibbs, MultLogit.hpp:261-372)
 // ------------------------------------------------------------------------------------
 // w_out: N x (J-1) x samp (or null), beta_out: P x (J-1) x samp, ty: (J-1) x N,
@@ -346,7 +513,7 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
     DevMem mem;
     mem.st = st;
     Sweep s;
-    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX;
+    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX; s.exchange = true;
     if (s.init(mem, err)) return 1;
     double *Z, *b0, *XB, *cj, *eta, *yj, *base;
     int *shape;
@@ -389,8 +556,8 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
             double *wj = wS ? wS + (size_t)N * j : s.w;
             cudaError_t e = launch_devroye_refill(wj, shape, eta, N, StreamId{seed, obs0, call}, st);
             if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
-            s.gram(wj);
             s.xtv(nullptr, 0.0, wj, cj, 1.0);              // X' Omega c_j
+            s.gram(wj, true);
             if (s.allreduce(true, err)) return 1;
             s.beta_draw(kBetaMvn, P0 + (size_t)P * P * j, base + (size_t)P * j, true, nullptr,
                         bS + (size_t)P * j, seed, call);
@@ -413,7 +580,7 @@ int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const doub
     DevMem mem;
     mem.st = st;
     Sweep s;
-    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX;
+    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX; s.exchange = true;
     if (s.init(mem, err)) return 1;
     double *kappa, *b0, *shape, *beta0;
     void *work;
@@ -437,8 +604,8 @@ int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const doub
             ? launch_hybrid_binned(w, shape, s.psi, (int)N, id, work, st)
             : launch_rpg(kHybrid, w, shape, s.psi, N, 0, nullptr, id, st);
         if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
-        s.gram(w);
         s.xtv(kappa, 1.0, w, nullptr, ld);                                     // X'(kappa + omega log d)
+        s.gram(w, true);
         if (s.allreduce(true, err)) return 1;
         s.beta_draw(kBetaPlain, P0, b0, true, nullptr, beta_out + (size_t)P * t, seed, (uint32_t)t);
     }
@@ -640,8 +807,58 @@ int comm_init(const void *id128, int rank, int world, std::string &err)
     return 0;
 }
 
+// Allocate (once) and zero this rank's window; out64 receives its CUDA IPC handle.
+int comm_peer_handle(void *out64, std::string &err)
+{
+    if (g_nccl.world <= 1) { err = "peer windows need a communicator of more than one rank (bl_comm_init first)"; return 1; }
+    if (g_nccl.world > kMaxPeers) { err = "peer windows support at most 8 ranks"; return 1; }
+    if (!g_peer.base) {
+        g_peer.slot_doubles = (size_t)kPeerMaxP * kPeerMaxP + kPeerMaxP;
+        size_t bytes = kPeerFlagBytes + 2 * (size_t)kMaxPeers * g_peer.slot_doubles * sizeof(double);
+        GB_CK(cudaMalloc(&g_peer.base, bytes));
+        GB_CK(cudaMalloc((void **)&g_peer.done, sizeof(unsigned)));
+        GB_CK(cudaMemset(g_peer.base, 0, bytes));
+        GB_CK(cudaMemset(g_peer.done, 0, sizeof(unsigned)));
+        GB_CK(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    GB_CK(cudaIpcGetMemHandle(&h, g_peer.base));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(out64, &h, 64);
+    return 0;
+}
+
+// handles: world x 64 bytes, rank order (every rank's comm_peer_handle output, all-gathered by the host).
+int comm_peer_open(const void *handles, std::string &err)
+{
+    if (!g_peer.base) { err = "bl_comm_peer_handle has not been called"; return 1; }
+    for (int r = 0; r < g_nccl.world; ++r) {
+        if (r == g_nccl.rank) { g_peer.win[r] = g_peer.base; continue; }
+        if (g_peer.win[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)r, 64);
+        GB_CK(cudaIpcOpenMemHandle(&g_peer.win[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    g_peer.open = true;
+    return 0;
+}
+
+void comm_peer_close()
+{
+    for (int r = 0; r < kMaxPeers; ++r) {
+        if (g_peer.win[r] && g_peer.win[r] != g_peer.base) cudaIpcCloseMemHandle(g_peer.win[r]);
+        g_peer.win[r] = nullptr;
+    }
+    g_peer.open = false;
+}
+
+int comm_peer_active() { return peer_active() ? 1 : 0; }
+
 void comm_destroy()
 {
+    comm_peer_close();
+    if (g_peer.base) { cudaDeviceSynchronize(); cudaFree(g_peer.base); cudaFree(g_peer.done); g_peer.base = nullptr; g_peer.done = nullptr; }
+    g_peer.epoch = 0;
     if (g_nccl.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g_nccl.comm);
     g_nccl.comm = nullptr;
     g_nccl.world = 1;

@@ -75,6 +75,52 @@ k_xbeta(double *__restrict__ psi, const double *__restrict__ tX, const double *_
     }
 }
 
+// The same for a batch of independent chains: rows [c N, (c+1) N) belong to chain c and meet
+// beta_c = beta[c * beta_stride ..).  Trips of 32 rows never straddle two chains.
+__global__ void __launch_bounds__(256, 2)
+k_xbeta_chains(double *__restrict__ psi, const double *__restrict__ tX, const double *__restrict__ beta,
+               int64_t beta_stride, int chains, int N, int P)
+{
+    const int lane = threadIdx.x & 31;
+    const int tpc = (N + 31) >> 5;                                   // trips per chain
+    const int64_t trips = (int64_t)chains * tpc;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (int64_t trip = wid; trip < trips; trip += warps) {
+        const int ch = (int)(trip / tpc);
+        const int i0 = (int)(trip - (int64_t)ch * tpc) << 5;
+        const double *bc = beta + ch * beta_stride;
+        const double *base = tX + ((size_t)ch * N + i0) * P;
+        double acc[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) acc[r] = 0.0;
+        const bool whole = i0 + 32 <= N;
+        for (int p = lane; p < P; p += 32) {
+            const double bp = __ldg(bc + p);
+            const double *col = base + p;
+            if (whole) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) acc[r] = fma(__ldg(col + (int64_t)r * P), bp, acc[r]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 32; ++r)
+                    if (i0 + r < N) acc[r] = fma(__ldg(col + (int64_t)r * P), bp, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int k = 0; k < o; ++k) {
+                double send = up ? acc[k] : acc[k + o];
+                double keep = up ? acc[k + o] : acc[k];
+                acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+        }
+        if (i0 + lane < N) psi[(size_t)ch * N + i0 + lane] = acc[0];
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // Weighted Gram, SYRK-shaped: G = sum_i w_i x_i x_i' over a slab of rows.
 //
@@ -188,6 +234,10 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
 {
     extern __shared__ __align__(16) double gsm[];
     const int nthr = blockDim.x;
+    // batched independent chains: blockIdx.z = chain (its own rows, weights and partial tiles)
+    tX += (size_t)blockIdx.z * N * P;
+    w += (size_t)blockIdx.z * N;
+    part += (size_t)blockIdx.z * gridDim.y * gridDim.x * (kBalancedDiag ? 1 : 2) * (kGramTile * kGramTile);
     int t = blockIdx.y, bi = 0;
     while (t >= nt - bi) { t -= nt - bi; ++bi; }
     const int bj = bi + t;
@@ -328,15 +378,145 @@ inline size_t gram_smem_bytes(bool any_offdiag)
     return (size_t)kGramStages * ((any_offdiag ? 2 : 1) * rows * kGramLdm + rows) * sizeof(double);
 }
 
+// ---------------------------------------------------------------------------------
+// Peer exchange (see the window layout in gibbs.cu).  PeerPush travels with the kernel that
+// produces the sums, PeerWait with the kernel that consumes them.
+// ---------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+
+struct PeerPush {
+    double *slot[kMaxPeers];      // slot [parity][my rank] inside every rank's window
+    unsigned *flag[kMaxPeers];    // flag [parity][my rank] inside every rank's window
+    unsigned *done;               // local CTA counter (zero between launches)
+    const double *tail;           // optional P extra sums appended after the P^2 (already reduced), or null
+    unsigned epoch;
+    int world;                    // <= 1: no exchange
+};
+
+struct PeerWait {
+    const double *slot[kMaxPeers];   // slot [parity][r] of the LOCAL window
+    const unsigned *flag;            // flags [parity][0..world) of the local window
+    unsigned epoch;
+    int world;                       // <= 1: no exchange
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    return t;
+}
+
+// Called by every thread of every CTA of the pushing kernel after its stores to the peers'
+// slots: the last CTA to arrive raises this rank's flag in every window.  One system-scope fence
+// per CTA (thread 0, after the CTA barrier: fences are cumulative over the stores the barrier
+// ordered before it), not one per thread.
+__device__ __forceinline__ void peer_publish(const PeerPush &px)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();             // the CTA's slot stores are performed system-wide
+        unsigned prev = atomicAdd(px.done, 1u);
+        if (prev == gridDim.x * gridDim.y - 1) {
+            *px.done = 0;                   // next launch on this stream starts from zero
+            __threadfence_system();
+            for (int r = 0; r < px.world; ++r) st_release_sys(px.flag[r], px.epoch);
+        }
+    }
+}
+
+// One CTA waits until every rank's flag has reached the epoch (flags only grow).  A peer that
+// never arrives (crashed rank) turns into status 2 after 20 s instead of a hung GPU.
+__device__ __forceinline__ void peer_wait(const PeerWait &pw, int *status)
+{
+    if ((int)threadIdx.x < pw.world) {
+        const unsigned long long t0 = global_timer_ns();
+        while ((int)(ld_acquire_sys(pw.flag + threadIdx.x) - pw.epoch) < 0) {
+            if (global_timer_ns() - t0 > 20000000000ull) { *status = 2; break; }
+            __nanosleep(40);
+        }
+    }
+    __syncthreads();
+}
+
+// A (ld x P, column-major) = P0 + sum_r slot_r[0..P^2), rhs = base_rhs + sum_r slot_r[P^2..P^2+P),
+// ranks added in index order (identical bits on every rank).  Slot loads bypass L1 (.cg): the
+// lines were written by other GPUs.  W = 0: world known only at run time.
+template <int W>
+__device__ __forceinline__ void peer_stage(const PeerWait &pw, double *A, double *rhs,
+                                           const double *__restrict__ P0, const double *__restrict__ base_rhs,
+                                           int add_tail, int P, int ld)
+{
+    constexpr int WW = W ? W : kMaxPeers;
+    const int world = W ? W : pw.world;
+    const int PP = P * P;
+    if ((P & 1) == 0) {
+        // pairs (k, k+1) share a column; two pairs per thread per trip -> 2 W 16-byte loads in flight
+        const int H = PP >> 1;
+        for (int h0 = threadIdx.x; h0 < H; h0 += 2 * blockDim.x) {
+            const int h1 = h0 + blockDim.x;
+            const bool v1 = h1 < H;
+            double2 x0[WW], x1[WW];
+#pragma unroll
+            for (int r = 0; r < WW; ++r) {
+                x0[r] = r < world ? __ldcg(reinterpret_cast<const double2 *>(pw.slot[r]) + h0) : make_double2(0.0, 0.0);
+                x1[r] = (r < world && v1) ? __ldcg(reinterpret_cast<const double2 *>(pw.slot[r]) + h1) : make_double2(0.0, 0.0);
+            }
+            // P0 is caller memory (8-byte alignment only)
+            double2 q0 = P0 ? make_double2(P0[2 * h0], P0[2 * h0 + 1]) : make_double2(0.0, 0.0);
+            double2 q1 = (P0 && v1) ? make_double2(P0[2 * h1], P0[2 * h1 + 1]) : make_double2(0.0, 0.0);
+            double2 s0 = x0[0], s1 = x1[0];
+#pragma unroll
+            for (int r = 1; r < WW; ++r)
+                if (r < world) { s0.x += x0[r].x; s0.y += x0[r].y; s1.x += x1[r].x; s1.y += x1[r].y; }
+            int k = 2 * h0;
+            double *d = A + k % P + (size_t)ld * (k / P);
+            d[0] = s0.x + q0.x; d[1] = s0.y + q0.y;
+            if (v1) {
+                k = 2 * h1;
+                d = A + k % P + (size_t)ld * (k / P);
+                d[0] = s1.x + q1.x; d[1] = s1.y + q1.y;
+            }
+        }
+    } else {
+        for (int k = threadIdx.x; k < PP; k += blockDim.x) {
+            double s = __ldcg(pw.slot[0] + k);
+            for (int r = 1; r < world; ++r) s += __ldcg(pw.slot[r] + k);
+            A[k % P + (size_t)ld * (k / P)] = s + (P0 ? P0[k] : 0.0);
+        }
+    }
+    for (int k = threadIdx.x; k < P; k += blockDim.x) {
+        double t = 0.0;
+        if (add_tail) {
+            t = __ldcg(pw.slot[0] + PP + k);
+            for (int r = 1; r < world; ++r) t += __ldcg(pw.slot[r] + PP + k);
+        }
+        rhs[k] = (base_rhs ? base_rhs[k] : 0.0) + t;
+    }
+}
+
 // PP = P0 + sum over slabs of the partial tiles, mirrored to a full symmetric P x P
 // column-major matrix.  One warp-row of threads per output element group: each CTA owns
 // 32 upper-triangle candidates, its 8 warps split the slabs, fixed summation order.
 __global__ void __launch_bounds__(256)
 k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
-              const double *__restrict__ part, int P, int nt, int nslab)
+              const double *__restrict__ part, int P, int nt, int nslab, PeerPush px)
 {
     __shared__ double red[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // batched independent chains: blockIdx.y = chain
+    PP += (size_t)blockIdx.y * ((size_t)P * P + P);
+    part += (size_t)blockIdx.y * (nt * (nt + 1) / 2) * nslab * (kGramTile * kGramTile);
     int e = blockIdx.x * 32 + lane;
     int a = e % P, b = e / P;
     bool want = e < P * P && a <= b;
@@ -358,8 +538,24 @@ k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
         double v = 0.0;
         for (int k = 0; k < 8; ++k) v += red[k][lane];
         v += P0 ? P0[a + (size_t)P * b] : 0.0;
-        PP[a + (size_t)P * b] = v;
-        PP[b + (size_t)P * a] = v;
+        if (px.world > 1) {
+            // sharded data: the sums go straight into every rank's window (NVLink stores)
+            for (int r = 0; r < px.world; ++r) {
+                px.slot[r][a + (size_t)P * b] = v;
+                px.slot[r][b + (size_t)P * a] = v;
+            }
+        } else {
+            PP[a + (size_t)P * b] = v;
+            PP[b + (size_t)P * a] = v;
+        }
+    }
+    if (px.world > 1) {
+        if (blockIdx.x == 0 && px.tail)
+            for (int k = threadIdx.x; k < P; k += blockDim.x) {
+                double t = px.tail[k];
+                for (int r = 0; r < px.world; ++r) px.slot[r][(size_t)P * P + k] = t;
+            }
+        peer_publish(px);
     }
 }
 
@@ -371,6 +567,12 @@ k_xtv_partial(double *__restrict__ part, const double *__restrict__ tX, const do
               int64_t N, int P, const double *__restrict__ c1_dev = nullptr)
 {
     if (c1_dev) c1 = *c1_dev;                  // coefficient produced on the device (NB: log d)
+    // batched independent chains: blockIdx.y = chain
+    tX += (size_t)blockIdx.y * N * P;
+    part += (size_t)blockIdx.y * gridDim.x * P;
+    if (v0) v0 += (size_t)blockIdx.y * N;
+    if (v1) v1 += (size_t)blockIdx.y * N;
+    if (v2) v2 += (size_t)blockIdx.y * N;
     extern __shared__ double sacc[];   // [warps][P]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int p = threadIdx.x; p < nw * P; p += blockDim.x) sacc[p] = 0.0;
@@ -400,6 +602,10 @@ __global__ void k_xtv_reduce(double *__restrict__ out, const double *__restrict_
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
+    // batched independent chains: blockIdx.y = chain (add0 is shared by the chains, add1 is not)
+    out += (size_t)blockIdx.y * P;
+    part += (size_t)blockIdx.y * nslab * P;
+    if (add1) add1 += (size_t)blockIdx.y * P;
     double s = 0.0;
     for (int k = 0; k < nslab; ++k) s += part[(size_t)k * P + p];
     out[p] = s + (add0 ? add0[p] : 0.0) + (add1 ? add1[p] : 0.0);

@@ -113,7 +113,12 @@ k_devroye_refill(double *__restrict__ x, const int *__restrict__ n, const double
                     remaining = ni < 1 ? 1 : ni;      // NTHROW clamp, PolyaGamma.cpp:128-135
                     sum = 0.0;
                     st = dev_setup(z[cand]);
-                    src.open(id.seed, id.obs0 + (uint64_t)cand, id.call_id);
+                    if (id.chain_len) {
+                        const uint32_t ch = (uint32_t)cand / id.chain_len;
+                        src.open(id.seed + ch, id.obs0 + ((uint32_t)cand - ch * id.chain_len), id.call_id);
+                    } else {
+                        src.open(id.seed, id.obs0 + (uint64_t)cand, id.call_id);
+                    }
                     active = true;
                 }
             }

@@ -195,6 +195,23 @@ def logit_gibbs(y, X, n, m0, P0, samp, burn, seed, flags=0, keep_w=True):
     return w, beta
 
 
+def logit_chains(y, X, n, m0, P0, samp, burn, seed, flags=0):
+    """A batch of independent chains sharing the prior: y, n [chains x N], X [chains x N x P].
+    Chain c is the chain logit_gibbs(y[c], X[c], n[c], ..., seed=seed + c) runs; all chains advance
+    together, one launch per kernel per iteration for the whole batch.  Returns beta [chains x samp x P]."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    chains, N, P = X.shape
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(chains, N)
+    n = np.ascontiguousarray(n, dtype=np.float64).reshape(chains, N)
+    m0 = _f(m0).ravel()
+    P0c = np.asfortranarray(_f(P0))
+    beta = np.zeros((chains, samp, P))
+    st = _lib.lib().bl_logit_chains(_p(beta), _p(y), _p(X), _p(n), _p(m0), P0c.ctypes.data, chains, N, P,
+                                    samp, burn, int(seed), int(flags))
+    _lib.check(st)
+    return beta
+
+
 def mlogit_gibbs(y, X, n, m0, P0, samp, burn, seed, flags=0, keep_w=True):
     """y: N x (J-1) proportions.  Returns (w [samp x (J-1) x N] or None, beta [samp x (J-1) x P])."""
     X = np.ascontiguousarray(X, dtype=np.float64)

@@ -200,11 +200,36 @@ int bl_nb_gibbs_df_dev(double *w_last, double *beta, double *d_out, const double
                        const double *m0, const double *P0, int64_t N, int P, int samp, int burn, uint64_t seed,
                        uint64_t obs0, void *stream);
 
+/* A batch of independent logit chains (BASELINE config 5; no reference C symbol: the reference
+ * would call gibbs() once per chain).  Chain c owns rows [c*N, (c+1)*N) of y, n (length chains*N)
+ * and tX (P x chains*N), shares m0 / P0, and is the chain bl_logit_gibbs runs on those rows with
+ * seed + c.  beta: [chains][samp][P] (chain c's P x samp block is what gibbs() would return);
+ * omega is not returned.  flags: BL_GIBBS_PLAIN_BETA or 0 (the reference's constrained draw).
+ * Block-distribute the chains over GPUs by calling with seed + first chain of the block. */
+int bl_logit_chains(double *beta, const double *y, const double *tX, const double *n, const double *m0,
+                    const double *P0, int chains, int N, int P, int samp, int burn, uint64_t seed, int flags);
+int bl_logit_chains_dev(double *beta, const double *y, const double *tX, const double *n, const double *m0,
+                        const double *P0, int chains, int64_t N, int P, int samp, int burn, uint64_t seed,
+                        int flags, void *stream);
+
 /* Communicator over NCCL (NVLink/NVSwitch): rank 0 creates a 128-byte id, the host side
  * broadcasts it (e.g. torch.distributed), every rank calls bl_comm_init. */
 int bl_comm_unique_id(void *out128);
 int bl_comm_init(const void *id128, int rank, int world);
 int bl_comm_destroy(void);
+
+/* Peer windows (ranks on one NVLink/NVSwitch node, at most 8): with them open, the sharded sweeps
+ * exchange the P*P + P sums of each beta draw through one fused kernel pair instead of
+ * ncclAllReduce -- the Gram reduce kernel stores its sums into every rank's window over NVLink and
+ * the beta-draw kernel adds the windows' slots in rank order (bit-identical on every rank).
+ * After bl_comm_init: every rank calls bl_comm_peer_handle (64-byte CUDA IPC handle of its
+ * window), the host all-gathers the handles in rank order, every rank calls bl_comm_peer_open
+ * with the world*64 bytes.  All ranks must open (or none): bl_comm_peer_close on failure anywhere.
+ * bl_comm_peer_active() != 0 when the sweeps will use the windows. */
+int bl_comm_peer_handle(void *out64);
+int bl_comm_peer_open(const void *handles);
+int bl_comm_peer_close(void);
+int bl_comm_peer_active(void);
 
 /* Component probes for parity tests (host pointers, elementwise). */
 int bl_probe_pg_moments(double *m1, double *m2, const double *b, const double *z, int64_t num);

@@ -73,6 +73,29 @@ def test_logit_burn_zero_and_no_w(gapi):
     assert w2 is None and np.array_equal(b2, b)
 
 
+@pytest.mark.parametrize("constrained", [False, True])
+@pytest.mark.parametrize("chains,N,P", [(7, 900, 5), (3, 2100, 32), (2, 515, 70)])
+def test_batched_chains_match_oracle_chain_by_chain(gapi, constrained, chains, N, P):
+    """BASELINE config 5 (independent chains) at oracle-sized shapes: chain c
+    of the batch equals the oracle's chain on its rows with seed + c, and the engine's own
+    single-chain entry point with that seed.  N not a multiple of 32 and P > 64 (several Gram
+    tiles) are covered."""
+    data = [synth_logit(N, P, 100 + 7 * c + P, binomial=(c % 2 == 1)) for c in range(chains)]
+    X = np.stack([d[0] for d in data]); y = np.stack([d[1] for d in data]); n = np.stack([d[2] for d in data])
+    m0 = np.linspace(-0.1, 0.1, P)
+    P0 = 0.5 * np.eye(P) + 0.01
+    samp, burn = (8, 4) if P < 64 else (4, 2)
+    flags = 0 if constrained else gapi.PLAIN_BETA
+    b = gapi.logit_chains(y, X, n, m0, P0, samp, burn, seed=500, flags=flags)
+    assert b.shape == (chains, samp, P)
+    for c in range(chains):
+        _, bo = loader.logit_gibbs(y[c], X[c], n[c], m0, P0, samp, burn, seed=500 + c, constrained=constrained)
+        close(b[c], bo)
+        _, b1 = gapi.logit_gibbs(y[c], X[c], n[c], m0, P0, samp, burn, seed=500 + c, flags=flags, keep_w=False)
+        close(b[c], b1)
+    assert not np.allclose(b[0], b[1][:, :P])          # different data and streams: different chains
+
+
 def test_mlogit_chain_matches_oracle(gapi):
     rng = np.random.default_rng(4)
     N, P, J = 2500, 6, 4

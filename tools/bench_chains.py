@@ -1,0 +1,90 @@
+#!/usr/bin/env python3
+"""Independent logit chains, BASELINE config 5b: 4096 chains of N = 10k, P = 32 (per GPU block of
+the chains when run under torchrun: chains are block-distributed, no communication).
+
+    python tools/bench_chains.py [--chains 4096 --N 10000 --P 32 --iters 20 --constrained]
+
+Prints one JSON line: chain-iterations/s through the batched entry point (bl_logit_chains_dev), and
+for comparison the same chains advanced one after the other through bl_logit_gibbs_dev (a sample).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--chains", type=int, default=4096)
+    ap.add_argument("--N", type=int, default=10_000)
+    ap.add_argument("--P", type=int, default=32)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--constrained", action="store_true")
+    ap.add_argument("--serial-sample", type=int, default=16)
+    a = ap.parse_args()
+    import torch
+    from bayeslogit_b200 import _lib
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L = _lib.lib()
+    _lib.check(L.bl_set_device(local))
+    C = a.chains // world
+    c0 = rank * C
+    N, P = a.N, a.P
+    g = torch.Generator(device=dev); g.manual_seed(20240006 + c0)
+    X = torch.randn(C, N, P, generator=g, device=dev, dtype=torch.float64)
+    X[:, :, P - 1] = 1.0
+    bt = torch.randn(C, P, generator=g, device=dev, dtype=torch.float64).abs() * 0.25
+    bt[:, P - 1] = -0.5
+    y = (torch.rand(C, N, generator=g, device=dev, dtype=torch.float64) < torch.sigmoid(torch.einsum("cnp,cp->cn", X, bt))).double()
+    n = torch.ones(C, N, device=dev, dtype=torch.float64)
+    m0 = torch.zeros(P, device=dev, dtype=torch.float64)
+    P0 = (0.01 * torch.eye(P, device=dev, dtype=torch.float64)).contiguous()
+    flags = 0 if a.constrained else 1
+    st = torch.cuda.current_stream().cuda_stream
+
+    def batch(k):
+        beta = torch.zeros(C, k, P, device=dev, dtype=torch.float64)
+        rc = L.bl_logit_chains_dev(beta.data_ptr(), y.data_ptr(), X.data_ptr(), n.data_ptr(), m0.data_ptr(),
+                                   P0.data_ptr(), C, N, P, k, 0, 20240006 + c0, flags, st)
+        if rc:
+            _lib.check(rc)
+        return beta
+
+    batch(3)
+    torch.cuda.synchronize()
+    l0 = L.bl_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); beta = batch(a.iters); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = L.bl_kernel_launches() - l0
+    # one after the other (the reference's usage: one gibbs() call per chain)
+    S = min(a.serial_sample, C)
+    e0.record()
+    for c in range(S):
+        b1 = torch.zeros(a.iters, P, device=dev, dtype=torch.float64)
+        rc = L.bl_logit_gibbs_dev(None, b1.data_ptr(), y[c].data_ptr(), X[c].data_ptr(), n[c].data_ptr(),
+                                  m0.data_ptr(), P0.data_ptr(), N, P, a.iters, 0, 20240006 + c0 + c, flags | 2, 0, st)
+        if rc:
+            _lib.check(rc)
+    e1.record(); torch.cuda.synchronize()
+    ms1 = e0.elapsed_time(e1)
+    same = float((b1 - beta[S - 1]).abs().max().item())
+    post = beta[:, a.iters // 2:].mean(1)
+    out = {"chain_iters_per_sec": C * a.iters / (ms * 1e-3), "ms_per_iteration_of_all_chains": ms / a.iters,
+           "chains": C, "N": N, "P": P, "iters": a.iters, "launches_per_iteration": launches / a.iters,
+           "beta_draw": "constrained" if a.constrained else "plain",
+           "one_after_the_other_chain_iters_per_sec": S * a.iters / (ms1 * 1e-3), "serial_sample_chains": S,
+           "max_abs_diff_batched_vs_single_entry": same,
+           "rms_err_vs_truth": float((post - bt).pow(2).mean().sqrt().item()), "n_gpus": world, "chain0": c0,
+           "x_bytes": C * N * P * 8}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

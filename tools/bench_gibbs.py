@@ -81,7 +81,9 @@ def run(N, P, iters, warm, constrained, rank, world, local, verify=False):
     launches = L.bl_kernel_launches() - l0
     post = beta[iters // 2:].mean(0)
     return {"iters_per_sec": iters / (ms * 1e-3), "ms_per_iter": ms / iters, "iters": iters, "N": N, "P": P,
-            "n_gpus": world, "beta_draw": "constrained (reference, Logit.hpp:322-400)" if constrained
+            "n_gpus": world, "exchange": ("peer windows (fused in the Gram-reduce / beta-draw kernels)"
+                                          if bdist.peer_exchange_active() else "ncclAllReduce") if world > 1 else None,
+            "beta_draw": "constrained (reference, Logit.hpp:322-400)" if constrained
             else "plain (Logit.hpp:291-320)", "launches_per_iter": launches / iters,
             "max_abs_err_vs_truth": float((post - bt).abs().max().item()),
             "beta_checksum": float(beta.sum().item())}
@@ -109,6 +111,7 @@ def main():
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
+        bdist.destroy_comm()
         dist.destroy_process_group()
 
 

@@ -55,6 +55,63 @@ for f in (0, 1):
     if rank == 0:
         print(f"flags={f}: world={world} max rel diff beta {t[0].item():.2e} omega {t[1].item():.2e}")
     ok = ok and t.max().item() < 1e-8
+
+
+# NB sweep (fixed d): exercises the P extra sums (X'v tail) of the exchange
+yc = rng.poisson(np.exp(np.clip(X @ bt * 0.3 + 2.0, None, 4.0))).astype(float)
+
+
+def nb_chain(lo, hi):
+    Xd = torch.from_numpy(X[lo:hi].copy()).to(dev); yd = torch.from_numpy(yc[lo:hi].copy()).to(dev)
+    m0 = torch.zeros(P, device=dev, dtype=torch.float64)
+    P0 = (0.1 * torch.eye(P, device=dev, dtype=torch.float64)).contiguous()
+    beta = torch.zeros(8, P, device=dev, dtype=torch.float64)
+    w = torch.zeros(hi - lo, device=dev, dtype=torch.float64)
+    rc = L.bl_nb_gibbs_dev(w.data_ptr(), beta.data_ptr(), yd.data_ptr(), Xd.data_ptr(), 5.0,
+                           m0.data_ptr(), P0.data_ptr(), hi - lo, P, 8, 777, lo, st)
+    if rc:
+        _lib.check(rc)
+    torch.cuda.synchronize()
+    return beta.cpu().numpy(), w.cpu().numpy()
+
+
+def compare_nb(tag, ref):
+    b, w = nb_chain(lo, hi)
+    eb = np.max(np.abs(b - ref[0]) / np.abs(ref[0]))
+    ew = np.max(np.abs(w - ref[1][lo:hi]) / ref[1][lo:hi])
+    t = torch.tensor([eb, ew], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"nb {tag}: max rel diff beta {t[0].item():.2e} omega {t[1].item():.2e}")
+    return t.max().item() < 1e-8, b
+
+
+peer = bdist.peer_exchange_active()
+bdist.destroy_comm()
+nb_full = nb_chain(0, N)                      # no communicator: single-GPU chain
+bdist.init_comm(rank, world, dev)
+ok_nb, b_peer = compare_nb("peer windows" if bdist.peer_exchange_active() else "nccl", nb_full)
+ok = ok and ok_nb
+# beta must be bit-identical on every rank (replicated draw from identical sums)
+g = [torch.empty(b_peer.shape, device=dev, dtype=torch.float64) for _ in range(world)]
+dist.all_gather(g, torch.from_numpy(b_peer).to(dev))
+same = all(torch.equal(g[0], x) for x in g)
+if rank == 0:
+    print(f"beta bit-identical across ranks: {same}; peer exchange active: {peer}")
+ok = ok and same
+if peer:
+    # the NCCL path on the same shards
+    bdist.destroy_comm()
+    os.environ["BL_PEER_EXCHANGE"] = "0"
+    bdist.init_comm(rank, world, dev)
+    assert not bdist.peer_exchange_active()
+    ok_nccl, _ = compare_nb("nccl", nb_full)
+    b, w = chain(lo, hi, 1)
+    eb = float(np.max(np.abs(b - full[1][0]) / np.abs(full[1][0])))
+    if rank == 0:
+        print(f"logit nccl: max rel diff beta {eb:.2e}")
+    ok = ok and ok_nccl and eb < 1e-8
 if rank == 0:
     print("MULTI_GPU_OK" if ok else "MULTI_GPU_MISMATCH")
+bdist.destroy_comm()
 dist.destroy_process_group()
