@@ -91,6 +91,16 @@ int ensure_ready()
                     "' is not sm_100 class; this library carries sm_100a code only");
     g.device = dev;
     for (int s = 0; s < kSlots; ++s) BL_CK(cudaStreamCreateWithFlags(&g.slot[s].stream, cudaStreamNonBlocking));
+    {
+        // the sweeps take their scratch from the stream-ordered pool; keep it mapped between calls
+        // (a fresh 2 GB of scratch costs ~0.1-0.2 s to map, every call, with the default threshold 0)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            const char *env = getenv("BAYESLOGIT_POOL_KEEP_MB");
+            uint64_t keep = (env ? strtoull(env, nullptr, 0) : 8192ull) << 20;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (g.seed == 0) {
         const char *env = getenv("BAYESLOGIT_SEED");
         g.seed = env ? strtoull(env, nullptr, 0)

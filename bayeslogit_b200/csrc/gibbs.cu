@@ -232,6 +232,8 @@ struct Sweep {
                                    (int)gram_smem_bytes(true)));
         GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRowsDiag, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)gram_smem_bytes(false)));
+        GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRowsDiag, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)gram_smem_bytes(false, true)));
         use_smem = beta_smem <= 200 * 1024;
         if (use_smem && beta_smem > 48 * 1024)
             GB_CK(cudaFuncSetAttribute(k_beta_draw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem));
@@ -241,7 +243,10 @@ struct Sweep {
     void xbeta(double *out, const double *beta, const double *off, double off_scale, double shift = 0.0)
     {
         int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (N + 255) / 256));
-        k_xbeta<<<grid, 256, P * sizeof(double), st>>>(out, tX, beta, off, off_scale, shift, N, P);
+        if (xbeta_mma_ok(tX, P))
+            k_xbeta_mma<<<grid, 256, 0, st>>>(out, tX, beta, 0, 1, N, P, off, off_scale, shift);
+        else
+            k_xbeta<<<grid, 256, P * sizeof(double), st>>>(out, tX, beta, off, off_scale, shift, N, P);
         count_launch();
     }
 
@@ -251,8 +256,11 @@ struct Sweep {
     void gram(const double *wv, bool with_tail = false)
     {
         int tiles = nt * (nt + 1) / 2;
+        const bool packed = gram_packed(P);
         if (nt > 1)
             k_gram_partial<kGramRows, false><<<dim3(nslab, tiles), 256, gram_smem_bytes(true), st>>>(part, tX, wv, N, P, nt);
+        else if (packed)
+            k_gram_partial<kGramRowsDiag, true, true><<<dim3(nslab, tiles), 256, gram_smem_bytes(false, true), st>>>(part, tX, wv, N, P, nt);
         else
             k_gram_partial<kGramRowsDiag, true><<<dim3(nslab, tiles), 256, gram_smem_bytes(false), st>>>(part, tX, wv, N, P, nt);
         PeerPush px{};
@@ -272,7 +280,7 @@ struct Sweep {
             }
             pending.flag = (const unsigned *)g_peer.base + par * kMaxPeers;
         }
-        k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nt > 1 ? 2 * nslab : nslab, px);
+        k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nt > 1 ? 2 * nslab : nslab, px, packed ? 1 : 0);
         count_launch(2);
     }
 
@@ -446,6 +454,9 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
                                (int)gram_smem_bytes(true)));
     GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRowsDiag, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)gram_smem_bytes(false)));
+    GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRowsDiag, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)gram_smem_bytes(false, true)));
+    const bool packed = gram_packed(P);
     if (beta_smem > 48 * 1024)
         GB_CK(cudaFuncSetAttribute(k_beta_draw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem));
     const int mode = (flags & BL_GIBBS_PLAIN_BETA) ? kBetaPlain : kBetaConstrained;
@@ -463,27 +474,49 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
     auto xbeta = [&](const double *beta) {
         const int64_t trips = (int64_t)chains * ((N + 31) / 32);
         int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (trips + 7) / 8));
-        k_xbeta_chains<<<grid, 256, 0, st>>>(psi, tX, beta, bstride, chains, (int)N, P);
+        if (xbeta_mma_ok(tX, P))
+            k_xbeta_mma<<<grid, 256, 0, st>>>(psi, tX, beta, bstride, chains, N, P, nullptr, 0.0, 0.0);
+        else
+            k_xbeta_chains<<<grid, 256, 0, st>>>(psi, tX, beta, bstride, chains, (int)N, P);
         count_launch();
     };
+    const bool timing = getenv("BL_GIBBS_TIMING") != nullptr;
+    cudaEvent_t ev[6];
+    if (timing) for (auto &x : ev) cudaEventCreate(&x);
     uint32_t t = 0;
     for (int phase = 0; phase < 2; ++phase) {
         int iters = phase == 0 ? burn : samp;
         double *bcur = beta_out, *bprev = beta_out;
         xbeta(bcur);
         for (int m = 1; m <= iters; ++m, ++t) {
+            const bool tm = timing && phase == 1 && m == iters;       // BL_GIBBS_TIMING=1: stage times
+            if (tm) cudaEventRecord(ev[0], st);
             StreamId id{seed, 0, t, (uint32_t)N};
             cudaError_t e = launch_devroye_refill(w, shape, psi, T, id, st, work);
             if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
+            if (tm) cudaEventRecord(ev[1], st);
             if (nt > 1)
                 k_gram_partial<kGramRows, false><<<dim3(nslab, tiles, chains), 256, gram_smem_bytes(true), st>>>(part, tX, w, N, P, nt);
+            else if (packed)
+                k_gram_partial<kGramRowsDiag, true, true><<<dim3(nslab, tiles, chains), 256, gram_smem_bytes(false, true), st>>>(part, tX, w, N, P, nt);
             else
                 k_gram_partial<kGramRowsDiag, true><<<dim3(nslab, tiles, chains), 256, gram_smem_bytes(false), st>>>(part, tX, w, N, P, nt);
-            k_gram_reduce<<<dim3(cdiv((int64_t)P * P, 32), chains), 256, 0, st>>>(acc, nullptr, part, P, nt, slabs_total, PeerPush{});
+            if (tm) cudaEventRecord(ev[2], st);
+            k_gram_reduce<<<dim3(cdiv((int64_t)P * P, 32), chains), 256, 0, st>>>(acc, nullptr, part, P, nt, slabs_total, PeerPush{}, packed ? 1 : 0);
+            if (tm) cudaEventRecord(ev[3], st);
             k_beta_draw<true><<<chains, 256, beta_smem, st>>>(mode, acc, P0, bP, 0, bprev, bcur, nullptr, P, seed, t, status,
                                                            PeerWait{}, bstride);
             count_launch(3);
+            if (tm) cudaEventRecord(ev[4], st);
             xbeta(bcur);
+            if (tm) {
+                cudaEventRecord(ev[5], st);
+                cudaEventSynchronize(ev[5]);
+                float d[5];
+                for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&d[k], ev[k], ev[k + 1]);
+                fprintf(stderr, "[bl chains timing, us] draw %.1f gram %.1f reduce %.1f beta %.1f xbeta %.1f\n",
+                        d[0] * 1e3, d[1] * 1e3, d[2] * 1e3, d[3] * 1e3, d[4] * 1e3);
+            }
             if (phase == 1) {
                 bprev = bcur;
                 if (m < iters) bcur += P;

@@ -170,6 +170,66 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// ---------------------------------------------------------------------------------
+// psi = X beta on the FP64 tensor cores, for even P and 16-byte aligned tX (else k_xbeta).
+// The matrix-vector product is issued as m8n8k4 MMAs whose B operand repeats beta in every column:
+// lane (gid, tig) loads the 16 bytes X[row0 + gid][c0 + 2 tig, +1] (four lanes cover 64 contiguous
+// bytes of a row: full 32-byte sectors) and feeds them as the A fragments of two MMAs against
+// beta[c0 + 2 tig] and beta[c0 + 2 tig + 1]; every column of the 8 x 8 accumulator then holds psi
+// of the 8 rows.  No cross-lane reduction and two accumulator registers per 8 rows, so a warp
+// keeps a whole 32-row trip of loads in flight; the lane-strided k_xbeta spends ~150 of its ~220
+// instructions per trip in the transposing butterfly and idles HBM meanwhile (4.6 TB/s at P = 64,
+// 2.4 TB/s at P = 32).  Chains: rows [c N, (c+1) N) meet beta + c * beta_stride.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+k_xbeta_mma(double *__restrict__ psi, const double *__restrict__ tX, const double *__restrict__ beta,
+            int64_t beta_stride, int chains, int64_t N, int P,
+            const double *__restrict__ off, double off_scale, double shift)
+{
+    const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+    const int64_t tpc = (N + 31) >> 5;                               // 32-row trips per chain
+    const int64_t trips = (int64_t)chains * tpc;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (int64_t trip = wid; trip < trips; trip += warps) {
+        const int64_t ch = chains > 1 ? trip / tpc : 0;
+        const int64_t i0 = (trip - ch * tpc) << 5;
+        const double *bc = beta + ch * beta_stride + 2 * tig;
+        const double *base = tX + ((size_t)ch * N + i0 + gid) * P + 2 * tig;
+        double c[4][2] = {};
+        bool rv[4];
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb) rv[rb] = i0 + 8 * rb + gid < N;
+#pragma unroll 4
+        for (int c0 = 0; c0 < P; c0 += 8) {
+            const bool cv = c0 + 2 * tig < P;
+            double2 a[4];
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb)
+                a[rb] = (cv && rv[rb]) ? __ldg(reinterpret_cast<const double2 *>(base + (size_t)(8 * rb) * P + c0))
+                                       : make_double2(0.0, 0.0);
+            const double b0 = cv ? __ldg(bc + c0) : 0.0, b1 = cv ? __ldg(bc + c0 + 1) : 0.0;
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb) {
+                dmma884(c[rb][0], c[rb][1], a[rb].x, b0);
+                dmma884(c[rb][0], c[rb][1], a[rb].y, b1);
+            }
+        }
+        if (tig == 0) {
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb) {
+                const int64_t i = i0 + 8 * rb + gid;
+                if (i < N) {
+                    const int64_t g = ch * N + i;
+                    psi[g] = (off ? c[rb][0] + off_scale * off[g] : c[rb][0]) + shift;
+                }
+            }
+        }
+    }
+}
+
+inline bool xbeta_mma_ok(const double *tX, int P) { return P % 2 == 0 && (reinterpret_cast<uintptr_t>(tX) & 15) == 0; }
+
 // Weighted Gram on the FP64 tensor cores (DMMA).  A register-tiled DFMA version of this kernel
 // was bound by shared-memory bandwidth (LSU data pipe 75% busy, FP64 pipe 11%: every 16 FMAs
 // cost 8 shared loads); an 8x8x4 MMA reuses each fragment element across a whole tile, so
@@ -227,7 +287,56 @@ __device__ __forceinline__ void gram_diag_store(const double (&c)[9][2], double 
     }
 }
 
-template <int kRows, bool kBalancedDiag>
+// P == 32: two observations per 64-wide shared-memory row.  X (N x 32, row-major) read as an
+// (N/2) x 64 matrix Y = [x_2r | x_2r+1] is the same bytes, so the chunks stream in dense; with the
+// A fragment scaled by the even row's weight in columns 0..31 and the odd row's in 32..63,
+// Y' W Y = [[G_even, *], [*, G_odd]] and the Gram is G_even + G_odd (added by k_gram_reduce).
+// Only the MMA tiles of the two diagonal 32 x 32 blocks are issued: warp slot A takes the row pair
+// (A, 7 - A) as before, now (4 - A) + (A + 1) = 5 tiles per k-step for TWO observations -- 3.6x
+// fewer DMMAs per observation than padding P = 32 to a 64 x 64 tile with zeros.
+// wts: [2r] even-row weight, [2r + 1] odd-row weight of packed row r.
+template <int A, int kRows>
+__device__ __forceinline__ void gram_pack_chunk(double (&c)[9][2], const double *chunk, const double *wts,
+                                                int grp, int gid, int tig)
+{
+    constexpr int kLo = 4 - A;
+#pragma unroll
+    for (int kk = 0; kk < kRows / 8; ++kk) {
+        const int r = grp * (kRows / 2) + kk * 4 + tig;          // this lane's k row (packed)
+        const double we = wts[2 * r], wo = wts[2 * r + 1];
+        const double *row = chunk + r * kGramLdm + gid;
+        double b[8];
+#pragma unroll
+        for (int j = A; j < 4; ++j) b[j] = row[8 * j];
+#pragma unroll
+        for (int j = 7 - A; j < 8; ++j) b[j] = row[8 * j];
+        const double alo = b[A] * we, ahi = b[7 - A] * wo;
+#pragma unroll
+        for (int j = A; j < 4; ++j) dmma884(c[j - A][0], c[j - A][1], alo, b[j]);
+#pragma unroll
+        for (int j = 7 - A; j < 8; ++j) dmma884(c[kLo + j - (7 - A)][0], c[kLo + j - (7 - A)][1], ahi, b[j]);
+    }
+}
+
+template <int A>
+__device__ __forceinline__ void gram_pack_store(const double (&c)[9][2], double *out, int gid, int tig)
+{
+    constexpr int kLo = 4 - A;
+#pragma unroll
+    for (int j = A; j < 4; ++j) {
+        int row = 8 * A + gid, col = 8 * j + 2 * tig;
+        out[row * kGramTile + col] = c[j - A][0];
+        out[row * kGramTile + col + 1] = c[j - A][1];
+    }
+#pragma unroll
+    for (int j = 7 - A; j < 8; ++j) {
+        int row = 8 * (7 - A) + gid, col = 8 * j + 2 * tig;
+        out[row * kGramTile + col] = c[kLo + j - (7 - A)][0];
+        out[row * kGramTile + col + 1] = c[kLo + j - (7 - A)][1];
+    }
+}
+
+template <int kRows, bool kBalancedDiag, bool kPacked = false>
 __global__ void __launch_bounds__(256)
 k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const double *__restrict__ w,
                int64_t N, int P, int nt)
@@ -243,7 +352,9 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
     const int bj = bi + t;
     const bool diag = bi == bj;
     const int npanel = diag ? 1 : 2;
-    const int stage_elems = npanel * kRows * kGramLdm + kRows;
+    static_assert(!kPacked || kBalancedDiag, "packed rows exist only for the single-tile kernel");
+    constexpr int kObs = kPacked ? 2 * kRows : kRows;            // observations per chunk
+    const int stage_elems = npanel * kRows * kGramLdm + kObs;
     const int w_off = npanel * kRows * kGramLdm;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -254,7 +365,8 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
 
     double c[4][4][2] = {};
     double c9[9][2] = {};                               // kBalancedDiag: this warp's 9 tiles
-    const int64_t slab = (N + gridDim.x - 1) / gridDim.x;
+    int64_t slab = (N + gridDim.x - 1) / gridDim.x;
+    if (kPacked) slab = (slab + 1) & ~(int64_t)1;               // packed rows pair observations (2r, 2r+1) of the chain
     const int64_t r0 = (int64_t)blockIdx.x * slab;
     const int64_t r1 = r0 + slab < N ? r0 + slab : N;
     const bool vec16 = (P % 2 == 0) && ((reinterpret_cast<uintptr_t>(tX) & 15) == 0);
@@ -267,8 +379,8 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
                     int pnl = e >= kRows * (kGramTile / 2);
                     int rem = e - pnl * (kRows * (kGramTile / 2));
                     int r = rem >> 5, cc = (rem & 31) * 2;
-                    int64_t i = base + r;
-                    int col = (pnl == 0 ? bi : bj) * kGramTile + cc;
+                    int64_t i = kPacked ? base + 2 * r + (cc >> 5) : base + r;
+                    int col = kPacked ? (cc & 31) : (pnl == 0 ? bi : bj) * kGramTile + cc;
                     bool ok = i < r1 && col < P;
                     cp_async16(&gsm[so + (pnl * kRows + r) * kGramLdm + cc], ok ? tX + i * P + col : tX, ok);
                 }
@@ -277,13 +389,13 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
                     int pnl = e >= kRows * kGramTile;
                     int rem = e - pnl * (kRows * kGramTile);
                     int r = rem >> 6, cc = rem & 63;
-                    int64_t i = base + r;
-                    int col = (pnl == 0 ? bi : bj) * kGramTile + cc;
+                    int64_t i = kPacked ? base + 2 * r + (cc >> 5) : base + r;
+                    int col = kPacked ? (cc & 31) : (pnl == 0 ? bi : bj) * kGramTile + cc;
                     bool ok = i < r1 && col < P;
                     cp_async8(&gsm[so + (pnl * kRows + r) * kGramLdm + cc], ok ? tX + i * P + col : tX, ok);
                 }
             }
-            if (threadIdx.x < kRows) {
+            if (threadIdx.x < kObs) {
                 int64_t i = base + threadIdx.x;
                 cp_async8(&gsm[so + w_off + threadIdx.x], i < r1 ? w + i : w, i < r1);
             }
@@ -292,14 +404,22 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
     };
 
     issue(r0, 0);
-    issue(r0 + kRows, 1);
+    issue(r0 + kObs, 1);
     int cur = 0;
-    for (int64_t base = r0; base < r1; base += kRows) {
+    for (int64_t base = r0; base < r1; base += kObs) {
         cp_async_wait<1>();
         __syncthreads();
         int nxt = cur + 2 >= kGramStages ? cur + 2 - kGramStages : cur + 2;
-        issue(base + 2 * kRows, nxt);
-        if (kBalancedDiag) {
+        issue(base + 2 * kObs, nxt);
+        if (kPacked) {
+            const double *chunk = gsm + cur * stage_elems;
+            switch (sub) {
+            case 0: gram_pack_chunk<0, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
+            case 1: gram_pack_chunk<1, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
+            case 2: gram_pack_chunk<2, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
+            default: gram_pack_chunk<3, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
+            }
+        } else if (kBalancedDiag) {
             const double *chunk = gsm + cur * stage_elems;
             switch (sub) {
             case 0: gram_diag_chunk<0, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
@@ -350,7 +470,14 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
     double *out = kBalancedDiag
         ? part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kGramTile * kGramTile)
         : part + ((size_t)blockIdx.y * (gridDim.x * 2) + blockIdx.x * 2 + grp) * (kGramTile * kGramTile);
-    if (kBalancedDiag) {
+    if (kPacked) {
+        if (grp == 0) switch (sub) {
+        case 0: gram_pack_store<0>(c9, out, gid, tig); break;
+        case 1: gram_pack_store<1>(c9, out, gid, tig); break;
+        case 2: gram_pack_store<2>(c9, out, gid, tig); break;
+        default: gram_pack_store<3>(c9, out, gid, tig); break;
+        }
+    } else if (kBalancedDiag) {
         if (grp == 0) switch (sub) {
         case 0: gram_diag_store<0>(c9, out, gid, tig); break;
         case 1: gram_diag_store<1>(c9, out, gid, tig); break;
@@ -372,11 +499,14 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
 
 inline int gram_rows(bool any_offdiag) { return any_offdiag ? kGramRows : kGramRowsDiag; }
 
-inline size_t gram_smem_bytes(bool any_offdiag)
+inline size_t gram_smem_bytes(bool any_offdiag, bool packed = false)
 {
     int rows = gram_rows(any_offdiag);
-    return (size_t)kGramStages * ((any_offdiag ? 2 : 1) * rows * kGramLdm + rows) * sizeof(double);
+    return (size_t)kGramStages * ((any_offdiag ? 2 : 1) * rows * kGramLdm + (packed ? 2 : 1) * rows) * sizeof(double);
 }
+
+// P == 32 rows are packed two per shared-memory row (gram_pack_chunk)
+inline bool gram_packed(int P) { return P == 32; }
 
 // ---------------------------------------------------------------------------------
 // Peer exchange (see the window layout in gibbs.cu).  PeerPush travels with the kernel that
@@ -510,7 +640,7 @@ __device__ __forceinline__ void peer_stage(const PeerWait &pw, double *A, double
 // 32 upper-triangle candidates, its 8 warps split the slabs, fixed summation order.
 __global__ void __launch_bounds__(256)
 k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
-              const double *__restrict__ part, int P, int nt, int nslab, PeerPush px)
+              const double *__restrict__ part, int P, int nt, int nslab, PeerPush px, int packed = 0)
 {
     __shared__ double red[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -531,6 +661,14 @@ k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
         const double *src = part + (size_t)tile * nslab * (kGramTile * kGramTile) + la * kGramTile + lb;
 #pragma unroll 8
         for (int k = warp; k < nslab; k += 8) s += src[(size_t)k * (kGramTile * kGramTile)];
+        if (packed) {
+            // the odd observations' sums sit in the second diagonal 32 x 32 block of the tile
+            const double *src2 = src + 32 * kGramTile + 32;
+            double s2 = 0.0;
+#pragma unroll 8
+            for (int k = warp; k < nslab; k += 8) s2 += src2[(size_t)k * (kGramTile * kGramTile)];
+            s += s2;
+        }
     }
     red[warp][lane] = s;
     __syncthreads();
