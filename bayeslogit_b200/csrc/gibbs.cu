@@ -193,6 +193,53 @@ struct DevMem {
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// part[chain][slab][P] = per-slab sums of X'(c0 v0 + c1 v1 v2): streaming kernel for power-of-two P,
+// tensor-core kernel for other even P, scalar kernel otherwise.
+void launch_xtv(dim3 grid, cudaStream_t st, double *part, const double *tX, const double *v0, double c0,
+                const double *v1, const double *v2, double c1, int64_t N, int P, const double *c1_dev)
+{
+    const size_t smem = 8 * P * sizeof(double);
+    const int q = xtv_stream_q(tX, P);
+    int log2L = 0;
+    while ((2 << log2L) < P) ++log2L;
+    if (q == 1) k_xtv_stream<1><<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, P, log2L, c1_dev);
+    else if (q == 2) k_xtv_stream<2><<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, P, log2L, c1_dev);
+    else if (q == 4) k_xtv_stream<4><<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, P, log2L, c1_dev);
+    else if (xbeta_mma_ok(tX, P)) k_xtv_mma<<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, P, c1_dev);
+    else k_xtv_partial<<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, P, c1_dev);
+}
+
+// BL_GIBBS_TIMING=1: CUDA-event stage times of one iteration (the one armed by the driver), to stderr.
+struct StageTimer {
+    bool enabled = getenv("BL_GIBBS_TIMING") != nullptr, armed = false;
+    cudaStream_t st = nullptr;
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
+    void arm(bool on) { armed = enabled && on; if (armed) mark("start"); }
+    void mark(const char *name)
+    {
+        if (!armed) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        marks.emplace_back(name, e);
+    }
+    void report(const char *tag)
+    {
+        if (!armed || marks.size() < 2) return;
+        cudaEventSynchronize(marks.back().second);
+        fprintf(stderr, "[bl %s timing, us]", tag);
+        for (size_t k = 1; k < marks.size(); ++k) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[k - 1].second, marks[k].second);
+            fprintf(stderr, " %s %.1f", marks[k].first, ms * 1e3);
+        }
+        fprintf(stderr, "\n");
+        for (auto &m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+        armed = false;
+    }
+};
+
 // Shared machinery of the three sweeps.
 struct Sweep {
     int64_t N = 0;          // local observations
@@ -288,7 +335,7 @@ struct Sweep {
     void xtv(const double *v0, double c0, const double *v1, const double *v2, double c1,
              const double *c1_dev = nullptr)
     {
-        k_xtv_partial<<<xtv_slabs, 256, 8 * P * sizeof(double), st>>>(xtv_part, tX, v0, c0, v1, v2, c1, N, P, c1_dev);
+        launch_xtv(dim3(xtv_slabs), st, xtv_part, tX, v0, c0, v1, v2, c1, N, P, c1_dev);
         k_xtv_reduce<<<cdiv(P, 128), 128, 0, st>>>(acc + (size_t)P * P, nullptr, nullptr, xtv_part, P, xtv_slabs);
         count_launch(2);
     }
@@ -466,7 +513,7 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
     k_kappa<<<cdiv(T, 256), 256, 0, st>>>(kappa, y, n, 0.0, T);
     k_shape_int<<<cdiv(T, 256), 256, 0, st>>>(shape, n, T);
     k_matvec<<<cdiv(P, 128), 128, 0, st>>>(b0, P0, m0, P);
-    k_xtv_partial<<<dim3(1, chains), 256, 8 * P * sizeof(double), st>>>(xtv_part, tX, kappa, 1.0, nullptr, nullptr, 0.0, N, P);
+    launch_xtv(dim3(1, chains), st, xtv_part, tX, kappa, 1.0, nullptr, nullptr, 0.0, N, P, nullptr);
     k_xtv_reduce<<<dim3(cdiv(P, 128), chains), 128, 0, st>>>(bP, b0, nullptr, xtv_part, P, 1);
     count_launch(5);
     GB_CK(cudaMemsetAsync(beta_out, 0, sizeof(double) * (size_t)bstride * chains, st));
@@ -578,23 +625,33 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
     if (keep_w) GB_CK(cudaMemsetAsync(w_out, 0, sizeof(double) * (size_t)N * U * samp, st));
     GB_CK(cudaMemsetAsync(XB, 0, sizeof(double) * (size_t)N * U, st));
     const int total = burn + samp;
+    StageTimer tmr;
+    tmr.st = st;
     for (int t = 0; t < total; ++t) {
         int slice = t <= burn ? 0 : t - burn;
         double *bS = beta_out + (size_t)P * U * slice;
         double *wS = keep_w ? w_out + (size_t)N * U * slice : nullptr;
         for (int j = 0; j < U; ++j) {
             uint32_t call = (uint32_t)t * (uint32_t)U + (uint32_t)j;
+            tmr.arm(t == total - 1 && j == U - 1);
             k_mlogit_offsets<<<cdiv(N, 256), 256, 0, st>>>(cj, eta, XB, N, U, j);
             count_launch();
+            tmr.mark("offsets");
             double *wj = wS ? wS + (size_t)N * j : s.w;
             cudaError_t e = launch_devroye_refill(wj, shape, eta, N, StreamId{seed, obs0, call}, st);
             if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
+            tmr.mark("draw");
             s.xtv(nullptr, 0.0, wj, cj, 1.0);              // X' Omega c_j
+            tmr.mark("xtv");
             s.gram(wj, true);
+            tmr.mark("gram");
             if (s.allreduce(true, err)) return 1;
             s.beta_draw(kBetaMvn, P0 + (size_t)P * P * j, base + (size_t)P * j, true, nullptr,
                         bS + (size_t)P * j, seed, call);
+            tmr.mark("beta");
             s.xbeta(XB + (size_t)N * j, bS + (size_t)P * j, nullptr, 0.0);
+            tmr.mark("xbeta");
+            tmr.report("mlogit");
         }
     }
     GB_CK(cudaGetLastError());
@@ -629,18 +686,27 @@ int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const doub
     count_launch(3);
     GB_CK(cudaMemsetAsync(beta0, 0, sizeof(double) * P, st));
     double *w = w_out ? w_out : s.w;
+    StageTimer tmr;
+    tmr.st = st;
     for (int t = 0; t < samp; ++t) {
         const double *bprev = t == 0 ? beta0 : beta_out + (size_t)P * (t - 1);
+        tmr.arm(t == samp - 1);
         s.xbeta(s.psi, bprev, nullptr, 0.0, -ld);                              // psi = X beta - log d
+        tmr.mark("xbeta");
         StreamId id{seed, obs0, (uint32_t)t};
         cudaError_t e = N >= (1 << 15)
             ? launch_hybrid_binned(w, shape, s.psi, (int)N, id, work, st)
             : launch_rpg(kHybrid, w, shape, s.psi, N, 0, nullptr, id, st);
         if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
+        tmr.mark("draw");
         s.xtv(kappa, 1.0, w, nullptr, ld);                                     // X'(kappa + omega log d)
+        tmr.mark("xtv");
         s.gram(w, true);
+        tmr.mark("gram");
         if (s.allreduce(true, err)) return 1;
         s.beta_draw(kBetaPlain, P0, b0, true, nullptr, beta_out + (size_t)P * t, seed, (uint32_t)t);
+        tmr.mark("beta");
+        tmr.report("nb");
     }
     GB_CK(cudaGetLastError());
     return s.check_status(err, "nb_gibbs");

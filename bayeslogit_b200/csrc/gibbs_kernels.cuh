@@ -734,6 +734,152 @@ k_xtv_partial(double *__restrict__ part, const double *__restrict__ tX, const do
     }
 }
 
+// The same on the FP64 tensor cores (even P, 16-byte aligned tX): out = X' v as m8n8k4 MMAs with
+// the four k slots on four consecutive rows and v repeated in every column of B.  Lane (gid, tig)
+// loads the 16 bytes X[i + tig][pc + 2 gid, +1] (the eight gid lanes cover 128 contiguous bytes
+// of the row) and feeds .x to the MMA that accumulates the even columns of a 16-column block and
+// .y to the one for the odd columns.  A warp owns one 64-column panel and every (8 / panels)-th
+// group of 16 rows of the CTA's slab, 16 loads of 16 bytes in flight per lane; the scalar
+// k_xtv_partial above keeps 4 rows in flight per warp and reaches 1.1 TB/s.
+__global__ void __launch_bounds__(256, 2)
+k_xtv_mma(double *__restrict__ part, const double *__restrict__ tX, const double *__restrict__ v0,
+          double c0, const double *__restrict__ v1, const double *__restrict__ v2, double c1,
+          int64_t N, int P, const double *__restrict__ c1_dev)
+{
+    if (c1_dev) c1 = *c1_dev;
+    tX += (size_t)blockIdx.y * N * P;
+    part += (size_t)blockIdx.y * gridDim.x * P;
+    if (v0) v0 += (size_t)blockIdx.y * N;
+    if (v1) v1 += (size_t)blockIdx.y * N;
+    if (v2) v2 += (size_t)blockIdx.y * N;
+    extern __shared__ double sacc[];                     // [row sub-groups][P]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+    const int panels = (P + 63) >> 6;                    // 1..4
+    const int nsub = 8 / panels;
+    const int panel = warp % panels, sub = warp / panels;
+    const int64_t slab = (N + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * slab;
+    const int64_t r1 = r0 + slab < N ? r0 + slab : N;
+    const int pc = panel * 64 + 2 * gid;                 // this lane's first column
+    double acc[4][2][2] = {};                            // [16-column block][even / odd][c0, c1]
+    if (sub < nsub) {
+        for (int64_t i0 = r0 + sub * 16; i0 < r1; i0 += nsub * 16) {
+            double2 a[4][4];
+            double vv[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int64_t i = i0 + 4 * g + tig;
+                const bool rv = i < r1;
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb)
+                    a[g][cb] = (rv && pc + 16 * cb < P) ? __ldg(reinterpret_cast<const double2 *>(tX + i * P + pc + 16 * cb))
+                                                        : make_double2(0.0, 0.0);
+                vv[g] = rv ? (v0 ? c0 * v0[i] : 0.0) + (v1 ? c1 * v1[i] * (v2 ? v2[i] : 1.0) : 0.0) : 0.0;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb)
+                    if (panel * 64 + 16 * cb < P) {              // warp-uniform: no MMAs on column blocks past P
+                        dmma884(acc[cb][0][0], acc[cb][0][1], a[g][cb].x, vv[g]);
+                        dmma884(acc[cb][1][0], acc[cb][1][1], a[g][cb].y, vv[g]);
+                    }
+        }
+        if (tig == 0) {
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb)
+                if (pc + 16 * cb < P) {
+                    sacc[sub * P + pc + 16 * cb] = acc[cb][0][0];
+                    sacc[sub * P + pc + 16 * cb + 1] = acc[cb][1][0];
+                }
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < nsub; ++k) s += sacc[k * P + p];
+        part[(size_t)blockIdx.x * P + p] = s;
+    }
+}
+
+// Streaming form for P a power of two (8 <= P <= 256) and 16-byte aligned tX: the CTA's slab is read
+// as one flat run of 16-byte column pairs, 512 consecutive pairs (8 KB) per warp trip with all 16
+// loads of a lane in flight; a lane meets the same column pair (kQ = 1: P <= 64) or the same kQ
+// column pairs in rotation (P = 128, 256) on every trip, so its sums stay in registers and there is
+// no index arithmetic beyond one shift per load.  ~3 instructions per 16 bytes, HBM-bound.
+template <int kQ>
+__global__ void __launch_bounds__(256, 2)
+k_xtv_stream(double *__restrict__ part, const double *__restrict__ tX, const double *__restrict__ v0,
+             double c0, const double *__restrict__ v1, const double *__restrict__ v2, double c1,
+             int64_t N, int P, int log2L, const double *__restrict__ c1_dev)
+{
+    if (c1_dev) c1 = *c1_dev;
+    tX += (size_t)blockIdx.y * N * P;
+    part += (size_t)blockIdx.y * gridDim.x * P;
+    if (v0) v0 += (size_t)blockIdx.y * N;
+    if (v1) v1 += (size_t)blockIdx.y * N;
+    if (v2) v2 += (size_t)blockIdx.y * N;
+    extern __shared__ double sacc[];                     // [warps][P]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int64_t slab = (N + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * slab;
+    const int64_t r1 = r0 + slab < N ? r0 + slab : N;
+    const int64_t npairs = r1 > r0 ? (r1 - r0) << log2L : 0;
+    const double2 *X2 = reinterpret_cast<const double2 *>(tX + r0 * P);
+    double2 acc[kQ];
+#pragma unroll
+    for (int q = 0; q < kQ; ++q) acc[q] = make_double2(0.0, 0.0);
+    for (int64_t e0 = (int64_t)warp * 512; e0 < npairs; e0 += (int64_t)nw * 512) {
+        double2 x[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int64_t e = e0 + u * 32 + lane;
+            x[u] = e < npairs ? __ldg(X2 + e) : make_double2(0.0, 0.0);
+        }
+        // the weights are 1/P of the traffic and mostly L1 hits: fetched while the X loads land
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int64_t e = e0 + u * 32 + lane;
+            const int64_t i = r0 + (e >> log2L);
+            double vi = 0.0;
+            if (e < npairs) vi = (v0 ? c0 * __ldg(v0 + i) : 0.0) + (v1 ? c1 * __ldg(v1 + i) * (v2 ? __ldg(v2 + i) : 1.0) : 0.0);
+            acc[u % kQ].x = fma(x[u].x, vi, acc[u % kQ].x);
+            acc[u % kQ].y = fma(x[u].y, vi, acc[u % kQ].y);
+        }
+    }
+    // lanes that share a column pair (P < 64: pair = lane mod P/2)
+    const int L = 1 << log2L;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+        if (o >= L) {
+#pragma unroll
+            for (int q = 0; q < kQ; ++q) {
+                acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o);
+                acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
+            }
+        }
+    if (lane < L) {
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) {
+            sacc[warp * P + 2 * (lane + 32 * q)] = acc[q].x;
+            sacc[warp * P + 2 * (lane + 32 * q) + 1] = acc[q].y;
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < nw; ++k) s += sacc[k * P + p];
+        part[(size_t)blockIdx.x * P + p] = s;
+    }
+}
+
+// 0: not eligible; else kQ of k_xtv_stream
+inline int xtv_stream_q(const double *tX, int P)
+{
+    if ((reinterpret_cast<uintptr_t>(tX) & 15) != 0 || P < 8 || P > 256 || (P & (P - 1)) != 0) return 0;
+    return P <= 64 ? 1 : P / 64;
+}
+
 __global__ void k_xtv_reduce(double *__restrict__ out, const double *__restrict__ add0,
                              const double *__restrict__ add1, const double *__restrict__ part,
                              int P, int nslab)

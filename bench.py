@@ -372,6 +372,17 @@ def main():
         gp = bench_gibbs.run(1_000_000, 64, args.gibbs_iters, 5, False, rank, world, local)
         gc = bench_gibbs.run(1_000_000, 64, max(10, args.gibbs_iters // 10), 2, True, rank, world, local)
         extras["gibbs_logit_N1M_P64"] = {"plain_beta": gp, "reference_constrained_beta": gc, "scaling": "strong"}
+        # (iii) the other sweeps of BASELINE.json's configs: NB regression (config 4), multinomial logit and the
+        # batch of independent chains (config 5); short runs, figures per iteration
+        import bench_chains
+        import bench_models
+        torch.cuda.empty_cache()
+        extras["chains_4096_N10k_P32"] = bench_chains.run(4096, 10_000, 32, 10, False, rank, world, local, serial_sample=4)
+        torch.cuda.empty_cache()
+        extras["mlogit_J10_N1M_P32"] = bench_models.run_mlogit(1_000_000, 32, 10, 10, rank, world, local)
+        torch.cuda.empty_cache()
+        extras["nb_N10M_P256"] = bench_models.run_nb(10_000_000, 256, 6, rank, world, local)
+        torch.cuda.empty_cache()
 
     if rank == 0:
         peaks = {}

@@ -48,7 +48,7 @@ def close(a, b, rel=CHAIN_REL):
 
 
 @pytest.mark.parametrize("constrained", [False, True])
-@pytest.mark.parametrize("N,P,binomial", [(3000, 7, False), (1500, 64, False), (2000, 5, True), (700, 70, False), (1501, 32, False)])
+@pytest.mark.parametrize("N,P,binomial", [(3000, 7, False), (1500, 64, False), (2000, 5, True), (700, 70, False), (1501, 32, False), (600, 128, False)])
 def test_logit_chain_matches_oracle(gapi, constrained, N, P, binomial):
     X, y, n, _ = synth_logit(N, P, 10 + P, binomial)
     m0 = np.linspace(-0.1, 0.1, P)
@@ -112,11 +112,12 @@ def test_mlogit_chain_matches_oracle(gapi):
     close(b, bo); close(w, wo)
 
 
-def test_nb_chain_matches_oracle(gapi):
+@pytest.mark.parametrize("P", [5, 8])
+def test_nb_chain_matches_oracle(gapi, P):
     rng = np.random.default_rng(6)
-    N, P, d = 2000, 5, 3.0
+    N, d = 2000, 3.0
     X = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
-    bt = np.array([0.9, -0.7, 0.6, 0.5, 2.6])          # counts 0..500: b = y + d spans Alt/SP/normal
+    bt = np.r_[[0.9, -0.7, 0.6, 0.5], np.zeros(P - 5), 2.6]          # counts 0..500: b = y + d spans Alt/SP/normal
     mu = np.exp(X @ bt)
     y = rng.negative_binomial(d, d / (mu + d)).astype(float)
     assert (y + d > 170).any() and (y + d < 13).any()
