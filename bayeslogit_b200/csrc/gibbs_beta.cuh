@@ -301,7 +301,7 @@ __device__ __forceinline__ void cta_ldl_upper(double *A, double *rd, int P, int 
 // written below in terms of t = D^-1/2-scaled quantities so only R and rd are touched.
 template <int KP>
 __device__ __forceinline__ void warp_solve_plain_k(const double *R, const double *rd, const double *b,
-                                                   const double *e, double *out, int P, int ld, int lane)
+                                                   const double *e, double *out, int P, int ld, int lane, bool rev)
 {
     double x[KP];
 #pragma unroll
@@ -347,16 +347,16 @@ __device__ __forceinline__ void warp_solve_plain_k(const double *R, const double
 #pragma unroll
     for (int q = 0; q < KP; ++q) {
         int m = lane + 32 * q;
-        if (m < P) out[m] = x[q];
+        if (m < P) out[rev ? P - 1 - m : m] = x[q];      // rev: solution of the index-reversed system
     }
 }
 
 __device__ inline void warp_solve_plain(const double *R, const double *rd, const double *b,
-                                        const double *e, double *out, int P, int ld, int lane)
+                                        const double *e, double *out, int P, int ld, int lane, bool rev = false)
 {
-    if (P <= 64) warp_solve_plain_k<2>(R, rd, b, e, out, P, ld, lane);
-    else if (P <= 128) warp_solve_plain_k<4>(R, rd, b, e, out, P, ld, lane);
-    else warp_solve_plain_k<8>(R, rd, b, e, out, P, ld, lane);
+    if (P <= 64) warp_solve_plain_k<2>(R, rd, b, e, out, P, ld, lane, rev);
+    else if (P <= 128) warp_solve_plain_k<4>(R, rd, b, e, out, P, ld, lane, rev);
+    else warp_solve_plain_k<8>(R, rd, b, e, out, P, ld, lane, rev);
 }
 
 // The coordinate-wise constrained draw, Logit.hpp:366-399, on one warp with beta and z held in
@@ -445,13 +445,32 @@ __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, do
     PhiloxSource src;
     src.open(seed, 0xFFFFFFFFFFFFFFFFull, call);
 
-    if (mode == kBetaPlain) {
-        // beta = PP^-1 bP + U^-1 eps = U^-1 (U^-T bP + eps)          (Logit.hpp:303-319)
+    if (mode == kBetaPlain || mode == kBetaMvn) {
+        // plain: beta = PP^-1 bP + U^-1 eps = U^-1 (U^-T bP + eps), U'U = PP        (Logit.hpp:303-319)
+        // mvn  : beta = PP^-1 b1 + L eps with L = chol(PP^-1) lower                 (Normal.hpp:98-131).
+        //   The reference inverts PP and factorises the inverse.  With J the index reversal and
+        //   J PP J = U'U (the same upper factorisation, of the reversed matrix), PP^-1 =
+        //   (J U^-1 J)(J U^-1 J)' and J U^-1 J is lower triangular with a positive diagonal, i.e. it IS
+        //   the Cholesky factor L (uniqueness).  So L eps = J U^-1 (J eps) and PP^-1 b1 = J U^-1 U^-T (J b1):
+        //   the mvn draw is the plain draw of the reversed system with the normals reversed -- one
+        //   factorisation and two substitutions instead of chol + P solves + a second chol.
+        const bool rev = mode == kBetaMvn;
+        if (rev) {
+            double *rw = const_cast<double *>(rhs);           // the CTA's own workspace (k_beta_draw)
+            const int PP2 = P * P;
+            for (int k = tid; k < PP2 / 2; k += blockDim.x) {
+                const int k2 = PP2 - 1 - k;
+                double *a = A + (k % P) + (size_t)ld * (k / P), *b = A + (k2 % P) + (size_t)ld * (k2 / P);
+                const double t = *a; *a = *b; *b = t;
+            }
+            for (int k = tid; k < P / 2; k += blockDim.x) { const double t = rw[k]; rw[k] = rw[P - 1 - k]; rw[P - 1 - k] = t; }
+            __syncthreads();
+        }
         double *rd = z;
 #ifdef BL_BETA_CLOCKS
         long long c0 = clock64();
 #endif
-        for (int i = tid; i < P; i += blockDim.x) e[i] = stream_normal(seed, call, i);
+        for (int i = tid; i < P; i += blockDim.x) e[i] = stream_normal(seed, call, rev ? P - 1 - i : i);
 #ifdef BL_BETA_CLOCKS
         long long c1 = clock64();
 #endif
@@ -460,7 +479,7 @@ __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, do
         long long c2 = clock64();
 #endif
         if (!ok) { if (tid == 0) *status = 1; return; }
-        if (tid < 32) warp_solve_plain(A, rd, rhs, e, beta_out, P, ld, lane);
+        if (tid < 32) warp_solve_plain(A, rd, rhs, e, beta_out, P, ld, lane, rev);
         __syncthreads();
 #ifdef BL_BETA_CLOCKS
         if (tid == 0 && call == 3) printf("[beta clocks] normals %lld ldl %lld solve %lld\n", c1 - c0, c2 - c1, clock64() - c2);
@@ -475,27 +494,6 @@ __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, do
     for (int k = tid; k < P * P; k += blockDim.x) B[k % P + (size_t)ld * (k / P)] = (k % P == k / P) ? 1.0 : 0.0;
     __syncthreads();
     cta_solve_utu(A, B, P, ld, P);
-
-    if (mode == kBetaMvn) {
-        // mean = V b1 ; lower = chol(V) ; draw = mean + lower * N(0,I)
-        for (int a = tid; a < P; a += blockDim.x) {
-            double m = 0.0;
-            for (int b = 0; b < P; ++b) m = fma(B[a + (size_t)ld * b], rhs[b], m);
-            mP[a] = m;
-        }
-        __syncthreads();
-        cta_chol_lower(B, P, ld, &ok);
-        if (!ok) { if (tid == 0) *status = 2; return; }
-        for (int i = tid; i < P; i += blockDim.x) e[i] = stream_normal(seed, call, i);
-        __syncthreads();
-        for (int a = tid; a < P; a += blockDim.x) {
-            double s = 0.0;
-            for (int b = 0; b <= a; ++b) s = fma(B[a + (size_t)ld * b], e[b], s);
-            beta_out[a] = mP[a] + s;
-        }
-        __syncthreads();
-        return;
-    }
 
     // constrained coordinate-wise draw (Logit.hpp:349-399)
     cta_chol_lower(B, P, ld, &ok);
