@@ -199,12 +199,20 @@ void launch_xtv(dim3 grid, cudaStream_t st, double *part, const double *tX, cons
                 const double *v1, const double *v2, double c1, int64_t N, int P, const double *c1_dev)
 {
     const size_t smem = 8 * P * sizeof(double);
-    const int q = xtv_stream_q(tX, P);
-    int log2L = 0;
-    while ((2 << log2L) < P) ++log2L;
-    if (q == 1) k_xtv_stream<1><<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, P, log2L, c1_dev);
-    else if (q == 2) k_xtv_stream<2><<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, P, log2L, c1_dev);
-    else if (q == 4) k_xtv_stream<4><<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, P, log2L, c1_dev);
+    // the streaming kernel indexes a slab's column pairs with 32 bits
+    const int64_t slab_pairs = ((N + grid.x - 1) / grid.x) * (P / 2);
+    const int l2 = slab_pairs < (1LL << 31) - 4096 ? xtv_stream_log2l(tX, P) : 0;
+    const int mode = (v0 && !v1 && !v2) ? 0 : (!v0 && v1 && v2) ? 1 : (v0 && v1 && !v2) ? 2 : -1;
+#define BL_XTV(L2, M) k_xtv_stream<L2, M><<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, c1_dev)
+#define BL_XTV_L(L2) (mode == 0 ? BL_XTV(L2, 0) : mode == 1 ? BL_XTV(L2, 1) : BL_XTV(L2, 2))
+    if (mode >= 0 && l2 == 2) BL_XTV_L(2);
+    else if (mode >= 0 && l2 == 3) BL_XTV_L(3);
+    else if (mode >= 0 && l2 == 4) BL_XTV_L(4);
+    else if (mode >= 0 && l2 == 5) BL_XTV_L(5);
+    else if (mode >= 0 && l2 == 6) BL_XTV_L(6);
+    else if (mode >= 0 && l2 == 7) BL_XTV_L(7);
+#undef BL_XTV_L
+#undef BL_XTV
     else if (xbeta_mma_ok(tX, P)) k_xtv_mma<<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, P, c1_dev);
     else k_xtv_partial<<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, P, c1_dev);
 }

@@ -802,53 +802,78 @@ k_xtv_mma(double *__restrict__ part, const double *__restrict__ tX, const double
     }
 }
 
-// Streaming form for P a power of two (8 <= P <= 256) and 16-byte aligned tX: the CTA's slab is read
-// as one flat run of 16-byte column pairs, 512 consecutive pairs (8 KB) per warp trip with all 16
-// loads of a lane in flight; a lane meets the same column pair (kQ = 1: P <= 64) or the same kQ
-// column pairs in rotation (P = 128, 256) on every trip, so its sums stay in registers and there is
-// no index arithmetic beyond one shift per load.  ~3 instructions per 16 bytes, HBM-bound.
-template <int kQ>
+// Streaming form for P a power of two (8 <= P <= 256; kLog2L = log2(P / 2)) and 16-byte aligned tX:
+// the CTA's slab is read as one flat run of 16-byte column pairs, 512 consecutive pairs (8 KB) per
+// warp trip with all 16 loads of a lane in flight.  A lane meets the same column pair (P <= 64) or
+// the same P/64 column pairs in rotation (P = 128, 256) on every trip, so its sums stay in registers,
+// and with the row length a compile-time power of two every row index of a trip is the first one
+// plus a constant: the loop is ~8 instructions per 16 bytes and HBM-bound.  (With a run-time shift
+// and 64-bit element indices the same loop issued 48 instructions per 16 bytes and sat at 3 TB/s.)
+// kMode: which of the weight arrays exist (compile-time, so the 16 weight fetches of a trip are
+// issued together instead of one by one behind null tests): 0: c0 v0; 1: c1 v1 v2; 2: c0 v0 + c1 v1.
+template <int kMode>
+__device__ __forceinline__ double xtv_weight(const double *w0, double c0, const double *w1, const double *w2,
+                                             double c1, int i)
+{
+    if (kMode == 0) return c0 * __ldg(w0 + i);
+    if (kMode == 1) return c1 * __ldg(w1 + i) * __ldg(w2 + i);
+    return c0 * __ldg(w0 + i) + c1 * __ldg(w1 + i);
+}
+
+template <int kLog2L, int kMode>
 __global__ void __launch_bounds__(256, 2)
 k_xtv_stream(double *__restrict__ part, const double *__restrict__ tX, const double *__restrict__ v0,
              double c0, const double *__restrict__ v1, const double *__restrict__ v2, double c1,
-             int64_t N, int P, int log2L, const double *__restrict__ c1_dev)
+             int64_t N, const double *__restrict__ c1_dev)
 {
+    constexpr int L = 1 << kLog2L, P = 2 * L;            // column pairs per row, columns
+    constexpr int kQ = L > 32 ? L / 32 : 1;              // column pairs a lane rotates through
     if (c1_dev) c1 = *c1_dev;
     tX += (size_t)blockIdx.y * N * P;
     part += (size_t)blockIdx.y * gridDim.x * P;
-    if (v0) v0 += (size_t)blockIdx.y * N;
-    if (v1) v1 += (size_t)blockIdx.y * N;
-    if (v2) v2 += (size_t)blockIdx.y * N;
     extern __shared__ double sacc[];                     // [warps][P]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int64_t slab = (N + gridDim.x - 1) / gridDim.x;
     const int64_t r0 = (int64_t)blockIdx.x * slab;
     const int64_t r1 = r0 + slab < N ? r0 + slab : N;
-    const int64_t npairs = r1 > r0 ? (r1 - r0) << log2L : 0;
+    const int np = r1 > r0 ? (int)((r1 - r0) << kLog2L) : 0;        // pairs in the slab (host keeps it < 2^31)
     const double2 *X2 = reinterpret_cast<const double2 *>(tX + r0 * P);
+    const size_t voff = (size_t)blockIdx.y * N + r0;
+    const double *w0 = v0 ? v0 + voff : nullptr, *w1 = v1 ? v1 + voff : nullptr, *w2 = v2 ? v2 + voff : nullptr;
     double2 acc[kQ];
 #pragma unroll
     for (int q = 0; q < kQ; ++q) acc[q] = make_double2(0.0, 0.0);
-    for (int64_t e0 = (int64_t)warp * 512; e0 < npairs; e0 += (int64_t)nw * 512) {
+    for (int e0 = warp * 512; e0 < np; e0 += nw * 512) {
+        const double2 *Xw = X2 + e0 + lane;
+        const int i0 = (e0 + lane) >> kLog2L;            // row of this lane's first pair (slab-relative)
         double2 x[16];
+        if (e0 + 512 <= np) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int64_t e = e0 + u * 32 + lane;
-            x[u] = e < npairs ? __ldg(X2 + e) : make_double2(0.0, 0.0);
-        }
-        // the weights are 1/P of the traffic and mostly L1 hits: fetched while the X loads land
+            for (int u = 0; u < 16; ++u) x[u] = __ldg(Xw + u * 32);
+            // rows advance by a constant per u: at most 16 distinct weights per trip (one when P >= 64 ... 256)
+            constexpr int kStep = L <= 32 ? 32 / L : 1, kEvery = L <= 32 ? 1 : L / 32;
+            double vi[16 / kEvery];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int64_t e = e0 + u * 32 + lane;
-            const int64_t i = r0 + (e >> log2L);
-            double vi = 0.0;
-            if (e < npairs) vi = (v0 ? c0 * __ldg(v0 + i) : 0.0) + (v1 ? c1 * __ldg(v1 + i) * (v2 ? __ldg(v2 + i) : 1.0) : 0.0);
-            acc[u % kQ].x = fma(x[u].x, vi, acc[u % kQ].x);
-            acc[u % kQ].y = fma(x[u].y, vi, acc[u % kQ].y);
+            for (int r = 0; r < 16 / kEvery; ++r) vi[r] = xtv_weight<kMode>(w0, c0, w1, w2, c1, i0 + r * kStep);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                acc[u % kQ].x = fma(x[u].x, vi[u / kEvery], acc[u % kQ].x);
+                acc[u % kQ].y = fma(x[u].y, vi[u / kEvery], acc[u % kQ].y);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) x[u] = e0 + u * 32 + lane < np ? __ldg(Xw + u * 32) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int i = i0 + ((u * 32) >> kLog2L);
+                double vi = 0.0;
+                if (e0 + u * 32 + lane < np) vi = xtv_weight<kMode>(w0, c0, w1, w2, c1, i);
+                acc[u % kQ].x = fma(x[u].x, vi, acc[u % kQ].x);
+                acc[u % kQ].y = fma(x[u].y, vi, acc[u % kQ].y);
+            }
         }
     }
     // lanes that share a column pair (P < 64: pair = lane mod P/2)
-    const int L = 1 << log2L;
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1)
         if (o >= L) {
@@ -873,11 +898,13 @@ k_xtv_stream(double *__restrict__ part, const double *__restrict__ tX, const dou
     }
 }
 
-// 0: not eligible; else kQ of k_xtv_stream
-inline int xtv_stream_q(const double *tX, int P)
+// 0: not eligible; else log2(P / 2) of k_xtv_stream
+inline int xtv_stream_log2l(const double *tX, int P)
 {
     if ((reinterpret_cast<uintptr_t>(tX) & 15) != 0 || P < 8 || P > 256 || (P & (P - 1)) != 0) return 0;
-    return P <= 64 ? 1 : P / 64;
+    int l = 0;
+    while ((2 << l) < P) ++l;
+    return l;
 }
 
 __global__ void k_xtv_reduce(double *__restrict__ out, const double *__restrict__ add0,
