@@ -326,7 +326,7 @@ struct Sweep {
             px.world = pending.world = g_nccl.world;
             px.epoch = pending.epoch = e;
             px.done = g_peer.done;
-            px.tail = with_tail ? acc + (size_t)P * P : nullptr;
+            px.with_tail = with_tail ? 1 : 0;
             for (int r = 0; r < g_nccl.world; ++r) {
                 char *w = (char *)g_peer.win[r];
                 px.flag[r] = (unsigned *)w + par * kMaxPeers + me;

@@ -518,7 +518,7 @@ struct PeerPush {
     double *slot[kMaxPeers];      // slot [parity][my rank] inside every rank's window
     unsigned *flag[kMaxPeers];    // flag [parity][my rank] inside every rank's window
     unsigned *done;               // local CTA counter (zero between launches)
-    const double *tail;           // optional P extra sums appended after the P^2 (already reduced), or null
+    int with_tail;                // also publish the P extra sums xtv() left behind the P^2 (acc[P^2 ..))
     unsigned epoch;
     int world;                    // <= 1: no exchange
 };
@@ -547,21 +547,47 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 
-// Called by every thread of every CTA of the pushing kernel after its stores to the peers'
-// slots: the last CTA to arrive raises this rank's flag in every window.  One system-scope fence
-// per CTA (thread 0, after the CTA barrier: fences are cumulative over the stores the barrier
-// ordered before it), not one per thread.
-__device__ __forceinline__ void peer_publish(const PeerPush &px)
+// Called by every thread of every CTA of the reducing kernel once its part of `acc` is written.
+// The last CTA to arrive copies the whole local result (cnt doubles, cnt even) into this rank's slot
+// of every window with coalesced 16-byte NVLink stores -- 512 contiguous bytes per warp instruction
+// instead of the reducing CTAs' scattered 8-byte element stores -- then one system-scope fence and
+// the flags.  (Scattering from all CTAs cost ~20 us at 8 GPUs: 2 x 8 small stores per element and a
+// system fence in each of the 128 CTAs.)
+__device__ __forceinline__ void peer_publish(const PeerPush &px, const double *acc, int cnt)
 {
+    __shared__ int last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();             // the CTA's slot stores are performed system-wide
+        __threadfence();                    // this CTA's part of acc is visible device-wide
         unsigned prev = atomicAdd(px.done, 1u);
-        if (prev == gridDim.x * gridDim.y - 1) {
-            *px.done = 0;                   // next launch on this stream starts from zero
-            __threadfence_system();
-            for (int r = 0; r < px.world; ++r) st_release_sys(px.flag[r], px.epoch);
+        last = prev == gridDim.x * gridDim.y - 1;
+        if (last) *px.done = 0;             // next launch on this stream starts from zero
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const double2 *src = reinterpret_cast<const double2 *>(acc);
+    const int n2 = cnt >> 1;
+    for (int i0 = threadIdx.x; i0 < n2; i0 += 4 * blockDim.x) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x;
+            v[u] = i < n2 ? __ldcg(src + i) : make_double2(0.0, 0.0);
         }
+        for (int r = 0; r < px.world; ++r) {
+            double2 *dst = reinterpret_cast<double2 *>(px.slot[r]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < n2) dst[i] = v[u];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();             // the slot stores are performed system-wide before the flags
+        for (int r = 0; r < px.world; ++r) st_release_sys(px.flag[r], px.epoch);
     }
 }
 
@@ -676,25 +702,11 @@ k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
         double v = 0.0;
         for (int k = 0; k < 8; ++k) v += red[k][lane];
         v += P0 ? P0[a + (size_t)P * b] : 0.0;
-        if (px.world > 1) {
-            // sharded data: the sums go straight into every rank's window (NVLink stores)
-            for (int r = 0; r < px.world; ++r) {
-                px.slot[r][a + (size_t)P * b] = v;
-                px.slot[r][b + (size_t)P * a] = v;
-            }
-        } else {
-            PP[a + (size_t)P * b] = v;
-            PP[b + (size_t)P * a] = v;
-        }
+        PP[a + (size_t)P * b] = v;
+        PP[b + (size_t)P * a] = v;
     }
-    if (px.world > 1) {
-        if (blockIdx.x == 0 && px.tail)
-            for (int k = threadIdx.x; k < P; k += blockDim.x) {
-                double t = px.tail[k];
-                for (int r = 0; r < px.world; ++r) px.slot[r][(size_t)P * P + k] = t;
-            }
-        peer_publish(px);
-    }
+    // sharded data: the finished sums (and the P sums behind them) go into every rank's window
+    if (px.world > 1) peer_publish(px, PP, P * P + (px.with_tail ? P : 0));
 }
 
 // out_p = sum_i x_i[p] * v_i  (X'v), v_i = c0*v0_i + c1*v1_i*v2_i  (v1/v2 optional).

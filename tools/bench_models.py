@@ -120,7 +120,8 @@ def run_mlogit(N, P, J, iters, rank, world, local):
     launches = L.bl_kernel_launches() - l0
     post = beta[iters // 2:].mean(0)                                             # [U][P]
     return {"iters_per_sec": iters / (ms * 1e-3), "ms_per_iter": ms / iters, "iters": iters, "N": N, "P": P, "J": J,
-            "n_gpus": world, "category_updates_per_sec": iters * U / (ms * 1e-3),
+            "n_gpus": world, "exchange": ("peer windows" if bdist.peer_exchange_active() else "ncclAllReduce") if world > 1 else None,
+            "category_updates_per_sec": iters * U / (ms * 1e-3),
             "launches_per_iter": launches / iters,
             "max_abs_err_vs_truth": float((post - B.t()).abs().max().item())}
 
