@@ -51,8 +51,11 @@ def run(chains, N, P, iters, constrained, rank, world, local, serial_sample=16):
     e0.record(); beta = batch(iters); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = L.bl_kernel_launches() - l0
-    # one after the other (the reference's usage: one gibbs() call per chain)
-    S = min(serial_sample, C)
+    # one after the other (the reference's usage: one gibbs() call per chain).  Only without a
+    # communicator: with one open, bl_logit_gibbs_dev treats the ranks' rows as shards of ONE chain
+    # and exchanges the Gram sums, which is not what independent chains are.
+    S = min(serial_sample, C) if world == 1 else 0
+    b1 = None
     e0.record()
     for c in range(S):
         b1 = torch.zeros(iters, P, device=dev, dtype=torch.float64)
@@ -62,7 +65,7 @@ def run(chains, N, P, iters, constrained, rank, world, local, serial_sample=16):
             _lib.check(rc)
     e1.record(); torch.cuda.synchronize()
     ms1 = e0.elapsed_time(e1)
-    same = float((b1 - beta[S - 1]).abs().max().item())
+    same = float((b1 - beta[S - 1]).abs().max().item()) if S else None
     post = beta[:, iters // 2:].mean(1)
     if world > 1:
         import torch.distributed as dist
@@ -73,7 +76,8 @@ def run(chains, N, P, iters, constrained, rank, world, local, serial_sample=16):
             "chains": C * world, "chains_per_gpu": C, "N": N, "P": P, "iters": iters,
             "launches_per_iteration": launches / iters,
             "beta_draw": "constrained" if constrained else "plain",
-            "one_after_the_other_chain_iters_per_sec_one_gpu": S * iters / (ms1 * 1e-3), "serial_sample_chains": S,
+            "one_after_the_other_chain_iters_per_sec_one_gpu": S * iters / (ms1 * 1e-3) if S else None,
+            "serial_sample_chains": S,
             "max_abs_diff_batched_vs_single_entry": same,
             "rms_err_vs_truth": float((post - bt).pow(2).mean().sqrt().item()), "n_gpus": world,
             "x_bytes_per_gpu": C * N * P * 8}
