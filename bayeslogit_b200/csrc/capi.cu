@@ -15,6 +15,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "engine.h"
 
@@ -147,15 +148,36 @@ int run_host(Method m, double *x, const void *shape, const double *z, int64_t nu
     if (num < 0) return fail("negative batch size");
     if (num == 0) return 0;
     if (!x || !shape || !z) return fail("null argument");
-    int64_t chunk = num < kChunk ? num : kChunk;
-    int64_t nchunks = (num + chunk - 1) / chunk;
+    // Chunk schedule: the pipeline's fill (H2D of the first chunk, nothing to compute yet) and drain
+    // (kernel + D2H of the last chunk, nothing left to copy in) are pure latency, so the batch opens
+    // and closes with small chunks -- 1M, 2M, 4M, then kChunk-sized ones, then 4M, 2M, 1M -- and the
+    // link stays busy from ~0.3 ms after the call until ~0.4 ms before it returns.  Results do not
+    // depend on the schedule (streams are keyed by the global observation index).
+    std::vector<int64_t> sizes;
+    {
+        const int64_t ramp[3] = {kChunk / 8, kChunk / 4, kChunk / 2};
+        int64_t head = 0, tail = 0;
+        std::vector<int64_t> tl;
+        if (num >= 4 * kChunk) {
+            for (int64_t r : ramp) { sizes.push_back(r); head += r; }
+            for (int64_t r : ramp) { tl.push_back(r); tail += r; }
+        }
+        int64_t body = num - head - tail;
+        while (body > 0) {
+            int64_t n = body < kChunk ? body : kChunk;
+            sizes.push_back(n);
+            body -= n;
+        }
+        for (auto it = tl.rbegin(); it != tl.rend(); ++it) sizes.push_back(*it);
+    }
+    const int64_t nchunks = (int64_t)sizes.size();
     for (int s = 0; s < kSlots && s < nchunks; ++s)
-        if (slot_reserve(g.slot[s], chunk)) return 1;
+        if (slot_reserve(g.slot[s], num < kChunk ? num : kChunk)) return 1;
     size_t ss = shape_size(m);
-    for (int64_t c = 0; c < nchunks; ++c) {
+    int64_t off = 0;
+    for (int64_t c = 0; c < nchunks; off += sizes[c], ++c) {
         Slot &s = g.slot[c % kSlots];
-        int64_t off = c * chunk;
-        int64_t n = num - off < chunk ? num - off : chunk;
+        const int64_t n = sizes[c];
         BL_CK(cudaMemcpyAsync(s.shape, (const char *)shape + off * ss, n * ss, cudaMemcpyHostToDevice, s.stream));
         BL_CK(cudaMemcpyAsync(s.z, z + off, n * sizeof(double), cudaMemcpyHostToDevice, s.stream));
         if (iter) BL_CK(cudaMemcpyAsync(s.iter, iter + off, n * sizeof(int), cudaMemcpyHostToDevice, s.stream));

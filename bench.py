@@ -45,7 +45,7 @@ KFLOP_PER_DRAW = {"pg1": 0.9, "hybrid": 0.786 * 9.0 + 0.058 * 3.0 + 0.15 * 0.3 +
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="hybrid", choices=["hybrid", "pg1"])
@@ -80,7 +80,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -91,19 +91,24 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [t.strip() for t in line.split(",")]))
 
-    def stop(self, t0, t1):
+    def stop(self, t0, t1, tw=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.3] or [r for _, r in self.rows]
+        # a row is stamped when it is READ, up to one polling period after nvidia-smi sampled it
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1]
+        window = "timed steps"
+        if len(rows) < 2 and tw is not None:     # a timed region shorter than two polling periods
+            rows = [r for t, r in self.rows if tw <= t <= t1 + 0.1]
+            window = "warm-up + timed steps (same kernels, back to back)"
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm = sorted(float(r[1]) for r in rows if len(r) > 2)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(len(r) > 5 + k and r[5 + k] == "Active" for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
-                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+                "samples": len(rows), "window": window, "power_w_max": max(float(r[3]) for r in rows)}
 
 
 def load_oracle():
@@ -216,10 +221,13 @@ def main():
         return float(t.item())
 
     # ---- device-resident timing ----------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(0.5)                                  # nvidia-smi start-up: first row after ~0.3 s
+    t_warm0 = time.time()
     for w in range(args.warmup):
         step_dev(1000 + w)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = L.bl_kernel_launches()
     t_wall0 = time.time()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -243,7 +251,7 @@ def main():
     if flush is None:
         kern_ms = ev[0].elapsed_time(ev[-1])
     kern_ms = max_over_ranks(kern_ms) / args.steps       # dominant kernel, per launch
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    clocks = sampler.stop(t_wall0, t_wall1, t_warm0) if sampler else None
     value = world * num * args.steps / (total_ms * 1e-3)
     mean_omega = float(x_d[: 1 << 20].mean().item())
     # dominant kernel of the step, timed live with CUDA events on the launch stream (separate,

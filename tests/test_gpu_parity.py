@@ -458,9 +458,11 @@ def test_dropin_entry_points_mirror_r_wrappers(engine, oracle, capsys):
 
 @pytest.mark.parametrize("method", ["devroye", "hybrid"])
 def test_large_batch_chunk_pipeline(engine, oracle, method):
-    """Several pipeline chunks (8M observations each, three slots in rotation) through the host-pointer
-    ABI: draws on both sides of the chunk boundaries equal the oracle's for the same global
-    observation index."""
+    """Many pipeline chunks (ramped schedule 1M, 2M, 4M, 8M ..., 4M, 2M, 1M; three slots in rotation)
+    through the host-pointer ABI: draws on both sides of every chunk boundary equal the oracle's for the
+    same global observation index, and the whole batch equals the device-resident entry point's."""
+    import torch
+    from bayeslogit_b200 import _lib
     M = 1 << 20
     num = 34 * M + 12345
     rng = np.random.default_rng(1)
@@ -472,9 +474,18 @@ def test_large_batch_chunk_pipeline(engine, oracle, method):
     x = engine.rpg_seeded(method, shape, z, seed=77, call_id=2)
     fn = getattr(oracle, "rpg_" + method)
     scale_all = normal_regime_amplification(shape, z) if method == "hybrid" else None
-    for i0 in (0, 8 * M - 2500, 16 * M - 2500, 24 * M - 2500, 32 * M - 2500, num - 5000):
+    tail = 27 * M + 12345            # 1+2+4 head, 8+8+(4M+12345) body, then 4M, 2M, 1M
+    bounds = [M, 3 * M, 7 * M, 15 * M, 23 * M, tail, tail + 4 * M, tail + 6 * M]
+    for i0 in [0] + [b - 2500 for b in bounds] + [num - 5000]:
         want = fn(shape[i0:i0 + 5000], z[i0:i0 + 5000], seed=77, call_id=2, obs0=i0)
         assert_close(x[i0:i0 + 5000], want, scale=None if scale_all is None else scale_all[i0:i0 + 5000])
+    dev = torch.device("cuda", 0)
+    sd, zd = torch.from_numpy(shape).to(dev), torch.from_numpy(z).to(dev)
+    xd = torch.empty(num, dtype=torch.float64, device=dev)
+    f_dev = getattr(_lib.lib(), "bl_rpg_%s_dev" % method)
+    _lib.check(f_dev(xd.data_ptr(), sd.data_ptr(), zd.data_ptr(), num, 77, 2, 0, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(x, xd.cpu().numpy()), "host pipeline and device-resident batch differ"
     if method == "devroye":
         m = 0.5 / z * np.tanh(z / 2)
         assert abs((x - m).mean()) < 5 * 0.2 / np.sqrt(num)
