@@ -50,6 +50,13 @@ cudaError_t launch_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint
 cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int64_t num,
                                   StreamId id, cudaStream_t stream, void *work = nullptr);
 
+// Fused psi = X beta + omega = PG(n, psi) of the logit sweeps (pg_devroye_kernel.cu); needs even P and a
+// 16-byte aligned tX (logit_psi_draw_ok).  chains > 1: rows [c N, (c+1) N) meet beta + c * beta_stride and
+// id.chain_len = N keys their streams by seed + c.
+bool logit_psi_draw_ok(const double *tX, int P);
+cudaError_t launch_logit_psi_draw(double *x, double *psi_out, const int *n, const double *tX, const double *beta,
+                                  int64_t beta_stride, int chains, int64_t N, int P, StreamId id, cudaStream_t stream);
+
 // rpg_hybrid through regime binning (pg_hybrid.cu); num <= 2^31-1, `work` = device scratch of
 // hybrid_workspace_bytes(num) bytes that stays valid until the stream has drained.
 size_t hybrid_workspace_bytes(int64_t num);

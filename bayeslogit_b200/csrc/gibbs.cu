@@ -408,6 +408,8 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
     GB_CK(mem.get(&bP, P));
     const bool keep_w = !(flags & BL_GIBBS_NO_W) && w_out;
     const int mode = (flags & BL_GIBBS_PLAIN_BETA) ? kBetaPlain : kBetaConstrained;
+    // psi = X beta and the omega draw as one pass over X (k_logit_psi_draw) unless asked otherwise
+    const bool fused = !(flags & BL_GIBBS_UNFUSED) && logit_psi_draw_ok(tX, P);
 
     // set_prior / set_bP: b0 = P0 m0, bP = b0 + X'(n (y - 1/2))   (Logit.hpp:174-190)
     k_kappa<<<cdiv(N, 256), 256, 0, st>>>(kappa, y, n, 0.0, N);
@@ -432,11 +434,14 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
         int iters = phase == 0 ? burn : samp;
         double *bcur = beta_out, *bprev = beta_out;
         double *wcur = keep_w ? w_out : s.w;
-        s.xbeta(s.psi, bcur, nullptr, 0.0);
+        const double *bpsi = bcur;                                    // the beta the next omega draw conditions on
+        if (!fused) s.xbeta(s.psi, bcur, nullptr, 0.0);
         for (int m = 1; m <= iters; ++m, ++t) {
             const bool tm = timing && phase == 1 && m == iters;       // BL_GIBBS_TIMING=1: stage times
             if (tm) cudaEventRecord(ev[0], st);
-            cudaError_t e = launch_devroye_refill(wcur, shape, s.psi, N, StreamId{seed, obs0, t}, st);
+            cudaError_t e = fused
+                ? launch_logit_psi_draw(wcur, nullptr, shape, tX, bpsi, 0, 1, N, P, StreamId{seed, obs0, t}, st)
+                : launch_devroye_refill(wcur, shape, s.psi, N, StreamId{seed, obs0, t}, st);
             if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
             if (tm) cudaEventRecord(ev[1], st);
             s.gram(wcur);
@@ -445,14 +450,15 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
             if (tm) cudaEventRecord(ev[3], st);
             s.beta_draw(mode, P0, bP, false, bprev, bcur, seed, t);
             if (tm) cudaEventRecord(ev[4], st);
-            s.xbeta(s.psi, bcur, nullptr, 0.0);
+            bpsi = bcur;
+            if (!fused) s.xbeta(s.psi, bcur, nullptr, 0.0);
             if (tm) {
                 cudaEventRecord(ev[5], st);
                 cudaEventSynchronize(ev[5]);
                 float d[5];
                 for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&d[k], ev[k], ev[k + 1]);
-                fprintf(stderr, "[bl gibbs timing, us] draw %.1f gram %.1f allreduce %.1f beta %.1f xbeta %.1f\n",
-                        d[0] * 1e3, d[1] * 1e3, d[2] * 1e3, d[3] * 1e3, d[4] * 1e3);
+                fprintf(stderr, "[bl gibbs timing, us] %s %.1f gram %.1f allreduce %.1f beta %.1f xbeta %.1f\n",
+                        fused ? "psi+draw" : "draw", d[0] * 1e3, d[1] * 1e3, d[2] * 1e3, d[3] * 1e3, d[4] * 1e3);
             }
             if (phase == 1) {
                 bprev = bcur;
@@ -535,6 +541,7 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
             k_xbeta_chains<<<grid, 256, 0, st>>>(psi, tX, beta, bstride, chains, (int)N, P);
         count_launch();
     };
+    const bool fused = !(flags & BL_GIBBS_UNFUSED) && logit_psi_draw_ok(tX, P);
     const bool timing = getenv("BL_GIBBS_TIMING") != nullptr;
     cudaEvent_t ev[6];
     if (timing) for (auto &x : ev) cudaEventCreate(&x);
@@ -542,12 +549,14 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
     for (int phase = 0; phase < 2; ++phase) {
         int iters = phase == 0 ? burn : samp;
         double *bcur = beta_out, *bprev = beta_out;
-        xbeta(bcur);
+        const double *bpsi = bcur;
+        if (!fused) xbeta(bcur);
         for (int m = 1; m <= iters; ++m, ++t) {
             const bool tm = timing && phase == 1 && m == iters;       // BL_GIBBS_TIMING=1: stage times
             if (tm) cudaEventRecord(ev[0], st);
             StreamId id{seed, 0, t, (uint32_t)N};
-            cudaError_t e = launch_devroye_refill(w, shape, psi, T, id, st, work);
+            cudaError_t e = fused ? launch_logit_psi_draw(w, nullptr, shape, tX, bpsi, bstride, chains, N, P, id, st)
+                                  : launch_devroye_refill(w, shape, psi, T, id, st, work);
             if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
             if (tm) cudaEventRecord(ev[1], st);
             if (nt > 1)
@@ -563,7 +572,8 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
                                                            PeerWait{}, bstride);
             count_launch(3);
             if (tm) cudaEventRecord(ev[4], st);
-            xbeta(bcur);
+            bpsi = bcur;
+            if (!fused) xbeta(bcur);
             if (tm) {
                 cudaEventRecord(ev[5], st);
                 cudaEventSynchronize(ev[5]);

@@ -360,8 +360,6 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int grp = warp >> 2, sub = warp & 3, si = sub >> 1, sj = sub & 1;
-    const bool live = !(diag && si > sj);
-    const bool tri = diag && si == sj;                 // diagonal sub-tile: MMA tiles with mi <= mj only
 
     double c[4][4][2] = {};
     double c9[9][2] = {};                               // kBalancedDiag: this warp's 9 tiles
@@ -427,7 +425,19 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
             case 2: gram_diag_chunk<2, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
             default: gram_diag_chunk<3, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
             }
-        } else if (live) {
+        } else if (diag) {
+            // a diagonal tile of a P > 64 Gram: the balanced deal of its 36 live MMA tiles (9 per warp,
+            // all 8 warps busy) instead of 32 x 32 sub-tiles (one warp of four idle, one with 16 tiles:
+            // the tile then cost as much as an off-diagonal one).  The 9 accumulators live in c's registers.
+            double (&cd)[9][2] = reinterpret_cast<double (&)[9][2]>(c);
+            const double *chunk = gsm + cur * stage_elems;
+            switch (sub) {
+            case 0: gram_diag_chunk<0, kRows>(cd, chunk, chunk + w_off, grp, gid, tig); break;
+            case 1: gram_diag_chunk<1, kRows>(cd, chunk, chunk + w_off, grp, gid, tig); break;
+            case 2: gram_diag_chunk<2, kRows>(cd, chunk, chunk + w_off, grp, gid, tig); break;
+            default: gram_diag_chunk<3, kRows>(cd, chunk, chunk + w_off, grp, gid, tig); break;
+            }
+        } else {
             const int so = cur * stage_elems;
             const int pa = so + si * 32 + gid;                                         // A: panel bi
             const int pb = so + (npanel - 1) * kRows * kGramLdm + sj * 32 + gid;   // B: panel bj
@@ -445,7 +455,7 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
                 for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                     for (int mj = 0; mj < 4; ++mj)
-                        if (!tri || mi <= mj) dmma884(c[mi][mj][0], c[mi][mj][1], a[mi], b[mj]);
+                        dmma884(c[mi][mj][0], c[mi][mj][1], a[mi], b[mj]);
             }
         }
         cur = cur + 1 == kGramStages ? 0 : cur + 1;
@@ -484,16 +494,23 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
         case 2: gram_diag_store<2>(c9, out, gid, tig); break;
         default: gram_diag_store<3>(c9, out, gid, tig); break;
         }
-    } else if (live) {
+    } else if (diag) {
+        const double (&cd)[9][2] = reinterpret_cast<const double (&)[9][2]>(c);
+        switch (sub) {
+        case 0: gram_diag_store<0>(cd, out, gid, tig); break;
+        case 1: gram_diag_store<1>(cd, out, gid, tig); break;
+        case 2: gram_diag_store<2>(cd, out, gid, tig); break;
+        default: gram_diag_store<3>(cd, out, gid, tig); break;
+        }
+    } else {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int mj = 0; mj < 4; ++mj)
-                if (!tri || mi <= mj) {
-                    int row = si * 32 + mi * 8 + gid, col = sj * 32 + mj * 8 + 2 * tig;
-                    out[row * kGramTile + col] = c[mi][mj][0];
-                    out[row * kGramTile + col + 1] = c[mi][mj][1];
-                }
+            for (int mj = 0; mj < 4; ++mj) {
+                int row = si * 32 + mi * 8 + gid, col = sj * 32 + mj * 8 + 2 * tig;
+                out[row * kGramTile + col] = c[mi][mj][0];
+                out[row * kGramTile + col + 1] = c[mi][mj][1];
+            }
     }
 }
 

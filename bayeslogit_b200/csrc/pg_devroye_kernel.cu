@@ -13,6 +13,8 @@
 // Work split: the batch is cut into chunks of kChunkObs observations dealt
 // round-robin to warps, so a drift of z along the array cannot unbalance the SMs.
 // HBM traffic: z and n in, omega out -- coalesced in runs of consecutive indices.
+#include <algorithm>
+
 #include "engine.h"
 #include "pg_devroye_fast.cuh"
 
@@ -146,6 +148,98 @@ k_devroye_refill(double *__restrict__ x, const int *__restrict__ n, const double
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused sweep half-step of the logit samplers: psi_i = x_i . beta and omega_i = PG(n_i, psi_i) in one
+// pass over X (Logit.hpp:421,431 then Logit::draw_w :283-289; the two statements are adjacent in
+// gibbs_block and psi has no other reader).  Separately the two kernels are bound by different
+// things -- k_xbeta_mma by HBM (N P 8 bytes, 18 % of the issue slots), the draw by the issue slots
+// (16 bytes per row of HBM) -- so one kernel whose warps alternate between the two phases lets some
+// warps' row loads fly while others draw.
+//   trip  : a warp takes 32 consecutive rows.  psi exactly as k_xbeta_mma forms it (same fragment
+//           layout, same MMA order: the bits of psi are those of the two-kernel path): lane
+//           (gid, tig) loads X[i0 + 8 rb + gid][c0 + 2 tig, +1], every column of accumulator rb
+//           holds psi of rows i0 + 8 rb + 0..7.
+//   hand-over: lane l takes row i0 + l = accumulator l >> 3, row-in-tile l & 7, read from lane
+//           (l & 7) << 2 by four shuffles.
+//   draw  : the per-lane Devroye loop of the refill kernel (dev_propose), stream keyed by the global
+//           observation index; PG(1, z) accepts 99.9 % of its first proposals, so the refill
+//           machinery of k_devroye_refill buys nothing here -- lanes differ by proposal branch only.
+// Chains: rows [c N, (c+1) N) meet beta + c * beta_stride and the streams of seed + c (trips never
+// straddle two chains).  psi_out may be null.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884_f(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
+k_logit_psi_draw(double *__restrict__ x, double *__restrict__ psi_out, const int *__restrict__ n,
+                 const double *__restrict__ tX, const double *__restrict__ beta, int64_t beta_stride,
+                 int chains, int64_t N, int P, StreamId id)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+    const int64_t tpc = (N + 31) >> 5;                               // 32-row trips per chain
+    const int64_t trips = (int64_t)chains * tpc;
+    const int64_t warps = (int64_t)gridDim.x * (kThreads >> 5);
+    const int64_t wid = (int64_t)blockIdx.x * (kThreads >> 5) + (threadIdx.x >> 5);
+    for (int64_t trip = wid; trip < trips; trip += warps) {
+        const int64_t ch = chains > 1 ? trip / tpc : 0;
+        const int64_t i0 = (trip - ch * tpc) << 5;
+        const double *bc = beta + ch * beta_stride + 2 * tig;
+        const double *base = tX + ((size_t)ch * N + i0 + gid) * P + 2 * tig;
+        double c[4][2] = {};
+        bool rv[4];
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb) rv[rb] = i0 + 8 * rb + gid < N;
+#pragma unroll 2
+        for (int c0 = 0; c0 < P; c0 += 8) {
+            const bool cv = c0 + 2 * tig < P;
+            double2 a[4];
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb)
+                a[rb] = (cv && rv[rb]) ? __ldg(reinterpret_cast<const double2 *>(base + (size_t)(8 * rb) * P + c0))
+                                       : make_double2(0.0, 0.0);
+            const double b0 = cv ? __ldg(bc + c0) : 0.0, b1 = cv ? __ldg(bc + c0 + 1) : 0.0;
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb) {
+                dmma884_f(c[rb][0], c[rb][1], a[rb].x, b0);
+                dmma884_f(c[rb][0], c[rb][1], a[rb].y, b1);
+            }
+        }
+        double z = 0.0;
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb) {
+            const double t = __shfl_sync(full, c[rb][0], (lane & 7) << 2);
+            if ((lane >> 3) == rb) z = t;
+        }
+        const int64_t i = i0 + lane;
+        if (i < N) {
+            const int64_t g = ch * N + i;
+            if (psi_out) psi_out[g] = z;
+            const int ni = n[g];
+            if (ni == 0) {
+                x[g] = 0.0;                                          // LogitWrapper.cpp:76-79
+            } else {
+                int remaining = ni < 1 ? 1 : ni;                     // NTHROW clamp, PolyaGamma.cpp:128-135
+                DevSetup st = dev_setup(z);
+                PhiloxSource src;
+                if (id.chain_len) src.open(id.seed + (uint64_t)ch, id.obs0 + (uint64_t)i, id.call_id);
+                else src.open(id.seed, id.obs0 + (uint64_t)i, id.call_id);
+                double sum = 0.0;
+                do {
+                    double X;
+                    while (!dev_propose(src, st, X)) {}
+                    sum += 0.25 * X;
+                } while (--remaining);
+                x[g] = sum;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int64_t num,
@@ -174,6 +268,29 @@ cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int6
         k_devroye_refill<false><<<grid, kThreads, 0, st>>>(x, n, z, num, id, nullptr, chunk);
         count_launch();
     }
+    return cudaGetLastError();
+}
+
+}  // namespace bl
+
+namespace bl {
+
+bool logit_psi_draw_ok(const double *tX, int P) { return P % 2 == 0 && (reinterpret_cast<uintptr_t>(tX) & 15) == 0; }
+
+// omega (and psi, when psi_out is given) for `chains` blocks of N rows each; see k_logit_psi_draw.
+cudaError_t launch_logit_psi_draw(double *x, double *psi_out, const int *n, const double *tX, const double *beta,
+                                  int64_t beta_stride, int chains, int64_t N, int P, StreamId id, cudaStream_t st)
+{
+    if (N <= 0 || chains <= 0) return cudaSuccess;
+    const int64_t trips = (int64_t)chains * ((N + 31) / 32);
+    const int wpc = kThreads / 32;
+    // three CTAs of 80 registers per SM: with 128 registers (the 16 loads of k_xbeta_mma in flight per
+    // lane) only 16 warps are resident and the draw phases of some warps do not cover the load phases of
+    // the others -- 189 us against 105 + 86 for the two kernels at N = 1M, P = 64; with 8 loads in flight
+    // and 24 warps 172 us (P = 32: 104 against 122; P = 128: 252 against 281).
+    int grid = (int)std::min<int64_t>(148 * 3, std::max<int64_t>(1, (trips + wpc - 1) / wpc));
+    k_logit_psi_draw<<<grid, kThreads, 0, st>>>(x, psi_out, n, tX, beta, beta_stride, chains, N, P, id);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -161,6 +161,8 @@ int bl_rpg_hybrid_tape(double *x, const double *h, const double *z, int64_t num,
 #define BL_GIBBS_PLAIN_BETA 1   /* unconstrained beta ~ N(PP^-1 bP, PP^-1) (Logit.hpp:291-320) instead of
                                    the constrained coordinate-wise draw the reference calls (:322-400) */
 #define BL_GIBBS_NO_W 2         /* do not return the omega chains (w may be NULL) */
+#define BL_GIBBS_UNFUSED 4      /* measurement / A-B aid: psi = X beta and the omega draw as two kernels instead of
+                                   the fused pass over X (same chain, bit for bit) */
 
 /* `gibbs` with an explicit seed and flags; host pointers, layouts as `gibbs`. */
 int bl_logit_gibbs(double *w, double *beta, const double *y, const double *tX, const double *n,

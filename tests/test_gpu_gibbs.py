@@ -189,3 +189,25 @@ def test_dropin_logit_and_mlogit_wrappers(gapi, engine):
     om = gapi.mlogit(Y, Xm, samp=200, burn=100, P0=np.stack([0.01 * np.eye(P)] * (J - 1), axis=2))
     assert om["beta"].shape == (200, P, J - 1) and om["w"].shape == (200, N, J - 1)
     assert np.max(np.abs(om["beta"].mean(0) - B)) < 0.3
+
+
+@pytest.mark.parametrize("N,P,binomial", [(4099, 64, False), (2000, 6, True), (1777, 34, False)])
+def test_fused_psi_draw_equals_two_kernel_path(gapi, N, P, binomial):
+    """k_logit_psi_draw (psi = X beta and omega = PG(n, psi) in one pass over X) forms psi with the MMA
+    order of k_xbeta_mma and draws with the sampler of k_devroye_refill: the chain -- omega and beta
+    -- must carry the same bits as the two-kernel path (flag BL_GIBBS_UNFUSED), single chain and
+    batched chains, ragged last trip (N not a multiple of 32) and n_i in {1..5} included."""
+    X, y, n, _ = synth_logit(N, P, 77 + P, binomial)
+    m0 = np.zeros(P)
+    P0 = 0.3 * np.eye(P)
+    w1, b1 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=5, flags=1)
+    w2, b2 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=5, flags=1 | 4)
+    assert np.array_equal(w1, w2) and np.array_equal(b1, b2)
+    assert np.all(w1 > 0) and np.all(np.isfinite(b1))
+    C_ = 3
+    Xc = np.stack([synth_logit(N, P, 200 + c, binomial)[0] for c in range(C_)])
+    yc = np.stack([synth_logit(N, P, 200 + c, binomial)[1] for c in range(C_)])
+    nc = np.stack([synth_logit(N, P, 200 + c, binomial)[2] for c in range(C_)])
+    c1 = gapi.logit_chains(yc, Xc, nc, m0, P0, 5, 2, seed=9, flags=1)
+    c2 = gapi.logit_chains(yc, Xc, nc, m0, P0, 5, 2, seed=9, flags=1 | 4)
+    assert np.array_equal(c1, c2)

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(chains, N, P, iters, constrained, rank, world, local, serial_sample=16):
+def run(chains, N, P, iters, constrained, rank, world, local, serial_sample=16, unfused=False):
     """Chains are block-distributed over the ranks (no communication); returns this rank's figures."""
     import torch
     from bayeslogit_b200 import _lib
@@ -33,7 +33,7 @@ def run(chains, N, P, iters, constrained, rank, world, local, serial_sample=16):
     n = torch.ones(C, N, device=dev, dtype=torch.float64)
     m0 = torch.zeros(P, device=dev, dtype=torch.float64)
     P0 = (0.01 * torch.eye(P, device=dev, dtype=torch.float64)).contiguous()
-    flags = 0 if constrained else 1
+    flags = (0 if constrained else 1) | (4 if unfused else 0)
     st = torch.cuda.current_stream().cuda_stream
 
     def batch(k):
@@ -76,6 +76,7 @@ def run(chains, N, P, iters, constrained, rank, world, local, serial_sample=16):
             "chains": C * world, "chains_per_gpu": C, "N": N, "P": P, "iters": iters,
             "launches_per_iteration": launches / iters,
             "beta_draw": "constrained" if constrained else "plain",
+            "psi_and_draw": "two kernels" if unfused else "one pass over X",
             "one_after_the_other_chain_iters_per_sec_one_gpu": S * iters / (ms1 * 1e-3) if S else None,
             "serial_sample_chains": S,
             "max_abs_diff_batched_vs_single_entry": same,
@@ -91,6 +92,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--constrained", action="store_true")
     ap.add_argument("--serial-sample", type=int, default=16)
+    ap.add_argument("--unfused", action="store_true")
     a = ap.parse_args()
     import torch
     from bayeslogit_b200 import _lib
@@ -101,7 +103,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    out = run(a.chains, a.N, a.P, a.iters, a.constrained, rank, world, local, a.serial_sample)
+    out = run(a.chains, a.N, a.P, a.iters, a.constrained, rank, world, local, a.serial_sample, a.unfused)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
