@@ -258,7 +258,7 @@ struct Sweep {
     double *psi = nullptr, *w = nullptr, *acc = nullptr, *part = nullptr, *xtv_part = nullptr;
     double *gwork = nullptr;
     int *status = nullptr;
-    int nt = 1, nslab = 1, xtv_slabs = 1;
+    int nt = 1, nslab = 1, nslab_diag = 0, xtv_slabs = 1;
     bool use_smem = true;
     size_t beta_smem = 0;
     bool exchange = false;  // sharded sweep: the Gram (+ tail) sums are exchanged between ranks before the beta draw
@@ -272,6 +272,15 @@ struct Sweep {
         int tiles = nt * (nt + 1) / 2;
         nslab = (int)std::min<int64_t>(std::max<int64_t>(1, 148 * 2 / tiles), std::max<int64_t>(1, N / (4 * kGramRows)));   // 2 CTAs/SM resident: one wave
         if (nslab < 1) nslab = 1;
+        if (nt > 1) {
+            // one wave of 2 CTAs per SM, slabs in proportion to the tile's cost (diagonal 36, off-diagonal 64
+            // MMA tiles per k-step): P = 256 -> 4 x 20 + 6 x 35 CTAs instead of 10 x 29 of unequal length
+            const int nd = nt, no = nt * (nt - 1) / 2, total = nd * 36 + no * 64;
+            const int64_t cap = std::max<int64_t>(1, N / (4 * kGramRows));
+            nslab = (int)std::min<int64_t>(std::max(1, 148 * 2 * 64 / total), cap);
+            nslab_diag = (int)std::min<int64_t>(std::max(1, 148 * 2 * 36 / total), cap);
+            if (nslab_diag > nslab) nslab_diag = nslab;
+        }
         xtv_slabs = (int)std::min<int64_t>(148 * 2, std::max<int64_t>(1, N / 64));
         GB_CK(m.get(&psi, N));
         GB_CK(m.get(&w, N));
@@ -313,7 +322,7 @@ struct Sweep {
         int tiles = nt * (nt + 1) / 2;
         const bool packed = gram_packed(P);
         if (nt > 1)
-            k_gram_partial<kGramRows, false><<<dim3(nslab, tiles), 256, gram_smem_bytes(true), st>>>(part, tX, wv, N, P, nt);
+            k_gram_partial<kGramRows, false><<<dim3(nslab, tiles), 256, gram_smem_bytes(true), st>>>(part, tX, wv, N, P, nt, nslab_diag);
         else if (packed)
             k_gram_partial<kGramRowsDiag, true, true><<<dim3(nslab, tiles), 256, gram_smem_bytes(false, true), st>>>(part, tX, wv, N, P, nt);
         else
@@ -335,7 +344,8 @@ struct Sweep {
             }
             pending.flag = (const unsigned *)g_peer.base + par * kMaxPeers;
         }
-        k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nt > 1 ? 2 * nslab : nslab, px, packed ? 1 : 0);
+        k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nt > 1 ? 2 * nslab : nslab, px, packed ? 1 : 0,
+                                                                2 * nslab_diag);
         count_launch(2);
     }
 

@@ -339,7 +339,7 @@ __device__ __forceinline__ void gram_pack_store(const double (&c)[9][2], double 
 template <int kRows, bool kBalancedDiag, bool kPacked = false>
 __global__ void __launch_bounds__(256)
 k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const double *__restrict__ w,
-               int64_t N, int P, int nt)
+               int64_t N, int P, int nt, int nslab_diag = 0)
 {
     extern __shared__ __align__(16) double gsm[];
     const int nthr = blockDim.x;
@@ -361,9 +361,14 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
     const int gid = lane >> 2, tig = lane & 3;
     const int grp = warp >> 2, sub = warp & 3, si = sub >> 1, sj = sub & 1;
 
+    // P > 64: a diagonal tile costs 36 MMA tiles per k-step against 64 for an off-diagonal one, so its
+    // rows are cut into fewer, longer slabs (nslab_diag of them; CTAs past that leave) and every CTA of
+    // the single wave carries the same work.  Partial tiles keep the uniform stride of gridDim.x slabs.
+    const int ns = (!kBalancedDiag && diag && nslab_diag > 0) ? nslab_diag : (int)gridDim.x;
+    if ((int)blockIdx.x >= ns) return;
     double c[4][4][2] = {};
     double c9[9][2] = {};                               // kBalancedDiag: this warp's 9 tiles
-    int64_t slab = (N + gridDim.x - 1) / gridDim.x;
+    int64_t slab = (N + ns - 1) / ns;
     if (kPacked) slab = (slab + 1) & ~(int64_t)1;               // packed rows pair observations (2r, 2r+1) of the chain
     const int64_t r0 = (int64_t)blockIdx.x * slab;
     const int64_t r1 = r0 + slab < N ? r0 + slab : N;
@@ -683,7 +688,8 @@ __device__ __forceinline__ void peer_stage(const PeerWait &pw, double *A, double
 // 32 upper-triangle candidates, its 8 warps split the slabs, fixed summation order.
 __global__ void __launch_bounds__(256)
 k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
-              const double *__restrict__ part, int P, int nt, int nslab, PeerPush px, int packed = 0)
+              const double *__restrict__ part, int P, int nt, int nslab, PeerPush px, int packed = 0,
+              int nslab_diag = 0)      // nslab: partial tiles per output tile (stride); diagonal tiles hold nslab_diag of them (0: nslab)
 {
     __shared__ double red[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -702,14 +708,15 @@ k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
         int la = a % kGramTile, lb = b % kGramTile;
         // a diagonal tile holds (row, col) wherever (row >> 3) <= (col >> 3): true for every la <= lb
         const double *src = part + (size_t)tile * nslab * (kGramTile * kGramTile) + la * kGramTile + lb;
+        const int cnt = (bi == bj && nslab_diag > 0) ? nslab_diag : nslab;
 #pragma unroll 8
-        for (int k = warp; k < nslab; k += 8) s += src[(size_t)k * (kGramTile * kGramTile)];
+        for (int k = warp; k < cnt; k += 8) s += src[(size_t)k * (kGramTile * kGramTile)];
         if (packed) {
             // the odd observations' sums sit in the second diagonal 32 x 32 block of the tile
             const double *src2 = src + 32 * kGramTile + 32;
             double s2 = 0.0;
 #pragma unroll 8
-            for (int k = warp; k < nslab; k += 8) s2 += src2[(size_t)k * (kGramTile * kGramTile)];
+            for (int k = warp; k < cnt; k += 8) s2 += src2[(size_t)k * (kGramTile * kGramTile)];
             s += s2;
         }
     }

@@ -48,8 +48,11 @@ def close(a, b, rel=CHAIN_REL):
 
 
 @pytest.mark.parametrize("constrained", [False, True])
-@pytest.mark.parametrize("N,P,binomial", [(3000, 7, False), (1500, 64, False), (2000, 5, True), (700, 70, False), (1501, 32, False), (3000, 128, False)])
+@pytest.mark.parametrize("N,P,binomial", [(3000, 7, False), (1500, 64, False), (2000, 5, True), (700, 70, False), (1501, 32, False), (3000, 128, False),
+                                          (40000, 72, False)])
 def test_logit_chain_matches_oracle(gapi, constrained, N, P, binomial):
+    # N = 40000, P = 72: enough rows for the cost-proportional slab counts of the P > 64 Gram (diagonal
+    # tiles cut into fewer slabs than off-diagonal ones; smaller N caps both at N / 128).
     # P = 128 runs the beta draw out of global scratch (2 P^2 doubles exceed shared memory) and the
     # four-way column rotation of k_xtv_stream.  N is kept >= ~20 P: the constrained draw starts on
     # the constraint boundary (beta = 0), where its truncation windows are a few ulps wide and the
