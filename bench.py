@@ -173,6 +173,12 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    # Exactly ONE line on stdout: native libraries write there too (NCCL prints its version banner on
+    # rank 0 when NCCL_DEBUG is set), so file descriptor 1 points at stderr for the duration of the run
+    # and the JSON line goes to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -461,7 +467,8 @@ def main():
                                      "peak_source": "nominal B200 vector FP64 (no measured FP64 peak in MEASURED_PEAKS.json)"}},
             "cpu_baseline": cpu, "mean_omega_first_1M": mean_omega, "extras": extras,
         }
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -10,3 +10,4 @@ d=json.load(open("gpurun_out/${T}_bench.json"))
 print("value %.4g e2e %.4g bound %.4g clocks %s" % (d["value"], d["e2e"]["value"], d["e2e"]["pcie_bound_draws_per_s"], d["clocks"]))
 PY
 BL_GIBBS_TIMING=1 timeout 120 python tools/bench_gibbs.py --iters 100 > gpurun_out/${T}_gibbs.log 2>&1; tail -3 gpurun_out/${T}_gibbs.log
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --no-extras --no-cpu-baseline > gpurun_out/${T}_ncu_bench.log 2>&1; echo "ncu launch list rc=$?"
