@@ -20,6 +20,7 @@ NA = float("nan")
 
 PLAIN_BETA = 1   # BL_GIBBS_PLAIN_BETA
 NO_W = 2         # BL_GIBBS_NO_W
+UNFUSED = 4      # BL_GIBBS_UNFUSED (psi = X beta and the omega draw as two kernels; A/B aid)
 
 
 def _f(a):

@@ -204,7 +204,7 @@ def test_fused_psi_draw_equals_two_kernel_path(gapi, N, P, binomial):
     m0 = np.zeros(P)
     P0 = 0.3 * np.eye(P)
     w1, b1 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=5, flags=1)
-    w2, b2 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=5, flags=1 | 4)
+    w2, b2 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=5, flags=gapi.PLAIN_BETA | gapi.UNFUSED)
     assert np.array_equal(w1, w2) and np.array_equal(b1, b2)
     assert np.all(w1 > 0) and np.all(np.isfinite(b1))
     C_ = 3
@@ -212,5 +212,5 @@ def test_fused_psi_draw_equals_two_kernel_path(gapi, N, P, binomial):
     yc = np.stack([synth_logit(N, P, 200 + c, binomial)[1] for c in range(C_)])
     nc = np.stack([synth_logit(N, P, 200 + c, binomial)[2] for c in range(C_)])
     c1 = gapi.logit_chains(yc, Xc, nc, m0, P0, 5, 2, seed=9, flags=1)
-    c2 = gapi.logit_chains(yc, Xc, nc, m0, P0, 5, 2, seed=9, flags=1 | 4)
+    c2 = gapi.logit_chains(yc, Xc, nc, m0, P0, 5, 2, seed=9, flags=gapi.PLAIN_BETA | gapi.UNFUSED)
     assert np.array_equal(c1, c2)
