@@ -60,6 +60,7 @@ bool nccl_load(std::string &err)
 }
 
 constexpr int kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+constexpr int kNcclInt32 = 2, kNcclUint64 = 5, kNcclMax = 2;
 
 // ------------------------------------------------------------------------------------
 // Peer exchange over NVLink (one node): every rank owns one cudaMalloc'd window that its peers
@@ -745,8 +746,9 @@ int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const doub
 // draw.df, NB-Shape.R:9-53): per iteration phi = X beta; d | beta by one random-walk
 // Metropolis step; psi = phi - log d; omega = PG(y + d, psi); beta | omega, d.  d, log d and
 // everything derived from them stay on the device.  beta_out: P x samp, d_out: samp (recorded
-// past burn-in), w_out: N (last omega) or null.  One GPU: the N-term log-likelihood sums are not
-// all-reduced.
+// past burn-in), w_out: N (last omega) or null.  Sharded rows (communicator open): ymax, the histogram
+// behind G and, every iteration, the four N-term log-likelihood sums are all-reduced (NCCL, 4 doubles);
+// the Metropolis uniforms come from a stream every rank shares, so d stays identical on all ranks.
 // ------------------------------------------------------------------------------------
 int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const double *y, const double *tX,
                        double d0, const double *m0, const double *P0, int64_t N, int P, int samp, int burn,
@@ -756,11 +758,11 @@ int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const dou
         err = "nb_gibbs_df: bad arguments (d0 must be a positive integer)";
         return 1;
     }
-    if (g_nccl.world > 1 && g_nccl.comm) { err = "nb_gibbs_df: sharded data is not supported"; return 1; }
+    const bool sharded = g_nccl.world > 1 && g_nccl.comm;
     DevMem mem;
     mem.st = st;
     Sweep s;
-    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX;
+    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX; s.exchange = true;
     if (s.init(mem, err)) return 1;
     double *kappa, *b0, *shape, *bcur, *dpair, *G, *dfpart;
     int *ymax_d;
@@ -774,9 +776,17 @@ int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const dou
     GB_CK(mem.get((char **)&work, hybrid_workspace_bytes(N)));
     const int nblk = (int)std::min<int64_t>(148 * 4, std::max<int64_t>(1, N / 1024));
     GB_CK(mem.get(&dfpart, (size_t)nblk * 4));
+    double *dfsum;
+    GB_CK(mem.get(&dfsum, 4));
+    auto nccl_ck = [&](int r, const char *what) {
+        if (r == 0) return 0;
+        err = std::string("nb_gibbs_df: ncclAllReduce (") + what + "): " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+        return 1;
+    };
     // ymax, G
     GB_CK(cudaMemsetAsync(ymax_d, 0, sizeof(int), st));
     k_nb_ymax<<<148 * 2, 256, 0, st>>>(ymax_d, y, N);
+    if (sharded && nccl_ck(g_nccl.AllReduce(ymax_d, ymax_d, 1, kNcclInt32, kNcclMax, g_nccl.comm, st), "ymax")) return 1;
     int ymax = 0;
     GB_CK(cudaMemcpyAsync(&ymax, ymax_d, sizeof(int), cudaMemcpyDeviceToHost, st));
     GB_CK(cudaStreamSynchronize(st));
@@ -785,6 +795,7 @@ int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const dou
     GB_CK(mem.get(&G, (size_t)ymax + 1));
     GB_CK(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * ((size_t)ymax + 2), st));
     k_nb_hist<<<148 * 2, 256, 0, st>>>(hist, y, N);
+    if (sharded && nccl_ck(g_nccl.AllReduce(hist, hist, (size_t)ymax + 2, kNcclUint64, kNcclSum, g_nccl.comm, st), "histogram")) return 1;
     k_nb_suffix<<<1, 1, 0, st>>>(G, hist, ymax);
     k_matvec<<<cdiv(P, 128), 128, 0, st>>>(b0, P0, m0, P);
     count_launch(4);
@@ -797,8 +808,13 @@ int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const dou
         double *bnext = t >= burn ? beta_out + (size_t)P * (t - burn) : bcur + (size_t)P * ((t + 1) & 1);
         s.xbeta(s.psi, bprev, nullptr, 0.0);                                   // phi = X beta
         k_nb_df_partial<<<nblk, 256, 0, st>>>(dfpart, s.psi, y, dpair, N, seed, (uint32_t)t);
-        k_nb_df_decide<<<1, 32, 0, st>>>(dpair, dpair + 1, t >= burn ? d_out + (t - burn) : nullptr, dfpart, nblk, G,
-                                         ymax, seed, (uint32_t)t);
+        if (sharded) {
+            k_nb_df_fold<<<1, 32, 0, st>>>(dfsum, dfpart, nblk);
+            count_launch();
+            if (nccl_ck(g_nccl.AllReduce(dfsum, dfsum, 4, kNcclFloat64, kNcclSum, g_nccl.comm, st), "log-likelihood sums")) return 1;
+        }
+        k_nb_df_decide<<<1, 32, 0, st>>>(dpair, dpair + 1, t >= burn ? d_out + (t - burn) : nullptr,
+                                         sharded ? dfsum : dfpart, sharded ? 1 : nblk, G, ymax, seed, (uint32_t)t);
         k_nb_prepare<<<cdiv(N, 256), 256, 0, st>>>(s.psi, shape, kappa, y, dpair, dpair + 1, N);
         count_launch(3);
         StreamId id{seed, obs0, (uint32_t)t};
@@ -806,8 +822,9 @@ int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const dou
             ? launch_hybrid_binned(w, shape, s.psi, (int)N, id, work, st)
             : launch_rpg(kHybrid, w, shape, s.psi, N, 0, nullptr, id, st);
         if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
-        s.gram(w);
         s.xtv(kappa, 1.0, w, nullptr, 0.0, dpair + 1);                         // X'(kappa + omega log d)
+        s.gram(w, true);
+        if (s.allreduce(true, err)) return 1;
         s.beta_draw(kBetaPlain, P0, b0, true, nullptr, bnext, seed, (uint32_t)t);
         // the next iteration reads beta from where this one wrote it
         if (t >= burn) {

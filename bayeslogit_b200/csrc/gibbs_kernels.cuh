@@ -1034,6 +1034,21 @@ k_nb_df_partial(double *__restrict__ part, const double *__restrict__ phi, const
     }
 }
 
+// Sharded rows: the CTA partials of this rank's rows folded to the four sums (fixed order) that the
+// ranks then all-reduce; k_nb_df_decide reads the result as a single partial.
+__global__ void k_nb_df_fold(double *__restrict__ sum4, const double *__restrict__ part, int nblk)
+{
+    const int lane = threadIdx.x;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = lane; b < nblk; b += 32)
+        for (int k = 0; k < 4; ++k) s[k] += part[(size_t)b * 4 + k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        for (int o = 16; o; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    if (lane == 0)
+        for (int k = 0; k < 4; ++k) sum4[k] = s[k];
+}
+
 __global__ void k_nb_df_decide(double *__restrict__ dptr, double *__restrict__ ldptr, double *__restrict__ d_rec,
                                const double *__restrict__ part, int nblk, const double *__restrict__ G, int ymax,
                                uint64_t seed, uint32_t call)

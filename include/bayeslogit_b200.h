@@ -197,7 +197,8 @@ int bl_mlogit_gibbs_dev(double *w, double *beta, const double *ty, const double 
 int bl_nb_gibbs_dev(double *w_last, double *beta, const double *y, const double *tX, double d,
                     const double *m0, const double *P0, int64_t N, int P, int samp, uint64_t seed,
                     uint64_t obs0, void *stream);
-/* single GPU only: the dispersion update's log-likelihood sums are not all-reduced */
+/* sharded rows: ymax, the count histogram and the four log-likelihood sums of every dispersion update are
+ * all-reduced over the communicator (NCCL); d stays identical on every rank */
 int bl_nb_gibbs_df_dev(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
                        const double *m0, const double *P0, int64_t N, int P, int samp, int burn, uint64_t seed,
                        uint64_t obs0, void *stream);

@@ -86,10 +86,36 @@ def compare_nb(tag, ref):
     return t.max().item() < 1e-8, b
 
 
+def nb_df_chain(lo, hi):
+    """NB sweep with the dispersion sampled on the device (draw.df): sharded, ymax / the count histogram /
+    the log-likelihood sums of every Metropolis step are all-reduced."""
+    Xd = torch.from_numpy(X[lo:hi].copy()).to(dev); yd = torch.from_numpy(yc[lo:hi].copy()).to(dev)
+    m0 = torch.zeros(P, device=dev, dtype=torch.float64)
+    P0 = (0.1 * torch.eye(P, device=dev, dtype=torch.float64)).contiguous()
+    beta = torch.zeros(10, P, device=dev, dtype=torch.float64)
+    dd = torch.zeros(10, device=dev, dtype=torch.float64)
+    rc = L.bl_nb_gibbs_df_dev(None, beta.data_ptr(), dd.data_ptr(), yd.data_ptr(), Xd.data_ptr(), 1.0,
+                              m0.data_ptr(), P0.data_ptr(), hi - lo, P, 10, 6, 4711, lo, st)
+    if rc:
+        _lib.check(rc)
+    torch.cuda.synchronize()
+    return beta.cpu().numpy(), dd.cpu().numpy()
+
+
 peer = bdist.peer_exchange_active()
 bdist.destroy_comm()
 nb_full = nb_chain(0, N)                      # no communicator: single-GPU chain
+nbdf_full = nb_df_chain(0, N)
 bdist.init_comm(rank, world, dev)
+b_df, d_df = nb_df_chain(lo, hi)
+e_df = float(np.max(np.abs(b_df - nbdf_full[0]) / np.abs(nbdf_full[0])))
+same_d = bool(np.array_equal(d_df, nbdf_full[1]))
+t = torch.tensor([e_df, 0.0 if same_d else 1.0], device=dev, dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print(f"nb with dispersion update: max rel diff beta {t[0].item():.2e}; d chain identical on every rank: {t[1].item() == 0.0} "
+          f"(d: {d_df[0]:.0f} .. {d_df[-1]:.0f})")
+ok = ok and t[0].item() < 1e-8 and t[1].item() == 0.0
 ok_nb, b_peer = compare_nb("peer windows" if bdist.peer_exchange_active() else "nccl", nb_full)
 ok = ok and ok_nb
 # beta must be bit-identical on every rank (replicated draw from identical sums)
