@@ -24,7 +24,10 @@ namespace bl {
 namespace {
 
 constexpr int kSlots = 3;
-constexpr int64_t kChunk = 1 << 23;  // observations per pipeline chunk (4M: 2.4e9, 8M: 2.7e9 draws/s end to end; PCIe floor 3.0e9)
+// observations per full-size pipeline chunk.  With the ramped schedule (run_host) and 100M mixed draws:
+// 1M 1.72e9, 2M 2.71e9, 4M 2.97e9, 8M 2.89e9, 16M 2.77e9, 32M 2.39e9 draws/s end to end (PCIe bound 3.1-3.3e9):
+// smaller chunks shorten fill and drain, larger ones amortise the ~27 launches of a binned batch.
+constexpr int64_t kChunkDefault = 1 << 22;
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -150,9 +153,15 @@ int run_host(Method m, double *x, const void *shape, const double *z, int64_t nu
     if (!x || !shape || !z) return fail("null argument");
     // Chunk schedule: the pipeline's fill (H2D of the first chunk, nothing to compute yet) and drain
     // (kernel + D2H of the last chunk, nothing left to copy in) are pure latency, so the batch opens
-    // and closes with small chunks -- 1M, 2M, 4M, then kChunk-sized ones, then 4M, 2M, 1M -- and the
+    // and closes with small chunks -- kChunk / 8, / 4, / 2, then kChunk-sized ones, then / 2, / 4, / 8 -- and the
     // link stays busy from ~0.3 ms after the call until ~0.4 ms before it returns.  Results do not
     // depend on the schedule (streams are keyed by the global observation index).
+    // BAYESLOGIT_PIPE_CHUNK_LOG2 (measurement aid): observations per full-size chunk, 2^20 .. 2^26
+    static const int64_t kChunk = [] {
+        const char *env = getenv("BAYESLOGIT_PIPE_CHUNK_LOG2");
+        int lg = env ? atoi(env) : 0;
+        return (lg >= 20 && lg <= 26) ? (int64_t)1 << lg : kChunkDefault;
+    }();
     std::vector<int64_t> sizes;
     {
         const int64_t ramp[3] = {kChunk / 8, kChunk / 4, kChunk / 2};

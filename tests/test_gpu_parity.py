@@ -458,9 +458,9 @@ def test_dropin_entry_points_mirror_r_wrappers(engine, oracle, capsys):
 
 @pytest.mark.parametrize("method", ["devroye", "hybrid"])
 def test_large_batch_chunk_pipeline(engine, oracle, method):
-    """Many pipeline chunks (ramped schedule 1M, 2M, 4M, 8M ..., 4M, 2M, 1M; three slots in rotation)
-    through the host-pointer ABI: draws on both sides of every chunk boundary equal the oracle's for the
-    same global observation index, and the whole batch equals the device-resident entry point's."""
+    """Many pipeline chunks (ramped schedule K/8, K/4, K/2, K ..., K/2, K/4, K/8 with K = 4M; three slots in
+    rotation) through the host-pointer ABI: draws on both sides of every chunk boundary equal the oracle's
+    for the same global observation index, and the whole batch equals the device-resident entry point's."""
     import torch
     from bayeslogit_b200 import _lib
     M = 1 << 20
@@ -474,8 +474,12 @@ def test_large_batch_chunk_pipeline(engine, oracle, method):
     x = engine.rpg_seeded(method, shape, z, seed=77, call_id=2)
     fn = getattr(oracle, "rpg_" + method)
     scale_all = normal_regime_amplification(shape, z) if method == "hybrid" else None
-    tail = 27 * M + 12345            # 1+2+4 head, 8+8+(4M+12345) body, then 4M, 2M, 1M
-    bounds = [M, 3 * M, 7 * M, 15 * M, 23 * M, tail, tail + 4 * M, tail + 6 * M]
+    K = 1 << 22                       # kChunkDefault of capi.cu
+    ramp = [K // 8, K // 4, K // 2]
+    body = num - 2 * sum(ramp)
+    sizes = ramp + [K] * (body // K) + ([body % K] if body % K else []) + ramp[::-1]
+    assert sum(sizes) == num
+    bounds = np.cumsum(sizes)[:-1].tolist()
     for i0 in [0] + [b - 2500 for b in bounds] + [num - 5000]:
         want = fn(shape[i0:i0 + 5000], z[i0:i0 + 5000], seed=77, call_id=2, obs0=i0)
         assert_close(x[i0:i0 + 5000], want, scale=None if scale_all is None else scale_all[i0:i0 + 5000])
