@@ -59,6 +59,8 @@ def lib():
     L.bl_get_seed.restype = u64
     L.bl_get_call_counter.restype = u32
     L.bl_kernel_launches.restype = u64
+    L.bl_probe_pipeline_schedule.argtypes = [i64, vp, ci]
+    L.bl_probe_pipeline_schedule.restype = ci
     tail = [u64, u32, u64]
     L.bl_rpg_devroye_dev.argtypes = [vp, vp, vp, i64, *tail, vp]
     L.bl_rpg_devroye_plain_dev.argtypes = [vp, vp, vp, i64, *tail, vp]

@@ -142,6 +142,37 @@ size_t shape_size(Method m)
     return (m == kDevroye || m == kDevroyePlain || m == kDevroyeLoop) ? sizeof(int) : sizeof(double);
 }
 
+// BAYESLOGIT_PIPE_CHUNK_LOG2 (measurement aid): observations per full-size chunk, 2^20 .. 2^26
+int64_t pipeline_chunk()
+{
+    static const int64_t chunk = [] {
+        const char *env = getenv("BAYESLOGIT_PIPE_CHUNK_LOG2");
+        int lg = env ? atoi(env) : 0;
+        return (lg >= 20 && lg <= 26) ? (int64_t)1 << lg : kChunkDefault;
+    }();
+    return chunk;
+}
+
+// Chunk sizes of a host-pointer batch of `num` observations, in order (see run_host).
+std::vector<int64_t> pipeline_schedule(int64_t num, int64_t chunk)
+{
+    std::vector<int64_t> sizes, tl;
+    const int64_t ramp[3] = {chunk / 8, chunk / 4, chunk / 2};
+    int64_t head = 0, tail = 0;
+    if (num >= 4 * chunk) {
+        for (int64_t r : ramp) { sizes.push_back(r); head += r; }
+        for (int64_t r : ramp) { tl.push_back(r); tail += r; }
+    }
+    int64_t body = num - head - tail;
+    while (body > 0) {
+        int64_t n = body < chunk ? body : chunk;
+        sizes.push_back(n);
+        body -= n;
+    }
+    for (auto it = tl.rbegin(); it != tl.rend(); ++it) sizes.push_back(*it);
+    return sizes;
+}
+
 // Host-pointer batch through the chunk pipeline.
 int run_host(Method m, double *x, const void *shape, const double *z, int64_t num, int trunc,
              int *iter, StreamId id)
@@ -156,29 +187,8 @@ int run_host(Method m, double *x, const void *shape, const double *z, int64_t nu
     // and closes with small chunks -- kChunk / 8, / 4, / 2, then kChunk-sized ones, then / 2, / 4, / 8 -- and the
     // link stays busy from ~0.3 ms after the call until ~0.4 ms before it returns.  Results do not
     // depend on the schedule (streams are keyed by the global observation index).
-    // BAYESLOGIT_PIPE_CHUNK_LOG2 (measurement aid): observations per full-size chunk, 2^20 .. 2^26
-    static const int64_t kChunk = [] {
-        const char *env = getenv("BAYESLOGIT_PIPE_CHUNK_LOG2");
-        int lg = env ? atoi(env) : 0;
-        return (lg >= 20 && lg <= 26) ? (int64_t)1 << lg : kChunkDefault;
-    }();
-    std::vector<int64_t> sizes;
-    {
-        const int64_t ramp[3] = {kChunk / 8, kChunk / 4, kChunk / 2};
-        int64_t head = 0, tail = 0;
-        std::vector<int64_t> tl;
-        if (num >= 4 * kChunk) {
-            for (int64_t r : ramp) { sizes.push_back(r); head += r; }
-            for (int64_t r : ramp) { tl.push_back(r); tail += r; }
-        }
-        int64_t body = num - head - tail;
-        while (body > 0) {
-            int64_t n = body < kChunk ? body : kChunk;
-            sizes.push_back(n);
-            body -= n;
-        }
-        for (auto it = tl.rbegin(); it != tl.rend(); ++it) sizes.push_back(*it);
-    }
+    const int64_t kChunk = pipeline_chunk();
+    const std::vector<int64_t> sizes = pipeline_schedule(num, kChunk);
     const int64_t nchunks = (int64_t)sizes.size();
     for (int s = 0; s < kSlots && s < nchunks; ++s)
         if (slot_reserve(g.slot[s], num < kChunk ? num : kChunk)) return 1;
@@ -525,6 +535,15 @@ int bl_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2)
 }
 
 uint64_t bl_kernel_launches(void) { return g_launches.load(); }
+
+// Host logic only (no device): the chunk sizes run_host would use for a batch of `num` observations.
+int bl_probe_pipeline_schedule(int64_t num, int64_t *sizes, int cap)
+{
+    if (num < 0) return -1;
+    const std::vector<int64_t> v = bl::pipeline_schedule(num, bl::pipeline_chunk());
+    for (size_t k = 0; k < v.size() && (int)k < cap; ++k) sizes[k] = v[k];
+    return (int)v.size();
+}
 
 void bl_hybrid_timing(int enable) { hybrid_timing_enable(enable != 0); }
 

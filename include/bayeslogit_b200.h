@@ -241,6 +241,11 @@ int bl_probe_specfun(double *out, int which, const double *a, const double *b, c
                      int64_t num);
 int bl_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2);
 
+/* Host logic probe (no device needed): chunk sizes, in order, that the host-pointer entry points use to
+ * stream a batch of num observations through HBM (small chunks open and close the batch so the pipeline
+ * fills and drains quickly).  Writes at most cap sizes; returns the number of chunks, -1 for num < 0. */
+int bl_probe_pipeline_schedule(int64_t num, int64_t *sizes, int cap);
+
 /* Number of kernels this library has launched since load (bench accounting). */
 uint64_t bl_kernel_launches(void);
 

@@ -474,11 +474,11 @@ def test_large_batch_chunk_pipeline(engine, oracle, method):
     x = engine.rpg_seeded(method, shape, z, seed=77, call_id=2)
     fn = getattr(oracle, "rpg_" + method)
     scale_all = normal_regime_amplification(shape, z) if method == "hybrid" else None
-    K = 1 << 22                       # kChunkDefault of capi.cu
-    ramp = [K // 8, K // 4, K // 2]
-    body = num - 2 * sum(ramp)
-    sizes = ramp + [K] * (body // K) + ([body % K] if body % K else []) + ramp[::-1]
-    assert sum(sizes) == num
+    import ctypes as C
+    buf = (C.c_int64 * 256)()
+    k = _lib.lib().bl_probe_pipeline_schedule(num, C.cast(buf, C.c_void_p), 256)
+    sizes = list(buf[:k])             # the chunk sizes run_host uses (ramp K/8, K/4, K/2 at both ends, K = 4M)
+    assert sum(sizes) == num and len(sizes) >= 10
     bounds = np.cumsum(sizes)[:-1].tolist()
     for i0 in [0] + [b - 2500 for b in bounds] + [num - 5000]:
         want = fn(shape[i0:i0 + 5000], z[i0:i0 + 5000], seed=77, call_id=2, obs0=i0)

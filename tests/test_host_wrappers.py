@@ -101,3 +101,31 @@ def test_compute_entry_points_fail_loudly_without_a_gpu(capsys):
         api.rpg_devroye(4, 1, 0.3)
     with pytest.raises(RuntimeError):
         gibbs_api.logit(np.array([0.0, 1.0, 1.0]), np.array([[1.0, 0.0], [0.0, 1.0], [1.0, 1.0]]), samp=2, burn=0)
+
+
+def _schedule(num):
+    import ctypes as C
+    buf = (C.c_int64 * 4096)()
+    k = _lib.lib().bl_probe_pipeline_schedule(int(num), C.cast(buf, C.c_void_p), 4096)
+    return list(buf[:k]) if k >= 0 else None
+
+
+def test_host_pipeline_schedule():
+    """Chunk schedule of the host-pointer entry points (capi.cu run_host): covers the batch exactly, full-size
+    chunks of 4M observations, and for batches of >= 4 chunks a ramp K/8, K/4, K/2 at both ends."""
+    K = 1 << 22
+    assert _schedule(-1) is None
+    assert _schedule(0) == []
+    assert _schedule(1) == [1]
+    assert _schedule(K) == [K]
+    assert _schedule(K + 5) == [K, 5]
+    assert _schedule(4 * K - 1) == [K, K, K, K - 1]                     # below the ramp threshold
+    ramp = [K // 8, K // 4, K // 2]
+    s = _schedule(4 * K)
+    assert s[:3] == ramp and s[-3:] == ramp[::-1] and sum(s) == 4 * K
+    for num in (100_000_000, 34 * (1 << 20) + 12345, 2**31 - 1, 5 * K + 1):
+        s = _schedule(num)
+        assert sum(s) == num and all(0 < c <= K for c in s)
+        assert s[:3] == ramp and s[-3:] == ramp[::-1]
+        body = s[3:-3]
+        assert all(c == K for c in body[:-1])                           # only the last body chunk may be short
