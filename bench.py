@@ -104,11 +104,17 @@ class ClockSampler:
             window = "warm-up + timed steps (same kernels, back to back)"
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[1]) for r in rows if len(r) > 2)
+        def num(v):                                   # nvidia-smi prints "[N/A]" for fields a board lacks
+            try:
+                return float(v)
+            except (TypeError, ValueError):
+                return None
+        sm = sorted(v for v in (num(r[1]) for r in rows if len(r) > 2) if v is not None)
+        pw = [v for v in (num(r[3]) for r in rows if len(r) > 3) if v is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(len(r) > 5 + k and r[5 + k] == "Active" for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
-                "samples": len(rows), "window": window, "power_w_max": max(float(r[3]) for r in rows)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": num(rows[0][2]) if len(rows[0]) > 2 else None,
+                "reasons": reasons, "samples": len(rows), "window": window, "power_w_max": max(pw) if pw else None}
 
 
 def load_oracle():
