@@ -2,7 +2,7 @@
 """Benchmark of the Polya-Gamma hot path (bench contract: see the task statement).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference]
-                    [--workload hybrid|pg1] [--num DRAWS]
+                    [--workload hybrid|pg1] [--num DRAWS | --draws DRAWS]
 
 Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): 100M mixed-shape
 PG(b,z) draws per GPU -- b: 50% real U(0.5,200), 50% integer U{1..200};
@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="hybrid", choices=["hybrid", "pg1"])
-    ap.add_argument("--num", type=int, default=100_000_000, help="draws per GPU per step")
+    # --draws: the same under torchrun, whose own parser rejects "--num" as an ambiguous prefix of --numa-binding
+    ap.add_argument("--num", "--draws", dest="num", type=int, default=100_000_000, help="draws per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the PG(1,z) and logit-Gibbs extras")
