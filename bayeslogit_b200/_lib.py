@@ -94,6 +94,7 @@ def lib():
     L.bl_logit_chains_dev.argtypes = [vp] * 6 + [ci, i64, ci, ci, ci, u64, ci, vp]
     L.bl_comm_unique_id.argtypes = [vp]
     L.bl_comm_init.argtypes = [vp, ci, ci]
+    L.bl_comm_init_local.argtypes = [ci, ci]
     L.bl_comm_peer_handle.argtypes = [vp]
     L.bl_comm_peer_open.argtypes = [vp]
     L.bl_probe_pg_moments.argtypes = [vp, vp, vp, vp, i64]

@@ -48,8 +48,6 @@ struct Context {
     uint64_t seed = 0;
     uint32_t call = 0;
     Slot slot[kSlots];
-    void *devwork = nullptr;   // scratch of the device-resident entry points (stream-ordered)
-    size_t devwork_cap = 0;
     std::string err;
 };
 
@@ -240,29 +238,23 @@ int run_dev(Method m, double *x, const void *shape, const double *z, int64_t num
     }
     if (num < 0) return fail("negative batch size");
     if ((m == kHybrid && num >= kBinMin) || (m == kDevroye && num >= (1 << 20))) {
-        std::lock_guard<std::mutex> lock(g.mu);
+        // index lists of the binned launches: stream-ordered scratch of THIS call on the caller's stream
+        // (the pool keeps it mapped), so concurrent calls on different streams never share a buffer
         int64_t per = num < kBinMax ? num : kBinMax;
-        size_t need = hybrid_workspace_bytes(per);
-        if (need > g.devwork_cap) {
-            BL_CK(cudaDeviceSynchronize());
-            if (g.devwork) cudaFree(g.devwork);
-            g.devwork = nullptr;
-            g.devwork_cap = 0;
-            BL_CK(cudaMalloc(&g.devwork, need));
-            g.devwork_cap = need;
-        }
-        for (int64_t off = 0; off < num; off += per) {
+        void *work = nullptr;
+        BL_CK(cudaMallocAsync(&work, hybrid_workspace_bytes(per), (cudaStream_t)stream));
+        int rc = 0;
+        for (int64_t off = 0; off < num && !rc; off += per) {
             int64_t n = num - off < per ? num - off : per;
             StreamId cid = id;
             cid.obs0 += (uint64_t)off;
-            if (m == kHybrid)
-                BL_CK(launch_hybrid_binned(x + off, (const double *)shape + off, z + off, (int)n, cid,
-                                           g.devwork, (cudaStream_t)stream));
-            else
-                BL_CK(launch_devroye_refill(x + off, (const int *)shape + off, z + off, n, cid,
-                                            (cudaStream_t)stream, g.devwork));
+            cudaError_t e = m == kHybrid
+                ? launch_hybrid_binned(x + off, (const double *)shape + off, z + off, (int)n, cid, work, (cudaStream_t)stream)
+                : launch_devroye_refill(x + off, (const int *)shape + off, z + off, n, cid, (cudaStream_t)stream, work);
+            if (e != cudaSuccess) rc = fail(std::string("binned launch: ") + cudaGetErrorString(e));
         }
-        return 0;
+        cudaFreeAsync(work, (cudaStream_t)stream);
+        return rc;
     }
     BL_CK(launch_rpg(m, x, shape, z, num, trunc, iter, id, (cudaStream_t)stream));
     return 0;

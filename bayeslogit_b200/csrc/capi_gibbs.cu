@@ -110,12 +110,14 @@ int merge_rows(double *ty, double *tX, double *n, int N, int P, int ny)
 
 uint64_t dropin_seed()
 {
-    // the reference draws from R's global generator; here: (engine seed, call counter) -> chain seed
+    // the reference draws from R's global generator; here: (engine seed, call counter) -> chain seed.
+    // Always through the mixer: the chain's streams (seed', obs i, call t) must never coincide with the
+    // streams (seed, obs i, call c) of the drop-in rpg_* calls that share the engine seed.
     uint64_t s = bl_get_seed();
     uint64_t c = bl_next_call_internal();
     uint64_t x = s + 0x9E3779B97F4A7C15ull * (c + 1);
     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
-    return c == 0 ? s : x;
+    return x ? x : 0x9E3779B97F4A7C15ull;
 }
 
 int host_logit(double *w, double *beta, const double *y, const double *tX, const double *n,
@@ -134,7 +136,7 @@ int host_logit(double *w, double *beta, const double *y, const double *tX, const
     if (!err.empty()) return report(err, "Aborting Gibbs sampler.");
     cudaStream_t st = (cudaStream_t)bl_stream_internal();
     if (logit_gibbs_device(dw, dbeta, dy, dX, dn, dm0, dP0, N, P, samp, burn, seed,
-                           keep_w ? flags : (flags | BL_GIBBS_NO_W), 0, st, err))
+                           keep_w ? flags : (flags | BL_GIBBS_NO_W), 0, false, st, err))
         return report(err, "Aborting Gibbs sampler.");
     cudaError_t e = cudaMemcpy(beta, dbeta, sizeof(double) * (size_t)P * samp, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && keep_w) e = cudaMemcpy(w, dw, sizeof(double) * (size_t)N * samp, cudaMemcpyDeviceToHost);
@@ -159,7 +161,7 @@ int host_mlogit(double *w, double *beta, const double *ty, const double *tX, con
     if (!err.empty()) return report(err, "Aborting Gibbs sampler.");
     cudaStream_t st = (cudaStream_t)bl_stream_internal();
     if (mlogit_gibbs_device(dw, dbeta, dy, dX, dn, dm0, dP0, N, P, J, samp, burn, seed,
-                            keep_w ? flags : (flags | BL_GIBBS_NO_W), 0, st, err))
+                            keep_w ? flags : (flags | BL_GIBBS_NO_W), 0, false, st, err))
         return report(err, "Aborting Gibbs sampler.");
     cudaError_t e = cudaMemcpy(beta, dbeta, sizeof(double) * (size_t)P * U * samp, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && keep_w) e = cudaMemcpy(w, dw, sizeof(double) * (size_t)N * U * samp, cudaMemcpyDeviceToHost);
@@ -258,7 +260,7 @@ int bl_nb_gibbs(double *w_last, double *beta, const double *y, const double *tX,
     double *dm0 = dv.put(m0, P, err), *dP0 = dv.put(P0, (size_t)P * P, err);
     double *dw = dv.put(nullptr, N, err), *dbeta = dv.put(nullptr, (size_t)P * samp, err);
     if (!err.empty()) return report(err, "Aborting Gibbs sampler.");
-    if (nb_gibbs_device(dw, dbeta, dy, dX, d, dm0, dP0, N, P, samp, seed, 0, (cudaStream_t)bl_stream_internal(), err))
+    if (nb_gibbs_device(dw, dbeta, dy, dX, d, dm0, dP0, N, P, samp, seed, 0, false, (cudaStream_t)bl_stream_internal(), err))
         return report(err, "Aborting Gibbs sampler.");
     cudaError_t e = cudaMemcpy(beta, dbeta, sizeof(double) * (size_t)P * samp, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && w_last) e = cudaMemcpy(w_last, dw, sizeof(double) * N, cudaMemcpyDeviceToHost);
@@ -277,7 +279,7 @@ int bl_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y,
     double *dw = dv.put(nullptr, N, err), *dbeta = dv.put(nullptr, (size_t)P * samp, err);
     double *dd = dv.put(nullptr, samp, err);
     if (!err.empty()) return report(err, "Aborting Gibbs sampler.");
-    if (nb_gibbs_df_device(dw, dbeta, dd, dy, dX, d0, dm0, dP0, N, P, samp, burn, seed, 0,
+    if (nb_gibbs_df_device(dw, dbeta, dd, dy, dX, d0, dm0, dP0, N, P, samp, burn, seed, 0, false,
                            (cudaStream_t)bl_stream_internal(), err))
         return report(err, "Aborting Gibbs sampler.");
     cudaError_t e = cudaMemcpy(beta, dbeta, sizeof(double) * (size_t)P * samp, cudaMemcpyDeviceToHost);
@@ -293,7 +295,7 @@ int bl_nb_gibbs_df_dev(double *w_last, double *beta, double *d_out, const double
 {
     if (bl_ensure_ready_internal()) return 1;
     std::string err;
-    if (nb_gibbs_df_device(w_last, beta, d_out, y, tX, d0, m0, P0, N, P, samp, burn, seed, obs0, (cudaStream_t)stream, err))
+    if (nb_gibbs_df_device(w_last, beta, d_out, y, tX, d0, m0, P0, N, P, samp, burn, seed, obs0, true, (cudaStream_t)stream, err))
         return report(err, nullptr);
     return 0;
 }
@@ -304,7 +306,7 @@ int bl_logit_gibbs_dev(double *w, double *beta, const double *y, const double *t
 {
     if (bl_ensure_ready_internal()) return 1;
     std::string err;
-    if (logit_gibbs_device(w, beta, y, tX, n, m0, P0, N, P, samp, burn, seed, flags, obs0, (cudaStream_t)stream, err))
+    if (logit_gibbs_device(w, beta, y, tX, n, m0, P0, N, P, samp, burn, seed, flags, obs0, true, (cudaStream_t)stream, err))
         return report(err, nullptr);
     return 0;
 }
@@ -346,7 +348,7 @@ int bl_mlogit_gibbs_dev(double *w, double *beta, const double *ty, const double 
 {
     if (bl_ensure_ready_internal()) return 1;
     std::string err;
-    if (mlogit_gibbs_device(w, beta, ty, tX, n, m0, P0, N, P, J, samp, burn, seed, flags, obs0, (cudaStream_t)stream, err))
+    if (mlogit_gibbs_device(w, beta, ty, tX, n, m0, P0, N, P, J, samp, burn, seed, flags, obs0, true, (cudaStream_t)stream, err))
         return report(err, nullptr);
     return 0;
 }
@@ -357,7 +359,7 @@ int bl_nb_gibbs_dev(double *w_last, double *beta, const double *y, const double 
 {
     if (bl_ensure_ready_internal()) return 1;
     std::string err;
-    if (nb_gibbs_device(w_last, beta, y, tX, d, m0, P0, N, P, samp, seed, obs0, (cudaStream_t)stream, err))
+    if (nb_gibbs_device(w_last, beta, y, tX, d, m0, P0, N, P, samp, seed, obs0, true, (cudaStream_t)stream, err))
         return report(err, nullptr);
     return 0;
 }
@@ -374,6 +376,14 @@ int bl_comm_init(const void *id128, int rank, int world)
     if (bl_ensure_ready_internal()) return 1;
     std::string err;
     if (comm_init(id128, rank, world, err)) return report(err, nullptr);
+    return 0;
+}
+
+int bl_comm_init_local(int rank, int world)
+{
+    if (bl_ensure_ready_internal()) return 1;
+    std::string err;
+    if (comm_init_local(rank, world, err)) return report(err, nullptr);
     return 0;
 }
 

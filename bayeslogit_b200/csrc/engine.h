@@ -66,18 +66,18 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
 // Gibbs sweeps on device-resident data (gibbs.cu); return 0 on success, message in err.
 int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const double *tX,
                        const double *n, const double *m0, const double *P0, int64_t N, int P,
-                       int samp, int burn, uint64_t seed, int flags, uint64_t obs0,
+                       int samp, int burn, uint64_t seed, int flags, uint64_t obs0, bool sharded,
                        cudaStream_t st, std::string &err);
 int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const double *tX,
                         const double *n, const double *m0, const double *P0, int64_t N, int P, int J,
-                        int samp, int burn, uint64_t seed, int flags, uint64_t obs0,
+                        int samp, int burn, uint64_t seed, int flags, uint64_t obs0, bool sharded,
                         cudaStream_t st, std::string &err);
 int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const double *tX, double d,
                     const double *m0, const double *P0, int64_t N, int P, int samp, uint64_t seed,
-                    uint64_t obs0, cudaStream_t st, std::string &err);
+                    uint64_t obs0, bool sharded, cudaStream_t st, std::string &err);
 int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const double *y, const double *tX,
                        double d0, const double *m0, const double *P0, int64_t N, int P, int samp, int burn,
-                       uint64_t seed, uint64_t obs0, cudaStream_t st, std::string &err);
+                       uint64_t seed, uint64_t obs0, bool sharded, cudaStream_t st, std::string &err);
 int logit_chains_device(double *beta_out, const double *y, const double *tX, const double *n,
                         const double *m0, const double *P0, int chains, int64_t N, int P, int samp, int burn,
                         uint64_t seed, int flags, cudaStream_t st, std::string &err);
@@ -85,6 +85,7 @@ int logit_em_device(double *beta, const double *y, const double *tX, const doubl
                     int P, double tol, int max_iter, int *iters, cudaStream_t st, std::string &err);
 int comm_unique_id(void *out128, std::string &err);
 int comm_init(const void *id128, int rank, int world, std::string &err);
+int comm_init_local(int rank, int world, std::string &err);
 void comm_destroy();
 int comm_peer_handle(void *out64, std::string &err);
 int comm_peer_open(const void *handles, std::string &err);

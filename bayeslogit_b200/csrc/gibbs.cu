@@ -35,6 +35,7 @@ struct Nccl {
     void *lib = nullptr;
     void *comm = nullptr;
     int rank = 0, world = 1;
+    bool local = false;            // ranks without an NCCL communicator (bl_comm_init_local): peer windows only
     int (*CommInitRank)(void **, int, char[128], int) = nullptr;   // ncclUniqueId by value (128 bytes)
     int (*GetUniqueId)(void *) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
@@ -60,7 +61,7 @@ bool nccl_load(std::string &err)
 }
 
 constexpr int kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
-constexpr int kNcclInt32 = 2, kNcclUint64 = 5, kNcclMax = 2;
+constexpr int kNcclUint64 = 5, kNcclMax = 2;
 
 // ------------------------------------------------------------------------------------
 // Peer exchange over NVLink (one node): every rank owns one cudaMalloc'd window that its peers
@@ -87,6 +88,85 @@ constexpr size_t kPeerFlagBytes = 256;
 constexpr int kPeerMaxP = 256;
 
 bool peer_active() { return g_peer.open && g_nccl.world > 1; }
+
+// Descriptors of the next exchange through the windows (advances the epoch: call once per exchange,
+// on every rank, in the same order).
+void peer_next(PeerPush &px, PeerWait &pw)
+{
+    const unsigned e = ++g_peer.epoch;
+    const int par = (int)(e & 1u), me = g_nccl.rank;
+    px = PeerPush{};
+    pw = PeerWait{};
+    px.world = pw.world = g_nccl.world;
+    px.epoch = pw.epoch = e;
+    px.done = g_peer.done;
+    for (int r = 0; r < g_nccl.world; ++r) {
+        char *w = (char *)g_peer.win[r];
+        px.flag[r] = (unsigned *)w + par * kMaxPeers + me;
+        px.slot[r] = (double *)(w + kPeerFlagBytes) + ((size_t)par * kMaxPeers + me) * g_peer.slot_doubles;
+        pw.slot[r] = (const double *)((char *)g_peer.base + kPeerFlagBytes) + ((size_t)par * kMaxPeers + r) * g_peer.slot_doubles;
+    }
+    pw.flag = (const unsigned *)g_peer.base + par * kMaxPeers;
+}
+
+}  // namespace
+
+// Small all-reduce through the peer windows, one CTA per rank: store the local words into this rank's
+// slot of every window, raise the flags, wait for the world's flags, combine the slots in rank order
+// (bit-identical on every rank).  8-byte words; kOp 0: double sum, 1: uint64 sum, 2: uint64 max.
+template <int kOp>
+__global__ void __launch_bounds__(256)
+k_peer_allreduce(unsigned long long *buf, int cnt, PeerPush px, PeerWait pw, int *status)
+{
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const unsigned long long v = buf[i];
+        for (int r = 0; r < px.world; ++r) reinterpret_cast<unsigned long long *>(px.slot[r])[i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int r = 0; r < px.world; ++r) st_release_sys(px.flag[r], px.epoch);
+    }
+    peer_wait(pw, status);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        unsigned long long a = __ldcg(reinterpret_cast<const unsigned long long *>(pw.slot[0]) + i);
+        for (int r = 1; r < pw.world; ++r) {
+            const unsigned long long b = __ldcg(reinterpret_cast<const unsigned long long *>(pw.slot[r]) + i);
+            if (kOp == 0) a = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b));
+            else if (kOp == 1) a += b;
+            else a = b > a ? b : a;
+        }
+        buf[i] = a;
+    }
+}
+
+namespace {
+
+enum SmallOp { kOpSumF64 = 0, kOpSumU64 = 1, kOpMaxU64 = 2 };
+
+// All-reduce of cnt 8-byte words in place across the ranks (set-up sums, the NB dispersion step): the
+// peer windows when they are open, else NCCL.  No-op without a communicator.
+int small_allreduce(void *buf, size_t cnt, SmallOp op, int *status, cudaStream_t st, std::string &err)
+{
+    if (g_nccl.world <= 1) return 0;
+    if (peer_active()) {
+        if (cnt > g_peer.slot_doubles) { err = "peer all-reduce: vector longer than a window slot"; return 1; }
+        PeerPush px;
+        PeerWait pw;
+        peer_next(px, pw);
+        unsigned long long *b = (unsigned long long *)buf;
+        if (op == kOpSumF64) k_peer_allreduce<0><<<1, 256, 0, st>>>(b, (int)cnt, px, pw, status);
+        else if (op == kOpSumU64) k_peer_allreduce<1><<<1, 256, 0, st>>>(b, (int)cnt, px, pw, status);
+        else k_peer_allreduce<2><<<1, 256, 0, st>>>(b, (int)cnt, px, pw, status);
+        count_launch();
+        return 0;
+    }
+    if (!g_nccl.comm) { err = "sharded sweep: no NCCL communicator and the peer windows are not open"; return 1; }
+    const int r = g_nccl.AllReduce(buf, buf, cnt, op == kOpSumF64 ? kNcclFloat64 : kNcclUint64,
+                                   op == kOpMaxU64 ? kNcclMax : kNcclSum, g_nccl.comm, st);
+    if (r != 0) { err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return 1; }
+    return 0;
+}
 
 }  // namespace
 
@@ -331,19 +411,8 @@ struct Sweep {
         PeerPush px{};
         pending = PeerWait{};
         if (exchange && peer_active()) {
-            const unsigned e = ++g_peer.epoch;
-            const int par = (int)(e & 1u), me = g_nccl.rank;
-            px.world = pending.world = g_nccl.world;
-            px.epoch = pending.epoch = e;
-            px.done = g_peer.done;
+            peer_next(px, pending);
             px.with_tail = with_tail ? 1 : 0;
-            for (int r = 0; r < g_nccl.world; ++r) {
-                char *w = (char *)g_peer.win[r];
-                px.flag[r] = (unsigned *)w + par * kMaxPeers + me;
-                px.slot[r] = (double *)(w + kPeerFlagBytes) + ((size_t)par * kMaxPeers + me) * g_peer.slot_doubles;
-                pending.slot[r] = (const double *)((char *)g_peer.base + kPeerFlagBytes) + ((size_t)par * kMaxPeers + r) * g_peer.slot_doubles;
-            }
-            pending.flag = (const unsigned *)g_peer.base + par * kMaxPeers;
         }
         k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nt > 1 ? 2 * nslab : nslab, px, packed ? 1 : 0,
                                                                 2 * nslab_diag);
@@ -361,8 +430,9 @@ struct Sweep {
 
     int allreduce(bool with_tail, std::string &err)
     {
-        if (g_nccl.world <= 1 || !g_nccl.comm) return 0;
+        if (!exchange || g_nccl.world <= 1) return 0;
         if (pending.world > 1) return 0;          // already pushed through the peer windows by gram()
+        if (!g_nccl.comm) { err = "sharded sweep: no NCCL communicator and the peer windows are not open"; return 1; }
         size_t cnt = (size_t)P * P + (with_tail ? P : 0);
         int r = g_nccl.AllReduce(acc, acc, cnt, kNcclFloat64, kNcclSum, g_nccl.comm, st);
         if (r != 0) { err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return 1; }
@@ -388,6 +458,7 @@ struct Sweep {
         GB_CK(cudaMemcpyAsync(&h, status, sizeof(int), cudaMemcpyDeviceToHost, st));
         GB_CK(cudaStreamSynchronize(st));
         if (h == 2) { err = std::string(what) + ": peer exchange timed out (a rank did not arrive)"; return 1; }
+        if (h == 3) { err = std::string(what) + ": inverse of the posterior precision is not positive definite (constrained beta draw)"; return 1; }
         if (h != 0) { err = std::string(what) + ": posterior precision is not positive definite"; return 1; }
         return 0;
     }
@@ -402,14 +473,14 @@ struct Sweep {
 // w_out: N x samp or null (flags & BL_GIBBS_NO_W); beta_out: P x samp.
 int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const double *tX,
                        const double *n, const double *m0, const double *P0, int64_t N, int P,
-                       int samp, int burn, uint64_t seed, int flags, uint64_t obs0,
+                       int samp, int burn, uint64_t seed, int flags, uint64_t obs0, bool sharded,
                        cudaStream_t st, std::string &err)
 {
     if (N <= 0 || P <= 0 || samp <= 0 || burn < 0) { err = "gibbs: bad dimensions"; return 1; }
     DevMem mem;
     mem.st = st;
     Sweep s;
-    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX; s.exchange = true;
+    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX; s.exchange = sharded;
     if (s.init(mem, err)) return 1;
     double *kappa, *b0, *bP;
     int *shape;
@@ -428,10 +499,7 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
     k_matvec<<<cdiv(P, 128), 128, 0, st>>>(b0, P0, m0, P);
     count_launch(3);
     s.xtv(kappa, 1.0, nullptr, nullptr, 0.0);
-    if (g_nccl.world > 1 && g_nccl.comm) {
-        int r = g_nccl.AllReduce(s.acc + (size_t)P * P, s.acc + (size_t)P * P, (size_t)P, kNcclFloat64, kNcclSum, g_nccl.comm, st);
-        if (r != 0) { err = "ncclAllReduce failed"; return 1; }
-    }
+    if (sharded && small_allreduce(s.acc + (size_t)P * P, (size_t)P, kOpSumF64, s.status, st, err)) return 1;
     k_xtv_reduce<<<cdiv(P, 128), 128, 0, st>>>(bP, b0, s.acc + (size_t)P * P, s.xtv_part, P, 0);
     count_launch();
 
@@ -470,6 +538,7 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
                 for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&d[k], ev[k], ev[k + 1]);
                 fprintf(stderr, "[bl gibbs timing, us] %s %.1f gram %.1f allreduce %.1f beta %.1f xbeta %.1f\n",
                         fused ? "psi+draw" : "draw", d[0] * 1e3, d[1] * 1e3, d[2] * 1e3, d[3] * 1e3, d[4] * 1e3);
+                for (auto &x : ev) cudaEventDestroy(x);
             }
             if (phase == 1) {
                 bprev = bcur;
@@ -592,6 +661,7 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
                 for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&d[k], ev[k], ev[k + 1]);
                 fprintf(stderr, "[bl chains timing, us] draw %.1f gram %.1f reduce %.1f beta %.1f xbeta %.1f\n",
                         d[0] * 1e3, d[1] * 1e3, d[2] * 1e3, d[3] * 1e3, d[4] * 1e3);
+                for (auto &x : ev) cudaEventDestroy(x);
             }
             if (phase == 1) {
                 bprev = bcur;
@@ -614,7 +684,7 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
 // m0: P x (J-1), P0: P x P x (J-1).
 int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const double *tX,
                         const double *n, const double *m0, const double *P0, int64_t N, int P, int J,
-                        int samp, int burn, uint64_t seed, int flags, uint64_t obs0,
+                        int samp, int burn, uint64_t seed, int flags, uint64_t obs0, bool sharded,
                         cudaStream_t st, std::string &err)
 {
     if (N <= 0 || P <= 0 || J < 2 || samp <= 0 || burn < 0) { err = "mult_gibbs: bad dimensions"; return 1; }
@@ -622,7 +692,7 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
     DevMem mem;
     mem.st = st;
     Sweep s;
-    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX; s.exchange = true;
+    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX; s.exchange = sharded;
     if (s.init(mem, err)) return 1;
     double *Z, *b0, *XB, *cj, *eta, *yj, *base;
     int *shape;
@@ -645,8 +715,7 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
         k_matvec<<<cdiv(P, 128), 128, 0, st>>>(b0 + (size_t)P * j, P0 + (size_t)P * P * j, m0 + (size_t)P * j, P);
         count_launch(2);
         s.xtv(cj, 1.0, nullptr, nullptr, 0.0);
-        if (g_nccl.world > 1 && g_nccl.comm)
-            g_nccl.AllReduce(s.acc + (size_t)P * P, s.acc + (size_t)P * P, (size_t)P, kNcclFloat64, kNcclSum, g_nccl.comm, st);
+        if (sharded && small_allreduce(s.acc + (size_t)P * P, (size_t)P, kOpSumF64, s.status, st, err)) return 1;
         k_xtv_reduce<<<cdiv(P, 128), 128, 0, st>>>(base + (size_t)P * j, b0 + (size_t)P * j, s.acc + (size_t)P * P, s.xtv_part, P, 0);
         count_launch();
     }
@@ -693,13 +762,13 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
 // beta_out: P x samp (every iteration kept), w_out: N (last omega) or null.
 int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const double *tX, double d,
                     const double *m0, const double *P0, int64_t N, int P, int samp, uint64_t seed,
-                    uint64_t obs0, cudaStream_t st, std::string &err)
+                    uint64_t obs0, bool sharded, cudaStream_t st, std::string &err)
 {
     if (N <= 0 || P <= 0 || samp <= 0 || !(d > 0)) { err = "nb_gibbs: bad arguments"; return 1; }
     DevMem mem;
     mem.st = st;
     Sweep s;
-    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX; s.exchange = true;
+    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX; s.exchange = sharded;
     if (s.init(mem, err)) return 1;
     double *kappa, *b0, *shape, *beta0;
     void *work;
@@ -752,20 +821,20 @@ int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const doub
 // ------------------------------------------------------------------------------------
 int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const double *y, const double *tX,
                        double d0, const double *m0, const double *P0, int64_t N, int P, int samp, int burn,
-                       uint64_t seed, uint64_t obs0, cudaStream_t st, std::string &err)
+                       uint64_t seed, uint64_t obs0, bool sharded_arg, cudaStream_t st, std::string &err)
 {
     if (N <= 0 || P <= 0 || samp <= 0 || burn < 0 || !(d0 >= 1.0) || d0 != floor(d0)) {
         err = "nb_gibbs_df: bad arguments (d0 must be a positive integer)";
         return 1;
     }
-    const bool sharded = g_nccl.world > 1 && g_nccl.comm;
+    const bool sharded = sharded_arg && g_nccl.world > 1;
     DevMem mem;
     mem.st = st;
     Sweep s;
-    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX; s.exchange = true;
+    s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX; s.exchange = sharded;
     if (s.init(mem, err)) return 1;
     double *kappa, *b0, *shape, *bcur, *dpair, *G, *dfpart;
-    int *ymax_d;
+    unsigned long long *ymax_d;
     void *work;
     GB_CK(mem.get(&kappa, N));
     GB_CK(mem.get(&shape, N));
@@ -778,24 +847,20 @@ int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const dou
     GB_CK(mem.get(&dfpart, (size_t)nblk * 4));
     double *dfsum;
     GB_CK(mem.get(&dfsum, 4));
-    auto nccl_ck = [&](int r, const char *what) {
-        if (r == 0) return 0;
-        err = std::string("nb_gibbs_df: ncclAllReduce (") + what + "): " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
-        return 1;
-    };
     // ymax, G
-    GB_CK(cudaMemsetAsync(ymax_d, 0, sizeof(int), st));
+    GB_CK(cudaMemsetAsync(ymax_d, 0, sizeof(unsigned long long), st));
     k_nb_ymax<<<148 * 2, 256, 0, st>>>(ymax_d, y, N);
-    if (sharded && nccl_ck(g_nccl.AllReduce(ymax_d, ymax_d, 1, kNcclInt32, kNcclMax, g_nccl.comm, st), "ymax")) return 1;
-    int ymax = 0;
-    GB_CK(cudaMemcpyAsync(&ymax, ymax_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (sharded && small_allreduce(ymax_d, 1, kOpMaxU64, s.status, st, err)) return 1;
+    unsigned long long ymax64 = 0;
+    GB_CK(cudaMemcpyAsync(&ymax64, ymax_d, sizeof(ymax64), cudaMemcpyDeviceToHost, st));
     GB_CK(cudaStreamSynchronize(st));
+    const int ymax = (int)ymax64;
     unsigned long long *hist;
     GB_CK(mem.get(&hist, (size_t)ymax + 2));
     GB_CK(mem.get(&G, (size_t)ymax + 1));
     GB_CK(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * ((size_t)ymax + 2), st));
     k_nb_hist<<<148 * 2, 256, 0, st>>>(hist, y, N);
-    if (sharded && nccl_ck(g_nccl.AllReduce(hist, hist, (size_t)ymax + 2, kNcclUint64, kNcclSum, g_nccl.comm, st), "histogram")) return 1;
+    if (sharded && small_allreduce(hist, (size_t)ymax + 2, kOpSumU64, s.status, st, err)) return 1;
     k_nb_suffix<<<1, 1, 0, st>>>(G, hist, ymax);
     k_matvec<<<cdiv(P, 128), 128, 0, st>>>(b0, P0, m0, P);
     count_launch(4);
@@ -811,7 +876,7 @@ int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const dou
         if (sharded) {
             k_nb_df_fold<<<1, 32, 0, st>>>(dfsum, dfpart, nblk);
             count_launch();
-            if (nccl_ck(g_nccl.AllReduce(dfsum, dfsum, 4, kNcclFloat64, kNcclSum, g_nccl.comm, st), "log-likelihood sums")) return 1;
+            if (small_allreduce(dfsum, 4, kOpSumF64, s.status, st, err)) return 1;
         }
         k_nb_df_decide<<<1, 32, 0, st>>>(dpair, dpair + 1, t >= burn ? d_out + (t - burn) : nullptr,
                                          sharded ? dfsum : dfpart, sharded ? 1 : nblk, G, ymax, seed, (uint32_t)t);
@@ -951,6 +1016,18 @@ int comm_init(const void *id128, int rank, int world, std::string &err)
     return 0;
 }
 
+// Ranks without NCCL (e.g. several processes sharing one device, which NCCL refuses): every exchange
+// then goes through the peer windows, which must be opened before the first sharded sweep.
+int comm_init_local(int rank, int world, std::string &err)
+{
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) { err = "bl_comm_init_local: need 0 <= rank < world <= 8"; return 1; }
+    g_nccl.rank = rank;
+    g_nccl.world = world;
+    g_nccl.comm = nullptr;
+    g_nccl.local = world > 1;
+    return 0;
+}
+
 // Allocate (once) and zero this rank's window; out64 receives its CUDA IPC handle.
 int comm_peer_handle(void *out64, std::string &err)
 {
@@ -1007,6 +1084,7 @@ void comm_destroy()
     g_nccl.comm = nullptr;
     g_nccl.world = 1;
     g_nccl.rank = 0;
+    g_nccl.local = false;
 }
 
 }  // namespace bl

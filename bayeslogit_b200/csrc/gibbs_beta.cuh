@@ -497,7 +497,7 @@ __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, do
 
     // constrained coordinate-wise draw (Logit.hpp:349-399)
     cta_chol_lower(B, P, ld, &ok);
-    if (!ok) { if (tid == 0) *status = 2; return; }
+    if (!ok) { if (tid == 0) *status = 3; return; }
     const double *L = B;
     if (tid < 32) {
         for (int i = lane; i < P; i += 32) mP[i] = rhs[i];

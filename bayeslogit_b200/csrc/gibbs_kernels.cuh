@@ -570,7 +570,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 }
 
 // Called by every thread of every CTA of the reducing kernel once its part of `acc` is written.
-// The last CTA to arrive copies the whole local result (cnt doubles, cnt even) into this rank's slot
+// The last CTA to arrive copies the whole local result (cnt doubles) into this rank's slot
 // of every window with coalesced 16-byte NVLink stores -- 512 contiguous bytes per warp instruction
 // instead of the reducing CTAs' scattered 8-byte element stores -- then one system-scope fence and
 // the flags.  (Scattering from all CTAs cost ~20 us at 8 GPUs: 2 x 8 small stores per element and a
@@ -606,6 +606,8 @@ __device__ __forceinline__ void peer_publish(const PeerPush &px, const double *a
             }
         }
     }
+    // odd cnt (logit sweep with odd P: P^2 sums, no tail): the last double travels on its own
+    if ((cnt & 1) && (int)threadIdx.x < px.world) px.slot[threadIdx.x][cnt - 1] = __ldcg(acc + cnt - 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();             // the slot stores are performed system-wide before the flags
@@ -1092,13 +1094,13 @@ __global__ void k_nb_prepare(double *__restrict__ psi, double *__restrict__ shap
 }
 
 // ymax and G[j] = #{y_i > j} (NBPG-logmean.R:65-67)
-__global__ void k_nb_ymax(int *__restrict__ ymax, const double *__restrict__ y, int64_t N)
+__global__ void k_nb_ymax(unsigned long long *__restrict__ ymax, const double *__restrict__ y, int64_t N)
 {
     int m = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
         m = max(m, (int)y[i]);
     for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(ymax, m);
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(ymax, (unsigned long long)m);
 }
 __global__ void k_nb_hist(unsigned long long *__restrict__ hist, const double *__restrict__ y, int64_t N)
 {

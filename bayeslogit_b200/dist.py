@@ -41,6 +41,20 @@ def init_comm(rank, world, device=None):
         _open_peer_windows(L, rank, world, device)
 
 
+def init_comm_local(rank, world):
+    """Engine communicator WITHOUT NCCL: every exchange goes through the CUDA-IPC peer windows.  For ranks
+    NCCL cannot join (several processes sharing one device -- the one-GPU test of the exchange); the
+    handles travel over whatever torch.distributed backend is up (gloo)."""
+    from . import _lib
+    L = _lib.lib()
+    _lib.check(L.bl_comm_init_local(rank, world))
+    if world <= 1:
+        return
+    _open_peer_windows(L, rank, world, None)
+    if not L.bl_comm_peer_active():
+        raise _lib.EngineError("bl_comm_init_local: the peer windows could not be mapped (CUDA IPC)")
+
+
 def _open_peer_windows(L, rank, world, device):
     """All-gather the ranks' CUDA IPC window handles and map them (one node, NVLink): the sharded
     sweeps then exchange their P*P + P sums inside the Gram-reduce / beta-draw kernels instead of

@@ -220,6 +220,11 @@ int bl_logit_chains_dev(double *beta, const double *y, const double *tX, const d
 int bl_comm_unique_id(void *out128);
 int bl_comm_init(const void *id128, int rank, int world);
 int bl_comm_destroy(void);
+/* The same ranks WITHOUT an NCCL communicator: every exchange then goes through the peer windows
+ * below, which must be opened (bl_comm_peer_handle / bl_comm_peer_open) before the first sharded
+ * sweep.  For ranks NCCL cannot join -- several processes sharing one device (how the exchange is
+ * tested on a one-GPU box) -- or to keep NCCL out of the process altogether. */
+int bl_comm_init_local(int rank, int world);
 
 /* Peer windows (ranks on one NVLink/NVSwitch node, at most 8): with them open, the sharded sweeps
  * exchange the P*P + P sums of each beta draw through one fused kernel pair instead of

@@ -119,6 +119,78 @@ def test_mlogit_chain_matches_oracle(gapi):
     close(b, bo); close(w, wo)
 
 
+def synth_mlogit(N, P, J, seed, scale=0.7):
+    rng = np.random.default_rng(seed)
+    X = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
+    B = rng.normal(0, scale, (P, J - 1))
+    eta = np.c_[X @ B, np.zeros(N)]
+    pr = np.exp(eta); pr /= pr.sum(1, keepdims=True)
+    cat = (pr.cumsum(1) < rng.random(N)[:, None]).sum(1)
+    Y = np.eye(J)[cat][:, :J - 1]
+    return X, Y, B
+
+
+def test_mlogit_chain_matches_oracle_at_the_benchmarked_shape(gapi):
+    """BASELINE config 5a's kernel instantiations (J = 10, P = 32) at an oracle-sized N: X'(Omega c_j) through
+    k_xtv_stream<4, 1> (P a power of two, weight mode omega * c), the packed P = 32 Gram, the mvn beta
+    draw at P = 32, nine category updates per iteration (MultLogit.hpp:242-258, 293-307)."""
+    N, P, J = 20_011, 32, 10
+    X, Y, _ = synth_mlogit(N, P, J, 41, scale=0.25)
+    rng = np.random.default_rng(5)
+    m0 = rng.normal(0, 0.05, (P, J - 1))
+    P0 = np.stack([(0.5 + 0.05 * j) * np.eye(P) for j in range(J - 1)], axis=2)
+    w, b = gapi.mlogit_gibbs(Y, X, np.ones(N), m0, P0, 3, 2, seed=77)
+    wo, bo = loader.mlogit_gibbs(Y, X, np.ones(N), m0, P0, 3, 2, seed=77)
+    close(b, bo); close(w, wo)
+
+
+@pytest.mark.parametrize("N,P", [(30_000, 32), (30_011, 64), (30_000, 256)])
+def test_nb_chain_matches_oracle_at_wide_P(gapi, N, P):
+    """BASELINE config 4's kernel instantiations at an oracle-sized N: k_xtv_stream<log2(P/2), 2> (weights
+    kappa + omega log d; P = 256 rotates four column pairs per lane), the P > 64 multi-tile Gram under
+    hybrid-sampler weights, the plain beta draw out of global scratch (P = 256), the regime-binned
+    rpg_hybrid on b = y + d (NBPG-logmean.R:13-34)."""
+    rng = np.random.default_rng(60 + P)
+    d = 10.0
+    X = np.c_[rng.standard_normal((N, P - 1)) / np.sqrt(P), np.ones(N)]
+    bt = np.r_[rng.normal(0, 1.0, P - 1), np.log(100.0)]                 # mean count ~ 100: b = y + d in the saddle-point range, a tail > 170
+    mu = np.exp(X @ bt)
+    y = rng.negative_binomial(d, d / (mu + d)).astype(float)
+    assert (y + d > 170).any() and ((y + d > 13) & (y + d <= 170)).mean() > 0.5
+    samp = 3
+    w, b = gapi.nb_gibbs(y, X, d, np.zeros(P), 0.01 * np.eye(P), samp, seed=18)
+    wo, bo = loader.nb_gibbs(y, X, d, np.zeros(P), 0.01 * np.eye(P), samp, seed=18)
+    close(b, bo, 1e-7); close(w, wo, 1e-7)
+
+
+@pytest.mark.parametrize("constrained", [False, True])
+def test_logit_chain_matches_oracle_at_full_size(gapi, constrained):
+    """BASELINE config 3 at its stated size, N = 1 000 000, P = 64: the multi-wave grids of the fused
+    psi + omega pass, the slab counts of the P = 64 Gram and both beta draws against the oracle
+    (OpenMP on the host cores: seconds)."""
+    N, P = 1_000_000, 64
+    X, y, n, _ = synth_logit(N, P, 20240003)
+    m0 = np.zeros(P)
+    P0 = 0.01 * np.eye(P)
+    flags = 0 if constrained else gapi.PLAIN_BETA
+    w, b = gapi.logit_gibbs(y, X, n, m0, P0, 2, 1, seed=20240003, flags=flags)
+    wo, bo = loader.logit_gibbs(y, X, n, m0, P0, 2, 1, seed=20240003, constrained=constrained)
+    close(b, bo); close(w, wo)
+
+
+def test_batched_chains_match_oracle_at_the_benchmarked_shape(gapi):
+    """BASELINE config 5b's per-chain shape (N = 10 000, P = 32) with the reference's constrained draw."""
+    chains, N, P = 3, 10_000, 32
+    data = [synth_logit(N, P, 300 + c) for c in range(chains)]
+    X = np.stack([d[0] for d in data]); y = np.stack([d[1] for d in data]); n = np.stack([d[2] for d in data])
+    m0 = np.zeros(P)
+    P0 = 0.01 * np.eye(P)
+    b = gapi.logit_chains(y, X, n, m0, P0, 4, 2, seed=20240006, flags=0)
+    for c in range(chains):
+        _, bo = loader.logit_gibbs(y[c], X[c], n[c], m0, P0, 4, 2, seed=20240006 + c, constrained=True)
+        close(b[c], bo)
+
+
 @pytest.mark.parametrize("P", [5, 8])
 def test_nb_chain_matches_oracle(gapi, P):
     rng = np.random.default_rng(6)

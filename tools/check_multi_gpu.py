@@ -1,7 +1,16 @@
 #!/usr/bin/env python3
-"""Multi-GPU check (run under torchrun, one rank per GPU): the sharded logit chain with the
-in-stream NCCL all-reduce equals the single-GPU chain, and the sampler's shards equal the
-unsharded batch.  Prints MULTI_GPU_OK on rank 0."""
+"""Multi-rank check of the sharded sweeps (run under torchrun): the row-sharded logit / NB chains
+equal the single-GPU chains, beta is bit-identical on every rank, on the peer-window exchange and
+on ncclAllReduce.  Prints MULTI_GPU_OK on rank 0.
+
+Two ways to run it:
+  * one rank per GPU (default): torch.distributed over NCCL, engine communicator = NCCL + peer windows;
+  * BL_MG_LOCAL=1: every rank on cuda:0 (a one-GPU box), torch.distributed over gloo, engine
+    communicator = bl_comm_init_local (no NCCL: it refuses two ranks on one device), every exchange
+    through the CUDA-IPC peer windows.  The ranks' kernels time-slice the device, so the exchange's
+    flag waits cost a time slice each -- slow, but the same kernels (peer_publish / peer_wait /
+    peer_stage / k_peer_allreduce) on the same code path.
+"""
 import os
 import sys
 
@@ -12,22 +21,56 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bayeslogit_b200 import _lib, dist as bdist  # noqa: E402
 
-rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+LOCAL_MODE = os.environ.get("BL_MG_LOCAL") == "1"
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+local = 0 if LOCAL_MODE else int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 L = _lib.lib()
 _lib.check(L.bl_set_device(local))
-dist.init_process_group("nccl", device_id=dev)
+if LOCAL_MODE:
+    dist.init_process_group("gloo")
+else:
+    dist.init_process_group("nccl", device_id=dev)
 
-rng = np.random.default_rng(0)
-N, P, samp, burn = 200_003, 16, 12, 4
-X = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
-bt = np.r_[np.abs(rng.normal(0, 0.3, P - 1)), -0.5]
-y = (rng.random(N) < 1 / (1 + np.exp(-X @ bt))).astype(float)
+
+def open_comm():
+    if LOCAL_MODE:
+        bdist.init_comm_local(rank, world)
+    else:
+        bdist.init_comm(rank, world, dev)
+
+
+def allmax(vals):
+    t = torch.tensor(list(vals), dtype=torch.float64, device="cpu" if LOCAL_MODE else dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.cpu()]
+
+
+def same_on_all_ranks(a):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if not LOCAL_MODE:
+        t = t.to(dev)
+    g = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(g, t)
+    return all(torch.equal(g[0], x) for x in g)
+
+
 st = torch.cuda.current_stream().cuda_stream
+samp, burn = 12, 4
 
 
-def chain(lo, hi, flags):
+def make(N, P, seed):
+    rng = np.random.default_rng(seed)
+    X = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
+    bt = np.r_[np.abs(rng.normal(0, 0.3, P - 1)), -0.5]
+    y = (rng.random(N) < 1 / (1 + np.exp(-X @ bt))).astype(float)
+    yc = rng.poisson(np.exp(np.clip(X @ bt * 0.3 + 2.0, None, 4.0))).astype(float)
+    return X, y, yc
+
+
+def chain(X, y, lo, hi, flags):
+    P = X.shape[1]
     Xd = torch.from_numpy(X[lo:hi].copy()).to(dev); yd = torch.from_numpy(y[lo:hi].copy()).to(dev)
     nd = torch.ones(hi - lo, device=dev, dtype=torch.float64)
     m0 = torch.zeros(P, device=dev, dtype=torch.float64)
@@ -42,26 +85,8 @@ def chain(lo, hi, flags):
     return beta.cpu().numpy(), w.cpu().numpy()
 
 
-full = {f: chain(0, N, f) for f in (0, 1)}          # before the communicator exists: single-GPU chains
-bdist.init_comm(rank, world, dev)
-lo, hi = bdist.shard_range(rank, world, N)
-ok = True
-for f in (0, 1):
-    b, w = chain(lo, hi, f)
-    eb = np.max(np.abs(b - full[f][0]) / np.abs(full[f][0]))
-    ew = np.max(np.abs(w - full[f][1][:, lo:hi]) / full[f][1][:, lo:hi])
-    t = torch.tensor([eb, ew], device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        print(f"flags={f}: world={world} max rel diff beta {t[0].item():.2e} omega {t[1].item():.2e}")
-    ok = ok and t.max().item() < 1e-8
-
-
-# NB sweep (fixed d): exercises the P extra sums (X'v tail) of the exchange
-yc = rng.poisson(np.exp(np.clip(X @ bt * 0.3 + 2.0, None, 4.0))).astype(float)
-
-
-def nb_chain(lo, hi):
+def nb_chain(X, yc, lo, hi):
+    P = X.shape[1]
     Xd = torch.from_numpy(X[lo:hi].copy()).to(dev); yd = torch.from_numpy(yc[lo:hi].copy()).to(dev)
     m0 = torch.zeros(P, device=dev, dtype=torch.float64)
     P0 = (0.1 * torch.eye(P, device=dev, dtype=torch.float64)).contiguous()
@@ -75,20 +100,10 @@ def nb_chain(lo, hi):
     return beta.cpu().numpy(), w.cpu().numpy()
 
 
-def compare_nb(tag, ref):
-    b, w = nb_chain(lo, hi)
-    eb = np.max(np.abs(b - ref[0]) / np.abs(ref[0]))
-    ew = np.max(np.abs(w - ref[1][lo:hi]) / ref[1][lo:hi])
-    t = torch.tensor([eb, ew], device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        print(f"nb {tag}: max rel diff beta {t[0].item():.2e} omega {t[1].item():.2e}")
-    return t.max().item() < 1e-8, b
-
-
-def nb_df_chain(lo, hi):
+def nb_df_chain(X, yc, lo, hi):
     """NB sweep with the dispersion sampled on the device (draw.df): sharded, ymax / the count histogram /
     the log-likelihood sums of every Metropolis step are all-reduced."""
+    P = X.shape[1]
     Xd = torch.from_numpy(X[lo:hi].copy()).to(dev); yd = torch.from_numpy(yc[lo:hi].copy()).to(dev)
     m0 = torch.zeros(P, device=dev, dtype=torch.float64)
     P0 = (0.1 * torch.eye(P, device=dev, dtype=torch.float64)).contiguous()
@@ -102,42 +117,66 @@ def nb_df_chain(lo, hi):
     return beta.cpu().numpy(), dd.cpu().numpy()
 
 
+# P = 16: the vectorised slot copy; P = 7, 15: odd P (P*P sums without a tail is an odd count -- the last
+# Gram entry travels on its own); N not a multiple of anything convenient
+CASES = [(200_003, 16), (50_001, 7), (60_001, 15)] if not LOCAL_MODE else [(60_003, 16), (20_001, 7), (20_001, 15)]
+data = {c: make(c[0], c[1], 10 + c[1]) for c in CASES}
+full = {(c, f): chain(data[c][0], data[c][1], 0, c[0], f) for c in CASES for f in (0, 1)}   # no communicator yet
+c0 = CASES[0]
+nb_full = nb_chain(data[c0][0], data[c0][2], 0, c0[0])
+nbdf_full = nb_df_chain(data[c0][0], data[c0][2], 0, c0[0])
+
+ok = True
+
+
+def sharded_pass(tag):
+    global ok
+    for c in CASES:
+        lo, hi = bdist.shard_range(rank, world, c[0])
+        for f in (0, 1):
+            b, w = chain(data[c][0], data[c][1], lo, hi, f)
+            fb, fw = full[(c, f)]
+            eb = np.max(np.abs(b - fb) / np.abs(fb))
+            ew = np.max(np.abs(w - fw[:, lo:hi]) / fw[:, lo:hi])
+            eb, ew = allmax([eb, ew])
+            same = same_on_all_ranks(b)
+            if rank == 0:
+                print(f"[{tag}] logit N={c[0]} P={c[1]} flags={f}: world={world} max rel diff beta {eb:.2e} omega {ew:.2e}; "
+                      f"beta bit-identical across ranks: {same}", flush=True)
+            ok = ok and max(eb, ew) < 1e-8 and same
+    lo, hi = bdist.shard_range(rank, world, c0[0])
+    b, w = nb_chain(data[c0][0], data[c0][2], lo, hi)
+    eb = np.max(np.abs(b - nb_full[0]) / np.abs(nb_full[0]))
+    ew = np.max(np.abs(w - nb_full[1][lo:hi]) / nb_full[1][lo:hi])
+    eb, ew = allmax([eb, ew])
+    same = same_on_all_ranks(b)
+    if rank == 0:
+        print(f"[{tag}] nb: max rel diff beta {eb:.2e} omega {ew:.2e}; beta bit-identical across ranks: {same}", flush=True)
+    ok = ok and max(eb, ew) < 1e-8 and same
+    b_df, d_df = nb_df_chain(data[c0][0], data[c0][2], lo, hi)
+    e_df = float(np.max(np.abs(b_df - nbdf_full[0]) / np.abs(nbdf_full[0])))
+    same_d = bool(np.array_equal(d_df, nbdf_full[1]))
+    e_df, bad_d = allmax([e_df, 0.0 if same_d else 1.0])
+    if rank == 0:
+        print(f"[{tag}] nb with dispersion update: max rel diff beta {e_df:.2e}; d chain identical to the single-GPU chain "
+              f"on every rank: {bad_d == 0.0} (d: {d_df[0]:.0f} .. {d_df[-1]:.0f})", flush=True)
+    ok = ok and e_df < 1e-8 and bad_d == 0.0
+
+
+open_comm()
 peer = bdist.peer_exchange_active()
-bdist.destroy_comm()
-nb_full = nb_chain(0, N)                      # no communicator: single-GPU chain
-nbdf_full = nb_df_chain(0, N)
-bdist.init_comm(rank, world, dev)
-b_df, d_df = nb_df_chain(lo, hi)
-e_df = float(np.max(np.abs(b_df - nbdf_full[0]) / np.abs(nbdf_full[0])))
-same_d = bool(np.array_equal(d_df, nbdf_full[1]))
-t = torch.tensor([e_df, 0.0 if same_d else 1.0], device=dev, dtype=torch.float64)
-dist.all_reduce(t, op=dist.ReduceOp.MAX)
-if rank == 0:
-    print(f"nb with dispersion update: max rel diff beta {t[0].item():.2e}; d chain identical on every rank: {t[1].item() == 0.0} "
-          f"(d: {d_df[0]:.0f} .. {d_df[-1]:.0f})")
-ok = ok and t[0].item() < 1e-8 and t[1].item() == 0.0
-ok_nb, b_peer = compare_nb("peer windows" if bdist.peer_exchange_active() else "nccl", nb_full)
-ok = ok and ok_nb
-# beta must be bit-identical on every rank (replicated draw from identical sums)
-g = [torch.empty(b_peer.shape, device=dev, dtype=torch.float64) for _ in range(world)]
-dist.all_gather(g, torch.from_numpy(b_peer).to(dev))
-same = all(torch.equal(g[0], x) for x in g)
-if rank == 0:
-    print(f"beta bit-identical across ranks: {same}; peer exchange active: {peer}")
-ok = ok and same
-if peer:
+if LOCAL_MODE:
+    assert peer, "local communicator without peer windows"
+sharded_pass("peer windows" if peer else "nccl")
+if peer and not LOCAL_MODE:
     # the NCCL path on the same shards
     bdist.destroy_comm()
     os.environ["BL_PEER_EXCHANGE"] = "0"
     bdist.init_comm(rank, world, dev)
     assert not bdist.peer_exchange_active()
-    ok_nccl, _ = compare_nb("nccl", nb_full)
-    b, w = chain(lo, hi, 1)
-    eb = float(np.max(np.abs(b - full[1][0]) / np.abs(full[1][0])))
-    if rank == 0:
-        print(f"logit nccl: max rel diff beta {eb:.2e}")
-    ok = ok and ok_nccl and eb < 1e-8
+    sharded_pass("nccl")
 if rank == 0:
-    print("MULTI_GPU_OK" if ok else "MULTI_GPU_MISMATCH")
+    print(f"peer exchange active: {peer}; local mode (all ranks on cuda:0, no NCCL): {LOCAL_MODE}")
+    print("MULTI_GPU_OK" if ok else "MULTI_GPU_MISMATCH", flush=True)
 bdist.destroy_comm()
 dist.destroy_process_group()
