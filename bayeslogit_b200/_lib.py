@@ -95,6 +95,8 @@ def lib():
     L.bl_comm_unique_id.argtypes = [vp]
     L.bl_comm_init.argtypes = [vp, ci, ci]
     L.bl_comm_init_local.argtypes = [ci, ci]
+    L.bl_vcomm_create.argtypes = [ci]
+    L.bl_vcomm_bind.argtypes = [ci]
     L.bl_comm_peer_handle.argtypes = [vp]
     L.bl_comm_peer_open.argtypes = [vp]
     L.bl_probe_pg_moments.argtypes = [vp, vp, vp, vp, i64]

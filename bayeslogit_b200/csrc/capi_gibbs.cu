@@ -411,6 +411,27 @@ int bl_comm_peer_close(void)
 
 int bl_comm_peer_active(void) { return comm_peer_active(); }
 
+int bl_vcomm_create(int world)
+{
+    if (bl_ensure_ready_internal()) return 1;
+    std::string err;
+    if (comm_virtual_create(world, err)) return report(err, nullptr);
+    return 0;
+}
+
+int bl_vcomm_bind(int rank)
+{
+    std::string err;
+    if (comm_virtual_bind(rank, err)) return report(err, nullptr);
+    return 0;
+}
+
+int bl_vcomm_destroy(void)
+{
+    comm_virtual_destroy();
+    return 0;
+}
+
 int bl_comm_destroy(void)
 {
     comm_destroy();

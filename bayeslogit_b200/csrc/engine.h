@@ -91,6 +91,9 @@ int comm_peer_handle(void *out64, std::string &err);
 int comm_peer_open(const void *handles, std::string &err);
 void comm_peer_close();
 int comm_peer_active();
+int comm_virtual_create(int world, std::string &err);
+int comm_virtual_bind(int rank, std::string &err);
+void comm_virtual_destroy();
 
 void hybrid_timing_enable(bool on);
 int hybrid_timing_last(double *ms8, int *launches8);

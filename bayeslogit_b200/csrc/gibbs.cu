@@ -16,7 +16,11 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -33,9 +37,6 @@ namespace {
 
 struct Nccl {
     void *lib = nullptr;
-    void *comm = nullptr;
-    int rank = 0, world = 1;
-    bool local = false;            // ranks without an NCCL communicator (bl_comm_init_local): peer windows only
     int (*CommInitRank)(void **, int, char[128], int) = nullptr;   // ncclUniqueId by value (128 bytes)
     int (*GetUniqueId)(void *) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
@@ -82,41 +83,87 @@ struct Peer {
     size_t slot_doubles = 0;
     uint32_t epoch = 0;                    // exchanges issued so far (identical on every rank: SPMD)
     bool open = false;
-} g_peer;
+};
+
+// Lock-step rendezvous of the host threads that drive VIRTUAL ranks (see VGroup below).
+struct VBarrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    int world = 1, arrived = 0;
+    uint64_t generation = 0;
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        const uint64_t g = generation;
+        if (++arrived == world) { arrived = 0; ++generation; cv.notify_all(); }
+        // a rank that left with an error never arrives: give up after two minutes rather than hang the test
+        else if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return generation != g; })) { arrived = 0; ++generation; cv.notify_all(); }
+    }
+};
+
+// Communicator state of one rank: the process-wide one (one process per GPU), or one of the virtual
+// ranks a test binds its threads to.
+struct CommState {
+    void *comm = nullptr;          // ncclComm_t
+    int rank = 0, world = 1;
+    bool local = false;            // no NCCL communicator (bl_comm_init_local): peer windows only
+    Peer peer;
+    VBarrier *vbar = nullptr;      // virtual ranks only
+};
+
+CommState g_cs;
+thread_local CommState *t_cs = nullptr;
+inline CommState &cs() { return t_cs ? *t_cs : g_cs; }
+
+// Virtual ranks (test aid for boxes with fewer GPUs than ranks): W ranks of one communicator live in ONE
+// process on ONE device, each driven by its own host thread (bl_vcomm_bind) and ALL enqueueing into the
+// same CUDA stream.  Their windows are plain device allocations of this process.  At every exchange the
+// threads meet at a host barrier between enqueueing the producing kernel (slot stores + flags) and the
+// consuming kernel (flag wait + rank-ordered sums), so in stream order every producer of an exchange
+// precedes every consumer: no kernel ever waits for a kernel behind it, nothing relies on two kernels
+// being resident at the same time.  Kernels, descriptors, epochs and parities are those of the real
+// multi-GPU exchange.
+struct VGroup {
+    std::vector<std::unique_ptr<CommState>> ranks;
+    VBarrier bar;
+};
+std::unique_ptr<VGroup> g_vgroup;
+
+inline void exchange_rendezvous() { if (cs().vbar) cs().vbar->wait(); }
 
 constexpr size_t kPeerFlagBytes = 256;
 constexpr int kPeerMaxP = 256;
 
-bool peer_active() { return g_peer.open && g_nccl.world > 1; }
+bool peer_active() { return cs().peer.open && cs().world > 1; }
 
 // Descriptors of the next exchange through the windows (advances the epoch: call once per exchange,
 // on every rank, in the same order).
 void peer_next(PeerPush &px, PeerWait &pw)
 {
-    const unsigned e = ++g_peer.epoch;
-    const int par = (int)(e & 1u), me = g_nccl.rank;
+    const unsigned e = ++cs().peer.epoch;
+    const int par = (int)(e & 1u), me = cs().rank;
     px = PeerPush{};
     pw = PeerWait{};
-    px.world = pw.world = g_nccl.world;
+    px.world = pw.world = cs().world;
     px.epoch = pw.epoch = e;
-    px.done = g_peer.done;
-    for (int r = 0; r < g_nccl.world; ++r) {
-        char *w = (char *)g_peer.win[r];
+    px.done = cs().peer.done;
+    for (int r = 0; r < cs().world; ++r) {
+        char *w = (char *)cs().peer.win[r];
         px.flag[r] = (unsigned *)w + par * kMaxPeers + me;
-        px.slot[r] = (double *)(w + kPeerFlagBytes) + ((size_t)par * kMaxPeers + me) * g_peer.slot_doubles;
-        pw.slot[r] = (const double *)((char *)g_peer.base + kPeerFlagBytes) + ((size_t)par * kMaxPeers + r) * g_peer.slot_doubles;
+        px.slot[r] = (double *)(w + kPeerFlagBytes) + ((size_t)par * kMaxPeers + me) * cs().peer.slot_doubles;
+        pw.slot[r] = (const double *)((char *)cs().peer.base + kPeerFlagBytes) + ((size_t)par * kMaxPeers + r) * cs().peer.slot_doubles;
     }
-    pw.flag = (const unsigned *)g_peer.base + par * kMaxPeers;
+    pw.flag = (const unsigned *)cs().peer.base + par * kMaxPeers;
 }
 
 }  // namespace
 
-// Small all-reduce through the peer windows, one CTA per rank: store the local words into this rank's
-// slot of every window, raise the flags, wait for the world's flags, combine the slots in rank order
-// (bit-identical on every rank).  8-byte words; kOp 0: double sum, 1: uint64 sum, 2: uint64 max.
-template <int kOp>
+// Small all-reduce through the peer windows, two one-CTA kernels per rank.  k_peer_put: store the local
+// words into this rank's slot of every window and raise the flags.  k_peer_combine: wait for the world's
+// flags, combine the slots in rank order (bit-identical on every rank).  8-byte words; kOp 0: double sum,
+// 1: uint64 sum, 2: uint64 max.
 __global__ void __launch_bounds__(256)
-k_peer_allreduce(unsigned long long *buf, int cnt, PeerPush px, PeerWait pw, int *status)
+k_peer_put(const unsigned long long *buf, int cnt, PeerPush px)
 {
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
         const unsigned long long v = buf[i];
@@ -127,6 +174,12 @@ k_peer_allreduce(unsigned long long *buf, int cnt, PeerPush px, PeerWait pw, int
         __threadfence_system();
         for (int r = 0; r < px.world; ++r) st_release_sys(px.flag[r], px.epoch);
     }
+}
+
+template <int kOp>
+__global__ void __launch_bounds__(256)
+k_peer_combine(unsigned long long *buf, int cnt, PeerWait pw, int *status)
+{
     peer_wait(pw, status);
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
         unsigned long long a = __ldcg(reinterpret_cast<const unsigned long long *>(pw.slot[0]) + i);
@@ -148,22 +201,24 @@ enum SmallOp { kOpSumF64 = 0, kOpSumU64 = 1, kOpMaxU64 = 2 };
 // peer windows when they are open, else NCCL.  No-op without a communicator.
 int small_allreduce(void *buf, size_t cnt, SmallOp op, int *status, cudaStream_t st, std::string &err)
 {
-    if (g_nccl.world <= 1) return 0;
+    if (cs().world <= 1) return 0;
     if (peer_active()) {
-        if (cnt > g_peer.slot_doubles) { err = "peer all-reduce: vector longer than a window slot"; return 1; }
+        if (cnt > cs().peer.slot_doubles) { err = "peer all-reduce: vector longer than a window slot"; return 1; }
         PeerPush px;
         PeerWait pw;
         peer_next(px, pw);
         unsigned long long *b = (unsigned long long *)buf;
-        if (op == kOpSumF64) k_peer_allreduce<0><<<1, 256, 0, st>>>(b, (int)cnt, px, pw, status);
-        else if (op == kOpSumU64) k_peer_allreduce<1><<<1, 256, 0, st>>>(b, (int)cnt, px, pw, status);
-        else k_peer_allreduce<2><<<1, 256, 0, st>>>(b, (int)cnt, px, pw, status);
-        count_launch();
+        k_peer_put<<<1, 256, 0, st>>>(b, (int)cnt, px);
+        exchange_rendezvous();
+        if (op == kOpSumF64) k_peer_combine<0><<<1, 256, 0, st>>>(b, (int)cnt, pw, status);
+        else if (op == kOpSumU64) k_peer_combine<1><<<1, 256, 0, st>>>(b, (int)cnt, pw, status);
+        else k_peer_combine<2><<<1, 256, 0, st>>>(b, (int)cnt, pw, status);
+        count_launch(2);
         return 0;
     }
-    if (!g_nccl.comm) { err = "sharded sweep: no NCCL communicator and the peer windows are not open"; return 1; }
+    if (!cs().comm) { err = "sharded sweep: no NCCL communicator and the peer windows are not open"; return 1; }
     const int r = g_nccl.AllReduce(buf, buf, cnt, op == kOpSumF64 ? kNcclFloat64 : kNcclUint64,
-                                   op == kOpMaxU64 ? kNcclMax : kNcclSum, g_nccl.comm, st);
+                                   op == kOpMaxU64 ? kNcclMax : kNcclSum, cs().comm, st);
     if (r != 0) { err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return 1; }
     return 0;
 }
@@ -417,6 +472,7 @@ struct Sweep {
         k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nt > 1 ? 2 * nslab : nslab, px, packed ? 1 : 0,
                                                                 2 * nslab_diag);
         count_launch(2);
+        if (px.world > 1) exchange_rendezvous();     // virtual ranks: every producer is enqueued before any consumer
     }
 
     // acc[P^2..P^2+P) <- X'(c0 v0 + c1 v1 v2)
@@ -430,11 +486,11 @@ struct Sweep {
 
     int allreduce(bool with_tail, std::string &err)
     {
-        if (!exchange || g_nccl.world <= 1) return 0;
+        if (!exchange || cs().world <= 1) return 0;
         if (pending.world > 1) return 0;          // already pushed through the peer windows by gram()
-        if (!g_nccl.comm) { err = "sharded sweep: no NCCL communicator and the peer windows are not open"; return 1; }
+        if (!cs().comm) { err = "sharded sweep: no NCCL communicator and the peer windows are not open"; return 1; }
         size_t cnt = (size_t)P * P + (with_tail ? P : 0);
-        int r = g_nccl.AllReduce(acc, acc, cnt, kNcclFloat64, kNcclSum, g_nccl.comm, st);
+        int r = g_nccl.AllReduce(acc, acc, cnt, kNcclFloat64, kNcclSum, cs().comm, st);
         if (r != 0) { err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return 1; }
         return 0;
     }
@@ -827,7 +883,7 @@ int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const dou
         err = "nb_gibbs_df: bad arguments (d0 must be a positive integer)";
         return 1;
     }
-    const bool sharded = sharded_arg && g_nccl.world > 1;
+    const bool sharded = sharded_arg && cs().world > 1;
     DevMem mem;
     mem.st = st;
     Sweep s;
@@ -1002,17 +1058,17 @@ int comm_unique_id(void *out128, std::string &err)
 
 int comm_init(const void *id128, int rank, int world, std::string &err)
 {
-    if (world <= 1) { g_nccl.world = 1; g_nccl.rank = 0; return 0; }
+    if (world <= 1) { cs().world = 1; cs().rank = 0; return 0; }
     if (!nccl_load(err)) return 1;
     UniqueId id;
     memcpy(id.bytes, id128, 128);
     // ncclCommInitRank(ncclComm_t*, int nranks, ncclUniqueId commId /*by value*/, int rank)
     typedef int (*init_fn)(void **, int, UniqueId, int);
     init_fn init = (init_fn)dlsym(g_nccl.lib, "ncclCommInitRank");
-    int r = init(&g_nccl.comm, world, id, rank);
+    int r = init(&cs().comm, world, id, rank);
     if (r != 0) { err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return 1; }
-    g_nccl.rank = rank;
-    g_nccl.world = world;
+    cs().rank = rank;
+    cs().world = world;
     return 0;
 }
 
@@ -1021,29 +1077,29 @@ int comm_init(const void *id128, int rank, int world, std::string &err)
 int comm_init_local(int rank, int world, std::string &err)
 {
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) { err = "bl_comm_init_local: need 0 <= rank < world <= 8"; return 1; }
-    g_nccl.rank = rank;
-    g_nccl.world = world;
-    g_nccl.comm = nullptr;
-    g_nccl.local = world > 1;
+    cs().rank = rank;
+    cs().world = world;
+    cs().comm = nullptr;
+    cs().local = world > 1;
     return 0;
 }
 
 // Allocate (once) and zero this rank's window; out64 receives its CUDA IPC handle.
 int comm_peer_handle(void *out64, std::string &err)
 {
-    if (g_nccl.world <= 1) { err = "peer windows need a communicator of more than one rank (bl_comm_init first)"; return 1; }
-    if (g_nccl.world > kMaxPeers) { err = "peer windows support at most 8 ranks"; return 1; }
-    if (!g_peer.base) {
-        g_peer.slot_doubles = (size_t)kPeerMaxP * kPeerMaxP + kPeerMaxP;
-        size_t bytes = kPeerFlagBytes + 2 * (size_t)kMaxPeers * g_peer.slot_doubles * sizeof(double);
-        GB_CK(cudaMalloc(&g_peer.base, bytes));
-        GB_CK(cudaMalloc((void **)&g_peer.done, sizeof(unsigned)));
-        GB_CK(cudaMemset(g_peer.base, 0, bytes));
-        GB_CK(cudaMemset(g_peer.done, 0, sizeof(unsigned)));
+    if (cs().world <= 1) { err = "peer windows need a communicator of more than one rank (bl_comm_init first)"; return 1; }
+    if (cs().world > kMaxPeers) { err = "peer windows support at most 8 ranks"; return 1; }
+    if (!cs().peer.base) {
+        cs().peer.slot_doubles = (size_t)kPeerMaxP * kPeerMaxP + kPeerMaxP;
+        size_t bytes = kPeerFlagBytes + 2 * (size_t)kMaxPeers * cs().peer.slot_doubles * sizeof(double);
+        GB_CK(cudaMalloc(&cs().peer.base, bytes));
+        GB_CK(cudaMalloc((void **)&cs().peer.done, sizeof(unsigned)));
+        GB_CK(cudaMemset(cs().peer.base, 0, bytes));
+        GB_CK(cudaMemset(cs().peer.done, 0, sizeof(unsigned)));
         GB_CK(cudaDeviceSynchronize());
     }
     cudaIpcMemHandle_t h;
-    GB_CK(cudaIpcGetMemHandle(&h, g_peer.base));
+    GB_CK(cudaIpcGetMemHandle(&h, cs().peer.base));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     memcpy(out64, &h, 64);
     return 0;
@@ -1052,39 +1108,85 @@ int comm_peer_handle(void *out64, std::string &err)
 // handles: world x 64 bytes, rank order (every rank's comm_peer_handle output, all-gathered by the host).
 int comm_peer_open(const void *handles, std::string &err)
 {
-    if (!g_peer.base) { err = "bl_comm_peer_handle has not been called"; return 1; }
-    for (int r = 0; r < g_nccl.world; ++r) {
-        if (r == g_nccl.rank) { g_peer.win[r] = g_peer.base; continue; }
-        if (g_peer.win[r]) continue;
+    if (!cs().peer.base) { err = "bl_comm_peer_handle has not been called"; return 1; }
+    for (int r = 0; r < cs().world; ++r) {
+        if (r == cs().rank) { cs().peer.win[r] = cs().peer.base; continue; }
+        if (cs().peer.win[r]) continue;
         cudaIpcMemHandle_t h;
         memcpy(&h, (const char *)handles + 64 * (size_t)r, 64);
-        GB_CK(cudaIpcOpenMemHandle(&g_peer.win[r], h, cudaIpcMemLazyEnablePeerAccess));
+        GB_CK(cudaIpcOpenMemHandle(&cs().peer.win[r], h, cudaIpcMemLazyEnablePeerAccess));
     }
-    g_peer.open = true;
+    cs().peer.open = true;
     return 0;
 }
 
 void comm_peer_close()
 {
     for (int r = 0; r < kMaxPeers; ++r) {
-        if (g_peer.win[r] && g_peer.win[r] != g_peer.base) cudaIpcCloseMemHandle(g_peer.win[r]);
-        g_peer.win[r] = nullptr;
+        if (cs().peer.win[r] && cs().peer.win[r] != cs().peer.base) cudaIpcCloseMemHandle(cs().peer.win[r]);
+        cs().peer.win[r] = nullptr;
     }
-    g_peer.open = false;
+    cs().peer.open = false;
 }
 
 int comm_peer_active() { return peer_active() ? 1 : 0; }
 
+// ---- virtual ranks (see VGroup) ---------------------------------------------------------------
+int comm_virtual_create(int world, std::string &err)
+{
+    if (world < 2 || world > kMaxPeers) { err = "bl_vcomm_create: need 2 <= world <= 8"; return 1; }
+    if (g_vgroup) { err = "bl_vcomm_create: a virtual communicator already exists"; return 1; }
+    std::unique_ptr<VGroup> g(new VGroup);
+    g->bar.world = world;
+    const size_t slot = (size_t)kPeerMaxP * kPeerMaxP + kPeerMaxP;
+    const size_t bytes = kPeerFlagBytes + 2 * (size_t)kMaxPeers * slot * sizeof(double);
+    for (int r = 0; r < world; ++r) {
+        std::unique_ptr<CommState> c(new CommState);
+        c->rank = r; c->world = world; c->local = true; c->vbar = &g->bar;
+        c->peer.slot_doubles = slot;
+        GB_CK(cudaMalloc(&c->peer.base, bytes));
+        GB_CK(cudaMalloc((void **)&c->peer.done, sizeof(unsigned)));
+        GB_CK(cudaMemset(c->peer.base, 0, bytes));
+        GB_CK(cudaMemset(c->peer.done, 0, sizeof(unsigned)));
+        g->ranks.push_back(std::move(c));
+    }
+    for (int r = 0; r < world; ++r) {
+        for (int q = 0; q < world; ++q) g->ranks[r]->peer.win[q] = g->ranks[q]->peer.base;
+        g->ranks[r]->peer.open = true;
+    }
+    GB_CK(cudaDeviceSynchronize());
+    g_vgroup = std::move(g);
+    return 0;
+}
+
+// Bind the calling host thread to virtual rank `rank` (rank < 0: back to the process communicator).
+int comm_virtual_bind(int rank, std::string &err)
+{
+    if (rank < 0) { t_cs = nullptr; return 0; }
+    if (!g_vgroup || rank >= (int)g_vgroup->ranks.size()) { err = "bl_vcomm_bind: no such virtual rank"; return 1; }
+    t_cs = g_vgroup->ranks[rank].get();
+    return 0;
+}
+
+void comm_virtual_destroy()
+{
+    t_cs = nullptr;
+    if (!g_vgroup) return;
+    cudaDeviceSynchronize();
+    for (auto &c : g_vgroup->ranks) { cudaFree(c->peer.base); cudaFree(c->peer.done); }
+    g_vgroup.reset();
+}
+
 void comm_destroy()
 {
     comm_peer_close();
-    if (g_peer.base) { cudaDeviceSynchronize(); cudaFree(g_peer.base); cudaFree(g_peer.done); g_peer.base = nullptr; g_peer.done = nullptr; }
-    g_peer.epoch = 0;
-    if (g_nccl.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g_nccl.comm);
-    g_nccl.comm = nullptr;
-    g_nccl.world = 1;
-    g_nccl.rank = 0;
-    g_nccl.local = false;
+    if (cs().peer.base) { cudaDeviceSynchronize(); cudaFree(cs().peer.base); cudaFree(cs().peer.done); cs().peer.base = nullptr; cs().peer.done = nullptr; }
+    cs().peer.epoch = 0;
+    if (cs().comm && g_nccl.CommDestroy) g_nccl.CommDestroy(cs().comm);
+    cs().comm = nullptr;
+    cs().world = 1;
+    cs().rank = 0;
+    cs().local = false;
 }
 
 }  // namespace bl

@@ -41,16 +41,16 @@ def init_comm(rank, world, device=None):
         _open_peer_windows(L, rank, world, device)
 
 
-def init_comm_local(rank, world):
-    """Engine communicator WITHOUT NCCL: every exchange goes through the CUDA-IPC peer windows.  For ranks
-    NCCL cannot join (several processes sharing one device -- the one-GPU test of the exchange); the
-    handles travel over whatever torch.distributed backend is up (gloo)."""
+def init_comm_local(rank, world, device=None):
+    """Engine communicator WITHOUT NCCL (one process per GPU, one NVLink node): every exchange, the set-up
+    sums included, goes through the CUDA-IPC peer windows.  The window handles travel over whatever
+    torch.distributed backend is up."""
     from . import _lib
     L = _lib.lib()
     _lib.check(L.bl_comm_init_local(rank, world))
     if world <= 1:
         return
-    _open_peer_windows(L, rank, world, None)
+    _open_peer_windows(L, rank, world, device)
     if not L.bl_comm_peer_active():
         raise _lib.EngineError("bl_comm_init_local: the peer windows could not be mapped (CUDA IPC)")
 

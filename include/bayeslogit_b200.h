@@ -239,6 +239,17 @@ int bl_comm_peer_open(const void *handles);
 int bl_comm_peer_close(void);
 int bl_comm_peer_active(void);
 
+/* Virtual ranks -- a test aid for boxes with fewer GPUs than ranks.  bl_vcomm_create(world) makes a
+ * communicator of `world` ranks that all live in THIS process on THIS device (windows = plain device
+ * allocations); a host thread calls bl_vcomm_bind(r) and then the *_dev sweeps on its shard, every
+ * thread passing the SAME CUDA stream.  The threads meet at a host barrier inside every exchange,
+ * between enqueueing its producing and its consuming kernel, so in stream order all producers precede
+ * all consumers and no kernel ever waits for a later one.  Kernels, slot/flag descriptors, epochs and
+ * parities are those of the multi-GPU exchange.  bl_vcomm_bind(-1) unbinds the thread. */
+int bl_vcomm_create(int world);
+int bl_vcomm_bind(int rank);
+int bl_vcomm_destroy(void);
+
 /* Component probes for parity tests (host pointers, elementwise). */
 int bl_probe_pg_moments(double *m1, double *m2, const double *b, const double *z, int64_t num);
 int bl_probe_v_eval(double *v, const double *y, int64_t num);

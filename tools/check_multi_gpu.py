@@ -1,16 +1,10 @@
 #!/usr/bin/env python3
-"""Multi-rank check of the sharded sweeps (run under torchrun): the row-sharded logit / NB chains
-equal the single-GPU chains, beta is bit-identical on every rank, on the peer-window exchange and
-on ncclAllReduce.  Prints MULTI_GPU_OK on rank 0.
-
-Two ways to run it:
-  * one rank per GPU (default): torch.distributed over NCCL, engine communicator = NCCL + peer windows;
-  * BL_MG_LOCAL=1: every rank on cuda:0 (a one-GPU box), torch.distributed over gloo, engine
-    communicator = bl_comm_init_local (no NCCL: it refuses two ranks on one device), every exchange
-    through the CUDA-IPC peer windows.  The ranks' kernels time-slice the device, so the exchange's
-    flag waits cost a time slice each -- slow, but the same kernels (peer_publish / peer_wait /
-    peer_stage / k_peer_allreduce) on the same code path.
-"""
+"""Multi-GPU check of the sharded sweeps (run under torchrun, one rank per GPU): the row-sharded logit /
+NB chains equal the single-GPU chains and beta is bit-identical on every rank -- on the peer-window
+exchange (NCCL communicator + NVLink windows), on ncclAllReduce alone (BL_PEER_EXCHANGE=0), and on the
+windows alone (bl_comm_init_local: no NCCL communicator, the set-up sums go through k_peer_put /
+k_peer_combine too).  Prints MULTI_GPU_OK on rank 0.  One-GPU boxes: tests/test_gpu_multi.py runs the
+same exchange kernels with virtual ranks (bl_vcomm_*)."""
 import os
 import sys
 
@@ -21,36 +15,31 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bayeslogit_b200 import _lib, dist as bdist  # noqa: E402
 
-LOCAL_MODE = os.environ.get("BL_MG_LOCAL") == "1"
+LOCAL_MODE = False           # set below for the pass without an NCCL communicator
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-local = 0 if LOCAL_MODE else int(os.environ["LOCAL_RANK"])
+local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 L = _lib.lib()
 _lib.check(L.bl_set_device(local))
-if LOCAL_MODE:
-    dist.init_process_group("gloo")
-else:
-    dist.init_process_group("nccl", device_id=dev)
+dist.init_process_group("nccl", device_id=dev)
 
 
 def open_comm():
     if LOCAL_MODE:
-        bdist.init_comm_local(rank, world)
+        bdist.init_comm_local(rank, world, dev)
     else:
         bdist.init_comm(rank, world, dev)
 
 
 def allmax(vals):
-    t = torch.tensor(list(vals), dtype=torch.float64, device="cpu" if LOCAL_MODE else dev)
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return [float(v) for v in t.cpu()]
 
 
 def same_on_all_ranks(a):
-    t = torch.from_numpy(np.ascontiguousarray(a))
-    if not LOCAL_MODE:
-        t = t.to(dev)
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     g = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(g, t)
     return all(torch.equal(g[0], x) for x in g)
@@ -119,7 +108,7 @@ def nb_df_chain(X, yc, lo, hi):
 
 # P = 16: the vectorised slot copy; P = 7, 15: odd P (P*P sums without a tail is an odd count -- the last
 # Gram entry travels on its own); N not a multiple of anything convenient
-CASES = [(200_003, 16), (50_001, 7), (60_001, 15)] if not LOCAL_MODE else [(60_003, 16), (20_001, 7), (20_001, 15)]
+CASES = [(200_003, 16), (50_001, 7), (60_001, 15)]
 data = {c: make(c[0], c[1], 10 + c[1]) for c in CASES}
 full = {(c, f): chain(data[c][0], data[c][1], 0, c[0], f) for c in CASES for f in (0, 1)}   # no communicator yet
 c0 = CASES[0]
@@ -165,18 +154,23 @@ def sharded_pass(tag):
 
 open_comm()
 peer = bdist.peer_exchange_active()
-if LOCAL_MODE:
-    assert peer, "local communicator without peer windows"
 sharded_pass("peer windows" if peer else "nccl")
-if peer and not LOCAL_MODE:
+if peer:
     # the NCCL path on the same shards
     bdist.destroy_comm()
     os.environ["BL_PEER_EXCHANGE"] = "0"
     bdist.init_comm(rank, world, dev)
     assert not bdist.peer_exchange_active()
     sharded_pass("nccl")
+    # ... and the windows alone, without an NCCL communicator
+    bdist.destroy_comm()
+    os.environ["BL_PEER_EXCHANGE"] = "1"
+    LOCAL_MODE = True
+    open_comm()
+    assert bdist.peer_exchange_active()
+    sharded_pass("peer windows, no NCCL communicator")
 if rank == 0:
-    print(f"peer exchange active: {peer}; local mode (all ranks on cuda:0, no NCCL): {LOCAL_MODE}")
+    print(f"peer exchange active: {peer}")
     print("MULTI_GPU_OK" if ok else "MULTI_GPU_MISMATCH", flush=True)
 bdist.destroy_comm()
 dist.destroy_process_group()
