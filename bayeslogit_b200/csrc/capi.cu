@@ -526,6 +526,16 @@ int bl_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2)
     return dout.get(out4, 16);
 }
 
+int bl_probe_peaks(double *out6)
+{
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (ensure_ready()) return 1;
+    if (!out6) return fail("null argument");
+    std::string err;
+    if (probe_peaks(out6, g.slot[0].stream, err)) return fail("bl_probe_peaks: " + err);
+    return 0;
+}
+
 uint64_t bl_kernel_launches(void) { return g_launches.load(); }
 
 // Host logic only (no device): the chunk sizes run_host would use for a batch of `num` observations.

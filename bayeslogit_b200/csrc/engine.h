@@ -95,6 +95,9 @@ int comm_virtual_create(int world, std::string &err);
 int comm_virtual_bind(int rank, std::string &err);
 void comm_virtual_destroy();
 
+// pipe-throughput microbenchmarks (probe_peaks.cu)
+int probe_peaks(double *out6, cudaStream_t stream, std::string &err);
+
 void hybrid_timing_enable(bool on);
 int hybrid_timing_last(double *ms8, int *launches8);
 

@@ -257,6 +257,12 @@ int bl_probe_specfun(double *out, int which, const double *a, const double *b, c
                      int64_t num);
 int bl_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2);
 
+/* Pipe-throughput microbenchmarks on the current device, the denominators of the sampler's compute
+ * roofline (bench.py): out6 = FP64 FMA TFLOP/s, FP32 FMA TFLOP/s, MUFU (ex2/lg2) Gop/s, FP64 tensor
+ * (DMMA m8n8k4) TFLOP/s, 32x32->64 integer multiply + fold (one Philox round half) Gop/s, issued warp
+ * instructions G/s.  Best of four launches each, ~10 ms in total. */
+int bl_probe_peaks(double *out6);
+
 /* Host logic probe (no device needed): chunk sizes, in order, that the host-pointer entry points use to
  * stream a batch of num observations through HBM (small chunks open and close the batch so the pipeline
  * fills and drains quickly).  Writes at most cap sizes; returns the number of chunks, -1 for num < 0. */
