@@ -536,6 +536,16 @@ int bl_probe_peaks(double *out6)
     return 0;
 }
 
+int bl_probe_dmma_scaling(double *out4)
+{
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (ensure_ready()) return 1;
+    if (!out4) return fail("null argument");
+    std::string err;
+    if (probe_dmma_scaling(out4, g.slot[0].stream, err)) return fail("bl_probe_dmma_scaling: " + err);
+    return 0;
+}
+
 uint64_t bl_kernel_launches(void) { return g_launches.load(); }
 
 // Host logic only (no device): the chunk sizes run_host would use for a batch of `num` observations.

@@ -97,6 +97,7 @@ void comm_virtual_destroy();
 
 // pipe-throughput microbenchmarks (probe_peaks.cu)
 int probe_peaks(double *out6, cudaStream_t stream, std::string &err);
+int probe_dmma_scaling(double *out4, cudaStream_t stream, std::string &err);
 
 void hybrid_timing_enable(bool on);
 int hybrid_timing_last(double *ms8, int *launches8);

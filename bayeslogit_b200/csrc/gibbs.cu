@@ -27,6 +27,7 @@
 #include "engine.h"
 #include "gibbs_beta.cuh"
 #include "gibbs_kernels.cuh"
+#include "gibbs_sweep.h"
 
 namespace bl {
 
@@ -548,6 +549,12 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
     const int mode = (flags & BL_GIBBS_PLAIN_BETA) ? kBetaPlain : kBetaConstrained;
     // psi = X beta and the omega draw as one pass over X (k_logit_psi_draw) unless asked otherwise
     const bool fused = !(flags & BL_GIBBS_UNFUSED) && logit_psi_draw_ok(tX, P);
+    // ... or, on request and for even P <= 64, psi, omega and the Gram from ONE TMA-staged read of X
+    // (k_logit_sweep): exactly N P 8 bytes of HBM traffic per iteration, but bound by the latency of the draw
+    // warps that fit beside the Gram warps (gibbs_sweep.cu), so not the default
+    const bool one_pass = (flags & BL_GIBBS_ONE_PASS) && !(flags & BL_GIBBS_UNFUSED) && logit_sweep_ok(tX, P);
+    LogitSweep k3;
+    if (one_pass && k3.init(tX, N, P, st, err)) return 1;
 
     // set_prior / set_bP: b0 = P0 m0, bP = b0 + X'(n (y - 1/2))   (Logit.hpp:174-190)
     k_kappa<<<cdiv(N, 256), 256, 0, st>>>(kappa, y, n, 0.0, N);
@@ -570,30 +577,40 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
         double *bcur = beta_out, *bprev = beta_out;
         double *wcur = keep_w ? w_out : s.w;
         const double *bpsi = bcur;                                    // the beta the next omega draw conditions on
-        if (!fused) s.xbeta(s.psi, bcur, nullptr, 0.0);
+        if (!fused && !one_pass) s.xbeta(s.psi, bcur, nullptr, 0.0);
         for (int m = 1; m <= iters; ++m, ++t) {
             const bool tm = timing && phase == 1 && m == iters;       // BL_GIBBS_TIMING=1: stage times
             if (tm) cudaEventRecord(ev[0], st);
-            cudaError_t e = fused
-                ? launch_logit_psi_draw(wcur, nullptr, shape, tX, bpsi, 0, 1, N, P, StreamId{seed, obs0, t}, st)
-                : launch_devroye_refill(wcur, shape, s.psi, N, StreamId{seed, obs0, t}, st);
-            if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
-            if (tm) cudaEventRecord(ev[1], st);
-            s.gram(wcur);
+            if (one_pass) {
+                PeerPush px{};
+                s.pending = PeerWait{};
+                if (s.exchange && peer_active()) peer_next(px, s.pending);
+                cudaError_t e = k3.launch(wcur, s.acc, shape, bpsi, StreamId{seed, obs0, t}, px);
+                if (e != cudaSuccess) { err = std::string("k_logit_sweep: ") + cudaGetErrorString(e); return 1; }
+                if (px.world > 1) exchange_rendezvous();
+                if (tm) cudaEventRecord(ev[1], st);
+            } else {
+                cudaError_t e = fused
+                    ? launch_logit_psi_draw(wcur, nullptr, shape, tX, bpsi, 0, 1, N, P, StreamId{seed, obs0, t}, st)
+                    : launch_devroye_refill(wcur, shape, s.psi, N, StreamId{seed, obs0, t}, st);
+                if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
+                if (tm) cudaEventRecord(ev[1], st);
+                s.gram(wcur);
+            }
             if (tm) cudaEventRecord(ev[2], st);
             if (s.allreduce(false, err)) return 1;
             if (tm) cudaEventRecord(ev[3], st);
             s.beta_draw(mode, P0, bP, false, bprev, bcur, seed, t);
             if (tm) cudaEventRecord(ev[4], st);
             bpsi = bcur;
-            if (!fused) s.xbeta(s.psi, bcur, nullptr, 0.0);
+            if (!fused && !one_pass) s.xbeta(s.psi, bcur, nullptr, 0.0);
             if (tm) {
                 cudaEventRecord(ev[5], st);
                 cudaEventSynchronize(ev[5]);
                 float d[5];
                 for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&d[k], ev[k], ev[k + 1]);
                 fprintf(stderr, "[bl gibbs timing, us] %s %.1f gram %.1f allreduce %.1f beta %.1f xbeta %.1f\n",
-                        fused ? "psi+draw" : "draw", d[0] * 1e3, d[1] * 1e3, d[2] * 1e3, d[3] * 1e3, d[4] * 1e3);
+                        one_pass ? "psi+draw+gram (one pass)" : fused ? "psi+draw" : "draw", d[0] * 1e3, d[1] * 1e3, d[2] * 1e3, d[3] * 1e3, d[4] * 1e3);
                 for (auto &x : ev) cudaEventDestroy(x);
             }
             if (phase == 1) {

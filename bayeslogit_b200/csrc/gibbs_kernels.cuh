@@ -31,7 +31,7 @@ namespace bl {
 // spent 66 warp instructions per row and ran at 4.3 TB/s with the LSU and ALU pipes half busy.
 // HBM-bound: N P 8 bytes.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2)
+static __global__ void __launch_bounds__(256, 2)
 k_xbeta(double *__restrict__ psi, const double *__restrict__ tX, const double *__restrict__ beta,
         const double *__restrict__ off, double off_scale, double shift, int64_t N, int P)
 {
@@ -77,7 +77,7 @@ k_xbeta(double *__restrict__ psi, const double *__restrict__ tX, const double *_
 
 // The same for a batch of independent chains: rows [c N, (c+1) N) belong to chain c and meet
 // beta_c = beta[c * beta_stride ..).  Trips of 32 rows never straddle two chains.
-__global__ void __launch_bounds__(256, 2)
+static __global__ void __launch_bounds__(256, 2)
 k_xbeta_chains(double *__restrict__ psi, const double *__restrict__ tX, const double *__restrict__ beta,
                int64_t beta_stride, int chains, int N, int P)
 {
@@ -181,7 +181,7 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 // instructions per trip in the transposing butterfly and idles HBM meanwhile (4.6 TB/s at P = 64,
 // 2.4 TB/s at P = 32).  Chains: rows [c N, (c+1) N) meet beta + c * beta_stride.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2)
+static __global__ void __launch_bounds__(256, 2)
 k_xbeta_mma(double *__restrict__ psi, const double *__restrict__ tX, const double *__restrict__ beta,
             int64_t beta_stride, int chains, int64_t N, int P,
             const double *__restrict__ off, double off_scale, double shift)
@@ -688,7 +688,7 @@ __device__ __forceinline__ void peer_stage(const PeerWait &pw, double *A, double
 // PP = P0 + sum over slabs of the partial tiles, mirrored to a full symmetric P x P
 // column-major matrix.  One warp-row of threads per output element group: each CTA owns
 // 32 upper-triangle candidates, its 8 warps split the slabs, fixed summation order.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
               const double *__restrict__ part, int P, int nt, int nslab, PeerPush px, int packed = 0,
               int nslab_diag = 0)      // nslab: partial tiles per output tile (stride); diagonal tiles hold nslab_diag of them (0: nslab)
@@ -737,7 +737,7 @@ k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
 
 // out_p = sum_i x_i[p] * v_i  (X'v), v_i = c0*v0_i + c1*v1_i*v2_i  (v1/v2 optional).
 // Per-CTA partial sums then a fixed-order reduce (k_xtv_reduce).
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_xtv_partial(double *__restrict__ part, const double *__restrict__ tX, const double *__restrict__ v0,
               double c0, const double *__restrict__ v1, const double *__restrict__ v2, double c1,
               int64_t N, int P, const double *__restrict__ c1_dev = nullptr)
@@ -779,7 +779,7 @@ k_xtv_partial(double *__restrict__ part, const double *__restrict__ tX, const do
 // .y to the one for the odd columns.  A warp owns one 64-column panel and every (8 / panels)-th
 // group of 16 rows of the CTA's slab, 16 loads of 16 bytes in flight per lane; the scalar
 // k_xtv_partial above keeps 4 rows in flight per warp and reaches 1.1 TB/s.
-__global__ void __launch_bounds__(256, 2)
+static __global__ void __launch_bounds__(256, 2)
 k_xtv_mma(double *__restrict__ part, const double *__restrict__ tX, const double *__restrict__ v0,
           double c0, const double *__restrict__ v1, const double *__restrict__ v2, double c1,
           int64_t N, int P, const double *__restrict__ c1_dev)
@@ -945,7 +945,7 @@ inline int xtv_stream_log2l(const double *tX, int P)
     return l;
 }
 
-__global__ void k_xtv_reduce(double *__restrict__ out, const double *__restrict__ add0,
+static __global__ void k_xtv_reduce(double *__restrict__ out, const double *__restrict__ add0,
                              const double *__restrict__ add1, const double *__restrict__ part,
                              int P, int nslab)
 {
@@ -961,7 +961,7 @@ __global__ void k_xtv_reduce(double *__restrict__ out, const double *__restrict_
 }
 
 // kappa_i = n_i (y_i - 1/2)   (Logit.hpp:180-181);  NB: kappa_i = (y_i - d)/2
-__global__ void k_kappa(double *__restrict__ kappa, const double *__restrict__ y,
+static __global__ void k_kappa(double *__restrict__ kappa, const double *__restrict__ y,
                         const double *__restrict__ n, double d, int64_t N)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -969,12 +969,12 @@ __global__ void k_kappa(double *__restrict__ kappa, const double *__restrict__ y
 }
 
 // shape_i = (int) n_i  (Logit.hpp:287)  /  b_i = y_i + d  (NBPG-logmean.R:88)
-__global__ void k_shape_int(int *__restrict__ out, const double *__restrict__ n, int64_t N)
+static __global__ void k_shape_int(int *__restrict__ out, const double *__restrict__ n, int64_t N)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < N) out[i] = (int)n[i];
 }
-__global__ void k_shape_add(double *__restrict__ out, const double *__restrict__ y, double d, int64_t N)
+static __global__ void k_shape_add(double *__restrict__ out, const double *__restrict__ y, double d, int64_t N)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < N) out[i] = y[i] + d;
@@ -1003,7 +1003,7 @@ __device__ __forceinline__ double nb_df_proposal(double d, uint64_t seed, uint32
     return lower + k;
 }
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_nb_df_partial(double *__restrict__ part, const double *__restrict__ phi, const double *__restrict__ y,
                 const double *__restrict__ dptr, int64_t N, uint64_t seed, uint32_t call)
 {
@@ -1038,7 +1038,7 @@ k_nb_df_partial(double *__restrict__ part, const double *__restrict__ phi, const
 
 // Sharded rows: the CTA partials of this rank's rows folded to the four sums (fixed order) that the
 // ranks then all-reduce; k_nb_df_decide reads the result as a single partial.
-__global__ void k_nb_df_fold(double *__restrict__ sum4, const double *__restrict__ part, int nblk)
+static __global__ void k_nb_df_fold(double *__restrict__ sum4, const double *__restrict__ part, int nblk)
 {
     const int lane = threadIdx.x;
     double s[4] = {0.0, 0.0, 0.0, 0.0};
@@ -1051,7 +1051,7 @@ __global__ void k_nb_df_fold(double *__restrict__ sum4, const double *__restrict
         for (int k = 0; k < 4; ++k) sum4[k] = s[k];
 }
 
-__global__ void k_nb_df_decide(double *__restrict__ dptr, double *__restrict__ ldptr, double *__restrict__ d_rec,
+static __global__ void k_nb_df_decide(double *__restrict__ dptr, double *__restrict__ ldptr, double *__restrict__ d_rec,
                                const double *__restrict__ part, int nblk, const double *__restrict__ G, int ymax,
                                uint64_t seed, uint32_t call)
 {
@@ -1081,7 +1081,7 @@ __global__ void k_nb_df_decide(double *__restrict__ dptr, double *__restrict__ l
 }
 
 // psi <- phi - log d, shape <- y + d, kappa <- (y - d)/2 with d from device memory (NBPG-logmean.R:88-94)
-__global__ void k_nb_prepare(double *__restrict__ psi, double *__restrict__ shape, double *__restrict__ kappa,
+static __global__ void k_nb_prepare(double *__restrict__ psi, double *__restrict__ shape, double *__restrict__ kappa,
                              const double *__restrict__ y, const double *__restrict__ dptr,
                              const double *__restrict__ ldptr, int64_t N)
 {
@@ -1094,7 +1094,7 @@ __global__ void k_nb_prepare(double *__restrict__ psi, double *__restrict__ shap
 }
 
 // ymax and G[j] = #{y_i > j} (NBPG-logmean.R:65-67)
-__global__ void k_nb_ymax(unsigned long long *__restrict__ ymax, const double *__restrict__ y, int64_t N)
+static __global__ void k_nb_ymax(unsigned long long *__restrict__ ymax, const double *__restrict__ y, int64_t N)
 {
     int m = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
@@ -1102,12 +1102,12 @@ __global__ void k_nb_ymax(unsigned long long *__restrict__ ymax, const double *_
     for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(ymax, (unsigned long long)m);
 }
-__global__ void k_nb_hist(unsigned long long *__restrict__ hist, const double *__restrict__ y, int64_t N)
+static __global__ void k_nb_hist(unsigned long long *__restrict__ hist, const double *__restrict__ y, int64_t N)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
         atomicAdd(&hist[(int)y[i]], 1ull);
 }
-__global__ void k_nb_suffix(double *__restrict__ G, const unsigned long long *__restrict__ hist, int ymax)
+static __global__ void k_nb_suffix(double *__restrict__ G, const unsigned long long *__restrict__ hist, int ymax)
 {
     unsigned long long run = 0;                    // G[j] = sum_{k > j} hist[k], j = ymax-1 .. 0
     for (int j = ymax - 1; j >= 0; --j) {
@@ -1119,7 +1119,7 @@ __global__ void k_nb_suffix(double *__restrict__ G, const unsigned long long *__
 // mlogit offsets for category j: A = sum_{k != j, k < J-1} exp(XB_k) + exp(0),
 // c = log A, eta = XB_j - c.  XB is N x (J-1) column-major (the reference's J-th
 // column is identically 0, MultLogit.hpp:275-277).  No max-subtraction, as there.
-__global__ void k_mlogit_offsets(double *__restrict__ c, double *__restrict__ eta,
+static __global__ void k_mlogit_offsets(double *__restrict__ c, double *__restrict__ eta,
                                  const double *__restrict__ XB, int64_t N, int U, int j)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -88,6 +88,25 @@ __global__ void __launch_bounds__(1024) k_peak_dmma(double *out, double a, doubl
     if (s == 12345.678) out[0] = s;
 }
 
+// The same with operands that change from one MMA to the next, as in a real contraction: every MMA reads its
+// own A and B registers (here: rotated through eight live values), so nothing comes from the operand reuse cache.
+__global__ void __launch_bounds__(1024) k_peak_dmma_operands(double *out, double a, double b)
+{
+    double c[kChains][2], av[kChains], bv[kChains];
+#pragma unroll
+    for (int k = 0; k < kChains; ++k) { c[k][0] = k; c[k][1] = -k; av[k] = a + 1e-3 * (threadIdx.x + k); bv[k] = b + 1e-3 * (threadIdx.x ^ k); }
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int k = 0; k < kChains; ++k)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(av[k]), "d"(bv[(k + it) & (kChains - 1)]));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kChains; ++k) s += c[k][0] + c[k][1];
+    if (s == 12345.678) out[0] = s;
+}
+
 // the Philox round's multiply: 32 x 32 -> 64 bit (IMAD.WIDE.U32), folded back to 32 bits
 __global__ void __launch_bounds__(1024) k_peak_imad(unsigned *out, unsigned m)
 {
@@ -178,6 +197,29 @@ int probe_peaks(double *out6, cudaStream_t st, std::string &err)
     out6[4] = ops / (ms * 1e-3) / 1e9;
     rc |= time_kernel([&] { k_peak_issue<<<grid, block, 0, st>>>((unsigned *)sink, 1.0000001f, 1e-9f, 12345u); }, &ms, st, err);
     out6[5] = (threads / 32) * kIters * kChains / (ms * 1e-3) / 1e9;
+    cudaFree(sink);
+    return rc;
+}
+
+// DMMA rate against resident warps: out[k] = TFLOP/s with 1 CTA per SM of 128 << k threads (k = 0..3: one, two,
+// four, eight warps per scheduler), eight independent accumulator pairs per warp.  Design aid for the Gram
+// kernels: how many warps a scheduler needs before the FP64 tensor path stays busy.
+int probe_dmma_scaling(double *out4, cudaStream_t st, std::string &err)   // out4: 8 doubles
+{
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    void *sink = nullptr;
+    if (cudaMalloc(&sink, 64) != cudaSuccess) { err = "cudaMalloc failed"; return 1; }
+    int rc = 0;
+    for (int k = 0; k < 4; ++k) {
+        const int block = 128 << k;
+        double ms = 0;
+        rc |= time_kernel([&] { k_peak_dmma<<<sms, block, 0, st>>>((double *)sink, 1.0000001, 1e-9); }, &ms, st, err);
+        out4[k] = ((double)sms * block / 32) * kIters * kChains * 512.0 / (ms * 1e-3) / 1e12;
+        rc |= time_kernel([&] { k_peak_dmma_operands<<<sms, block, 0, st>>>((double *)sink, 1.0000001, 1e-9); }, &ms, st, err);
+        out4[4 + k] = ((double)sms * block / 32) * kIters * kChains * 512.0 / (ms * 1e-3) / 1e12;
+    }
     cudaFree(sink);
     return rc;
 }

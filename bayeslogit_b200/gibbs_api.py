@@ -21,6 +21,7 @@ NA = float("nan")
 PLAIN_BETA = 1   # BL_GIBBS_PLAIN_BETA
 NO_W = 2         # BL_GIBBS_NO_W
 UNFUSED = 4      # BL_GIBBS_UNFUSED (psi = X beta and the omega draw as two kernels; A/B aid)
+ONE_PASS = 8     # BL_GIBBS_ONE_PASS (psi, omega and the Gram from one TMA-staged read of X; even P <= 64)
 
 
 def _f(a):

@@ -164,6 +164,10 @@ int bl_rpg_hybrid_tape(double *x, const double *h, const double *z, int64_t num,
 #define BL_GIBBS_UNFUSED 4      /* measurement / A-B aid: psi = X beta and the omega draw as two kernels instead of
                                    the fused pass over X (same chain, bit for bit) */
 
+#define BL_GIBBS_ONE_PASS 8      /* even P <= 64: psi, omega and X' Omega X from ONE TMA-staged read of X per iteration
+                                   (k_logit_sweep, gibbs_sweep.cu) instead of two passes (k_logit_psi_draw + k_gram_partial);
+                                   same chain up to the summation order of psi and the Gram */
+
 /* `gibbs` with an explicit seed and flags; host pointers, layouts as `gibbs`. */
 int bl_logit_gibbs(double *w, double *beta, const double *y, const double *tX, const double *n,
                    const double *m0, const double *P0, int N, int P, int samp, int burn,
@@ -262,6 +266,9 @@ int bl_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2);
  * (DMMA m8n8k4) TFLOP/s, 32x32->64 integer multiply + fold (one Philox round half) Gop/s, issued warp
  * instructions G/s.  Best of four launches each, ~10 ms in total. */
 int bl_probe_peaks(double *out6);
+/* FP64 tensor (DMMA) TFLOP/s with one, two, four and eight resident warps per scheduler: out8[0..4) with the
+ * same A/B registers in every MMA, out8[4..8) with operands that change from MMA to MMA (design aid). */
+int bl_probe_dmma_scaling(double *out8);
 
 /* Host logic probe (no device needed): chunk sizes, in order, that the host-pointer entry points use to
  * stream a batch of num observations through HBM (small chunks open and close the batch so the pipeline

@@ -70,6 +70,20 @@ def test_logit_chain_matches_oracle(gapi, constrained, N, P, binomial):
         assert np.all(b[:, :-1] >= 0)
 
 
+@pytest.mark.parametrize("constrained", [False, True])
+@pytest.mark.parametrize("N,P", [(1500, 64), (20_001, 40), (1_000_000, 64)])
+def test_one_pass_sweep_matches_oracle(gapi, constrained, N, P):
+    """The one-pass sweep kernel against the oracle directly (N = 1 000 000, P = 64 is BASELINE config 3's shape)."""
+    X, y, n, _ = synth_logit(N, P, 31 + P)
+    m0 = np.zeros(P)
+    P0 = 0.05 * np.eye(P)
+    samp, burn = (2, 1) if N > 100_000 else (5, 3)
+    flags = gapi.ONE_PASS | (0 if constrained else gapi.PLAIN_BETA)
+    w, b = gapi.logit_gibbs(y, X, n, m0, P0, samp, burn, seed=91, flags=flags)
+    wo, bo = loader.logit_gibbs(y, X, n, m0, P0, samp, burn, seed=91, constrained=constrained)
+    close(b, bo); close(w, wo)
+
+
 def test_logit_burn_zero_and_no_w(gapi):
     X, y, n, _ = synth_logit(1000, 4, 5)
     P0 = np.eye(4)
@@ -266,6 +280,25 @@ def test_dropin_logit_and_mlogit_wrappers(gapi, engine):
     assert np.max(np.abs(om["beta"].mean(0) - B)) < 0.3
 
 
+@pytest.mark.parametrize("constrained", [False, True])
+@pytest.mark.parametrize("N,P,binomial", [(4099, 64, False), (200_001, 64, False), (2000, 6, True), (1777, 34, False), (50_000, 32, True),
+                                          (97, 2, False)])
+def test_one_pass_sweep_matches_two_pass_path(gapi, constrained, N, P, binomial):
+    """k_logit_sweep (flag BL_GIBBS_ONE_PASS: psi, omega and X' Omega X from one TMA-staged read of X) against
+    the default two-pass path (k_logit_psi_draw + k_gram_partial).  The two sum psi and the Gram in different
+    orders (fp64, N terms), so the chains agree to rounding, not bit for bit: 1e-9 over 9 iterations.
+    Covers every column-box count (P = 2, 6, 32, 34, 64), ragged last tiles, n_i in {1..5}, a grid of
+    148 CTAs (N = 200 001) and grids smaller than the reduction's 128 entry runs."""
+    X, y, n, _ = synth_logit(N, P, 99 + P, binomial)
+    m0 = np.linspace(-0.1, 0.1, P)
+    P0 = 0.3 * np.eye(P) + 0.01
+    f = 0 if constrained else gapi.PLAIN_BETA
+    w1, b1 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=15, flags=f | gapi.ONE_PASS)
+    w2, b2 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=15, flags=f)
+    close(b1, b2, 1e-9); close(w1, w2, 1e-9)
+    assert np.all(w1 > 0)
+
+
 @pytest.mark.parametrize("N,P,binomial", [(4099, 64, False), (2000, 6, True), (1777, 34, False)])
 def test_fused_psi_draw_equals_two_kernel_path(gapi, N, P, binomial):
     """k_logit_psi_draw (psi = X beta and omega = PG(n, psi) in one pass over X) forms psi with the MMA
@@ -275,7 +308,7 @@ def test_fused_psi_draw_equals_two_kernel_path(gapi, N, P, binomial):
     X, y, n, _ = synth_logit(N, P, 77 + P, binomial)
     m0 = np.zeros(P)
     P0 = 0.3 * np.eye(P)
-    w1, b1 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=5, flags=1)
+    w1, b1 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=5, flags=gapi.PLAIN_BETA)
     w2, b2 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=5, flags=gapi.PLAIN_BETA | gapi.UNFUSED)
     assert np.array_equal(w1, w2) and np.array_equal(b1, b2)
     assert np.all(w1 > 0) and np.all(np.isfinite(b1))
