@@ -269,19 +269,21 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
         cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status);
         return;
     }
-    // stage PP = Gram + P0 (batched loads: four columns in flight per thread)
-    for (int col0 = 0; col0 < P; col0 += 16) {
-        double g[4], q[4];
+    // stage PP = Gram + P0.  P <= 64: every load of the thread (16 Gram entries, 16 prior entries) is issued before
+    // the first use -- one L2 round trip instead of four.
+    if (P <= 64) {
+        double g[16], q[16];
+        const int PP2 = P * P;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            int col = col0 + (threadIdx.x >> 6) + 4 * u, row = threadIdx.x & 63;
-            g[u] = 0.0; q[u] = 0.0;
-            for (int r = row; r < P && col < P; r += 64) { g[u] = acc[r + (size_t)P * col]; q[u] = P0 ? P0[r + (size_t)P * col] : 0.0; if (P <= 64) break; }
+        for (int u = 0; u < 16; ++u) {
+            const int k = threadIdx.x + 256 * u;
+            g[u] = k < PP2 ? __ldcg(acc + k) : 0.0;
+            q[u] = (k < PP2 && P0) ? __ldg(P0 + k) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            int col = col0 + (threadIdx.x >> 6) + 4 * u, row = threadIdx.x & 63;
-            if (P <= 64) { if (row < P && col < P) A[row + (size_t)ld * col] = g[u] + q[u]; }
+        for (int u = 0; u < 16; ++u) {
+            const int k = threadIdx.x + 256 * u;
+            if (k < PP2) A[k % P + (size_t)ld * (k / P)] = g[u] + q[u];
         }
     }
     if (P > 64)

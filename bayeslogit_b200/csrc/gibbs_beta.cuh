@@ -235,7 +235,23 @@ __device__ inline double stream_normal(uint64_t seed, uint32_t call, int k)
 //   (b) one thread per column right of the block finishes the 8 panel rows of that column
 //       (forward substitution with the block, no barrier inside);
 //   (c) all threads apply the rank-8 update to the trailing matrix.
-__device__ __forceinline__ void cta_ldl_upper(double *A, double *rd, int P, int ld, int *ok)
+// 1 / d for a positive normal d: hardware seed (20 bits) and two Newton steps, ~6 dependent operations
+// instead of the ~25 of an IEEE division -- eight of these sit on the critical path of every panel.  Within
+// an ulp of 1 / d; every rank runs the same code, so the replicated draws still agree bit for bit.
+__device__ __forceinline__ double rcp_newton(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+}
+
+// `normals` (optional): e[i] = stream_normal(seed, call, rev ? P - 1 - i : i) is produced by the warps that would
+// otherwise idle while warp 0 factorises the first diagonal block.
+__device__ __forceinline__ void cta_ldl_upper(double *A, double *rd, int P, int ld, int *ok, double *normals = nullptr,
+                                              uint64_t seed = 0, uint32_t call = 0, bool rev = false)
 {
     constexpr int NB = 8;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -243,19 +259,35 @@ __device__ __forceinline__ void cta_ldl_upper(double *A, double *rd, int P, int 
         const int nb = P - k0 < NB ? P - k0 : NB;
         const int kend = k0 + nb;
         if (tid < 32) {
-            for (int j = k0; j < kend; ++j) {
-                double d = A[j + (size_t)ld * j];
-                if (!(d > 0.0)) { if (tid == 0) *ok = 0; break; }
-                double inv = 1.0 / d;
-                if (tid == 0) rd[j] = inv;
-                const int k = k0 + (tid & 7);
-                if (k > j && k < kend) {
-                    double s = A[j + (size_t)ld * k] * inv;
-                    for (int i = j + 1 + (tid >> 3); i <= k; i += 4)
-                        A[i + (size_t)ld * k] = fma(-A[j + (size_t)ld * i], s, A[i + (size_t)ld * k]);
-                }
-                __syncwarp();
+            // The 8 x 8 diagonal block lives in the warp's registers for its eight elimination steps: lane
+            // (i = lane >> 3, k = lane & 7) holds rows i and i + 4 of column k; a step broadcasts the pivot and the
+            // pivot row by shuffles (no shared-memory round trip, no warp barrier).  Rows / columns past the
+            // matrix edge act as an identity block.
+            const int i = tid >> 3, k = tid & 7;
+            double a0 = (i < nb && k < nb) ? A[(k0 + i) + (size_t)ld * (k0 + k)] : (i == k ? 1.0 : 0.0);
+            double a1 = (i + 4 < nb && k < nb) ? A[(k0 + i + 4) + (size_t)ld * (k0 + k)] : (i + 4 == k ? 1.0 : 0.0);
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int src = (j & 3) * 8;
+                const double vj = j < 4 ? a0 : a1;                       // row j as held by lanes src .. src + 7
+                const double d = __shfl_sync(0xffffffffu, vj, src + j);
+                bad = bad || !(d > 0.0);
+                const double inv = rcp_newton(d);
+                if (tid == 0 && j < nb) rd[k0 + j] = inv;
+                const double s = __shfl_sync(0xffffffffu, vj, src + k) * inv;
+                const double rji = __shfl_sync(0xffffffffu, vj, src + i);
+                const double rji4 = __shfl_sync(0xffffffffu, vj, src + i + 4);
+                if (i > j && i <= k) a0 = fma(-rji, s, a0);
+                if (i + 4 > j && i + 4 <= k) a1 = fma(-rji4, s, a1);
             }
+            if (bad) { if (tid == 0) *ok = 0; }
+            else {
+                if (i < nb && k < nb && i <= k) A[(k0 + i) + (size_t)ld * (k0 + k)] = a0;
+                if (i + 4 < nb && k < nb && i + 4 <= k) A[(k0 + i + 4) + (size_t)ld * (k0 + k)] = a1;
+            }
+        } else if (k0 == 0 && normals) {
+            for (int m = tid - 32; m < P; m += nt - 32) normals[m] = stream_normal(seed, call, rev ? P - 1 - m : m);
         }
         __syncthreads();
         if (!*ok) return;
@@ -470,11 +502,10 @@ __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, do
 #ifdef BL_BETA_CLOCKS
         long long c0 = clock64();
 #endif
-        for (int i = tid; i < P; i += blockDim.x) e[i] = stream_normal(seed, call, rev ? P - 1 - i : i);
 #ifdef BL_BETA_CLOCKS
         long long c1 = clock64();
 #endif
-        cta_ldl_upper(A, rd, P, ld, &ok);
+        cta_ldl_upper(A, rd, P, ld, &ok, e, seed, call, rev);
 #ifdef BL_BETA_CLOCKS
         long long c2 = clock64();
 #endif

@@ -139,6 +139,50 @@ def time_cpu(workload, sample, nthreads):
     return time.perf_counter() - t, O.kind
 
 
+def measured_pipe_peaks(L):
+    """Pipe throughputs of THIS device, measured now (bl_probe_peaks): the denominators of the compute roofline."""
+    import ctypes as C
+    from bayeslogit_b200 import _lib
+    b = (C.c_double * 6)()
+    _lib.check(L.bl_probe_peaks(C.cast(b, C.c_void_p)))
+    v = list(b)
+    return {"fp64_fma_tflops": v[0], "fp32_fma_tflops": v[1], "mufu_gops": v[2], "fp64_tensor_dmma_tflops": v[3],
+            "imad_wide_gops": v[4],
+            # warp instructions issued per second: the better of the mixed FFMA + IMAD kernel and the FFMA kernel
+            # (one FFMA warp instruction = 64 flop)
+            "issue_gwarp_inst": max(v[5], v[1] * 1e3 / 64.0),
+            "how": "bl_probe_peaks (bayeslogit_b200/csrc/probe_peaks.cu): 8 independent chains per thread, 2 x 1024 threads "
+                   "per SM, best of 4 launches, in this run at this run's clocks"}
+
+
+def cpu_gibbs_baseline(N, P, iters_all, iters_one):
+    """Logit::gibbs_block (Logit.hpp:402-457) restated on the host cores (oracle/gibbs_oracle.c: psi, draw_w through the
+    port sampler, the sqrt(w)-scaled Gram, both beta draws), timed on the C3 shape: all host threads (OpenMP) and one."""
+    import numpy as np
+    from oracle import loader
+    rng = np.random.default_rng(20240003)
+    X = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
+    bt = np.r_[np.abs(rng.normal(0, 0.25, P - 1)), -0.5]
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(-X @ bt))).astype(np.float64)
+    n = np.ones(N)
+    m0, P0 = np.zeros(P), 0.01 * np.eye(P)
+    cores = os.cpu_count() or 1
+    out = {"N": N, "P": P, "cores": cores, "kind": "port",
+           "what": "oracle/gibbs_oracle.c pgb_logit_gibbs = restatement of Logit::gibbs_block (the reference's model layer "
+                   "needs the absent Matrix/BLAS libraries); plain loops, OpenMP over observations"}
+    for label, constrained in (("plain_beta", False), ("reference_constrained_beta", True)):
+        loader.logit_gibbs(y, X, n, m0, P0, 1, 1, seed=1, constrained=constrained, nthreads=cores)      # warm-up
+        t = time.perf_counter()
+        loader.logit_gibbs(y, X, n, m0, P0, 1, iters_all - 1, seed=20240003, constrained=constrained, nthreads=cores)
+        dt_all = time.perf_counter() - t
+        t = time.perf_counter()
+        loader.logit_gibbs(y, X, n, m0, P0, 1, iters_one - 1, seed=20240003, constrained=constrained, nthreads=1)
+        dt_one = time.perf_counter() - t
+        out[label] = {"iters_per_sec_all_cores": iters_all / dt_all, "iters_all_cores": iters_all,
+                      "iters_per_sec_1_core": iters_one / dt_one, "iters_1_core": iters_one}
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -153,13 +197,19 @@ def run_reference(args, rank, world):
         t += dt
     value = sample * args.steps / t
     desc = f"first {sample} draws of the workload per step, all {cores} host threads (OpenMP, one RNG+sampler per thread)"
+    one = max(sample // 8, 1)
+    dt1, _ = time_cpu(args.workload, one, 1)
     print(json.dumps({
         "impl": "reference", "metric": "pg_draws_per_sec", "value": value, "unit": "draws/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "draws/s", "cores": cores, "kind": kind, "sample": desc},
+        "config": dict(workload_config(args), timed_sample_per_step=sample,
+                       note="a rate: each step draws the first timed_sample_per_step observations of the workload"),
+        "cpu_baseline": {"value": value, "unit": "draws/s", "cores": cores, "kind": kind, "sample": desc,
+                         "value_1_core": one / dt1,
+                         "sample_1_core": f"first {one} draws, one thread (the reference's shipped serial loop, "
+                                          f"LogitWrapper.cpp:129-167)"},
         "e2e": {"value": value, "unit": "draws/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -201,6 +251,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    pipe_peaks = measured_pipe_peaks(L)
     num = args.num
     obs0 = rank * num
     wl = args.workload
@@ -353,8 +404,13 @@ def main():
         sample = min(CPU_SAMPLE[wl], num)
         time_cpu(wl, max(sample // 16, 1), cores)
         dt, kind = time_cpu(wl, sample, cores)
+        one = max(sample // 8, 1)
+        dt1, _ = time_cpu(wl, one, 1)
         cpu = {"value": sample / dt, "unit": "draws/s", "cores": cores, "kind": kind,
-               "sample": f"first {sample} draws of the workload, all {cores} host threads, {dt:.2f} s wall"}
+               "sample": f"first {sample} draws of the workload, all {cores} host threads, {dt:.2f} s wall",
+               "value_1_core": one / dt1,
+               "sample_1_core": f"first {one} draws of the workload, one thread (the reference's shipped serial loop, "
+                                f"LogitWrapper.cpp:129-167), {dt1:.2f} s wall"}
 
     # ---- extras: the two other figures BASELINE.json's metric names -------------------------
     extras = {}
@@ -380,7 +436,6 @@ def main():
         extras["pg1"] = {"draws_per_sec": world * n1 / (ms1 * 1e-3), "ms_per_launch": ms1, "draws_per_gpu": n1,
                          "workload": "rpg_devroye PG(1,z), z~U(-5,5), device-resident",
                          "kernel": "k_devroye_refill",
-                         "roofline_compute_frac": world * n1 / (ms1 * 1e-3) * 0.9e3 / 1e12 / (37.0 * world),
                          "hbm_GBs": n1 * 20 / (ms1 * 1e-3) / 1e9}
         del z1, s1, x1
         torch.cuda.empty_cache()
@@ -393,6 +448,10 @@ def main():
         gp = bench_gibbs.run(1_000_000, 64, args.gibbs_iters, 5, False, rank, world, local)
         gc = bench_gibbs.run(1_000_000, 64, max(10, args.gibbs_iters // 10), 2, True, rank, world, local)
         extras["gibbs_logit_N1M_P64"] = {"plain_beta": gp, "reference_constrained_beta": gc, "scaling": "strong"}
+        go = bench_gibbs.run(1_000_000, 64, max(20, args.gibbs_iters // 4), 3, False, rank, world, local, one_pass=True)
+        extras["gibbs_logit_N1M_P64"]["plain_beta_one_pass_kernel"] = go
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            extras["gibbs_logit_N1M_P64"]["cpu_baseline"] = cpu_gibbs_baseline(1_000_000, 64, 20, 3)
         # (iii) the other sweeps of BASELINE.json's configs: NB regression (config 4), multinomial logit and the
         # batch of independent chains (config 5); short runs, figures per iteration
         import bench_chains
@@ -412,7 +471,6 @@ def main():
         except OSError:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        fp64_peak = 37.0   # TFLOP/s, B200 vector FP64 (not in MEASURED_PEAKS.json)
         counters = {}
         try:
             counters = json.load(open(os.path.join(ROOT, "profiles", "ncu_counters.json")))
@@ -427,51 +485,63 @@ def main():
             n_launch = max(1, stage_launches[dom_stage])
             dom_units, dom_ms = regime_counts["saddle_point"] / n_launch, stage_ms[dom_stage] / n_launch
             dom_share = stage_ms[dom_stage] / (total_ms / args.steps)
-            dom_kflop = 9.0
             # HBM bytes the design moves per saddle-point draw in this kernel:
             # set-up: idx 4 + h 8 + z 8 in, 19 state doubles out; loop: idx 4 + h 8 + z 8 + state in, x 8 out
             design_bytes = {"sp_setup": 20 + 152, "sp_loop": 20 + 152 + 8}[dom_stage]
         else:
-            dom_units, dom_ms, dom_name, dom_kflop = num, kern_ms, "k_devroye_refill", KFLOP_PER_DRAW[wl]
+            dom_units, dom_ms, dom_name = num, kern_ms, "k_devroye_refill"
             dom_share, n_launch, design_bytes = 1.0, 1, BYTES_PER_DRAW[wl]
-        achieved = dom_units * BYTES_PER_DRAW[wl] / (dom_ms * 1e-3) / 1e9
+        hbm_achieved = dom_units * BYTES_PER_DRAW[wl] / (dom_ms * 1e-3) / 1e9
         ctr = counters.get(dom_name, {})
         traffic = None
         if ctr.get("dram_bytes_per_unit") is not None:
             traffic = ctr["dram_bytes_per_unit"] * dom_units
-        tf_all = None
-        if stage_ms:
-            sp_ms = stage_ms["sp_setup"] + stage_ms["sp_loop"]
-            tf_all = regime_counts["saddle_point"] * dom_kflop * 1e3 / (sp_ms * 1e-3) / 1e12
+        # The binding roof.  The sampler kernels move 24 B per draw (3 % of HBM at this rate) and are bound by the
+        # SM: what they run out of is issue slots (warp instructions per second), so that is the roof quoted --
+        # achieved = the warp instructions the kernel EXECUTES per draw (ncu smsp__inst_executed.sum of the same
+        # kernel at bench size, profiles/ncu_counters.json) x draws per launch / its live CUDA-event time; peak =
+        # the issue rate measured on this device in this run.  The per-pipe shares (ncu pct of peak) follow.
+        issue_peak = pipe_peaks["issue_gwarp_inst"]
+        if ctr.get("warp_instr_per_unit"):
+            issue_achieved = ctr["warp_instr_per_unit"] * dom_units / (dom_ms * 1e-3) / 1e9
+            roofline = {"bound": "issue", "achieved": issue_achieved, "peak": issue_peak, "unit": "Gwarp-inst/s",
+                        "frac": issue_achieved / issue_peak, "traffic": traffic, "peak_source": "measured (bl_probe_peaks, this run)",
+                        "warp_inst_per_unit": ctr["warp_instr_per_unit"],
+                        "active_threads_per_warp_inst": ctr.get("active_threads_per_warp_instr"),
+                        "pipes_pct_of_peak_ncu": {k: ctr.get(k) for k in ("issue_slots_busy_pct", "fp64_pipe_pct", "fma_pipe_pct",
+                                                                            "alu_pipe_pct", "xu_pipe_pct", "lsu_pipe_pct")},
+                        "counters_source": ctr.get("source")}
         else:
-            tf_all = dom_units * dom_kflop * 1e3 / (dom_ms * 1e-3) / 1e12
+            roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": hbm_achieved / hbm_peak, "traffic": traffic,
+                        "peak_source": "measured" if peaks else "fallback",
+                        "note": "no ncu instruction counts for this kernel in profiles/ncu_counters.json: HBM roof quoted, "
+                                "which does not bind (the sampler is issue-bound)"}
+        roofline.update({
+            "kernel": dom_name, "kernel_ms": dom_ms, "launches_per_step": n_launch, "units_per_launch": dom_units,
+            "share_of_step": dom_share, "stage_ms": stage_ms, "stage_launches": stage_launches, "regime_counts": regime_counts,
+            "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                    "bytes_per_unit": BYTES_PER_DRAW[wl], "design_bytes_per_unit": design_bytes,
+                    "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                    "note": "algorithmic bytes (shape, z in; omega out) against the copy bandwidth: not the binding roof"},
+        })
+        # the PG(1,z) kernel of the extras against the same issue roof
+        if "pg1" in extras and counters.get("k_devroye_refill", {}).get("warp_instr_per_unit"):
+            c1 = counters["k_devroye_refill"]
+            rate = extras["pg1"]["draws_per_sec"] / world * c1["warp_instr_per_unit"] / 1e9
+            extras["pg1"]["roofline"] = {"bound": "issue", "achieved": rate, "peak": issue_peak, "unit": "Gwarp-inst/s",
+                                         "frac": rate / issue_peak, "warp_inst_per_unit": c1["warp_instr_per_unit"],
+                                         "active_threads_per_warp_inst": c1.get("active_threads_per_warp_instr"),
+                                         "counters_source": c1.get("source")}
         out = {
             "metric": "pg_draws_per_sec", "value": value, "unit": "draws/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic,
-                         "peak_source": "measured" if peaks else "fallback",
-                         "kernel": dom_name, "kernel_ms": dom_ms, "launches_per_step": n_launch,
-                         "units_per_launch": dom_units, "bytes_per_unit": BYTES_PER_DRAW[wl],
-                         "design_bytes_per_unit": design_bytes,
-                         "share_of_step": dom_share,
-                         "stage_ms": stage_ms, "stage_launches": stage_launches, "regime_counts": regime_counts,
-                         "note": "the sampler is bound by the issue slots / FP64 pipe, not HBM (SURVEY.md 8d): "
-                                 "see roofline_compute; traffic = ncu dram bytes per draw (profiles/ncu_counters.json) "
-                                 "x units_per_launch"},
-            "roofline_compute": {"bound": "sm issue / fp64 pipe", "kernel": dom_name,
-                                 "ncu": {k: ctr.get(k) for k in ("issue_slots_busy_pct", "fp64_pipe_pct", "alu_pipe_pct",
-                                                                  "xu_pipe_pct", "active_threads_per_warp_instr",
-                                                                  "warp_instr_per_unit", "source")} if ctr else None,
-                                 "reference_equivalent": {
-                                     "achieved": tf_all, "peak": fp64_peak, "frac": tf_all / fp64_peak,
-                                     "unit": "TFLOP/s the REFERENCE algorithm would need at this draw rate "
-                                             "(SURVEY.md 8d cost model, %.1f kFLOP/draw); the engine executes far fewer "
-                                             "(tables instead of Newton, fp32 decision filters)" % dom_kflop,
-                                     "peak_source": "nominal B200 vector FP64 (no measured FP64 peak in MEASURED_PEAKS.json)"}},
+            "roofline": roofline,
+            "peaks_measured": dict(pipe_peaks, hbm_gbs=peaks.get("hbm_gbs"), bf16_tflops=peaks.get("bf16_tflops"),
+                                   hbm_source="MEASURED_PEAKS.json (driver-written)" if peaks else "absent"),
             "cpu_baseline": cpu, "mean_omega_first_1M": mean_omega, "extras": extras,
         }
         sys.stdout.flush()
