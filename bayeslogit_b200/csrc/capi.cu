@@ -10,20 +10,135 @@
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "engine.h"
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 namespace bl {
 
 namespace {
 
 constexpr int kSlots = 3;
+
+// Large one-shot copies between pageable and pinned memory: streaming (non-temporal) stores, so the destination
+// lines are not read into the cache first -- a third less memory traffic than a cached memcpy, and the copy is
+// bound by exactly that traffic.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void copy_stream_avx2(char *d, const char *s, size_t n)
+{
+    while (n && (reinterpret_cast<uintptr_t>(d) & 31)) { *d++ = *s++; --n; }
+    for (; n >= 128; n -= 128, d += 128, s += 128) {
+        __m256i a = _mm256_loadu_si256((const __m256i *)s), b = _mm256_loadu_si256((const __m256i *)(s + 32));
+        __m256i c = _mm256_loadu_si256((const __m256i *)(s + 64)), e = _mm256_loadu_si256((const __m256i *)(s + 96));
+        _mm256_stream_si256((__m256i *)d, a);
+        _mm256_stream_si256((__m256i *)(d + 32), b);
+        _mm256_stream_si256((__m256i *)(d + 64), c);
+        _mm256_stream_si256((__m256i *)(d + 96), e);
+    }
+    _mm_sfence();
+    if (n) memcpy(d, s, n);
+}
+#endif
+
+void copy_stream(char *d, const char *s, size_t n)
+{
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2 && n >= 4096) { copy_stream_avx2(d, s, n); return; }
+#endif
+    memcpy(d, s, n);
+}
+
+// Host threads that copy between the caller's PAGEABLE buffers and the pipeline's pinned staging buffers.
+// R's .C() interface hands over ordinary (pageable) vectors (LogitWrapper.R:29,49); a cudaMemcpyAsync from
+// such memory is staged by the driver on one thread at a fraction of the link's bandwidth and blocks the
+// caller meanwhile.  Here every chunk is copied by all pool threads at once into pinned memory and goes
+// over the link as a true asynchronous DMA that overlaps the kernels of the neighbouring chunks.
+class CopyPool {
+    struct Job { char *d; const char *s; size_t n; };
+    std::vector<std::thread> threads_;
+    std::vector<Job> jobs_;
+    std::mutex mu_;
+    std::condition_variable go_, done_;
+    uint64_t generation_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+
+    void worker(int k)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                go_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+                j = jobs_[k];
+            }
+            if (j.n) copy_stream(j.d, j.s, j.n);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+
+public:
+    int size() const { return (int)threads_.size(); }
+    void start()
+    {
+        if (!threads_.empty()) return;
+        const char *env = getenv("BAYESLOGIT_COPY_THREADS");
+        int hw = (int)std::thread::hardware_concurrency();
+        int n = env ? atoi(env) : (hw > 2 ? (hw - 1 < 24 ? hw - 1 : 24) : 1);
+        if (n < 1) n = 1;
+        jobs_.resize(n);
+        for (int k = 0; k < n; ++k) threads_.emplace_back([this, k] { worker(k); });
+    }
+    // dst[0..bytes) = src[0..bytes), split into 64-byte-aligned pieces over the pool (the caller takes one too)
+    void copy(void *dst, const void *src, size_t bytes)
+    {
+        const int n = size();
+        if (n == 0 || bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+        size_t piece = ((bytes / (n + 1)) + 63) & ~(size_t)63;
+        size_t off = 0;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (int k = 0; k < n; ++k) {
+                size_t len = off < bytes ? (bytes - off < piece ? bytes - off : piece) : 0;
+                jobs_[k] = Job{(char *)dst + off, (const char *)src + off, len};
+                off += len;
+            }
+            pending_ = n;
+            ++generation_;
+        }
+        go_.notify_all();
+        if (off < bytes) copy_stream((char *)dst + off, (const char *)src + off, bytes - off);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        go_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+};
 // observations per full-size pipeline chunk.  With the ramped schedule (run_host) and 100M mixed draws:
 // 1M 1.72e9, 2M 2.71e9, 4M 2.97e9, 8M 2.89e9, 16M 2.77e9, 32M 2.39e9 draws/s end to end (PCIe bound 3.1-3.3e9):
 // smaller chunks shorten fill and drain, larger ones amortise the ~27 launches of a binned batch.
@@ -36,7 +151,14 @@ struct Slot {
     int *iter = nullptr;
     void *work = nullptr;      // regime-binning scratch (pg_hybrid.cu)
     int64_t cap = 0;
+    // pinned staging buffers for pageable callers (allocated on the first such call)
+    void *h_shape = nullptr;
+    double *h_z = nullptr, *h_x = nullptr;
+    int *h_iter = nullptr;
+    int64_t h_cap = 0;
 };
+
+constexpr int64_t kStageMin = 1 << 18;   // smaller pageable batches go through the driver's own staging
 
 constexpr int64_t kBinMin = 1 << 15;         // below this the per-lane dispatch kernel is used
 constexpr int64_t kBinMax = 1 << 30;         // observations per binned launch (int32 index lists)
@@ -48,6 +170,7 @@ struct Context {
     uint64_t seed = 0;
     uint32_t call = 0;
     Slot slot[kSlots];
+    CopyPool pool;
     std::string err;
 };
 
@@ -135,6 +258,31 @@ int slot_reserve(Slot &s, int64_t n)
     return 0;
 }
 
+int stage_reserve(Slot &s, int64_t n)
+{
+    if (n <= s.h_cap) return 0;
+    BL_CK(cudaStreamSynchronize(s.stream));
+    if (s.h_shape) cudaFreeHost(s.h_shape);
+    if (s.h_z) cudaFreeHost(s.h_z);
+    if (s.h_x) cudaFreeHost(s.h_x);
+    if (s.h_iter) cudaFreeHost(s.h_iter);
+    s.h_shape = nullptr; s.h_z = s.h_x = nullptr; s.h_iter = nullptr; s.h_cap = 0;
+    BL_CK(cudaHostAlloc(&s.h_shape, n * sizeof(double), cudaHostAllocDefault));
+    BL_CK(cudaHostAlloc((void **)&s.h_z, n * sizeof(double), cudaHostAllocDefault));
+    BL_CK(cudaHostAlloc((void **)&s.h_x, n * sizeof(double), cudaHostAllocDefault));
+    BL_CK(cudaHostAlloc((void **)&s.h_iter, n * sizeof(int), cudaHostAllocDefault));
+    s.h_cap = n;
+    return 0;
+}
+
+// true when the driver knows nothing about the pointer: ordinary malloc'ed (pageable) host memory
+bool is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 size_t shape_size(Method m)
 {
     return (m == kDevroye || m == kDevroyePlain || m == kDevroyeLoop) ? sizeof(int) : sizeof(double);
@@ -191,13 +339,46 @@ int run_host(Method m, double *x, const void *shape, const double *z, int64_t nu
     for (int s = 0; s < kSlots && s < nchunks; ++s)
         if (slot_reserve(g.slot[s], num < kChunk ? num : kChunk)) return 1;
     size_t ss = shape_size(m);
-    int64_t off = 0;
-    for (int64_t c = 0; c < nchunks; off += sizes[c], ++c) {
+    // Pageable caller buffers (what R's .C() passes): stage every chunk through pinned memory with the copy pool.
+    // BAYESLOGIT_NO_STAGING=1 keeps the driver's own staging (measurement aid).
+    const bool staged = num >= kStageMin && !getenv("BAYESLOGIT_NO_STAGING") &&
+                        (is_pageable(x) || is_pageable(shape) || is_pageable(z));
+    if (staged) {
+        g.pool.start();
+        for (int s = 0; s < kSlots && s < nchunks; ++s)
+            if (stage_reserve(g.slot[s], num < kChunk ? num : kChunk)) return 1;
+    }
+    std::vector<int64_t> offs(nchunks);
+    {
+        int64_t o = 0;
+        for (int64_t c = 0; c < nchunks; ++c) { offs[c] = o; o += sizes[c]; }
+    }
+    // results of chunk c leave the staging buffer once its stream has drained (its slot is reused by chunk c + kSlots)
+    auto stage_out = [&](int64_t c) -> int {
         Slot &s = g.slot[c % kSlots];
-        const int64_t n = sizes[c];
-        BL_CK(cudaMemcpyAsync(s.shape, (const char *)shape + off * ss, n * ss, cudaMemcpyHostToDevice, s.stream));
-        BL_CK(cudaMemcpyAsync(s.z, z + off, n * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-        if (iter) BL_CK(cudaMemcpyAsync(s.iter, iter + off, n * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+        BL_CK(cudaStreamSynchronize(s.stream));
+        g.pool.copy(x + offs[c], s.h_x, sizes[c] * sizeof(double));
+        if (iter) g.pool.copy(iter + offs[c], s.h_iter, sizes[c] * sizeof(int));
+        return 0;
+    };
+    for (int64_t c = 0; c < nchunks; ++c) {
+        Slot &s = g.slot[c % kSlots];
+        const int64_t n = sizes[c], off = offs[c];
+        const void *src_shape = (const char *)shape + off * ss;
+        const double *src_z = z + off;
+        const int *src_iter = iter ? iter + off : nullptr;
+        double *dst_x = x + off;
+        int *dst_iter = iter ? iter + off : nullptr;
+        if (staged) {
+            if (c >= kSlots && stage_out(c - kSlots)) return 1;
+            g.pool.copy(s.h_shape, src_shape, n * ss);
+            g.pool.copy(s.h_z, src_z, n * sizeof(double));
+            if (iter) g.pool.copy(s.h_iter, src_iter, n * sizeof(int));
+            src_shape = s.h_shape; src_z = s.h_z; src_iter = s.h_iter; dst_x = s.h_x; dst_iter = s.h_iter;
+        }
+        BL_CK(cudaMemcpyAsync(s.shape, src_shape, n * ss, cudaMemcpyHostToDevice, s.stream));
+        BL_CK(cudaMemcpyAsync(s.z, src_z, n * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        if (iter) BL_CK(cudaMemcpyAsync(s.iter, src_iter, n * sizeof(int), cudaMemcpyHostToDevice, s.stream));
         StreamId cid = id;
         cid.obs0 += (uint64_t)off;
         if (m == kHybrid && n >= kBinMin)
@@ -206,10 +387,15 @@ int run_host(Method m, double *x, const void *shape, const double *z, int64_t nu
             BL_CK(launch_devroye_refill(s.x, (const int *)s.shape, s.z, n, cid, s.stream, s.work));
         else
             BL_CK(launch_rpg(m, s.x, s.shape, s.z, n, trunc, iter ? s.iter : nullptr, cid, s.stream));
-        BL_CK(cudaMemcpyAsync(x + off, s.x, n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-        if (iter) BL_CK(cudaMemcpyAsync(iter + off, s.iter, n * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        BL_CK(cudaMemcpyAsync(dst_x, s.x, n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (iter) BL_CK(cudaMemcpyAsync(dst_iter, s.iter, n * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     }
-    for (int s = 0; s < kSlots && s < nchunks; ++s) BL_CK(cudaStreamSynchronize(g.slot[s].stream));
+    if (staged) {
+        for (int64_t c = nchunks > kSlots ? nchunks - kSlots : 0; c < nchunks; ++c)
+            if (stage_out(c)) return 1;
+    } else {
+        for (int s = 0; s < kSlots && s < nchunks; ++s) BL_CK(cudaStreamSynchronize(g.slot[s].stream));
+    }
     return 0;
 }
 

@@ -389,7 +389,33 @@ def main():
         torch.cuda.synchronize()
         h2d_gbs = 3 * probe.numel() * 8 / (time.perf_counter() - tp0) / 1e9
         del probe, probe_d, probe_o, probe_do
-        e2e = {"value": world * num * e_steps / dt, "unit": "draws/s",
+        # the same call with PAGEABLE caller buffers -- what R's .C() hands over (LogitWrapper.R:29,49): the library stages
+        # the chunks through its own pinned ring with a pool of copy threads; and, for reference, with that switched
+        # off (the driver's own single-threaded staging)
+        x_pg = np.zeros(num)
+        pageable = {}
+        for label, env in (("staged_by_library", None), ("driver_staging", "1")):
+            if env:
+                os.environ["BAYESLOGIT_NO_STAGING"] = env
+            else:
+                os.environ.pop("BAYESLOGIT_NO_STAGING", None)
+            _lib.check(fn_host(x_pg.ctypes.data, shape_h.ctypes.data, z_h.ctypes.data, num, SEED, 2100, obs0))
+            barrier()
+            tq = time.perf_counter()
+            for k in range(2):
+                _lib.check(fn_host(x_pg.ctypes.data, shape_h.ctypes.data, z_h.ctypes.data, num, SEED, k, obs0))
+            pageable[label] = world * num * 2 / max_over_ranks(time.perf_counter() - tq)
+        os.environ.pop("BAYESLOGIT_NO_STAGING", None)
+        fn_host(x_pg.ctypes.data, shape_h.ctypes.data, z_h.ctypes.data, num, SEED, 0, obs0)
+        same_pg = bool(np.array_equal(x_pg[: 1 << 20], x_p[: 1 << 20].numpy()))
+        del x_pg
+        e2e = {"value": world * num * e_steps / dt, "unit": "draws/s", "host_memory": "pinned",
+               "pageable": {"value": pageable["staged_by_library"], "unit": "draws/s",
+                            "frac_of_pinned": pageable["staged_by_library"] / (world * num * e_steps / dt),
+                            "driver_staging_value": pageable["driver_staging"],
+                            "how": "numpy (malloc) buffers; chunks staged through the library's pinned ring by its copy threads "
+                                   "(capi.cu CopyPool); driver_staging_value: the same call with BAYESLOGIT_NO_STAGING=1",
+                            "matches_pinned": same_pg},
                "h2d_GBs_measured_with_d2h_busy": h2d_gbs,
                "pcie_bound_draws_per_s": world * h2d_gbs * 1e9 / (BYTES_PER_DRAW[wl] - 8),
                "h2d_bytes_per_step": int(world * num * (BYTES_PER_DRAW[wl] - 8)),
