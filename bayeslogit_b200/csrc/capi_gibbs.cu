@@ -122,24 +122,25 @@ uint64_t dropin_seed()
 
 int host_logit(double *w, double *beta, const double *y, const double *tX, const double *n,
                const double *m0, const double *P0, int N, int P, int samp, int burn, uint64_t seed,
-               int flags)
+               int flags, int w_every = 1)
 {
     if (bl_ensure_ready_internal()) return 1;
-    if (N <= 0 || P <= 0 || samp <= 0 || burn < 0) return report("gibbs: bad dimensions", "Aborting Gibbs sampler.");
+    if (N <= 0 || P <= 0 || samp <= 0 || burn < 0 || w_every < 1) return report("gibbs: bad dimensions", "Aborting Gibbs sampler.");
+    const size_t wslots = ((size_t)samp + w_every - 1) / w_every;
     std::string err;
     Dev d;
     double *dy = d.put(y, N, err), *dX = d.put(tX, (size_t)N * P, err), *dn = d.put(n, N, err);
     double *dm0 = d.put(m0, P, err), *dP0 = d.put(P0, (size_t)P * P, err);
     bool keep_w = w && !(flags & BL_GIBBS_NO_W);
-    double *dw = keep_w ? d.put(nullptr, (size_t)N * samp, err) : nullptr;
+    double *dw = keep_w ? d.put(nullptr, (size_t)N * wslots, err) : nullptr;
     double *dbeta = d.put(nullptr, (size_t)P * samp, err);
     if (!err.empty()) return report(err, "Aborting Gibbs sampler.");
     cudaStream_t st = (cudaStream_t)bl_stream_internal();
     if (logit_gibbs_device(dw, dbeta, dy, dX, dn, dm0, dP0, N, P, samp, burn, seed,
-                           keep_w ? flags : (flags | BL_GIBBS_NO_W), 0, false, st, err))
+                           keep_w ? flags : (flags | BL_GIBBS_NO_W), 0, false, st, err, w_every))
         return report(err, "Aborting Gibbs sampler.");
     cudaError_t e = cudaMemcpy(beta, dbeta, sizeof(double) * (size_t)P * samp, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && keep_w) e = cudaMemcpy(w, dw, sizeof(double) * (size_t)N * samp, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && keep_w) e = cudaMemcpy(w, dw, sizeof(double) * (size_t)N * wslots, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return report(cudaGetErrorString(e), "Aborting Gibbs sampler.");
     return 0;
 }
@@ -243,6 +244,19 @@ int bl_logit_gibbs(double *w, double *beta, const double *y, const double *tX, c
     return host_logit(w, beta, y, tX, n, m0, P0, N, P, samp, burn, seed, flags);
 }
 
+int bl_logit_gibbs_thin(double *w, double *beta, const double *y, const double *tX, const double *n,
+                        const double *m0, const double *P0, int N, int P, int samp, int burn,
+                        uint64_t seed, int flags, int w_every)
+{
+    return host_logit(w, beta, y, tX, n, m0, P0, N, P, samp, burn, seed, flags, w_every);
+}
+
+// R-side seeding shim: .C("bl_set_seed_r", as.integer(seed)) next to set.seed(seed)
+void bl_set_seed_r(int *seed)
+{
+    if (seed) bl_set_seed((uint64_t)(uint32_t)*seed);
+}
+
 int bl_mlogit_gibbs(double *w, double *beta, const double *ty, const double *tX, const double *n,
                     const double *m0, const double *P0, int N, int P, int J, int samp, int burn,
                     uint64_t seed, int flags)
@@ -268,8 +282,8 @@ int bl_nb_gibbs(double *w_last, double *beta, const double *y, const double *tX,
     return 0;
 }
 
-int bl_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
-                   const double *m0, const double *P0, int N, int P, int samp, int burn, uint64_t seed)
+static int host_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
+                            const double *m0, const double *P0, int N, int P, int samp, int burn, uint64_t seed, int real_d)
 {
     if (bl_ensure_ready_internal()) return 1;
     std::string err;
@@ -279,7 +293,7 @@ int bl_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y,
     double *dw = dv.put(nullptr, N, err), *dbeta = dv.put(nullptr, (size_t)P * samp, err);
     double *dd = dv.put(nullptr, samp, err);
     if (!err.empty()) return report(err, "Aborting Gibbs sampler.");
-    if (nb_gibbs_df_device(dw, dbeta, dd, dy, dX, d0, dm0, dP0, N, P, samp, burn, seed, 0, false,
+    if (nb_gibbs_df_device(dw, dbeta, dd, dy, dX, d0, dm0, dP0, N, P, samp, burn, seed, 0, false, real_d,
                            (cudaStream_t)bl_stream_internal(), err))
         return report(err, "Aborting Gibbs sampler.");
     cudaError_t e = cudaMemcpy(beta, dbeta, sizeof(double) * (size_t)P * samp, cudaMemcpyDeviceToHost);
@@ -289,13 +303,36 @@ int bl_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y,
     return 0;
 }
 
+int bl_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
+                   const double *m0, const double *P0, int N, int P, int samp, int burn, uint64_t seed)
+{
+    return host_nb_gibbs_df(w_last, beta, d_out, y, tX, d0, m0, P0, N, P, samp, burn, seed, 0);
+}
+
+int bl_nb_gibbs_dfreal(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
+                       const double *m0, const double *P0, int N, int P, int samp, int burn, uint64_t seed)
+{
+    return host_nb_gibbs_df(w_last, beta, d_out, y, tX, d0, m0, P0, N, P, samp, burn, seed, 1);
+}
+
+int bl_nb_gibbs_dfreal_dev(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
+                           const double *m0, const double *P0, int64_t N, int P, int samp, int burn, uint64_t seed,
+                           uint64_t obs0, void *stream)
+{
+    if (bl_ensure_ready_internal()) return 1;
+    std::string err;
+    if (nb_gibbs_df_device(w_last, beta, d_out, y, tX, d0, m0, P0, N, P, samp, burn, seed, obs0, true, 1, (cudaStream_t)stream, err))
+        return report(err, nullptr);
+    return 0;
+}
+
 int bl_nb_gibbs_df_dev(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
                        const double *m0, const double *P0, int64_t N, int P, int samp, int burn, uint64_t seed,
                        uint64_t obs0, void *stream)
 {
     if (bl_ensure_ready_internal()) return 1;
     std::string err;
-    if (nb_gibbs_df_device(w_last, beta, d_out, y, tX, d0, m0, P0, N, P, samp, burn, seed, obs0, true, (cudaStream_t)stream, err))
+    if (nb_gibbs_df_device(w_last, beta, d_out, y, tX, d0, m0, P0, N, P, samp, burn, seed, obs0, true, 0, (cudaStream_t)stream, err))
         return report(err, nullptr);
     return 0;
 }

@@ -67,7 +67,7 @@ cudaError_t launch_hybrid_binned(double *x, const double *h, const double *z, in
 int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const double *tX,
                        const double *n, const double *m0, const double *P0, int64_t N, int P,
                        int samp, int burn, uint64_t seed, int flags, uint64_t obs0, bool sharded,
-                       cudaStream_t st, std::string &err);
+                       cudaStream_t st, std::string &err, int w_every = 1);   // w_out: N x ceil(samp / w_every)
 int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const double *tX,
                         const double *n, const double *m0, const double *P0, int64_t N, int P, int J,
                         int samp, int burn, uint64_t seed, int flags, uint64_t obs0, bool sharded,
@@ -77,7 +77,7 @@ int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const doub
                     uint64_t obs0, bool sharded, cudaStream_t st, std::string &err);
 int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const double *y, const double *tX,
                        double d0, const double *m0, const double *P0, int64_t N, int P, int samp, int burn,
-                       uint64_t seed, uint64_t obs0, bool sharded, cudaStream_t st, std::string &err);
+                       uint64_t seed, uint64_t obs0, bool sharded, int real_d, cudaStream_t st, std::string &err);
 int logit_chains_device(double *beta_out, const double *y, const double *tX, const double *n,
                         const double *m0, const double *P0, int chains, int64_t N, int P, int samp, int burn,
                         uint64_t seed, int flags, cudaStream_t st, std::string &err);

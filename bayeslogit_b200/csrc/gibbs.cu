@@ -533,9 +533,9 @@ struct Sweep {
 int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const double *tX,
                        const double *n, const double *m0, const double *P0, int64_t N, int P,
                        int samp, int burn, uint64_t seed, int flags, uint64_t obs0, bool sharded,
-                       cudaStream_t st, std::string &err)
+                       cudaStream_t st, std::string &err, int w_every)
 {
-    if (N <= 0 || P <= 0 || samp <= 0 || burn < 0) { err = "gibbs: bad dimensions"; return 1; }
+    if (N <= 0 || P <= 0 || samp <= 0 || burn < 0 || w_every < 1) { err = "gibbs: bad dimensions"; return 1; }
     DevMem mem;
     mem.st = st;
     Sweep s;
@@ -569,7 +569,7 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
     count_launch();
 
     GB_CK(cudaMemsetAsync(beta_out, 0, sizeof(double) * (size_t)P * samp, st));
-    if (keep_w) GB_CK(cudaMemsetAsync(w_out, 0, sizeof(double) * (size_t)N * samp, st));
+    if (keep_w) GB_CK(cudaMemsetAsync(w_out, 0, sizeof(double) * (size_t)N * ((samp + w_every - 1) / w_every), st));
     const bool timing = getenv("BL_GIBBS_TIMING") != nullptr;
     cudaEvent_t ev[6];
     if (timing) for (auto &x : ev) cudaEventCreate(&x);
@@ -577,11 +577,14 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
     for (int phase = 0; phase < 2; ++phase) {
         int iters = phase == 0 ? burn : samp;
         double *bcur = beta_out, *bprev = beta_out;
-        double *wcur = keep_w ? w_out : s.w;
         const double *bpsi = bcur;                                    // the beta the next omega draw conditions on
         if (!fused && !one_pass) s.xbeta(s.psi, bcur, nullptr, 0.0);
         for (int m = 1; m <= iters; ++m, ++t) {
             const bool tm = timing && phase == 1 && m == iters;       // BL_GIBBS_TIMING=1: stage times
+            // omega of sampling iteration m goes to slot m - 1 (Logit.hpp:402-457; burn-in overwrites slot 0); with
+            // thinning only every w_every-th iteration is kept, in slot (m - 1) / w_every, the others stay in scratch
+            double *wcur = !keep_w ? s.w : phase == 0 ? w_out
+                           : ((m - 1) % w_every == 0 ? w_out + (size_t)N * ((m - 1) / w_every) : s.w);
             if (tm) cudaEventRecord(ev[0], st);
             if (one_pass) {
                 PeerPush px{};
@@ -617,7 +620,7 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
             }
             if (phase == 1) {
                 bprev = bcur;
-                if (m < iters) { bcur += P; if (keep_w) wcur += N; }
+                if (m < iters) bcur += P;
             }
         }
     }
@@ -896,10 +899,11 @@ int nb_gibbs_device(double *w_out, double *beta_out, const double *y, const doub
 // ------------------------------------------------------------------------------------
 int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const double *y, const double *tX,
                        double d0, const double *m0, const double *P0, int64_t N, int P, int samp, int burn,
-                       uint64_t seed, uint64_t obs0, bool sharded_arg, cudaStream_t st, std::string &err)
+                       uint64_t seed, uint64_t obs0, bool sharded_arg, int real_d, cudaStream_t st, std::string &err)
 {
-    if (N <= 0 || P <= 0 || samp <= 0 || burn < 0 || !(d0 >= 1.0) || d0 != floor(d0)) {
-        err = "nb_gibbs_df: bad arguments (d0 must be a positive integer)";
+    if (N <= 0 || P <= 0 || samp <= 0 || burn < 0 || (real_d ? !(d0 > 0.0) : (!(d0 >= 1.0) || d0 != floor(d0)))) {
+        err = real_d ? "nb_gibbs_dfreal: bad arguments (d0 must be positive)"
+                     : "nb_gibbs_df: bad arguments (d0 must be a positive integer)";
         return 1;
     }
     const bool sharded = sharded_arg && cs().world > 1;
@@ -947,14 +951,19 @@ int nb_gibbs_df_device(double *w_out, double *beta_out, double *d_out, const dou
         const double *bprev = bcur + (size_t)P * (t & 1);
         double *bnext = t >= burn ? beta_out + (size_t)P * (t - burn) : bcur + (size_t)P * ((t + 1) & 1);
         s.xbeta(s.psi, bprev, nullptr, 0.0);                                   // phi = X beta
-        k_nb_df_partial<<<nblk, 256, 0, st>>>(dfpart, s.psi, y, dpair, N, seed, (uint32_t)t);
+        if (real_d) k_nb_dfreal_partial<<<nblk, 256, 0, st>>>(dfpart, s.psi, y, dpair, N, seed, (uint32_t)t);
+        else k_nb_df_partial<<<nblk, 256, 0, st>>>(dfpart, s.psi, y, dpair, N, seed, (uint32_t)t);
         if (sharded) {
             k_nb_df_fold<<<1, 32, 0, st>>>(dfsum, dfpart, nblk);
             count_launch();
             if (small_allreduce(dfsum, 4, kOpSumF64, s.status, st, err)) return 1;
         }
-        k_nb_df_decide<<<1, 32, 0, st>>>(dpair, dpair + 1, t >= burn ? d_out + (t - burn) : nullptr,
-                                         sharded ? dfsum : dfpart, sharded ? 1 : nblk, G, ymax, seed, (uint32_t)t);
+        if (real_d)
+            k_nb_dfreal_decide<<<1, 32, 0, st>>>(dpair, dpair + 1, t >= burn ? d_out + (t - burn) : nullptr,
+                                                 sharded ? dfsum : dfpart, sharded ? 1 : nblk, seed, (uint32_t)t);
+        else
+            k_nb_df_decide<<<1, 32, 0, st>>>(dpair, dpair + 1, t >= burn ? d_out + (t - burn) : nullptr,
+                                             sharded ? dfsum : dfpart, sharded ? 1 : nblk, G, ymax, seed, (uint32_t)t);
         k_nb_prepare<<<cdiv(N, 256), 256, 0, st>>>(s.psi, shape, kappa, y, dpair, dpair + 1, N);
         count_launch(3);
         StreamId id{seed, obs0, (uint32_t)t};

@@ -1080,6 +1080,67 @@ static __global__ void k_nb_df_decide(double *__restrict__ dptr, double *__restr
     }
 }
 
+// draw.df.real.mean (NB-Shape.R:86-96; the alternative at NBPG-logmean.R:87): random walk on the reals,
+// rstar ~ U(r - 1, r + 1) (U(0, 2) when r <= 1), target sum_i dnbinom(y_i, size r, prob mu_i / (mu_i + r), log) as
+// written there; log density restated as lgamma(y + r) - lgamma(r) - lgamma(y + 1) + r log p + y log(1 - p).
+// Same stream as draw.df: first uniform the proposal, second the one of lu = log(runif(1)).
+__device__ __forceinline__ double nb_dfreal_proposal(double r, uint64_t seed, uint32_t call, double *lu)
+{
+    PhiloxSource s;
+    s.open(seed, kDfObs, call);
+    const double u = s.unif();
+    const double rs = r > 1.0 ? (r - 1.0) + 2.0 * u : 2.0 * u;
+    if (lu) *lu = log(s.unif());
+    return rs;
+}
+
+// part[b] = {sum_i t_i(r), 0, sum_i t_i(rstar), 0} over the CTA's rows (the four-slot layout of k_nb_df_partial)
+static __global__ void __launch_bounds__(256)
+k_nb_dfreal_partial(double *__restrict__ part, const double *__restrict__ phi, const double *__restrict__ y,
+                    const double *__restrict__ dptr, int64_t N, uint64_t seed, uint32_t call)
+{
+    __shared__ double red[8][2];
+    const double r = *dptr, rs = nb_dfreal_proposal(r, seed, call, nullptr);
+    const double lgr = lgamma(r), lgs = lgamma(rs), lr = log(r), ls = log(rs);
+    double s0 = 0.0, s1 = 0.0;
+    const int64_t slab = (N + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * slab, r1 = r0 + slab < N ? r0 + slab : N;
+    for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+        const double ph = phi[i], mu = exp(ph), yi = y[i], lgy = lgamma(yi + 1.0);
+        const double l0 = log(mu + r), l1 = log(mu + rs);
+        s0 += lgamma(yi + r) - lgr - lgy + r * (ph - l0) + yi * (lr - l0);
+        s1 += lgamma(yi + rs) - lgs - lgy + rs * (ph - l1) + yi * (ls - l1);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 16; o; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    if (lane == 0) { red[warp][0] = s0; red[warp][1] = s1; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double v = 0.0;
+        if ((threadIdx.x & 1) == 0)
+            for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x >> 1];
+        part[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+    }
+}
+
+static __global__ void k_nb_dfreal_decide(double *__restrict__ dptr, double *__restrict__ ldptr, double *__restrict__ d_rec,
+                                          const double *__restrict__ part, int nblk, uint64_t seed, uint32_t call)
+{
+    const int lane = threadIdx.x;
+    const double r = *dptr;
+    double lu;
+    const double rs = nb_dfreal_proposal(r, seed, call, &lu);
+    double s0 = 0.0, s1 = 0.0;
+    for (int b = lane; b < nblk; b += 32) { s0 += part[(size_t)b * 4]; s1 += part[(size_t)b * 4 + 2]; }
+    for (int o = 16; o; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    if (lane == 0) {
+        const double dn = lu < s1 - s0 ? rs : r;
+        *dptr = dn;
+        *ldptr = log(dn);
+        if (d_rec) *d_rec = dn;
+    }
+}
+
 // psi <- phi - log d, shape <- y + d, kappa <- (y - d)/2 with d from device memory (NBPG-logmean.R:88-94)
 static __global__ void k_nb_prepare(double *__restrict__ psi, double *__restrict__ shape, double *__restrict__ kappa,
                              const double *__restrict__ y, const double *__restrict__ dptr,

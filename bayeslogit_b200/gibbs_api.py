@@ -182,17 +182,18 @@ def mlogit(y, X, n=None, m0=None, P0=None, samp=1000, burn=500):
 # row-major-transposed arrays are handled here so tests read naturally)
 # ---------------------------------------------------------------------------------
 
-def logit_gibbs(y, X, n, m0, P0, samp, burn, seed, flags=0, keep_w=True):
-    """Chain with an explicit seed.  Returns (w [samp x N] or None, beta [samp x P])."""
+def logit_gibbs(y, X, n, m0, P0, samp, burn, seed, flags=0, keep_w=True, w_every=1):
+    """Chain with an explicit seed.  Returns (w [ceil(samp / w_every) x N] or None, beta [samp x P]); w_every > 1
+    thins the omega chain (row k = sampling iteration k * w_every + 1)."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     N, P = X.shape
     y, n, m0 = _f(y).ravel(), _f(n).ravel(), _f(m0).ravel()
     P0c = np.asfortranarray(_f(P0))
     beta = np.zeros((samp, P))
-    w = np.zeros((samp, N)) if keep_w else None
-    st = _lib.lib().bl_logit_gibbs(_p(w) if keep_w else None, _p(beta), _p(y), _p(X), _p(n), _p(m0),
-                                   P0c.ctypes.data, N, P, samp, burn, int(seed),
-                                   int(flags) | (0 if keep_w else NO_W))
+    w = np.zeros(((samp + w_every - 1) // w_every, N)) if keep_w else None
+    st = _lib.lib().bl_logit_gibbs_thin(_p(w) if keep_w else None, _p(beta), _p(y), _p(X), _p(n), _p(m0),
+                                        P0c.ctypes.data, N, P, samp, burn, int(seed),
+                                        int(flags) | (0 if keep_w else NO_W), int(w_every))
     _lib.check(st)
     return w, beta
 
@@ -245,9 +246,9 @@ def nb_gibbs(y, X, d, m0, P0, samp, seed):
     return w, beta
 
 
-def nb_gibbs_df(y, X, m0, P0, samp, burn, seed, d0=1.0):
-    """NB regression with the dispersion sampled (NB.PG.gibbs, NBPG-logmean.R:36-113).
-    Returns (w_last [N], beta [samp x P], d [samp])."""
+def nb_gibbs_df(y, X, m0, P0, samp, burn, seed, d0=1.0, real_d=False):
+    """NB regression with the dispersion sampled (NB.PG.gibbs, NBPG-logmean.R:36-113): draw.df on the integers, or
+    (real_d) draw.df.real.mean on the reals (NB-Shape.R:86-96).  Returns (w_last [N], beta [samp x P], d [samp])."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     N, P = X.shape
     y, m0 = _f(y).ravel(), _f(m0).ravel()
@@ -255,8 +256,8 @@ def nb_gibbs_df(y, X, m0, P0, samp, burn, seed, d0=1.0):
     beta = np.zeros((samp, P))
     d = np.zeros(samp)
     w = np.zeros(N)
-    st = _lib.lib().bl_nb_gibbs_df(_p(w), _p(beta), _p(d), _p(y), _p(X), float(d0), _p(m0), P0c.ctypes.data,
-                                   N, P, samp, burn, int(seed))
+    fn = _lib.lib().bl_nb_gibbs_dfreal if real_d else _lib.lib().bl_nb_gibbs_df
+    st = fn(_p(w), _p(beta), _p(d), _p(y), _p(X), float(d0), _p(m0), P0c.ctypes.data, N, P, samp, burn, int(seed))
     _lib.check(st)
     return w, beta, d
 

@@ -92,6 +92,9 @@ int bl_get_device(void);
  * calls is reproducible. */
 void bl_set_seed(uint64_t seed);
 uint64_t bl_get_seed(void);
+/* The same through R's .C() convention (an int vector of length 1): the shim an R front end calls next to
+ * set.seed(), see INTEGRATION.md. */
+void bl_set_seed_r(int *seed);
 uint32_t bl_get_call_counter(void);
 
 /* Device-resident batch draws: all pointers are DEVICE pointers; the work is
@@ -172,6 +175,13 @@ int bl_rpg_hybrid_tape(double *x, const double *h, const double *z, int64_t num,
 int bl_logit_gibbs(double *w, double *beta, const double *y, const double *tX, const double *n,
                    const double *m0, const double *P0, int N, int P, int samp, int burn,
                    uint64_t seed, int flags);
+/* The same with the omega chain thinned: omega of sampling iteration m (1-based) is returned only when
+ * (m - 1) % w_every == 0, in slot (m - 1) / w_every; w: N x ceil(samp / w_every) (beta: every iteration, P x samp).
+ * `gibbs` returns N x samp doubles of omega -- 40 GB at N = 1M, samp = 5000 (LogitWrapper.cpp:207-221); a caller
+ * that wants beta and an occasional omega asks for w_every = 100, or passes BL_GIBBS_NO_W. */
+int bl_logit_gibbs_thin(double *w, double *beta, const double *y, const double *tX, const double *n,
+                        const double *m0, const double *P0, int N, int P, int samp, int burn,
+                        uint64_t seed, int flags, int w_every);
 /* `mult_gibbs` with an explicit seed (no duplicate-row merge: call mult_combine first). */
 int bl_mlogit_gibbs(double *w, double *beta, const double *ty, const double *tX, const double *n,
                     const double *m0, const double *P0, int N, int P, int J, int samp, int burn,
@@ -187,6 +197,16 @@ int bl_nb_gibbs(double *w_last, double *beta, const double *y, const double *tX,
  * d_out: samp; w_last: N (omega of the last iteration) or NULL. */
 int bl_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
                    const double *m0, const double *P0, int N, int P, int samp, int burn, uint64_t seed);
+
+/* ... with the real-valued random walk draw.df.real.mean (Code/R/NB-Shape.R:86-96, the alternative the reference
+ * keeps commented out at NBPG-logmean.R:87): rstar ~ U(d - 1, d + 1) (U(0, 2) for d <= 1), target
+ * sum_i dnbinom(y_i, d, mu_i / (mu_i + d), log = TRUE) as written there; b = y + d is then non-integer, so omega comes
+ * from the alternate / saddle-point samplers.  d0 > 0. */
+int bl_nb_gibbs_dfreal(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
+                       const double *m0, const double *P0, int N, int P, int samp, int burn, uint64_t seed);
+int bl_nb_gibbs_dfreal_dev(double *w_last, double *beta, double *d_out, const double *y, const double *tX, double d0,
+                           const double *m0, const double *P0, int64_t N, int P, int samp, int burn, uint64_t seed,
+                           uint64_t obs0, void *stream);
 
 /* Device-resident shards (all pointers DEVICE pointers; one process per GPU).  Rank r holds
  * observations [obs0, obs0+N) of the global data set; with a communicator (bl_comm_init) the

@@ -6,7 +6,9 @@
  *                           (driver: LogitWrapper.cpp:176-234)
  *   multinomial logit       /root/reference/Code/C/MultLogit.hpp:214-219, 234-372,
  *                           include/Normal.hpp:98-131 (driver: LogitWrapper.cpp:316-374)
- *   negative binomial       /root/reference/Code/R/NBPG-logmean.R:13-113 (beta | omega, d fixed)
+ *   negative binomial       /root/reference/Code/R/NBPG-logmean.R:13-113 (beta | omega, d fixed or sampled:
+ *                           draw.df / draw.df.real.mean, Code/R/NB-Shape.R:9-96)
+ *   posterior mode by EM    /root/reference/Code/C/Logit.hpp:488-554
  * The reference's own model layer cannot be compiled here (it needs the absent
  * jwindle/Matrix library + BLAS/LAPACK), so dense algebra is
  * written as plain loops with the LAPACK semantics the reference calls
@@ -465,9 +467,26 @@ static double df_llh(const double *y, double d, const double *phi, const double 
     return llh1 + d * s2 + s3;
 }
 
-int pgb_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y, const double *tX,
-                    double d0, const double *m0, const double *P0, int N, int P, int samp, int burn,
-                    uint64_t seed, int nthreads)
+/* draw.df.real.mean, NB-Shape.R:86-96 (the commented-out alternative at NBPG-logmean.R:87): random walk on
+ * the reals, rstar ~ U(r - 1, r + 1) (U(0, 2) when r <= 1), target sum_i dnbinom(y_i, size r, prob mu_i / (mu_i + r),
+ * log = TRUE) exactly as written there.  dnbinom's log density is restated as
+ *   lgamma(y + r) - lgamma(r) - lgamma(y + 1) + r log p + y log(1 - p),   log p = phi - log(mu + r),
+ *   log(1 - p) = log r - log(mu + r)
+ * (R evaluates it through dbinom_raw; same function, different rounding).  Variates: the proposal's uniform, then
+ * the uniform of lu = log(runif(1)), both from the stream (seed, obs 2^64-2, call j). */
+static double dfreal_ll(const double *y, double r, const double *phi, int N)
+{
+    double s = 0.0, lgr = lgamma(r), lr = log(r);
+    for (int i = 0; i < N; ++i) {
+        double lmr = log(exp(phi[i]) + r);
+        s += lgamma(y[i] + r) - lgr - lgamma(y[i] + 1.0) + r * (phi[i] - lmr) + y[i] * (lr - lmr);
+    }
+    return s;
+}
+
+static int nb_gibbs_df_impl(double *w_last, double *beta, double *d_out, const double *y, const double *tX,
+                            double d0, const double *m0, const double *P0, int N, int P, int samp, int burn,
+                            uint64_t seed, int nthreads, int real_d)
 {
 #ifdef _OPENMP
     if (nthreads <= 0) nthreads = omp_get_max_threads();
@@ -490,7 +509,14 @@ int pgb_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y
     int status = 0;
     for (int t = 0; t < samp + burn && !status; ++t) {
         xbeta(phi, tX, bcur, N, P, nthreads);
-        {   /* draw.df */
+        if (real_d) {   /* draw.df.real.mean */
+            pgo_src sd;
+            pgo_src_philox(&sd, seed, DF_OBS, (uint32_t)t);
+            double u = pgo_unif(&sd);
+            double rstar = d > 1.0 ? (d - 1.0) + 2.0 * u : 2.0 * u;
+            double lalpha = dfreal_ll(y, rstar, phi, N) - dfreal_ll(y, d, phi, N);
+            if (log(pgo_unif(&sd)) < lalpha) d = rstar;
+        } else {   /* draw.df */
             pgo_src sd;
             pgo_src_philox(&sd, seed, DF_OBS, (uint32_t)t);
             double lower = d - 1.0 > 1.0 ? d - 1.0 : 1.0;
@@ -525,5 +551,70 @@ int pgb_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y
     }
     free(G); free(b0); free(PP); free(bP); free(phi); free(bcur);
     return status;
+}
+
+int pgb_nb_gibbs_df(double *w_last, double *beta, double *d_out, const double *y, const double *tX,
+                    double d0, const double *m0, const double *P0, int N, int P, int samp, int burn,
+                    uint64_t seed, int nthreads)
+{
+    return nb_gibbs_df_impl(w_last, beta, d_out, y, tX, d0, m0, P0, N, P, samp, burn, seed, nthreads, 0);
+}
+
+int pgb_nb_gibbs_dfreal(double *w_last, double *beta, double *d_out, const double *y, const double *tX,
+                        double d0, const double *m0, const double *P0, int N, int P, int samp, int burn,
+                        uint64_t seed, int nthreads)
+{
+    return nb_gibbs_df_impl(w_last, beta, d_out, y, tX, d0, m0, P0, N, P, samp, burn, seed, nthreads, 1);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Posterior mode by EM, Logit::EM (Logit.hpp:488-554) as LogitWrapper.cpp:238-273 calls it: default (flat)
+ * prior, beta = 0 to start; per iteration psi = X beta, w_i = E[omega_i] = n_i tanh(psi_i/2) / (psi_i/2) / 4
+ * (series below |psi_i/2| < 0.01, :517-523), PP = X' diag(w) X through the sqrt(w)-scaled copy (:530-541),
+ * beta = PP^-1 bP by Cholesky (:543-546), dist = max_a |beta_a - beta_old_a| (:551-552);
+ * loop while dist > tol && iter < max_iter.  Returns the iteration count (-1: not positive definite).
+ * --------------------------------------------------------------------------------------------- */
+int pgb_logit_em(double *beta, const double *y, const double *tX, const double *n, int N, int P,
+                 double tol, int max_iter, int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+    double *bP = (double *)calloc(P, sizeof(double));
+    double *P0 = (double *)calloc((size_t)P * P, sizeof(double));
+    double *PP = (double *)malloc(sizeof(double) * P * P);
+    double *psi = (double *)malloc(sizeof(double) * N);
+    double *w = (double *)malloc(sizeof(double) * N);
+    double *old = (double *)malloc(sizeof(double) * P);
+    for (int i = 0; i < N; ++i) {
+        double alpha = n[i] * (y[i] - 0.5);
+        for (int a = 0; a < P; ++a) bP[a] += tX[a + (size_t)P * i] * alpha;
+    }
+    for (int a = 0; a < P; ++a) beta[a] = 0.0;
+    double dist = tol + 1.0;
+    int iter = 0;
+    while (dist > tol && iter < max_iter) {
+        xbeta(psi, tX, beta, N, P, nthreads);
+        for (int i = 0; i < N; ++i) {
+            double h = psi[i] * 0.5;
+            if (fabs(h) < 0.01)
+                w[i] = n[i] / cosh(h) * (1 + h * h / 6.0 + pow(h, 4.0) / 120.0 + pow(h, 6) / 5040.0) * 0.25;
+            else
+                w[i] = n[i] * tanh(h) / h * 0.25;
+        }
+        memcpy(old, beta, sizeof(double) * P);
+        weighted_gram(PP, P0, tX, w, N, P, nthreads);
+        if (chol_upper(PP, P)) { iter = -1; break; }
+        memcpy(beta, bP, sizeof(double) * P);
+        solve_Ut(PP, beta, P);
+        solve_U(PP, beta, P);
+        dist = 0.0;
+        for (int a = 0; a < P; ++a) dist = fmax(dist, fabs(beta[a] - old[a]));
+        ++iter;
+    }
+    free(bP); free(P0); free(PP); free(psi); free(w); free(old);
+    return iter;
 }
 

@@ -70,6 +70,8 @@ class Oracle:
             lib.pgb_mlogit_gibbs.argtypes = [vp] * 7 + [ci, ci, ci, ci, ci, u64, ci]
             lib.pgb_nb_gibbs.argtypes = [vp, vp, vp, vp, C.c_double, vp, vp, ci, ci, ci, u64, ci]
             lib.pgb_nb_gibbs_df.argtypes = [vp, vp, vp, vp, vp, C.c_double, vp, vp, ci, ci, ci, ci, u64, ci]
+            lib.pgb_nb_gibbs_dfreal.argtypes = [vp, vp, vp, vp, vp, C.c_double, vp, vp, ci, ci, ci, ci, u64, ci]
+            lib.pgb_logit_em.argtypes = [vp, vp, vp, vp, ci, ci, C.c_double, ci, ci]
 
     # -- stream helpers ------------------------------------------------------
     @staticmethod
@@ -202,19 +204,35 @@ def nb_gibbs(y, X, d, m0, P0, samp, seed, nthreads=0):
     return w, beta
 
 
-def nb_gibbs_df(y, X, m0, P0, samp, burn, seed, d0=1.0, nthreads=0):
-    """CPU restatement of NB.PG.gibbs with draw.df.  Returns (w_last [N], beta [samp x P], d [samp])."""
+def nb_gibbs_df(y, X, m0, P0, samp, burn, seed, d0=1.0, nthreads=0, real_d=False):
+    """CPU restatement of NB.PG.gibbs with draw.df (real_d: with draw.df.real.mean, NB-Shape.R:86-96).
+    Returns (w_last [N], beta [samp x P], d [samp])."""
     O = _gibbs_port()
     X = np.ascontiguousarray(X, dtype=np.float64)
     N, P = X.shape
     y, m0 = _f64(y).ravel(), _f64(m0).ravel()
     P0c = np.asfortranarray(_f64(P0))
     w, beta, d = np.zeros(N), np.zeros((samp, P)), np.zeros(samp)
-    st = O.lib.pgb_nb_gibbs_df(w.ctypes.data, beta.ctypes.data, d.ctypes.data, y.ctypes.data, X.ctypes.data,
-                               float(d0), m0.ctypes.data, P0c.ctypes.data, N, P, samp, burn, int(seed), nthreads)
+    fn = O.lib.pgb_nb_gibbs_dfreal if real_d else O.lib.pgb_nb_gibbs_df
+    st = fn(w.ctypes.data, beta.ctypes.data, d.ctypes.data, y.ctypes.data, X.ctypes.data,
+            float(d0), m0.ctypes.data, P0c.ctypes.data, N, P, samp, burn, int(seed), nthreads)
     if st:
         raise RuntimeError("oracle nb_gibbs_df: precision not positive definite")
     return w, beta, d
+
+
+def logit_em(y, X, n, tol=1e-9, max_iter=100, nthreads=0):
+    """CPU restatement of Logit::EM (Logit.hpp:488-554).  Returns (beta [P], iterations)."""
+    O = _gibbs_port()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    N, P = X.shape
+    y, n = _f64(y).ravel(), _f64(n).ravel()
+    beta = np.zeros(P)
+    it = O.lib.pgb_logit_em(beta.ctypes.data, y.ctypes.data, X.ctypes.data, n.ctypes.data, N, P, float(tol),
+                            int(max_iter), nthreads)
+    if it < 0:
+        raise RuntimeError("oracle logit_em: X' Omega X not positive definite")
+    return beta, it
 
 
 def make_tape(num, lu=0, le=0, ln=0, lg=0, g_shape=None, seed=0):

@@ -242,6 +242,46 @@ def test_nb_chain_with_dispersion_update_matches_oracle(gapi):
     close(b, bo, 1e-7); close(w, wo, 1e-7)
 
 
+def test_nb_chain_with_real_valued_dispersion_matches_oracle(gapi):
+    """draw.df.real.mean (NB-Shape.R:86-96): the dispersion walks on the reals, so b = y + d is non-integer and every
+    omega comes from the alternate / saddle-point / normal samplers.  d equal step for step (decisions lu < lalpha
+    on N-term sums: equal unless a tie to rounding), beta and omega within the chain tolerance."""
+    rng = np.random.default_rng(26)
+    N, P, d = 30_000, 4, 4.0
+    X = np.c_[rng.standard_normal((N, P - 1)), np.ones(N)]
+    bt = np.array([0.8, -0.6, 0.5, 2.2])
+    y = rng.negative_binomial(d, d / (np.exp(X @ bt) + d)).astype(float)
+    w, b, ds = gapi.nb_gibbs_df(y, X, np.zeros(P), 0.01 * np.eye(P), 12, 6, seed=8, d0=2.5, real_d=True)
+    wo, bo, dso = loader.nb_gibbs_df(y, X, np.zeros(P), 0.01 * np.eye(P), 12, 6, seed=8, d0=2.5, real_d=True)
+    assert len(set(ds)) > 2 and np.any(ds != np.floor(ds))
+    close(ds, dso, 1e-12)
+    close(b, bo, 1e-7); close(w, wo, 1e-7)
+
+
+def test_em_matches_oracle_restatement(gapi):
+    """logit.EM against the restatement of Logit::EM (Logit.hpp:488-554): same beta AND the same iteration count --
+    the loop runs while max|beta - beta_old| > tol and iter < max_iter, and max_iter cuts it when tol is not met."""
+    X, y, n, _ = synth_logit(20_000, 6, 9, binomial=True)
+    for tol, max_iter in ((1e-6, 100), (1e-11, 200), (1e-14, 7)):
+        out = gapi.logit_EM(y, X, n, tol=tol, max_iter=max_iter)
+        bo, ito = loader.logit_em(y, X, n, tol=tol, max_iter=max_iter)
+        assert out["iter"] == ito, (tol, max_iter, out["iter"], ito)
+        assert np.allclose(out["beta"], bo, rtol=1e-9, atol=1e-12)
+    assert gapi.logit_EM(y, X, n, tol=1e-14, max_iter=7)["iter"] == 7
+
+
+def test_thinned_omega_chain(gapi):
+    """bl_logit_gibbs_thin: beta every iteration, omega every w_every-th sampling iteration -- the rows of the
+    unthinned chain, bit for bit."""
+    X, y, n, _ = synth_logit(3000, 6, 5)
+    P0 = 0.2 * np.eye(6)
+    w, b = gapi.logit_gibbs(y, X, n, np.zeros(6), P0, 11, 4, seed=3)
+    for every in (3, 5, 11, 20):
+        wt, bt = gapi.logit_gibbs(y, X, n, np.zeros(6), P0, 11, 4, seed=3, w_every=every)
+        assert np.array_equal(bt, b)
+        assert wt.shape == ((11 + every - 1) // every, 3000) and np.array_equal(wt, w[::every])
+
+
 def test_em_matches_newton_mode(gapi):
     """logit.EM (Logit.hpp:488-554): flat prior -> the MLE."""
     X, y, n, _ = synth_logit(4000, 6, 9, binomial=True)

@@ -493,3 +493,18 @@ def test_large_batch_chunk_pipeline(engine, oracle, method):
     if method == "devroye":
         m = 0.5 / z * np.tanh(z / 2)
         assert abs((x - m).mean()) < 5 * 0.2 / np.sqrt(num)
+
+
+def test_r_seed_shim(engine):
+    """bl_set_seed_r(int*) -- what an R front end calls next to set.seed(): same state as bl_set_seed."""
+    import ctypes as C
+    from bayeslogit_b200 import _lib
+    L = _lib.lib()
+    z = np.linspace(-3, 3, 1000)
+    seed = C.c_int(4711)
+    L.bl_set_seed_r(C.cast(C.byref(seed), C.c_void_p))
+    assert L.bl_get_seed() == 4711 and L.bl_get_call_counter() == 0
+    a = engine.rpg_devroye(1000, 1, z)
+    engine.set_seed(4711)
+    b = engine.rpg_devroye(1000, 1, z)
+    assert np.array_equal(a, b)
