@@ -108,6 +108,38 @@ int merge_rows(double *ty, double *tX, double *n, int N, int P, int ny)
     return M;
 }
 
+// The merge the entry points use: on the device (merge.cu: row hashes, a stable radix sort by first occurrence,
+// the reference's running weighted mean replayed per group -- bit-identical to merge_rows) for data sets large
+// enough to pay for the upload; the exact host merge for small ones, when no device is usable, or when the device
+// path reports rows it cannot decide by hash (a collision, NaN covariates).  BAYESLOGIT_MERGE=host|device forces one.
+int merge_rows_auto(double *ty, double *tX, double *n, int N, int P, int ny)
+{
+    const char *mode = getenv("BAYESLOGIT_MERGE");
+    const bool force_host = mode && !strcmp(mode, "host"), force_dev = mode && !strcmp(mode, "device");
+    if (force_host || (!force_dev && (size_t)N * P < (1u << 16))) return merge_rows(ty, tX, n, N, P, ny);
+    if (bl_ensure_ready_internal()) {
+        if (force_dev) return N;                         // the error is set; nothing merged
+        bl_set_error_internal("");
+        return merge_rows(ty, tX, n, N, P, ny);
+    }
+    std::string err;
+    Dev d;
+    double *dy = d.put(ty, (size_t)N * ny, err), *dX = d.put(tX, (size_t)N * P, err), *dn = d.put(n, N, err);
+    if (!err.empty()) { report(err, nullptr); return merge_rows(ty, tX, n, N, P, ny); }
+    const int M = merge_rows_device(dy, dX, dn, N, P, ny, (cudaStream_t)bl_stream_internal(), err);
+    if (M == -2) return merge_rows(ty, tX, n, N, P, ny);
+    if (M < 0) { report(err, nullptr); return merge_rows(ty, tX, n, N, P, ny); }
+    if (M != N) {
+        cudaError_t e = cudaMemcpy(ty, dy, sizeof(double) * (size_t)M * ny, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(tX, dX, sizeof(double) * (size_t)M * P, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(n, dn, sizeof(double) * M, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { report(cudaGetErrorString(e), nullptr); return N; }
+        printf("Warning: data was combined!\n");     // Logit.hpp:248-251
+        printf("N: %i, P: %i \n", M, P);
+    }
+    return M;
+}
+
 uint64_t dropin_seed()
 {
     // the reference draws from R's global generator; here: (engine seed, call counter) -> chain seed.
@@ -198,7 +230,7 @@ void mult_gibbs(double *wp, double *betap, double *typ, double *tXp, double *np,
     // on its own copies, so the caller's data buffers are left as they were
     int U = *J - 1;
     std::vector<double> ty(typ, typ + (size_t)U * *N), tX(tXp, tXp + (size_t)*P * *N), n(np, np + *N);
-    int M = merge_rows(ty.data(), tX.data(), n.data(), *N, *P, U);
+    int M = merge_rows_auto(ty.data(), tX.data(), n.data(), *N, *P, U);
     if (host_mlogit(wp, betap, ty.data(), tX.data(), n.data(), m0p, P0p, M, *P, *J, *sampp, *burnp,
                     dropin_seed(), 0) == 0)
         *N = M;
@@ -207,13 +239,13 @@ void mult_gibbs(double *wp, double *betap, double *typ, double *tXp, double *np,
 void combine(double *yp, double *tXp, double *np, int *N, int *P)
 {
     if (!yp || !tXp || !np || !N || !P) { report("combine: null argument", "Aborting combine."); return; }
-    *N = merge_rows(yp, tXp, np, *N, *P, 1);
+    *N = merge_rows_auto(yp, tXp, np, *N, *P, 1);
 }
 
 void mult_combine(double *typ, double *tXp, double *np, int *N, int *P, int *J)
 {
     if (!typ || !tXp || !np || !N || !P || !J) { report("mult_combine: null argument", "Aborting combine."); return; }
-    *N = merge_rows(typ, tXp, np, *N, *P, *J - 1);
+    *N = merge_rows_auto(typ, tXp, np, *N, *P, *J - 1);
 }
 
 void EM(double *betap, double *yp, double *tXp, double *np, int *Np, int *Pp, double *tolp, int *max_iterp)

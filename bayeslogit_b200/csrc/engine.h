@@ -83,6 +83,8 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
                         uint64_t seed, int flags, cudaStream_t st, std::string &err);
 int logit_em_device(double *beta, const double *y, const double *tX, const double *n, int64_t N,
                     int P, double tol, int max_iter, int *iters, cudaStream_t st, std::string &err);
+// duplicate-row merge on device-resident data (merge.cu); returns M, -1 (CUDA error), -2 (needs the exact host merge)
+int merge_rows_device(double *ty, double *tX, double *n, int N, int P, int ny, cudaStream_t st, std::string &err);
 int comm_unique_id(void *out128, std::string &err);
 int comm_init(const void *id128, int rank, int world, std::string &err);
 int comm_init_local(int rank, int world, std::string &err);

@@ -359,3 +359,50 @@ def test_fused_psi_draw_equals_two_kernel_path(gapi, N, P, binomial):
     c1 = gapi.logit_chains(yc, Xc, nc, m0, P0, 5, 2, seed=9, flags=1)
     c2 = gapi.logit_chains(yc, Xc, nc, m0, P0, 5, 2, seed=9, flags=gapi.PLAIN_BETA | gapi.UNFUSED)
     assert np.array_equal(c1, c2)
+
+
+def _combine(gapi, mode, y, X, n):
+    import os
+    os.environ["BAYESLOGIT_MERGE"] = mode
+    try:
+        return gapi.logit_combine(y, X, n) if np.ndim(y) == 1 else gapi.mlogit_combine(y, X, n)
+    finally:
+        os.environ.pop("BAYESLOGIT_MERGE", None)
+
+
+@pytest.mark.parametrize("case", ["groups", "all_identical", "no_duplicates", "signed_zero", "nan_rows", "mlogit", "wide"])
+def test_device_merge_equals_host_merge(gapi, case):
+    """combine / mult_combine on the device (merge.cu: row hashes, stable radix sort by first occurrence, the
+    reference's running weighted mean replayed per group; Logit.hpp:192-270, MultLogit.hpp:137-208) against the
+    host merge: same rows in the same (first-occurrence) order, y and n BIT-identical.  Rows the hash cannot decide
+    (NaN covariates never equal themselves) take the exact host path."""
+    rng = np.random.default_rng(7)
+    N, P, D = 120_000, 6, 900
+    if case == "wide":
+        N, P, D = 300_000, 64, 40_000
+    base = rng.standard_normal((D, P))
+    idx = rng.integers(0, D, N)
+    X = base[idx].copy()
+    n = rng.integers(1, 5, N).astype(float)
+    y = rng.binomial(n.astype(int), 0.35) / n
+    if case == "all_identical":
+        X = np.ones((50_000, 1)); n = n[:50_000]; y = y[:50_000]
+    elif case == "no_duplicates":
+        X = rng.standard_normal((N, P))
+    elif case == "signed_zero":
+        X[:, 0] = np.where(rng.random(N) < 0.5, 0.0, -0.0)          # -0 == +0: such rows still merge
+    elif case == "nan_rows":
+        X[::1000, 2] = np.nan
+    elif case == "mlogit":
+        U = 3
+        cat = rng.integers(0, U + 1, N)
+        y = np.eye(U + 1)[cat][:, :U]
+    dev = _combine(gapi, "device", y, X, n)
+    host = _combine(gapi, "host", y, X, n)
+    assert dev["X"].shape == host["X"].shape
+    assert np.array_equal(dev["X"], host["X"], equal_nan=True)
+    assert np.array_equal(dev["n"], host["n"]) and np.array_equal(dev["y"], host["y"])
+    if case == "all_identical":
+        assert dev["X"].shape[0] == 1 and dev["n"][0] == n.sum()
+    if case == "no_duplicates":
+        assert dev["X"].shape[0] == N
