@@ -107,73 +107,107 @@ __device__ __forceinline__ bool dev_series_test(double X, double u)
     return dev_series_exact(X, u);
 }
 
+// The proposal of PolyaGamma::draw_like_devroye in pieces, so that callers can either run them back to back on
+// one lane (dev_propose) or regroup draws by piece first (k_devroye_regroup): variates are consumed in exactly
+// the reference's order either way.
+//   dev_pick          U_mix -> which piece the proposal comes from: 1 right (t + E / fz, PolyaGamma.cpp:171),
+//                     2 inverse-chi^2 pairs with thinning (Z < 1/t, :87-101), 3 inverse Gaussian (:103-113)
+//   dev_piece_*       the proposal X of that piece
+//   dev_series_test   the alternating-series accept test on the next uniform
+template <class Src>
+__device__ __forceinline__ int dev_pick(Src &s, DevSetup &st)
+{
+    const double umix = s.unif();
+    if (dev_choose_right(st, umix)) return 1;
+    return 1.0 / kTrunc > st.Z ? 2 : 3;
+}
+
+template <class Src>
+__device__ __forceinline__ double dev_piece_right(Src &s, const DevSetup &st)
+{
+    return dev_x_right(s.expon(), st.fz);
+}
+
+template <class Src>
+__device__ __forceinline__ double dev_piece_pair(Src &s, const DevSetup &st)
+{
+    const double t = kTrunc;
+    double X = 0.0;
+    float hz2 = (float)(0.5 * st.Z * st.Z);
+    float alpha32 = 0.0f;        // first pass: alpha = 0, the loop is always entered
+    bool first = true;
+    for (;;) {
+        double ua = s.unif();
+        if (!first) {
+            bool cont;
+            double a = (double)alpha32;
+            if (ua > a + 5e-6) cont = true;
+            else if (ua < a - 5e-6) cont = false;
+            else cont = ua > exp(-0.5 * st.Z * st.Z * X);
+            if (!cont) break;
+        }
+        first = false;
+        typename Src::LazyE l1, l2;
+        for (;;) {
+            l1 = s.expon_lazy();
+            l2 = s.expon_lazy();
+            float e1 = Src::approx(l1), e2 = Src::approx(l2);
+            float d = 0.32f * e1 * e1 - e2;                 // E1^2 > 2 E2 / t  <=>  d > 0
+            float band = 2e-6f * (0.32f * e1 * e1 + e2 + 1.0f);
+            bool again;
+            if (d > band) again = true;
+            else if (d < -band) again = false;
+            else {
+                double E1 = Src::exact(l1), E2 = Src::exact(l2);
+                again = E1 * E1 > 2 * E2 / t;
+            }
+            if (!again) break;
+        }
+        X = dev_x_pair(Src::exact(l1));
+        alpha32 = __expf(-hz2 * (float)X);
+    }
+    return X;
+}
+
+template <class Src>
+__device__ __forceinline__ double dev_piece_ig(Src &s, const DevSetup &st)
+{
+    const double t = kTrunc;
+    double X;
+    double mu = 1.0 / st.Z;
+    float muf = (float)mu;
+    for (;;) {
+        typename Src::LazyN ln = s.norm_lazy();
+        double u = s.unif();
+        float nf = Src::approx(ln);
+        float w = muf * nf * nf;
+        float x32 = __fdividef(muf, 1.0f + 0.5f * w + sqrtf(w + 0.25f * w * w));
+        float p32 = __fdividef(muf, muf + x32);
+        bool decided = false, accept = false, flip = false;
+        if (fabs(u - (double)p32) > 5e-5 * (double)p32 + 1e-7) {
+            flip = u > (double)p32;
+            float xf = flip ? __fdividef(muf * muf, x32) : x32;
+            if (xf > 0.64f * (1.0f + 5e-5f)) { decided = true; accept = false; }
+            else if (xf < 0.64f * (1.0f - 5e-5f)) { decided = true; accept = true; }
+        }
+        if (decided && !accept) continue;
+        // accepted or ambiguous: the reference's fp64 expression
+        X = dev_x_ig(Src::exact(ln), mu);
+        if (decided ? flip : (u > dev_ig_flip_threshold(X, mu))) X = dev_x_ig_flip(X, mu);
+        if (decided || !(X > t)) break;
+    }
+    return X;
+}
+
 // One proposal + series test.  Returns true when the proposal X is accepted.
 // Variates are consumed in exactly the reference's order.
 template <class Src>
 __device__ __forceinline__ bool dev_propose(Src &s, DevSetup &st, double &X)
 {
-    const double t = kTrunc;
-    double umix = s.unif();
-    if (dev_choose_right(st, umix)) {
-        X = dev_x_right(s.expon(), st.fz);                             // PolyaGamma.cpp:171
-    } else if (1.0 / kTrunc > st.Z) {                                   // :87-101
-        float hz2 = (float)(0.5 * st.Z * st.Z);
-        float alpha32 = 0.0f;        // first pass: alpha = 0, the loop is always entered
-        bool first = true;
-        for (;;) {
-            double ua = s.unif();
-            if (!first) {
-                bool cont;
-                double a = (double)alpha32;
-                if (ua > a + 5e-6) cont = true;
-                else if (ua < a - 5e-6) cont = false;
-                else cont = ua > exp(-0.5 * st.Z * st.Z * X);
-                if (!cont) break;
-            }
-            first = false;
-            typename Src::LazyE l1, l2;
-            for (;;) {
-                l1 = s.expon_lazy();
-                l2 = s.expon_lazy();
-                float e1 = Src::approx(l1), e2 = Src::approx(l2);
-                float d = 0.32f * e1 * e1 - e2;                 // E1^2 > 2 E2 / t  <=>  d > 0
-                float band = 2e-6f * (0.32f * e1 * e1 + e2 + 1.0f);
-                bool again;
-                if (d > band) again = true;
-                else if (d < -band) again = false;
-                else {
-                    double E1 = Src::exact(l1), E2 = Src::exact(l2);
-                    again = E1 * E1 > 2 * E2 / t;
-                }
-                if (!again) break;
-            }
-            X = dev_x_pair(Src::exact(l1));
-            alpha32 = __expf(-hz2 * (float)X);
-        }
-    } else {                                                            // :103-113
-        double mu = 1.0 / st.Z;
-        float muf = (float)mu;
-        for (;;) {
-            typename Src::LazyN ln = s.norm_lazy();
-            double u = s.unif();
-            float nf = Src::approx(ln);
-            float w = muf * nf * nf;
-            float x32 = __fdividef(muf, 1.0f + 0.5f * w + sqrtf(w + 0.25f * w * w));
-            float p32 = __fdividef(muf, muf + x32);
-            bool decided = false, accept = false, flip = false;
-            if (fabs(u - (double)p32) > 5e-5 * (double)p32 + 1e-7) {
-                flip = u > (double)p32;
-                float xf = flip ? __fdividef(muf * muf, x32) : x32;
-                if (xf > 0.64f * (1.0f + 5e-5f)) { decided = true; accept = false; }
-                else if (xf < 0.64f * (1.0f - 5e-5f)) { decided = true; accept = true; }
-            }
-            if (decided && !accept) continue;
-            // accepted or ambiguous: the reference's fp64 expression
-            X = dev_x_ig(Src::exact(ln), mu);
-            if (decided ? flip : (u > dev_ig_flip_threshold(X, mu))) X = dev_x_ig_flip(X, mu);
-            if (decided || !(X > t)) break;
-        }
-    }
+    const int piece = dev_pick(s, st);
+    if (piece == 1) X = dev_piece_right(s, st);
+    else if (piece == 2) X = dev_piece_pair(s, st);
+    else X = dev_piece_ig(s, st);
     return dev_series_test(X, s.unif());
 }
 

@@ -14,6 +14,7 @@
 // round-robin to warps, so a drift of z along the array cannot unbalance the SMs.
 // HBM traffic: z and n in, omega out -- coalesced in runs of consecutive indices.
 #include <algorithm>
+#include <cstdlib>
 
 #include "engine.h"
 #include "pg_devroye_fast.cuh"
@@ -150,6 +151,162 @@ k_devroye_refill(double *__restrict__ x, const int *__restrict__ n, const double
 
 
 // ---------------------------------------------------------------------------------------------
+// PG(1,z) / sum of PG(1) with CTA-level regrouping by proposal piece (large batches).
+//
+// In k_devroye_refill a lane owns a draw, and every trip of a warp runs all the proposal pieces its
+// 32 lanes happen to need -- the right piece (about half of the proposals for z ~ U(-5,5)) and one or
+// both left pieces -- one after the other: 9-18 of 32 lanes were active in the average instruction.
+// Here draws live in SLOTS in shared memory (Z, the fp32 right-mass estimate, the Philox position, the
+// running sum of a Sigma PG(1) draw) and any thread can advance any slot.  Every trip the CTA
+//   (i)   refills empty slots (each warp from its own chunks of the batch; set-up, first U_mix -> piece),
+//   (ii)  sorts the live slots by the piece of their pending proposal: ballot ranks + a prefix over the
+//         warps; piece 1 from the front of `perm`, piece 3 right behind it, piece 2 from the back,
+//   (iii) lets thread t run the proposal of slot perm[t], the series test, and -- accepted or not -- the
+//         U_mix that decides the piece of the slot's next proposal.
+// All warps but the (at most two) on a boundary then run one piece.  Variates are consumed per draw in the
+// reference's order, from the stream keyed by the draw's global index: results are bit-identical to
+// k_devroye_refill and to the per-lane loops (test_devroye_regroup_equals_refill).
+// ---------------------------------------------------------------------------------------------
+constexpr int kDrThreads = 256;
+constexpr int kDrChunk = 128;
+
+struct DrSlots {
+    double Z[kDrThreads];
+    double sum[kDrThreads];
+    uint4 buf[kDrThreads];
+    uint32_t blk[kDrThreads];
+    float pr32[kDrThreads];
+    int pos[kDrThreads];
+    int obs[kDrThreads];
+    int remaining[kDrThreads];
+    int phase[kDrThreads];                     // -1 empty, else the pending piece (1, 2, 3)
+    int perm[kDrThreads];
+    int wcnt[kDrThreads / 32][3];
+};
+
+__device__ __forceinline__ void dr_open(PhiloxSource &src, const StreamId &id, int obs)
+{
+    if (id.chain_len) {
+        const uint32_t ch = (uint32_t)obs / id.chain_len;
+        src.open(id.seed + ch, id.obs0 + ((uint32_t)obs - ch * id.chain_len), id.call_id);
+    } else {
+        src.open(id.seed, id.obs0 + (uint64_t)obs, id.call_id);
+    }
+}
+
+__global__ void __launch_bounds__(kDrThreads)
+k_devroye_regroup(double *__restrict__ x, const int *__restrict__ n, const double *__restrict__ z, int num, StreamId id)
+{
+    __shared__ DrSlots S;
+    const unsigned full = 0xffffffffu;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    constexpr int kWarps = kDrThreads / 32;
+    const int gwarp = blockIdx.x * kWarps + warp;
+    const long long stride = (long long)gridDim.x * kWarps * kDrChunk;
+    long long cur = (long long)gwarp * kDrChunk, cend = cur + kDrChunk;
+
+    S.phase[t] = -1;
+    __syncthreads();
+    for (;;) {
+        // (i) refill this warp's empty home slots from its chunk
+        const bool empty = S.phase[t] < 0;
+        const unsigned want = __ballot_sync(full, empty);
+        if (want && cur < num) {
+            const int rank = __popc(want & lt_mask);
+            long long cand = cur + rank;
+            if (cand >= cend) cand += stride - kDrChunk;
+            if (empty && cand < num) {
+                const int obs = (int)cand;
+                const int ni = n[obs];
+                if (ni == 0) {
+                    x[obs] = 0.0;                                    // LogitWrapper.cpp:76-79
+                } else {
+                    DevSetup st = dev_setup(z[obs]);
+                    PhiloxSource src;
+                    dr_open(src, id, obs);
+                    S.phase[t] = dev_pick(src, st);
+                    S.Z[t] = st.Z;
+                    S.pr32[t] = st.pr32;
+                    S.sum[t] = 0.0;
+                    S.remaining[t] = ni < 1 ? 1 : ni;                // NTHROW clamp, PolyaGamma.cpp:128-135
+                    S.obs[t] = obs;
+                    S.buf[t] = src.buf;
+                    S.blk[t] = src.blk;
+                    S.pos[t] = src.pos;
+                }
+            }
+            cur += __popc(want);
+            if (cur >= cend) {
+                const long long over = cur - cend;
+                cend += stride;
+                cur = cend - kDrChunk + over;
+            }
+        }
+        // (ii) sort live slots by piece
+        const int ph = S.phase[t];
+        const unsigned m1 = __ballot_sync(full, ph == 1), m2 = __ballot_sync(full, ph == 2), m3 = __ballot_sync(full, ph == 3);
+        if (lane == 0) { S.wcnt[warp][0] = __popc(m1); S.wcnt[warp][1] = __popc(m2); S.wcnt[warp][2] = __popc(m3); }
+        __syncthreads();
+        int tot1 = 0, tot2 = 0, tot3 = 0, b1 = 0, b2 = 0, b3 = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const int a = S.wcnt[w][0], b = S.wcnt[w][1], c = S.wcnt[w][2];
+            if (w < warp) { b1 += a; b2 += b; b3 += c; }
+            tot1 += a;
+            tot2 += b;
+            tot3 += c;
+        }
+        if (tot1 + tot2 + tot3 == 0) {
+            if (!__syncthreads_or(cur < num)) break;                    // nothing live, nothing left anywhere
+            continue;
+        }
+        if (ph == 1) S.perm[b1 + __popc(m1 & lt_mask)] = t;
+        else if (ph == 3) S.perm[tot1 + b3 + __popc(m3 & lt_mask)] = t;
+        else if (ph == 2) S.perm[kDrThreads - 1 - (b2 + __popc(m2 & lt_mask))] = t;
+        __syncthreads();
+        // (iii) thread t advances slot perm[t] by one proposal
+        if (t < tot1 + tot3 || t >= kDrThreads - tot2) {
+            const int sl = S.perm[t];
+            const int obs = S.obs[sl];
+            PhiloxSource src;
+            dr_open(src, id, obs);
+            src.buf = S.buf[sl];
+            src.blk = S.blk[sl];
+            src.pos = S.pos[sl];
+            DevSetup st;
+            st.Z = S.Z[sl];
+            st.fz = dev_fz(st.Z);
+            st.pr32 = S.pr32[sl];
+            st.pr64 = nan("");
+            const int piece = S.phase[sl];
+            double X;
+            if (piece == 1) X = dev_piece_right(src, st);
+            else if (piece == 2) X = dev_piece_pair(src, st);
+            else X = dev_piece_ig(src, st);
+            bool done = false;
+            if (dev_series_test(X, src.unif())) {
+                const double sum = S.sum[sl] + 0.25 * X;
+                if (--S.remaining[sl] == 0) {
+                    x[obs] = sum;
+                    S.phase[sl] = -1;
+                    done = true;
+                } else {
+                    S.sum[sl] = sum;
+                }
+            }
+            if (!done) {
+                S.phase[sl] = dev_pick(src, st);                        // piece of the next proposal
+                S.buf[sl] = src.buf;
+                S.blk[sl] = src.blk;
+                S.pos[sl] = src.pos;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fused sweep half-step of the logit samplers: psi_i = x_i . beta and omega_i = PG(n_i, psi_i) in one
 // pass over X (Logit.hpp:421,431 then Logit::draw_w :283-289; the two statements are adjacent in
 // gibbs_block and psi has no other reader).  Separately the two kernels are bound by different
@@ -254,7 +411,21 @@ cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int6
     int64_t chunks = (num + chunk - 1) / chunk;
     int64_t blocks = (chunks + (kThreads / 32) - 1) / (kThreads / 32);
     int grid = (int)(blocks < cap ? blocks : cap);
-    if (work && num >= (1 << 20) && num < (1LL << 31)) {
+    // BL_DEVROYE_REGROUP=1: slots regrouped by proposal piece across the CTA (k_devroye_regroup) -- bit-identical
+    // results, but measured SLOWER than the per-lane kernel (1.14e10 against 1.26e10 draws/s at 2^27 draws; 113 us
+    // against 105 us for the 1M draws of a Gibbs sweep): a PG(1,z) proposal is ~150 instructions, and the two
+    // CTA barriers, the slot traffic and the wait for the slowest warp of every trip cost more than the
+    // divergence they remove.  Kept as a measured alternative, not the default.
+    const bool regroup = getenv("BL_DEVROYE_REGROUP") != nullptr;
+    if (regroup && num >= (1 << 15) && num < (1LL << 31)) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_devroye_regroup, kDrThreads, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        const int64_t want = (num + kDrThreads - 1) / kDrThreads;
+        const int rgrid = (int)std::min<int64_t>(148LL * per_sm, std::max<int64_t>(1, want));
+        k_devroye_regroup<<<rgrid, kDrThreads, 0, st>>>(x, n, z, (int)num, id);
+        count_launch();
+    } else if (work && num >= (1 << 20) && num < (1LL << 31)) {
         int *meta = (int *)work, *idx = meta + 32;
         cudaError_t e = cudaMemsetAsync(meta, 0, 32 * sizeof(int), st);
         if (e != cudaSuccess) return e;

@@ -508,3 +508,26 @@ def test_r_seed_shim(engine):
     engine.set_seed(4711)
     b = engine.rpg_devroye(1000, 1, z)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("num", [40_000, 1_500_003])
+def test_devroye_regroup_equals_refill(engine, oracle, num):
+    """k_devroye_regroup (draws in shared-memory slots, regrouped by proposal piece across the CTA every trip;
+    BL_DEVROYE_REGROUP=1, batches >= 2^15) against k_devroye_refill (a lane owns a draw; the default) and the oracle: the same
+    stream per observation consumed in the same order, so the same bits -- n_i in {0, 1, 2, 5, -3} (zeros, sums of
+    PG(1), the NTHROW clamp) and |z| up to 40 (every proposal piece, both series branches)."""
+    import os
+    rng = np.random.default_rng(17)
+    z = np.where(rng.random(num) < 0.9, rng.uniform(-5, 5, num), rng.uniform(-40, 40, num))
+    n = rng.choice(np.array([0, 1, 1, 1, 1, 2, 5, -3], dtype=np.int32), num)
+    a = engine.rpg_seeded("devroye", n, z, seed=4242, call_id=3, obs0=17)
+    os.environ["BL_DEVROYE_REGROUP"] = "1"
+    try:
+        b = engine.rpg_seeded("devroye", n, z, seed=4242, call_id=3, obs0=17)
+    finally:
+        os.environ.pop("BL_DEVROYE_REGROUP", None)
+    assert np.array_equal(a, b)
+    m = min(num, 200_000)
+    want = oracle.rpg_devroye(n[:m], z[:m], seed=4242, call_id=3, obs0=17, nthreads=8)
+    assert_close(a[:m], want)
+    assert np.all(a[n == 0] == 0.0) and np.all(a[n != 0] > 0)
