@@ -551,10 +551,14 @@ int logit_gibbs_device(double *w_out, double *beta_out, const double *y, const d
     const int mode = (flags & BL_GIBBS_PLAIN_BETA) ? kBetaPlain : kBetaConstrained;
     // psi = X beta and the omega draw as one pass over X (k_logit_psi_draw) unless asked otherwise
     const bool fused = !(flags & BL_GIBBS_UNFUSED) && logit_psi_draw_ok(tX, P);
-    // ... or, on request and for even P <= 64, psi, omega and the Gram from ONE TMA-staged read of X
-    // (k_logit_sweep): exactly N P 8 bytes of HBM traffic per iteration, but bound by the latency of the draw
-    // warps that fit beside the Gram warps (gibbs_sweep.cu), so not the default
-    const bool one_pass = (flags & BL_GIBBS_ONE_PASS) && !(flags & BL_GIBBS_UNFUSED) && logit_sweep_ok(tX, P);
+    // ... or, for even P <= 64, psi, omega and the Gram from ONE TMA-staged read of X (k_logit_sweep, gibbs_sweep.cu):
+    // exactly N P 8 bytes of HBM traffic and two launches per iteration.  Its rate is set by the latency of the draw
+    // warps that fit beside the Gram warps, so on long shards the two-pass path is as fast or a little faster
+    // (N = 1M: 378 us against 372; 500k rows per GPU: 219 against 216), while on short ones the launches and the
+    // separate reduce it saves dominate (125k rows per GPU, 8 GPUs: 84 us against 106): default up to 2^18 local rows.
+    // BL_GIBBS_ONE_PASS / BL_GIBBS_TWO_PASS force either.
+    const bool one_pass = !(flags & (BL_GIBBS_UNFUSED | BL_GIBBS_TWO_PASS)) && logit_sweep_ok(tX, P) &&
+                          ((flags & BL_GIBBS_ONE_PASS) || N <= (1 << 18));
     LogitSweep k3;
     if (one_pass && k3.init(tX, N, P, st, err)) return 1;
 

@@ -107,6 +107,32 @@ __global__ void __launch_bounds__(1024) k_peak_dmma_operands(double *out, double
     if (s == 12345.678) out[0] = s;
 }
 
+// ... and with the weighted-Gram pattern: the A operand of every group of MMAs is the product of a fragment
+// and a weight, formed by a DMUL right in front of them (kMulEvery MMAs per DMUL).  DMUL and DMMA share the
+// FP64 pipe; this measures what the interleaving costs.
+template <int kMulEvery>
+__global__ void __launch_bounds__(1024) k_peak_dmma_mul(double *out, double a, double b)
+{
+    double c[kChains][2], av[kChains], bv[kChains];
+#pragma unroll
+    for (int k = 0; k < kChains; ++k) { c[k][0] = k; c[k][1] = -k; av[k] = a + 1e-3 * (threadIdx.x + k); bv[k] = b + 1e-3 * (threadIdx.x ^ k); }
+    double w = 1.0 + 1e-9 * threadIdx.x;
+    for (int it = 0; it < kIters; ++it) {
+        double aw = 0.0;
+#pragma unroll
+        for (int k = 0; k < kChains; ++k) {
+            if (k % kMulEvery == 0) aw = av[k] * w;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(aw), "d"(bv[(k + it) & (kChains - 1)]));
+        }
+        w += 1e-12;
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kChains; ++k) s += c[k][0] + c[k][1];
+    if (s == 12345.678) out[0] = s;
+}
+
 // the Philox round's multiply: 32 x 32 -> 64 bit (IMAD.WIDE.U32), folded back to 32 bits
 __global__ void __launch_bounds__(1024) k_peak_imad(unsigned *out, unsigned m)
 {
@@ -204,7 +230,7 @@ int probe_peaks(double *out6, cudaStream_t st, std::string &err)
 // DMMA rate against resident warps: out[k] = TFLOP/s with 1 CTA per SM of 128 << k threads (k = 0..3: one, two,
 // four, eight warps per scheduler), eight independent accumulator pairs per warp.  Design aid for the Gram
 // kernels: how many warps a scheduler needs before the FP64 tensor path stays busy.
-int probe_dmma_scaling(double *out4, cudaStream_t st, std::string &err)   // out4: 8 doubles
+int probe_dmma_scaling(double *out4, cudaStream_t st, std::string &err)   // out4: 16 doubles
 {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -219,6 +245,10 @@ int probe_dmma_scaling(double *out4, cudaStream_t st, std::string &err)   // out
         out4[k] = ((double)sms * block / 32) * kIters * kChains * 512.0 / (ms * 1e-3) / 1e12;
         rc |= time_kernel([&] { k_peak_dmma_operands<<<sms, block, 0, st>>>((double *)sink, 1.0000001, 1e-9); }, &ms, st, err);
         out4[4 + k] = ((double)sms * block / 32) * kIters * kChains * 512.0 / (ms * 1e-3) / 1e12;
+        rc |= time_kernel([&] { k_peak_dmma_mul<4><<<sms, block, 0, st>>>((double *)sink, 1.0000001, 1e-9); }, &ms, st, err);
+        out4[8 + k] = ((double)sms * block / 32) * kIters * kChains * 512.0 / (ms * 1e-3) / 1e12;
+        rc |= time_kernel([&] { k_peak_dmma_mul<8><<<sms, block, 0, st>>>((double *)sink, 1.0000001, 1e-9); }, &ms, st, err);
+        out4[12 + k] = ((double)sms * block / 32) * kIters * kChains * 512.0 / (ms * 1e-3) / 1e12;
     }
     cudaFree(sink);
     return rc;

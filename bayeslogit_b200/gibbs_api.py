@@ -22,6 +22,7 @@ PLAIN_BETA = 1   # BL_GIBBS_PLAIN_BETA
 NO_W = 2         # BL_GIBBS_NO_W
 UNFUSED = 4      # BL_GIBBS_UNFUSED (psi = X beta and the omega draw as two kernels; A/B aid)
 ONE_PASS = 8     # BL_GIBBS_ONE_PASS (psi, omega and the Gram from one TMA-staged read of X; even P <= 64)
+TWO_PASS = 16    # BL_GIBBS_TWO_PASS (never the one-pass kernel)
 
 
 def _f(a):

@@ -169,7 +169,9 @@ int bl_rpg_hybrid_tape(double *x, const double *h, const double *z, int64_t num,
 
 #define BL_GIBBS_ONE_PASS 8      /* even P <= 64: psi, omega and X' Omega X from ONE TMA-staged read of X per iteration
                                    (k_logit_sweep, gibbs_sweep.cu) instead of two passes (k_logit_psi_draw + k_gram_partial);
-                                   same chain up to the summation order of psi and the Gram */
+                                   same chain up to the summation order of psi and the Gram.  Without either flag the
+                                   one-pass kernel is used for shards of at most 2^18 rows, where it is the faster one. */
+#define BL_GIBBS_TWO_PASS 16     /* the two-pass path whatever the shard size */
 
 /* `gibbs` with an explicit seed and flags; host pointers, layouts as `gibbs`. */
 int bl_logit_gibbs(double *w, double *beta, const double *y, const double *tX, const double *n,
@@ -287,8 +289,9 @@ int bl_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint32_t *key2);
  * instructions G/s.  Best of four launches each, ~10 ms in total. */
 int bl_probe_peaks(double *out6);
 /* FP64 tensor (DMMA) TFLOP/s with one, two, four and eight resident warps per scheduler: out8[0..4) with the
- * same A/B registers in every MMA, out8[4..8) with operands that change from MMA to MMA (design aid). */
-int bl_probe_dmma_scaling(double *out8);
+ * same A/B registers in every MMA, out16[4..8) with operands that change from MMA to MMA, [8..12) / [12..16) with a
+ * DMUL forming the A operand in front of every 4 / 8 MMAs, as in a weighted Gram (design aid). */
+int bl_probe_dmma_scaling(double *out16);
 
 /* Host logic probe (no device needed): chunk sizes, in order, that the host-pointer entry points use to
  * stream a batch of num observations through HBM (small chunks open and close the batch so the pipeline

@@ -334,7 +334,7 @@ def test_one_pass_sweep_matches_two_pass_path(gapi, constrained, N, P, binomial)
     P0 = 0.3 * np.eye(P) + 0.01
     f = 0 if constrained else gapi.PLAIN_BETA
     w1, b1 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=15, flags=f | gapi.ONE_PASS)
-    w2, b2 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=15, flags=f)
+    w2, b2 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=15, flags=f | gapi.TWO_PASS)
     close(b1, b2, 1e-9); close(w1, w2, 1e-9)
     assert np.all(w1 > 0)
 
@@ -348,7 +348,7 @@ def test_fused_psi_draw_equals_two_kernel_path(gapi, N, P, binomial):
     X, y, n, _ = synth_logit(N, P, 77 + P, binomial)
     m0 = np.zeros(P)
     P0 = 0.3 * np.eye(P)
-    w1, b1 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=5, flags=gapi.PLAIN_BETA)
+    w1, b1 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=5, flags=gapi.PLAIN_BETA | gapi.TWO_PASS)
     w2, b2 = gapi.logit_gibbs(y, X, n, m0, P0, 6, 3, seed=5, flags=gapi.PLAIN_BETA | gapi.UNFUSED)
     assert np.array_equal(w1, w2) and np.array_equal(b1, b2)
     assert np.all(w1 > 0) and np.all(np.isfinite(b1))

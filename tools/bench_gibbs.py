@@ -41,7 +41,7 @@ def make_shard(N, P, lo, hi, device):
     return torch.cat(rows).contiguous(), torch.cat(ys).contiguous(), bt
 
 
-def run(N, P, iters, warm, constrained, rank, world, local, verify=False, unfused=False, one_pass=False):
+def run(N, P, iters, warm, constrained, rank, world, local, verify=False, unfused=False, one_pass=False, two_pass=False):
     import torch
     import torch.distributed as dist
     from bayeslogit_b200 import _lib, dist as bdist
@@ -52,7 +52,7 @@ def run(N, P, iters, warm, constrained, rank, world, local, verify=False, unfuse
     n = torch.ones(hi - lo, device=dev, dtype=torch.float64)
     m0 = torch.zeros(P, device=dev, dtype=torch.float64)
     P0 = (0.01 * torch.eye(P, device=dev, dtype=torch.float64)).contiguous()
-    flags = 2 | (0 if constrained else 1) | (4 if unfused else 0) | (8 if one_pass else 0)   # NO_W | PLAIN_BETA | UNFUSED | ONE_PASS
+    flags = 2 | (0 if constrained else 1) | (4 if unfused else 0) | (8 if one_pass else 0) | (16 if two_pass else 0)   # NO_W | PLAIN_BETA | UNFUSED | ONE_PASS | TWO_PASS
     st = torch.cuda.current_stream().cuda_stream
 
     def chain(k, seed):
@@ -81,8 +81,9 @@ def run(N, P, iters, warm, constrained, rank, world, local, verify=False, unfuse
     launches = L.bl_kernel_launches() - l0
     post = beta[iters // 2:].mean(0)
     return {"iters_per_sec": iters / (ms * 1e-3), "ms_per_iter": ms / iters, "iters": iters, "N": N, "P": P,
-            "n_gpus": world, "psi_and_draw": "two kernels" if unfused else "psi + omega + Gram from one TMA-staged read of X (k_logit_sweep)" if one_pass
-            else "one pass over X (k_logit_psi_draw)",
+            "n_gpus": world, "psi_and_draw": "two kernels" if unfused
+            else "psi + omega + Gram from one TMA-staged read of X (k_logit_sweep)" if (one_pass or (not two_pass and P % 2 == 0 and P <= 64 and hi - lo <= (1 << 18)))
+            else "one pass over X (k_logit_psi_draw), Gram in a second",
             "exchange": ("peer windows (fused in the Gram-reduce / beta-draw kernels)"
                                           if bdist.peer_exchange_active() else "ncclAllReduce") if world > 1 else None,
             "beta_draw": "constrained (reference, Logit.hpp:322-400)" if constrained
@@ -100,6 +101,7 @@ def main():
     ap.add_argument("--constrained", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="psi = X beta and the omega draw as two kernels (A/B)")
     ap.add_argument("--one-pass", action="store_true", help="the one-pass sweep kernel (k_logit_sweep)")
+    ap.add_argument("--two-pass", action="store_true", help="never the one-pass sweep kernel")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -111,7 +113,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         bdist.init_comm(rank, world, torch.device("cuda", local))
-    out = run(a.N, a.P, a.iters, a.warmup, a.constrained, rank, world, local, unfused=a.unfused, one_pass=a.one_pass)
+    out = run(a.N, a.P, a.iters, a.warmup, a.constrained, rank, world, local, unfused=a.unfused, one_pass=a.one_pass, two_pass=a.two_pass)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

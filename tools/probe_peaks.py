@@ -14,8 +14,10 @@ for _ in range(2):
     b = (C.c_double * 6)()
     _lib.check(L.bl_probe_peaks(C.cast(b, C.c_void_p)))
     print({n: round(v, 2) for n, v in zip(names, b)})
-d = (C.c_double * 8)()
+d = (C.c_double * 16)()
 L.bl_probe_dmma_scaling.argtypes = [C.c_void_p]
 _lib.check(L.bl_probe_dmma_scaling(C.cast(d, C.c_void_p)))
 print("dmma TFLOP/s at 1, 2, 4, 8 warps per scheduler (8 accumulator pairs per warp):", [round(v, 2) for v in d[:4]])
-print("  ... with A/B operands that change from MMA to MMA:", [round(v, 2) for v in d[4:]])
+print("  ... with A/B operands that change from MMA to MMA:", [round(v, 2) for v in d[4:8]])
+print("  ... and a DMUL forming the A operand in front of every 4 MMAs:", [round(v, 2) for v in d[8:12]])
+print("  ... in front of every 8 MMAs:", [round(v, 2) for v in d[12:16]])
