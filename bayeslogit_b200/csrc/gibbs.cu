@@ -456,24 +456,28 @@ struct Sweep {
     // acc[0..P^2) <- sum_i w_i x_i x_i'  (local shard).  Sharded sweeps with the peer windows open:
     // the reduce kernel stores the sums (and, with_tail, the P sums xtv() left in acc[P^2..]) into
     // every rank's window instead, and beta_draw() picks them up there -- call xtv() before gram().
-    void gram(const double *wv, bool with_tail = false)
+    // cvec (packed kernel, P == 32, only): the X'v tail acc[P^2 ..) = X' (wv o cvec) comes out of the same pass
+    // (gram_tail_fused() says whether that is possible); otherwise call xtv() first.
+    bool gram_tail_fused() const { return gram_packed(P) && nt == 1; }
+    void gram(const double *wv, bool with_tail = false, const double *cvec = nullptr)
     {
         int tiles = nt * (nt + 1) / 2;
         const bool packed = gram_packed(P);
         if (nt > 1)
             k_gram_partial<kGramRows, false><<<dim3(nslab, tiles), 256, gram_smem_bytes(true), st>>>(part, tX, wv, N, P, nt, nslab_diag);
         else if (packed)
-            k_gram_partial<kGramRowsDiag, true, true><<<dim3(nslab, tiles), 256, gram_smem_bytes(false, true), st>>>(part, tX, wv, N, P, nt);
+            k_gram_partial<kGramRowsDiag, true, true><<<dim3(nslab, tiles), 256, gram_smem_bytes(false, true), st>>>(part, tX, wv, N, P, nt, 0, cvec);
         else
             k_gram_partial<kGramRowsDiag, true><<<dim3(nslab, tiles), 256, gram_smem_bytes(false), st>>>(part, tX, wv, N, P, nt);
+        const int tail_in_part = packed && cvec ? 1 : 0;
         PeerPush px{};
         pending = PeerWait{};
         if (exchange && peer_active()) {
             peer_next(px, pending);
             px.with_tail = with_tail ? 1 : 0;
         }
-        k_gram_reduce<<<cdiv((int64_t)P * P, 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nt > 1 ? 2 * nslab : nslab, px, packed ? 1 : 0,
-                                                                2 * nslab_diag);
+        k_gram_reduce<<<cdiv((int64_t)P * P + (tail_in_part ? P : 0), 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nt > 1 ? 2 * nslab : nslab, px,
+                                                                                         packed ? 1 : 0, 2 * nslab_diag, tail_in_part);
         count_launch(2);
         if (px.world > 1) exchange_rendezvous();     // virtual ranks: every producer is enqueued before any consumer
     }
@@ -821,9 +825,13 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
             cudaError_t e = launch_devroye_refill(wj, shape, eta, N, StreamId{seed, obs0, call}, st);
             if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
             tmr.mark("draw");
-            s.xtv(nullptr, 0.0, wj, cj, 1.0);              // X' Omega c_j
-            tmr.mark("xtv");
-            s.gram(wj, true);
+            if (s.gram_tail_fused()) {
+                s.gram(wj, true, cj);                      // X' Omega X and X' Omega c_j from one pass (packed P = 32 kernel)
+            } else {
+                s.xtv(nullptr, 0.0, wj, cj, 1.0);          // X' Omega c_j
+                tmr.mark("xtv");
+                s.gram(wj, true);
+            }
             tmr.mark("gram");
             if (s.allreduce(true, err)) return 1;
             s.beta_draw(kBetaMvn, P0 + (size_t)P * P * j, base + (size_t)P * j, true, nullptr,

@@ -295,9 +295,13 @@ __device__ __forceinline__ void gram_diag_store(const double (&c)[9][2], double 
 // (A, 7 - A) as before, now (4 - A) + (A + 1) = 5 tiles per k-step for TWO observations -- 3.6x
 // fewer DMMAs per observation than padding P = 32 to a 64 x 64 tile with zeros.
 // wts: [2r] even-row weight, [2r + 1] odd-row weight of packed row r.
+// xt (slots 0 and 3 only, cvs != nullptr): the same fragments also give X' (Omega c) -- slot 0 holds every column
+// of the even observation of a packed row (b[0..3]), slot 3 every column of the odd one (b[4..7]) -- as four
+// DFMAs per k-step: xt[j] += X[r][8 j + gid] w_r c_r.  That is MultLogit.hpp:249,253's tXOmC without a second
+// pass over X (k_xtv_stream: 71 of the 380 us of a category update at N = 1M).
 template <int A, int kRows>
 __device__ __forceinline__ void gram_pack_chunk(double (&c)[9][2], const double *chunk, const double *wts,
-                                                int grp, int gid, int tig)
+                                                int grp, int gid, int tig, const double *cvs, double (&xt)[4])
 {
     constexpr int kLo = 4 - A;
 #pragma unroll
@@ -315,6 +319,11 @@ __device__ __forceinline__ void gram_pack_chunk(double (&c)[9][2], const double 
         for (int j = A; j < 4; ++j) dmma884(c[j - A][0], c[j - A][1], alo, b[j]);
 #pragma unroll
         for (int j = 7 - A; j < 8; ++j) dmma884(c[kLo + j - (7 - A)][0], c[kLo + j - (7 - A)][1], ahi, b[j]);
+        if (cvs && (A == 0 || A == 3)) {
+            const double wc = A == 0 ? we * cvs[2 * r] : wo * cvs[2 * r + 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xt[j] = fma(b[A == 0 ? j : 4 + j], wc, xt[j]);
+        }
     }
 }
 
@@ -339,13 +348,14 @@ __device__ __forceinline__ void gram_pack_store(const double (&c)[9][2], double 
 template <int kRows, bool kBalancedDiag, bool kPacked = false>
 __global__ void __launch_bounds__(256)
 k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const double *__restrict__ w,
-               int64_t N, int P, int nt, int nslab_diag = 0)
+               int64_t N, int P, int nt, int nslab_diag = 0, const double *__restrict__ cv = nullptr)
 {
     extern __shared__ __align__(16) double gsm[];
     const int nthr = blockDim.x;
     // batched independent chains: blockIdx.z = chain (its own rows, weights and partial tiles)
     tX += (size_t)blockIdx.z * N * P;
     w += (size_t)blockIdx.z * N;
+    if (cv) cv += (size_t)blockIdx.z * N;
     part += (size_t)blockIdx.z * gridDim.y * gridDim.x * (kBalancedDiag ? 1 : 2) * (kGramTile * kGramTile);
     int t = blockIdx.y, bi = 0;
     while (t >= nt - bi) { t -= nt - bi; ++bi; }
@@ -354,8 +364,9 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
     const int npanel = diag ? 1 : 2;
     static_assert(!kPacked || kBalancedDiag, "packed rows exist only for the single-tile kernel");
     constexpr int kObs = kPacked ? 2 * kRows : kRows;            // observations per chunk
-    const int stage_elems = npanel * kRows * kGramLdm + kObs;
+    const int stage_elems = npanel * kRows * kGramLdm + (kPacked ? 2 : 1) * kObs;     // packed: weights, then the c vector
     const int w_off = npanel * kRows * kGramLdm;
+    const int c_off = w_off + kObs;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
@@ -368,6 +379,7 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
     if ((int)blockIdx.x >= ns) return;
     double c[4][4][2] = {};
     double c9[9][2] = {};                               // kBalancedDiag: this warp's 9 tiles
+    double xt[4] = {0.0, 0.0, 0.0, 0.0};                // packed + cv: this lane's part of X' (Omega c)
     int64_t slab = (N + ns - 1) / ns;
     if (kPacked) slab = (slab + 1) & ~(int64_t)1;               // packed rows pair observations (2r, 2r+1) of the chain
     const int64_t r0 = (int64_t)blockIdx.x * slab;
@@ -401,6 +413,7 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
             if (threadIdx.x < kObs) {
                 int64_t i = base + threadIdx.x;
                 cp_async8(&gsm[so + w_off + threadIdx.x], i < r1 ? w + i : w, i < r1);
+                if (kPacked && cv) cp_async8(&gsm[so + c_off + threadIdx.x], i < r1 ? cv + i : cv, i < r1);
             }
         }
         cp_async_commit();
@@ -416,11 +429,12 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
         issue(base + 2 * kObs, nxt);
         if (kPacked) {
             const double *chunk = gsm + cur * stage_elems;
+            const double *cvs = cv ? chunk + c_off : nullptr;
             switch (sub) {
-            case 0: gram_pack_chunk<0, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
-            case 1: gram_pack_chunk<1, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
-            case 2: gram_pack_chunk<2, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
-            default: gram_pack_chunk<3, kRows>(c9, chunk, chunk + w_off, grp, gid, tig); break;
+            case 0: gram_pack_chunk<0, kRows>(c9, chunk, chunk + w_off, grp, gid, tig, cvs, xt); break;
+            case 1: gram_pack_chunk<1, kRows>(c9, chunk, chunk + w_off, grp, gid, tig, cvs, xt); break;
+            case 2: gram_pack_chunk<2, kRows>(c9, chunk, chunk + w_off, grp, gid, tig, cvs, xt); break;
+            default: gram_pack_chunk<3, kRows>(c9, chunk, chunk + w_off, grp, gid, tig, cvs, xt); break;
             }
         } else if (kBalancedDiag) {
             const double *chunk = gsm + cur * stage_elems;
@@ -480,6 +494,29 @@ k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const d
 #pragma unroll
             for (int t = 0; t < 9; ++t) { c9[t][0] += fold[2 * t]; c9[t][1] += fold[2 * t + 1]; }
         }
+        if (kPacked && cv) {
+            // X' (Omega c): add the four k rows of a lane group (tig), then the two row groups, and park the 32 + 32
+            // sums (even / odd observations of the packed rows) in the unused off-diagonal block of the partial tile:
+            // rows 0 and 1, columns 32..63.  k_gram_reduce adds the two rows and the slabs.
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                xt[j] += __shfl_xor_sync(0xffffffffu, xt[j], 1);
+                xt[j] += __shfl_xor_sync(0xffffffffu, xt[j], 2);
+            }
+            __syncthreads();
+            double *tf = gsm + 4 * 32 * 19;                     // past the accumulator fold area
+            if ((sub == 0 || sub == 3) && grp == 1 && tig == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tf[(sub == 3 ? 32 : 0) + 8 * j + gid] = xt[j];
+            }
+            __syncthreads();
+            if ((sub == 0 || sub == 3) && grp == 0 && tig == 0) {
+                double *o = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kGramTile * kGramTile) +
+                            (sub == 3 ? kGramTile : 0) + 32;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[8 * j + gid] = xt[j] + tf[(sub == 3 ? 32 : 0) + 8 * j + gid];
+            }
+        }
     }
     // partial tile of (slab[, row group]): entries exist where (row >> 3) <= (col >> 3) on diagonal tiles
     double *out = kBalancedDiag
@@ -524,7 +561,7 @@ inline int gram_rows(bool any_offdiag) { return any_offdiag ? kGramRows : kGramR
 inline size_t gram_smem_bytes(bool any_offdiag, bool packed = false)
 {
     int rows = gram_rows(any_offdiag);
-    return (size_t)kGramStages * ((any_offdiag ? 2 : 1) * rows * kGramLdm + (packed ? 2 : 1) * rows) * sizeof(double);
+    return (size_t)kGramStages * ((any_offdiag ? 2 : 1) * rows * kGramLdm + (packed ? 4 : 1) * rows) * sizeof(double);
 }
 
 // P == 32 rows are packed two per shared-memory row (gram_pack_chunk)
@@ -691,7 +728,8 @@ __device__ __forceinline__ void peer_stage(const PeerWait &pw, double *A, double
 static __global__ void __launch_bounds__(256)
 k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
               const double *__restrict__ part, int P, int nt, int nslab, PeerPush px, int packed = 0,
-              int nslab_diag = 0)      // nslab: partial tiles per output tile (stride); diagonal tiles hold nslab_diag of them (0: nslab)
+              int nslab_diag = 0,      // nslab: partial tiles per output tile (stride); diagonal tiles hold nslab_diag of them (0: nslab)
+              int tail_in_part = 0)    // packed tiles also carry X'(Omega c): the CTAs past the P^2 entries sum it into PP[P^2 ..)
 {
     __shared__ double red[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -701,7 +739,14 @@ k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
     int e = blockIdx.x * 32 + lane;
     int a = e % P, b = e / P;
     bool want = e < P * P && a <= b;
+    const bool tail = tail_in_part && e >= P * P && e < P * P + P;
     double s = 0.0;
+    if (tail) {
+        // rows 0 (even observations) and 1 (odd) of the tile's unused off-diagonal block, columns 32 + p
+        const double *src = part + 32 + (e - P * P);
+        for (int k = warp; k < nslab; k += 8)
+            s += src[(size_t)k * (kGramTile * kGramTile)] + src[(size_t)k * (kGramTile * kGramTile) + kGramTile];
+    }
     if (want) {
         int bi = a / kGramTile, bj = b / kGramTile;
         int tile = 0;
@@ -730,6 +775,11 @@ k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
         v += P0 ? P0[a + (size_t)P * b] : 0.0;
         PP[a + (size_t)P * b] = v;
         PP[b + (size_t)P * a] = v;
+    }
+    if (warp == 0 && tail) {
+        double v = 0.0;
+        for (int k = 0; k < 8; ++k) v += red[k][lane];
+        PP[e] = v;
     }
     // sharded data: the finished sums (and the P sums behind them) go into every rank's window
     if (px.world > 1) peer_publish(px, PP, P * P + (px.with_tail ? P : 0));

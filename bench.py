@@ -183,6 +183,30 @@ def cpu_gibbs_baseline(N, P, iters_all, iters_one):
     return out
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-rank runs: keep this rank's host threads -- and with them the first-touch placement of its pinned
+    buffers and the library's copy threads -- on the NUMA node its GPU hangs off, so that the ranks' host-side
+    traffic does not cross sockets.  Returns the node, or None when the topology cannot be read."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -246,6 +270,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     L = _lib.lib()
     _lib.check(L.bl_set_device(local))
     if world > 1:
@@ -410,6 +435,7 @@ def main():
         same_pg = bool(np.array_equal(x_pg[: 1 << 20], x_p[: 1 << 20].numpy()))
         del x_pg
         e2e = {"value": world * num * e_steps / dt, "unit": "draws/s", "host_memory": "pinned",
+               "rank0_numa_node": numa_node,
                "pageable": {"value": pageable["staged_by_library"], "unit": "draws/s",
                             "frac_of_pinned": pageable["staged_by_library"] / (world * num * e_steps / dt),
                             "driver_staging_value": pageable["driver_staging"],
