@@ -256,6 +256,9 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
     double *B = A + (size_t)ld * P;
     double *v = B + (size_t)ld * P;
     double *rhs = v + 4 * P;
+    // constrained draw: P^2 + 2P precomputed rejection normals behind the workspace (gibbs_beta.cuh)
+    double *nbuf = rhs + P;
+    const int nbuf_len = mode == kBetaConstrained ? P * P + 2 * P : 0;
     if (pw.world > 1) {
         // sharded data: PP and the rhs tail are the rank-ordered sums of the slots the peers pushed
         peer_wait(pw, status);
@@ -266,7 +269,7 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
         default: peer_stage<0>(pw, A, rhs, P0, base_rhs, add_tail, P, ld); break;
         }
         __syncthreads();
-        cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status);
+        cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len);
         return;
     }
     // stage PP = Gram + P0.  P <= 64: every load of the thread (16 Gram entries, 16 prior entries) is issued before
@@ -295,7 +298,7 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
 #ifdef BL_BETA_CLOCKS
     if (threadIdx.x == 0 && call == 3) printf("[beta clocks] load %lld\n", clock64() - k0);
 #endif
-    cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status);
+    cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len);
 }
 
 __global__ void k_matvec(double *out, const double *A, const double *x, int P)   // out = A x, col-major
@@ -399,7 +402,7 @@ struct Sweep {
     int *status = nullptr;
     int nt = 1, nslab = 1, nslab_diag = 0, xtv_slabs = 1;
     bool use_smem = true;
-    size_t beta_smem = 0;
+    size_t beta_smem = 0, beta_smem_tn = 0;   // workspace of the beta draw; the constrained draw adds its rejection normals
     bool exchange = false;  // sharded sweep: the Gram (+ tail) sums are exchanged between ranks before the beta draw
     PeerWait pending{};     // set by gram() when it pushed to the peers; consumed by beta_draw()
 
@@ -426,20 +429,22 @@ struct Sweep {
         GB_CK(m.get(&acc, (size_t)P * P + P));
         GB_CK(m.get(&part, (size_t)tiles * nslab * 2 * kGramTile * kGramTile));
         GB_CK(m.get(&xtv_part, (size_t)xtv_slabs * P));
-        GB_CK(m.get(&gwork, 2 * (size_t)(P + 1) * P + 5 * (size_t)P));
+        GB_CK(m.get(&gwork, 2 * (size_t)(P + 1) * P + 5 * (size_t)P + (size_t)P * P + 2 * (size_t)P));
         GB_CK(m.get(&status, 1));
         GB_CK(cudaMemsetAsync(status, 0, sizeof(int), st));
         GB_CK(cudaMemsetAsync(acc, 0, ((size_t)P * P + P) * sizeof(double), st));
+        // A, B (ld x P each), 5 P vector scratch; the constrained draw's P^2 + 2P rejection normals behind them
         beta_smem = (2 * (size_t)(P | 1) * P + 5 * (size_t)P) * sizeof(double);
+        beta_smem_tn = beta_smem + ((size_t)P * P + 2 * (size_t)P) * sizeof(double);
         GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRows, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)gram_smem_bytes(true)));
         GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRowsDiag, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)gram_smem_bytes(false)));
         GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRowsDiag, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)gram_smem_bytes(false, true)));
-        use_smem = beta_smem <= 200 * 1024;
-        if (use_smem && beta_smem > 48 * 1024)
-            GB_CK(cudaFuncSetAttribute(k_beta_draw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem));
+        use_smem = beta_smem_tn <= 200 * 1024;
+        if (use_smem && beta_smem_tn > 48 * 1024)
+            GB_CK(cudaFuncSetAttribute(k_beta_draw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem_tn));
         return 0;
     }
 
@@ -506,7 +511,7 @@ struct Sweep {
                    const double *beta_prev, double *beta_out, uint64_t seed, uint32_t call)
     {
         if (use_smem)
-            k_beta_draw<true><<<1, 256, beta_smem, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
+            k_beta_draw<true><<<1, 256, mode == kBetaConstrained ? beta_smem_tn : beta_smem, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
                                                          beta_out, gwork, P, seed, call, status, pending, 0);
         else
             k_beta_draw<false><<<1, 256, 0, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
@@ -653,7 +658,9 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
     const int64_t T = (int64_t)chains * N;
     if (T >= (1LL << 31)) { err = "logit_chains: chains * N must stay below 2^31 observations per call"; return 1; }
     if (P > 256) { err = "P > 256 covariates is not supported by the single-CTA beta draw"; return 1; }
-    const size_t beta_smem = (2 * (size_t)(P | 1) * P + 5 * (size_t)P) * sizeof(double);
+    const int mode = (flags & BL_GIBBS_PLAIN_BETA) ? kBetaPlain : kBetaConstrained;
+    const size_t beta_smem = (2 * (size_t)(P | 1) * P + 5 * (size_t)P +
+                              (mode == kBetaConstrained ? (size_t)P * P + 2 * (size_t)P : 0)) * sizeof(double);
     if (beta_smem > 200 * 1024) { err = "logit_chains: P too large for the shared-memory beta draw"; return 1; }
     DevMem mem;
     mem.st = st;
@@ -686,7 +693,6 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
     const bool packed = gram_packed(P);
     if (beta_smem > 48 * 1024)
         GB_CK(cudaFuncSetAttribute(k_beta_draw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem));
-    const int mode = (flags & BL_GIBBS_PLAIN_BETA) ? kBetaPlain : kBetaConstrained;
     const int64_t bstride = (int64_t)P * samp;
 
     // bP_c = P0 m0 + X_c'(n (y - 1/2))

@@ -216,6 +216,18 @@ __device__ inline double tnorm_std_warp(PhiloxSource &s, double a, double b, int
 // k-th normal of the beta stream (seed, obs 2^64-1, call): a normal always takes three
 // words, so the k-th one starts at word 3k -- counter-based generation lets every lane
 // jump straight to its own.
+__device__ inline double stream_normal_obs(uint64_t seed, uint64_t obs, uint32_t call, int k)
+{
+    PhiloxSource s;
+    s.open(seed, obs, call);
+    s.blk = (uint32_t)(3 * k) >> 2;
+    for (int skip = (3 * k) & 3; skip > 0; --skip) s.word();
+    return s.norm();
+}
+
+// Stream of the constrained draw's rejection normals (below): (seed, obs 2^64-3, call).
+constexpr uint64_t kTnObs = 0xFFFFFFFFFFFFFFFDull;
+
 __device__ inline double stream_normal(uint64_t seed, uint32_t call, int k)
 {
     PhiloxSource s;
@@ -397,11 +409,23 @@ __device__ inline void warp_solve_plain(const double *R, const double *rd, const
 // owned entry, a 5-stage min/max butterfly, the truncated normal, and one FMA per owned entry.
 // `is` is the permutation scratch (shared memory); all lanes draw every variate so their 32 copies
 // of the stream stay in step.
+//
+// The truncated normal itself.  Inverse CDF costs an erfc pair and an inverse normal CDF of dependent FP64 latency
+// (~2 200 cycles on one lane) per coordinate, P^2 times per beta draw.  But in a well-identified model nearly every
+// window (cmin, cmax) is wide -- the constraint beta_j >= 0 binds only for coefficients near zero -- and for a wide
+// window plain rejection from N(0,1) is exact and almost always accepts at the first try.  So: when
+// cmin < 1, cmax > -1 and cmax - cmin >= 1/2, take up to four normals from their own stream (seed, obs 2^64-3, call),
+// normal number m at words 3m..3m+2, PRECOMPUTED in parallel by the whole CTA before the sweeps (nbuf; past its end
+// they are generated on the spot), and return the first one inside the window; otherwise, or after four misses, the
+// inverse-CDF / tail sampler on the beta stream as before.  Every branch returns an exact truncated normal, so the
+// draw's distribution is unchanged; the oracle (draw_beta_constrained) mirrors the rule variate for variate.
 template <int KP>
 __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const double *iL, const double *z_in,
                                                         const double *beta_prev, double *beta_out, int *is,
-                                                        PhiloxSource &src, int P, int ld, int lane)
+                                                        PhiloxSource &src, int P, int ld, int lane,
+                                                        const double *nbuf, int nbuf_len, uint64_t seed, uint32_t call)
 {
+    int mnorm = 0;                         // normals of the rejection stream consumed so far (warp-uniform)
     double beta[KP], z[KP];
 #pragma unroll
     for (int q = 0; q < KP; ++q) {
@@ -443,7 +467,16 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
                 if (a > cmin) cmin = a;
                 if (b < cmax) cmax = b;
             }
-            const double z2 = tnorm_std_warp(src, cmin, cmax, lane);
+            double z2 = 0.0;
+            bool got = false;
+            if (cmin < cmax && cmin < 1.0 && cmax > -1.0 && cmax - cmin >= 0.5) {
+                for (int tr = 0; tr < 4 && !got; ++tr) {
+                    const double Z = mnorm < nbuf_len ? nbuf[mnorm] : stream_normal_obs(seed, kTnObs, call, mnorm);
+                    ++mnorm;
+                    if (Z > cmin && Z < cmax) { z2 = Z; got = true; }
+                }
+            }
+            if (!got) z2 = tnorm_std_warp(src, cmin, cmax, lane);
             const double dz = z2 - z1;
 #pragma unroll
             for (int q = 0; q < KP; ++q) {
@@ -467,7 +500,7 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
 // rhs = bP (precision-weighted mean), beta_prev (constrained only), beta_out.
 __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, double *v, const double *rhs,
                                      const double *beta_prev, double *beta_out, int P, int ld,
-                                     uint64_t seed, uint32_t call, int *status)
+                                     uint64_t seed, uint32_t call, int *status, double *nbuf = nullptr, int nbuf_len = 0)
 {
     __shared__ int ok;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -546,12 +579,14 @@ __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, do
         int j = e2 % P, c = e2 / P;
         if (j >= c) iL[j + (size_t)ld * c] = 1.0 / L[j + (size_t)ld * c];
     }
+    // the rejection normals of the sweeps (see warp_constrained_sweeps), all threads
+    for (int m = tid; m < nbuf_len; m += blockDim.x) nbuf[m] = stream_normal_obs(seed, kTnObs, call, m);
     __syncthreads();
     if (tid < 32) {
         int *is = (int *)e;                  // the permutation lives in the e[] scratch as ints
-        if (P <= 64) warp_constrained_sweeps<2>(L, iL, z, beta_prev, beta_out, is, src, P, ld, lane);
-        else if (P <= 128) warp_constrained_sweeps<4>(L, iL, z, beta_prev, beta_out, is, src, P, ld, lane);
-        else warp_constrained_sweeps<8>(L, iL, z, beta_prev, beta_out, is, src, P, ld, lane);
+        if (P <= 64) warp_constrained_sweeps<2>(L, iL, z, beta_prev, beta_out, is, src, P, ld, lane, nbuf, nbuf_len, seed, call);
+        else if (P <= 128) warp_constrained_sweeps<4>(L, iL, z, beta_prev, beta_out, is, src, P, ld, lane, nbuf, nbuf_len, seed, call);
+        else warp_constrained_sweeps<8>(L, iL, z, beta_prev, beta_out, is, src, P, ld, lane, nbuf, nbuf_len, seed, call);
     }
     __syncthreads();
 }

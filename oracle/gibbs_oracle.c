@@ -166,9 +166,19 @@ static int draw_beta_plain(double *beta, double *PP, const double *bP, int P, pg
 
 /* Constrained coordinate-wise draw, beta_j >= 0 for j < P-1 (the variant the
  * reference actually calls, Logit.hpp:322-400 via :429). */
+/* The truncated normal of the coordinate sweeps (r.tnorm at Logit.hpp:393 lives in the reference's absent RNG
+ * library, so the construction is this project's; any exact sampler restates it).  Wide windows -- cmin < 1,
+ * cmax > -1, cmax - cmin >= 1/2 -- try plain rejection from N(0,1) first: up to four normals from the stream
+ * (seed, obs 2^64-3, call), consumed in order; the first one inside (cmin, cmax) is the draw.  Otherwise, or after
+ * four misses, pgo_tnorm (inverse CDF / Robert's tail samplers) on the beta stream.  The engine precomputes the
+ * rejection normals in parallel, which is the point of the rule (gibbs_beta.cuh). */
+#define TN_OBS 0xFFFFFFFFFFFFFFFDull
+
 static int draw_beta_constrained(double *beta, double *PP, const double *bP, const double *beta_prev,
-                                 int P, pgo_src *s)
+                                 int P, pgo_src *s, uint64_t seed, uint32_t call)
 {
+    pgo_src sn;
+    pgo_src_philox(&sn, seed, TN_OBS, call);
     if (chol_upper(PP, P)) return 1;
     double *S = (double *)calloc((size_t)P * P, sizeof(double));
     double *mP = (double *)malloc(sizeof(double) * P);
@@ -208,7 +218,14 @@ static int draw_beta_constrained(double *beta, double *PP, const double *bP, con
                     if (l1 > 0.0 && c1 > cmin) cmin = c1;
                     else if (l1 < 0.0 && c1 < cmax) cmax = c1;
                 }
-                double z2 = pgo_tnorm(s, cmin, cmax, 0.0, 1.0);
+                double z2 = 0.0;
+                int got = 0;
+                if (cmin < cmax && cmin < 1.0 && cmax > -1.0 && cmax - cmin >= 0.5)
+                    for (int tr = 0; tr < 4 && !got; ++tr) {
+                        double Z = pgo_norm(&sn);
+                        if (Z > cmin && Z < cmax) { z2 = Z; got = 1; }
+                    }
+                if (!got) z2 = pgo_tnorm(s, cmin, cmax, 0.0, 1.0);
                 z[c] = z2;
                 for (unsigned j = c; j < (unsigned)P; ++j) beta[j] += L[j + (size_t)P * c] * (z2 - z1);
             }
@@ -260,7 +277,7 @@ int pgb_logit_gibbs(double *w, double *beta, const double *y, const double *tX, 
             weighted_gram(PP, P0, tX, wcur, N, P, nthreads);
             pgo_src sb;
             pgo_src_philox(&sb, seed, BETA_OBS, t);
-            status = constrained ? draw_beta_constrained(bnew, PP, bP, bprev, P, &sb)
+            status = constrained ? draw_beta_constrained(bnew, PP, bP, bprev, P, &sb, seed, t)
                                  : draw_beta_plain(bnew, PP, bP, P, &sb);
             memcpy(bcur, bnew, sizeof(double) * P);
             xbeta(psi, tX, bcur, N, P, nthreads);

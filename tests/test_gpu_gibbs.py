@@ -95,12 +95,14 @@ def test_logit_burn_zero_and_no_w(gapi):
 
 
 @pytest.mark.parametrize("constrained", [False, True])
-@pytest.mark.parametrize("chains,N,P", [(7, 900, 5), (3, 2101, 32), (2, 515, 70)])
+@pytest.mark.parametrize("chains,N,P", [(7, 900, 5), (3, 2101, 32), (2, 2115, 70)])
 def test_batched_chains_match_oracle_chain_by_chain(gapi, constrained, chains, N, P):
     """BASELINE config 5 (independent chains) at oracle-sized shapes: chain c
     of the batch equals the oracle's chain on its rows with seed + c, and the engine's own
     single-chain entry point with that seed.  N not a multiple of 32 and P > 64 (several Gram
-    tiles) are covered."""
+    tiles) are covered.  (N >= 30 P: with N = 7 P the constrained chain's map amplifies last-bit differences
+    from 1e-16 to 1e-6 within eight iterations -- conditioning of the test problem, see the note at
+    test_logit_chain_matches_oracle.)"""
     data = [synth_logit(N, P, 100 + 7 * c + P, binomial=(c % 2 == 1)) for c in range(chains)]
     X = np.stack([d[0] for d in data]); y = np.stack([d[1] for d in data]); n = np.stack([d[2] for d in data])
     m0 = np.linspace(-0.1, 0.1, P)
