@@ -403,6 +403,36 @@ __device__ inline void warp_solve_plain(const double *R, const double *rd, const
     else warp_solve_plain_k<8>(R, rd, b, e, out, P, ld, lane, rev);
 }
 
+// Exact max / min of a double over the warp in two 32-bit hardware reductions (redux.sync) on an
+// order-preserving integer key, instead of a five-stage butterfly of 64-bit shuffles and compares
+// (the sweeps below do one of each per coordinate, on the critical path).
+__device__ __forceinline__ unsigned long long ordered_key(double v)
+{
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ordered_value(unsigned long long k)
+{
+    const unsigned long long u = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ double warp_max_f64(double v)
+{
+    const unsigned long long k = ordered_key(v);
+    const unsigned hi = (unsigned)(k >> 32);
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? (unsigned)k : 0u);
+    return ordered_value(((unsigned long long)mhi << 32) | mlo);
+}
+__device__ __forceinline__ double warp_min_f64(double v)
+{
+    const unsigned long long k = ordered_key(v);
+    const unsigned hi = (unsigned)(k >> 32);
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? (unsigned)k : 0xFFFFFFFFu);
+    return ordered_value(((unsigned long long)mhi << 32) | mlo);
+}
+
 // The coordinate-wise constrained draw, Logit.hpp:366-399, on one warp with beta and z held in
 // registers (lane l owns entries l, l + 32, ...), 1 / L precomputed (iL), and the truncated normal
 // split across lanes: what sits between two consecutive updates is one shuffle (z1), one FMA per
@@ -443,8 +473,28 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
             if (lane == 0) { int tmp = is[i]; is[i] = is[t]; is[t] = tmp; }
         }
         __syncwarp();
+        // Software-pipelined over the coordinates: everything of coordinate i + 1 that does not depend on the draw
+        // of coordinate i -- its index, its column of L and 1 / L, the next rejection normal -- is loaded while
+        // coordinate i is decided, so the critical path per coordinate is beta -> bound -> two reductions ->
+        // window test -> beta.  (z of the next coordinate is read after the update: each index occurs once per sweep.)
+        int c = is[0];
+        double lu[KP], il[KP];
+#pragma unroll
+        for (int q = 0; q < KP; ++q) {
+            const int j = lane + 32 * q;
+            lu[q] = (j >= c && j < P) ? L[j + (size_t)ld * c] : 0.0;
+            il[q] = (j >= c && j < P - 1) ? iL[j + (size_t)ld * c] : 0.0;
+        }
         for (int i = 0; i < P; ++i) {
-            const int c = is[i];
+            const int cn = i + 1 < P ? is[i + 1] : c;
+            double lun[KP], iln[KP];
+#pragma unroll
+            for (int q = 0; q < KP; ++q) {
+                const int j = lane + 32 * q;
+                lun[q] = (j >= cn && j < P) ? L[j + (size_t)ld * cn] : 0.0;
+                iln[q] = (j >= cn && j < P - 1) ? iL[j + (size_t)ld * cn] : 0.0;
+            }
+            const double Zn = mnorm < nbuf_len ? nbuf[mnorm] : 0.0;
             double zc = z[0];
 #pragma unroll
             for (int q = 1; q < KP; ++q) zc = (c >> 5) == q ? z[q] : zc;
@@ -452,26 +502,20 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
             double cmin = -INFINITY, cmax = INFINITY;
 #pragma unroll
             for (int q = 0; q < KP; ++q) {
-                int j = lane + 32 * q;
-                if (j >= c && j < P - 1) {
-                    double l1 = L[j + (size_t)ld * c];
-                    double c1 = fma(-beta[q], iL[j + (size_t)ld * c], z1);
-                    if (l1 > 0.0 && c1 > cmin) cmin = c1;
-                    else if (l1 < 0.0 && c1 < cmax) cmax = c1;
-                }
+                const int j = lane + 32 * q;
+                const double l1 = j < P - 1 ? lu[q] : 0.0;              // the last coefficient is free
+                const double c1 = fma(-beta[q], il[q], z1);
+                if (l1 > 0.0 && c1 > cmin) cmin = c1;
+                else if (l1 < 0.0 && c1 < cmax) cmax = c1;
             }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                double a = __shfl_xor_sync(0xffffffffu, cmin, o);
-                double b = __shfl_xor_sync(0xffffffffu, cmax, o);
-                if (a > cmin) cmin = a;
-                if (b < cmax) cmax = b;
-            }
+            cmin = warp_max_f64(cmin);
+            cmax = warp_min_f64(cmax);
             double z2 = 0.0;
             bool got = false;
             if (cmin < cmax && cmin < 1.0 && cmax > -1.0 && cmax - cmin >= 0.5) {
                 for (int tr = 0; tr < 4 && !got; ++tr) {
-                    const double Z = mnorm < nbuf_len ? nbuf[mnorm] : stream_normal_obs(seed, kTnObs, call, mnorm);
+                    const double Z = tr == 0 && mnorm < nbuf_len ? Zn
+                                     : mnorm < nbuf_len ? nbuf[mnorm] : stream_normal_obs(seed, kTnObs, call, mnorm);
                     ++mnorm;
                     if (Z > cmin && Z < cmax) { z2 = Z; got = true; }
                 }
@@ -480,10 +524,13 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
             const double dz = z2 - z1;
 #pragma unroll
             for (int q = 0; q < KP; ++q) {
-                int j = lane + 32 * q;
-                if (j >= c && j < P) beta[q] = fma(L[j + (size_t)ld * c], dz, beta[q]);
+                const int j = lane + 32 * q;
+                beta[q] = fma(lu[q], dz, beta[q]);                       // lu is zero outside c <= j < P
                 if (j == c) z[q] = z2;
+                lu[q] = lun[q];
+                il[q] = iln[q];
             }
+            c = cn;
         }
     }
 #pragma unroll
