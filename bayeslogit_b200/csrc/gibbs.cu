@@ -234,6 +234,12 @@ int small_allreduce(void *buf, size_t cnt, SmallOp op, int *status, cudaStream_t
 // PP = acc + P0; rhs = base_rhs (+ acc tail); then the draw.
 // SMEM = true: the workspace is the CTA's shared memory (address space known to the compiler ->
 // LDS/STS); false: global scratch for P too large for shared memory.
+#ifdef BL_BETA_SLOW
+constexpr bool kSlowBeta = true;          // A/B build: the panel factorisation of cta_ldl_upper for every P
+#else
+constexpr bool kSlowBeta = false;
+#endif
+
 template <bool SMEM>
 __global__ void __launch_bounds__(256)
 k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__ P0,
@@ -259,6 +265,10 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
     // constrained draw: P^2 + 2P precomputed rejection normals behind the workspace (gibbs_beta.cuh)
     double *nbuf = rhs + P;
     const int nbuf_len = mode == kBetaConstrained ? P * P + 2 * P : 0;
+    // plain / mvn draw with P <= 64: the padded layout of cta_plain_fast (its normals live behind the workspace)
+    const bool fast = SMEM && !kSlowBeta && mode != kBetaConstrained && P <= 64;
+    double *efast = fast ? sm + beta_fast_e_offset(P) : nullptr;
+    const bool rev = mode == kBetaMvn;
     if (pw.world > 1) {
         // sharded data: PP and the rhs tail are the rank-ordered sums of the slots the peers pushed
         peer_wait(pw, status);
@@ -269,7 +279,43 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
         default: peer_stage<0>(pw, A, rhs, P0, base_rhs, add_tail, P, ld); break;
         }
         __syncthreads();
-        cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len);
+        cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len, efast);
+        return;
+    }
+    if (fast) {
+        // straight into the padded layout: element (i = tid & 63, column (tid >> 6) + 4 u), every load issued
+        // before the first is consumed; the mvn draw reads the index-reversed system
+        const BetaFast w(sm, P);
+        const int i = threadIdx.x & 63, cb = threadIdx.x >> 6;
+        double g[16], q[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int c = cb + 4 * u;
+            const bool in = i < P && c < P;
+            const int k = rev ? (P - 1 - i) + P * (P - 1 - c) : i + P * c;
+            g[u] = in ? __ldcg(acc + k) : (i == c ? 1.0 : 0.0);
+            q[u] = (in && P0) ? __ldg(P0 + k) : 0.0;
+        }
+        double rr = 0.0;
+        if ((int)threadIdx.x < P) {
+            const int k = rev ? P - 1 - (int)threadIdx.x : (int)threadIdx.x;
+            rr = (base_rhs ? base_rhs[k] : 0.0) + (add_tail ? __ldcg(acc + (size_t)P * P + k) : 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int c = cb + 4 * u;
+            if (i < w.Pp && c < w.Pp) w.F[i + w.LD * c] = g[u] + q[u];
+        }
+        if ((int)threadIdx.x < w.Pp) w.F[threadIdx.x + w.LD * w.Pp] = rr;
+        if (threadIdx.x < 56) w.Sn[(threadIdx.x / 7) * kFastLdS + w.Pp + 1 + threadIdx.x % 7] = 0.0;
+        __shared__ int ok_fast;
+        if (threadIdx.x == 0) ok_fast = 1;
+        __syncthreads();
+#ifdef BL_BETA_CLOCKS
+        if (threadIdx.x == 0 && call == 3) printf("[beta clocks] load %lld\n", clock64() - k0);
+#endif
+        cta_plain_fast(sm, efast, beta_out, P, rev, &ok_fast, seed, call);
+        if (!ok_fast && threadIdx.x == 0) *status = 1;
         return;
     }
     // stage PP = Gram + P0.  P <= 64: every load of the thread (16 Gram entries, 16 prior entries) is issued before
@@ -435,6 +481,7 @@ struct Sweep {
         GB_CK(cudaMemsetAsync(acc, 0, ((size_t)P * P + P) * sizeof(double), st));
         // A, B (ld x P each), 5 P vector scratch; the constrained draw's P^2 + 2P rejection normals behind them
         beta_smem = (2 * (size_t)(P | 1) * P + 5 * (size_t)P) * sizeof(double);
+        if (P <= 64) beta_smem = (beta_fast_e_offset(P) + 64) * sizeof(double);      // cta_plain_fast: + its normals
         beta_smem_tn = beta_smem + ((size_t)P * P + 2 * (size_t)P) * sizeof(double);
         GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRows, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)gram_smem_bytes(true)));
@@ -510,7 +557,9 @@ struct Sweep {
     void beta_draw(int mode, const double *P0, const double *base_rhs, bool add_tail,
                    const double *beta_prev, double *beta_out, uint64_t seed, uint32_t call)
     {
+        static const int twice = getenv("BL_BETA_TWICE") ? 2 : 1;      // measurement aid: the second launch finds its code cached
         if (use_smem)
+            for (int r = 0; r < twice; ++r)
             k_beta_draw<true><<<1, 256, mode == kBetaConstrained ? beta_smem_tn : beta_smem, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
                                                          beta_out, gwork, P, seed, call, status, pending, 0);
         else
@@ -659,8 +708,9 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
     if (T >= (1LL << 31)) { err = "logit_chains: chains * N must stay below 2^31 observations per call"; return 1; }
     if (P > 256) { err = "P > 256 covariates is not supported by the single-CTA beta draw"; return 1; }
     const int mode = (flags & BL_GIBBS_PLAIN_BETA) ? kBetaPlain : kBetaConstrained;
-    const size_t beta_smem = (2 * (size_t)(P | 1) * P + 5 * (size_t)P +
-                              (mode == kBetaConstrained ? (size_t)P * P + 2 * (size_t)P : 0)) * sizeof(double);
+    const size_t beta_smem = std::max((2 * (size_t)(P | 1) * P + 5 * (size_t)P +
+                                       (mode == kBetaConstrained ? (size_t)P * P + 2 * (size_t)P : 0)) * sizeof(double),
+                                      P <= 64 ? (beta_fast_e_offset(P) + 64) * sizeof(double) : (size_t)0);
     if (beta_smem > 200 * 1024) { err = "logit_chains: P too large for the shared-memory beta draw"; return 1; }
     DevMem mem;
     mem.st = st;

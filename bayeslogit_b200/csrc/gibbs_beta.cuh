@@ -403,6 +403,251 @@ __device__ inline void warp_solve_plain(const double *R, const double *rd, const
     else warp_solve_plain_k<8>(R, rd, b, e, out, P, ld, lane, rev);
 }
 
+
+// ---- plain / mvn draw for P <= 64: blocked factorisation with look-ahead ----------------------------------------
+// The panel loop of cta_ldl_upper costs ~3 900 cycles per 8 columns at P = 64 (BL_BETA_CLOCKS: 31 000 cycles for the
+// factorisation, 12 600 for the two substitutions), most of it one warp's diagonal-block recurrence with the other
+// seven waiting, then everyone's trailing update with that warp's result.  Here:
+//   * the matrix is padded to a multiple of 8 with an identity block, so every panel is a full 8 x 8;
+//   * the right-hand side rides along as column Pp: the panel step applied to it IS the forward substitution;
+//   * the trailing update runs on the FP64 tensor path, one 8 x 8 tile = two DMMA m8n8k4 (A = the panel's rows,
+//     B = the same rows scaled by -1/d, kept in a side buffer by the panel step);
+//   * look-ahead: warp 0 updates the NEXT diagonal tile first and factorises it while warps 1-7 finish the other
+//     tiles, so the serial recurrence (8 pivots x ~185 cycles) overlaps the bulk of the update.
+// Workspace W: F [LD x (Pp + 8)] column-major, LD = Pp + 1 (odd); Sn [8 x 76]; rd [64]; e [64].
+constexpr int kFastLdS = 76;                  // row stride of Sn: 4 tig + gid distinct mod 16 -> conflict-free B fragments
+
+__host__ __device__ inline size_t beta_fast_doubles(int P)           // F, Sn, rd
+{
+    const int Pp = (P + 7) & ~7;
+    return (size_t)(Pp + 1) * (Pp + 8) + 8 * kFastLdS + 64;
+}
+// doubles of the CTA's workspace in front of the fast path's normals e[64]: the longer of the two layouts
+__host__ __device__ inline size_t beta_fast_e_offset(int P)
+{
+    const size_t plain = 2 * (size_t)(P | 1) * P + 5 * (size_t)P, fast = beta_fast_doubles(P);
+    return plain > fast ? plain : fast;
+}
+
+__device__ __forceinline__ void beta_dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// 1 / d as rcp_newton, with ONE third-order step on the 20-bit hardware seed (error e^3 < 2^-58): three dependent
+// operations instead of four -- it sits on the critical path of every pivot.
+__device__ __forceinline__ double rcp_newton3(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    const double e = fma(-d, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
+}
+
+// The 8 x 8 diagonal block at (k0, k0) in one warp's registers: lane (i = lane >> 3, k = lane & 7) holds rows i and
+// i + 4 of column k; a step broadcasts the pivot and the pivot row by shuffles.  Writes the block's rows of R and rd.
+__device__ __forceinline__ bool warp_ldl_diag8(double *F, double *rd, int k0, int LD, int lane)
+{
+    const int i = lane >> 3, k = lane & 7;
+    double a0 = F[(k0 + i) + LD * (k0 + k)];
+    double a1 = F[(k0 + i + 4) + LD * (k0 + k)];
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int src = (j & 3) * 8;
+        const double vj = j < 4 ? a0 : a1;
+        const double d = __shfl_sync(0xffffffffu, vj, src + j);
+        bad = bad || !(d > 0.0);
+        const double inv = rcp_newton3(d);
+        if (lane == 0) rd[k0 + j] = inv;
+        const double s = __shfl_sync(0xffffffffu, vj, src + k) * inv;
+        const double rji = __shfl_sync(0xffffffffu, vj, src + i);
+        const double rji4 = __shfl_sync(0xffffffffu, vj, src + i + 4);
+        if (i > j && i <= k) a0 = fma(-rji, s, a0);
+        if (i + 4 > j && i + 4 <= k) a1 = fma(-rji4, s, a1);
+    }
+    if (i <= k) F[(k0 + i) + LD * (k0 + k)] = a0;
+    if (i + 4 <= k) F[(k0 + i + 4) + LD * (k0 + k)] = a1;
+    return !bad;
+}
+
+// Workspace split of the fast path (doubles from the start of the CTA's workspace); the normals e[64] live behind
+// whichever of the two layouts is longer (k_beta_draw computes them before the matrix arrives).
+struct BetaFast {
+    double *F, *Sn, *rd;
+    int Pp, LD, nblk;
+    __device__ __forceinline__ BetaFast(double *W, int P)
+    {
+        Pp = (P + 7) & ~7; LD = Pp + 1; nblk = Pp >> 3;
+        F = W; Sn = F + LD * (Pp + 8); rd = Sn + 8 * kFastLdS;
+    }
+};
+
+// A (ld, P x P, full symmetric) and rhs, both in the CTA's workspace, -> the padded layout, which overlays them:
+// through registers, element (i = tid & 63, column (tid >> 6) + 4 u).  256 threads.
+__device__ __forceinline__ void beta_fast_relayout(double *W, const double *A, int ld, const double *rhs, int P)
+{
+    const BetaFast w(W, P);
+    const int tid = threadIdx.x, i = tid & 63, cb = tid >> 6;
+    double g[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const int c = cb + 4 * u;
+        g[u] = (i < P && c < P) ? A[i + (size_t)ld * c] : (i == c ? 1.0 : 0.0);
+    }
+    const double rr = tid < P ? rhs[tid] : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const int c = cb + 4 * u;
+        if (i < w.Pp && c < w.Pp) w.F[i + w.LD * c] = g[u];
+    }
+    if (tid < w.Pp) w.F[tid + w.LD * w.Pp] = rr;
+    if (tid < 56) w.Sn[(tid / 7) * kFastLdS + w.Pp + 1 + tid % 7] = 0.0;       // the rhs tile's seven unused columns
+    __syncthreads();
+}
+
+// The factorisation and both substitutions on the padded layout (F, rhs column and Sn padding in place; the caller
+// has synchronised).  256 threads: warps 0-6 factorise (named barrier 1 over their 224 threads), warp 7 produces the
+// P normals of the draw meanwhile (~5 000 cycles of one thread's latency, needed only by the backward substitution).
+// `rev`: the system is the index-reversed one (mvn draw).
+__device__ __forceinline__ void cta_plain_fast(double *W, double *e, double *beta_out, int P, bool rev, int *ok,
+                                               uint64_t seed, uint32_t call)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const BetaFast w(W, P);
+    double *F = w.F, *Sn = w.Sn, *rd = w.rd;
+    const int Pp = w.Pp, LD = w.LD, nblk = w.nblk;
+#ifdef BL_BETA_CLOCKS
+    long long ck[40]; int nck = 0;
+    ck[nck++] = clock64();
+#define BL_CK() ck[nck++] = clock64()
+#else
+#define BL_CK()
+#endif
+#define BL_BAR7() asm volatile("bar.sync 1, 224;" ::: "memory")
+    if (warp == 7) {
+        for (int m = lane; m < Pp; m += 32) e[m] = m < P ? stream_normal(seed, call, rev ? P - 1 - m : m) : 0.0;
+    } else {
+        if (warp == 0 && !warp_ldl_diag8(F, rd, 0, LD, lane)) *ok = 0;
+        BL_CK();
+        BL_BAR7();
+        const int gid = lane >> 2, tig = lane & 3;
+        for (int p = 0; p < nblk; ++p) {
+            const int k0 = 8 * p, kend = k0 + 8;
+            // panel rows of every column right of the block, the rhs column (index Pp) included: one thread per column
+            {
+                const int k = kend + tid;
+                if (k <= Pp) {
+                    double r[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = F[(k0 + j) + LD * k];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const double s = r[j] * rd[k0 + j];
+                        Sn[j * kFastLdS + k] = -s;
+#pragma unroll
+                        for (int j2 = j + 1; j2 < 8; ++j2) r[j2] = fma(-F[(k0 + j) + LD * (k0 + j2)], s, r[j2]);
+                    }
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) F[(k0 + j) + LD * k] = r[j];
+                }
+            }
+            BL_CK();
+            BL_BAR7();
+            if (!*ok) break;
+            if (warp == 0) {
+                if (p + 1 < nblk) {
+                    // look-ahead: the next diagonal tile, updated in the factorisation's own register layout (two
+                    // chains of four FMAs per entry), then factorised while warps 1-6 update the other tiles
+                    const int i = lane >> 3, k = lane & 7;
+                    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const double s0 = Sn[j * kFastLdS + kend + k], s1 = Sn[(j + 1) * kFastLdS + kend + k];
+                        a0 = fma(F[(k0 + j) + LD * (kend + i)], s0, a0);
+                        b0 = fma(F[(k0 + j + 1) + LD * (kend + i)], s1, b0);
+                        a1 = fma(F[(k0 + j) + LD * (kend + i + 4)], s0, a1);
+                        b1 = fma(F[(k0 + j + 1) + LD * (kend + i + 4)], s1, b1);
+                    }
+                    F[(kend + i) + LD * (kend + k)] += a0 + b0;
+                    F[(kend + i + 4) + LD * (kend + k)] += a1 + b1;
+                    __syncwarp();
+                    BL_CK();
+                    if (!warp_ldl_diag8(F, rd, kend, LD, lane)) *ok = 0;
+                }
+            } else {
+                // The block's columns are final and no later step reads them: scale them by their pivots'
+                // reciprocals for the backward substitution (a step there is then one shuffle and one FMA:
+                // x_m -= (R[m,i] rd_i) x_i(raw), with x_i = rd_i x_i(raw) off the critical path).
+                for (int el = tid - 32; el < 8 * 64; el += 192) {
+                    const int col = k0 + (el >> 6), m = el & 63;
+                    if (m < col) F[m + LD * col] *= rd[col];
+                }
+                // trailing tiles (ti, tk), p < ti <= tk <= nblk (tk = nblk: the rhs column's tile), row block by
+                // row block, dealt round-robin to warps 1-6; tile 0 is warp 0's
+                const int nrem = nblk - (p + 1);
+                const int T = nrem * (nrem + 1) / 2 + nrem;
+                int a = 0, base = 0;                                           // base = first tile index of row block a
+                for (int q = warp; q < T; q += 6) {
+                    while (q >= base + (nrem - a + 1)) { base += nrem - a + 1; ++a; }
+                    const int ti = p + 1 + a, tk = ti + (q - base);
+                    double *c = F + (8 * ti + gid) + LD * (8 * tk + 2 * tig);
+                    double c0 = c[0], c1 = c[LD];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        beta_dmma884(c0, c1, F[(k0 + 4 * h + tig) + LD * (8 * ti + gid)], Sn[(4 * h + tig) * kFastLdS + 8 * tk + gid]);
+                    c[0] = c0; c[LD] = c1;
+                }
+            }
+            BL_CK();
+            if (p + 1 < nblk) BL_BAR7();
+        }
+    }
+    __syncthreads();
+    BL_CK();
+    if (!*ok) return;
+    // column Pp holds y = the forward substitution.  Backward: R x = y + e / sqrt(rd), x in one warp's registers.
+    if (warp == 0) {
+        double x[2], rdl[2];
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+            const int m = lane + 32 * qq;
+            rdl[qq] = m < Pp ? rd[m] : 1.0;
+            x[qq] = m < Pp ? F[m + LD * Pp] + e[m] / sqrt(rdl[qq]) : 0.0;
+        }
+        for (int i = Pp - 1; i >= 0; --i) {
+            const double own = (i >> 5) ? x[1] : x[0];
+            double rr[2];
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+                const int m = lane + 32 * qq;
+                rr[qq] = m < i ? F[m + LD * i] : 0.0;
+            }
+            const double xi = __shfl_sync(0xffffffffu, own, i & 31);
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) x[qq] = fma(-rr[qq], xi, x[qq]);     // rr is zero at and below the diagonal
+        }
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+            const int m = lane + 32 * qq;
+            if (m < P) beta_out[rev ? P - 1 - m : m] = x[qq] * rdl[qq];
+        }
+    }
+#ifdef BL_BETA_CLOCKS
+    BL_CK();
+    if (tid == (call == 3 ? 0 : 32) && (call == 3 || call == 4)) {
+        printf("[beta fast clocks] tid %d:", tid);
+        for (int q = 1; q < nck; ++q) printf(" %lld", ck[q] - ck[q - 1]);
+        printf("\n");
+    }
+#endif
+    __syncthreads();
+#undef BL_BAR7
+}
+
 // Exact max / min of a double over the warp in two 32-bit hardware reductions (redux.sync) on an
 // order-preserving integer key, instead of a five-stage butterfly of 64-bit shuffles and compares
 // (the sweeps below do one of each per coordinate, on the critical path).
@@ -547,7 +792,8 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
 // rhs = bP (precision-weighted mean), beta_prev (constrained only), beta_out.
 __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, double *v, const double *rhs,
                                      const double *beta_prev, double *beta_out, int P, int ld,
-                                     uint64_t seed, uint32_t call, int *status, double *nbuf = nullptr, int nbuf_len = 0)
+                                     uint64_t seed, uint32_t call, int *status, double *nbuf = nullptr, int nbuf_len = 0,
+                                     double *efast = nullptr)
 {
     __shared__ int ok;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -577,6 +823,18 @@ __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, do
             }
             for (int k = tid; k < P / 2; k += blockDim.x) { const double t = rw[k]; rw[k] = rw[P - 1 - k]; rw[P - 1 - k] = t; }
             __syncthreads();
+        }
+        if (efast) {
+#ifdef BL_BETA_CLOCKS
+            long long f0 = clock64();
+#endif
+            beta_fast_relayout(A, A, ld, rhs, P);
+            cta_plain_fast(A, efast, beta_out, P, rev, &ok, seed, call);
+            if (!ok && tid == 0) *status = 1;
+#ifdef BL_BETA_CLOCKS
+            if (tid == 0 && call == 3) printf("[beta clocks] fast path %lld\n", clock64() - f0);
+#endif
+            return;
         }
         double *rd = z;
 #ifdef BL_BETA_CLOCKS
