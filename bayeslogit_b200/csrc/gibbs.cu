@@ -248,6 +248,10 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
             PeerWait pw, int64_t chain_stride)
 {
     extern __shared__ double sm[];
+    // programmatic dependent launch (Sweep::beta_draw; no-ops otherwise): the next kernel's CTAs may be scheduled
+    // from now on (they wait for this grid's completion themselves), and this one waits for the sums' producer
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // batched independent chains: blockIdx.x = chain (own sums, own rhs, own beta, seed + chain; P0 shared)
     acc += (size_t)blockIdx.x * ((size_t)P * P + P);
     if (base_rhs) base_rhs += (size_t)blockIdx.x * P;
@@ -557,12 +561,22 @@ struct Sweep {
     void beta_draw(int mode, const double *P0, const double *base_rhs, bool add_tail,
                    const double *beta_prev, double *beta_out, uint64_t seed, uint32_t call)
     {
-        static const int twice = getenv("BL_BETA_TWICE") ? 2 : 1;      // measurement aid: the second launch finds its code cached
-        if (use_smem)
-            for (int r = 0; r < twice; ++r)
-            k_beta_draw<true><<<1, 256, mode == kBetaConstrained ? beta_smem_tn : beta_smem, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
-                                                         beta_out, gwork, P, seed, call, status, pending, 0);
-        else
+        if (use_smem) {
+            // programmatic dependent launch: the CTA is scheduled while the kernel that produces the sums drains and
+            // waits for its completion on the device (griddepcontrol.wait at the top of k_beta_draw) -- the launch
+            // latency of the one kernel that sits between two sweeps leaves the critical path
+            static const bool pdl = getenv("BL_GIBBS_NO_PDL") == nullptr;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(1); cfg.blockDim = dim3(256);
+            cfg.dynamicSmemBytes = mode == kBetaConstrained ? beta_smem_tn : beta_smem;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+            cudaLaunchKernelEx(&cfg, k_beta_draw<true>, mode, (const double *)acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
+                               beta_out, gwork, P, seed, call, status, pending, (int64_t)0);
+        } else
             k_beta_draw<false><<<1, 256, 0, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
                                                   beta_out, gwork, P, seed, call, status, pending, 0);
         pending = PeerWait{};

@@ -173,8 +173,10 @@ k_logit_sweep(const __grid_constant__ CUtensorMap tmap, SweepArgs a, PeerPush px
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // programmatic dependent launch: everything above is independent of the kernel before this one
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x < 64)
-        asm volatile("st.shared.f64 [%0], %1;" ::"r"(beta_sm + 8 * threadIdx.x), "d"((int)threadIdx.x < a.P ? __ldg(a.beta + threadIdx.x) : 0.0) : "memory");
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(beta_sm + 8 * threadIdx.x), "d"((int)threadIdx.x < a.P ? __ldcg(a.beta + threadIdx.x) : 0.0) : "memory");
     // boxes past P are never written by TMA: zero them once in every stage (generic-proxy stores, ordered
     // before any read by the barrier below; TMA never touches them)
     if (nboxes < 4) {
@@ -433,7 +435,24 @@ cudaError_t LogitSweep::launch(double *w_out, double *PP, const int *shape, cons
     PeerPush pxc = px;
     void *args[] = {map, &a, &pxc};
     const int threads = 32 * (1 + gram_warps + draw_warps);
-    cudaError_t e = cudaLaunchCooperativeKernel(gram_warps == 16 ? (const void *)k_logit_sweep<16> : (const void *)k_logit_sweep<8>, dim3(grid), dim3(threads), args, smem, stream);
+    const void *fn = gram_warps == 16 ? (const void *)k_logit_sweep<16> : (const void *)k_logit_sweep<8>;
+    // Cooperative AND programmatic dependent launch: the CTAs are scheduled while the beta draw before them still
+    // runs -- barrier set-up and the first TMA loads of X do not depend on beta; every thread passes
+    // griddepcontrol.wait before beta is read or anything is written.  Drivers that refuse the combination get
+    // the plain cooperative launch.
+    static int pdl = getenv("BL_GIBBS_NO_PDL") ? 0 : 1;
+    cudaError_t e = cudaErrorNotSupported;
+    if (pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 2;
+        e = cudaLaunchKernelExC(&cfg, fn, args);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); pdl = 0; }
+    }
+    if (e != cudaSuccess) e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, stream);
     count_launch();
     return e;
 }
