@@ -503,9 +503,17 @@ struct Sweep {
     {
         int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (N + 255) / 256));
         if (xbeta_mma_ok(tX, P))
-            k_xbeta_mma<<<grid, 256, 0, st>>>(out, tX, beta, 0, 1, N, P, off, off_scale, shift);
+            k_xbeta_mma<false><<<grid, 256, 0, st>>>(out, tX, beta, 0, 1, N, P, off, off_scale, shift, MlogitNext{});
         else
             k_xbeta<<<grid, 256, P * sizeof(double), st>>>(out, tX, beta, off, off_scale, shift, N, P);
+        count_launch();
+    }
+
+    // mlogit: XB_j = X beta_j, E_j = exp(XB_j) and the next category's offset and tilt in one pass (k_xbeta_mma<true>)
+    void xbeta_mlogit(double *out, const double *beta, const MlogitNext &mn)
+    {
+        int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (N + 255) / 256));
+        k_xbeta_mma<true><<<grid, 256, 0, st>>>(out, tX, beta, 0, 1, N, P, nullptr, 0.0, 0.0, mn);
         count_launch();
     }
 
@@ -772,7 +780,7 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
         const int64_t trips = (int64_t)chains * ((N + 31) / 32);
         int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (trips + 7) / 8));
         if (xbeta_mma_ok(tX, P))
-            k_xbeta_mma<<<grid, 256, 0, st>>>(psi, tX, beta, bstride, chains, N, P, nullptr, 0.0, 0.0);
+            k_xbeta_mma<false><<<grid, 256, 0, st>>>(psi, tX, beta, bstride, chains, N, P, nullptr, 0.0, 0.0, MlogitNext{});
         else
             k_xbeta_chains<<<grid, 256, 0, st>>>(psi, tX, beta, bstride, chains, (int)N, P);
         count_launch();
@@ -850,8 +858,11 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
     Sweep s;
     s.N = N; s.P = P; s.obs0 = obs0; s.st = st; s.tX = tX; s.exchange = sharded;
     if (s.init(mem, err)) return 1;
-    double *Z, *b0, *XB, *cj, *eta, *yj, *base;
+    double *Z, *b0, *XB, *cj, *eta, *yj, *base, *EX = nullptr;
     int *shape;
+    // psi, exp(psi) and the next category's offsets from one pass over X (k_xbeta_mma<true>); BL_MLOGIT_UNFUSED
+    // keeps the psi kernel and the offsets kernel per category (A/B: bit-identical chains)
+    const bool fuse_next = xbeta_mma_ok(tX, P) && U <= kMlogitMaxU && !getenv("BL_MLOGIT_UNFUSED");
     GB_CK(mem.get(&Z, (size_t)P * U));
     GB_CK(mem.get(&b0, (size_t)P * U));
     GB_CK(mem.get(&base, (size_t)P * U));
@@ -860,6 +871,9 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
     GB_CK(mem.get(&eta, N));
     GB_CK(mem.get(&yj, N));
     GB_CK(mem.get(&shape, N));
+    void *work = nullptr;                      // branch-class binning of the PG(1, eta) draws (large N)
+    GB_CK(mem.get((char **)&work, (32 + (size_t)N) * sizeof(int)));          // [meta][index list]
+    if (fuse_next) GB_CK(mem.get(&EX, (size_t)N * U));
     const bool keep_w = !(flags & BL_GIBBS_NO_W) && w_out;
     k_shape_int<<<cdiv(N, 256), 256, 0, st>>>(shape, n, N);
     count_launch();
@@ -878,6 +892,10 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
     GB_CK(cudaMemsetAsync(beta_out, 0, sizeof(double) * (size_t)P * U * samp, st));
     if (keep_w) GB_CK(cudaMemsetAsync(w_out, 0, sizeof(double) * (size_t)N * U * samp, st));
     GB_CK(cudaMemsetAsync(XB, 0, sizeof(double) * (size_t)N * U, st));
+    if (fuse_next) {
+        k_fill<<<(int)std::min<int64_t>(148 * 8, cdiv((int64_t)N * U, 256)), 256, 0, st>>>(EX, 1.0, (int64_t)N * U);   // exp(0)
+        count_launch();
+    }
     const int total = burn + samp;
     StageTimer tmr;
     tmr.st = st;
@@ -888,11 +906,13 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
         for (int j = 0; j < U; ++j) {
             uint32_t call = (uint32_t)t * (uint32_t)U + (uint32_t)j;
             tmr.arm(t == total - 1 && j == U - 1);
-            k_mlogit_offsets<<<cdiv(N, 256), 256, 0, st>>>(cj, eta, XB, N, U, j);
-            count_launch();
+            if (!fuse_next || (t == 0 && j == 0)) {
+                k_mlogit_offsets<<<cdiv(N, 256), 256, 0, st>>>(cj, eta, XB, N, U, j);
+                count_launch();
+            }
             tmr.mark("offsets");
             double *wj = wS ? wS + (size_t)N * j : s.w;
-            cudaError_t e = launch_devroye_refill(wj, shape, eta, N, StreamId{seed, obs0, call}, st);
+            cudaError_t e = launch_devroye_refill(wj, shape, eta, N, StreamId{seed, obs0, call}, st, work, 1 << 18);
             if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
             tmr.mark("draw");
             if (s.gram_tail_fused()) {
@@ -907,7 +927,8 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
             s.beta_draw(kBetaMvn, P0 + (size_t)P * P * j, base + (size_t)P * j, true, nullptr,
                         bS + (size_t)P * j, seed, call);
             tmr.mark("beta");
-            s.xbeta(XB + (size_t)N * j, bS + (size_t)P * j, nullptr, 0.0);
+            if (fuse_next) s.xbeta_mlogit(XB + (size_t)N * j, bS + (size_t)P * j, MlogitNext{EX, XB, cj, eta, U, j, (j + 1) % U});
+            else s.xbeta(XB + (size_t)N * j, bS + (size_t)P * j, nullptr, 0.0);
             tmr.mark("xbeta");
             tmr.report("mlogit");
         }

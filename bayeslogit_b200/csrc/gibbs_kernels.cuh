@@ -181,10 +181,24 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 // instructions per trip in the transposing butterfly and idles HBM meanwhile (4.6 TB/s at P = 64,
 // 2.4 TB/s at P = 32).  Chains: rows [c N, (c+1) N) meet beta + c * beta_stride.
 // ---------------------------------------------------------------------------------
+// mlogit epilogue (MultLogit.hpp:246-258, 275-277): the category whose coefficients were just drawn gets its new
+// linear predictor XB_j = X beta_j and E_j = exp(XB_j) (cached so that no category's exponentials are recomputed
+// until its own beta changes); the NEXT category jn gets its offset c = log(sum_{k != jn} E_k + 1) -- same
+// summation order as k_mlogit_offsets, same exp() of the same numbers, same bits -- and eta = XB_jn - c.  One
+// pass over X replaces the psi kernel and the offsets kernel of every category update.
+constexpr int kMlogitMaxU = 16;       // categories - 1 the fused pass keeps in registers (more: the separate kernels)
+struct MlogitNext {
+    double *E;              // [N x U] exp(XB), column-major
+    const double *XB;       // [N x U]
+    double *c, *eta;        // [N] offset and PG tilt of category jn
+    int U, j, jn;
+};
+
+template <bool kMlogit>
 static __global__ void __launch_bounds__(256, 2)
 k_xbeta_mma(double *__restrict__ psi, const double *__restrict__ tX, const double *__restrict__ beta,
             int64_t beta_stride, int chains, int64_t N, int P,
-            const double *__restrict__ off, double off_scale, double shift)
+            const double *__restrict__ off, double off_scale, double shift, MlogitNext mn)
 {
     const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
     const int64_t tpc = (N + 31) >> 5;                               // 32-row trips per chain
@@ -200,6 +214,16 @@ k_xbeta_mma(double *__restrict__ psi, const double *__restrict__ tX, const doubl
         bool rv[4];
 #pragma unroll
         for (int rb = 0; rb < 4; ++rb) rv[rb] = i0 + 8 * rb + gid < N;
+        // mlogit: this lane's row is 8 tig + gid; the other categories' exponentials and the next category's
+        // linear predictor do not depend on this trip's product -- their loads go out with the first loads of X
+        double ek[kMlogit ? kMlogitMaxU : 1], xbn = 0.0;
+        if (kMlogit) {
+            const int64_t i = i0 + 8 * tig + gid;
+#pragma unroll
+            for (int k = 0; k < kMlogitMaxU; ++k)
+                ek[k] = (k < mn.U && k != mn.j && k != mn.jn && i < N) ? __ldcg(mn.E + i + (size_t)N * k) : 0.0;
+            if (mn.jn != mn.j && i < N) xbn = __ldcg(mn.XB + i + (size_t)N * mn.jn);
+        }
 #pragma unroll 4
         for (int c0 = 0; c0 < P; c0 += 8) {
             const bool cv = c0 + 2 * tig < P;
@@ -215,7 +239,24 @@ k_xbeta_mma(double *__restrict__ psi, const double *__restrict__ tX, const doubl
                 dmma884(c[rb][0], c[rb][1], a[rb].y, b1);
             }
         }
-        if (tig == 0) {
+        if (kMlogit) {
+            // every column of an accumulator tile holds psi of its 8 rows: lane (gid, tig) takes row 8 tig + gid
+            const double xb = tig == 0 ? c[0][0] : tig == 1 ? c[1][0] : tig == 2 ? c[2][0] : c[3][0];
+            const int64_t i = i0 + 8 * tig + gid;
+            if (i < N) {
+                psi[i] = xb;
+                const double ej = exp(xb);
+                mn.E[i + (size_t)N * mn.j] = ej;
+                double A = 0.0;
+#pragma unroll
+                for (int k = 0; k < kMlogitMaxU; ++k)
+                    if (k < mn.U && k != mn.jn) A += k == mn.j ? ej : ek[k];
+                A += 1.0;
+                const double cj = log(A);
+                mn.c[i] = cj;
+                mn.eta[i] = (mn.jn == mn.j ? xb : xbn) - cj;
+            }
+        } else if (tig == 0) {
 #pragma unroll
             for (int rb = 0; rb < 4; ++rb) {
                 const int64_t i = i0 + 8 * rb + gid;
@@ -1225,6 +1266,11 @@ static __global__ void k_nb_suffix(double *__restrict__ G, const unsigned long l
         run += hist[j + 1];
         G[j] = (double)run;
     }
+}
+
+static __global__ void k_fill(double *__restrict__ x, double v, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = v;
 }
 
 // mlogit offsets for category j: A = sum_{k != j, k < J-1} exp(XB_k) + exp(0),

@@ -400,7 +400,7 @@ k_logit_psi_draw(double *__restrict__ x, double *__restrict__ psi_out, const int
 }  // namespace
 
 cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int64_t num,
-                                  StreamId id, cudaStream_t st, void *work)
+                                  StreamId id, cudaStream_t st, void *work, int64_t bin_min_arg)
 {
     if (num <= 0) return cudaSuccess;
     int64_t cap = 148LL * 4;                 // 148 SMs x resident CTAs
@@ -417,6 +417,8 @@ cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int6
     // CTA barriers, the slot traffic and the wait for the slowest warp of every trip cost more than the
     // divergence they remove.  Kept as a measured alternative, not the default.
     const bool regroup = getenv("BL_DEVROYE_REGROUP") != nullptr;
+    static const int64_t bin_env = getenv("BL_DEVROYE_BIN_MIN") ? atoll(getenv("BL_DEVROYE_BIN_MIN")) : -1;
+    const int64_t bin_min = bin_env >= 0 ? bin_env : bin_min_arg;
     if (regroup && num >= (1 << 15) && num < (1LL << 31)) {
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_devroye_regroup, kDrThreads, 0) != cudaSuccess || per_sm < 1)
@@ -425,7 +427,7 @@ cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int6
         const int rgrid = (int)std::min<int64_t>(148LL * per_sm, std::max<int64_t>(1, want));
         k_devroye_regroup<<<rgrid, kDrThreads, 0, st>>>(x, n, z, (int)num, id);
         count_launch();
-    } else if (work && num >= (1 << 20) && num < (1LL << 31)) {
+    } else if (work && num >= bin_min && num < (1LL << 31)) {
         int *meta = (int *)work, *idx = meta + 32;
         cudaError_t e = cudaMemsetAsync(meta, 0, 32 * sizeof(int), st);
         if (e != cudaSuccess) return e;

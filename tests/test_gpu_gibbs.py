@@ -160,6 +160,25 @@ def test_mlogit_chain_matches_oracle_at_the_benchmarked_shape(gapi):
     close(b, bo); close(w, wo)
 
 
+def test_mlogit_fused_psi_and_next_offsets_equal_the_separate_kernels(gapi):
+    """k_xbeta_mma<true> (psi_j, exp(psi_j) cached, offsets and tilt of the next category from one pass over X)
+    against the psi kernel + k_mlogit_offsets per category (BL_MLOGIT_UNFUSED): same exp() of the same numbers in
+    the same order (MultLogit.hpp:246-258), so the chains agree bit for bit."""
+    import os
+    N, P, J = 6_007, 32, 5
+    X, Y, _ = synth_mlogit(N, P, J, 43, scale=0.3)
+    rng = np.random.default_rng(6)
+    m0 = rng.normal(0, 0.05, (P, J - 1))
+    P0 = np.stack([(0.5 + 0.05 * j) * np.eye(P) for j in range(J - 1)], axis=2)
+    w1, b1 = gapi.mlogit_gibbs(Y, X, np.ones(N), m0, P0, 4, 2, seed=79)
+    os.environ["BL_MLOGIT_UNFUSED"] = "1"
+    try:
+        w2, b2 = gapi.mlogit_gibbs(Y, X, np.ones(N), m0, P0, 4, 2, seed=79)
+    finally:
+        del os.environ["BL_MLOGIT_UNFUSED"]
+    assert np.array_equal(b1, b2) and np.array_equal(w1, w2)
+
+
 @pytest.mark.parametrize("N,P", [(30_000, 32), (30_011, 64), (30_000, 256)])
 def test_nb_chain_matches_oracle_at_wide_P(gapi, N, P):
     """BASELINE config 4's kernel instantiations at an oracle-sized N: k_xtv_stream<log2(P/2), 2> (weights
