@@ -228,6 +228,13 @@ __device__ inline double stream_normal_obs(uint64_t seed, uint64_t obs, uint32_t
 // Stream of the constrained draw's rejection normals (below): (seed, obs 2^64-3, call).
 constexpr uint64_t kTnObs = 0xFFFFFFFFFFFFFFFDull;
 
+// Rejection normal number m generated on the spot -- only when the precomputed ones have run out; out of line so that
+// the Philox rounds and the Box-Muller transform stay out of the coordinate loop's instruction stream.
+static __device__ __noinline__ double tn_normal_spot(uint64_t seed, uint32_t call, int m)
+{
+    return stream_normal_obs(seed, kTnObs, call, m);
+}
+
 __device__ inline double stream_normal(uint64_t seed, uint32_t call, int k)
 {
     PhiloxSource s;
@@ -688,11 +695,11 @@ __device__ __forceinline__ double warp_min_f64(double v)
 // The truncated normal itself.  Inverse CDF costs an erfc pair and an inverse normal CDF of dependent FP64 latency
 // (~2 200 cycles on one lane) per coordinate, P^2 times per beta draw.  But in a well-identified model nearly every
 // window (cmin, cmax) is wide -- the constraint beta_j >= 0 binds only for coefficients near zero -- and for a wide
-// window plain rejection from N(0,1) is exact and almost always accepts at the first try.  So: when
-// cmin < 1, cmax > -1 and cmax - cmin >= 1/2, take up to four normals from their own stream (seed, obs 2^64-3, call),
-// normal number m at words 3m..3m+2, PRECOMPUTED in parallel by the whole CTA before the sweeps (nbuf; past its end
-// they are generated on the spot), and return the first one inside the window; otherwise, or after four misses, the
-// inverse-CDF / tail sampler on the beta stream as before.  Every branch returns an exact truncated normal, so the
+// window plain rejection from N(0,1) is exact and almost always accepts at the first try.  So: one normal from the
+// rejection stream (seed, obs 2^64-3, call) -- normal number m at words 3m..3m+2, PRECOMPUTED in parallel by the whole
+// CTA before the sweeps (nbuf; past its end they are generated on the spot) -- is ALWAYS tried first; if it misses and
+// cmin < 1, cmax > -1 and cmax - cmin >= 1/2, up to three more; otherwise, or after four misses, the inverse-CDF /
+// tail sampler on the beta stream as before.  Every branch returns an exact truncated normal, so the
 // draw's distribution is unchanged; the oracle (draw_beta_constrained) mirrors the rule variate for variate.
 template <int KP>
 __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const double *iL, const double *z_in,
@@ -701,6 +708,9 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
                                                         const double *nbuf, int nbuf_len, uint64_t seed, uint32_t call)
 {
     int mnorm = 0;                         // normals of the rejection stream consumed so far (warp-uniform)
+#ifdef BL_BETA_CLOCKS
+    long long t_perm = 0, t_coord = 0; int n_fall = 0, n_rej = 0;
+#endif
     double beta[KP], z[KP];
 #pragma unroll
     for (int q = 0; q < KP; ++q) {
@@ -711,73 +721,154 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
     for (int i = lane; i < P; i += 32) is[i] = i;
     __syncwarp();
     for (int k = 0; k < P; ++k) {
-        for (int i = 0; i < P - 1; ++i) {
-            double f = (double)i + ((double)P - (double)i) * src.unif();       // r.flat(i, P)
-            unsigned t = (unsigned)f;
-            if (t > (unsigned)(P - 1)) t = (unsigned)(P - 1);
-            if (lane == 0) { int tmp = is[i]; is[i] = is[t]; is[t] = tmp; }
+#ifdef BL_BETA_CLOCKS
+        long long tp0 = clock64();
+#endif
+        // r.flat(i, P) for i = 0 .. P-2 takes one stream word each, words a0 .. a0 + P - 2 of the beta stream: lane l
+        // forms the swap targets of i = l, l + 32, ... straight from the counter (the block that holds its word),
+        // the stream is moved past them, and lane 0 is left with the swaps alone -- drawn one after the other
+        // by every lane this loop was a third of the whole constrained draw (BL_BETA_CLOCKS: 15 500 of 49 000
+        // cycles per sweep at P = 64).
+        {
+            const int a0 = 4 * ((int)src.blk - 1) + src.pos;
+            int *tt = is + P;
+            for (int i = lane; i < P - 1; i += 32) {
+                const int a = a0 + i;
+                const uint4 b = philox_block_ool(src.c0, src.c1, (uint32_t)(a >> 2), src.c3, src.key);
+                const uint32_t wv = (a & 3) == 0 ? b.x : (a & 3) == 1 ? b.y : (a & 3) == 2 ? b.z : b.w;
+                const double f = (double)i + ((double)P - (double)i) * word_to_unif(wv);
+                unsigned t = (unsigned)f;
+                if (t > (unsigned)(P - 1)) t = (unsigned)(P - 1);
+                tt[i] = (int)t;
+            }
+            const int a1 = a0 + P - 1;
+            src.buf = philox_block_ool(src.c0, src.c1, (uint32_t)(a1 >> 2), src.c3, src.key);
+            src.blk = (uint32_t)(a1 >> 2) + 1u;
+            src.pos = a1 & 3;
+            __syncwarp();
+            if (lane == 0)
+                for (int i = 0; i < P - 1; ++i) { const int t = tt[i]; const int tmp = is[i]; is[i] = is[t]; is[t] = tmp; }
         }
         __syncwarp();
-        // Software-pipelined over the coordinates: everything of coordinate i + 1 that does not depend on the draw
-        // of coordinate i -- its index, its column of L and 1 / L, the next rejection normal -- is loaded while
-        // coordinate i is decided, so the critical path per coordinate is beta -> bound -> two reductions ->
-        // window test -> beta.  (z of the next coordinate is read after the update: each index occurs once per sweep.)
+        // Software-pipelined over the coordinates.  Everything of coordinate i + 1 that does not depend on the draw
+        // of coordinate i is fetched while coordinate i is decided: its index, its column of L and 1 / L, the signs
+        // of that column, its own current value z1 (each index occurs once per sweep, so z[c'] is not touched by
+        // coordinate c) and -- assuming the common outcome, first normal accepted -- its rejection normal.  The
+        // first normal Z0 is tried against the constraints lane by lane in a branch-free form,
+        //     Z0 inside lane j's bound  <=>  sign(L_jc) (beta_j / L_jc + (Z0 - z1)) > 0,
+        // one FMA and two compares per owned entry and ONE warp vote (Z0 lies in the window iff it clears every
+        // lane's own bounds); the updated beta = beta + L_c (Z0 - z1) is formed beside the test and kept when the
+        // vote passes.  The critical path per coordinate is then FMA -> compare -> vote -> select (~100 cycles; the
+        // window-forming version with its two exact max / min reductions spent ~520).  The window itself is only
+        // formed on a miss.
+#ifdef BL_BETA_CLOCKS
+        long long tp1 = clock64(); t_perm += tp1 - tp0;
+#endif
         int c = is[0];
         double lu[KP], il[KP];
+        bool pos[KP], neg[KP];
 #pragma unroll
         for (int q = 0; q < KP; ++q) {
             const int j = lane + 32 * q;
             lu[q] = (j >= c && j < P) ? L[j + (size_t)ld * c] : 0.0;
             il[q] = (j >= c && j < P - 1) ? iL[j + (size_t)ld * c] : 0.0;
+            pos[q] = j < P - 1 && lu[q] > 0.0;                           // the last coefficient is free
+            neg[q] = j < P - 1 && lu[q] < 0.0;
         }
+        double z1;
+        {
+            double zc = z[0];
+#pragma unroll
+            for (int q = 1; q < KP; ++q) zc = (c >> 5) == q ? z[q] : zc;
+            z1 = __shfl_sync(0xffffffffu, zc, c & 31);
+        }
+        double Z0 = mnorm < nbuf_len ? nbuf[mnorm] : tn_normal_spot(seed, call, mnorm);
         for (int i = 0; i < P; ++i) {
             const int cn = i + 1 < P ? is[i + 1] : c;
             double lun[KP], iln[KP];
+            bool posn[KP], negn[KP];
 #pragma unroll
             for (int q = 0; q < KP; ++q) {
                 const int j = lane + 32 * q;
                 lun[q] = (j >= cn && j < P) ? L[j + (size_t)ld * cn] : 0.0;
                 iln[q] = (j >= cn && j < P - 1) ? iL[j + (size_t)ld * cn] : 0.0;
+                posn[q] = j < P - 1 && lun[q] > 0.0;
+                negn[q] = j < P - 1 && lun[q] < 0.0;
             }
-            const double Zn = mnorm < nbuf_len ? nbuf[mnorm] : 0.0;
-            double zc = z[0];
+            double z1n;
+            {
+                double zc = z[0];
 #pragma unroll
-            for (int q = 1; q < KP; ++q) zc = (c >> 5) == q ? z[q] : zc;
-            const double z1 = __shfl_sync(0xffffffffu, zc, c & 31);
-            double cmin = -INFINITY, cmax = INFINITY;
+                for (int q = 1; q < KP; ++q) zc = (cn >> 5) == q ? z[q] : zc;
+                z1n = __shfl_sync(0xffffffffu, zc, cn & 31);             // unused (and stale) when i + 1 == P
+            }
+            const double Zn = mnorm + 1 < nbuf_len ? nbuf[mnorm + 1] : 0.0;
+            const double u = Z0 - z1;
+            double bnew[KP];
+            bool inside = true;
 #pragma unroll
             for (int q = 0; q < KP; ++q) {
-                const int j = lane + 32 * q;
-                const double l1 = j < P - 1 ? lu[q] : 0.0;              // the last coefficient is free
-                const double c1 = fma(-beta[q], il[q], z1);
-                if (l1 > 0.0 && c1 > cmin) cmin = c1;
-                else if (l1 < 0.0 && c1 < cmax) cmax = c1;
+                const double v = fma(beta[q], il[q], u);
+                inside = inside & ((v > 0.0) | !pos[q]) & ((v < 0.0) | !neg[q]);     // bitwise: no short-circuit branches
+                bnew[q] = fma(lu[q], u, beta[q]);                        // lu is zero outside c <= j < P
             }
-            cmin = warp_max_f64(cmin);
-            cmax = warp_min_f64(cmax);
-            double z2 = 0.0;
-            bool got = false;
-            if (cmin < cmax && cmin < 1.0 && cmax > -1.0 && cmax - cmin >= 0.5) {
-                for (int tr = 0; tr < 4 && !got; ++tr) {
-                    const double Z = tr == 0 && mnorm < nbuf_len ? Zn
-                                     : mnorm < nbuf_len ? nbuf[mnorm] : stream_normal_obs(seed, kTnObs, call, mnorm);
-                    ++mnorm;
-                    if (Z > cmin && Z < cmax) { z2 = Z; got = true; }
+            ++mnorm;
+            double z2 = Z0;
+            const bool hit = __all_sync(0xffffffffu, inside);
+            if (__builtin_expect(hit, 1)) {
+#pragma unroll
+                for (int q = 0; q < KP; ++q) beta[q] = bnew[q];
+            } else {
+#ifdef BL_BETA_CLOCKS
+                ++n_fall;
+#endif
+                double cmin = -INFINITY, cmax = INFINITY;
+#pragma unroll
+                for (int q = 0; q < KP; ++q) {
+                    const double c1 = fma(-beta[q], il[q], z1);
+                    if (pos[q] && c1 > cmin) cmin = c1;
+                    else if (neg[q] && c1 < cmax) cmax = c1;
                 }
+                cmin = warp_max_f64(cmin);
+                cmax = warp_min_f64(cmax);
+                bool got = false;
+                if (cmin < cmax && cmin < 1.0 && cmax > -1.0 && cmax - cmin >= 0.5) {
+                    for (int tr = 1; tr < 4 && !got; ++tr) {
+                        const double Z = mnorm < nbuf_len ? nbuf[mnorm] : tn_normal_spot(seed, call, mnorm);
+                        ++mnorm;
+                        if (Z > cmin && Z < cmax) { z2 = Z; got = true; }
+                    }
+                }
+#ifdef BL_BETA_CLOCKS
+                if (!got) ++n_rej;
+#endif
+                if (!got) z2 = tnorm_std_warp(src, cmin, cmax, lane);
+                const double dz = z2 - z1;
+#pragma unroll
+                for (int q = 0; q < KP; ++q) beta[q] = fma(lu[q], dz, beta[q]);
             }
-            if (!got) z2 = tnorm_std_warp(src, cmin, cmax, lane);
-            const double dz = z2 - z1;
 #pragma unroll
             for (int q = 0; q < KP; ++q) {
                 const int j = lane + 32 * q;
-                beta[q] = fma(lu[q], dz, beta[q]);                       // lu is zero outside c <= j < P
                 if (j == c) z[q] = z2;
                 lu[q] = lun[q];
                 il[q] = iln[q];
+                pos[q] = posn[q];
+                neg[q] = negn[q];
             }
+            // the next coordinate's normal: the prefetched one after a hit (mnorm advanced by exactly one)
+            Z0 = hit ? Zn : nbuf[mnorm < nbuf_len ? mnorm : 0];
+            if (__builtin_expect(mnorm >= nbuf_len && i + 1 < P, 0)) Z0 = tn_normal_spot(seed, call, mnorm);
+            z1 = z1n;
             c = cn;
         }
+#ifdef BL_BETA_CLOCKS
+        t_coord += clock64() - tp1;
+#endif
     }
+#ifdef BL_BETA_CLOCKS
+    if (lane == 0 && call == 3) printf("[beta constrained clocks] permutation %lld coordinates %lld (first normal missed %d times, %d inverse-CDF draws)\n", t_perm, t_coord, n_fall, n_rej);
+#endif
 #pragma unroll
     for (int q = 0; q < KP; ++q) {
         int m = lane + 32 * q;

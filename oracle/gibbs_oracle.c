@@ -218,10 +218,11 @@ static int draw_beta_constrained(double *beta, double *PP, const double *bP, con
                     if (l1 > 0.0 && c1 > cmin) cmin = c1;
                     else if (l1 < 0.0 && c1 < cmax) cmax = c1;
                 }
-                double z2 = 0.0;
-                int got = 0;
-                if (cmin < cmax && cmin < 1.0 && cmax > -1.0 && cmax - cmin >= 0.5)
-                    for (int tr = 0; tr < 4 && !got; ++tr) {
+                /* one normal of the rejection stream is always tried; up to three more when the window is wide */
+                double z2 = pgo_norm(&sn);
+                int got = z2 > cmin && z2 < cmax;
+                if (!got && cmin < cmax && cmin < 1.0 && cmax > -1.0 && cmax - cmin >= 0.5)
+                    for (int tr = 1; tr < 4 && !got; ++tr) {
                         double Z = pgo_norm(&sn);
                         if (Z > cmin && Z < cmax) { z2 = Z; got = 1; }
                     }
