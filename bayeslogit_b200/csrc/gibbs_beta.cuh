@@ -764,53 +764,37 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
 #ifdef BL_BETA_CLOCKS
         long long tp1 = clock64(); t_perm += tp1 - tp0;
 #endif
-        int c = is[0];
-        double lu[KP], il[KP];
-        bool pos[KP], neg[KP];
-#pragma unroll
-        for (int q = 0; q < KP; ++q) {
-            const int j = lane + 32 * q;
-            lu[q] = (j >= c && j < P) ? L[j + (size_t)ld * c] : 0.0;
-            il[q] = (j >= c && j < P - 1) ? iL[j + (size_t)ld * c] : 0.0;
-            pos[q] = j < P - 1 && lu[q] > 0.0;                           // the last coefficient is free
-            neg[q] = j < P - 1 && lu[q] < 0.0;
-        }
-        double z1;
-        {
-            double zc = z[0];
-#pragma unroll
-            for (int q = 1; q < KP; ++q) zc = (c >> 5) == q ? z[q] : zc;
-            z1 = __shfl_sync(0xffffffffu, zc, c & 31);
-        }
-        double Z0 = mnorm < nbuf_len ? nbuf[mnorm] : tn_normal_spot(seed, call, mnorm);
-        for (int i = 0; i < P; ++i) {
-            const int cn = i + 1 < P ? is[i + 1] : c;
-            double lun[KP], iln[KP];
-            bool posn[KP], negn[KP];
+        // two register sets (current / next coordinate) used alternately: no copies at the end of an iteration
+        struct Col { double lu[KP], il[KP]; bool pos[KP], neg[KP]; double z1; int c; };
+        auto fetch = [&](Col &k, int c) {
+            k.c = c;
 #pragma unroll
             for (int q = 0; q < KP; ++q) {
                 const int j = lane + 32 * q;
-                lun[q] = (j >= cn && j < P) ? L[j + (size_t)ld * cn] : 0.0;
-                iln[q] = (j >= cn && j < P - 1) ? iL[j + (size_t)ld * cn] : 0.0;
-                posn[q] = j < P - 1 && lun[q] > 0.0;
-                negn[q] = j < P - 1 && lun[q] < 0.0;
+                k.lu[q] = j < P ? L[j + (size_t)ld * c] : 0.0;               // L is zero above its diagonal
+                k.il[q] = j < P ? iL[j + (size_t)ld * c] : 0.0;              // zero where no constraint applies
+                k.pos[q] = k.il[q] > 0.0;
+                k.neg[q] = k.il[q] < 0.0;
             }
-            double z1n;
-            {
-                double zc = z[0];
+            double zc = z[0];
 #pragma unroll
-                for (int q = 1; q < KP; ++q) zc = (cn >> 5) == q ? z[q] : zc;
-                z1n = __shfl_sync(0xffffffffu, zc, cn & 31);             // unused (and stale) when i + 1 == P
-            }
+            for (int q = 1; q < KP; ++q) zc = (c >> 5) == q ? z[q] : zc;
+            k.z1 = __shfl_sync(0xffffffffu, zc, c & 31);
+        };
+        double Z0 = mnorm < nbuf_len ? nbuf[mnorm] : tn_normal_spot(seed, call, mnorm);
+        auto step = [&](const Col &k, Col &kn, int i) {
+            // the next coordinate: index, column, signs, its own current value (stale and unused when i + 1 == P),
+            // and its normal assuming a hit
+            fetch(kn, i + 1 < P ? is[i + 1] : k.c);
             const double Zn = mnorm + 1 < nbuf_len ? nbuf[mnorm + 1] : 0.0;
-            const double u = Z0 - z1;
+            const double z1 = k.z1, u = Z0 - z1;
             double bnew[KP];
             bool inside = true;
 #pragma unroll
             for (int q = 0; q < KP; ++q) {
-                const double v = fma(beta[q], il[q], u);
-                inside = inside & ((v > 0.0) | !pos[q]) & ((v < 0.0) | !neg[q]);     // bitwise: no short-circuit branches
-                bnew[q] = fma(lu[q], u, beta[q]);                        // lu is zero outside c <= j < P
+                const double v = fma(beta[q], k.il[q], u);
+                inside = inside & ((v > 0.0) | !k.pos[q]) & ((v < 0.0) | !k.neg[q]);     // bitwise: no short-circuit branches
+                bnew[q] = fma(k.lu[q], u, beta[q]);
             }
             ++mnorm;
             double z2 = Z0;
@@ -825,9 +809,9 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
                 double cmin = -INFINITY, cmax = INFINITY;
 #pragma unroll
                 for (int q = 0; q < KP; ++q) {
-                    const double c1 = fma(-beta[q], il[q], z1);
-                    if (pos[q] && c1 > cmin) cmin = c1;
-                    else if (neg[q] && c1 < cmax) cmax = c1;
+                    const double c1 = fma(-beta[q], k.il[q], z1);
+                    if (k.pos[q] && c1 > cmin) cmin = c1;
+                    else if (k.neg[q] && c1 < cmax) cmax = c1;
                 }
                 cmin = warp_max_f64(cmin);
                 cmax = warp_min_f64(cmax);
@@ -845,23 +829,23 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
                 if (!got) z2 = tnorm_std_warp(src, cmin, cmax, lane);
                 const double dz = z2 - z1;
 #pragma unroll
-                for (int q = 0; q < KP; ++q) beta[q] = fma(lu[q], dz, beta[q]);
+                for (int q = 0; q < KP; ++q) beta[q] = fma(k.lu[q], dz, beta[q]);
             }
 #pragma unroll
-            for (int q = 0; q < KP; ++q) {
-                const int j = lane + 32 * q;
-                if (j == c) z[q] = z2;
-                lu[q] = lun[q];
-                il[q] = iln[q];
-                pos[q] = posn[q];
-                neg[q] = negn[q];
-            }
+            for (int q = 0; q < KP; ++q)
+                if (lane + 32 * q == k.c) z[q] = z2;
             // the next coordinate's normal: the prefetched one after a hit (mnorm advanced by exactly one)
             Z0 = hit ? Zn : nbuf[mnorm < nbuf_len ? mnorm : 0];
             if (__builtin_expect(mnorm >= nbuf_len && i + 1 < P, 0)) Z0 = tn_normal_spot(seed, call, mnorm);
-            z1 = z1n;
-            c = cn;
+        };
+        Col ka, kb;
+        fetch(ka, is[0]);
+        int i = 0;
+        for (; i + 1 < P; i += 2) {
+            step(ka, kb, i);
+            step(kb, ka, i + 1);
         }
+        if (i < P) step(ka, kb, i);
 #ifdef BL_BETA_CLOCKS
         t_coord += clock64() - tp1;
 #endif
@@ -969,11 +953,14 @@ __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, do
         warp_solve_l(L, z, P, ld, lane);
     }
     __syncthreads();
-    // U is no longer needed: its storage takes 1 / L for the sweeps (entries on and below the diagonal)
+    // U is no longer needed: its storage takes 1 / L for the sweeps -- entries on and below the diagonal of the rows
+    // that carry a constraint; zero above the diagonal and in the last row (the free coefficient), so that the sweeps
+    // read a column without masks and take the constraint's direction from the sign of 1 / L alone
     double *iL = A;
     for (int e2 = tid; e2 < P * P; e2 += blockDim.x) {
         int j = e2 % P, c = e2 / P;
-        if (j >= c) iL[j + (size_t)ld * c] = 1.0 / L[j + (size_t)ld * c];
+        const double l = L[j + (size_t)ld * c];
+        iL[j + (size_t)ld * c] = (j >= c && j < P - 1 && l != 0.0) ? 1.0 / l : 0.0;      // L_jc = 0: no constraint from row j
     }
     // the rejection normals of the sweeps (see warp_constrained_sweeps), all threads
     for (int m = tid; m < nbuf_len; m += blockDim.x) nbuf[m] = stream_normal_obs(seed, kTnObs, call, m);
