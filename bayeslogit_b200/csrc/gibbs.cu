@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256)
 k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__ P0,
             const double *__restrict__ base_rhs, int add_tail, const double *beta_prev,
             double *beta_out, double *gwork, int P, uint64_t seed, uint32_t call, int *status,
-            PeerWait pw, int64_t chain_stride)
+            PeerWait pw, int64_t chain_stride, const double *tn_pre, int tn_fast)
 {
     extern __shared__ double sm[];
     // programmatic dependent launch (Sweep::beta_draw; no-ops otherwise): the next kernel's CTAs may be scheduled
@@ -283,7 +283,7 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
         default: peer_stage<0>(pw, A, rhs, P0, base_rhs, add_tail, P, ld); break;
         }
         __syncthreads();
-        cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len, efast);
+        cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len, efast, tn_pre, SMEM && tn_fast);
         return;
     }
     if (fast) {
@@ -348,7 +348,14 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
 #ifdef BL_BETA_CLOCKS
     if (threadIdx.x == 0 && call == 3) printf("[beta clocks] load %lld\n", clock64() - k0);
 #endif
-    cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len);
+    cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len, nullptr, tn_pre, SMEM && tn_fast);
+}
+
+// rejection normals of one constrained beta draw: normal m of the stream (seed, obs 2^64-3, call), gibbs_beta.cuh
+__global__ void k_tn_normals(double *out, int n, uint64_t seed, uint32_t call)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < n) out[m] = stream_normal_obs(seed, kTnObs, call, m);
 }
 
 __global__ void k_matvec(double *out, const double *A, const double *x, int P)   // out = A x, col-major
@@ -449,6 +456,7 @@ struct Sweep {
     const double *tX = nullptr;
     double *psi = nullptr, *w = nullptr, *acc = nullptr, *part = nullptr, *xtv_part = nullptr;
     double *gwork = nullptr;
+    double *tnbuf = nullptr;   // the constrained draw's rejection normals of one iteration, made by k_tn_normals
     int *status = nullptr;
     int nt = 1, nslab = 1, nslab_diag = 0, xtv_slabs = 1;
     bool use_smem = true;
@@ -486,7 +494,8 @@ struct Sweep {
         // A, B (ld x P each), 5 P vector scratch; the constrained draw's P^2 + 2P rejection normals behind them
         beta_smem = (2 * (size_t)(P | 1) * P + 5 * (size_t)P) * sizeof(double);
         if (P <= 64) beta_smem = (beta_fast_e_offset(P) + 64) * sizeof(double);      // cta_plain_fast: + its normals
-        beta_smem_tn = beta_smem + ((size_t)P * P + 2 * (size_t)P) * sizeof(double);
+        beta_smem_tn = std::max(beta_smem + ((size_t)P * P + 2 * (size_t)P) * sizeof(double), beta_tn_doubles(P) * sizeof(double));
+        GB_CK(m.get(&tnbuf, (size_t)P * P + 2 * (size_t)P));
         GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRows, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)gram_smem_bytes(true)));
         GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRowsDiag, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -570,6 +579,14 @@ struct Sweep {
                    const double *beta_prev, double *beta_out, uint64_t seed, uint32_t call)
     {
         if (use_smem) {
+            const bool tn = mode == kBetaConstrained && tnbuf != nullptr;
+            if (tn) {
+                // the draw's P^2 + 2P rejection normals depend on (seed, call) alone: one thread each, a few
+                // microseconds on the whole chip, instead of 17 in a row on each of the draw's 256 threads
+                const int n = P * P + 2 * P;
+                k_tn_normals<<<cdiv(n, 128), 128, 0, st>>>(tnbuf, n, seed, call);
+                count_launch();
+            }
             // programmatic dependent launch: the CTA is scheduled while the kernel that produces the sums drains and
             // waits for its completion on the device (griddepcontrol.wait at the top of k_beta_draw) -- the launch
             // latency of the one kernel that sits between two sweeps leaves the critical path
@@ -583,10 +600,11 @@ struct Sweep {
             at[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
             cudaLaunchKernelEx(&cfg, k_beta_draw<true>, mode, (const double *)acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
-                               beta_out, gwork, P, seed, call, status, pending, (int64_t)0);
+                               beta_out, gwork, P, seed, call, status, pending, (int64_t)0,
+                               (const double *)(tn ? tnbuf : nullptr), 1);
         } else
             k_beta_draw<false><<<1, 256, 0, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
-                                                  beta_out, gwork, P, seed, call, status, pending, 0);
+                                                  beta_out, gwork, P, seed, call, status, pending, 0, nullptr, 0);
         pending = PeerWait{};
         count_launch();
     }
@@ -730,9 +748,10 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
     if (T >= (1LL << 31)) { err = "logit_chains: chains * N must stay below 2^31 observations per call"; return 1; }
     if (P > 256) { err = "P > 256 covariates is not supported by the single-CTA beta draw"; return 1; }
     const int mode = (flags & BL_GIBBS_PLAIN_BETA) ? kBetaPlain : kBetaConstrained;
-    const size_t beta_smem = std::max((2 * (size_t)(P | 1) * P + 5 * (size_t)P +
-                                       (mode == kBetaConstrained ? (size_t)P * P + 2 * (size_t)P : 0)) * sizeof(double),
-                                      P <= 64 ? (beta_fast_e_offset(P) + 64) * sizeof(double) : (size_t)0);
+    const size_t beta_smem = mode == kBetaConstrained
+        ? beta_tn_doubles(P) * sizeof(double)
+        : std::max((2 * (size_t)(P | 1) * P + 5 * (size_t)P) * sizeof(double),
+                   P <= 64 ? (beta_fast_e_offset(P) + 64) * sizeof(double) : (size_t)0);
     if (beta_smem > 200 * 1024) { err = "logit_chains: P too large for the shared-memory beta draw"; return 1; }
     DevMem mem;
     mem.st = st;
@@ -813,7 +832,7 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
             k_gram_reduce<<<dim3(cdiv((int64_t)P * P, 32), chains), 256, 0, st>>>(acc, nullptr, part, P, nt, slabs_total, PeerPush{}, packed ? 1 : 0);
             if (tm) cudaEventRecord(ev[3], st);
             k_beta_draw<true><<<chains, 256, beta_smem, st>>>(mode, acc, P0, bP, 0, bprev, bcur, nullptr, P, seed, t, status,
-                                                           PeerWait{}, bstride);
+                                                           PeerWait{}, bstride, nullptr, 1);
             count_launch(3);
             if (tm) cudaEventRecord(ev[4], st);
             bpsi = bcur;

@@ -429,6 +429,18 @@ __host__ __device__ inline size_t beta_fast_doubles(int P)           // F, Sn, r
     const int Pp = (P + 7) & ~7;
     return (size_t)(Pp + 1) * (Pp + 8) + 8 * kFastLdS + 64;
 }
+// doubles in front of the scratch of the constrained draw's fast set-up (192 + Pp^2 doubles: cta_constrained_setup_fast)
+__host__ __device__ inline size_t beta_tn_scratch_offset(int P)
+{
+    const size_t plain = 2 * (size_t)(P | 1) * P + 5 * (size_t)P + (size_t)P * P + 2 * (size_t)P, fast = beta_fast_doubles(P);
+    return plain > fast ? plain : fast;
+}
+__host__ __device__ inline size_t beta_tn_doubles(int P)
+{
+    const int Pp = (P + 7) & ~7;
+    return P <= 64 ? beta_tn_scratch_offset(P) + 192 + (size_t)(Pp + 4) * Pp
+                   : 2 * (size_t)(P | 1) * P + 5 * (size_t)P + (size_t)P * P + 2 * (size_t)P;
+}
 // doubles of the CTA's workspace in front of the fast path's normals e[64]: the longer of the two layouts
 __host__ __device__ inline size_t beta_fast_e_offset(int P)
 {
@@ -520,6 +532,8 @@ __device__ __forceinline__ void beta_fast_relayout(double *W, const double *A, i
 // has synchronised).  256 threads: warps 0-6 factorise (named barrier 1 over their 224 threads), warp 7 produces the
 // P normals of the draw meanwhile (~5 000 cycles of one thread's latency, needed only by the backward substitution).
 // `rev`: the system is the index-reversed one (mvn draw).
+//   kDraw = false: the solve alone (no normals, R left unscaled for the caller) -- the set-up of the constrained draw.
+template <bool kDraw = true>
 __device__ __forceinline__ void cta_plain_fast(double *W, double *e, double *beta_out, int P, bool rev, int *ok,
                                                uint64_t seed, uint32_t call)
 {
@@ -536,7 +550,8 @@ __device__ __forceinline__ void cta_plain_fast(double *W, double *e, double *bet
 #endif
 #define BL_BAR7() asm volatile("bar.sync 1, 224;" ::: "memory")
     if (warp == 7) {
-        for (int m = lane; m < Pp; m += 32) e[m] = m < P ? stream_normal(seed, call, rev ? P - 1 - m : m) : 0.0;
+        if (kDraw)
+            for (int m = lane; m < Pp; m += 32) e[m] = m < P ? stream_normal(seed, call, rev ? P - 1 - m : m) : 0.0;
     } else {
         if (warp == 0 && !warp_ldl_diag8(F, rd, 0, LD, lane)) *ok = 0;
         BL_CK();
@@ -589,10 +604,11 @@ __device__ __forceinline__ void cta_plain_fast(double *W, double *e, double *bet
                 // The block's columns are final and no later step reads them: scale them by their pivots'
                 // reciprocals for the backward substitution (a step there is then one shuffle and one FMA:
                 // x_m -= (R[m,i] rd_i) x_i(raw), with x_i = rd_i x_i(raw) off the critical path).
-                for (int el = tid - 32; el < 8 * 64; el += 192) {
-                    const int col = k0 + (el >> 6), m = el & 63;
-                    if (m < col) F[m + LD * col] *= rd[col];
-                }
+                if (kDraw)
+                    for (int el = tid - 32; el < 8 * 64; el += 192) {
+                        const int col = k0 + (el >> 6), m = el & 63;
+                        if (m < col) F[m + LD * col] *= rd[col];
+                    }
                 // trailing tiles (ti, tk), p < ti <= tk <= nblk (tk = nblk: the rhs column's tile), row block by
                 // row block, dealt round-robin to warps 1-6; tile 0 is warp 0's
                 const int nrem = nblk - (p + 1);
@@ -623,7 +639,7 @@ __device__ __forceinline__ void cta_plain_fast(double *W, double *e, double *bet
         for (int qq = 0; qq < 2; ++qq) {
             const int m = lane + 32 * qq;
             rdl[qq] = m < Pp ? rd[m] : 1.0;
-            x[qq] = m < Pp ? F[m + LD * Pp] + e[m] / sqrt(rdl[qq]) : 0.0;
+            x[qq] = m < Pp ? F[m + LD * Pp] + (kDraw ? e[m] / sqrt(rdl[qq]) : 0.0) : 0.0;
         }
         for (int i = Pp - 1; i >= 0; --i) {
             const double own = (i >> 5) ? x[1] : x[0];
@@ -633,7 +649,8 @@ __device__ __forceinline__ void cta_plain_fast(double *W, double *e, double *bet
                 const int m = lane + 32 * qq;
                 rr[qq] = m < i ? F[m + LD * i] : 0.0;
             }
-            const double xi = __shfl_sync(0xffffffffu, own, i & 31);
+            double xi = __shfl_sync(0xffffffffu, own, i & 31);
+            if (!kDraw) xi *= rd[i];                                            // unscaled columns
 #pragma unroll
             for (int qq = 0; qq < 2; ++qq) x[qq] = fma(-rr[qq], xi, x[qq]);     // rr is zero at and below the diagonal
         }
@@ -653,6 +670,131 @@ __device__ __forceinline__ void cta_plain_fast(double *W, double *e, double *bet
 #endif
     __syncthreads();
 #undef BL_BAR7
+}
+
+
+// Set-up of the constrained draw for P <= 64 (256 threads): what Logit.hpp:338-365 obtains from two Cholesky
+// factorisations, P + 1 pairs of triangular solves and one more triangular solve -- mP = PP^-1 bP,
+// L = chol_lower(PP^-1), z = L^-1 (beta_prev - mP), 98 000 + 126 000 + 75 000 + 157 000 cycles as written in
+// cta_chol_* / cta_solve_utu / warp_solve_* -- from ONE blocked factorisation of the index-reversed matrix:
+// with J the reversal and J PP J = U'U,   PP^-1 = (J U^-1 J)(J U^-1 J)'   and J U^-1 J is lower triangular with a
+// positive diagonal, so it IS L.  Hence
+//   mP = J (J PP J)^-1 J bP          the blocked solve (cta_plain_fast<false>),
+//   L  = J U^-1 J                    an explicit triangular inverse, four threads per column,
+//   z  = L^-1 d = J U (J d)          a triangular matrix-vector product, no solve.
+// On entry A (ld) holds PP and rhs holds bP; on exit B (ld) holds L (strict upper part zero), A (ld) holds 1 / L
+// with zeros where no constraint applies, mP and z are filled.  X (P x P doubles) is scratch -- the rejection
+// normals' buffer, which is loaded afterwards.
+// `scratch` (192 + (Pp + 4) Pp doubles) lies behind BOTH workspace layouts (beta_tn_scratch_offset): for small P the vectors
+// of the plain layout sit inside the padded matrix.
+__device__ __forceinline__ void cta_constrained_setup_fast(double *A, double *B, double *mP_out, double *z_out,
+                                                           double *rhs, const double *beta_prev, double *scratch,
+                                                           int P, int ld, int *ok, uint64_t seed, uint32_t call)
+{
+    const int tid = threadIdx.x;
+    const int PP2 = P * P;
+    double *mP = scratch, *z = scratch + 64, *rdv = scratch + 128, *X = scratch + 192;
+#ifdef BL_BETA_CLOCKS
+    long long sc[6]; sc[0] = clock64();
+#endif
+    // index reversal in place (as the mvn draw)
+    for (int k = tid; k < PP2 / 2; k += blockDim.x) {
+        const int k2 = PP2 - 1 - k;
+        double *a = A + (k % P) + (size_t)ld * (k / P), *b = A + (k2 % P) + (size_t)ld * (k2 / P);
+        const double t = *a; *a = *b; *b = t;
+    }
+    for (int k = tid; k < P / 2; k += blockDim.x) { const double t = rhs[k]; rhs[k] = rhs[P - 1 - k]; rhs[P - 1 - k] = t; }
+    __syncthreads();
+    beta_fast_relayout(A, A, ld, rhs, P);
+#ifdef BL_BETA_CLOCKS
+    sc[1] = clock64();
+#endif
+    cta_plain_fast<false>(A, nullptr, mP, P, true, ok, seed, call);          // mP in the original order
+    if (!*ok) return;
+#ifdef BL_BETA_CLOCKS
+    sc[2] = clock64();
+#endif
+    const BetaFast w(A, P);
+    const int Pp = w.Pp, LD = w.LD;
+    const double *R = w.F;
+    if (tid < Pp) rdv[tid] = w.rd[tid];
+    __syncthreads();
+    // X = U^-1 (upper), U = D^-1/2 R:  x_c = sqrt(rd_c),  x_k = -rd_k sum_{i > k} R[k,i] x_i.  Column c of X belongs to
+    // threads 4 c .. 4 c + 3, which keep its running sums r_m = sum_{i > m} R[m,i] x_i for the rows m = t mod 4 in the
+    // column's own storage; x_k travels from its owner to the other three by shuffle.
+    {
+        const int c = tid >> 2, sub = tid & 3;
+        double *xc = X + (size_t)(Pp + 4) * c;                                // leading dimension Pp + 4: the quads of a half-warp hit distinct banks
+        if (c < Pp)
+            for (int m = sub; m < Pp; m += 4) xc[m] = 0.0;
+        __syncwarp();
+        for (int k = Pp - 1; k >= 0; --k) {
+            // every thread of a quad evaluates x_k from the row owner's sum
+            double xk = 0.0;
+            const int owner = (tid & ~3) | (k & 3);
+            double rk = (c < Pp && k <= c && sub == (k & 3)) ? xc[k] : 0.0;
+            rk = __shfl_sync(0xffffffffu, rk, owner & 31);
+            if (c < Pp && k <= c) {
+                xk = k == c ? sqrt(rdv[c]) : -rdv[k] * rk;
+                if (sub == (k & 3)) xc[k] = xk;
+                int m = sub;
+                for (; m + 12 < k; m += 16) {                                    // four rows at a time: their loads go out together
+                    const double r0 = R[m + LD * k], r1 = R[m + 4 + LD * k], r2 = R[m + 8 + LD * k], r3 = R[m + 12 + LD * k];
+                    const double x0 = xc[m], x1 = xc[m + 4], x2 = xc[m + 8], x3 = xc[m + 12];
+                    xc[m] = fma(r0, xk, x0); xc[m + 4] = fma(r1, xk, x1); xc[m + 8] = fma(r2, xk, x2); xc[m + 12] = fma(r3, xk, x3);
+                }
+                for (; m < k; m += 4) xc[m] = fma(R[m + LD * k], xk, xc[m]);
+            }
+        }
+    }
+    __syncthreads();
+#ifdef BL_BETA_CLOCKS
+    sc[3] = clock64();
+#endif
+    // z = J U (J d), d = beta_prev - mP: row i of U against the reversed d; thread i (four partial sums)
+    if (tid < P) {
+        const int i = tid;
+        const double sq = sqrt(rdv[i]);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int k = i + 1;
+        for (; k + 3 < P; k += 4) {
+            s0 = fma(R[i + LD * k], beta_prev[P - 1 - k] - mP[P - 1 - k], s0);
+            s1 = fma(R[i + LD * (k + 1)], beta_prev[P - 2 - k] - mP[P - 2 - k], s1);
+            s2 = fma(R[i + LD * (k + 2)], beta_prev[P - 3 - k] - mP[P - 3 - k], s2);
+            s3 = fma(R[i + LD * (k + 3)], beta_prev[P - 4 - k] - mP[P - 4 - k], s3);
+        }
+        for (; k < P; ++k) s0 = fma(R[i + LD * k], beta_prev[P - 1 - k] - mP[P - 1 - k], s0);
+        // U[i,i] = 1 / sqrt(rd_i), U[i,k] = sqrt(rd_i) R[i,k]
+        z[P - 1 - i] = (beta_prev[P - 1 - i] - mP[P - 1 - i]) / sq + sq * ((s0 + s1) + (s2 + s3));
+    }
+    __syncthreads();
+#ifdef BL_BETA_CLOCKS
+    sc[4] = clock64();
+#endif
+    // L[j,c] = X[P-1-j, P-1-c] into B, 1 / L into A (both ld); element (j = tid & 63, column (tid >> 6) + 4 u)
+    {
+        const int j = tid & 63, cb = tid >> 6;
+        double g[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int c = cb + 4 * u;
+            g[u] = (j < P && c < P && j >= c) ? X[(P - 1 - j) + (size_t)(Pp + 4) * (P - 1 - c)] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int c = cb + 4 * u;
+            if (j < P && c < P) {
+                B[j + (size_t)ld * c] = g[u];
+                A[j + (size_t)ld * c] = (j >= c && j < P - 1 && g[u] != 0.0) ? 1.0 / g[u] : 0.0;
+            }
+        }
+        if (tid < P) { mP_out[tid] = mP[tid]; z_out[tid] = z[tid]; }
+    }
+    __syncthreads();
+#ifdef BL_BETA_CLOCKS
+    if (tid == 0 && call == 3) printf("[beta constrained set-up clocks] reverse + layout %lld solve %lld inverse %lld z %lld L, 1/L %lld\n", sc[1] - sc[0], sc[2] - sc[1], sc[3] - sc[2], sc[4] - sc[3], clock64() - sc[4]);
+#endif
 }
 
 // Exact max / min of a double over the warp in two 32-bit hardware reductions (redux.sync) on an
@@ -746,8 +888,19 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
             src.blk = (uint32_t)(a1 >> 2) + 1u;
             src.pos = a1 & 3;
             __syncwarp();
-            if (lane == 0)
-                for (int i = 0; i < P - 1; ++i) { const int t = tt[i]; const int tmp = is[i]; is[i] = is[t]; is[t] = tmp; }
+            if (lane == 0) {
+                // the swaps themselves are sequential (a target may have been moved by an earlier swap); their
+                // targets are fetched eight at a time so that only the two loads of a swap wait on each other
+                int i = 0;
+                for (; i + 8 <= P - 1; i += 8) {
+                    int t8[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) t8[r] = tt[i + r];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) { const int a = is[i + r], b = is[t8[r]]; is[i + r] = b; is[t8[r]] = a; }
+                }
+                for (; i < P - 1; ++i) { const int t = tt[i]; const int a = is[i], b = is[t]; is[i] = b; is[t] = a; }
+            }
         }
         __syncwarp();
         // Software-pipelined over the coordinates.  Everything of coordinate i + 1 that does not depend on the draw
@@ -868,7 +1021,7 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
 __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, double *v, const double *rhs,
                                      const double *beta_prev, double *beta_out, int P, int ld,
                                      uint64_t seed, uint32_t call, int *status, double *nbuf = nullptr, int nbuf_len = 0,
-                                     double *efast = nullptr)
+                                     double *efast = nullptr, const double *tn_pre = nullptr, bool tn_fast = false)
 {
     __shared__ int ok;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -931,40 +1084,50 @@ __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, do
         return;
     }
 
-    cta_chol_upper(A, P, ld, &ok);
-    if (!ok) { if (tid == 0) *status = 1; return; }
-
-    // S = PP^-1 by solving against the identity (Logit.hpp:338-347; Normal.hpp:106-107)
-    for (int k = tid; k < P * P; k += blockDim.x) B[k % P + (size_t)ld * (k / P)] = (k % P == k / P) ? 1.0 : 0.0;
-    __syncthreads();
-    cta_solve_utu(A, B, P, ld, P);
-
-    // constrained coordinate-wise draw (Logit.hpp:349-399)
-    cta_chol_lower(B, P, ld, &ok);
-    if (!ok) { if (tid == 0) *status = 3; return; }
     const double *L = B;
-    if (tid < 32) {
-        for (int i = lane; i < P; i += 32) mP[i] = rhs[i];
-        __syncwarp();
-        warp_solve_ut(A, mP, P, ld, lane);
-        warp_solve_u(A, mP, P, ld, lane);
-        for (int i = lane; i < P; i += 32) z[i] = beta_prev[i] - mP[i];
-        __syncwarp();
-        warp_solve_l(L, z, P, ld, lane);
-    }
-    __syncthreads();
-    // U is no longer needed: its storage takes 1 / L for the sweeps -- entries on and below the diagonal of the rows
-    // that carry a constraint; zero above the diagonal and in the last row (the free coefficient), so that the sweeps
-    // read a column without masks and take the constraint's direction from the sign of 1 / L alone
     double *iL = A;
-    for (int e2 = tid; e2 < P * P; e2 += blockDim.x) {
-        int j = e2 % P, c = e2 / P;
-        const double l = L[j + (size_t)ld * c];
-        iL[j + (size_t)ld * c] = (j >= c && j < P - 1 && l != 0.0) ? 1.0 / l : 0.0;      // L_jc = 0: no constraint from row j
+    if (P <= 64 && blockDim.x == 256 && tn_fast) {
+        // (mP, L, 1 / L, z) from one blocked factorisation; the rejection normals arrive precomputed (tn_pre) or are
+        // generated here, after the scratch they share with the inverse is free
+        cta_constrained_setup_fast(A, B, mP, z, const_cast<double *>(rhs), beta_prev, A + beta_tn_scratch_offset(P), P, ld, &ok, seed, call);
+        if (!ok) { if (tid == 0) *status = 1; return; }
+        if (tn_pre) for (int m = tid; m < nbuf_len; m += blockDim.x) nbuf[m] = __ldcg(tn_pre + m);
+        else for (int m = tid; m < nbuf_len; m += blockDim.x) nbuf[m] = stream_normal_obs(seed, kTnObs, call, m);
+        __syncthreads();
+    } else {
+        cta_chol_upper(A, P, ld, &ok);
+        if (!ok) { if (tid == 0) *status = 1; return; }
+
+        // S = PP^-1 by solving against the identity (Logit.hpp:338-347; Normal.hpp:106-107)
+        for (int k = tid; k < P * P; k += blockDim.x) B[k % P + (size_t)ld * (k / P)] = (k % P == k / P) ? 1.0 : 0.0;
+        __syncthreads();
+        cta_solve_utu(A, B, P, ld, P);
+
+        // constrained coordinate-wise draw (Logit.hpp:349-399)
+        cta_chol_lower(B, P, ld, &ok);
+        if (!ok) { if (tid == 0) *status = 3; return; }
+        if (tid < 32) {
+            for (int i = lane; i < P; i += 32) mP[i] = rhs[i];
+            __syncwarp();
+            warp_solve_ut(A, mP, P, ld, lane);
+            warp_solve_u(A, mP, P, ld, lane);
+            for (int i = lane; i < P; i += 32) z[i] = beta_prev[i] - mP[i];
+            __syncwarp();
+            warp_solve_l(L, z, P, ld, lane);
+        }
+        __syncthreads();
+        // U is no longer needed: its storage takes 1 / L for the sweeps -- entries on and below the diagonal of the
+        // rows that carry a constraint; zero above the diagonal and in the last row (the free coefficient), so that
+        // the sweeps read a column without masks and take the constraint's direction from the sign of 1 / L alone
+        for (int e2 = tid; e2 < P * P; e2 += blockDim.x) {
+            int j = e2 % P, c = e2 / P;
+            const double l = L[j + (size_t)ld * c];
+            iL[j + (size_t)ld * c] = (j >= c && j < P - 1 && l != 0.0) ? 1.0 / l : 0.0;      // L_jc = 0: no constraint from row j
+        }
+        // the rejection normals of the sweeps (see warp_constrained_sweeps), all threads
+        for (int m = tid; m < nbuf_len; m += blockDim.x) nbuf[m] = tn_pre ? __ldcg(tn_pre + m) : stream_normal_obs(seed, kTnObs, call, m);
+        __syncthreads();
     }
-    // the rejection normals of the sweeps (see warp_constrained_sweeps), all threads
-    for (int m = tid; m < nbuf_len; m += blockDim.x) nbuf[m] = stream_normal_obs(seed, kTnObs, call, m);
-    __syncthreads();
     if (tid < 32) {
         int *is = (int *)e;                  // the permutation lives in the e[] scratch as ints
         if (P <= 64) warp_constrained_sweeps<2>(L, iL, z, beta_prev, beta_out, is, src, P, ld, lane, nbuf, nbuf_len, seed, call);
