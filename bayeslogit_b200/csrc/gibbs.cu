@@ -283,7 +283,7 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
         default: peer_stage<0>(pw, A, rhs, P0, base_rhs, add_tail, P, ld); break;
         }
         __syncthreads();
-        cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len, efast, tn_pre, SMEM && tn_fast);
+        cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len, efast, tn_pre, SMEM ? tn_fast : 0);
         return;
     }
     if (fast) {
@@ -348,7 +348,7 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
 #ifdef BL_BETA_CLOCKS
     if (threadIdx.x == 0 && call == 3) printf("[beta clocks] load %lld\n", clock64() - k0);
 #endif
-    cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len, nullptr, tn_pre, SMEM && tn_fast);
+    cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len, nullptr, tn_pre, SMEM ? tn_fast : 0);
 }
 
 // rejection normals of one constrained beta draw: normal m of the stream (seed, obs 2^64-3, call), gibbs_beta.cuh
@@ -601,7 +601,7 @@ struct Sweep {
             cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
             cudaLaunchKernelEx(&cfg, k_beta_draw<true>, mode, (const double *)acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
                                beta_out, gwork, P, seed, call, status, pending, (int64_t)0,
-                               (const double *)(tn ? tnbuf : nullptr), 1);
+                               (const double *)(tn ? tnbuf : nullptr), getenv("BL_BETA_NO_SPEC") ? 3 : 1);
         } else
             k_beta_draw<false><<<1, 256, 0, st>>>(mode, acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
                                                   beta_out, gwork, P, seed, call, status, pending, 0, nullptr, 0);
@@ -832,7 +832,7 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
             k_gram_reduce<<<dim3(cdiv((int64_t)P * P, 32), chains), 256, 0, st>>>(acc, nullptr, part, P, nt, slabs_total, PeerPush{}, packed ? 1 : 0);
             if (tm) cudaEventRecord(ev[3], st);
             k_beta_draw<true><<<chains, 256, beta_smem, st>>>(mode, acc, P0, bP, 0, bprev, bcur, nullptr, P, seed, t, status,
-                                                           PeerWait{}, bstride, nullptr, 1);
+                                                           PeerWait{}, bstride, nullptr, getenv("BL_BETA_NO_SPEC") ? 3 : 1);
             count_launch(3);
             if (tm) cudaEventRecord(ev[4], st);
             bpsi = bcur;

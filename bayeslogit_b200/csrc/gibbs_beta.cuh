@@ -843,6 +843,137 @@ __device__ __forceinline__ double warp_min_f64(double v)
 // cmin < 1, cmax > -1 and cmax - cmin >= 1/2, up to three more; otherwise, or after four misses, the inverse-CDF /
 // tail sampler on the beta stream as before.  Every branch returns an exact truncated normal, so the
 // draw's distribution is unchanged; the oracle (draw_beta_constrained) mirrors the rule variate for variate.
+// One sweep's random order (Logit.hpp:367-374): is[i] <-> is[r.flat(i, P)] for i = 0 .. P-2, one warp.
+__device__ __forceinline__ void warp_sweep_permutation(int *is, PhiloxSource &src, int P, int lane)
+{
+    // r.flat(i, P) for i = 0 .. P-2 takes one stream word each, words a0 .. a0 + P - 2 of the beta stream: lane l
+    // forms the swap targets of i = l, l + 32, ... straight from the counter (the block that holds its word),
+    // the stream is moved past them, and lane 0 is left with the swaps alone -- drawn one after the other
+    // by every lane this loop was a third of the whole constrained draw (BL_BETA_CLOCKS: 15 500 of 49 000
+    // cycles per sweep at P = 64).
+    {
+        const int a0 = 4 * ((int)src.blk - 1) + src.pos;
+        int *tt = is + P;
+        for (int i = lane; i < P - 1; i += 32) {
+            const int a = a0 + i;
+            const uint4 b = philox_block_ool(src.c0, src.c1, (uint32_t)(a >> 2), src.c3, src.key);
+            const uint32_t wv = (a & 3) == 0 ? b.x : (a & 3) == 1 ? b.y : (a & 3) == 2 ? b.z : b.w;
+            const double f = (double)i + ((double)P - (double)i) * word_to_unif(wv);
+            unsigned t = (unsigned)f;
+            if (t > (unsigned)(P - 1)) t = (unsigned)(P - 1);
+            tt[i] = (int)t;
+        }
+        const int a1 = a0 + P - 1;
+        src.buf = philox_block_ool(src.c0, src.c1, (uint32_t)(a1 >> 2), src.c3, src.key);
+        src.blk = (uint32_t)(a1 >> 2) + 1u;
+        src.pos = a1 & 3;
+        __syncwarp();
+        if (lane == 0) {
+            // the swaps themselves are sequential (a target may have been moved by an earlier swap); their
+            // targets are fetched eight at a time so that only the two loads of a swap wait on each other
+            int i = 0;
+            for (; i + 8 <= P - 1; i += 8) {
+                int t8[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) t8[r] = tt[i + r];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) { const int a = is[i + r], b = is[t8[r]]; is[i + r] = b; is[t8[r]] = a; }
+            }
+            for (; i < P - 1; ++i) { const int t = tt[i]; const int a = is[i], b = is[t]; is[i] = b; is[t] = a; }
+        }
+    }
+    __syncwarp();
+}
+
+// Coordinates i0 .. i1-1 of one sweep (in the order is[]), one warp, beta and z in registers (lane l owns entries l,
+// l + 32, ...).  Returns with beta, z, mnorm and the stream advanced.
+template <int KP>
+__device__ __forceinline__ void warp_seq_range(const double *L, const double *iL, const int *is, int i0, int i1,
+                                               double (&beta)[KP], double (&z)[KP], int &mnorm, PhiloxSource &src,
+                                               int P, int ld, int lane, const double *nbuf, int nbuf_len,
+                                               uint64_t seed, uint32_t call, int &n_fall, int &n_rej)
+{
+    if (i0 >= i1) return;
+    // two register sets (current / next coordinate) used alternately: no copies at the end of an iteration
+    struct Col { double lu[KP], il[KP]; bool pos[KP], neg[KP]; double z1; int c; };
+    auto fetch = [&](Col &k, int c) {
+        k.c = c;
+#pragma unroll
+        for (int q = 0; q < KP; ++q) {
+            const int j = lane + 32 * q;
+            k.lu[q] = j < P ? L[j + (size_t)ld * c] : 0.0;               // L is zero above its diagonal
+            k.il[q] = j < P ? iL[j + (size_t)ld * c] : 0.0;              // zero where no constraint applies
+            k.pos[q] = k.il[q] > 0.0;
+            k.neg[q] = k.il[q] < 0.0;
+        }
+        double zc = z[0];
+#pragma unroll
+        for (int q = 1; q < KP; ++q) zc = (c >> 5) == q ? z[q] : zc;
+        k.z1 = __shfl_sync(0xffffffffu, zc, c & 31);
+    };
+    double Z0 = mnorm < nbuf_len ? nbuf[mnorm] : tn_normal_spot(seed, call, mnorm);
+    auto step = [&](const Col &k, Col &kn, int i) {
+        // the next coordinate: index, column, signs, its own current value (stale and unused when i + 1 == P),
+        // and its normal assuming a hit
+        fetch(kn, i + 1 < i1 ? is[i + 1] : k.c);
+        const double Zn = mnorm + 1 < nbuf_len ? nbuf[mnorm + 1] : 0.0;
+        const double z1 = k.z1, u = Z0 - z1;
+        double bnew[KP];
+        bool inside = true;
+#pragma unroll
+        for (int q = 0; q < KP; ++q) {
+            const double v = fma(beta[q], k.il[q], u);
+            inside = inside & ((v > 0.0) | !k.pos[q]) & ((v < 0.0) | !k.neg[q]);     // bitwise: no short-circuit branches
+            bnew[q] = fma(k.lu[q], u, beta[q]);
+        }
+        ++mnorm;
+        double z2 = Z0;
+        const bool hit = __all_sync(0xffffffffu, inside);
+        if (__builtin_expect(hit, 1)) {
+#pragma unroll
+            for (int q = 0; q < KP; ++q) beta[q] = bnew[q];
+        } else {
+            ++n_fall;
+            double cmin = -INFINITY, cmax = INFINITY;
+#pragma unroll
+            for (int q = 0; q < KP; ++q) {
+                const double c1 = fma(-beta[q], k.il[q], z1);
+                if (k.pos[q] && c1 > cmin) cmin = c1;
+                else if (k.neg[q] && c1 < cmax) cmax = c1;
+            }
+            cmin = warp_max_f64(cmin);
+            cmax = warp_min_f64(cmax);
+            bool got = false;
+            if (cmin < cmax && cmin < 1.0 && cmax > -1.0 && cmax - cmin >= 0.5) {
+                for (int tr = 1; tr < 4 && !got; ++tr) {
+                    const double Z = mnorm < nbuf_len ? nbuf[mnorm] : tn_normal_spot(seed, call, mnorm);
+                    ++mnorm;
+                    if (Z > cmin && Z < cmax) { z2 = Z; got = true; }
+                }
+            }
+            if (!got) ++n_rej;
+            if (!got) z2 = tnorm_std_warp(src, cmin, cmax, lane);
+            const double dz = z2 - z1;
+#pragma unroll
+            for (int q = 0; q < KP; ++q) beta[q] = fma(k.lu[q], dz, beta[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < KP; ++q)
+            if (lane + 32 * q == k.c) z[q] = z2;
+        // the next coordinate's normal: the prefetched one after a hit (mnorm advanced by exactly one)
+        Z0 = hit ? Zn : nbuf[mnorm < nbuf_len ? mnorm : 0];
+        if (__builtin_expect(mnorm >= nbuf_len && i + 1 < i1, 0)) Z0 = tn_normal_spot(seed, call, mnorm);
+    };
+    Col ka, kb;
+    fetch(ka, is[i0]);
+    int i = i0;
+    for (; i + 1 < i1; i += 2) {
+        step(ka, kb, i);
+        step(kb, ka, i + 1);
+    }
+    if (i < i1) step(ka, kb, i);
+}
+
 template <int KP>
 __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const double *iL, const double *z_in,
                                                         const double *beta_prev, double *beta_out, int *is,
@@ -850,8 +981,9 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
                                                         const double *nbuf, int nbuf_len, uint64_t seed, uint32_t call)
 {
     int mnorm = 0;                         // normals of the rejection stream consumed so far (warp-uniform)
+    int n_fall = 0, n_rej = 0;          // first normals that missed, inverse-CDF draws (BL_BETA_CLOCKS prints them)
 #ifdef BL_BETA_CLOCKS
-    long long t_perm = 0, t_coord = 0; int n_fall = 0, n_rej = 0;
+    long long t_perm = 0, t_coord = 0;
 #endif
     double beta[KP], z[KP];
 #pragma unroll
@@ -866,43 +998,7 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
 #ifdef BL_BETA_CLOCKS
         long long tp0 = clock64();
 #endif
-        // r.flat(i, P) for i = 0 .. P-2 takes one stream word each, words a0 .. a0 + P - 2 of the beta stream: lane l
-        // forms the swap targets of i = l, l + 32, ... straight from the counter (the block that holds its word),
-        // the stream is moved past them, and lane 0 is left with the swaps alone -- drawn one after the other
-        // by every lane this loop was a third of the whole constrained draw (BL_BETA_CLOCKS: 15 500 of 49 000
-        // cycles per sweep at P = 64).
-        {
-            const int a0 = 4 * ((int)src.blk - 1) + src.pos;
-            int *tt = is + P;
-            for (int i = lane; i < P - 1; i += 32) {
-                const int a = a0 + i;
-                const uint4 b = philox_block_ool(src.c0, src.c1, (uint32_t)(a >> 2), src.c3, src.key);
-                const uint32_t wv = (a & 3) == 0 ? b.x : (a & 3) == 1 ? b.y : (a & 3) == 2 ? b.z : b.w;
-                const double f = (double)i + ((double)P - (double)i) * word_to_unif(wv);
-                unsigned t = (unsigned)f;
-                if (t > (unsigned)(P - 1)) t = (unsigned)(P - 1);
-                tt[i] = (int)t;
-            }
-            const int a1 = a0 + P - 1;
-            src.buf = philox_block_ool(src.c0, src.c1, (uint32_t)(a1 >> 2), src.c3, src.key);
-            src.blk = (uint32_t)(a1 >> 2) + 1u;
-            src.pos = a1 & 3;
-            __syncwarp();
-            if (lane == 0) {
-                // the swaps themselves are sequential (a target may have been moved by an earlier swap); their
-                // targets are fetched eight at a time so that only the two loads of a swap wait on each other
-                int i = 0;
-                for (; i + 8 <= P - 1; i += 8) {
-                    int t8[8];
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) t8[r] = tt[i + r];
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) { const int a = is[i + r], b = is[t8[r]]; is[i + r] = b; is[t8[r]] = a; }
-                }
-                for (; i < P - 1; ++i) { const int t = tt[i]; const int a = is[i], b = is[t]; is[i] = b; is[t] = a; }
-            }
-        }
-        __syncwarp();
+        warp_sweep_permutation(is, src, P, lane);
         // Software-pipelined over the coordinates.  Everything of coordinate i + 1 that does not depend on the draw
         // of coordinate i is fetched while coordinate i is decided: its index, its column of L and 1 / L, the signs
         // of that column, its own current value z1 (each index occurs once per sweep, so z[c'] is not touched by
@@ -917,88 +1013,7 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
 #ifdef BL_BETA_CLOCKS
         long long tp1 = clock64(); t_perm += tp1 - tp0;
 #endif
-        // two register sets (current / next coordinate) used alternately: no copies at the end of an iteration
-        struct Col { double lu[KP], il[KP]; bool pos[KP], neg[KP]; double z1; int c; };
-        auto fetch = [&](Col &k, int c) {
-            k.c = c;
-#pragma unroll
-            for (int q = 0; q < KP; ++q) {
-                const int j = lane + 32 * q;
-                k.lu[q] = j < P ? L[j + (size_t)ld * c] : 0.0;               // L is zero above its diagonal
-                k.il[q] = j < P ? iL[j + (size_t)ld * c] : 0.0;              // zero where no constraint applies
-                k.pos[q] = k.il[q] > 0.0;
-                k.neg[q] = k.il[q] < 0.0;
-            }
-            double zc = z[0];
-#pragma unroll
-            for (int q = 1; q < KP; ++q) zc = (c >> 5) == q ? z[q] : zc;
-            k.z1 = __shfl_sync(0xffffffffu, zc, c & 31);
-        };
-        double Z0 = mnorm < nbuf_len ? nbuf[mnorm] : tn_normal_spot(seed, call, mnorm);
-        auto step = [&](const Col &k, Col &kn, int i) {
-            // the next coordinate: index, column, signs, its own current value (stale and unused when i + 1 == P),
-            // and its normal assuming a hit
-            fetch(kn, i + 1 < P ? is[i + 1] : k.c);
-            const double Zn = mnorm + 1 < nbuf_len ? nbuf[mnorm + 1] : 0.0;
-            const double z1 = k.z1, u = Z0 - z1;
-            double bnew[KP];
-            bool inside = true;
-#pragma unroll
-            for (int q = 0; q < KP; ++q) {
-                const double v = fma(beta[q], k.il[q], u);
-                inside = inside & ((v > 0.0) | !k.pos[q]) & ((v < 0.0) | !k.neg[q]);     // bitwise: no short-circuit branches
-                bnew[q] = fma(k.lu[q], u, beta[q]);
-            }
-            ++mnorm;
-            double z2 = Z0;
-            const bool hit = __all_sync(0xffffffffu, inside);
-            if (__builtin_expect(hit, 1)) {
-#pragma unroll
-                for (int q = 0; q < KP; ++q) beta[q] = bnew[q];
-            } else {
-#ifdef BL_BETA_CLOCKS
-                ++n_fall;
-#endif
-                double cmin = -INFINITY, cmax = INFINITY;
-#pragma unroll
-                for (int q = 0; q < KP; ++q) {
-                    const double c1 = fma(-beta[q], k.il[q], z1);
-                    if (k.pos[q] && c1 > cmin) cmin = c1;
-                    else if (k.neg[q] && c1 < cmax) cmax = c1;
-                }
-                cmin = warp_max_f64(cmin);
-                cmax = warp_min_f64(cmax);
-                bool got = false;
-                if (cmin < cmax && cmin < 1.0 && cmax > -1.0 && cmax - cmin >= 0.5) {
-                    for (int tr = 1; tr < 4 && !got; ++tr) {
-                        const double Z = mnorm < nbuf_len ? nbuf[mnorm] : tn_normal_spot(seed, call, mnorm);
-                        ++mnorm;
-                        if (Z > cmin && Z < cmax) { z2 = Z; got = true; }
-                    }
-                }
-#ifdef BL_BETA_CLOCKS
-                if (!got) ++n_rej;
-#endif
-                if (!got) z2 = tnorm_std_warp(src, cmin, cmax, lane);
-                const double dz = z2 - z1;
-#pragma unroll
-                for (int q = 0; q < KP; ++q) beta[q] = fma(k.lu[q], dz, beta[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < KP; ++q)
-                if (lane + 32 * q == k.c) z[q] = z2;
-            // the next coordinate's normal: the prefetched one after a hit (mnorm advanced by exactly one)
-            Z0 = hit ? Zn : nbuf[mnorm < nbuf_len ? mnorm : 0];
-            if (__builtin_expect(mnorm >= nbuf_len && i + 1 < P, 0)) Z0 = tn_normal_spot(seed, call, mnorm);
-        };
-        Col ka, kb;
-        fetch(ka, is[0]);
-        int i = 0;
-        for (; i + 1 < P; i += 2) {
-            step(ka, kb, i);
-            step(kb, ka, i + 1);
-        }
-        if (i < P) step(ka, kb, i);
+        warp_seq_range<KP>(L, iL, is, 0, P, beta, z, mnorm, src, P, ld, lane, nbuf, nbuf_len, seed, call, n_fall, n_rej);
 #ifdef BL_BETA_CLOCKS
         t_coord += clock64() - tp1;
 #endif
@@ -1013,6 +1028,158 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
     }
 }
 
+// The P sweeps of the constrained draw on the whole CTA (P <= 64, 256 threads), SPECULATING on the common outcome:
+// in a well-identified model nearly every coordinate accepts its first rejection normal, and then a sweep is nothing
+// but the chain  beta <- beta + L_c (Z - z_c)  over its P coordinates with one test per coordinate that always
+// passes.  So, per sweep, after the permutation (warp 0):
+//   * u_i = Z_i - z_{c_i} for all remaining coordinates at once (a coordinate occurs once per sweep, so its z is
+//     the committed one; a hit consumes exactly one normal, so Z_i is normal number mnorm + i - i_s);
+//   * warp w takes the eight coordinates [i_s + 8 w, i_s + 8 w + 8): it replays the chain of the coordinates
+//     before its block -- the same FMAs in the same order as the sequential loop, so the same bits -- and then tests
+//     and applies its own eight; the first miss of the sweep is found with a shared-memory minimum;
+//   * no miss: the last warp's chain is the sweep's result.  A miss at i_f: warp 0 replays the chain up to i_f,
+//     decides coordinate i_f the long way (window, further tries, inverse CDF -- warp_seq_range on that one
+//     coordinate) and the speculation restarts behind it.  After three misses in one sweep the rest of the sweep
+//     (and the whole next sweep, if this one had more) runs in the sequential loop: models whose constraints bind
+//     pay one wasted pass per sweep.
+// Identical variates, identical operation order, hence bit-identical to warp_constrained_sweeps (BL_BETA_NO_SPEC
+// selects that one; test_constrained_draw_speculation_is_bit_identical).
+__device__ __forceinline__ void cta_constrained_sweeps_spec(const double *L, const double *iL, const double *z_in,
+                                                            const double *beta_prev, double *beta_out, int *is,
+                                                            double *work, PhiloxSource &src, int P, int ld,
+                                                            const double *nbuf, int nbuf_len, uint64_t seed, uint32_t call)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double *sb = work, *sz = work + 64, *su = work + 128, *sbf = work + 192;       // committed beta, z; u; a pass's result
+    int *ctl = reinterpret_cast<int *>(work + 256);                               // [0] first miss, [1] mnorm, [2] i_s, [3] mode
+    int n_fall = 0, n_rej = 0;
+    if (tid < 64) {
+        sb[tid] = tid < P ? beta_prev[tid] : 0.0;
+        sz[tid] = tid < P ? z_in[tid] : 0.0;
+        if (tid < P) is[tid] = tid;
+    }
+    if (tid == 0) { ctl[1] = 0; ctl[3] = 0; }
+    __syncthreads();
+    for (int k = 0; k < P; ++k) {
+        if (warp == 0) warp_sweep_permutation(is, src, P, lane);
+        if (tid == 0) ctl[2] = 0;
+        __syncthreads();
+        int misses = 0;
+        for (;;) {
+            const int i_s = ctl[2], mnorm = ctl[1];
+            if (i_s >= P) break;
+            const bool sequential = ctl[3] != 0 || misses >= 3 || mnorm + (P - i_s) > nbuf_len;
+            if (sequential) {
+                // the rest of this sweep in the one-warp loop
+                if (warp == 0) {
+                    double beta[2], z[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) { beta[q] = sb[lane + 32 * q]; z[q] = sz[lane + 32 * q]; }
+                    int mn = mnorm, nf = 0;
+                    warp_seq_range<2>(L, iL, is, i_s, P, beta, z, mn, src, P, ld, lane, nbuf, nbuf_len, seed, call, nf, n_rej);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) { sb[lane + 32 * q] = beta[q]; sz[lane + 32 * q] = z[q]; }
+                    if (lane == 0) { ctl[1] = mn; ctl[2] = P; ctl[3] = (misses + nf) > 6 ? 1 : 0; }
+                    n_fall += nf;
+                }
+                __syncthreads();
+                break;
+            }
+            // ---- one speculative pass over the coordinates [i_s, P) ----
+            if (tid < P - i_s) su[i_s + tid] = nbuf[mnorm + tid] - sz[is[i_s + tid]];
+            if (tid == 0) ctl[0] = P;
+            __syncthreads();
+            {
+                const int a = i_s + 8 * warp, b = min(a + 8, P);
+                if (a < P) {
+                    double b0 = sb[lane], b1 = sb[lane + 32];
+                    const bool v0 = lane < P, v1 = lane + 32 < P;
+                    // the chain of the coordinates before this warp's block, four columns' loads in flight
+                    int i = i_s;
+                    for (; i + 4 <= a; i += 4) {
+                        int c[4]; double u[4], l0[4], l1[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) { c[r] = is[i + r]; u[r] = su[i + r]; }
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            l0[r] = v0 ? L[lane + (size_t)ld * c[r]] : 0.0;
+                            l1[r] = v1 ? L[lane + 32 + (size_t)ld * c[r]] : 0.0;
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) { b0 = fma(l0[r], u[r], b0); b1 = fma(l1[r], u[r], b1); }
+                    }
+                    for (; i < a; ++i) {
+                        const int c = is[i];
+                        const double u = su[i];
+                        b0 = fma(v0 ? L[lane + (size_t)ld * c] : 0.0, u, b0);
+                        b1 = fma(v1 ? L[lane + 32 + (size_t)ld * c] : 0.0, u, b1);
+                    }
+                    // this warp's own coordinates: test, then apply
+                    bool clean = true;
+                    for (i = a; i < b; ++i) {
+                        const int c = is[i];
+                        const double u = su[i];
+                        const double il0 = v0 ? iL[lane + (size_t)ld * c] : 0.0, il1 = v1 ? iL[lane + 32 + (size_t)ld * c] : 0.0;
+                        const double l0 = v0 ? L[lane + (size_t)ld * c] : 0.0, l1 = v1 ? L[lane + 32 + (size_t)ld * c] : 0.0;
+                        const double w0 = fma(b0, il0, u), w1 = fma(b1, il1, u);
+                        const bool inside = ((w0 > 0.0) | !(il0 > 0.0)) & ((w0 < 0.0) | !(il0 < 0.0)) &
+                                            ((w1 > 0.0) | !(il1 > 0.0)) & ((w1 < 0.0) | !(il1 < 0.0));
+                        if (!__all_sync(0xffffffffu, inside)) {
+                            if (lane == 0) atomicMin(&ctl[0], i);
+                            clean = false;
+                            break;
+                        }
+                        b0 = fma(l0, u, b0);
+                        b1 = fma(l1, u, b1);
+                    }
+                    if (clean && b == P) { sbf[lane] = b0; sbf[lane + 32] = b1; }
+                }
+            }
+            __syncthreads();
+            const int i_f = ctl[0];
+            if (i_f >= P) {
+                // every remaining coordinate accepted its first normal: the last block's chain is the new beta
+                if (tid < 64) sb[tid] = sbf[tid];
+                __syncthreads();                                                  // su / sz are read and written by different threads
+                if (tid < P - i_s) sz[is[i_s + tid]] = nbuf[mnorm + tid];
+                if (tid == 0) { ctl[1] = mnorm + (P - i_s); ctl[2] = P; if (misses == 0) ctl[3] = 0; }
+                __syncthreads();
+                break;
+            }
+            // a miss at i_f: warp 0 replays the accepted prefix and decides coordinate i_f the long way
+            if (warp == 0) {
+                double beta[2], z[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) beta[q] = sb[lane + 32 * q];
+                for (int i = i_s; i < i_f; ++i) {
+                    const int c = is[i];
+                    const double u = su[i];
+                    beta[0] = fma(lane < P ? L[lane + (size_t)ld * c] : 0.0, u, beta[0]);
+                    beta[1] = fma(lane + 32 < P ? L[lane + 32 + (size_t)ld * c] : 0.0, u, beta[1]);
+                }
+                __syncwarp();
+                for (int i = i_s + lane; i < i_f; i += 32) sz[is[i]] = nbuf[mnorm + (i - i_s)];
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 2; ++q) z[q] = sz[lane + 32 * q];
+                int mn = mnorm + (i_f - i_s), nf = 0;
+                warp_seq_range<2>(L, iL, is, i_f, i_f + 1, beta, z, mn, src, P, ld, lane, nbuf, nbuf_len, seed, call, nf, n_rej);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) { sb[lane + 32 * q] = beta[q]; sz[lane + 32 * q] = z[q]; }
+                if (lane == 0) { ctl[1] = mn; ctl[2] = i_f + 1; }
+                n_fall += nf;
+            }
+            ++misses;
+            __syncthreads();
+        }
+    }
+    if (tid < P) beta_out[tid] = sb[tid];
+#ifdef BL_BETA_CLOCKS
+    if (tid == 0 && call == 3) printf("[beta constrained spec] first normal missed %d times, %d inverse-CDF draws\n", n_fall, n_rej);
+#endif
+    __syncthreads();
+}
+
 // One beta draw.  Workspace (all column-major, ld = P):
 //   A  [P*P]  in: PP (posterior precision, full symmetric)   -> U
 //   B  [P*P]  scratch: S = PP^-1 -> L                        (constrained, mvn)
@@ -1021,8 +1188,9 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
 __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, double *v, const double *rhs,
                                      const double *beta_prev, double *beta_out, int P, int ld,
                                      uint64_t seed, uint32_t call, int *status, double *nbuf = nullptr, int nbuf_len = 0,
-                                     double *efast = nullptr, const double *tn_pre = nullptr, bool tn_fast = false)
+                                     double *efast = nullptr, const double *tn_pre = nullptr, int tn_flags = 0)
 {
+    const bool tn_fast = (tn_flags & 1) != 0;          // bit 0: fast set-up (+ speculative sweeps unless bit 1)
     __shared__ int ok;
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) ok = 1;
@@ -1086,6 +1254,8 @@ __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, do
 
     const double *L = B;
     double *iL = A;
+    // the scratch of the fast set-up is free again when the sweeps start: the speculative sweeps take it
+    double *spec_work = (P <= 64 && blockDim.x == 256 && tn_fast && !(tn_flags & 2)) ? A + beta_tn_scratch_offset(P) : nullptr;
     if (P <= 64 && blockDim.x == 256 && tn_fast) {
         // (mP, L, 1 / L, z) from one blocked factorisation; the rejection normals arrive precomputed (tn_pre) or are
         // generated here, after the scratch they share with the inverse is free
@@ -1127,6 +1297,10 @@ __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, do
         // the rejection normals of the sweeps (see warp_constrained_sweeps), all threads
         for (int m = tid; m < nbuf_len; m += blockDim.x) nbuf[m] = tn_pre ? __ldcg(tn_pre + m) : stream_normal_obs(seed, kTnObs, call, m);
         __syncthreads();
+    }
+    if (spec_work) {
+        cta_constrained_sweeps_spec(L, iL, z, beta_prev, beta_out, (int *)e, spec_work, src, P, ld, nbuf, nbuf_len, seed, call);
+        return;
     }
     if (tid < 32) {
         int *is = (int *)e;                  // the permutation lives in the e[] scratch as ints

@@ -160,6 +160,27 @@ def test_mlogit_chain_matches_oracle_at_the_benchmarked_shape(gapi):
     close(b, bo); close(w, wo)
 
 
+@pytest.mark.parametrize("N,P,active", [(20_000, 64, False), (20_000, 64, True), (8_000, 32, True), (5_000, 7, True)])
+def test_constrained_draw_speculation_is_bit_identical(gapi, N, P, active):
+    """cta_constrained_sweeps_spec (whole CTA, speculating that every coordinate accepts its first rejection normal,
+    replaying the chain of FMAs in the sequential order) against the one-warp sequential sweeps (BL_BETA_NO_SPEC):
+    same variates, same operation order, same bits (Logit.hpp:366-399).  `active`: a model whose constraints bind
+    (negative coefficients), so misses, re-speculation and the sequential fallback all run."""
+    import os
+    rng = np.random.default_rng(900 + P + int(active))
+    X = np.c_[rng.standard_normal((N, P - 1)) / np.sqrt(P), np.ones(N)]
+    bt = rng.normal(0, 1.0, P) if active else np.abs(rng.normal(0, 1.0, P)) + 0.5
+    y = (rng.random(N) < 1 / (1 + np.exp(-X @ bt))).astype(float)
+    m0, P0 = np.zeros(P), 0.01 * np.eye(P)
+    w1, b1 = gapi.logit_gibbs(y, X, np.ones(N), m0, P0, 5, 2, seed=31, keep_w=False)
+    os.environ["BL_BETA_NO_SPEC"] = "1"
+    try:
+        w2, b2 = gapi.logit_gibbs(y, X, np.ones(N), m0, P0, 5, 2, seed=31, keep_w=False)
+    finally:
+        del os.environ["BL_BETA_NO_SPEC"]
+    assert np.array_equal(b1, b2)
+
+
 def test_mlogit_fused_psi_and_next_offsets_equal_the_separate_kernels(gapi):
     """k_xbeta_mma<true> (psi_j, exp(psi_j) cached, offsets and tilt of the next category from one pass over X)
     against the psi kernel + k_mlogit_offsets per category (BL_MLOGIT_UNFUSED): same exp() of the same numbers in
