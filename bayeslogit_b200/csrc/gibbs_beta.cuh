@@ -844,45 +844,50 @@ __device__ __forceinline__ double warp_min_f64(double v)
 // tail sampler on the beta stream as before.  Every branch returns an exact truncated normal, so the
 // draw's distribution is unchanged; the oracle (draw_beta_constrained) mirrors the rule variate for variate.
 // One sweep's random order (Logit.hpp:367-374): is[i] <-> is[r.flat(i, P)] for i = 0 .. P-2, one warp.
-__device__ __forceinline__ void warp_sweep_permutation(int *is, PhiloxSource &src, int P, int lane)
+// r.flat(i, P) takes one stream word each, words a0 .. a0 + P - 2 of the beta stream: lane l forms the swap targets of
+// i = l, l + 32, ... straight from the counter (the block that holds its word) and lane 0 is left with the swaps
+// alone -- drawn one after the other by every lane this was a third of the whole constrained draw (BL_BETA_CLOCKS:
+// 15 500 of 49 000 cycles per sweep at P = 64).  `src` only supplies the stream's key and counter words.
+__device__ __forceinline__ void warp_sweep_permutation_at(int *is, int *tt, int a0, const PhiloxSource &src, int P, int lane)
 {
-    // r.flat(i, P) for i = 0 .. P-2 takes one stream word each, words a0 .. a0 + P - 2 of the beta stream: lane l
-    // forms the swap targets of i = l, l + 32, ... straight from the counter (the block that holds its word),
-    // the stream is moved past them, and lane 0 is left with the swaps alone -- drawn one after the other
-    // by every lane this loop was a third of the whole constrained draw (BL_BETA_CLOCKS: 15 500 of 49 000
-    // cycles per sweep at P = 64).
-    {
-        const int a0 = 4 * ((int)src.blk - 1) + src.pos;
-        int *tt = is + P;
-        for (int i = lane; i < P - 1; i += 32) {
-            const int a = a0 + i;
-            const uint4 b = philox_block_ool(src.c0, src.c1, (uint32_t)(a >> 2), src.c3, src.key);
-            const uint32_t wv = (a & 3) == 0 ? b.x : (a & 3) == 1 ? b.y : (a & 3) == 2 ? b.z : b.w;
-            const double f = (double)i + ((double)P - (double)i) * word_to_unif(wv);
-            unsigned t = (unsigned)f;
-            if (t > (unsigned)(P - 1)) t = (unsigned)(P - 1);
-            tt[i] = (int)t;
-        }
-        const int a1 = a0 + P - 1;
-        src.buf = philox_block_ool(src.c0, src.c1, (uint32_t)(a1 >> 2), src.c3, src.key);
-        src.blk = (uint32_t)(a1 >> 2) + 1u;
-        src.pos = a1 & 3;
-        __syncwarp();
-        if (lane == 0) {
-            // the swaps themselves are sequential (a target may have been moved by an earlier swap); their
-            // targets are fetched eight at a time so that only the two loads of a swap wait on each other
-            int i = 0;
-            for (; i + 8 <= P - 1; i += 8) {
-                int t8[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) t8[r] = tt[i + r];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) { const int a = is[i + r], b = is[t8[r]]; is[i + r] = b; is[t8[r]] = a; }
-            }
-            for (; i < P - 1; ++i) { const int t = tt[i]; const int a = is[i], b = is[t]; is[i] = b; is[t] = a; }
-        }
+    for (int i = lane; i < P - 1; i += 32) {
+        const int a = a0 + i;
+        const uint4 b = philox_block_ool(src.c0, src.c1, (uint32_t)(a >> 2), src.c3, src.key);
+        const uint32_t wv = (a & 3) == 0 ? b.x : (a & 3) == 1 ? b.y : (a & 3) == 2 ? b.z : b.w;
+        const double f = (double)i + ((double)P - (double)i) * word_to_unif(wv);
+        unsigned t = (unsigned)f;
+        if (t > (unsigned)(P - 1)) t = (unsigned)(P - 1);
+        tt[i] = (int)t;
     }
     __syncwarp();
+    if (lane == 0) {
+        // the swaps themselves are sequential (a target may have been moved by an earlier swap); their
+        // targets are fetched eight at a time so that only the two loads of a swap wait on each other
+        int i = 0;
+        for (; i + 8 <= P - 1; i += 8) {
+            int t8[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) t8[r] = tt[i + r];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { const int a = is[i + r], b = is[t8[r]]; is[i + r] = b; is[t8[r]] = a; }
+        }
+        for (; i < P - 1; ++i) { const int t = tt[i]; const int a = is[i], b = is[t]; is[i] = b; is[t] = a; }
+    }
+    __syncwarp();
+}
+// absolute index of the stream's next word / the stream moved to an absolute word index
+__device__ __forceinline__ int philox_tell(const PhiloxSource &src) { return 4 * ((int)src.blk - 1) + src.pos; }
+__device__ __forceinline__ void philox_seek(PhiloxSource &src, int a)
+{
+    src.buf = philox_block_ool(src.c0, src.c1, (uint32_t)(a >> 2), src.c3, src.key);
+    src.blk = (uint32_t)(a >> 2) + 1u;
+    src.pos = a & 3;
+}
+__device__ __forceinline__ void warp_sweep_permutation(int *is, PhiloxSource &src, int P, int lane)
+{
+    const int a0 = philox_tell(src);
+    warp_sweep_permutation_at(is, is + P, a0, src, P, lane);
+    philox_seek(src, a0 + P - 1);
 }
 
 // Coordinates i0 .. i1-1 of one sweep (in the order is[]), one warp, beta and z in registers (lane l owns entries l,
@@ -1031,17 +1036,20 @@ __device__ __forceinline__ void warp_constrained_sweeps(const double *L, const d
 // The P sweeps of the constrained draw on the whole CTA (P <= 64, 256 threads), SPECULATING on the common outcome:
 // in a well-identified model nearly every coordinate accepts its first rejection normal, and then a sweep is nothing
 // but the chain  beta <- beta + L_c (Z - z_c)  over its P coordinates with one test per coordinate that always
-// passes.  So, per sweep, after the permutation (warp 0):
+// passes.  So, per sweep (warps 0-6, named barrier 1 over their 224 threads):
 //   * u_i = Z_i - z_{c_i} for all remaining coordinates at once (a coordinate occurs once per sweep, so its z is
 //     the committed one; a hit consumes exactly one normal, so Z_i is normal number mnorm + i - i_s);
-//   * warp w takes the eight coordinates [i_s + 8 w, i_s + 8 w + 8): it replays the chain of the coordinates
-//     before its block -- the same FMAs in the same order as the sequential loop, so the same bits -- and then tests
-//     and applies its own eight; the first miss of the sweep is found with a shared-memory minimum;
-//   * no miss: the last warp's chain is the sweep's result.  A miss at i_f: warp 0 replays the chain up to i_f,
+//   * warp w takes a block of the remaining coordinates: it replays the chain of the coordinates before its block
+//     -- the same FMAs in the same order as the sequential loop, so the same bits -- and then tests and applies its
+//     own; the first miss of the sweep is found with a shared-memory minimum;
+//   * no miss: the last block's chain is the sweep's result.  A miss at i_f: warp 0 replays the chain up to i_f,
 //     decides coordinate i_f the long way (window, further tries, inverse CDF -- warp_seq_range on that one
 //     coordinate) and the speculation restarts behind it.  After three misses in one sweep the rest of the sweep
-//     (and the whole next sweep, if this one had more) runs in the sequential loop: models whose constraints bind
-//     pay one wasted pass per sweep.
+//     (and the whole next sweep, if this one had more than six) runs in the sequential loop: models whose
+//     constraints bind pay one wasted pass per sweep.
+// Warp 7 meanwhile prepares the NEXT sweep's order (the 63 sequential swaps are ~4 300 cycles, as long as a sweep's
+// passes), from the stream position the beta stream will have if this sweep needs no inverse-CDF draw; warp 0
+// checks that at the end of the sweep and redoes the order from the true position otherwise.
 // Identical variates, identical operation order, hence bit-identical to warp_constrained_sweeps (BL_BETA_NO_SPEC
 // selects that one; test_constrained_draw_speculation_is_bit_identical).
 __device__ __forceinline__ void cta_constrained_sweeps_spec(const double *L, const double *iL, const double *z_in,
@@ -1051,8 +1059,13 @@ __device__ __forceinline__ void cta_constrained_sweeps_spec(const double *L, con
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double *sb = work, *sz = work + 64, *su = work + 128, *sbf = work + 192;       // committed beta, z; u; a pass's result
-    int *ctl = reinterpret_cast<int *>(work + 256);                               // [0] first miss, [1] mnorm, [2] i_s, [3] mode
+    int *ctl = reinterpret_cast<int *>(work + 256);      // [0] first miss, [1] mnorm, [2] i_s, [3] mode, [4] stream position
+    int *isv[2] = {is, is + 2 * P};                      // this sweep's order / the next one's; swap targets behind each
     int n_fall = 0, n_rej = 0;
+#define BL_BAR7() asm volatile("bar.sync 1, 224;" ::: "memory")
+#ifdef BL_BETA_CLOCKS
+    long long t_pass = 0, t_miss = 0, t_redo = 0; int n_pass = 0, n_redo = 0;
+#endif
     if (tid < 64) {
         sb[tid] = tid < P ? beta_prev[tid] : 0.0;
         sz[tid] = tid < P ? z_in[tid] : 0.0;
@@ -1060,124 +1073,170 @@ __device__ __forceinline__ void cta_constrained_sweeps_spec(const double *L, con
     }
     if (tid == 0) { ctl[1] = 0; ctl[3] = 0; }
     __syncthreads();
+    if (warp == 0) {
+        warp_sweep_permutation(isv[0], src, P, lane);
+        if (lane == 0) { ctl[2] = 0; ctl[4] = philox_tell(src); }
+    }
+    __syncthreads();
     for (int k = 0; k < P; ++k) {
-        if (warp == 0) warp_sweep_permutation(is, src, P, lane);
-        if (tid == 0) ctl[2] = 0;
-        __syncthreads();
-        int misses = 0;
-        for (;;) {
-            const int i_s = ctl[2], mnorm = ctl[1];
-            if (i_s >= P) break;
-            const bool sequential = ctl[3] != 0 || misses >= 3 || mnorm + (P - i_s) > nbuf_len;
-            if (sequential) {
-                // the rest of this sweep in the one-warp loop
+        const int *cur = isv[k & 1];
+        int *nxt = isv[(k & 1) ^ 1];
+        if (warp == 7) {
+            if (k + 1 < P) {
+                for (int i = lane; i < P; i += 32) nxt[i] = cur[i];
+                __syncwarp();
+                warp_sweep_permutation_at(nxt, nxt + P, ctl[4], src, P, lane);
+            }
+        } else {
+            int misses = 0;
+            for (;;) {
+                const int i_s = ctl[2], mnorm = ctl[1];
+                if (i_s >= P) break;
+                const bool sequential = ctl[3] != 0 || misses >= 3 || mnorm + (P - i_s) > nbuf_len;
+                if (sequential) {
+                    // the rest of this sweep in the one-warp loop
+                    if (warp == 0) {
+                        double beta[2], z[2];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) { beta[q] = sb[lane + 32 * q]; z[q] = sz[lane + 32 * q]; }
+                        int mn = mnorm, nf = 0;
+                        warp_seq_range<2>(L, iL, cur, i_s, P, beta, z, mn, src, P, ld, lane, nbuf, nbuf_len, seed, call, nf, n_rej);
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) { sb[lane + 32 * q] = beta[q]; sz[lane + 32 * q] = z[q]; }
+                        if (lane == 0) { ctl[1] = mn; ctl[2] = P; ctl[3] = (misses + nf) > 6 ? 1 : 0; }
+                        n_fall += nf;
+                    }
+                    BL_BAR7();
+                    break;
+                }
+                // ---- one speculative pass over the coordinates [i_s, P) ----
+#ifdef BL_BETA_CLOCKS
+                long long q1 = clock64(); ++n_pass;
+#endif
+                if (tid < P - i_s) su[i_s + tid] = nbuf[mnorm + tid] - sz[cur[i_s + tid]];
+                if (tid == 0) ctl[0] = P;
+                BL_BAR7();
+                {
+                    const int blk = (P - i_s + 6) / 7;
+                    const int a = i_s + blk * warp, b = min(a + blk, P);
+                    if (a < P) {
+                        double b0 = sb[lane], b1 = sb[lane + 32];
+                        const bool v0 = lane < P, v1 = lane + 32 < P;
+                        // the chain of the coordinates before this warp's block, four columns' loads in flight
+                        int i = i_s;
+                        for (; i + 4 <= a; i += 4) {
+                            int c[4]; double u[4], l0[4], l1[4];
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) { c[r] = cur[i + r]; u[r] = su[i + r]; }
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                l0[r] = v0 ? L[lane + (size_t)ld * c[r]] : 0.0;
+                                l1[r] = v1 ? L[lane + 32 + (size_t)ld * c[r]] : 0.0;
+                            }
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) { b0 = fma(l0[r], u[r], b0); b1 = fma(l1[r], u[r], b1); }
+                        }
+                        for (; i < a; ++i) {
+                            const int c = cur[i];
+                            const double u = su[i];
+                            b0 = fma(v0 ? L[lane + (size_t)ld * c] : 0.0, u, b0);
+                            b1 = fma(v1 ? L[lane + 32 + (size_t)ld * c] : 0.0, u, b1);
+                        }
+                        // this warp's own coordinates: test, then apply
+                        bool clean = true;
+                        for (i = a; i < b; ++i) {
+                            const int c = cur[i];
+                            const double u = su[i];
+                            const double il0 = v0 ? iL[lane + (size_t)ld * c] : 0.0, il1 = v1 ? iL[lane + 32 + (size_t)ld * c] : 0.0;
+                            const double l0 = v0 ? L[lane + (size_t)ld * c] : 0.0, l1 = v1 ? L[lane + 32 + (size_t)ld * c] : 0.0;
+                            const double w0 = fma(b0, il0, u), w1 = fma(b1, il1, u);
+                            const bool inside = ((w0 > 0.0) | !(il0 > 0.0)) & ((w0 < 0.0) | !(il0 < 0.0)) &
+                                                ((w1 > 0.0) | !(il1 > 0.0)) & ((w1 < 0.0) | !(il1 < 0.0));
+                            if (!__all_sync(0xffffffffu, inside)) {
+                                if (lane == 0) atomicMin(&ctl[0], i);
+                                clean = false;
+                                break;
+                            }
+                            b0 = fma(l0, u, b0);
+                            b1 = fma(l1, u, b1);
+                        }
+                        if (clean && b == P) { sbf[lane] = b0; sbf[lane + 32] = b1; }
+                    }
+                }
+                BL_BAR7();
+#ifdef BL_BETA_CLOCKS
+                long long q2 = clock64(); t_pass += q2 - q1;
+#endif
+                const int i_f = ctl[0];
+                if (i_f >= P) {
+                    // every remaining coordinate accepted its first normal: the last block's chain is the new beta
+                    if (tid < 64) sb[tid] = sbf[tid];
+                    if (tid < P - i_s) sz[cur[i_s + tid]] = nbuf[mnorm + tid];
+                    BL_BAR7();                                                    // ctl is still being read above
+                    if (tid == 0) { ctl[1] = mnorm + (P - i_s); ctl[2] = P; }
+                    BL_BAR7();
+                    break;
+                }
+                // a miss at i_f: warp 0 replays the accepted prefix and decides coordinate i_f the long way
                 if (warp == 0) {
                     double beta[2], z[2];
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) { beta[q] = sb[lane + 32 * q]; z[q] = sz[lane + 32 * q]; }
-                    int mn = mnorm, nf = 0;
-                    warp_seq_range<2>(L, iL, is, i_s, P, beta, z, mn, src, P, ld, lane, nbuf, nbuf_len, seed, call, nf, n_rej);
+                    for (int q = 0; q < 2; ++q) beta[q] = sb[lane + 32 * q];
+                    for (int i = i_s; i < i_f; ++i) {
+                        const int c = cur[i];
+                        const double u = su[i];
+                        beta[0] = fma(lane < P ? L[lane + (size_t)ld * c] : 0.0, u, beta[0]);
+                        beta[1] = fma(lane + 32 < P ? L[lane + 32 + (size_t)ld * c] : 0.0, u, beta[1]);
+                    }
+                    __syncwarp();
+                    for (int i = i_s + lane; i < i_f; i += 32) sz[cur[i]] = nbuf[mnorm + (i - i_s)];
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) z[q] = sz[lane + 32 * q];
+                    int mn = mnorm + (i_f - i_s), nf = 0;
+                    warp_seq_range<2>(L, iL, cur, i_f, i_f + 1, beta, z, mn, src, P, ld, lane, nbuf, nbuf_len, seed, call, nf, n_rej);
 #pragma unroll
                     for (int q = 0; q < 2; ++q) { sb[lane + 32 * q] = beta[q]; sz[lane + 32 * q] = z[q]; }
-                    if (lane == 0) { ctl[1] = mn; ctl[2] = P; ctl[3] = (misses + nf) > 6 ? 1 : 0; }
+                    if (lane == 0) { ctl[1] = mn; ctl[2] = i_f + 1; }
                     n_fall += nf;
                 }
-                __syncthreads();
-                break;
+                ++misses;
+                BL_BAR7();
+#ifdef BL_BETA_CLOCKS
+                t_miss += clock64() - q2;
+#endif
             }
-            // ---- one speculative pass over the coordinates [i_s, P) ----
-            if (tid < P - i_s) su[i_s + tid] = nbuf[mnorm + tid] - sz[is[i_s + tid]];
-            if (tid == 0) ctl[0] = P;
-            __syncthreads();
-            {
-                const int a = i_s + 8 * warp, b = min(a + 8, P);
-                if (a < P) {
-                    double b0 = sb[lane], b1 = sb[lane + 32];
-                    const bool v0 = lane < P, v1 = lane + 32 < P;
-                    // the chain of the coordinates before this warp's block, four columns' loads in flight
-                    int i = i_s;
-                    for (; i + 4 <= a; i += 4) {
-                        int c[4]; double u[4], l0[4], l1[4];
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) { c[r] = is[i + r]; u[r] = su[i + r]; }
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            l0[r] = v0 ? L[lane + (size_t)ld * c[r]] : 0.0;
-                            l1[r] = v1 ? L[lane + 32 + (size_t)ld * c[r]] : 0.0;
-                        }
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) { b0 = fma(l0[r], u[r], b0); b1 = fma(l1[r], u[r], b1); }
-                    }
-                    for (; i < a; ++i) {
-                        const int c = is[i];
-                        const double u = su[i];
-                        b0 = fma(v0 ? L[lane + (size_t)ld * c] : 0.0, u, b0);
-                        b1 = fma(v1 ? L[lane + 32 + (size_t)ld * c] : 0.0, u, b1);
-                    }
-                    // this warp's own coordinates: test, then apply
-                    bool clean = true;
-                    for (i = a; i < b; ++i) {
-                        const int c = is[i];
-                        const double u = su[i];
-                        const double il0 = v0 ? iL[lane + (size_t)ld * c] : 0.0, il1 = v1 ? iL[lane + 32 + (size_t)ld * c] : 0.0;
-                        const double l0 = v0 ? L[lane + (size_t)ld * c] : 0.0, l1 = v1 ? L[lane + 32 + (size_t)ld * c] : 0.0;
-                        const double w0 = fma(b0, il0, u), w1 = fma(b1, il1, u);
-                        const bool inside = ((w0 > 0.0) | !(il0 > 0.0)) & ((w0 < 0.0) | !(il0 < 0.0)) &
-                                            ((w1 > 0.0) | !(il1 > 0.0)) & ((w1 < 0.0) | !(il1 < 0.0));
-                        if (!__all_sync(0xffffffffu, inside)) {
-                            if (lane == 0) atomicMin(&ctl[0], i);
-                            clean = false;
-                            break;
-                        }
-                        b0 = fma(l0, u, b0);
-                        b1 = fma(l1, u, b1);
-                    }
-                    if (clean && b == P) { sbf[lane] = b0; sbf[lane + 32] = b1; }
-                }
-            }
-            __syncthreads();
-            const int i_f = ctl[0];
-            if (i_f >= P) {
-                // every remaining coordinate accepted its first normal: the last block's chain is the new beta
-                if (tid < 64) sb[tid] = sbf[tid];
-                __syncthreads();                                                  // su / sz are read and written by different threads
-                if (tid < P - i_s) sz[is[i_s + tid]] = nbuf[mnorm + tid];
-                if (tid == 0) { ctl[1] = mnorm + (P - i_s); ctl[2] = P; if (misses == 0) ctl[3] = 0; }
-                __syncthreads();
-                break;
-            }
-            // a miss at i_f: warp 0 replays the accepted prefix and decides coordinate i_f the long way
-            if (warp == 0) {
-                double beta[2], z[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) beta[q] = sb[lane + 32 * q];
-                for (int i = i_s; i < i_f; ++i) {
-                    const int c = is[i];
-                    const double u = su[i];
-                    beta[0] = fma(lane < P ? L[lane + (size_t)ld * c] : 0.0, u, beta[0]);
-                    beta[1] = fma(lane + 32 < P ? L[lane + 32 + (size_t)ld * c] : 0.0, u, beta[1]);
-                }
-                __syncwarp();
-                for (int i = i_s + lane; i < i_f; i += 32) sz[is[i]] = nbuf[mnorm + (i - i_s)];
-                __syncwarp();
-#pragma unroll
-                for (int q = 0; q < 2; ++q) z[q] = sz[lane + 32 * q];
-                int mn = mnorm + (i_f - i_s), nf = 0;
-                warp_seq_range<2>(L, iL, is, i_f, i_f + 1, beta, z, mn, src, P, ld, lane, nbuf, nbuf_len, seed, call, nf, n_rej);
-#pragma unroll
-                for (int q = 0; q < 2; ++q) { sb[lane + 32 * q] = beta[q]; sz[lane + 32 * q] = z[q]; }
-                if (lane == 0) { ctl[1] = mn; ctl[2] = i_f + 1; }
-                n_fall += nf;
-            }
-            ++misses;
-            __syncthreads();
         }
+        __syncthreads();
+        // the next sweep: warp 7's order stands if the beta stream is where it was assumed to be
+        if (warp == 0 && k + 1 < P) {
+#ifdef BL_BETA_CLOCKS
+            long long q3 = clock64();
+#endif
+            const int a_true = philox_tell(src), a_assumed = ctl[4];
+            if (a_true == a_assumed) {
+                philox_seek(src, a_assumed + P - 1);
+            } else {
+                for (int i = lane; i < P; i += 32) nxt[i] = cur[i];
+                __syncwarp();
+                warp_sweep_permutation(nxt, src, P, lane);
+#ifdef BL_BETA_CLOCKS
+                ++n_redo;
+#endif
+            }
+            if (lane == 0) { ctl[2] = 0; ctl[4] = philox_tell(src); }
+#ifdef BL_BETA_CLOCKS
+            t_redo += clock64() - q3;
+#endif
+        }
+        __syncthreads();
     }
     if (tid < P) beta_out[tid] = sb[tid];
 #ifdef BL_BETA_CLOCKS
-    if (tid == 0 && call == 3) printf("[beta constrained spec] first normal missed %d times, %d inverse-CDF draws\n", n_fall, n_rej);
+    if (tid == 0 && call == 3) printf("[beta constrained spec] %d passes %lld, misses %lld, order check %lld cycles (%d redone); first normal missed %d times, %d inverse-CDF draws\n", n_pass, t_pass, t_miss, t_redo, n_redo, n_fall, n_rej);
 #endif
     __syncthreads();
+#undef BL_BAR7
 }
 
 // One beta draw.  Workspace (all column-major, ld = P):
