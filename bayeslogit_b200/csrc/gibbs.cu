@@ -240,8 +240,10 @@ constexpr bool kSlowBeta = true;          // A/B build: the panel factorisation 
 constexpr bool kSlowBeta = false;
 #endif
 
-template <bool SMEM>
-__global__ void __launch_bounds__(256)
+// kPlainOnly: the plain / mvn draw with P <= 64 alone (cta_plain_fast) -- a tenth of the code, and registers for two
+// CTAs per SM: the batched chains run one CTA per chain.
+template <bool SMEM, bool kPlainOnly = false>
+__global__ void __launch_bounds__(256, kPlainOnly ? 2 : 1)
 k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__ P0,
             const double *__restrict__ base_rhs, int add_tail, const double *beta_prev,
             double *beta_out, double *gwork, int P, uint64_t seed, uint32_t call, int *status,
@@ -283,7 +285,7 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
         default: peer_stage<0>(pw, A, rhs, P0, base_rhs, add_tail, P, ld); break;
         }
         __syncthreads();
-        cta_beta_draw(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len, efast, tn_pre, SMEM ? tn_fast : 0);
+        cta_beta_draw<kPlainOnly>(mode, A, B, v, rhs, beta_prev, beta_out, P, ld, seed, call, status, nbuf, nbuf_len, efast, tn_pre, SMEM ? tn_fast : 0);
         return;
     }
     if (fast) {
@@ -322,6 +324,7 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
         if (!ok_fast && threadIdx.x == 0) *status = 1;
         return;
     }
+    if (kPlainOnly) return;                   // (the host picks this instantiation only when `fast` holds)
     // stage PP = Gram + P0.  P <= 64: every load of the thread (16 Gram entries, 16 prior entries) is issued before
     // the first use -- one L2 round trip instead of four.
     if (P <= 64) {
@@ -505,6 +508,8 @@ struct Sweep {
         use_smem = beta_smem_tn <= 200 * 1024;
         if (use_smem && beta_smem_tn > 48 * 1024)
             GB_CK(cudaFuncSetAttribute(k_beta_draw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem_tn));
+        if (use_smem && beta_smem > 48 * 1024)
+            GB_CK(cudaFuncSetAttribute(k_beta_draw<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem));
         return 0;
     }
 
@@ -599,7 +604,9 @@ struct Sweep {
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-            cudaLaunchKernelEx(&cfg, k_beta_draw<true>, mode, (const double *)acc, P0, base_rhs, add_tail ? 1 : 0, beta_prev,
+            const bool lean = mode != kBetaConstrained && P <= 64 && !kSlowBeta;
+            cudaLaunchKernelEx(&cfg, lean ? k_beta_draw<true, true> : k_beta_draw<true, false>, mode, (const double *)acc, P0,
+                               base_rhs, add_tail ? 1 : 0, beta_prev,
                                beta_out, gwork, P, seed, call, status, pending, (int64_t)0,
                                (const double *)(tn ? tnbuf : nullptr), getenv("BL_BETA_NO_SPEC") ? 3 : 1);
         } else
@@ -782,8 +789,10 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
     GB_CK(cudaFuncSetAttribute(k_gram_partial<kGramRowsDiag, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)gram_smem_bytes(false, true)));
     const bool packed = gram_packed(P);
-    if (beta_smem > 48 * 1024)
+    if (beta_smem > 48 * 1024) {
         GB_CK(cudaFuncSetAttribute(k_beta_draw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem));
+        GB_CK(cudaFuncSetAttribute(k_beta_draw<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)beta_smem));
+    }
     const int64_t bstride = (int64_t)P * samp;
 
     // bP_c = P0 m0 + X_c'(n (y - 1/2))
@@ -831,8 +840,12 @@ int logit_chains_device(double *beta_out, const double *y, const double *tX, con
             if (tm) cudaEventRecord(ev[2], st);
             k_gram_reduce<<<dim3(cdiv((int64_t)P * P, 32), chains), 256, 0, st>>>(acc, nullptr, part, P, nt, slabs_total, PeerPush{}, packed ? 1 : 0);
             if (tm) cudaEventRecord(ev[3], st);
-            k_beta_draw<true><<<chains, 256, beta_smem, st>>>(mode, acc, P0, bP, 0, bprev, bcur, nullptr, P, seed, t, status,
-                                                           PeerWait{}, bstride, nullptr, getenv("BL_BETA_NO_SPEC") ? 3 : 1);
+            if (mode != kBetaConstrained && P <= 64 && !kSlowBeta)
+                k_beta_draw<true, true><<<chains, 256, beta_smem, st>>>(mode, acc, P0, bP, 0, bprev, bcur, nullptr, P, seed, t, status,
+                                                                     PeerWait{}, bstride, nullptr, 1);
+            else
+                k_beta_draw<true><<<chains, 256, beta_smem, st>>>(mode, acc, P0, bP, 0, bprev, bcur, nullptr, P, seed, t, status,
+                                                               PeerWait{}, bstride, nullptr, getenv("BL_BETA_NO_SPEC") ? 3 : 1);
             count_launch(3);
             if (tm) cudaEventRecord(ev[4], st);
             bpsi = bcur;

@@ -1244,6 +1244,7 @@ __device__ __forceinline__ void cta_constrained_sweeps_spec(const double *L, con
 //   B  [P*P]  scratch: S = PP^-1 -> L                        (constrained, mvn)
 //   v  [4*P]  scratch vectors
 // rhs = bP (precision-weighted mean), beta_prev (constrained only), beta_out.
+template <bool kPlainOnly = false>
 __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, double *v, const double *rhs,
                                      const double *beta_prev, double *beta_out, int P, int ld,
                                      uint64_t seed, uint32_t call, int *status, double *nbuf = nullptr, int nbuf_len = 0,
@@ -1311,6 +1312,7 @@ __device__ __forceinline__ void cta_beta_draw(int mode, double *A, double *B, do
         return;
     }
 
+    if (kPlainOnly) return;                // this instantiation never sees the constrained draw
     const double *L = B;
     double *iL = A;
     // the scratch of the fast set-up is free again when the sweeps start: the speculative sweeps take it
