@@ -195,7 +195,7 @@ struct MlogitNext {
 };
 
 template <bool kMlogit>
-static __global__ void __launch_bounds__(256, kMlogit ? 3 : 2)
+static __global__ void __launch_bounds__(256, 2)
 k_xbeta_mma(double *__restrict__ psi, const double *__restrict__ tX, const double *__restrict__ beta,
             int64_t beta_stride, int chains, int64_t N, int P,
             const double *__restrict__ off, double off_scale, double shift, MlogitNext mn)
