@@ -142,6 +142,7 @@ struct SweepArgs {
     int P;
     int ntiles;                // ceil(N / 32)
     int draw_warps, stages;
+    int serial_publish;        // A/B: publish from the last CTA alone
     int debug_nodraw;          // measurement aid: omega = 0.25 without drawing (Gram rate of the pipeline alone)
     StreamId id;
 };
@@ -342,8 +343,43 @@ k_logit_sweep(const __grid_constant__ CUtensorMap tmap, SweepArgs a, PeerPush px
             }
         }
     }
-    // sharded data: the finished sums go into every rank's window
-    if (px.world > 1) peer_publish(px, a.PP, a.P * a.P);
+    // Sharded data: the finished sums go into every rank's window -- one CTA per destination.  (From the last CTA
+    // alone, one window after the other, the kernel was 4 us longer at 2 ranks and 20 us longer at 8 than on a GPU
+    // that runs the same shard alone.)  The grid counter makes a second round: every CTA adds one when its part of
+    // PP is stored, CTA r waits for the round to complete, copies PP into rank r's window with coalesced 16-byte
+    // stores, and sets its flag there behind a system-scope fence.  All CTAs are resident (cooperative launch), so
+    // the wait cannot starve the CTAs it waits for.
+    if (px.world > 1 && a.serial_publish) {
+        peer_publish(px, a.PP, a.P * a.P);                   // A/B: the last CTA publishes to every rank (BL_K3_SERIAL_PUBLISH)
+    } else if (px.world > 1) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(a.grid_ctr, 1u);
+        }
+        if ((int)blockIdx.x < px.world) {
+            if (threadIdx.x == 0) {
+                unsigned spins = 0;
+                while ((int)(ld_acquire_gpu(a.grid_ctr) - (a.grid_target + gridDim.x)) < 0) {
+                    __nanosleep(32);
+                    if (++spins > (1u << 26)) __trap();
+                }
+            }
+            __syncthreads();
+            const int cnt = a.P * a.P, n2 = cnt >> 1;
+            const double2 *src = reinterpret_cast<const double2 *>(a.PP);
+            for (int r = blockIdx.x; r < px.world; r += gridDim.x) {
+                double2 *dst = reinterpret_cast<double2 *>(px.slot[r]);
+                for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldcg(src + i);
+                if ((cnt & 1) && threadIdx.x == 0) px.slot[r][cnt - 1] = __ldcg(a.PP + cnt - 1);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence_system();             // the slot stores are performed system-wide before the flags
+                for (int r = blockIdx.x; r < px.world; r += gridDim.x) st_release_sys(px.flag[r], px.epoch);
+            }
+        }
+    }
 }
 
 typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -412,6 +448,7 @@ int LogitSweep::init(const double *tX, int64_t N_, int P_, cudaStream_t st, std:
     }
     stream = st;
     launches = 0;
+    ctr_rounds = 0;
     return 0;
 }
 
@@ -427,7 +464,10 @@ cudaError_t LogitSweep::launch(double *w_out, double *PP, const int *shape, cons
     SweepArgs a;
     a.w_out = w_out; a.shape = shape; a.beta = beta; a.part = part; a.PP = PP;
     a.grid_ctr = ctr;
-    a.grid_target = (unsigned)((launches + 1) * (uint64_t)grid);
+    a.serial_publish = getenv("BL_K3_SERIAL_PUBLISH") ? 1 : 0;
+    // two rounds of the grid counter per sharded launch (barrier, publish), one otherwise
+    a.grid_target = (unsigned)(ctr_rounds + (uint64_t)grid);
+    ctr_rounds += (uint64_t)grid * (px.world > 1 && !a.serial_publish ? 2 : 1);
     a.N = N; a.P = P; a.ntiles = ntiles; a.draw_warps = draw_warps; a.stages = stages; a.id = id;
     a.debug_nodraw = getenv("BL_K3_NODRAW") ? atoi(getenv("BL_K3_NODRAW")) : 0;
     ++launches;

@@ -24,6 +24,7 @@ struct LogitSweep {
     double *part = nullptr;                          // [grid][64 x 64] per-CTA partial tiles
     unsigned *ctr = nullptr;                         // grid barrier counter
     uint64_t launches = 0;
+    uint64_t ctr_rounds = 0;                         // increments the grid counter has seen (barrier + publish rounds)
     cudaStream_t stream = nullptr;
 
     int init(const double *tX, int64_t N, int P, cudaStream_t st, std::string &err);
