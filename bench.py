@@ -491,6 +491,32 @@ def main():
                          "hbm_GBs": n1 * 20 / (ms1 * 1e-3) / 1e9}
         del z1, s1, x1
         torch.cuda.empty_cache()
+        # (i') BASELINE config 0 at its stated size: ONE batch of 1M PG(1,z) draws through the drop-in entry with
+        # host pointers (what R's .C("rpg_devroye") does), beside the reference's serial loop on one host core
+        if rank == 0:
+            import numpy as np
+            n0 = 1_000_000
+            r0 = np.random.default_rng(SEED + 5)
+            z0 = r0.uniform(-5.0, 5.0, n0)
+            s0 = np.ones(n0, dtype=np.int32)
+            x0 = np.empty(n0)
+            fn0 = L.bl_rpg_devroye_seeded
+            for w in range(3):
+                _lib.check(fn0(x0.ctypes.data, s0.ctypes.data, z0.ctypes.data, n0, SEED, 700 + w, 0))
+            t0 = time.perf_counter()
+            for k in range(10):
+                _lib.check(fn0(x0.ctypes.data, s0.ctypes.data, z0.ctypes.data, n0, SEED, k, 0))
+            host_ms = (time.perf_counter() - t0) / 10 * 1e3
+            c0 = {"batch": n0, "api": "rpg_devroye C ABI, pageable host pointers, one call per batch",
+                  "ms_per_batch_e2e": host_ms, "draws_per_sec_e2e": n0 / (host_ms * 1e-3)}
+            if not args.no_cpu_baseline:
+                O = load_oracle()
+                t0 = time.perf_counter()
+                O.rpg_devroye(s0, z0, seed=SEED, nthreads=1)
+                cpu_s = time.perf_counter() - t0
+                c0["cpu_reference_1_core_ms_per_batch"] = cpu_s * 1e3
+                c0["cpu_kind"] = O.kind
+            extras["config0_pg1_1M_batch"] = c0
         # (ii) logit Gibbs iterations/s at N=1M, P=64 (strong scaling: the N rows are sharded)
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_gibbs
