@@ -501,6 +501,11 @@ int run_tape(Method m, double *x, const void *shape, const double *z, int64_t nu
 }  // namespace
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+bool pdl_enabled()
+{
+    static const bool on = getenv("BL_GIBBS_NO_PDL") == nullptr;
+    return on;
+}
 
 }  // namespace bl
 

@@ -108,6 +108,29 @@ int hybrid_timing_last(double *ms8, int *launches8);
 
 void count_launch(int n = 1);
 
+// Programmatic dependent launch for the kernels of the Gibbs sweeps' inner loops: launch_pdl() sets the attribute
+// (BL_GIBBS_NO_PDL in the environment drops it) and the kernel opens with BL_PDL_ENTER(), which waits until the kernel
+// before it has completed and its writes are visible -- the launch latency between two kernels leaves the critical
+// path.  No-op in a kernel launched without the attribute (<<< >>>).  The kernels do NOT trigger their dependents
+// early (griddepcontrol.launch_dependents): the Gram kernels are sized for exactly one wave of CTAs, and a
+// successor's CTAs that take their places while they wait cost a second, partial wave (measured: packed Gram 97 ->
+// 148 us, N = 1M logit iteration 396 -> 449 us).
+#define BL_PDL_ENTER() asm volatile("griddepcontrol.wait;" ::: "memory")
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace bl
 
 // internal hooks of the context in capi.cu

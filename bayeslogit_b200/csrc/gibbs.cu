@@ -357,6 +357,7 @@ k_beta_draw(int mode, const double *__restrict__ acc, const double *__restrict__
 // rejection normals of one constrained beta draw: normal m of the stream (seed, obs 2^64-3, call), gibbs_beta.cuh
 __global__ void k_tn_normals(double *out, int n, uint64_t seed, uint32_t call)
 {
+    BL_PDL_ENTER();
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m < n) out[m] = stream_normal_obs(seed, kTnObs, call, m);
 }
@@ -405,7 +406,7 @@ void launch_xtv(dim3 grid, cudaStream_t st, double *part, const double *tX, cons
     const int64_t slab_pairs = ((N + grid.x - 1) / grid.x) * (P / 2);
     const int l2 = slab_pairs < (1LL << 31) - 4096 ? xtv_stream_log2l(tX, P) : 0;
     const int mode = (v0 && !v1 && !v2) ? 0 : (!v0 && v1 && v2) ? 1 : (v0 && v1 && !v2) ? 2 : -1;
-#define BL_XTV(L2, M) k_xtv_stream<L2, M><<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, c1_dev)
+#define BL_XTV(L2, M) launch_pdl(k_xtv_stream<L2, M>, dim3(grid), dim3(256), smem, st, part, tX, v0, c0, v1, v2, c1, N, c1_dev)
 #define BL_XTV_L(L2) (mode == 0 ? BL_XTV(L2, 0) : mode == 1 ? BL_XTV(L2, 1) : BL_XTV(L2, 2))
     if (mode >= 0 && l2 == 2) BL_XTV_L(2);
     else if (mode >= 0 && l2 == 3) BL_XTV_L(3);
@@ -415,8 +416,8 @@ void launch_xtv(dim3 grid, cudaStream_t st, double *part, const double *tX, cons
     else if (mode >= 0 && l2 == 7) BL_XTV_L(7);
 #undef BL_XTV_L
 #undef BL_XTV
-    else if (xbeta_mma_ok(tX, P)) k_xtv_mma<<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, P, c1_dev);
-    else k_xtv_partial<<<grid, 256, smem, st>>>(part, tX, v0, c0, v1, v2, c1, N, P, c1_dev);
+    else if (xbeta_mma_ok(tX, P)) launch_pdl(k_xtv_mma, dim3(grid), dim3(256), smem, st, part, tX, v0, c0, v1, v2, c1, N, P, c1_dev);
+    else launch_pdl(k_xtv_partial, dim3(grid), dim3(256), smem, st, part, tX, v0, c0, v1, v2, c1, N, P, c1_dev);
 }
 
 // BL_GIBBS_TIMING=1: CUDA-event stage times of one iteration (the one armed by the driver), to stderr.
@@ -517,7 +518,7 @@ struct Sweep {
     {
         int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (N + 255) / 256));
         if (xbeta_mma_ok(tX, P))
-            k_xbeta_mma<false><<<grid, 256, 0, st>>>(out, tX, beta, 0, 1, N, P, off, off_scale, shift, MlogitNext{});
+            launch_pdl(k_xbeta_mma<false>, dim3(grid), dim3(256), 0, st, out, tX, beta, 0, 1, N, P, off, off_scale, shift, MlogitNext{});
         else
             k_xbeta<<<grid, 256, P * sizeof(double), st>>>(out, tX, beta, off, off_scale, shift, N, P);
         count_launch();
@@ -527,7 +528,7 @@ struct Sweep {
     void xbeta_mlogit(double *out, const double *beta, const MlogitNext &mn)
     {
         int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (N + 255) / 256));
-        k_xbeta_mma<true><<<grid, 256, 0, st>>>(out, tX, beta, 0, 1, N, P, nullptr, 0.0, 0.0, mn);
+        launch_pdl(k_xbeta_mma<true>, dim3(grid), dim3(256), 0, st, out, tX, beta, 0, 1, N, P, nullptr, 0.0, 0.0, mn);
         count_launch();
     }
 
@@ -542,11 +543,11 @@ struct Sweep {
         int tiles = nt * (nt + 1) / 2;
         const bool packed = gram_packed(P);
         if (nt > 1)
-            k_gram_partial<kGramRows, false><<<dim3(nslab, tiles), 256, gram_smem_bytes(true), st>>>(part, tX, wv, N, P, nt, nslab_diag);
+            launch_pdl(k_gram_partial<kGramRows, false>, dim3(nslab, tiles), dim3(256), gram_smem_bytes(true), st, part, tX, wv, N, P, nt, nslab_diag, nullptr);
         else if (packed)
-            k_gram_partial<kGramRowsDiag, true, true><<<dim3(nslab, tiles), 256, gram_smem_bytes(false, true), st>>>(part, tX, wv, N, P, nt, 0, cvec);
+            launch_pdl(k_gram_partial<kGramRowsDiag, true, true>, dim3(nslab, tiles), dim3(256), gram_smem_bytes(false, true), st, part, tX, wv, N, P, nt, 0, cvec);
         else
-            k_gram_partial<kGramRowsDiag, true><<<dim3(nslab, tiles), 256, gram_smem_bytes(false), st>>>(part, tX, wv, N, P, nt);
+            launch_pdl(k_gram_partial<kGramRowsDiag, true>, dim3(nslab, tiles), dim3(256), gram_smem_bytes(false), st, part, tX, wv, N, P, nt, 0, nullptr);
         const int tail_in_part = packed && cvec ? 1 : 0;
         PeerPush px{};
         pending = PeerWait{};
@@ -554,8 +555,8 @@ struct Sweep {
             peer_next(px, pending);
             px.with_tail = with_tail ? 1 : 0;
         }
-        k_gram_reduce<<<cdiv((int64_t)P * P + (tail_in_part ? P : 0), 32), 256, 0, st>>>(acc, nullptr, part, P, nt, nt > 1 ? 2 * nslab : nslab, px,
-                                                                                         packed ? 1 : 0, 2 * nslab_diag, tail_in_part);
+        launch_pdl(k_gram_reduce, dim3(cdiv((int64_t)P * P + (tail_in_part ? P : 0), 32)), dim3(256), 0, st, acc, nullptr, part, P, nt,
+                   nt > 1 ? 2 * nslab : nslab, px, packed ? 1 : 0, 2 * nslab_diag, tail_in_part);
         count_launch(2);
         if (px.world > 1) exchange_rendezvous();     // virtual ranks: every producer is enqueued before any consumer
     }
@@ -565,7 +566,7 @@ struct Sweep {
              const double *c1_dev = nullptr)
     {
         launch_xtv(dim3(xtv_slabs), st, xtv_part, tX, v0, c0, v1, v2, c1, N, P, c1_dev);
-        k_xtv_reduce<<<cdiv(P, 128), 128, 0, st>>>(acc + (size_t)P * P, nullptr, nullptr, xtv_part, P, xtv_slabs);
+        launch_pdl(k_xtv_reduce, dim3(cdiv(P, 128)), dim3(128), 0, st, acc + (size_t)P * P, nullptr, nullptr, xtv_part, P, xtv_slabs);
         count_launch(2);
     }
 
@@ -589,7 +590,7 @@ struct Sweep {
                 // the draw's P^2 + 2P rejection normals depend on (seed, call) alone: one thread each, a few
                 // microseconds on the whole chip, instead of 17 in a row on each of the draw's 256 threads
                 const int n = P * P + 2 * P;
-                k_tn_normals<<<cdiv(n, 128), 128, 0, st>>>(tnbuf, n, seed, call);
+                launch_pdl(k_tn_normals, dim3(cdiv(n, 128)), dim3(128), 0, st, tnbuf, n, seed, call);
                 count_launch();
             }
             // programmatic dependent launch: the CTA is scheduled while the kernel that produces the sums drains and

@@ -200,6 +200,7 @@ k_xbeta_mma(double *__restrict__ psi, const double *__restrict__ tX, const doubl
             int64_t beta_stride, int chains, int64_t N, int P,
             const double *__restrict__ off, double off_scale, double shift, MlogitNext mn)
 {
+    BL_PDL_ENTER();
     const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
     const int64_t tpc = (N + 31) >> 5;                               // 32-row trips per chain
     const int64_t trips = (int64_t)chains * tpc;
@@ -391,6 +392,7 @@ __global__ void __launch_bounds__(256)
 k_gram_partial(double *__restrict__ part, const double *__restrict__ tX, const double *__restrict__ w,
                int64_t N, int P, int nt, int nslab_diag = 0, const double *__restrict__ cv = nullptr)
 {
+    BL_PDL_ENTER();
     extern __shared__ __align__(16) double gsm[];
     const int nthr = blockDim.x;
     // batched independent chains: blockIdx.z = chain (its own rows, weights and partial tiles)
@@ -772,6 +774,7 @@ k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
               int nslab_diag = 0,      // nslab: partial tiles per output tile (stride); diagonal tiles hold nslab_diag of them (0: nslab)
               int tail_in_part = 0)    // packed tiles also carry X'(Omega c): the CTAs past the P^2 entries sum it into PP[P^2 ..)
 {
+    BL_PDL_ENTER();
     __shared__ double red[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // batched independent chains: blockIdx.y = chain
@@ -833,6 +836,7 @@ k_xtv_partial(double *__restrict__ part, const double *__restrict__ tX, const do
               double c0, const double *__restrict__ v1, const double *__restrict__ v2, double c1,
               int64_t N, int P, const double *__restrict__ c1_dev = nullptr)
 {
+    BL_PDL_ENTER();
     if (c1_dev) c1 = *c1_dev;                  // coefficient produced on the device (NB: log d)
     // batched independent chains: blockIdx.y = chain
     tX += (size_t)blockIdx.y * N * P;
@@ -875,6 +879,7 @@ k_xtv_mma(double *__restrict__ part, const double *__restrict__ tX, const double
           double c0, const double *__restrict__ v1, const double *__restrict__ v2, double c1,
           int64_t N, int P, const double *__restrict__ c1_dev)
 {
+    BL_PDL_ENTER();
     if (c1_dev) c1 = *c1_dev;
     tX += (size_t)blockIdx.y * N * P;
     part += (size_t)blockIdx.y * gridDim.x * P;
@@ -955,6 +960,7 @@ k_xtv_stream(double *__restrict__ part, const double *__restrict__ tX, const dou
              double c0, const double *__restrict__ v1, const double *__restrict__ v2, double c1,
              int64_t N, const double *__restrict__ c1_dev)
 {
+    BL_PDL_ENTER();
     constexpr int L = 1 << kLog2L, P = 2 * L;            // column pairs per row, columns
     constexpr int kQ = L > 32 ? L / 32 : 1;              // column pairs a lane rotates through
     if (c1_dev) c1 = *c1_dev;
@@ -1040,6 +1046,7 @@ static __global__ void k_xtv_reduce(double *__restrict__ out, const double *__re
                              const double *__restrict__ add1, const double *__restrict__ part,
                              int P, int nslab)
 {
+    BL_PDL_ENTER();
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     // batched independent chains: blockIdx.y = chain (add0 is shared by the chains, add1 is not)

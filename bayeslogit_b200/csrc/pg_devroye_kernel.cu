@@ -37,6 +37,7 @@ __device__ __forceinline__ int dev_class(double z) { return fabs(z) * 0.5 >= 1.0
 __global__ void __launch_bounds__(kBinThreads)
 k_cls_count(const double *__restrict__ z, int n, int *__restrict__ meta)
 {
+    BL_PDL_ENTER();
     int c = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += dev_class(z[i]);
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -51,6 +52,7 @@ k_cls_count(const double *__restrict__ z, int n, int *__restrict__ meta)
 __global__ void __launch_bounds__(kBinThreads)
 k_cls_scatter(const double *__restrict__ z, int n, int *__restrict__ meta, int *__restrict__ idx)
 {
+    BL_PDL_ENTER();
     __shared__ int wcnt[kBinThreads / 32][2];
     __shared__ int base[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(kThreads)
 k_devroye_refill(double *__restrict__ x, const int *__restrict__ n, const double *__restrict__ z,
                  int64_t num, StreamId id, const int *__restrict__ idx, int chunk)
 {
+    BL_PDL_ENTER();
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -336,6 +339,7 @@ k_logit_psi_draw(double *__restrict__ x, double *__restrict__ psi_out, const int
                  const double *__restrict__ tX, const double *__restrict__ beta, int64_t beta_stride,
                  int chains, int64_t N, int P, StreamId id)
 {
+    BL_PDL_ENTER();
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
     const int64_t tpc = (N + 31) >> 5;                               // 32-row trips per chain
@@ -433,12 +437,12 @@ cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int6
         if (e != cudaSuccess) return e;
         int tiles = (int)((num + kBinThreads - 1) / kBinThreads);
         int bgrid = tiles < 148 * 8 ? tiles : 148 * 8;
-        k_cls_count<<<bgrid, kBinThreads, 0, st>>>(z, (int)num, meta);
-        k_cls_scatter<<<bgrid, kBinThreads, 0, st>>>(z, (int)num, meta, idx);
-        k_devroye_refill<true><<<grid, kThreads, 0, st>>>(x, n, z, num, id, idx, chunk);
+        launch_pdl(k_cls_count, dim3(bgrid), dim3(kBinThreads), 0, st, z, (int)num, meta);
+        launch_pdl(k_cls_scatter, dim3(bgrid), dim3(kBinThreads), 0, st, z, (int)num, meta, idx);
+        launch_pdl(k_devroye_refill<true>, dim3(grid), dim3(kThreads), 0, st, x, n, z, num, id, (const int *)idx, chunk);
         count_launch(3);
     } else {
-        k_devroye_refill<false><<<grid, kThreads, 0, st>>>(x, n, z, num, id, nullptr, chunk);
+        launch_pdl(k_devroye_refill<false>, dim3(grid), dim3(kThreads), 0, st, x, n, z, num, id, (const int *)nullptr, chunk);
         count_launch();
     }
     return cudaGetLastError();
@@ -462,7 +466,7 @@ cudaError_t launch_logit_psi_draw(double *x, double *psi_out, const int *n, cons
     // the others -- 189 us against 105 + 86 for the two kernels at N = 1M, P = 64; with 8 loads in flight
     // and 24 warps 172 us (P = 32: 104 against 122; P = 128: 252 against 281).
     int grid = (int)std::min<int64_t>(148 * 3, std::max<int64_t>(1, (trips + wpc - 1) / wpc));
-    k_logit_psi_draw<<<grid, kThreads, 0, st>>>(x, psi_out, n, tX, beta, beta_stride, chains, N, P, id);
+    launch_pdl(k_logit_psi_draw, dim3(grid), dim3(kThreads), 0, st, x, psi_out, n, tX, beta, beta_stride, chains, N, P, id);
     count_launch();
     return cudaGetLastError();
 }
