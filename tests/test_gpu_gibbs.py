@@ -49,7 +49,7 @@ def close(a, b, rel=CHAIN_REL):
 
 @pytest.mark.parametrize("constrained", [False, True])
 @pytest.mark.parametrize("N,P,binomial", [(3000, 7, False), (1500, 64, False), (2000, 5, True), (700, 70, False), (1501, 32, False), (3000, 128, False),
-                                          (40000, 72, False)])
+                                          (40000, 72, False), (4301, 33, False), (7300, 63, False), (1200, 2, False), (1100, 1, False)])
 def test_logit_chain_matches_oracle(gapi, constrained, N, P, binomial):
     # N = 40000, P = 72: enough rows for the cost-proportional slab counts of the P > 64 Gram (diagonal
     # tiles cut into fewer slabs than off-diagonal ones; smaller N caps both at N / 128).
@@ -57,6 +57,8 @@ def test_logit_chain_matches_oracle(gapi, constrained, N, P, binomial):
     # four-way column rotation of k_xtv_stream.  N is kept >= ~20 P: the constrained draw starts on
     # the constraint boundary (beta = 0), where its truncation windows are a few ulps wide and the
     # chain map amplifies last-bit differences of erfc without bound when N is only a few P.
+    # P = 33 / 63: the second register of a lane's pair is only partly populated (identity-padded fast beta draws);
+    # P = 1, 2: no / one constrained coefficient.
     X, y, n, _ = synth_logit(N, P, 10 + P, binomial)
     m0 = np.linspace(-0.1, 0.1, P)
     P0 = 0.5 * np.eye(P) + 0.01
