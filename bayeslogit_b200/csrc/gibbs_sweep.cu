@@ -54,7 +54,6 @@ namespace {
 constexpr int kTileRows = 32;
 constexpr int kBoxCols = 16;                       // 16 doubles = 128 bytes = the swizzle span
 constexpr int kBoxBytes = kTileRows * kBoxCols * 8;   // 4096
-constexpr int kGramWarpsMax = 16;
 constexpr int kMaxThreads = 640;                   // 1 producer + 8 Gram + up to 11 draw warps: 96 registers per thread (ptxas sizes for multiples of 128 threads)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
