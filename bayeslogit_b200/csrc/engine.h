@@ -50,7 +50,9 @@ cudaError_t launch_probe_philox(uint32_t *out4, const uint32_t *ctr4, const uint
 // `bin_min` draws (BL_DEVROYE_BIN_MIN overrides).  z ~ U(-5, 5) gains nothing below ~2^20 draws; the one-sided
 // tilts of an mlogit sweep (eta = psi_j - log sum exp) gain 30 % at 10^6.
 cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int64_t num,
-                                  StreamId id, cudaStream_t stream, void *work = nullptr, int64_t bin_min = 1 << 20);
+                                  StreamId id, cudaStream_t stream, void *work = nullptr, int64_t bin_min = 1 << 20,
+                                  bool prebinned = false);   // prebinned: work already holds the class-ordered index list
+bool devroye_binned(int64_t num, int64_t bin_min);         // whether a batch of this size takes the binned path
 
 // Fused psi = X beta + omega = PG(n, psi) of the logit sweeps (pg_devroye_kernel.cu); needs even P and a
 // 16-byte aligned tX (logit_psi_draw_ok).  chains > 1: rows [c N, (c+1) N) meet beta + c * beta_stride and

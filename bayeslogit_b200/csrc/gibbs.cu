@@ -896,6 +896,7 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
     // psi, exp(psi) and the next category's offsets from one pass over X (k_xbeta_mma<true>); BL_MLOGIT_UNFUSED
     // keeps the psi kernel and the offsets kernel per category (A/B: bit-identical chains)
     const bool fuse_next = xbeta_mma_ok(tX, P) && U <= kMlogitMaxU && !getenv("BL_MLOGIT_UNFUSED");
+    const bool prebin = fuse_next && devroye_binned(N, 1 << 18);      // the psi pass also orders the next draw's rows by class
     GB_CK(mem.get(&Z, (size_t)P * U));
     GB_CK(mem.get(&b0, (size_t)P * U));
     GB_CK(mem.get(&base, (size_t)P * U));
@@ -945,7 +946,8 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
             }
             tmr.mark("offsets");
             double *wj = wS ? wS + (size_t)N * j : s.w;
-            cudaError_t e = launch_devroye_refill(wj, shape, eta, N, StreamId{seed, obs0, call}, st, work, 1 << 18);
+            cudaError_t e = launch_devroye_refill(wj, shape, eta, N, StreamId{seed, obs0, call}, st, work, 1 << 18,
+                                                  prebin && !(t == 0 && j == 0));
             if (e != cudaSuccess) { err = cudaGetErrorString(e); return 1; }
             tmr.mark("draw");
             if (s.gram_tail_fused()) {
@@ -960,7 +962,12 @@ int mlogit_gibbs_device(double *w_out, double *beta_out, const double *ty, const
             s.beta_draw(kBetaMvn, P0 + (size_t)P * P * j, base + (size_t)P * j, true, nullptr,
                         bS + (size_t)P * j, seed, call);
             tmr.mark("beta");
-            if (fuse_next) s.xbeta_mlogit(XB + (size_t)N * j, bS + (size_t)P * j, MlogitNext{EX, XB, cj, eta, U, j, (j + 1) % U});
+            if (fuse_next) {
+                // the next draw's class-ordered index list comes out of the same pass (cursors zeroed first)
+                int *bm = prebin ? (int *)work : nullptr;
+                if (prebin) GB_CK(cudaMemsetAsync(bm, 0, 32 * sizeof(int), st));
+                s.xbeta_mlogit(XB + (size_t)N * j, bS + (size_t)P * j, MlogitNext{EX, XB, cj, eta, U, j, (j + 1) % U, bm, bm ? bm + 32 : nullptr});
+            }
             else s.xbeta(XB + (size_t)N * j, bS + (size_t)P * j, nullptr, 0.0);
             tmr.mark("xbeta");
             tmr.report("mlogit");

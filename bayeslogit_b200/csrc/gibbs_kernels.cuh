@@ -192,6 +192,9 @@ struct MlogitNext {
     const double *XB;       // [N x U]
     double *c, *eta;        // [N] offset and PG tilt of category jn
     int U, j, jn;
+    int *bin_meta, *bin_idx;   // optional: the next draw's rows ordered by branch class (two cursors + index list, as
+                               // k_cls_scatter leaves them) -- the tilt is in a register here, so the ordering costs two
+                               // shared cursors' atomics per 32 rows instead of a pass over eta
 };
 
 template <bool kMlogit>
@@ -244,6 +247,7 @@ k_xbeta_mma(double *__restrict__ psi, const double *__restrict__ tX, const doubl
             // every column of an accumulator tile holds psi of its 8 rows: lane (gid, tig) takes row 8 tig + gid
             const double xb = tig == 0 ? c[0][0] : tig == 1 ? c[1][0] : tig == 2 ? c[2][0] : c[3][0];
             const int64_t i = i0 + 8 * tig + gid;
+            int cls = -1;
             if (i < N) {
                 psi[i] = xb;
                 const double ej = exp(xb);
@@ -255,7 +259,23 @@ k_xbeta_mma(double *__restrict__ psi, const double *__restrict__ tX, const doubl
                 A += 1.0;
                 const double cj = log(A);
                 mn.c[i] = cj;
-                mn.eta[i] = (mn.jn == mn.j ? xb : xbn) - cj;
+                const double et = (mn.jn == mn.j ? xb : xbn) - cj;
+                mn.eta[i] = et;
+                if (mn.bin_idx) cls = fabs(et) * 0.5 >= 1.0 / 0.64 ? 1 : 0;        // dev_class (pg_devroye_kernel.cu), kTrunc = 0.64
+            }
+            if (mn.bin_idx) {
+                // class 0 from the front, class 1 from the back, a warp's rows in one atomic per class
+                const unsigned m1 = __ballot_sync(0xffffffffu, cls == 1), m0 = __ballot_sync(0xffffffffu, cls == 0);
+                int b0 = 0, b1 = 0;
+                if (lane == 0) {
+                    if (m0) b0 = atomicAdd(&mn.bin_meta[1], __popc(m0));
+                    if (m1) b1 = atomicAdd(&mn.bin_meta[2], __popc(m1));
+                }
+                b0 = __shfl_sync(0xffffffffu, b0, 0);
+                b1 = __shfl_sync(0xffffffffu, b1, 0);
+                const unsigned lt = (1u << lane) - 1u;
+                if (cls == 0) mn.bin_idx[b0 + __popc(m0 & lt)] = (int)i;
+                else if (cls == 1) mn.bin_idx[(int)N - 1 - (b1 + __popc(m1 & lt))] = (int)i;
             }
         } else if (tig == 0) {
 #pragma unroll

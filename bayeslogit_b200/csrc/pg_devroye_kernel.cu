@@ -34,21 +34,9 @@ constexpr int kBinThreads = 256;
 
 __device__ __forceinline__ int dev_class(double z) { return fabs(z) * 0.5 >= 1.0 / kTrunc ? 1 : 0; }
 
-__global__ void __launch_bounds__(kBinThreads)
-k_cls_count(const double *__restrict__ z, int n, int *__restrict__ meta)
-{
-    BL_PDL_ENTER();
-    int c = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += dev_class(z[i]);
-    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    __shared__ int tot;
-    if (threadIdx.x == 0) tot = 0;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&tot, c);
-    __syncthreads();
-    if (threadIdx.x == 0 && tot) atomicAdd(&meta[0], tot);
-}
-
+// idx = the observations ordered by branch class: class 0 from the front, class 1 from the back (two cursors in
+// meta[1], meta[2]) -- no counting pass.  The order inside a class depends on the CTAs' timing; the draws do not
+// (their streams are keyed by the observation).
 __global__ void __launch_bounds__(kBinThreads)
 k_cls_scatter(const double *__restrict__ z, int n, int *__restrict__ meta, int *__restrict__ idx)
 {
@@ -57,7 +45,6 @@ k_cls_scatter(const double *__restrict__ z, int n, int *__restrict__ meta, int *
     __shared__ int base[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    const int off1 = n - meta[0];                                  // class 1 starts after all of class 0
     int tiles = (n + kBinThreads - 1) / kBinThreads;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         int i = tile * kBinThreads + threadIdx.x;
@@ -69,13 +56,13 @@ k_cls_scatter(const double *__restrict__ z, int n, int *__restrict__ meta, int *
         if (threadIdx.x < 2) {
             int t = 0;
             for (int w = 0; w < kBinThreads / 32; ++w) t += wcnt[w][threadIdx.x];
-            base[threadIdx.x] = (threadIdx.x ? off1 : 0) + (t ? atomicAdd(&meta[1 + threadIdx.x], t) : 0);
+            base[threadIdx.x] = t ? atomicAdd(&meta[1 + threadIdx.x], t) : 0;
         }
         __syncthreads();
         if (cls >= 0) {
             int off = base[cls];
             for (int w = 0; w < warp; ++w) off += wcnt[w][cls];
-            idx[off + rank] = i;
+            idx[cls ? n - 1 - (off + rank) : off + rank] = i;
         }
         __syncthreads();
     }
@@ -403,8 +390,15 @@ k_logit_psi_draw(double *__restrict__ x, double *__restrict__ psi_out, const int
 
 }  // namespace
 
+bool devroye_binned(int64_t num, int64_t bin_min_arg)
+{
+    static const int64_t bin_env = getenv("BL_DEVROYE_BIN_MIN") ? atoll(getenv("BL_DEVROYE_BIN_MIN")) : -1;
+    const int64_t bin_min = bin_env >= 0 ? bin_env : bin_min_arg;
+    return !getenv("BL_DEVROYE_REGROUP") && num >= bin_min && num < (1LL << 31);
+}
+
 cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int64_t num,
-                                  StreamId id, cudaStream_t st, void *work, int64_t bin_min_arg)
+                                  StreamId id, cudaStream_t st, void *work, int64_t bin_min_arg, bool prebinned)
 {
     if (num <= 0) return cudaSuccess;
     int64_t cap = 148LL * 4;                 // 148 SMs x resident CTAs
@@ -433,14 +427,16 @@ cudaError_t launch_devroye_refill(double *x, const int *n, const double *z, int6
         count_launch();
     } else if (work && num >= bin_min && num < (1LL << 31)) {
         int *meta = (int *)work, *idx = meta + 32;
-        cudaError_t e = cudaMemsetAsync(meta, 0, 32 * sizeof(int), st);
-        if (e != cudaSuccess) return e;
-        int tiles = (int)((num + kBinThreads - 1) / kBinThreads);
-        int bgrid = tiles < 148 * 8 ? tiles : 148 * 8;
-        launch_pdl(k_cls_count, dim3(bgrid), dim3(kBinThreads), 0, st, z, (int)num, meta);
-        launch_pdl(k_cls_scatter, dim3(bgrid), dim3(kBinThreads), 0, st, z, (int)num, meta, idx);
+        if (!prebinned) {
+            cudaError_t e = cudaMemsetAsync(meta, 0, 32 * sizeof(int), st);
+            if (e != cudaSuccess) return e;
+            int tiles = (int)((num + kBinThreads - 1) / kBinThreads);
+            int bgrid = tiles < 148 * 8 ? tiles : 148 * 8;
+            launch_pdl(k_cls_scatter, dim3(bgrid), dim3(kBinThreads), 0, st, z, (int)num, meta, idx);
+            count_launch();
+        }
         launch_pdl(k_devroye_refill<true>, dim3(grid), dim3(kThreads), 0, st, x, n, z, num, id, (const int *)idx, chunk);
-        count_launch(3);
+        count_launch();
     } else {
         launch_pdl(k_devroye_refill<false>, dim3(grid), dim3(kThreads), 0, st, x, n, z, num, id, (const int *)nullptr, chunk);
         count_launch();
