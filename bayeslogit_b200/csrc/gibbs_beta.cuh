@@ -1059,7 +1059,7 @@ __device__ __forceinline__ void cta_constrained_sweeps_spec(const double *L, con
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double *sb = work, *sz = work + 64, *su = work + 128, *sbf = work + 192;       // committed beta, z; u; a pass's result
-    int *ctl = reinterpret_cast<int *>(work + 256);      // [0] first miss, [1] mnorm, [2] i_s, [3] mode, [4] stream position
+    int *ctl = reinterpret_cast<int *>(work + 256);      // [0] first miss, [1] mnorm, [2] i_s, [3] mode, [4] stream position, [5] miss resolved by its finder
     int *isv[2] = {is, is + 2 * P};                      // this sweep's order / the next one's; swap targets behind each
     int n_fall = 0, n_rej = 0;
 #define BL_BAR7() asm volatile("bar.sync 1, 224;" ::: "memory")
@@ -1114,14 +1114,16 @@ __device__ __forceinline__ void cta_constrained_sweeps_spec(const double *L, con
                 long long q1 = clock64(); ++n_pass;
 #endif
                 if (tid < P - i_s) su[i_s + tid] = nbuf[mnorm + tid] - sz[cur[i_s + tid]];
-                if (tid == 0) ctl[0] = P;
+                if (tid == 0) { ctl[0] = P; ctl[5] = 0; }
                 BL_BAR7();
+                double b0 = 0.0, b1 = 0.0;                 // this warp's chain: beta in front of coordinate miss_at on a miss
+                int miss_at = -1;
+                const bool v0 = lane < P, v1 = lane + 32 < P;
                 {
                     const int blk = (P - i_s + 6) / 7;
                     const int a = i_s + blk * warp, b = min(a + blk, P);
                     if (a < P) {
-                        double b0 = sb[lane], b1 = sb[lane + 32];
-                        const bool v0 = lane < P, v1 = lane + 32 < P;
+                        b0 = sb[lane]; b1 = sb[lane + 32];
                         // the chain of the coordinates before this warp's block, four columns' loads in flight
                         int i = i_s;
                         for (; i + 4 <= a; i += 4) {
@@ -1155,6 +1157,7 @@ __device__ __forceinline__ void cta_constrained_sweeps_spec(const double *L, con
                             if (!__all_sync(0xffffffffu, inside)) {
                                 if (lane == 0) atomicMin(&ctl[0], i);
                                 clean = false;
+                                miss_at = i;
                                 break;
                             }
                             b0 = fma(l0, u, b0);
@@ -1177,8 +1180,43 @@ __device__ __forceinline__ void cta_constrained_sweeps_spec(const double *L, con
                     BL_BAR7();
                     break;
                 }
-                // a miss at i_f: warp 0 replays the accepted prefix and decides coordinate i_f the long way
-                if (warp == 0) {
+                // A miss at i_f.  The warp that found it holds beta in front of that coordinate: it forms the window and
+                // takes the further tries (the same normals, in the same order, as the sequential loop would); when one
+                // of them lands it commits the prefix and the coordinate itself.  Otherwise (a narrow or far window, three
+                // more misses, normals exhausted) nothing is committed and warp 0, which owns the beta stream, replays
+                // the accepted prefix and decides the coordinate the long way.
+                if (miss_at == i_f) {
+                    const int c = cur[i_f];
+                    const double z1 = sz[c];
+                    const double il0 = v0 ? iL[lane + (size_t)ld * c] : 0.0, il1 = v1 ? iL[lane + 32 + (size_t)ld * c] : 0.0;
+                    double cmin = -INFINITY, cmax = INFINITY;
+                    const double c10 = fma(-b0, il0, z1), c11 = fma(-b1, il1, z1);
+                    if (il0 > 0.0 && c10 > cmin) cmin = c10;
+                    else if (il0 < 0.0 && c10 < cmax) cmax = c10;
+                    if (il1 > 0.0 && c11 > cmin) cmin = c11;
+                    else if (il1 < 0.0 && c11 < cmax) cmax = c11;
+                    cmin = warp_max_f64(cmin);
+                    cmax = warp_min_f64(cmax);
+                    int mn = mnorm + (i_f - i_s) + 1;                              // the first normal is spent
+                    bool got = false;
+                    double z2 = 0.0;
+                    if (cmin < cmax && cmin < 1.0 && cmax > -1.0 && cmax - cmin >= 0.5) {
+                        for (int tr = 1; tr < 4 && !got && mn < nbuf_len; ++tr) {
+                            const double Z = nbuf[mn];
+                            ++mn;
+                            if (Z > cmin && Z < cmax) { z2 = Z; got = true; }
+                        }
+                    }
+                    if (got) {
+                        const double dz = z2 - z1;
+                        sb[lane] = fma(v0 ? L[lane + (size_t)ld * c] : 0.0, dz, b0);
+                        sb[lane + 32] = fma(v1 ? L[lane + 32 + (size_t)ld * c] : 0.0, dz, b1);
+                        for (int i = i_s + lane; i < i_f; i += 32) sz[cur[i]] = nbuf[mnorm + (i - i_s)];
+                        if (lane == 0) { sz[c] = z2; ctl[1] = mn; ctl[2] = i_f + 1; ctl[5] = 1; }
+                    }
+                }
+                BL_BAR7();
+                if (warp == 0 && ctl[5] == 0) {
                     double beta[2], z[2];
 #pragma unroll
                     for (int q = 0; q < 2; ++q) beta[q] = sb[lane + 32 * q];
