@@ -801,7 +801,9 @@ k_gram_reduce(double *__restrict__ PP, const double *__restrict__ P0,
     PP += (size_t)blockIdx.y * ((size_t)P * P + P);
     part += (size_t)blockIdx.y * (nt * (nt + 1) / 2) * nslab * (kGramTile * kGramTile);
     int e = blockIdx.x * 32 + lane;
-    int a = e % P, b = e / P;
+    // consecutive lanes take consecutive COLUMNS of a tile row (the partial tiles are row-major: one 256-byte run per
+    // warp load; with consecutive rows every lane touched its own 32-byte sector, four times the L2 traffic)
+    int a = e / P, b = e % P;
     bool want = e < P * P && a <= b;
     const bool tail = tail_in_part && e >= P * P && e < P * P + P;
     double s = 0.0;
